@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: env-steps/s at d=5 depolarising p=0.007 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config C3 of SURVEY.md section 8): d=5, depolarising noise, p_phys = p_meas = 0.007, volume depth 5,
+16384 lattices per GPU (weak scaling: C4 = 8 x 16384), shipped referee table, random-legal policy.
+One "step" = one vectorised env step of every lattice: the policy kernel picks an action per lattice
+from its legal mask, the env kernel advances all lattices and writes a fresh observation.
+
+  value     all-GPU env-steps/s with everything resident in HBM; the K steps run as CUDA-graph replays
+            of 16 (policy, step) pairs, each pair writing its observations into a different slot of a
+            16-slot ring (222 MB > the 126 MB L2, so observation writes cannot be absorbed by L2)
+  roofline  env-step kernel only: algorithmic bytes per launch (996 B per lattice-step)
+            over its mean duration, measured with CUDA events around every launch of an eager pass
+            whose launches are queued behind a device-side delay so the events see back-to-back kernels
+  e2e       the same steps through dq_env_step_host: actions come from pinned host memory, every output
+            (observations, reward, done, lifetime, legal mask) is copied back to the host each step
+  cpu_baseline / --impl reference
+            the CPU oracle (oracle/dq_oracle.c, a C restatement of the reference env; the Python
+            reference itself cannot travel to the GPU box) on all host cores, same workload
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D, VD, P, MODEL, USE_Y = 5, 5, 0.007, "DP", False
+N_PER_GPU = 16384
+SEED = 2026
+RING = 16
+METRIC = "env-steps/sec at d=5 depolarising p=0.007"
+UNIT = "env-steps/s"
+BYTES_PER_STEP = 996          # obs 847 + action 4 + reward 4 + done 1 + lifetime 4 + mask 8 + 2 x 64 state
+WORKLOAD = ("C3: d=5 DP p_phys=p_meas=0.007 volume_depth=5 use_Y=False, %d lattices/GPU, random-legal policy, "
+            "referee = shipped nn_d5_DP_p5 tabulated" % N_PER_GPU)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_run(budget_s, n=N_PER_GPU):
+    """Times the oracle on all host cores: random-legal policy + step, like the GPU loop."""
+    import numpy as np
+    from oracle import oracle as O
+    from deepq_decoding_b200 import referee as REF
+    o = O.OracleVecEnv(D, MODEL, USE_Y, VD, P, P, n, SEED)
+    ref = REF.shipped(D, MODEL)
+    o.set_referee(ref.mode, ref.lut_a, ref.lut_b)
+    _, legal = o.reset()
+    cores = O.lib().dqo_num_threads()
+    for t in range(3):
+        legal = o.step(o.random_legal_actions(legal, t), auto_reset=True)[4]
+    steps, t0 = 0, time.perf_counter()
+    while True:
+        acts = o.random_legal_actions(legal, 3 + steps)
+        legal = o.step(acts, auto_reset=True)[4]
+        steps += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s:
+            break
+    return dict(value=n * steps / el, unit=UNIT, cores=cores, kind="port",
+                sample="%d vectorised steps of %d lattices (%.1f s wall) of the same workload, oracle/dq_oracle.c "
+                       "with OpenMP over lattices" % (steps, n, el)), n * steps / el, el / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_budget = min(60.0, max(5.0, 0.02 * (args.steps + args.warmup)))
+    cb, value, s_per_step = cpu_oracle_run(t_budget)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU oracle port of the reference env on the host cores; each step is "
+                       "one vectorised step of 16384 lattices; the run is time-bounded, not step-bounded"},
+            "cpu_baseline": dict(cb, value=value),
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in rows for i in range(4) if len(r) >= 8 and r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(rows)}
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from deepq_decoding_b200 import _lib
+    from deepq_decoding_b200.envs import VecSurfaceCodeEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, max(args.warmup, 3)
+    n = N_PER_GPU
+    L = _lib.lib()
+
+    env = VecSurfaceCodeEnv(D, P, P, MODEL, USE_Y, VD, None, n_envs=n, seed=SEED, env_id_base=rank * n, device=dev)
+    h = env._h
+    ring = torch.zeros((RING,) + tuple(env.obs.shape), dtype=torch.uint8, device=dev)
+    actions = torch.zeros(n, dtype=torch.int32, device=dev)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    p_act, p_rew, p_done, p_life, p_legal = vp(actions), vp(env.reward), vp(env.done), vp(env.lifetime), vp(env.legal_mask)
+    p_ring = [C.c_void_p(ring[s].data_ptr()) for s in range(RING)]
+
+    def pair(slot, stream):
+        _lib.check(L.dq_policy_random_legal_next(h, p_legal, p_act, stream))
+        _lib.check(L.dq_env_step(h, p_act, p_ring[slot], p_rew, p_done, p_life, p_legal, 1, stream))
+
+    cur = lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    env.reset()
+    _lib.check(L.dq_policy_seek(h, 0, cur()))
+    torch.cuda.synchronize()
+
+    # CUDA graph of RING (policy, step) pairs
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for s in range(RING):
+            pair(s, cur())                      # warm the kernels before capture
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for s in range(RING):
+            pair(s, cur())
+
+    def run_steps(k):
+        full, rest = divmod(k, RING)
+        for _ in range(full):
+            graph.replay()
+        for s in range(rest):
+            pair(s, cur())
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    run_steps(Wm)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record()
+    run_steps(K)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    value = world * n * K / (ms * 1e-3)
+
+    # ---- roofline: per-launch duration of the env-step kernel, CUDA events around every launch.
+    # The launches are queued behind a ~25 ms device-side delay so that, when the GPU reaches them,
+    # they run back to back and the event pairs bracket device time only (not Python launch gaps).
+    roof = None
+    if rank == 0:
+        nprof = 128
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nprof)]
+        torch.cuda._sleep(int(25e-3 * 1.9e9))
+        st = cur()
+        for i in range(nprof):
+            _lib.check(L.dq_policy_random_legal_next(h, p_legal, p_act, st))
+            evs[i][0].record()
+            _lib.check(L.dq_env_step(h, p_act, p_ring[i % RING], p_rew, p_done, p_life, p_legal, 1, st))
+            evs[i][1].record()
+        torch.cuda.synchronize()
+        durs = sorted(a.elapsed_time(b) * 1e-3 for a, b in evs)
+        mean_s = sum(durs) / len(durs)
+        peak, peak_src = measured_peak()
+        achieved = n * BYTES_PER_STEP / mean_s / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "env_step_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm", "kernel": "env_step_kernel<5,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel_us_mean": mean_s * 1e6, "kernel_us_median": durs[len(durs) // 2] * 1e6,
+                "algorithmic_bytes_per_launch": n * BYTES_PER_STEP, "launches_timed": nprof}
+
+    # ---- e2e: host buffers through dq_env_step_host (H2D actions, D2H every output, every step)
+    ke = min(K, 64)
+    rng = np.random.default_rng(SEED + rank)
+    host_actions = torch.from_numpy(rng.integers(0, env.num_actions, size=(ke + 3, n), dtype=np.int32)).pin_memory()
+    hb = env._host_buffers()
+    hp = lambda t: C.c_void_p(t.data_ptr())
+    torch.cuda.synchronize()
+
+    def host_step(i):
+        _lib.check(L.dq_env_step_host(h, C.c_void_p(host_actions[i].data_ptr()), hp(hb["obs"]), hp(hb["reward"]),
+                                      hp(hb["done"]), hp(hb["lifetime"]), hp(hb["legal"]), 1))
+    for i in range(3):
+        host_step(i)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(3, ke + 3):
+        host_step(i)
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * ke / float(dt.item())
+    h2d = n * 4
+    d2h = n * (env.obs[0].numel() + 4 + 1 + 4 + 8 * env.mask_words)
+
+    if rank == 0:
+        cb, _, _ = cpu_oracle_run(args.cpu_seconds)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "lattices_total": world * n,
+                           "l2": "each step writes its %.1f MB of observations into one of %d ring slots (%.0f MB > L2), "
+                                 "so no step's writes are absorbed by the previous step's lines" % (
+                                     ring[0].numel() / 1e6, RING, ring.numel() / 1e6),
+                           "launch": "CUDA graph of %d (policy, env-step) kernel pairs" % RING,
+                           "parallelism": "lattices sharded by rank, no data-path collective"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": ke, "api": "dq_env_step_host (pinned host actions in, all outputs to pinned host buffers)",
+                        "policy": "uniform random action indices pre-generated on the host"},
+                "gpu_launches": 2 * K,
+                "roofline": roof, "cpu_baseline": cb}
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=32768)
+    ap.add_argument("--warmup", type=int, default=64)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall budget of the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

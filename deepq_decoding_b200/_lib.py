@@ -1,0 +1,70 @@
+"""ctypes binding of the C ABI (include/dq_decoding.h -> libdq_decoding.so).
+
+There is no fallback: if the shared library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdq_decoding.so")
+
+OK, EINVAL, ECUDA, ESTATE = 0, -1, -2, -3
+MODEL = {"X": 0, "DP": 1}
+REFEREE_JOINT, REFEREE_SPLIT = 0, 1
+(INFO_NUM_ACTIONS, INFO_OBS_CHANNELS, INFO_OBS_SIDE, INFO_MASK_WORDS, INFO_STATE_WORDS,
+ INFO_STATE_STRIDE, INFO_NUM_STABS, INFO_N_TYPE3, INFO_N_TYPE1, INFO_RNG_BLOCKS) = range(10)
+
+
+class DQError(RuntimeError):
+    pass
+
+
+_lib = None
+_vp, _i, _i64, _u64, _u32, _dbl = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_double
+
+_SIGNATURES = {
+    "dq_last_error": (C.c_char_p, []),
+    "dq_version": (_i, []),
+    "dq_launch_count": (_i64, []),
+    "dq_env_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _dbl, _dbl, _i64, _u64, _i64, _i]),
+    "dq_env_destroy": (_i, [_vp]),
+    "dq_env_info": (_i, [_vp, _i, C.POINTER(_i64)]),
+    "dq_env_set_noise": (_i, [_vp, _dbl, _dbl]),
+    "dq_env_set_referee_lut": (_i, [_vp, _i, _vp, _i64, _vp, _i64]),
+    "dq_env_reset": (_i, [_vp, _vp, _vp, _vp]),
+    "dq_env_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "dq_env_reset_host": (_i, [_vp, _vp, _vp]),
+    "dq_env_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "dq_env_get_state": (_i, [_vp, _vp, _vp]),
+    "dq_env_set_state": (_i, [_vp, _vp, _vp]),
+    "dq_policy_random_legal": (_i, [_vp, _vp, _u32, _vp, _vp]),
+    "dq_policy_seek": (_i, [_vp, _u32, _vp]),
+    "dq_policy_random_legal_next": (_i, [_vp, _vp, _vp, _vp]),
+}
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DQError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C deepq_decoding_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise DQError("dq error %d: %s" % (rc, lib().dq_last_error().decode(errors="replace")))
+
+
+def launch_count():
+    return int(lib().dq_launch_count())

@@ -1,0 +1,131 @@
+/*
+ * dq_decoding.h -- C ABI of the B200-native DeepQ-Decoding hot path.
+ *
+ * Drop-in boundary for the reference's per-step environment / DQN inner loop.  The
+ * reference has no FFI (it is one Python process); each entry point below names the
+ * reference interface it replaces (paths relative to the reference repo root,
+ * EN = example_notebooks/, SPTS = cluster_scripts/d5_dp/0.001/Single_Point_Training_Script.py).
+ * INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative DQ_E* code on failure;
+ *     dq_last_error() returns a thread-local message for the last failure;
+ *   - the caller owns every device/host buffer it passes (the library never frees
+ *     them); the library owns only the opaque handles and their internal state;
+ *   - device entry points are asynchronous on the passed stream (a cudaStream_t
+ *     cast to void*; NULL = the legacy default stream) and never synchronise;
+ *     *_host entry points take HOST pointers, copy in/out on an internal stream and
+ *     return after the results have landed;
+ *   - a handle is not thread-safe; distinct handles are independent;
+ *   - there is no CPU fallback: without a CUDA device every call fails with DQ_ECUDA.
+ *
+ * Shapes (N = n_envs, A = num_actions, C = volume_depth + action layers, H = 2d+1,
+ * W = ceil(A/64)):
+ *   obs        uint8  [N][C][H][H]   the reference's board_state (EN/Environments.py:91), 0/1 cells
+ *   legal_mask uint64 [N][W]         bit a of word a/64 set  <=>  a in env.legal_actions
+ *   actions    int32  [N]            action index as passed to env.step(); values outside [0,A) act as identity
+ *   reward     float  [N]            1.0f / 0.0f   (EN/Environments.py:146-149)
+ *   done       uint8  [N]            env.done after the step
+ *   lifetime   int32  [N]            env.lifetime after the step (the finished episode's value when done)
+ */
+#ifndef DQ_DECODING_H
+#define DQ_DECODING_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DQ_OK        0
+#define DQ_EINVAL   -1   /* bad argument */
+#define DQ_ECUDA    -2   /* CUDA runtime failure / no device */
+#define DQ_ESTATE   -3   /* call not valid in this state (e.g. step before referee set) */
+
+#define DQ_MODEL_X   0   /* error_model == "X"  */
+#define DQ_MODEL_DP  1   /* error_model == "DP" */
+
+#define DQ_REFEREE_JOINT 0  /* one table over all d*d-1 stabilizers, 2-bit class X+2Z            */
+#define DQ_REFEREE_SPLIT 1  /* table A: X class over type-3 stabilizers; table B: Z class, type-1 */
+
+/* dq_env_info selectors */
+#define DQ_INFO_NUM_ACTIONS   0
+#define DQ_INFO_OBS_CHANNELS  1
+#define DQ_INFO_OBS_SIDE      2
+#define DQ_INFO_MASK_WORDS    3
+#define DQ_INFO_STATE_WORDS   4   /* rows of the packed state matrix  */
+#define DQ_INFO_STATE_STRIDE  5   /* columns (n_envs rounded up to 32) */
+#define DQ_INFO_NUM_STABS     6
+#define DQ_INFO_N_TYPE3       7
+#define DQ_INFO_N_TYPE1       8
+#define DQ_INFO_RNG_BLOCKS    9   /* Philox blocks per volume attempt (B of the RNG contract) */
+
+typedef struct dq_env dq_env;
+typedef void* dq_stream;
+
+const char* dq_last_error(void);
+int dq_version(void);
+
+/* Replaces Surface_Code_Environment_Multi_Decoding_Cycles.__init__ (EN/Environments.py:45-97)
+ * for n_envs independent lattices living on `device`.  d in {3,5,7}; volume_depth in [1,8].
+ * seed / env_id_base select the Philox streams: env i uses stream id
+ * env_id_base + i, so a sharded run reproduces the unsharded one. */
+int dq_env_create(dq_env** out, int d, int error_model, int use_Y, int volume_depth,
+                  double p_phys, double p_meas, int64_t n_envs, uint64_t seed,
+                  int64_t env_id_base, int device);
+int dq_env_destroy(dq_env* env);
+int dq_env_info(const dq_env* env, int what, int64_t* out);
+
+/* env.p_phys / env.p_meas are assignable in the reference (SPTS:200-201). */
+int dq_env_set_noise(dq_env* env, double p_phys, double p_meas);
+
+/* Replaces the duck-typed static_decoder.predict + argmax (EN/Environments.py:144,150) by
+ * table lookups.  Tables are DEVICE pointers, 2 bits per entry, 4 entries per byte, entry i
+ * in bits 2*(i&3) of byte i>>2.  The library keeps the pointers (caller keeps them alive).
+ * JOINT: lut_a has 2^(d*d-1) entries indexed by the true syndrome in stabilizer draw order
+ * (bulk row-major, top, bottom, left, right -- EN/Function_Library.py:186-233).
+ * SPLIT: lut_a has 2^(#type-3) entries (logical-X class bit), lut_b 2^(#type-1) entries
+ * (logical-Z class bit; ignored for DQ_MODEL_X), each indexed in draw order restricted to its type. */
+int dq_env_set_referee_lut(dq_env* env, int mode, const void* dev_lut_a, int64_t bytes_a,
+                           const void* dev_lut_b, int64_t bytes_b);
+
+/* env.reset() for every lattice (EN/Environments.py:99-115).  obs / legal_mask may be NULL. */
+int dq_env_reset(dq_env* env, uint8_t* obs, uint64_t* legal_mask, dq_stream stream);
+
+/* env.step(action) for every lattice (EN/Environments.py:118-204).  With auto_reset != 0 a
+ * lattice that finishes (done=1) is reset inside the same call: done/lifetime/reward describe
+ * the finished step, obs/legal_mask the first state of the new episode.  With auto_reset == 0
+ * the reference's behaviour is kept (done stays set until dq_env_reset).  Any output may be NULL. */
+int dq_env_step(dq_env* env, const int32_t* actions, uint8_t* obs, float* reward, uint8_t* done,
+                int32_t* lifetime, uint64_t* legal_mask, int auto_reset, dq_stream stream);
+
+/* Same two calls with HOST buffers (the path bench.py's e2e number times). */
+int dq_env_reset_host(dq_env* env, uint8_t* h_obs, uint64_t* h_legal_mask);
+int dq_env_step_host(dq_env* env, const int32_t* h_actions, uint8_t* h_obs, float* h_reward,
+                     uint8_t* h_done, int32_t* h_lifetime, uint64_t* h_legal_mask, int auto_reset);
+
+/* Packed per-lattice state, uint64 [STATE_WORDS][STATE_STRIDE] on the device (layout in
+ * DESIGN.md section 2): what env.hidden_state / completed_actions / lifetime / done hold in the
+ * reference.  Parity tests inspect and inject it; also the checkpoint format. */
+int dq_env_get_state(dq_env* env, uint64_t* dev_words, dq_stream stream);
+int dq_env_set_state(dq_env* env, const uint64_t* dev_words, dq_stream stream);
+
+/* Uniform pick over the sorted legal actions of every lattice (the random-legal policy the
+ * env-only benchmark uses; also the epsilon branch of EpsGreedyQPolicy, SPTS:110-114).
+ * Draw = Philox(stream id, step_index, block 0, domain 1) word 0; index = floor(u*n/2^32). */
+int dq_policy_random_legal(const dq_env* env, const uint64_t* legal_mask, uint32_t step_index,
+                           int32_t* actions, dq_stream stream);
+
+/* Same pick, with the step index kept in device memory by the handle: dq_policy_seek sets it, every
+ * dq_policy_random_legal_next launch uses it and then advances it by one ON THE DEVICE, so a captured
+ * CUDA graph of (policy, step) pairs draws fresh words on every replay. */
+int dq_policy_seek(dq_env* env, uint32_t step_index, dq_stream stream);
+int dq_policy_random_legal_next(dq_env* env, const uint64_t* legal_mask, int32_t* actions, dq_stream stream);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t dq_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DQ_DECODING_H */

@@ -1,0 +1,226 @@
+"""GPU parity of the CUDA environment (through the C ABI) against the CPU oracle.
+
+Bit-exact on every integer output (obs, done, lifetime, legal mask, packed state) and on the
+0/1 float reward, for every step of seeded trajectories, at sizes the oracle finishes in seconds.
+Full-size (BASELINE config) runs use size-independent properties.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from deepq_decoding_b200 import referee as REF
+
+pytestmark = pytest.mark.gpu
+
+
+def random_referee(rng, d, model):
+    ns = d * d - 1
+    if model == "X" or d == 7:
+        la = rng.integers(0, 256, size=(1 << (ns // 2)) // 4 + 1, dtype=np.uint8) & 0x55
+        lb = rng.integers(0, 256, size=(1 << (ns // 2)) // 4 + 1, dtype=np.uint8) & 0x55
+        return REF.RefereeLUT(d, model, REF.SPLIT, la, lb if model == "DP" else None)
+    return REF.RefereeLUT(d, model, REF.JOINT, rng.integers(0, 256, size=(1 << ns) // 4 + 1, dtype=np.uint8))
+
+
+def make_pair(d, model, use_Y, vd, p, n, seed, base=0, referee=None, auto_reset=True):
+    from deepq_decoding_b200.envs import VecSurfaceCodeEnv
+    rng = np.random.default_rng(1000 * d + vd)
+    ref = referee or random_referee(rng, d, model)
+    env = VecSurfaceCodeEnv(d, p, p, model, use_Y, vd, ref, n_envs=n, seed=seed, env_id_base=base, auto_reset=auto_reset)
+    o = O.OracleVecEnv(d, model, use_Y, vd, p, p, n, seed, base)
+    o.set_referee(ref.mode, ref.lut_a, ref.lut_b)
+    return env, o
+
+
+def compare_state(env, o, idx):
+    for i in idx:
+        st, ost = env.decode_state(i), o.get_env(i)
+        assert np.array_equal(st["hidden_state"], ost["hidden"])
+        assert st["lifetime"] == ost["lifetime"] and st["attempts"] == ost["attempts"] and st["done"] == ost["done"]
+
+
+CASES = [(3, "X", False, 3, 0.05, 1),        # BASELINE config 1: one lattice
+         (3, "X", False, 3, 0.05, 1000),
+         (5, "X", False, 5, 0.02, 777),       # ragged tail CTA
+         (5, "DP", False, 5, 0.02, 1024),
+         (5, "DP", True, 3, 0.03, 33),
+         (7, "DP", False, 7, 0.011, 300),
+         (7, "DP", True, 8, 0.02, 40),        # deepest volume, widest action mask (148 actions, 3 words)
+         (3, "DP", True, 2, 0.08, 64)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "d%d_%s_y%d_vd%d_n%d" % (c[0], c[1], c[2], c[3], c[5]))
+def test_trajectory_parity(case):
+    import torch
+    d, model, use_Y, vd, p, n = case
+    env, o = make_pair(d, model, use_Y, vd, p, n, seed=42, base=5)
+    rng = np.random.default_rng(d + n)
+    obs = env.reset().cpu().numpy()
+    oobs, olegal = o.reset()
+    assert np.array_equal(obs, oobs)
+    assert np.array_equal(env.legal_mask.cpu().numpy().view(np.uint64), olegal)
+    steps = 150 if n <= 1024 else 40
+    ndone = 0
+    for t in range(steps):
+        acts = env.random_legal_actions(t).cpu().numpy().copy()
+        assert np.array_equal(acts, o.random_legal_actions(olegal, t)), "random-legal policy"
+        arb = rng.random(n) < 0.2
+        acts[arb] = rng.integers(-1, o.A + 1, size=int(arb.sum()))      # includes out-of-range -> identity
+        oacts = np.where((acts < 0) | (acts >= o.A), o.A - 1, acts).astype(np.int32)
+        obs, rew, done, info = env.step(torch.from_numpy(acts).cuda())
+        oobs, orew, odone, olife, olegal = o.step(oacts, auto_reset=True)
+        assert np.array_equal(obs.cpu().numpy(), oobs), "obs t=%d" % t
+        assert np.array_equal(rew.cpu().numpy(), orew), "reward t=%d" % t
+        assert np.array_equal(done.cpu().numpy(), odone.astype(bool)), "done t=%d" % t
+        assert np.array_equal(info["lifetime"].cpu().numpy(), olife), "lifetime t=%d" % t
+        assert np.array_equal(info["legal_mask"].cpu().numpy().view(np.uint64), olegal), "legal t=%d" % t
+        ndone += int(odone.sum())
+        if t % 50 == 0:
+            compare_state(env, o, rng.integers(0, n, size=min(n, 4)))
+    if n >= 64:
+        assert ndone > 0
+    env.close()
+
+
+def test_no_auto_reset_keeps_reference_semantics():
+    """auto_reset=0: done is sticky and the lattice keeps evolving, as the reference object does."""
+    import torch
+    env, o = make_pair(5, "DP", False, 5, 0.05, 256, seed=7, auto_reset=False)
+    env.reset(); _, olegal = o.reset()
+    for t in range(60):
+        acts = o.random_legal_actions(olegal, t)
+        obs, rew, done, info = env.step(torch.from_numpy(acts).cuda())
+        oobs, orew, odone, olife, olegal = o.step(acts, auto_reset=False)
+        assert np.array_equal(obs.cpu().numpy(), oobs)
+        assert np.array_equal(done.cpu().numpy(), odone.astype(bool))
+        assert np.array_equal(info["lifetime"].cpu().numpy(), olife)
+    assert odone.sum() > 10
+    # reset clears done / lifetime but keeps the position in the random stream
+    obs = env.reset().cpu().numpy(); oobs, _ = o.reset()
+    assert np.array_equal(obs, oobs)
+    compare_state(env, o, [0, 100, 255])
+    env.close()
+
+
+def test_host_buffer_entry_points_and_noise_setter():
+    env, o = make_pair(5, "X", False, 5, 0.01, 100, seed=3)
+    obs, legal = env.reset_host(); oobs, olegal = o.reset()
+    assert np.array_equal(obs, oobs) and np.array_equal(legal, olegal)
+    for t in range(40):
+        if t == 20:                       # the test sweep mutates env.p_phys / env.p_meas in place (SPTS:200-201)
+            env.p_phys = 0.03; env.p_meas = 0.02; o.set_noise(0.03, 0.02)
+        acts = o.random_legal_actions(olegal, t)
+        obs, rew, done, info = env.step_host(acts)
+        oobs, orew, odone, olife, olegal = o.step(acts, auto_reset=True)
+        assert np.array_equal(obs, oobs) and np.array_equal(rew, orew) and np.array_equal(done, odone.astype(bool))
+        assert np.array_equal(info["lifetime"], olife) and np.array_equal(info["legal_mask"], olegal)
+    env.close()
+
+
+def test_sharding_is_invisible():
+    """Lattices [0,N) on one handle == two handles covering [0,N/2) and [N/2,N) (stream id = global index)."""
+    import torch
+    full, _ = make_pair(5, "DP", False, 5, 0.02, 128, seed=11)
+    lo, _ = make_pair(5, "DP", False, 5, 0.02, 64, seed=11, base=0)
+    hi, _ = make_pair(5, "DP", False, 5, 0.02, 64, seed=11, base=64)
+    a = full.reset().clone(); b = torch.cat([lo.reset(), hi.reset()])
+    assert torch.equal(a, b)
+    for t in range(30):
+        fa = full.random_legal_actions(t).clone()
+        la, ha = lo.random_legal_actions(t).clone(), hi.random_legal_actions(t).clone()
+        assert torch.equal(fa, torch.cat([la, ha]))
+        a = full.step(fa)[0]
+        b = torch.cat([lo.step(la)[0], hi.step(ha)[0]])
+        assert torch.equal(a, b)
+    for e in (full, lo, hi):
+        e.close()
+
+
+def test_state_roundtrip_and_injection():
+    """get_state/set_state: a restored handle continues bit-identically (checkpoint contract)."""
+    import torch
+    env, _ = make_pair(5, "DP", False, 5, 0.02, 96, seed=5)
+    env.reset()
+    for t in range(10):
+        env.step(env.random_legal_actions(t))
+    words = env.get_state_words().clone()
+    legal = env.legal_mask.clone()
+    ref_traj = []
+    for t in range(10, 20):
+        ref_traj.append(env.step(env.random_legal_actions(t))[0].clone())
+    env.set_state_words(words)
+    env.legal_mask.copy_(legal)
+    for k, t in enumerate(range(10, 20)):
+        assert torch.equal(env.step(env.random_legal_actions(t))[0], ref_traj[k])
+    env.close()
+
+
+def test_single_error_syndrome_kat():
+    """Notebook 3 cells 18/20 (README.md:719-780): X on qubit (4,1) of a d=5 lattice lights true
+    syndrome bits (4,1) and (5,2)."""
+    import torch
+    from deepq_decoding_b200.envs import VecSurfaceCodeEnv, true_syndrome_of
+    hidden = np.zeros((5, 5), int); hidden[4, 1] = 1
+    syn = true_syndrome_of(hidden)
+    assert {(int(a), int(b)) for a, b in zip(*np.nonzero(syn))} == {(4, 1), (5, 2)}
+    # same through the kernel: inject the frame with p=0 so the volume shows the noiseless syndrome
+    env = VecSurfaceCodeEnv(5, 0.0, 0.0, "X", False, 5, REF.min_weight(5, "X"), n_envs=1, auto_reset=False)
+    w = torch.zeros((env.state_words, env.state_stride), dtype=torch.int64)
+    w[0, 0] = 1 << (4 * 6 + 1)
+    env.set_state_words(w)
+    obs, rew, done, info = env.step(torch.tensor([env.identity_index], dtype=torch.int32, device="cuda"))
+    layer = obs[0, 0].cpu().numpy()
+    assert {(int(a), int(b)) for a, b in zip(*np.nonzero(layer[::2, ::2]))} == {(4, 1), (5, 2)}
+    assert float(rew[0]) == 0.0 and int(info["lifetime"][0]) == 5
+    # legal moves = qubits touching those two plaquettes (+ identity)
+    assert env.legal_actions(0) == {15, 16, 20, 21, 22, 25}
+    env.close()
+
+
+def test_full_size_properties():
+    """BASELINE config 3 shape (d=5 DP p=0.007, 16384 lattices): size-independent invariants."""
+    import torch
+    from deepq_decoding_b200.envs import VecSurfaceCodeEnv
+    env = VecSurfaceCodeEnv(5, 0.007, 0.007, "DP", False, 5, None, n_envs=16384, seed=1)
+    obs = env.reset()
+    marker = obs[0, 0].clone(); marker[::2, ::2] = 0
+    heavy_frac = []
+    for t in range(50):
+        acts = env.random_legal_actions(t).clone()
+        legal = env.legal_mask.clone()
+        before = (env.get_state_words()[2, :16384] & 0xFFFFFFFF).to(torch.int32)     # stored lifetime
+        # the policy only ever picks legal actions
+        assert bool(((legal[:, 0] >> acts.long()) & 1).all())
+        obs, rew, done, info = env.step(acts)
+        # cells are 0/1 and every syndrome layer carries the constant marker pattern
+        assert int(obs.max()) <= 1
+        m = obs[:, :5].clone(); m[:, :, ::2, ::2] = 0
+        assert bool((m == marker).all())
+        # lifetime moves in multiples of volume_depth, only on identity / repeated actions
+        dl = info["lifetime"] - before
+        assert bool((dl % 5 == 0).all()) and bool((dl >= 0).all())
+        heavy = (acts == 50) | (dl > 0)
+        assert bool(((dl > 0) == heavy).all())
+        heavy_frac.append(float((dl > 0).float().mean()))
+        # a fresh volume is never trivial and clears the action layers; identity is always legal
+        fresh = (dl > 0) | done
+        assert bool((obs[fresh][:, :5, ::2, ::2].sum(dim=(1, 2, 3)) > 0).all())
+        assert int(obs[fresh][:, 5:].sum()) == 0
+        assert bool(((info["legal_mask"][:, 0] >> 50) & 1).all())
+        # reward 1 implies not done
+        assert not bool(((rew == 1.0) & done).any())
+    assert 0.05 < np.mean(heavy_frac) < 0.25          # 11.7 % heavy under random-legal
+    env.close()
+
+
+def test_errors_are_loud():
+    from deepq_decoding_b200 import _lib
+    from deepq_decoding_b200.envs import VecSurfaceCodeEnv
+    with pytest.raises(Exception):
+        VecSurfaceCodeEnv(4, 0.01, 0.01, "DP", False, 3, None, n_envs=4)          # even d (FL:38-39)
+    with pytest.raises(ValueError):
+        VecSurfaceCodeEnv(5, 0.01, 0.01, "IIDXZ", False, 3, None, n_envs=4)
+    with pytest.raises(_lib.DQError):
+        VecSurfaceCodeEnv(9, 0.01, 0.01, "DP", False, 3, REF.RefereeLUT(9, "DP", 1, np.zeros(4, np.uint8)), n_envs=4)
+    with pytest.raises(_lib.DQError):
+        VecSurfaceCodeEnv(5, 0.01, 0.01, "DP", False, 9, None, n_envs=4)          # volume_depth > 8
