@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdq_decoding.so")
+# DQ_DECODING_LIB selects an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("DQ_DECODING_LIB") or os.path.join(_HERE, "libdq_decoding.so")
 
 OK, EINVAL, ECUDA, ESTATE = 0, -1, -2, -3
 MODEL = {"X": 0, "DP": 1}

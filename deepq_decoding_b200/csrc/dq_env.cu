@@ -29,11 +29,20 @@
 
 namespace dq {
 
-constexpr int kEnvsPerCta = 32;
-constexpr int kThreads = 256;
+#ifndef DQ_LATTICES_PER_WARP
+#define DQ_LATTICES_PER_WARP 4
+#endif
+#ifndef DQ_THREADS
+#define DQ_THREADS 64
+#endif
+constexpr int kLpw = DQ_LATTICES_PER_WARP;     // k*L observation bytes are a multiple of k for every L: k-byte stores
+constexpr int kThreads = DQ_THREADS;           // a CTA is just kWarps independent warps
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxVd = 8;
-constexpr int kMaxChunks = 4 * 7 + 2;     // d=7, vd=8: 776 items -> 7 rounds -> 28 ballot words (+2 pad)
+// The reference loops until a volume is non-trivial, forever if p_phys = p_meas = 0 on a clean frame.
+// A kernel must end: after this many attempts in one call the (trivial) volume is accepted.
+constexpr int kMaxAttemptsPerCall = 1 << 20;
+static_assert(kLpw == 4 || kLpw == 8 || kLpw == 16, "a warp's observations must form a 4-, 8- or 16-byte aligned span");
 
 // rows of the packed state matrix
 constexpr int ROW_XB = 0, ROW_ZB = 1, ROW_META = 2, ROW_ACT = 3, ROW_SYN = 6;
@@ -52,6 +61,7 @@ struct EnvParams {
     const uint8_t* lut_a;
     const uint8_t* lut_b;
     u64* state;                                 // [STATE_WORDS][npad]
+    int warp_smem;                              // bytes of shared memory per warp
 };
 
 // ---------------------------------------------------------------- PTX wrappers (TMA bulk copy + mbarrier)
@@ -90,7 +100,7 @@ __device__ __forceinline__ int lut2(const uint8_t* lut, u32 idx) { return (__ldg
 
 template <int D>
 __device__ __forceinline__ int referee_class(const EnvParams& p, u64 syn) {
-    if (p.ref_mode == DQ_REFEREE_JOINT) return lut2(p.lut_a, (u32)stabs_grid_to_compact<D>(syn));
+    if (p.ref_mode == DQ_REFEREE_JOINT) return lut2(p.lut_a, stabs_grid_to_joint_index<D>(syn));
     int c = lut2(p.lut_a, stabs_grid_to_type_index<D, 1>(syn)) & 1;
     if (p.model == DQ_MODEL_DP && p.lut_b) c |= (lut2(p.lut_b, stabs_grid_to_type_index<D, 0>(syn)) & 1) << 1;
     return c;
@@ -106,109 +116,143 @@ __device__ __forceinline__ void stream_or64(u32* s, int off, u64 v) {
     if (x2) atomicOr(s + w + 2, x2);
 }
 
-struct Smem {
-    u64 st[ROW_SYN + kMaxVd][kEnvsPerCta];   // state tile, [row][lattice]
-    u32 chA[kWarps][kMaxChunks + 2];         // ballot streams: x-flip / measurement-flip bits
-    u32 chB[kWarps][kMaxChunks + 2];         // ballot streams: z-flip bits (DP)
-    int32_t life_out[kEnvsPerCta];
-    uint8_t task[kEnvsPerCta];               // lattices needing volume generation
-    uint8_t task_flags[kEnvsPerCta];         // bit0: heavy volume, bit1: reset afterwards
-    int ntask;
-    alignas(8) u64 bar;
-};
-
-// One volume (Environments.py:158-176 / :216-235) for lattice `slot`, executed by a full warp.
-// Updates xb, zb (frame), life, attempts; leaves the vd faulty slices in sm.st[ROW_SYN + j][slot].
+// A fired draw (rare: p ~ 1e-2 per draw) is folded into the per-slice flip accumulators of the warp,
+// acc[kind][slice] as two 32-bit halves, kind 0 = data-qubit X flips, 1 = Z flips, 2 = measurement flips.
 template <int D>
-__device__ __forceinline__ void generate_volume(const EnvParams& p, Smem& sm, int warp, int lane, int slot,
-                                                u32 env_id, u64& xb, u64& zb, u32& life, u32& attempts) {
+__device__ __noinline__ void record_event(u32* acc, int item, u32 uv, int nq_items, int n_items, u32 T1, u32 T2, int dp) {
     typedef Lat<D> L;
-    const int vd = p.vd, R = p.rounds, nq_items = vd * L::NQ;
-    const u32 TA = (p.model == DQ_MODEL_DP) ? p.T2 : p.T;
-    u32* chA = sm.chA[warp];
-    u32* chB = sm.chB[warp];
+    if (item < nq_items) {
+        const int j = item / L::NQ, q = item - j * L::NQ, pos = q + q / D;
+        const u32 bit = 1u << (pos & 31);
+        if (!dp || uv < T2) atomicXor(&acc[((0 * kMaxVd + j) << 1) + (pos >> 5)], bit);     // X or Y
+        if (dp && uv >= T1) atomicXor(&acc[((1 * kMaxVd + j) << 1) + (pos >> 5)], bit);     // Y or Z
+    } else if (item < n_items) {
+        const int mi = item - nq_items, j = mi / L::NS, k = mi - j * L::NS, pos = L::stab_pos(k);
+        atomicXor(&acc[((2 * kMaxVd + j) << 1) + (pos >> 5)], 1u << (pos & 31));
+    }
+}
+
+// One volume (Environments.py:158-176 / :216-235) for one lattice, executed by a full warp.
+// A volume attempt = R rounds of one Philox4x32-10 block per lane (draw i = word i/B of block i%B),
+// issued two rounds at a time so two Philox chains overlap.  Every lane thresholds its own draws;
+// the few that fire are XOR-ed into shared-memory accumulators (record_event).  Lane j < vd then owns
+// slice j: a warp prefix-XOR gives the frame after every slice, one shifted-XOR syndrome per lane the
+// faulty slices.  Updates xb, zb (frame), life, attempts (all warp-uniform); returns this lane's slice.
+template <int D>
+__device__ __forceinline__ u64 generate_volume(const EnvParams& p, u32* acc, int lane, u32 env_id,
+                                               u64& xb, u64& zb, u32& life, u32& attempts) {
+    typedef Lat<D> L;
+    constexpr u32 FULL = 0xffffffffu;
+    const int vd = p.vd, R = p.rounds, nq_items = vd * L::NQ, n_items = vd * (L::NQ + L::NS);
+    const int dp = p.model == DQ_MODEL_DP;
     bool nontrivial;
     u64 f = 0;
+    int guard = 0;
     do {
-        for (int r = 0; r < R; ++r) {
-            const int blk = r * 32 + lane;
-            Philox4 u = philox4x32_10(env_id, attempts, (u32)blk, 0u, p.k0, p.k1);
-            const u32 uu[4] = {u.x, u.y, u.z, u.w};
+        if (lane < 3 * kMaxVd) { acc[2 * lane] = 0; acc[2 * lane + 1] = 0; }
+        __syncwarp();
+        bool evq = false;
+        for (int r = 0; r < R; r += 2) {
+            const Philox4 u0 = philox4x32_10(env_id, attempts, (u32)(r * 32 + lane), 0u, p.k0, p.k1);
+            const Philox4 u1 = philox4x32_10(env_id, attempts, (u32)(r * 32 + 32 + lane), 0u, p.k0, p.k1);
+            const u32 uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const int item = (w * R + r) * 32 + lane;            // = w*B + blk
-                const bool isq = item < nq_items;
-                const bool a = uu[w] < (isq ? TA : p.Tm);
-                const bool b = isq && (p.model == DQ_MODEL_DP) && uu[w] >= p.T1 && uu[w] < p.T;
-                const u32 ba = __ballot_sync(0xffffffffu, a), bb = __ballot_sync(0xffffffffu, b);
-                if (lane == 0) { chA[w * R + r] = ba; chB[w * R + r] = bb; }
+            for (int w = 0; w < 8; ++w) {
+                const int rr = r + (w >> 2);
+                const int item = ((w & 3) * R + rr) * 32 + lane;      // = word*B + block
+                const u32 thr = (item < nq_items) ? p.T : p.Tm;
+                if (rr < R && uu[w] < thr) {
+                    record_event<D>(acc, item, uu[w], nq_items, n_items, p.T1, p.T2, dp);
+                    evq |= item < nq_items;
+                }
             }
         }
-        if (lane < 2) { chA[4 * R + lane] = 0; chB[4 * R + lane] = 0; }
+        const bool anyq = __any_sync(FULL, evq);
         __syncwarp();
         u64 ex = 0, ez = 0, m = 0;
         if (lane < vd) {
-            ex = qubits_compact_to_grid<D>(extract_bits(chA, lane * L::NQ, L::NQ));
-            if (p.model == DQ_MODEL_DP) ez = qubits_compact_to_grid<D>(extract_bits(chB, lane * L::NQ, L::NQ));
-            m = stabs_compact_to_grid<D>(extract_bits(chA, nq_items + lane * L::NS, L::NS));
+            const u64* a64 = reinterpret_cast<const u64*>(acc);
+            ex = a64[0 * kMaxVd + lane]; ez = a64[1 * kMaxVd + lane]; m = a64[2 * kMaxVd + lane];
         }
         __syncwarp();
-        // inclusive prefix XOR over slices: frame delta after slice `lane`
+        if (anyq) {                           // inclusive prefix XOR over slices: frame delta after slice `lane`
 #pragma unroll
-        for (int off = 1; off < kMaxVd; off <<= 1) {
-            u64 tx = __shfl_up_sync(0xffffffffu, ex, off), tz = __shfl_up_sync(0xffffffffu, ez, off);
-            if (lane >= off) { ex ^= tx; ez ^= tz; }
+            for (int off = 1; off < kMaxVd; off <<= 1) {
+                const u64 tx = __shfl_up_sync(FULL, ex, off), tz = __shfl_up_sync(FULL, ez, off);
+                if (lane >= off) { ex ^= tx; ez ^= tz; }
+            }
         }
         const u64 fx = xb ^ ex, fz = zb ^ ez;
-        f = true_syndrome<D>(fx, fz) ^ m;
-        nontrivial = __ballot_sync(0xffffffffu, lane < vd && f != 0) != 0;
-        xb = __shfl_sync(0xffffffffu, fx, vd - 1);
-        zb = __shfl_sync(0xffffffffu, fz, vd - 1);
+        f = (lane < vd) ? (true_syndrome<D>(fx, fz) ^ m) : 0ull;
+        nontrivial = __any_sync(FULL, f != 0);
+        if (anyq) {
+            xb = __shfl_sync(FULL, fx, vd - 1);
+            zb = __shfl_sync(FULL, fz, vd - 1);
+        }
         life += (u32)vd;
         attempts += 1;
-    } while (!nontrivial);
-    if (lane < vd) sm.st[ROW_SYN + lane][slot] = f;
+    } while (!nontrivial && ++guard < kMaxAttemptsPerCall);
+    return f;
 }
 
+// Every warp owns kLpw lattices end to end; warps never synchronise with each other.
+//   A  lane = lattice: apply the action to the Pauli frame, true syndrome by shifted XORs, homology
+//      label, referee table lookup, reward / done, heavy (identity | repeat) flag
+//   B  for every flagged lattice, the whole warp draws a fresh volume (generate_volume)
+//   C  lane per (lattice, layer): legal-move mask, and the layer's (2d+1)^2-cell bitmap OR-ed into the
+//      warp's contiguous observation bit stream in shared memory
+//   D  stream bits -> observation bytes; the warp's kLpw observations are one contiguous span of HBM
 template <int D, bool RESET>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 896 / kThreads)
 env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t* __restrict__ obs,
                 float* __restrict__ reward, uint8_t* __restrict__ done_out, int32_t* __restrict__ lifetime,
                 u64* __restrict__ legal, int auto_reset) {
     typedef Lat<D> L;
+    constexpr u32 FULL = 0xffffffffu;
+    constexpr int kPre = (kLpw * kMaxVd + 31) / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-    u32* bits = reinterpret_cast<u32*>(smem_raw + ((sizeof(Smem) + 15) & ~size_t(15)));   // obs_bits u32 words (+2 pad)
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int env0 = blockIdx.x * kEnvsPerCta;
-    const int nrows_used = ROW_SYN + p.vd;
+    const int env0 = (blockIdx.x * kWarps + warp) * kLpw;
+    if (env0 >= p.npad) return;
     const int C = p.vd + p.layers;
+    const int nvalid = max(0, min(kLpw, p.n - env0));
+    const int stream_words = (kLpw * p.obs_bits + 31) / 32;
 
-    // ---- stage the state tile: one 256 B TMA bulk copy per used row
-    if (tid == 0) { mbar_init(&sm.bar, 1); sm.ntask = 0; }
-    __syncthreads();
-    if (tid == 0) {
-        const int nrows = 3 + p.layers + p.vd;
-        mbar_expect_tx(&sm.bar, (u32)(nrows * kEnvsPerCta * 8));
-        for (int r = 0; r < nrows_used; ++r) {
-            if (r >= ROW_ACT + p.layers && r < ROW_SYN) continue;
-            bulk_load(&sm.st[r][0], p.state + (size_t)r * p.npad + env0, kEnvsPerCta * 8, &sm.bar);
+    // per-warp shared memory: [syndrome + action rows: (kMaxVd+3) x kLpw u64][flip accumulators][bit stream]
+    unsigned char* wbase = smem_raw + (size_t)warp * p.warp_smem;
+    u64 (*rows)[kLpw] = reinterpret_cast<u64 (*)[kLpw]>(wbase);
+    u32* acc = reinterpret_cast<u32*>(wbase + (size_t)(kMaxVd + 3) * kLpw * 8);
+    u32* bits = acc + 3 * kMaxVd * 2;
+
+    // ---- loads: the syndrome rows are only needed for the observation; fetch them now, park them in
+    //      shared memory after phase A
+    u64 pre[kPre];
+#pragma unroll
+    for (int i = 0; i < kPre; ++i) {
+        const int t = i * 32 + lane;
+        pre[i] = (t < p.vd * kLpw) ? p.state[(size_t)(ROW_SYN + t / kLpw) * p.npad + env0 + t % kLpw] : 0ull;
+    }
+    const int e = env0 + lane;
+    const bool mine = lane < kLpw, live = lane < nvalid;
+    u64 xb = 0, zb = 0, meta = 0, act[3] = {0, 0, 0};
+    int a = p.A - 1;
+    if (mine) {
+        meta = p.state[(size_t)ROW_META * p.npad + e];
+        if (!RESET) {
+            if (live) a = actions[e];
+            xb = p.state[(size_t)ROW_XB * p.npad + e];
+            zb = p.state[(size_t)ROW_ZB * p.npad + e];
+#pragma unroll
+            for (int l = 0; l < 3; ++l) if (l < p.layers) act[l] = p.state[(size_t)(ROW_ACT + l) * p.npad + e];
         }
     }
-    for (int i = tid; i < p.obs_bits + 2; i += kThreads) bits[i] = 0;
-    mbar_wait(&sm.bar, 0);
+    for (int i = lane; i < (stream_words + 6) / 4; i += 32) reinterpret_cast<uint4*>(bits)[i] = make_uint4(0, 0, 0, 0);
 
-    // ---- phase A: lane = lattice
-    if (warp == 0) {
-        const int e = env0 + lane;
-        u64 xb = 0, zb = 0, meta = sm.st[ROW_META][lane], act[3] = {0, 0, 0};
-        u32 flags = 0;
+    // ---- phase A: lane = lattice (lanes >= kLpw idle)
+    u32 flags = 0;
+    int32_t life_out = 0;
+    if (mine) {
         if (!RESET) {
-            xb = sm.st[ROW_XB][lane]; zb = sm.st[ROW_ZB][lane];
-#pragma unroll
-            for (int l = 0; l < 3; ++l) if (l < p.layers) act[l] = sm.st[ROW_ACT + l][lane];
-            int a = (e < p.n) ? actions[e] : p.A - 1;
             if (a < 0 || a >= p.A) a = p.A - 1;
             const bool ident = (a == p.A - 1);
             const int layer = ident ? 0 : a / L::NQ, q = ident ? 0 : a % L::NQ;
@@ -227,112 +271,142 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             u32 dn = (u32)(meta >> 63);
             float rw = 0.f;
             if (label == 0 && syn == 0) rw = 1.f;
-            else if (referee_class<D>(p, syn) != label) dn = 1;
+            else if (live && referee_class<D>(p, syn) != label) dn = 1;
             if (!heavy) {
                 if (layer == 0) act[0] |= bit; else if (layer == 1) act[1] |= bit; else act[2] |= bit;
             }
             meta = (meta & ~(1ull << 63)) | ((u64)dn << 63);
-            if (e < p.n) {
+            if (live) {
                 if (reward) reward[e] = rw;
                 if (done_out) done_out[e] = (uint8_t)dn;
+                flags = (heavy ? 1u : 0u) | ((dn && auto_reset) ? 2u : 0u);   // padding lattices never draw volumes
             }
-            flags = (heavy ? 1u : 0u) | ((dn && auto_reset) ? 2u : 0u);
-            sm.life_out[lane] = (int32_t)(u32)meta;
-        } else {
-            flags = 2u;           // reset keeps only the attempt counter (the RNG position)
+            life_out = (int32_t)(u32)meta;
+        } else if (live) {
+            flags = 2u;               // reset keeps only the attempt counter (the position in the random stream)
         }
-        sm.st[ROW_XB][lane] = xb; sm.st[ROW_ZB][lane] = zb; sm.st[ROW_META][lane] = meta;
+    }
 #pragma unroll
-        for (int l = 0; l < 3; ++l) if (l < p.layers) sm.st[ROW_ACT + l][lane] = act[l];
-        const u32 tmask = __ballot_sync(0xffffffffu, flags != 0);
-        if (flags) {
-            const int pos = __popc(tmask & ((1u << lane) - 1));
-            sm.task[pos] = (uint8_t)lane; sm.task_flags[pos] = (uint8_t)flags;
-        }
-        if (lane == 0) sm.ntask = __popc(tmask);
+    for (int i = 0; i < kPre; ++i) {
+        const int t = i * 32 + lane;
+        if (t < p.vd * kLpw) rows[t / kLpw][t % kLpw] = pre[i];
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- phase B: warp per lattice that needs a new volume
-    for (int t = warp; t < sm.ntask; t += kWarps) {
-        const int slot = sm.task[t], flags = sm.task_flags[t];
+    // ---- phase B: one volume (two when a finished lattice restarts) per flagged lattice, whole warp each
+    u32 todo = __ballot_sync(FULL, flags != 0);
+    while (todo) {
+        const int slot = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const u32 fl = __shfl_sync(FULL, flags, slot);
+        u64 bx = __shfl_sync(FULL, xb, slot), bz = __shfl_sync(FULL, zb, slot);
+        const u64 bm = __shfl_sync(FULL, meta, slot);
+        u32 life = (u32)bm, attempts = (u32)(bm >> 32) & 0x7FFFFFFFu, dn = (u32)(bm >> 63);
         const u32 env_id = p.env_id_base + (u32)(env0 + slot);
-        u64 xb = sm.st[ROW_XB][slot], zb = sm.st[ROW_ZB][slot], meta = sm.st[ROW_META][slot];
-        u32 life = (u32)meta, attempts = (u32)(meta >> 32) & 0x7FFFFFFFu, dn = (u32)(meta >> 63);
-        if (flags & 1) generate_volume<D>(p, sm, warp, lane, slot, env_id, xb, zb, life, attempts);
-        if (!RESET && lane == 0) sm.life_out[slot] = (int32_t)life;
-        if (flags & 2) {               // reset: zero frame, fresh counters, one more volume
-            __syncwarp();
-            xb = 0; zb = 0; life = 0; dn = 0;
-            generate_volume<D>(p, sm, warp, lane, slot, env_id, xb, zb, life, attempts);
+        u64 f = 0;
+        int32_t lo = (int32_t)life;
+        for (int pass = 0; pass < 2; ++pass) {          // pass 0: heavy step, pass 1: restart of a finished lattice
+            if (!(fl & (1u << pass))) continue;
+            if (pass == 1) { bx = 0; bz = 0; life = 0; dn = 0; }
+            f = generate_volume<D>(p, acc, lane, env_id, bx, bz, life, attempts);
+            if (pass == 0) lo = (int32_t)life;
         }
-        if (lane == 0) {
-            sm.st[ROW_XB][slot] = xb; sm.st[ROW_ZB][slot] = zb;
-            sm.st[ROW_META][slot] = meta_pack(life, attempts, dn);
-            for (int l = 0; l < p.layers; ++l) sm.st[ROW_ACT + l][slot] = 0;
+        if (lane < p.vd) {
+            rows[lane][slot] = f;
+            p.state[(size_t)(ROW_SYN + lane) * p.npad + env0 + slot] = f;
+        }
+        if (lane == slot) {
+            xb = bx; zb = bz; meta = meta_pack(life, attempts, dn);
+            act[0] = act[1] = act[2] = 0;
+            if (!RESET) life_out = lo;
         }
     }
-    __syncthreads();
+    if (mine) {                       // persistent state back to HBM (syndrome rows were stored where they changed)
+        p.state[(size_t)ROW_XB * p.npad + e] = xb;
+        p.state[(size_t)ROW_ZB * p.npad + e] = zb;
+        p.state[(size_t)ROW_META * p.npad + e] = meta;
+#pragma unroll
+        for (int l = 0; l < 3; ++l)
+            if (l < p.layers) { p.state[(size_t)(ROW_ACT + l) * p.npad + e] = act[l]; rows[p.vd + l][lane] = act[l]; }
+        if (live && lifetime && !RESET) lifetime[e] = life_out;
+    }
+    __syncwarp();
 
-    // ---- phase C: thread per (lattice, layer): legal mask + layer bitmap into the CTA bit stream
-    for (int t = tid; t < kEnvsPerCta * C; t += kThreads) {
-        const int slot = t % kEnvsPerCta, layer = t / kEnvsPerCta;
-        const int e = env0 + slot;
+    // ---- phase C: lane per (lattice, layer): legal mask + layer bitmap OR-ed into the warp's bit stream
+    for (int t = lane; t < kLpw * C; t += 32) {
+        const int slot = t % kLpw, layer = t / kLpw;
         u64 w[L::PW];
-        if (layer < p.vd) syndrome_layer_bitmap<D>(sm.st[ROW_SYN + layer][slot], w);
-        else action_layer_bitmap<D>(sm.st[ROW_ACT + layer - p.vd][slot], w);
+        if (layer < p.vd) syndrome_layer_bitmap<D>(rows[layer][slot], w);
+        else action_layer_bitmap<D>(rows[layer][slot], w);
         const int off = slot * p.obs_bits + layer * L::P;
 #pragma unroll
         for (int i = 0; i < L::PW; ++i) stream_or64(bits, off + 64 * i, w[i]);
-        if (layer == 0 && e < p.n) {
-            if (lifetime && !RESET) lifetime[e] = sm.life_out[slot];
-            if (legal) {
-                u64 summed = 0, acted = 0;
-                for (int j = 0; j < p.vd; ++j) summed |= sm.st[ROW_SYN + j][slot];
-                for (int l = 0; l < p.layers; ++l) acted |= sm.st[ROW_ACT + l][slot];
-                const u64 lq = qubits_grid_to_compact<D>(qubits_adjacent_to<D>(summed) | qubits_neighbours_of<D>(acted));
-                u64 mw[3] = {0, 0, 0};
-                for (int l = 0; l < p.layers; ++l) {
+        if (layer == 0 && slot < nvalid && legal) {
+            u64 summed = 0, acted = 0;
+            for (int j = 0; j < p.vd; ++j) summed |= rows[j][slot];
+            for (int l = 0; l < p.layers; ++l) acted |= rows[p.vd + l][slot];
+            const u64 lq = qubits_grid_to_compact<D>(qubits_adjacent_to<D>(summed) | qubits_neighbours_of<D>(acted));
+            u64 mw[3] = {0, 0, 0};
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                if (l < p.layers) {
                     const int o = l * L::NQ, i = o >> 6, s = o & 63;
                     mw[i] |= lq << s;
                     if (s && i + 1 < 3) mw[i + 1] |= lq >> (64 - s);
                 }
-                mw[(p.A - 1) >> 6] |= 1ull << ((p.A - 1) & 63);
-                for (int i = 0; i < p.W; ++i) legal[(size_t)e * p.W + i] = mw[i];
+            }
+            const int ib = p.A - 1;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                if (i == (ib >> 6)) mw[i] |= 1ull << (ib & 63);
+                if (i < p.W) legal[(size_t)(env0 + slot) * p.W + i] = mw[i];
             }
         }
     }
-    fence_proxy_async();      // phase A/B wrote the state tile through the generic proxy
-    __syncthreads();
+    __syncwarp();
 
-    // ---- write the state tile back (TMA bulk store), overlapped with phase D
-    if (tid == 0) {
-        for (int r = 0; r < nrows_used; ++r) {
-            if (r >= ROW_ACT + p.layers && r < ROW_SYN) continue;
-            bulk_store(p.state + (size_t)r * p.npad + env0, &sm.st[r][0], kEnvsPerCta * 8);
-        }
-    }
-
-    // ---- phase D: 16 stream bits -> 16 observation bytes per 128-bit store
-    if (obs) {
-        const int nvalid = min(kEnvsPerCta, p.n - env0);
+    // ---- phase D: stream bits -> observation bytes, widest store the span's alignment allows
+    if (obs && nvalid > 0) {
         const long long vbytes = (long long)nvalid * p.obs_bits;
         uint8_t* out = obs + (size_t)env0 * p.obs_bits;
-        const int units = (int)(vbytes >> 4);
-        for (int u = tid; u < units; u += kThreads) {
-            const u32 word = bits[u >> 1];
-            const u32 h = (u & 1) ? (word >> 16) : (word & 0xFFFFu);
-            uint4 v;
-            v.x = ((h & 0xFu) * 0x00204081u) & 0x01010101u;
-            v.y = (((h >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
-            v.z = (((h >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
-            v.w = (((h >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
-            *reinterpret_cast<uint4*>(out + ((size_t)u << 4)) = v;
+        long long done_bytes;
+        if (kLpw % 16 == 0) {                                   // 16-byte aligned span: 128-bit stores
+            const int units = (int)(vbytes >> 4);
+#pragma unroll 2
+            for (int u = lane; u < units; u += 32) {
+                const u32 word = bits[u >> 1];
+                const u32 h = (u & 1) ? (word >> 16) : word;
+                uint4 v;
+                v.x = ((h & 0xFu) * 0x00204081u) & 0x01010101u;
+                v.y = (((h >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+                v.z = (((h >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+                v.w = (((h >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+                *reinterpret_cast<uint4*>(out + ((size_t)u << 4)) = v;
+            }
+            done_bytes = (long long)units << 4;
+        } else if (kLpw % 8 == 0) {                             // 8-byte aligned span: 64-bit stores
+            const int units = (int)(vbytes >> 3);
+#pragma unroll 2
+            for (int u = lane; u < units; u += 32) {
+                const u32 h = bits[u >> 2] >> ((u & 3) * 8);
+                uint2 v;
+                v.x = ((h & 0xFu) * 0x00204081u) & 0x01010101u;
+                v.y = (((h >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+                *reinterpret_cast<uint2*>(out + ((size_t)u << 3)) = v;
+            }
+            done_bytes = (long long)units << 3;
+        } else {                                                // 4-byte aligned span: 32-bit stores
+            const int units = (int)(vbytes >> 2);
+#pragma unroll 4
+            for (int u = lane; u < units; u += 32) {
+                const u32 h = (bits[u >> 3] >> ((u & 7) * 4)) & 0xFu;
+                *reinterpret_cast<u32*>(out + ((size_t)u << 2)) = (h * 0x00204081u) & 0x01010101u;
+            }
+            done_bytes = (long long)units << 2;
         }
-        for (long long b = ((long long)units << 4) + tid; b < vbytes; b += kThreads)
+        for (long long b = done_bytes + lane; b < vbytes; b += 32)
             out[b] = (uint8_t)((bits[b >> 5] >> (b & 31)) & 1u);
     }
-    if (tid == 0) bulk_commit_wait_read();
 }
 
 // Uniform pick over the sorted legal actions.  `ctr` (optional) = {step index, finished-CTA count} in
@@ -341,12 +415,18 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
 __global__ void policy_random_legal_kernel(const u64* __restrict__ legal, int n, int W, int A, u32 env_id_base,
                                            u32 step, u32* __restrict__ ctr, u32 k0, u32 k1,
                                            int32_t* __restrict__ actions) {
+    __shared__ u32 s_step;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ctr) step = *reinterpret_cast<volatile u32*>(ctr);
-    if (e < n) {
-        u64 m[3] = {0, 0, 0};
-        int cnt = 0;
+    u64 m[3] = {0, 0, 0};
+    int cnt = 0;
+    if (e < n)
         for (int i = 0; i < W; ++i) { m[i] = legal[(size_t)e * W + i]; cnt += popc64(m[i]); }
+    if (ctr) {                                // thread 0's read has landed before anyone passes the barrier
+        if (threadIdx.x == 0) s_step = *reinterpret_cast<volatile u32*>(ctr);
+        __syncthreads();
+        step = s_step;
+    }
+    if (e < n) {
         const Philox4 u = philox4x32_10(env_id_base + (u32)e, step, 0u, 1u, k0, k1);
         int pick = (int)mulhi32(u.x, (u32)cnt), act = A - 1;
         for (int i = 0; i < W; ++i) {
@@ -356,13 +436,8 @@ __global__ void policy_random_legal_kernel(const u64* __restrict__ legal, int n,
         }
         actions[e] = act;
     }
-    if (ctr) {
-        __syncthreads();                      // every thread of this CTA has read the step index
-        if (threadIdx.x == 0) {
-            __threadfence();
-            if (atomicAdd(ctr + 1, 1u) == gridDim.x - 1) { ctr[1] = 0; atomicAdd(ctr, 1u); }
-        }
-    }
+    // the last CTA to get here advances the step index: by then every CTA has read it
+    if (ctr && threadIdx.x == 0 && atomicAdd(ctr + 1, 1u) == gridDim.x - 1) { ctr[1] = 0; atomicAdd(ctr, 1u); }
 }
 
 __global__ void set_u32_kernel(u32* p, u32 v) { p[0] = v; p[1] = 0; }
@@ -450,7 +525,8 @@ extern "C" int dq_env_create(dq_env** out, int d, int error_model, int use_Y, in
     p.ref_mode = -1;
     e->device = device;
     e->state_rows = ROW_SYN + volume_depth;
-    e->smem_bytes = ((sizeof(Smem) + 15) & ~size_t(15)) + (size_t)(p.obs_bits + 2) * 4;
+    p.warp_smem = (int)(((size_t)(kMaxVd + 3) * kLpw * 8 + 3 * kMaxVd * 8 + ((size_t)(kLpw * p.obs_bits + 31) / 32 + 8) * 4 + 127) / 128 * 128);
+    e->smem_bytes = (size_t)p.warp_smem * kWarps;
     cudaError_t err = cudaMalloc(&p.state, (size_t)e->state_rows * p.npad * sizeof(u64));
     if (err != cudaSuccess) { delete e; return fail(DQ_ECUDA, std::string("cudaMalloc(state): ") + cudaGetErrorString(err)); }
     err = cudaMemset(p.state, 0, (size_t)e->state_rows * p.npad * sizeof(u64));
@@ -524,7 +600,7 @@ static int launch_env(dq_env* e, const int32_t* actions, uint8_t* obs, float* re
                       u64* legal, int auto_reset, cudaStream_t st) {
     const EnvParams& p = e->p;
     if (obs && (reinterpret_cast<uintptr_t>(obs) & 15)) return fail(DQ_EINVAL, "obs must be 16-byte aligned");
-    const dim3 grid(p.npad / kEnvsPerCta), block(kThreads);
+    const dim3 grid((p.npad / kLpw + kWarps - 1) / kWarps), block(kThreads);
     switch (p.d) {
         case 3: env_step_kernel<3, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset); break;
         case 5: env_step_kernel<5, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset); break;
@@ -615,7 +691,7 @@ extern "C" int dq_env_set_state(dq_env* e, const uint64_t* dev_words, dq_stream 
 
 static int launch_policy(const dq_env* e, const uint64_t* legal, u32 step, u32* ctr, int32_t* actions, cudaStream_t st) {
     const EnvParams& p = e->p;
-    policy_random_legal_kernel<<<(p.n + 255) / 256, 256, 0, st>>>((const u64*)legal, p.n, p.W, p.A, p.env_id_base, step, ctr,
+    policy_random_legal_kernel<<<(p.n + 127) / 128, 128, 0, st>>>((const u64*)legal, p.n, p.W, p.A, p.env_id_base, step, ctr,
                                                                   p.k0, p.k1, actions);
     g_launches.fetch_add(1);
     DQ_CUDA(cudaGetLastError());

@@ -155,6 +155,19 @@ template <int D> DQ_HD u64 stabs_compact_to_grid(u64 c) {
     for (int k = 0; k < 4 * nb; ++k) s |= ((c >> (M * M + k)) & 1ull) << Lat<D>::stab_pos(M * M + k);
     return s;
 }
+// JOINT referee-table index ("joint order", include/dq_decoding.h): grid rows 1..D-1 are D contiguous
+// present plaquettes each (columns 1..D on odd rows, 0..D-1 on even rows); the top and bottom boundary
+// rows interleave into columns 1..D-1.  Only present plaquettes are ever set in a true syndrome.
+template <int D> DQ_HD u32 stabs_grid_to_joint_index(u64 s) {
+    constexpr int G = D + 1;
+    static_assert(D * D - 1 <= 32 || D == 7, "joint index must fit 32 bits");
+    if (D * D - 1 > 32) return 0;             // d = 7 has no joint table (dq_env_set_referee_lut rejects it)
+    u32 idx = 0;
+#pragma unroll
+    for (int a = 1; a < D; ++a) idx |= ((u32)(s >> (a * G + (a & 1))) & ((1u << D) - 1)) << (((a - 1) * D) & 31);
+    const u32 tb = ((u32)s | (u32)(s >> (D * G))) & ((1u << D) - 1);
+    return idx | ((tb >> 1) << ((D * (D - 1)) & 31));
+}
 // index over the stabilizers of one type (ODD=1: type 3 / X-sensitive), draw order restricted
 template <int D, int ODD> DQ_HD u32 stabs_grid_to_type_index(u64 s) {
     u32 c = 0;

@@ -8,7 +8,7 @@ with one canonical fp64 evaluator makes `done` a pure integer function that is i
 on the CPU oracle and on the GPU (SURVEY section 7 "Referee exactness").
 
 Table formats are those of `dq_env_set_referee_lut` (include/dq_decoding.h):
-  JOINT  one table over all stabilizers in draw order, 2-bit entries holding X + 2Z
+  JOINT  one table over all stabilizers in `joint_order`, 2-bit entries holding X + 2Z
   SPLIT  table A over the type-3 (X-sensitive) stabilizers -> X bit,
          table B over the type-1 (Z-sensitive) stabilizers -> Z bit
 
@@ -47,6 +47,15 @@ def stabilizer_order(d):
     return order
 
 
+def joint_order(d):
+    """Bit order of a JOINT table index: grid rows 1..d-1 left to right (d stabilizers each), then the
+    top/bottom boundary stabilizers by column (odd columns sit on the top row, even ones on the bottom)."""
+    order = [(a, b) for a in range(1, d) for b in range(d + 1) if plaquette_present(d, a, b)]
+    order += [((0 if b % 2 else d), b) for b in range(1, d)]
+    assert sorted(order) == sorted(stabilizer_order(d))
+    return order
+
+
 def type_order(d, odd):
     """Stabilizers of one type (odd=1: type 3, flips on X/Y) in draw order."""
     return [(a, b) for a, b in stabilizer_order(d) if (a + b) % 2 == odd]
@@ -78,7 +87,7 @@ class RefereeLUT:
         self.lut_b = None if lut_b is None else np.ascontiguousarray(lut_b, np.uint8)
         self.source = source
         self.n_classes = 2 if error_model == "X" else 4
-        self._order = stabilizer_order(d)
+        self._order = joint_order(d)
         self._dev = {}
 
     # -- host-side evaluation (used by .predict and by tests) --
@@ -166,7 +175,7 @@ def from_keras_mlp(path, d, error_model, device="cpu", batch=1 << 16, progress=N
     if error_model == "X":
         positions, mode = type_order(d, 1), SPLIT       # only X-sensitive stabilizers can fire
     else:
-        positions, mode = stabilizer_order(d), JOINT
+        positions, mode = joint_order(d), JOINT
     n = 1 << len(positions)
     classes = np.empty(n, np.uint8)
     with torch.no_grad():
@@ -188,7 +197,7 @@ def from_predict(static_decoder, d, error_model, batch=1 << 14):
     if error_model == "X":
         positions, mode = type_order(d, 1), SPLIT
     else:
-        positions, mode = stabilizer_order(d), JOINT
+        positions, mode = joint_order(d), JOINT
         if len(positions) > 26:
             raise ValueError("joint tabulation needs d*d-1 <= 26 stabilizers")
     n = 1 << len(positions)

@@ -82,10 +82,12 @@ int dq_env_set_noise(dq_env* env, double p_phys, double p_meas);
 /* Replaces the duck-typed static_decoder.predict + argmax (EN/Environments.py:144,150) by
  * table lookups.  Tables are DEVICE pointers, 2 bits per entry, 4 entries per byte, entry i
  * in bits 2*(i&3) of byte i>>2.  The library keeps the pointers (caller keeps them alive).
- * JOINT: lut_a has 2^(d*d-1) entries indexed by the true syndrome in stabilizer draw order
- * (bulk row-major, top, bottom, left, right -- EN/Function_Library.py:186-233).
+ * JOINT: lut_a has 2^(d*d-1) entries; index bit k = true-syndrome bit of the k-th stabilizer in
+ * "joint order": plaquette-grid rows 1..d-1 left to right (d stabilizers each), then the top/bottom
+ * boundary stabilizers by column 1..d-1 (odd columns lie on row 0, even ones on row d).
  * SPLIT: lut_a has 2^(#type-3) entries (logical-X class bit), lut_b 2^(#type-1) entries
- * (logical-Z class bit; ignored for DQ_MODEL_X), each indexed in draw order restricted to its type. */
+ * (logical-Z class bit; ignored for DQ_MODEL_X), each indexed in the stabilizer draw order of
+ * EN/Function_Library.py:186-233 (bulk row-major, top, bottom, left, right) restricted to its type. */
 int dq_env_set_referee_lut(dq_env* env, int mode, const void* dev_lut_a, int64_t bytes_a,
                            const void* dev_lut_b, int64_t bytes_b);
 

@@ -107,6 +107,7 @@ typedef struct {
     int8_t ptype[MAXG][MAXG];             /* 0 absent, 1 / 3 plaquette type        */
     int stab_a[MAXG * MAXG], stab_b[MAXG * MAXG];   /* compact (draw) order        */
     int n3, n1;                           /* #type-3 / #type-1 stabilizers         */
+    int joint_a[MAXG * MAXG], joint_b[MAXG * MAXG];   /* joint-table bit order       */
     int ref_mode;                         /* -1 none, 0 joint, 1 split             */
     const uint8_t* lut_a;                 /* joint table, or X-class table         */
     const uint8_t* lut_b;                 /* Z-class table (split, DP only)        */
@@ -136,6 +137,12 @@ static void build_lattice(oracle_t* o) {
     for (int x = 0; x < nb; ++x) { o->stab_a[k] = 2 * x + 2; o->stab_b[k] = 0;     ++k; }
     for (int x = 0; x < nb; ++x) { o->stab_a[k] = 2 * x + 1; o->stab_b[k] = g - 1; ++k; }
     o->ns = k;
+    /* joint referee table bit order (include/dq_decoding.h): grid rows 1..d-1 left to right,
+     * then the top/bottom boundary stabilizers by column */
+    int m = 0;
+    for (int a = 1; a < d; ++a)
+        for (int b = 0; b <= d; ++b) if (o->ptype[a][b]) { o->joint_a[m] = a; o->joint_b[m] = b; ++m; }
+    for (int b = 1; b < d; ++b) { o->joint_a[m] = (b % 2) ? 0 : d; o->joint_b[m] = b; ++m; }
     o->n3 = o->n1 = 0;
     for (int i = 0; i < k; ++i) {
         if (o->ptype[o->stab_a[i]][o->stab_b[i]] == 3) o->n3++; else o->n1++;
@@ -184,8 +191,8 @@ static int referee_class(const oracle_t* o, const env_t* e) {
     for (int k = 0; k < o->ns; ++k) {
         int a = o->stab_a[k], b = o->stab_b[k];
         uint64_t bit = (uint64_t)e->true_syn[a][b];
-        all |= bit << k;
         if (o->ptype[a][b] == 3) i3 |= bit << c3++; else i1 |= bit << c1++;
+        all |= (uint64_t)e->true_syn[o->joint_a[k]][o->joint_b[k]] << k;
     }
     if (o->ref_mode == 0) return lut2(o->lut_a, all);
     if (o->ref_mode == 1) {
@@ -362,7 +369,7 @@ void dqo_set_noise(void* h, double p_phys, double p_meas) {
     o->T1 = o->T / 3; o->T2 = (uint32_t)((2ull * o->T) / 3);
 }
 
-/* mode 0: lut_a = joint 2-bit table over all ns stabilizers (compact order);
+/* mode 0: lut_a = joint 2-bit table over all ns stabilizers (joint order: rows 1..d-1, then top/bottom by column);
  * mode 1: lut_a = X-class table over type-3 stabilizers, lut_b = Z-class table over
  *         type-1 stabilizers (each in compact order restricted to its type).    */
 void dqo_set_referee(void* h, int mode, const uint8_t* lut_a, const uint8_t* lut_b) {

@@ -152,6 +152,13 @@ def stab_order(d):
     return order
 
 
+def joint_order(d):
+    present = lambda a, b: not ((a == 0 and b % 2 == 0) or (a == d and b % 2 == 1) or
+                                (b == 0 and a % 2 == 1) or (b == d and a % 2 == 0))
+    order = [(a, b) for a in range(1, d) for b in range(d + 1) if present(a, b)]
+    return order + [((0 if b % 2 else d), b) for b in range(1, d)]
+
+
 class LutReferee:
     """`.predict` answering from the packed 2-bit referee tables (same bytes as the CUDA path)."""
 
@@ -160,6 +167,7 @@ class LutReferee:
         self.lut_a = np.asarray(lut_a, np.uint8)
         self.lut_b = None if lut_b is None else np.asarray(lut_b, np.uint8)
         self.order = stab_order(d)
+        self.jorder = joint_order(d)
         self.n_classes = 2 if error_model == "X" else 4
 
     @staticmethod
@@ -170,9 +178,10 @@ class LutReferee:
         g = self.d + 1
         allb = i3 = i1 = 0
         c3 = c1 = 0
+        for k, (a, b) in enumerate(self.jorder):
+            allb |= int(vec[a * g + b]) << k
         for k, (a, b) in enumerate(self.order):
             bit = int(vec[a * g + b])
-            allb |= bit << k
             if (a + b) % 2 == 1:
                 i3 |= bit << c3
                 c3 += 1

@@ -12,6 +12,7 @@ u64 hb_q_c2g(int d, u64 c) { return DISPATCH(qubits_compact_to_grid<3>(c), qubit
 u64 hb_q_g2c(int d, u64 g) { return DISPATCH(qubits_grid_to_compact<3>(g), qubits_grid_to_compact<5>(g), qubits_grid_to_compact<7>(g)); }
 u64 hb_s_c2g(int d, u64 c) { return DISPATCH(stabs_compact_to_grid<3>(c), stabs_compact_to_grid<5>(c), stabs_compact_to_grid<7>(c)); }
 u64 hb_s_g2c(int d, u64 g) { return DISPATCH(stabs_grid_to_compact<3>(g), stabs_grid_to_compact<5>(g), stabs_grid_to_compact<7>(g)); }
+u32 hb_joint_index(int d, u64 s) { return d == 3 ? stabs_grid_to_joint_index<3>(s) : stabs_grid_to_joint_index<5>(s); }
 u32 hb_type_index(int d, int odd, u64 s) {
     if (odd) return DISPATCH((stabs_grid_to_type_index<3, 1>(s)), (stabs_grid_to_type_index<5, 1>(s)), (stabs_grid_to_type_index<7, 1>(s)));
     return DISPATCH((stabs_grid_to_type_index<3, 0>(s)), (stabs_grid_to_type_index<5, 0>(s)), (stabs_grid_to_type_index<7, 0>(s)));

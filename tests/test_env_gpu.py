@@ -136,6 +136,23 @@ def test_sharding_is_invisible():
         e.close()
 
 
+def test_graph_capturable_policy_counter():
+    """dq_policy_random_legal_next == dq_policy_random_legal at the device-side step index, which it advances."""
+    import ctypes as C
+    import torch
+    from deepq_decoding_b200 import _lib
+    env, _ = make_pair(5, "DP", False, 5, 0.02, 1000, seed=5)
+    env.reset()
+    L = _lib.lib()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out = torch.zeros(1000, dtype=torch.int32, device="cuda")
+    _lib.check(L.dq_policy_seek(env._h, 7, st))
+    for step in (7, 8, 9):
+        _lib.check(L.dq_policy_random_legal_next(env._h, C.c_void_p(env.legal_mask.data_ptr()), C.c_void_p(out.data_ptr()), st))
+        assert torch.equal(out, env.random_legal_actions(step))
+    env.close()
+
+
 def test_state_roundtrip_and_injection():
     """get_state/set_state: a restored handle continues bit-identically (checkpoint contract)."""
     import torch

@@ -28,7 +28,7 @@ def hb():
     u64, u32, i = C.c_uint64, C.c_uint32, C.c_int
     for name, res, args in [("hb_true_syndrome", u64, [i, u64, u64]), ("hb_label", i, [i, u64, u64]),
                             ("hb_q_c2g", u64, [i, u64]), ("hb_q_g2c", u64, [i, u64]), ("hb_s_c2g", u64, [i, u64]),
-                            ("hb_s_g2c", u64, [i, u64]), ("hb_type_index", u32, [i, i, u64]),
+                            ("hb_s_g2c", u64, [i, u64]), ("hb_type_index", u32, [i, i, u64]), ("hb_joint_index", u32, [i, u64]),
                             ("hb_adjacent", u64, [i, u64]), ("hb_neighbours", u64, [i, u64]),
                             ("hb_syn_layer", None, [i, u64, C.c_void_p]), ("hb_act_layer", None, [i, u64, C.c_void_p]),
                             ("hb_philox", None, [u32] * 6 + [C.c_void_p]), ("hb_extract_bits", u64, [C.c_void_p, i, i]),
@@ -80,6 +80,8 @@ def test_syndrome_label_and_orders(hb, d):
         c = hb.hb_s_g2c(d, s)
         assert c == sum(int(syn[a, b]) << k for k, (a, b) in enumerate(R.stabilizer_order(d)))
         assert hb.hb_s_c2g(d, c) == s
+        if d <= 5:
+            assert hb.hb_joint_index(d, s) == sum(int(syn[a, b]) << k for k, (a, b) in enumerate(R.joint_order(d)))
         for odd in (0, 1):
             assert hb.hb_type_index(d, odd, s) == sum(int(syn[a, b]) << k for k, (a, b) in enumerate(R.type_order(d, odd)))
         q = int(rng.integers(0, 1 << (d * d)))
