@@ -1,19 +1,21 @@
 // dq_env.cu -- sm_100a environment-step kernel + C ABI (include/dq_decoding.h).
 //
-// One CTA advances 32 independent lattices.  Per-lattice state is bit-packed into
-// STATE_WORDS uint64 rows of a [row][lattice] matrix in HBM; a CTA's tile
-// is one 256-byte segment per row, staged through shared memory with 1-D TMA bulk copies
-// (cp.async.bulk + mbarrier in, cp.async.bulk.bulk_group out).  Phases:
-//   A  warp 0, lane = lattice: apply the action to the Pauli frame, true syndrome by shifted
-//      XORs, homology label, referee table lookup, reward / done, heavy(identity|repeat) flag
-//   B  warp per heavy lattice: a volume attempt = R rounds of one Philox4x32-10 block per lane;
-//      threshold compares become __ballot_sync words which ARE the per-slice error /
-//      measurement-flip bit streams; lanes < volume_depth each rebuild one slice, a warp
-//      prefix-XOR gives the frame after every slice; repeat until the summed volume is non-trivial
-//   C  thread per (lattice, layer): legal-move mask, and the layer's (2d+1)^2-cell bitmap OR-ed
-//      into one contiguous bit stream for the CTA
-//   D  all threads: 16 stream bits -> 16 observation bytes, one aligned 128-bit store each
-//      (the CTA's 32 observations are one contiguous, 16-byte aligned span of HBM)
+// One CTA (4 warps) advances a tile of 16 independent lattices.  Per-lattice state is bit-packed into
+// uint64 rows of a [row][lattice] matrix that stays L2-resident between steps:
+// Pauli-frame planes, action boards, counters, AND the already-rendered (2d+1)^2-cell bitmap of every
+// observation layer, so that a step only re-renders what changed.  Phases (3 block barriers):
+//   0  every thread prefetches the cached layer bitmap of "its" (lattice, layer) pair
+//   A  warp 0, lane = lattice: apply the action to the Pauli frame, true syndrome by shifted XORs,
+//      homology label, referee table lookup, reward / done, heavy (identity | repeat) flag
+//   B  warp per flagged lattice: draw a fresh syndrome volume (generate_volume) -- Philox4x32-10, one
+//      block per lane, fired draws folded into per-slice flip masks, warp prefix-XOR over slices --
+//      and re-render that lattice's layer bitmaps (lane per (slice, plaquette row))
+//   C  thread per (lattice, layer): OR the layer bitmap into the tile's contiguous observation bit
+//      stream in shared memory; layer-0 threads also emit the legal-move mask
+//   D  all threads: 16 stream bits -> 16 observation bytes, one aligned 128-bit store each (the tile's
+//      16 observations are one contiguous, 16-byte aligned span of HBM)
+// Earlier variants (32-lattice tiles staged by TMA bulk copies; warp-autonomous 4/8-lattice groups) and
+// the ncu evidence that led here are summarised in profiles/README.md.
 //
 // Replaces (reference paths relative to example_notebooks/): Environments.py:99-115 (reset),
 // :118-204 (step), :206-235, :238-314 and the Function_Library.py helpers they call.
@@ -29,23 +31,22 @@
 
 namespace dq {
 
-#ifndef DQ_LATTICES_PER_WARP
-#define DQ_LATTICES_PER_WARP 4
-#endif
 #ifndef DQ_THREADS
-#define DQ_THREADS 64
+#define DQ_THREADS 128
 #endif
-constexpr int kLpw = DQ_LATTICES_PER_WARP;     // k*L observation bytes are a multiple of k for every L: k-byte stores
-constexpr int kThreads = DQ_THREADS;           // a CTA is just kWarps independent warps
+constexpr int kEpc = 16;                       // lattices per CTA: 16*L observation bytes are a multiple of 16 for every L
+constexpr int kThreads = DQ_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxVd = 8;
+constexpr int kMaxLayers = kMaxVd + 3;
+constexpr int kTaskIters = (kEpc * kMaxLayers + kThreads - 1) / kThreads;
 // The reference loops until a volume is non-trivial, forever if p_phys = p_meas = 0 on a clean frame.
 // A kernel must end: after this many attempts in one call the (trivial) volume is accepted.
 constexpr int kMaxAttemptsPerCall = 1 << 20;
-static_assert(kLpw == 4 || kLpw == 8 || kLpw == 16, "a warp's observations must form a 4-, 8- or 16-byte aligned span");
 
-// rows of the packed state matrix
-constexpr int ROW_XB = 0, ROW_ZB = 1, ROW_META = 2, ROW_ACT = 3, ROW_SYN = 6;
+// rows of the packed state matrix: frame planes, counters, action boards, OR of the volume's slices,
+// then the rendered bitmap of observation layer l in rows ROW_BM + l*PW .. +PW-1 (PW = ceil((2d+1)^2/64))
+constexpr int ROW_XB = 0, ROW_ZB = 1, ROW_META = 2, ROW_ACT = 3, ROW_SUM = 6, ROW_BM = 7;
 // meta word: [lifetime:32][attempt counter:31][done:1]
 DQ_HD u64 meta_pack(u32 life, u32 attempts, u32 done) { return (u64)life | ((u64)(attempts & 0x7FFFFFFFu) << 32) | ((u64)done << 63); }
 
@@ -61,7 +62,6 @@ struct EnvParams {
     const uint8_t* lut_a;
     const uint8_t* lut_b;
     u64* state;                                 // [STATE_WORDS][npad]
-    int warp_smem;                              // bytes of shared memory per warp
 };
 
 // ---------------------------------------------------------------- PTX wrappers (TMA bulk copy + mbarrier)
@@ -195,13 +195,26 @@ __device__ __forceinline__ u64 generate_volume(const EnvParams& p, u32* acc, int
     return f;
 }
 
-// Every warp owns kLpw lattices end to end; warps never synchronise with each other.
-//   A  lane = lattice: apply the action to the Pauli frame, true syndrome by shifted XORs, homology
-//      label, referee table lookup, reward / done, heavy (identity | repeat) flag
-//   B  for every flagged lattice, the whole warp draws a fresh volume (generate_volume)
-//   C  lane per (lattice, layer): legal-move mask, and the layer's (2d+1)^2-cell bitmap OR-ed into the
-//      warp's contiguous observation bit stream in shared memory
-//   D  stream bits -> observation bytes; the warp's kLpw observations are one contiguous span of HBM
+struct Smem {
+    u64 bm[kMaxLayers * 4][kEpc];     // freshly rendered layer bitmaps (valid where fresh[slot])
+    u64 fx[kEpc], fz[kEpc], fmeta[kEpc];   // phase A -> B hand-off: frame planes, counters
+    u64 sum[kEpc], acted[kEpc];       // OR of the volume's slices; OR of the action boards
+    u32 acc[kWarps][3 * kMaxVd * 2];  // per-warp flip accumulators of generate_volume
+    int actbit[kEpc];                 // light step: (action layer << 16) | cell bit to set, else -1
+    int32_t life_out[kEpc];
+    uint8_t task[kEpc], task_flags[kEpc], fresh[kEpc];
+    int ntask;
+};
+
+template <int D> __device__ __forceinline__ u64 marker_word_rt(int i) {
+    switch (i) {
+        case 0: return Lat<D>::marker_word(0);
+        case 1: return Lat<D>::marker_word(1);
+        case 2: return Lat<D>::marker_word(2);
+        default: return Lat<D>::marker_word(3);
+    }
+}
+
 template <int D, bool RESET>
 __global__ void __launch_bounds__(kThreads, 896 / kThreads)
 env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t* __restrict__ obs,
@@ -209,202 +222,221 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                 u64* __restrict__ legal, int auto_reset) {
     typedef Lat<D> L;
     constexpr u32 FULL = 0xffffffffu;
-    constexpr int kPre = (kLpw * kMaxVd + 31) / 32;
+    constexpr int PW = L::PW, G = L::G, H = L::H;
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    u32* bits = reinterpret_cast<u32*>(smem_raw + ((sizeof(Smem) + 15) & ~size_t(15)));   // the tile's observation bit stream
+
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int env0 = (blockIdx.x * kWarps + warp) * kLpw;
-    if (env0 >= p.npad) return;
+    const int env0 = blockIdx.x * kEpc;
     const int C = p.vd + p.layers;
-    const int nvalid = max(0, min(kLpw, p.n - env0));
-    const int stream_words = (kLpw * p.obs_bits + 31) / 32;
+    const int nvalid = min(kEpc, p.n - env0);
+    const size_t np = (size_t)p.npad;
 
-    // per-warp shared memory: [syndrome + action rows: (kMaxVd+3) x kLpw u64][flip accumulators][bit stream]
-    unsigned char* wbase = smem_raw + (size_t)warp * p.warp_smem;
-    u64 (*rows)[kLpw] = reinterpret_cast<u64 (*)[kLpw]>(wbase);
-    u32* acc = reinterpret_cast<u32*>(wbase + (size_t)(kMaxVd + 3) * kLpw * 8);
-    u32* bits = acc + 3 * kMaxVd * 2;
-
-    // ---- loads: the syndrome rows are only needed for the observation; fetch them now, park them in
-    //      shared memory after phase A
-    u64 pre[kPre];
+    // ---- phase 0: prefetch the cached bitmap of this thread's (lattice, layer) pairs; clear scratch
+    u64 bmw[kTaskIters][PW];
 #pragma unroll
-    for (int i = 0; i < kPre; ++i) {
-        const int t = i * 32 + lane;
-        pre[i] = (t < p.vd * kLpw) ? p.state[(size_t)(ROW_SYN + t / kLpw) * p.npad + env0 + t % kLpw] : 0ull;
-    }
-    const int e = env0 + lane;
-    const bool mine = lane < kLpw, live = lane < nvalid;
-    u64 xb = 0, zb = 0, meta = 0, act[3] = {0, 0, 0};
-    int a = p.A - 1;
-    if (mine) {
-        meta = p.state[(size_t)ROW_META * p.npad + e];
-        if (!RESET) {
-            if (live) a = actions[e];
-            xb = p.state[(size_t)ROW_XB * p.npad + e];
-            zb = p.state[(size_t)ROW_ZB * p.npad + e];
+    for (int it = 0; it < kTaskIters; ++it) {
+        const int t = it * kThreads + tid;
 #pragma unroll
-            for (int l = 0; l < 3; ++l) if (l < p.layers) act[l] = p.state[(size_t)(ROW_ACT + l) * p.npad + e];
-        }
+        for (int i = 0; i < PW; ++i)
+            bmw[it][i] = (t < kEpc * C) ? p.state[(ROW_BM + (t / kEpc) * PW + i) * np + env0 + t % kEpc] : 0ull;
     }
-    for (int i = lane; i < (stream_words + 6) / 4; i += 32) reinterpret_cast<uint4*>(bits)[i] = make_uint4(0, 0, 0, 0);
+    const u64 sum_pref = (tid < kEpc) ? p.state[ROW_SUM * np + env0 + tid] : 0ull;
+    {
+        const int nvec = (kEpc * p.obs_bits + 31) / 32 / 4 + 1;
+        uint4* b4 = reinterpret_cast<uint4*>(bits);
+        for (int i = tid; i < nvec; i += kThreads) b4[i] = make_uint4(0, 0, 0, 0);
+        if (tid < kEpc) { sm.fresh[tid] = 0; sm.actbit[tid] = -1; }
+    }
 
-    // ---- phase A: lane = lattice (lanes >= kLpw idle)
-    u32 flags = 0;
-    int32_t life_out = 0;
-    if (mine) {
-        if (!RESET) {
-            if (a < 0 || a >= p.A) a = p.A - 1;
-            const bool ident = (a == p.A - 1);
-            const int layer = ident ? 0 : a / L::NQ, q = ident ? 0 : a % L::NQ;
-            const u64 bit = ident ? 0ull : (1ull << (q + q / D));
-            const u64 cur = layer == 0 ? act[0] : (layer == 1 ? act[1] : act[2]);
-            const bool heavy = ident || (cur & bit) != 0;
-            // Pauli applied by this action layer (Function_Library.py:253-304)
-            bool fx, fz;
-            if (p.model == DQ_MODEL_X) { fx = true; fz = false; }
-            else if (p.use_y) { fx = layer <= 1; fz = layer >= 1; }
-            else { fx = layer == 0; fz = layer == 1; }
-            if (fx) xb ^= bit;
-            if (fz) zb ^= bit;
-            const u64 syn = true_syndrome<D>(xb, zb);
-            const int label = homology_label<D>(xb, zb);
-            u32 dn = (u32)(meta >> 63);
-            float rw = 0.f;
-            if (label == 0 && syn == 0) rw = 1.f;
-            else if (live && referee_class<D>(p, syn) != label) dn = 1;
-            if (!heavy) {
-                if (layer == 0) act[0] |= bit; else if (layer == 1) act[1] |= bit; else act[2] |= bit;
+    // ---- phase A: warp 0, lane = lattice
+    if (warp == 0) {
+        const int e = env0 + lane;
+        const bool mine = lane < kEpc, live = lane < nvalid;
+        u64 xb = 0, zb = 0, meta = 0, act[3] = {0, 0, 0};
+        u32 flags = 0;
+        if (mine) {
+            meta = p.state[ROW_META * np + e];
+            int actbit = -1;
+            if (!RESET) {
+                int a = live ? actions[e] : p.A - 1;
+                xb = p.state[ROW_XB * np + e];
+                zb = p.state[ROW_ZB * np + e];
+#pragma unroll
+                for (int l = 0; l < 3; ++l) if (l < p.layers) act[l] = p.state[(ROW_ACT + l) * np + e];
+                if (a < 0 || a >= p.A) a = p.A - 1;
+                const bool ident = (a == p.A - 1);
+                const int layer = ident ? 0 : a / L::NQ, q = ident ? 0 : a % L::NQ;
+                const int qr = q / D, qc = q - qr * D;
+                const u64 bit = ident ? 0ull : (1ull << (q + qr));
+                const u64 cur = layer == 0 ? act[0] : (layer == 1 ? act[1] : act[2]);
+                const bool heavy = ident || (cur & bit) != 0;
+                // Pauli applied by this action layer (Function_Library.py:253-304)
+                bool fx, fz;
+                if (p.model == DQ_MODEL_X) { fx = true; fz = false; }
+                else if (p.use_y) { fx = layer <= 1; fz = layer >= 1; }
+                else { fx = layer == 0; fz = layer == 1; }
+                if (fx) xb ^= bit;
+                if (fz) zb ^= bit;
+                const u64 syn = true_syndrome<D>(xb, zb);
+                const int label = homology_label<D>(xb, zb);
+                u32 dn = (u32)(meta >> 63);
+                float rw = 0.f;
+                if (label == 0 && syn == 0) rw = 1.f;
+                else if (live && referee_class<D>(p, syn) != label) dn = 1;
+                if (!heavy) {
+                    if (layer == 0) act[0] |= bit; else if (layer == 1) act[1] |= bit; else act[2] |= bit;
+                    actbit = (layer << 16) | ((2 * qr + 1) * H + 2 * qc + 1);
+                }
+                meta = (meta & ~(1ull << 63)) | ((u64)dn << 63);
+                if (live) {
+                    if (reward) reward[e] = rw;
+                    if (done_out) done_out[e] = (uint8_t)dn;
+                    flags = (heavy ? 1u : 0u) | ((dn && auto_reset) ? 2u : 0u);   // padding lattices never draw volumes
+                }
+                sm.life_out[lane] = (int32_t)(u32)meta;
+                if (!flags) {                  // light step: the frame and the touched action board go back now
+                    p.state[ROW_XB * np + e] = xb;
+                    p.state[ROW_ZB * np + e] = zb;
+                    p.state[ROW_META * np + e] = meta;
+                    if (!ident) p.state[(ROW_ACT + layer) * np + e] = layer == 0 ? act[0] : (layer == 1 ? act[1] : act[2]);
+                }
+            } else if (live) {
+                flags = 2u;               // reset keeps only the attempt counter (the position in the random stream)
             }
-            meta = (meta & ~(1ull << 63)) | ((u64)dn << 63);
-            if (live) {
-                if (reward) reward[e] = rw;
-                if (done_out) done_out[e] = (uint8_t)dn;
-                flags = (heavy ? 1u : 0u) | ((dn && auto_reset) ? 2u : 0u);   // padding lattices never draw volumes
-            }
-            life_out = (int32_t)(u32)meta;
-        } else if (live) {
-            flags = 2u;               // reset keeps only the attempt counter (the position in the random stream)
+            sm.fx[lane] = xb; sm.fz[lane] = zb; sm.fmeta[lane] = meta;
+            sm.acted[lane] = act[0] | act[1] | act[2];
+            sm.actbit[lane] = flags ? -1 : actbit;
         }
+        const u32 tmask = __ballot_sync(FULL, flags != 0);
+        if (flags) {
+            const int pos = __popc(tmask & ((1u << lane) - 1));
+            sm.task[pos] = (uint8_t)lane; sm.task_flags[pos] = (uint8_t)flags;
+        }
+        if (lane == 0) sm.ntask = __popc(tmask);
     }
-#pragma unroll
-    for (int i = 0; i < kPre; ++i) {
-        const int t = i * 32 + lane;
-        if (t < p.vd * kLpw) rows[t / kLpw][t % kLpw] = pre[i];
-    }
-    __syncwarp();
+    __syncthreads();
 
-    // ---- phase B: one volume (two when a finished lattice restarts) per flagged lattice, whole warp each
-    u32 todo = __ballot_sync(FULL, flags != 0);
-    while (todo) {
-        const int slot = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const u32 fl = __shfl_sync(FULL, flags, slot);
-        u64 bx = __shfl_sync(FULL, xb, slot), bz = __shfl_sync(FULL, zb, slot);
-        const u64 bm = __shfl_sync(FULL, meta, slot);
-        u32 life = (u32)bm, attempts = (u32)(bm >> 32) & 0x7FFFFFFFu, dn = (u32)(bm >> 63);
+    // ---- phase B: warp per flagged lattice: fresh volume(s), then re-render its layer bitmaps
+    for (int t = warp; t < sm.ntask; t += kWarps) {
+        const int slot = sm.task[t], fl = sm.task_flags[t];
         const u32 env_id = p.env_id_base + (u32)(env0 + slot);
+        const int e = env0 + slot;
+        u64 bx = sm.fx[slot], bz = sm.fz[slot];
+        const u64 bm0 = sm.fmeta[slot];
+        u32 life = (u32)bm0, attempts = (u32)(bm0 >> 32) & 0x7FFFFFFFu, dn = (u32)(bm0 >> 63);
         u64 f = 0;
         int32_t lo = (int32_t)life;
         for (int pass = 0; pass < 2; ++pass) {          // pass 0: heavy step, pass 1: restart of a finished lattice
-            if (!(fl & (1u << pass))) continue;
+            if (!(fl & (1 << pass))) continue;
             if (pass == 1) { bx = 0; bz = 0; life = 0; dn = 0; }
-            f = generate_volume<D>(p, acc, lane, env_id, bx, bz, life, attempts);
+            f = generate_volume<D>(p, sm.acc[warp], lane, env_id, bx, bz, life, attempts);
             if (pass == 0) lo = (int32_t)life;
         }
-        if (lane < p.vd) {
-            rows[lane][slot] = f;
-            p.state[(size_t)(ROW_SYN + lane) * p.npad + env0 + slot] = f;
+        u64 summed = f;                                 // lanes >= vd hold 0
+        summed |= __shfl_xor_sync(FULL, summed, 1);
+        summed |= __shfl_xor_sync(FULL, summed, 2);
+        summed |= __shfl_xor_sync(FULL, summed, 4);
+        if (lane == 0) {
+            p.state[ROW_XB * np + e] = bx;
+            p.state[ROW_ZB * np + e] = bz;
+            p.state[ROW_META * np + e] = meta_pack(life, attempts, dn);
+            p.state[ROW_SUM * np + e] = summed;
+            sm.sum[slot] = summed; sm.acted[slot] = 0; sm.fresh[slot] = 1;
+            if (!RESET) sm.life_out[slot] = lo;
         }
-        if (lane == slot) {
-            xb = bx; zb = bz; meta = meta_pack(life, attempts, dn);
-            act[0] = act[1] = act[2] = 0;
-            if (!RESET) life_out = lo;
-        }
-    }
-    if (mine) {                       // persistent state back to HBM (syndrome rows were stored where they changed)
-        p.state[(size_t)ROW_XB * p.npad + e] = xb;
-        p.state[(size_t)ROW_ZB * p.npad + e] = zb;
-        p.state[(size_t)ROW_META * p.npad + e] = meta;
-#pragma unroll
-        for (int l = 0; l < 3; ++l)
-            if (l < p.layers) { p.state[(size_t)(ROW_ACT + l) * p.npad + e] = act[l]; rows[p.vd + l][lane] = act[l]; }
-        if (live && lifetime && !RESET) lifetime[e] = life_out;
-    }
-    __syncwarp();
-
-    // ---- phase C: lane per (lattice, layer): legal mask + layer bitmap OR-ed into the warp's bit stream
-    for (int t = lane; t < kLpw * C; t += 32) {
-        const int slot = t % kLpw, layer = t / kLpw;
-        u64 w[L::PW];
-        if (layer < p.vd) syndrome_layer_bitmap<D>(rows[layer][slot], w);
-        else action_layer_bitmap<D>(rows[layer][slot], w);
-        const int off = slot * p.obs_bits + layer * L::P;
-#pragma unroll
-        for (int i = 0; i < L::PW; ++i) stream_or64(bits, off + 64 * i, w[i]);
-        if (layer == 0 && slot < nvalid && legal) {
-            u64 summed = 0, acted = 0;
-            for (int j = 0; j < p.vd; ++j) summed |= rows[j][slot];
-            for (int l = 0; l < p.layers; ++l) acted |= rows[p.vd + l][slot];
-            const u64 lq = qubits_grid_to_compact<D>(qubits_adjacent_to<D>(summed) | qubits_neighbours_of<D>(acted));
-            u64 mw[3] = {0, 0, 0};
-#pragma unroll
-            for (int l = 0; l < 3; ++l) {
-                if (l < p.layers) {
-                    const int o = l * L::NQ, i = o >> 6, s = o & 63;
-                    mw[i] |= lq << s;
-                    if (s && i + 1 < 3) mw[i + 1] |= lq >> (64 - s);
+        if (lane < p.layers) p.state[(ROW_ACT + lane) * np + e] = 0;
+        // render: markers first, then lane per (slice, plaquette row) ORs its spread row in
+        for (int i = lane; i < C * PW; i += 32) sm.bm[i][slot] = (i < p.vd * PW) ? marker_word_rt<D>(i % PW) : 0ull;
+        __syncwarp();
+        for (int base = 0; base < p.vd * G; base += 32) {
+            const int idx = base + lane;
+            const int j = min(idx / G, p.vd - 1), a = idx - (idx / G) * G;
+            const u64 fj = __shfl_sync(FULL, f, j);
+            if (idx < p.vd * G) {
+                const u32 v = spread2_8((u32)(fj >> (a * G)) & ((1u << G) - 1));
+                const int off = 2 * a * H, k = off >> 5, sh = off & 31;          // 32-bit word k of the layer bitmap
+                if (v) {
+                    u32* w0 = reinterpret_cast<u32*>(&sm.bm[j * PW + (k >> 1)][slot]) + (k & 1);
+                    atomicOr(w0, v << sh);
+                    if (sh > 17 && (v >> (32 - sh))) {
+                        u32* w1 = reinterpret_cast<u32*>(&sm.bm[j * PW + ((k + 1) >> 1)][slot]) + ((k + 1) & 1);
+                        atomicOr(w1, v >> (32 - sh));
+                    }
                 }
             }
-            const int ib = p.A - 1;
+        }
+        __syncwarp();
+        for (int i = lane; i < C * PW; i += 32) p.state[(ROW_BM + i) * np + e] = sm.bm[i][slot];
+    }
+    __syncthreads();
+
+    // ---- phase C: thread per (lattice, layer): layer bitmap into the tile's bit stream; legal mask
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                if (i == (ib >> 6)) mw[i] |= 1ull << (ib & 63);
-                if (i < p.W) legal[(size_t)(env0 + slot) * p.W + i] = mw[i];
+    for (int it = 0; it < kTaskIters; ++it) {
+        const int t = it * kThreads + tid;
+        if (t >= kEpc * C) break;
+        const int slot = t % kEpc, layer = t / kEpc;
+        const bool fresh = sm.fresh[slot] != 0;
+        u64 w[PW];
+#pragma unroll
+        for (int i = 0; i < PW; ++i) w[i] = fresh ? sm.bm[layer * PW + i][slot] : bmw[it][i];
+        const int ab = sm.actbit[slot];
+        if (ab >= 0 && layer - p.vd == (ab >> 16)) {              // this step's action lights one more cell
+            const int pos = ab & 0xFFFF;
+#pragma unroll
+            for (int i = 0; i < PW; ++i)
+                if ((pos >> 6) == i) {
+                    w[i] |= 1ull << (pos & 63);
+                    p.state[(ROW_BM + layer * PW + i) * np + env0 + slot] = w[i];
+                }
+        }
+        const int off = slot * p.obs_bits + layer * L::P;
+#pragma unroll
+        for (int i = 0; i < PW; ++i) stream_or64(bits, off + 64 * i, w[i]);
+        if (layer == 0 && slot < nvalid) {
+            if (lifetime && !RESET) lifetime[env0 + slot] = sm.life_out[slot];
+            if (legal) {
+                const u64 summed = fresh ? sm.sum[slot] : sum_pref;
+                const u64 lq = qubits_grid_to_compact<D>(qubits_adjacent_to<D>(summed) | qubits_neighbours_of<D>(sm.acted[slot]));
+                u64 mw[3] = {0, 0, 0};
+#pragma unroll
+                for (int l = 0; l < 3; ++l) {
+                    if (l < p.layers) {
+                        const int o = l * L::NQ, i = o >> 6, s = o & 63;
+                        mw[i] |= lq << s;
+                        if (s && i + 1 < 3) mw[i + 1] |= lq >> (64 - s);
+                    }
+                }
+                const int ib = p.A - 1;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    if (i == (ib >> 6)) mw[i] |= 1ull << (ib & 63);
+                    if (i < p.W) legal[(size_t)(env0 + slot) * p.W + i] = mw[i];
+                }
             }
         }
     }
-    __syncwarp();
+    __syncthreads();
 
-    // ---- phase D: stream bits -> observation bytes, widest store the span's alignment allows
-    if (obs && nvalid > 0) {
+    // ---- phase D: 16 stream bits -> 16 observation bytes per 128-bit store
+    if (obs) {
         const long long vbytes = (long long)nvalid * p.obs_bits;
         uint8_t* out = obs + (size_t)env0 * p.obs_bits;
-        long long done_bytes;
-        if (kLpw % 16 == 0) {                                   // 16-byte aligned span: 128-bit stores
-            const int units = (int)(vbytes >> 4);
+        const int units = (int)(vbytes >> 4);
 #pragma unroll 2
-            for (int u = lane; u < units; u += 32) {
-                const u32 word = bits[u >> 1];
-                const u32 h = (u & 1) ? (word >> 16) : word;
-                uint4 v;
-                v.x = ((h & 0xFu) * 0x00204081u) & 0x01010101u;
-                v.y = (((h >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
-                v.z = (((h >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
-                v.w = (((h >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
-                *reinterpret_cast<uint4*>(out + ((size_t)u << 4)) = v;
-            }
-            done_bytes = (long long)units << 4;
-        } else if (kLpw % 8 == 0) {                             // 8-byte aligned span: 64-bit stores
-            const int units = (int)(vbytes >> 3);
-#pragma unroll 2
-            for (int u = lane; u < units; u += 32) {
-                const u32 h = bits[u >> 2] >> ((u & 3) * 8);
-                uint2 v;
-                v.x = ((h & 0xFu) * 0x00204081u) & 0x01010101u;
-                v.y = (((h >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
-                *reinterpret_cast<uint2*>(out + ((size_t)u << 3)) = v;
-            }
-            done_bytes = (long long)units << 3;
-        } else {                                                // 4-byte aligned span: 32-bit stores
-            const int units = (int)(vbytes >> 2);
-#pragma unroll 4
-            for (int u = lane; u < units; u += 32) {
-                const u32 h = (bits[u >> 3] >> ((u & 7) * 4)) & 0xFu;
-                *reinterpret_cast<u32*>(out + ((size_t)u << 2)) = (h * 0x00204081u) & 0x01010101u;
-            }
-            done_bytes = (long long)units << 2;
+        for (int u = tid; u < units; u += kThreads) {
+            const u32 word = bits[u >> 1];
+            const u32 h = (u & 1) ? (word >> 16) : word;
+            uint4 v;
+            v.x = ((h & 0xFu) * 0x00204081u) & 0x01010101u;
+            v.y = (((h >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+            v.z = (((h >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+            v.w = (((h >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+            *reinterpret_cast<uint4*>(out + ((size_t)u << 4)) = v;
         }
-        for (long long b = done_bytes + lane; b < vbytes; b += 32)
+        for (long long b = ((long long)units << 4) + tid; b < vbytes; b += kThreads)
             out[b] = (uint8_t)((bits[b >> 5] >> (b & 31)) & 1u);
     }
 }
@@ -524,9 +556,8 @@ extern "C" int dq_env_create(dq_env** out, int d, int error_model, int use_Y, in
     p.env_id_base = (u32)env_id_base;
     p.ref_mode = -1;
     e->device = device;
-    e->state_rows = ROW_SYN + volume_depth;
-    p.warp_smem = (int)(((size_t)(kMaxVd + 3) * kLpw * 8 + 3 * kMaxVd * 8 + ((size_t)(kLpw * p.obs_bits + 31) / 32 + 8) * 4 + 127) / 128 * 128);
-    e->smem_bytes = (size_t)p.warp_smem * kWarps;
+    e->state_rows = ROW_BM + (volume_depth + p.layers) * (((2 * d + 1) * (2 * d + 1) + 63) / 64);
+    e->smem_bytes = ((sizeof(Smem) + 15) & ~size_t(15)) + ((size_t)(kEpc * p.obs_bits + 31) / 32 / 4 + 2) * 16;
     cudaError_t err = cudaMalloc(&p.state, (size_t)e->state_rows * p.npad * sizeof(u64));
     if (err != cudaSuccess) { delete e; return fail(DQ_ECUDA, std::string("cudaMalloc(state): ") + cudaGetErrorString(err)); }
     err = cudaMemset(p.state, 0, (size_t)e->state_rows * p.npad * sizeof(u64));
@@ -600,7 +631,7 @@ static int launch_env(dq_env* e, const int32_t* actions, uint8_t* obs, float* re
                       u64* legal, int auto_reset, cudaStream_t st) {
     const EnvParams& p = e->p;
     if (obs && (reinterpret_cast<uintptr_t>(obs) & 15)) return fail(DQ_EINVAL, "obs must be 16-byte aligned");
-    const dim3 grid((p.npad / kLpw + kWarps - 1) / kWarps), block(kThreads);
+    const dim3 grid(p.npad / kEpc), block(kThreads);
     switch (p.d) {
         case 3: env_step_kernel<3, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset); break;
         case 5: env_step_kernel<5, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset); break;

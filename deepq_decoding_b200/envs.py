@@ -232,7 +232,7 @@ class VecSurfaceCodeEnv:
         return text
 
 
-ROW_XB, ROW_ZB, ROW_META, ROW_ACT, ROW_SYN = 0, 1, 2, 3, 6
+ROW_XB, ROW_ZB, ROW_META, ROW_ACT, ROW_SUM, ROW_BM = 0, 1, 2, 3, 6, 7
 
 
 def _grid(word, g, rows, cols):
@@ -241,15 +241,22 @@ def _grid(word, g, rows, cols):
 
 
 def decode_state_column(col, d, vd, layers, error_model, use_Y):
-    g = d + 1
+    """One column of the packed state matrix -> the reference's attributes."""
+    g, H = d + 1, 2 * d + 1
+    pw = (H * H + 63) // 64
     xb, zb = _grid(col[ROW_XB], g, d, d), _grid(col[ROW_ZB], g, d, d)
     hidden = np.where(xb & zb, 2, np.where(xb, 1, np.where(zb, 3, 0)))
     meta = int(col[ROW_META])
     completed = np.zeros(layers * d * d + 1, np.int64)
     for l in range(layers):
         completed[l * d * d:(l + 1) * d * d] = _grid(col[ROW_ACT + l], g, d, d).reshape(-1)
-    faulty = np.stack([_grid(col[ROW_SYN + j], g, g, g) for j in range(vd)])
-    return dict(hidden_state=hidden, completed_actions=completed, faulty_syndromes=faulty,
+    board = np.zeros((vd + layers, H, H), np.int64)            # the cached, rendered observation layers
+    for l in range(vd + layers):
+        big = sum(int(col[ROW_BM + l * pw + i]) << (64 * i) for i in range(pw))
+        board[l] = np.array([(big >> k) & 1 for k in range(H * H)]).reshape(H, H)
+    faulty = board[:vd, ::2, ::2].copy()
+    return dict(hidden_state=hidden, completed_actions=completed, faulty_syndromes=faulty, board_state=board,
+                summed_syndrome_volume=_grid(col[ROW_SUM], g, g, g),
                 lifetime=meta & 0xFFFFFFFF, attempts=(meta >> 32) & 0x7FFFFFFF, done=bool(meta >> 63))
 
 

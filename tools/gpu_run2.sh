@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q --timeout 180 > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
 tail -15 gpurun_out/pytest.log
-for v in default 4x32 4x128 8x64 8x128; do
+for v in default; do
   if [ $v = default ]; then unset DQ_DECODING_LIB; else export DQ_DECODING_LIB=$PWD/deepq_decoding_b200/libdq_variant_$v.so; fi
   timeout 300 python bench.py --steps 8192 --warmup 64 --cpu-seconds 0.5 > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err
   python - <<PY
@@ -14,6 +14,6 @@ except Exception as e:
 PY
 done
 unset DQ_DECODING_LIB
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r1d_launches.csv python bench.py --steps 64 --warmup 16 --cpu-seconds 0.2 > gpurun_out/ncu1.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:env_step_kernel -s 40 -c 3 -o gpurun_out/r1d_env_step python bench.py --steps 64 --warmup 16 --cpu-seconds 0.2 > gpurun_out/ncu2.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r1e_launches.csv python bench.py --steps 64 --warmup 16 --cpu-seconds 0.2 > gpurun_out/ncu1.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:env_step_kernel -s 40 -c 3 -o gpurun_out/r1e_env_step python bench.py --steps 64 --warmup 16 --cpu-seconds 0.2 > gpurun_out/ncu2.log 2>&1
 ls gpurun_out
