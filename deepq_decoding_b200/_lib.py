@@ -14,6 +14,7 @@ MODEL = {"X": 0, "DP": 1}
 REFEREE_JOINT, REFEREE_SPLIT = 0, 1
 (INFO_NUM_ACTIONS, INFO_OBS_CHANNELS, INFO_OBS_SIDE, INFO_MASK_WORDS, INFO_STATE_WORDS,
  INFO_STATE_STRIDE, INFO_NUM_STABS, INFO_N_TYPE3, INFO_N_TYPE1, INFO_RNG_BLOCKS) = range(10)
+QINFO_NUM_PARAMS, QINFO_PACKED_ROWS, QINFO_NUM_TENSORS, QINFO_FLOPS_PER_SAMPLE = range(4)
 
 
 class DQError(RuntimeError):
@@ -21,7 +22,7 @@ class DQError(RuntimeError):
 
 
 _lib = None
-_vp, _i, _i64, _u64, _u32, _dbl = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_double
+_vp, _i, _i64, _u64, _u32, _dbl, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_double, C.c_float
 
 _SIGNATURES = {
     "dq_last_error": (C.c_char_p, []),
@@ -41,6 +42,20 @@ _SIGNATURES = {
     "dq_policy_random_legal": (_i, [_vp, _vp, _u32, _vp, _vp]),
     "dq_policy_seek": (_i, [_vp, _u32, _vp]),
     "dq_policy_random_legal_next": (_i, [_vp, _vp, _vp, _vp]),
+    "dq_env_packed_obs": (_i, [_vp, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
+    "dq_qnet_create": (_i, [C.POINTER(_vp), _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i64, _i]),
+    "dq_qnet_destroy": (_i, [_vp]),
+    "dq_qnet_info": (_i, [_vp, _i, C.POINTER(_i64)]),
+    "dq_qnet_param_layout": (_i, [_vp, _vp, _vp]),
+    "dq_qnet_pack_obs": (_i, [_vp, _vp, _vp, _i64, _i64, _vp]),
+    "dq_qnet_forward": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _i, _u64, _vp]),
+    "dq_qnet_backward": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "dq_qnet_activation": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i64)]),
+    "dq_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i64, _f, _vp]),
+    "dq_dqn_targets": (_i, [_vp, _vp, _vp, _vp, _f, _i64, _i, _vp, _vp]),
+    "dq_dqn_loss_grad": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
+    "dq_policy_eps_greedy": (_i, [_vp, _vp, _i64, _i, _i, _u32, _u64, _u32, _vp, _dbl, _i, _vp, _vp]),
+    "dq_replay_sample": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i64, _i, _i, _i, _i64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -490,10 +490,13 @@ struct dq_env {
     int32_t* s_actions; uint8_t* s_obs; float* s_reward; uint8_t* s_done; int32_t* s_life; u64* s_legal;
 };
 
-static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
+namespace dq {
+thread_local std::string g_err_q;                 // last error message of this thread (shared by all translation units)
+void count_launch() { g_launches.fetch_add(1); }
+}
 
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+static int fail(int code, const std::string& msg) { dq::g_err_q = msg; return code; }
 #define DQ_CUDA(expr)                                                                       \
     do {                                                                                    \
         cudaError_t _e = (expr);                                                            \
@@ -521,7 +524,7 @@ static void set_thresholds(EnvParams& p, double p_phys, double p_meas) {
     p.T1 = p.T / 3; p.T2 = (u32)((2ull * p.T) / 3);
 }
 
-extern "C" const char* dq_last_error(void) { return g_err.c_str(); }
+extern "C" const char* dq_last_error(void) { return dq::g_err_q.c_str(); }
 extern "C" int dq_version(void) { return 100; }
 extern "C" int64_t dq_launch_count(void) { return g_launches.load(); }
 
@@ -704,6 +707,14 @@ extern "C" int dq_env_step_host(dq_env* e, const int32_t* h_actions, uint8_t* h_
                            auto_reset, e->hstream);
     if (rc) return rc;
     return copy_out(e, h_obs, h_reward, h_done, h_life, h_legal);
+}
+
+extern "C" int dq_env_packed_obs(dq_env* e, uint64_t** dev_rows, int64_t* n_rows, int64_t* stride) {
+    if (!e || !dev_rows) return fail(DQ_EINVAL, "NULL argument");
+    *dev_rows = e->p.state + (size_t)ROW_BM * e->p.npad;
+    if (n_rows) *n_rows = e->state_rows - ROW_BM;
+    if (stride) *stride = e->p.npad;
+    return DQ_OK;
 }
 
 extern "C" int dq_env_get_state(dq_env* e, uint64_t* dev_words, dq_stream stream) {

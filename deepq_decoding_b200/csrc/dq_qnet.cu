@@ -1,0 +1,769 @@
+// dq_qnet.cu -- Q-network forward / backward, Keras-Adam, DQN targets + loss, policies, replay ring
+// (sm_100a, fp32 SIMT path; the bf16 tcgen05 path for the dense contractions lives in dq_gemm_tc.cu).
+//
+// Replaces, for N lattices / a batch of B transitions at a time:
+//   build_convolutional_nn + the keras-rl dueling head ... example_notebooks/Function_Library.py:338-377
+//   DQNAgent.forward / backward (double DQN, hard target copy, Adam) ... keras-rl 0.4.x semantics,
+//       call sites cluster_scripts/d5_dp/0.001/Single_Point_Training_Script.py:109-152
+//   EpsGreedyQPolicy / GreedyQPolicy with legal-action masking ... same script :110-115, 166-167
+//   SequentialMemory(limit, window_length=1) ... same script :109
+//
+// Data layout.  Observations never exist as bytes on this path: a network input is the PACKED
+// observation, one (2d+1)^2-cell bitmap per layer in PW uint64 words, stored row-major as
+// [layer*PW + word][sample] -- exactly rows ROW_BM.. of the environment's state matrix, so acting reads
+// the env state in place.  Activations are fp32, channels-last ([sample][position][channel]); every
+// layer after the first is then a GEMM whose A rows are gathered patches (implicit im2col), and the
+// first layer, whose input is binary, is a sparse sum of weight rows over the set taps.
+// Parameters / gradients / Adam moments are caller-owned flat fp32 buffers (layout: dq_qnet_param_layout).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+#include <math.h>
+#include <atomic>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/dq_decoding.h"
+#include "dq_lattice.cuh"
+
+namespace dq {
+
+extern thread_local std::string g_err_q;
+void count_launch();
+
+constexpr int kMaxConv = 4, kMaxDense = 4;
+
+struct ConvL { int cin, ih, oh, ksz, stride, filters, K, P; };     // square maps; K = ksz*ksz*cin; P = oh*oh
+struct QCfg {
+    int C, H, PW, rows;                 // input layers, side, words per layer, packed rows = C*PW
+    int n_conv; ConvL conv[kMaxConv];
+    int n_fc;   int fc_in[kMaxDense + 2], fc_out[kMaxDense + 2]; float drop[kMaxDense + 2];
+    int A, dueling, n_hidden;
+    long long w_off[kMaxConv + kMaxDense + 2], b_off[kMaxConv + kMaxDense + 2];   // offsets in the flat buffer
+    long long n_params;
+};
+
+// ------------------------------------------------------------------------------------------------ layer 1
+// conv on binary input: out[b][pos][co] = relu(bias[co] + sum over set taps k of W[k][co]),
+// k = (ky*ksz + kx)*C + ci  (Keras HWIO flattened).  One warp per (sample, position); lane = output channel(s).
+__device__ __forceinline__ u32 layer_taps(const u64* __restrict__ packed, long long stride, long long b, int ci, int PW,
+                                          int H, int y0, int x0, int ksz) {
+    // ksz x ksz window of layer ci at (y0, x0) as a bit mask, tap t = ky*ksz + kx
+    u32 taps = 0;
+    for (int ky = 0; ky < ksz; ++ky) {
+        const int bit = (y0 + ky) * H + x0, w = bit >> 6, s = bit & 63;
+        u64 v = packed[(long long)(ci * PW + w) * stride + b] >> s;
+        if (s + ksz > 64 && w + 1 < PW) v |= packed[(long long)(ci * PW + w + 1) * stride + b] << (64 - s);
+        taps |= (u32)(v & ((1u << ksz) - 1)) << (ky * ksz);
+    }
+    return taps;
+}
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(256)
+conv1_bits_kernel(const u64* __restrict__ packed, long long stride, long long batch, ConvL L, int C, int PW, int H,
+                  const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ out,
+                  const float* __restrict__ dY, float* __restrict__ dW) {
+    extern __shared__ float sW[];                      // forward: W [K][F]; backward: dW accumulator [K][F]
+    const int F = L.filters, K = L.K;
+    for (int i = threadIdx.x; i < K * F; i += blockDim.x) sW[i] = BACKWARD ? 0.f : W[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const long long total = batch * L.P;
+    for (long long job = (long long)blockIdx.x * nwarp + warp; job < total; job += (long long)gridDim.x * nwarp) {
+        const long long b = job / L.P;
+        const int pos = (int)(job - b * L.P), oy = pos / L.oh, ox = pos - oy * L.oh;
+        u32 taps = 0;
+        if (lane < C) taps = layer_taps(packed, stride, b, lane, PW, H, oy * L.stride, ox * L.stride, L.ksz);
+        if (!BACKWARD) {
+            float acc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = (lane + 32 * j < F) ? bias[lane + 32 * j] : 0.f;
+            for (int ci = 0; ci < C; ++ci) {
+                u32 m = __shfl_sync(0xffffffffu, taps, ci);
+                while (m) {
+                    const int t = __ffs(m) - 1; m &= m - 1;
+                    const float* wr = sW + (t * C + ci) * F;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (lane + 32 * j < F) acc[j] += wr[lane + 32 * j];
+                }
+            }
+            float* o = out + job * F;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (lane + 32 * j < F) o[lane + 32 * j] = fmaxf(acc[j], 0.f);
+        } else {
+            float g[4];
+            const float* gy = dY + job * F;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) g[j] = (lane + 32 * j < F) ? gy[lane + 32 * j] : 0.f;
+            for (int ci = 0; ci < C; ++ci) {
+                u32 m = __shfl_sync(0xffffffffu, taps, ci);
+                while (m) {
+                    const int t = __ffs(m) - 1; m &= m - 1;
+                    float* wr = sW + (t * C + ci) * F;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (lane + 32 * j < F && g[j] != 0.f) atomicAdd(wr + lane + 32 * j, g[j]);
+                }
+            }
+        }
+    }
+    if (BACKWARD) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < K * F; i += blockDim.x) if (sW[i] != 0.f) atomicAdd(dW + i, sW[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ patch GEMMs
+// A "patch matrix" A[m][k]: m = (sample, oy, ox), k = (ky, kx, c) over a channels-last input [B][ih][ih][cin].
+// Dense layers are the degenerate case ih = oh = ksz = 1, cin = K.
+struct Patch { int P, oh, ih, cin, ksz, stride; };
+__device__ __forceinline__ long long patch_row(const Patch& g, long long m) {
+    const long long b = m / g.P;
+    const int pos = (int)(m - b * g.P), oy = pos / g.oh, ox = pos - oy * g.oh;
+    return ((b * g.ih + oy * g.stride) * g.ih + ox * g.stride) * (long long)g.cin;
+}
+__device__ __forceinline__ int patch_col(const Patch& g, int k) {
+    const int seg = k / g.cin, c = k - seg * g.cin, ky = seg / g.ksz, kx = seg - ky * g.ksz;
+    return (ky * g.ih + kx) * g.cin + c;
+}
+
+constexpr int TB = 64, TK = 16;        // 64x64 output tile, 16-deep steps, 256 threads, 4x4 per thread
+
+// Y[m][n] = act(sum_k A[m][k] W[k][n] + bias[n]);  act: 0 linear, 1 ReLU
+__global__ void __launch_bounds__(256)
+gemm_fwd_kernel(const float* __restrict__ X, Patch g, const float* __restrict__ W, const float* __restrict__ bias,
+                float* __restrict__ Y, long long M, int N, int K, int act) {
+    __shared__ float As[TK][TB + 4], Bs[TK][TB + 4];
+    __shared__ long long rowoff[TB];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const long long m0 = (long long)blockIdx.x * TB;
+    const int n0 = blockIdx.y * TB;
+    if (tid < TB) rowoff[tid] = (m0 + tid < M) ? patch_row(g, m0 + tid) : -1;
+    __syncthreads();
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += TK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                  // A tile: 64 rows x 16 k
+            const int e = tid + i * 256, r = e >> 4, kk = e & 15, k = k0 + kk;
+            float v = 0.f;
+            if (k < K && rowoff[r] >= 0) v = X[rowoff[r] + patch_col(g, k)];
+            As[kk][r] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                  // W tile: 16 k x 64 n
+            const int e = tid + i * 256, kk = e >> 6, c = e & 63, k = k0 + kk, n = n0 + c;
+            Bs[kk][c] = (k < K && n < N) ? W[(long long)k * N + n] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < TK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j] + (bias ? bias[n] : 0.f);
+            if (act == 1) v = fmaxf(v, 0.f);
+            Y[m * N + n] = v;
+        }
+    }
+}
+
+// dW[k][n] += sum_m A[m][k] dY[m][n]   over this CTA's slice of m (grid.z), atomically
+__global__ void __launch_bounds__(256)
+gemm_dw_kernel(const float* __restrict__ X, Patch g, const float* __restrict__ dY, float* __restrict__ dW,
+               long long M, int N, int K, long long m_chunk) {
+    __shared__ float As[TK][TB + 4], Bs[TK][TB + 4];
+    __shared__ int coloff[TB];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int k0 = blockIdx.x * TB, n0 = blockIdx.y * TB;
+    const long long mb = (long long)blockIdx.z * m_chunk, me = min(M, mb + m_chunk);
+    if (tid < TB) coloff[tid] = (k0 + tid < K) ? patch_col(g, k0 + tid) : -1;
+    __syncthreads();
+    float acc[4][4] = {};
+    for (long long ms = mb; ms < me; ms += TK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                  // A^T tile: 16 m x 64 k
+            const int e = tid + i * 256, mm = e >> 6, c = e & 63;
+            const long long m = ms + mm;
+            float v = 0.f;
+            if (m < me && coloff[c] >= 0) v = X[patch_row(g, m) + coloff[c]];
+            As[mm][c] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                  // dY tile: 16 m x 64 n
+            const int e = tid + i * 256, mm = e >> 6, c = e & 63;
+            const long long m = ms + mm;
+            Bs[mm][c] = (m < me && n0 + c < N) ? dY[m * N + n0 + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int mm = 0; mm < TK; ++mm) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[mm][ty * 4 + i]; b[i] = Bs[mm][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = k0 + ty * 4 + i;
+        if (k >= K) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < N && acc[i][j] != 0.f) atomicAdd(dW + (long long)k * N + n, acc[i][j]);
+        }
+    }
+}
+
+// dX[patch(m,k)] (+)= sum_n dY[m][n] W[k][n];  overlapping patches (conv) accumulate atomically into a zeroed dX
+__global__ void __launch_bounds__(256)
+gemm_dx_kernel(const float* __restrict__ dY, const float* __restrict__ W, float* __restrict__ dX, Patch g,
+               long long M, int N, int K, int overlap) {
+    __shared__ float As[TK][TB + 4], Bs[TK][TB + 4];
+    __shared__ long long rowoff[TB];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const long long m0 = (long long)blockIdx.x * TB;
+    const int k0 = blockIdx.y * TB;
+    if (tid < TB) rowoff[tid] = (m0 + tid < M) ? patch_row(g, m0 + tid) : -1;
+    __syncthreads();
+    float acc[4][4] = {};
+    for (int ns = 0; ns < N; ns += TK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                  // dY tile: 64 m x 16 n
+            const int e = tid + i * 256, r = e >> 4, nn = e & 15;
+            As[nn][r] = (m0 + r < M && ns + nn < N) ? dY[(m0 + r) * N + ns + nn] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                  // W^T tile: 16 n x 64 k
+            const int e = tid + i * 256, c = e >> 4, nn = e & 15;
+            Bs[nn][c] = (k0 + c < K && ns + nn < N) ? W[(long long)(k0 + c) * N + ns + nn] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int nn = 0; nn < TK; ++nn) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[nn][ty * 4 + i]; b[i] = Bs[nn][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = ty * 4 + i;
+        if (rowoff[r] < 0) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + tx * 4 + j;
+            if (k >= K) continue;
+            float* dst = dX + rowoff[r] + patch_col(g, k);
+            if (overlap) atomicAdd(dst, acc[i][j]); else *dst = acc[i][j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise
+// dY *= (Y > 0) [* mask];  Y is the layer's post-activation output
+__global__ void relu_bwd_kernel(float* __restrict__ dY, const float* __restrict__ Y, const float* __restrict__ mask, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float g = (Y[i] > 0.f) ? dY[i] : 0.f;
+        if (mask) g *= mask[i];
+        dY[i] = g;
+    }
+}
+// training-mode dropout after a ReLU layer: mask = keep ? 1/(1-rate) : 0 (Keras inverted dropout); Y *= mask
+__global__ void dropout_kernel(float* __restrict__ Y, float* __restrict__ mask, long long n, float rate, u32 k0, u32 k1, u32 tag) {
+    const u32 thr = (u32)fminf(rate * 4294967296.f, 4294967295.f);
+    const float scale = 1.f / (1.f - rate);
+    for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 * 4 < n; i4 += (long long)gridDim.x * blockDim.x) {
+        const Philox4 u = philox4x32_10((u32)i4, (u32)(i4 >> 32), tag, 3u, k0, k1);      // domain 3: dropout
+        const u32 uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long i = i4 * 4 + j;
+            if (i < n) { const float mk = (uu[j] >= thr) ? scale : 0.f; mask[i] = mk; Y[i] *= mk; }
+        }
+    }
+}
+__global__ void colsum_kernel(const float* __restrict__ dY, float* __restrict__ db, long long M, int N) {
+    // grid.x covers columns in blocks of 32; each block reduces a slice of rows (grid.y) and adds atomically
+    __shared__ float part[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
+    float s = 0.f;
+    if (c < N)
+        for (long long m = (long long)blockIdx.y * 8 + w; m < M; m += (long long)gridDim.y * 8) s += dY[m * N + c];
+    part[w][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (w == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+        if (c < N && t != 0.f) atomicAdd(db + c, t);
+    }
+}
+// dueling head (dueling_type='avg'): Q[b][a] = y[b][0] + y[b][1+a] - mean_a y[b][1+a]
+__global__ void dueling_fwd_kernel(const float* __restrict__ y, float* __restrict__ q, long long B, int A) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float* r = y + b * (A + 1);
+    float s = 0.f;
+    for (int a = 0; a < A; ++a) s += r[1 + a];
+    const float base = r[0] - s / (float)A;
+    for (int a = 0; a < A; ++a) q[b * A + a] = base + r[1 + a];
+}
+__global__ void dueling_bwd_kernel(const float* __restrict__ dq, float* __restrict__ dy, long long B, int A) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float s = 0.f;
+    for (int a = 0; a < A; ++a) s += dq[b * A + a];
+    dy[b * (A + 1)] = s;
+    for (int a = 0; a < A; ++a) dy[b * (A + 1) + 1 + a] = dq[b * A + a] - s / (float)A;
+}
+// Keras-2 Adam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v EMA; p -= lr_t*m/(sqrt(v)+eps).  g is scaled by gscale first
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
+                            long long n, float lr_t, float b1, float b2, float eps, float gscale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i] * gscale;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+// double-DQN target: y = r + gamma*(1-terminal)*Qt[argmax_a Qo[a]]   (ties -> lowest index)
+__global__ void dqn_target_kernel(const float* __restrict__ qo, const float* __restrict__ qt, const float* __restrict__ r,
+                                  const uint8_t* __restrict__ term, float gamma, long long B, int A, float* __restrict__ y) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int best = 0; float bv = qo[b * A];
+    for (int a = 1; a < A; ++a) { const float v = qo[b * A + a]; if (v > bv) { bv = v; best = a; } }
+    y[b] = r[b] + (term[b] ? 0.f : gamma * qt[b * A + best]);
+}
+// loss = mean_b 0.5*(y - Q[b][a_b])^2;  dQ = d loss / dQ;  stats += {sum of 0.5*err^2, sum of max_a Q}
+__global__ void dqn_loss_grad_kernel(const float* __restrict__ q, const int32_t* __restrict__ act, const float* __restrict__ y,
+                                     long long B, int A, float* __restrict__ dq, float* __restrict__ stats) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float l = 0.f, mq = 0.f;
+    if (b < B) {
+        const int a = act[b];
+        float mx = q[b * A];
+        for (int j = 0; j < A; ++j) { dq[b * A + j] = 0.f; mx = fmaxf(mx, q[b * A + j]); }
+        const float err = q[b * A + a] - y[b];
+        dq[b * A + a] = err / (float)B;
+        l = 0.5f * err * err; mq = mx;
+    }
+    for (int o = 16; o; o >>= 1) { l += __shfl_xor_sync(0xffffffffu, l, o); mq += __shfl_xor_sync(0xffffffffu, mq, o); }
+    if ((threadIdx.x & 31) == 0 && stats) { atomicAdd(stats, l); atomicAdd(stats + 1, mq); }
+}
+// eps-greedy over legal actions (EpsGreedyQPolicy: with probability eps uniform over env.legal_actions, else argmax
+// over all actions, or over the legal ones when masked_greedy).  eps = 0 + masked_greedy is GreedyQPolicy(masked).
+// Draws: Philox(stream id, step, 0, domain 1): word 0 -> the uniform pick (same as dq_policy_random_legal),
+// word 1 -> the eps test (u < floor(eps*2^32)).
+__global__ void eps_greedy_kernel(const float* __restrict__ q, const u64* __restrict__ legal, int n, int W, int A, u32 env_id_base,
+                                  u32 step, u32* __restrict__ ctr, u32 k0, u32 k1, u32 eps_thr, int masked_greedy,
+                                  int32_t* __restrict__ actions) {
+    __shared__ u32 s_step;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ctr) {
+        if (threadIdx.x == 0) s_step = *reinterpret_cast<volatile u32*>(ctr);
+        __syncthreads();
+        step = s_step;
+    }
+    if (e < n) {
+        u64 m[3] = {0, 0, 0};
+        int cnt = 0;
+        for (int i = 0; i < W; ++i) { m[i] = legal[(size_t)e * W + i]; cnt += popc64(m[i]); }
+        const Philox4 u = philox4x32_10(env_id_base + (u32)e, step, 0u, 1u, k0, k1);
+        int act = A - 1;
+        if (u.y < eps_thr) {
+            int pick = (int)mulhi32(u.x, (u32)cnt);
+            for (int i = 0; i < W; ++i) {
+                const int c = popc64(m[i]);
+                if (pick < c) { act = i * 64 + select64(m[i], pick); break; }
+                pick -= c;
+            }
+        } else {
+            float bv = -INFINITY; int best = -1;
+            for (int a = 0; a < A; ++a) {
+                if (masked_greedy && !((m[a >> 6] >> (a & 63)) & 1)) continue;
+                const float v = q[(size_t)e * A + a];
+                if (best < 0 || v > bv) { bv = v; best = a; }
+            }
+            act = best < 0 ? A - 1 : best;
+        }
+        actions[e] = act;
+    }
+    if (ctr && threadIdx.x == 0 && atomicAdd(ctr + 1, 1u) == gridDim.x - 1) { ctr[1] = 0; atomicAdd(ctr, 1u); }
+}
+// bytes [B][C][H][H] -> packed [C*PW][stride]
+__global__ void pack_obs_kernel(const uint8_t* __restrict__ obs, u64* __restrict__ packed, long long stride, long long B,
+                                int C, int PW, int cells) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // one thread per (row, sample)
+    if (t >= B * C * PW) return;
+    const long long b = t % B; const int row = (int)(t / B), layer = row / PW, w = row - layer * PW;
+    const uint8_t* src = obs + (b * C + layer) * cells;
+    u64 v = 0;
+    for (int i = 0; i < 64; ++i) { const int c = w * 64 + i; if (c < cells && src[c]) v |= 1ull << i; }
+    packed[(long long)row * stride + b] = v;
+}
+// replay sample: uniform (slot, lattice) pairs -> packed s / s' batches + action, reward, terminal
+__global__ void replay_sample_kernel(const u64* __restrict__ ring_obs, const int32_t* __restrict__ ring_act,
+                                     const float* __restrict__ ring_rew, const uint8_t* __restrict__ ring_term,
+                                     int rows, long long npad, int n, int cap, int head, int filled, long long batch,
+                                     u32 k0, u32 k1, u32 draw, u64* __restrict__ s0, u64* __restrict__ s1,
+                                     int32_t* __restrict__ act, float* __restrict__ rew, uint8_t* __restrict__ term,
+                                     int32_t* __restrict__ picked) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    // transitions live in the `filled` most recent completed slots; slot `head` is the one being written next
+    const Philox4 u = philox4x32_10((u32)b, (u32)(b >> 32), draw, 2u, k0, k1);                  // domain 2: replay
+    const int age = (int)mulhi32(u.x, (u32)filled);                // 0 = most recent completed transition
+    const int i = (int)mulhi32(u.y, (u32)n);
+    const int t = (head - 1 - age + 2 * cap) % cap, t1 = (t + 1) % cap;
+    for (int r = 0; r < rows; ++r) {
+        s0[(long long)r * batch + b] = ring_obs[((long long)t * rows + r) * npad + i];
+        s1[(long long)r * batch + b] = ring_obs[((long long)t1 * rows + r) * npad + i];
+    }
+    act[b] = ring_act[(long long)t * n + i];
+    rew[b] = ring_rew[(long long)t * n + i];
+    term[b] = ring_term[(long long)t * n + i];
+    if (picked) { picked[2 * b] = t; picked[2 * b + 1] = i; }
+}
+
+}  // namespace dq
+
+// ================================================================================================ host / C ABI
+using namespace dq;
+
+static int qfail(int code, const std::string& msg) { dq::g_err_q = msg; return code; }
+#define QCUDA(expr)                                                                          \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) return qfail(DQ_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+struct dq_qnet {
+    QCfg c;
+    int device;
+    long long max_batch;
+    // activations (fp32, channels-last) of the last forward; gradient scratch of the same shapes
+    float* act_conv[kMaxConv]; float* dact_conv[kMaxConv];
+    float* act_fc[kMaxDense + 2]; float* dact_fc[kMaxDense + 2]; float* mask_fc[kMaxDense + 2];
+    u64* pack_scratch;
+    int last_train;
+};
+
+static int grid_for(long long n, int block, int cap = 148 * 16) {
+    long long g = (n + block - 1) / block;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+extern "C" int dq_qnet_create(dq_qnet** out, int in_channels, int in_side, int n_conv, const int* filters, const int* kernels,
+                              const int* strides, int n_dense, const int* units, const float* dropout, int num_actions,
+                              int dueling, int64_t max_batch, int device) {
+    if (!out) return qfail(DQ_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (n_conv < 1 || n_conv > kMaxConv || n_dense < 0 || n_dense > kMaxDense) return qfail(DQ_EINVAL, "1..4 conv layers and 0..4 hidden dense layers are supported");
+    if (in_channels < 1 || in_channels > 32 || in_side < 3 || in_side > 15) return qfail(DQ_EINVAL, "input must be [<=32][<=15][<=15]");
+    if (num_actions < 2 || max_batch < 1) return qfail(DQ_EINVAL, "bad num_actions / max_batch");
+    int ndev = 0;
+    QCUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return qfail(DQ_EINVAL, "no such CUDA device");
+    int prev = 0; cudaGetDevice(&prev); cudaSetDevice(device);
+    dq_qnet* h = new dq_qnet();
+    memset(h, 0, sizeof(*h));
+    QCfg& c = h->c;
+    c.C = in_channels; c.H = in_side; c.PW = (in_side * in_side + 63) / 64; c.rows = c.C * c.PW;
+    c.n_conv = n_conv; c.A = num_actions; c.dueling = dueling ? 1 : 0; c.n_hidden = n_dense;
+    int cin = in_channels, side = in_side;
+    long long off = 0;
+    int t = 0;
+    for (int l = 0; l < n_conv; ++l) {
+        ConvL& L = c.conv[l];
+        L.cin = cin; L.ih = side; L.ksz = kernels[l]; L.stride = strides[l]; L.filters = filters[l];
+        if (L.ksz < 1 || L.ksz > 4 || L.stride < 1 || L.ksz > side || L.filters < 1 || L.filters > 128) { delete h; cudaSetDevice(prev); return qfail(DQ_EINVAL, "unsupported conv layer"); }
+        L.oh = (side - L.ksz) / L.stride + 1; L.K = L.ksz * L.ksz * cin; L.P = L.oh * L.oh;
+        c.w_off[t] = off; off += (long long)L.K * L.filters; c.b_off[t] = off; off += L.filters; ++t;
+        cin = L.filters; side = L.oh;
+    }
+    int fin = cin * side * side;
+    c.n_fc = n_dense + 1 + (dueling ? 1 : 0);
+    for (int i = 0; i < c.n_fc; ++i) {
+        const int fo = i < n_dense ? units[i] : (i == n_dense ? num_actions : num_actions + 1);
+        c.fc_in[i] = fin; c.fc_out[i] = fo; c.drop[i] = (i < n_dense && dropout) ? dropout[i] : 0.f;
+        c.w_off[t] = off; off += (long long)fin * fo; c.b_off[t] = off; off += fo; ++t;
+        fin = fo;
+    }
+    c.n_params = off;
+    h->device = device; h->max_batch = max_batch;
+    cudaError_t err = cudaSuccess;
+    auto alloc = [&](float** p, long long n) { if (err == cudaSuccess) err = cudaMalloc(p, (size_t)n * sizeof(float)); };
+    for (int l = 0; l < n_conv; ++l) {
+        const long long n = max_batch * c.conv[l].P * c.conv[l].filters;
+        alloc(&h->act_conv[l], n); alloc(&h->dact_conv[l], n);
+    }
+    for (int i = 0; i < c.n_fc; ++i) {
+        const long long n = max_batch * c.fc_out[i];
+        alloc(&h->act_fc[i], n); alloc(&h->dact_fc[i], n);
+        if (c.drop[i] > 0.f) alloc(&h->mask_fc[i], n);
+    }
+    if (err == cudaSuccess) err = cudaMalloc(&h->pack_scratch, (size_t)c.rows * max_batch * 8);
+    cudaSetDevice(prev);
+    if (err != cudaSuccess) { return qfail(DQ_ECUDA, std::string("cudaMalloc(activations): ") + cudaGetErrorString(err)); }
+    *out = h;
+    return DQ_OK;
+}
+
+extern "C" int dq_qnet_destroy(dq_qnet* h) {
+    if (!h) return DQ_OK;
+    int prev = 0; cudaGetDevice(&prev); cudaSetDevice(h->device);
+    for (int l = 0; l < kMaxConv; ++l) { cudaFree(h->act_conv[l]); cudaFree(h->dact_conv[l]); }
+    for (int i = 0; i < kMaxDense + 2; ++i) { cudaFree(h->act_fc[i]); cudaFree(h->dact_fc[i]); cudaFree(h->mask_fc[i]); }
+    cudaFree(h->pack_scratch);
+    cudaSetDevice(prev);
+    delete h;
+    return DQ_OK;
+}
+
+extern "C" int dq_qnet_info(const dq_qnet* h, int what, int64_t* out) {
+    if (!h || !out) return qfail(DQ_EINVAL, "NULL argument");
+    switch (what) {
+        case DQ_QINFO_NUM_PARAMS: *out = h->c.n_params; break;
+        case DQ_QINFO_PACKED_ROWS: *out = h->c.rows; break;
+        case DQ_QINFO_NUM_TENSORS: *out = 2 * (h->c.n_conv + h->c.n_fc); break;
+        case DQ_QINFO_FLOPS_PER_SAMPLE: {
+            long long f = 0;
+            for (int l = 0; l < h->c.n_conv; ++l) f += 2ll * h->c.conv[l].K * h->c.conv[l].filters * h->c.conv[l].P;
+            for (int i = 0; i < h->c.n_fc; ++i) f += 2ll * h->c.fc_in[i] * h->c.fc_out[i];
+            *out = f; break;
+        }
+        default: return qfail(DQ_EINVAL, "unknown info selector");
+    }
+    return DQ_OK;
+}
+
+// offsets[2*t] = kernel offset, offsets[2*t+1] = bias offset of tensor pair t (conv layers first, then dense);
+// shapes[2*t], shapes[2*t+1] = (rows K, cols N) of the kernel.  Conv kernels are Keras HWIO flattened to [K][N];
+// the first dense kernel's rows are in (position, channel) order (see qnet.py for the permutation from Keras' C,H,W).
+extern "C" int dq_qnet_param_layout(const dq_qnet* h, int64_t* offsets, int64_t* shapes) {
+    if (!h || !offsets || !shapes) return qfail(DQ_EINVAL, "NULL argument");
+    const QCfg& c = h->c;
+    int t = 0;
+    for (int l = 0; l < c.n_conv; ++l, ++t) { offsets[2 * t] = c.w_off[t]; offsets[2 * t + 1] = c.b_off[t]; shapes[2 * t] = c.conv[l].K; shapes[2 * t + 1] = c.conv[l].filters; }
+    for (int i = 0; i < c.n_fc; ++i, ++t) { offsets[2 * t] = c.w_off[t]; offsets[2 * t + 1] = c.b_off[t]; shapes[2 * t] = c.fc_in[i]; shapes[2 * t + 1] = c.fc_out[i]; }
+    return DQ_OK;
+}
+
+extern "C" int dq_qnet_pack_obs(dq_qnet* h, const uint8_t* obs, uint64_t* packed, int64_t stride, int64_t batch, dq_stream stream) {
+    if (!h || !obs || !packed || batch < 1 || stride < batch) return qfail(DQ_EINVAL, "bad argument");
+    const QCfg& c = h->c;
+    const long long n = batch * c.rows;
+    pack_obs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(obs, (u64*)packed, stride, batch, c.C, c.PW, c.H * c.H);
+    count_launch();
+    QCUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+static Patch conv_patch(const ConvL& L) { Patch g; g.P = L.P; g.oh = L.oh; g.ih = L.ih; g.cin = L.cin; g.ksz = L.ksz; g.stride = L.stride; return g; }
+static Patch dense_patch(int K) { Patch g; g.P = 1; g.oh = 1; g.ih = 1; g.cin = K; g.ksz = 1; g.stride = 1; return g; }
+
+extern "C" int dq_qnet_forward(dq_qnet* h, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
+                               float* q_out, int train, uint64_t dropout_seed, dq_stream stream) {
+    if (!h || !params || !packed || !q_out) return qfail(DQ_EINVAL, "NULL argument");
+    if (batch < 1 || batch > h->max_batch) return qfail(DQ_EINVAL, "batch exceeds max_batch of the handle");
+    const QCfg& c = h->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    int t = 0;
+    {   // layer 1 on packed bits
+        const ConvL& L = c.conv[0];
+        const size_t smem = (size_t)L.K * L.filters * sizeof(float);
+        if (smem > 48 * 1024) QCUDA(cudaFuncSetAttribute(conv1_bits_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = grid_for(batch * L.P, 8, 148 * 8);
+        conv1_bits_kernel<false><<<grid, 256, smem, st>>>((const u64*)packed, stride, batch, L, c.C, c.PW, c.H,
+                                                           params + c.w_off[0], params + c.b_off[0], h->act_conv[0], nullptr, nullptr);
+        count_launch(); ++t;
+    }
+    const float* x = h->act_conv[0];
+    for (int l = 1; l < c.n_conv; ++l, ++t) {
+        const ConvL& L = c.conv[l];
+        const long long M = batch * L.P;
+        dim3 grid((unsigned)((M + TB - 1) / TB), (L.filters + TB - 1) / TB);
+        gemm_fwd_kernel<<<grid, 256, 0, st>>>(x, conv_patch(L), params + c.w_off[t], params + c.b_off[t], h->act_conv[l], M, L.filters, L.K, 1);
+        count_launch();
+        x = h->act_conv[l];
+    }
+    for (int i = 0; i < c.n_fc; ++i, ++t) {
+        const int K = c.fc_in[i], N = c.fc_out[i];
+        dim3 grid((unsigned)((batch + TB - 1) / TB), (N + TB - 1) / TB);
+        gemm_fwd_kernel<<<grid, 256, 0, st>>>(x, dense_patch(K), params + c.w_off[t], params + c.b_off[t], h->act_fc[i], batch, N, K, i < c.n_hidden ? 1 : 0);
+        count_launch();
+        if (train && c.drop[i] > 0.f) {
+            const long long n = batch * N;
+            dropout_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(h->act_fc[i], h->mask_fc[i], n, c.drop[i], (u32)dropout_seed, (u32)(dropout_seed >> 32), (u32)i);
+            count_launch();
+        }
+        x = h->act_fc[i];
+    }
+    if (c.dueling) {
+        dueling_fwd_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(x, q_out, batch, c.A);
+        count_launch();
+    } else {
+        QCUDA(cudaMemcpyAsync(q_out, x, (size_t)batch * c.A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    h->last_train = train;
+    QCUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+// Gradients of sum_b sum_a dq[b][a]*Q[b][a] w.r.t. every parameter, for the batch of the LAST dq_qnet_forward call
+// (same packed input, train flag honoured: dropout masks are reused).  grads (flat, n_params) is overwritten.
+extern "C" int dq_qnet_backward(dq_qnet* h, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
+                                const float* dq, float* grads, dq_stream stream) {
+    if (!h || !params || !packed || !dq || !grads) return qfail(DQ_EINVAL, "NULL argument");
+    if (batch < 1 || batch > h->max_batch) return qfail(DQ_EINVAL, "batch exceeds max_batch of the handle");
+    const QCfg& c = h->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    QCUDA(cudaMemsetAsync(grads, 0, (size_t)c.n_params * sizeof(float), st));
+    const int nt = c.n_conv + c.n_fc;
+    // head
+    float* dy = h->dact_fc[c.n_fc - 1];
+    if (c.dueling) { dueling_bwd_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(dq, dy, batch, c.A); count_launch(); }
+    else QCUDA(cudaMemcpyAsync(dy, dq, (size_t)batch * c.A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // dense stack, last to first
+    for (int i = c.n_fc - 1; i >= 0; --i) {
+        const int t = c.n_conv + i, K = c.fc_in[i], N = c.fc_out[i];
+        float* dY = h->dact_fc[i];
+        if (i < c.n_hidden) {       // ReLU (+ dropout) layer: mask the incoming gradient
+            const long long n = batch * N;
+            relu_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(dY, h->act_fc[i], (h->last_train && c.drop[i] > 0.f) ? h->mask_fc[i] : nullptr, n);
+            count_launch();
+        }
+        const float* xin = i > 0 ? h->act_fc[i - 1] : h->act_conv[c.n_conv - 1];
+        float* dxin = i > 0 ? h->dact_fc[i - 1] : h->dact_conv[c.n_conv - 1];
+        const long long chunk = 1024;
+        dim3 gw((K + TB - 1) / TB, (N + TB - 1) / TB, (unsigned)((batch + chunk - 1) / chunk));
+        gemm_dw_kernel<<<gw, 256, 0, st>>>(xin, dense_patch(K), dY, grads + c.w_off[t], batch, N, K, chunk);
+        colsum_kernel<<<dim3((N + 31) / 32, (unsigned)std::min<long long>(64, (batch + 7) / 8)), 256, 0, st>>>(dY, grads + c.b_off[t], batch, N);
+        dim3 gx((unsigned)((batch + TB - 1) / TB), (K + TB - 1) / TB);
+        gemm_dx_kernel<<<gx, 256, 0, st>>>(dY, params + c.w_off[t], dxin, dense_patch(K), batch, N, K, 0);
+        count_launch(); count_launch(); count_launch();
+    }
+    // conv stack, last to second
+    for (int l = c.n_conv - 1; l >= 1; --l) {
+        const ConvL& L = c.conv[l];
+        const long long M = batch * L.P, n = M * L.filters;
+        float* dY = h->dact_conv[l];
+        relu_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(dY, h->act_conv[l], nullptr, n);
+        const long long chunk = 4096;
+        dim3 gw((L.K + TB - 1) / TB, (L.filters + TB - 1) / TB, (unsigned)((M + chunk - 1) / chunk));
+        gemm_dw_kernel<<<gw, 256, 0, st>>>(h->act_conv[l - 1], conv_patch(L), dY, grads + c.w_off[l], M, L.filters, L.K, chunk);
+        colsum_kernel<<<dim3((L.filters + 31) / 32, (unsigned)std::min<long long>(64, (M + 7) / 8)), 256, 0, st>>>(dY, grads + c.b_off[l], M, L.filters);
+        const ConvL& Lp = c.conv[l - 1];
+        QCUDA(cudaMemsetAsync(h->dact_conv[l - 1], 0, (size_t)batch * Lp.P * Lp.filters * sizeof(float), st));
+        dim3 gx((unsigned)((M + TB - 1) / TB), (L.K + TB - 1) / TB);
+        gemm_dx_kernel<<<gx, 256, 0, st>>>(dY, params + c.w_off[l], h->dact_conv[l - 1], conv_patch(L), M, L.filters, L.K, 1);
+        count_launch(); count_launch(); count_launch(); count_launch();
+    }
+    {   // layer 1
+        const ConvL& L = c.conv[0];
+        const long long M = batch * L.P, n = M * L.filters;
+        float* dY = h->dact_conv[0];
+        relu_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(dY, h->act_conv[0], nullptr, n);
+        colsum_kernel<<<dim3((L.filters + 31) / 32, (unsigned)std::min<long long>(64, (M + 7) / 8)), 256, 0, st>>>(dY, grads + c.b_off[0], M, L.filters);
+        const size_t smem = (size_t)L.K * L.filters * sizeof(float);
+        if (smem > 48 * 1024) QCUDA(cudaFuncSetAttribute(conv1_bits_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv1_bits_kernel<true><<<grid_for(M, 8, 148 * 4), 256, smem, st>>>((const u64*)packed, stride, batch, L, c.C, c.PW, c.H,
+                                                                           nullptr, nullptr, nullptr, dY, grads + c.w_off[0]);
+        count_launch(); count_launch(); count_launch();
+    }
+    (void)nt;
+    QCUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+extern "C" int dq_qnet_activation(dq_qnet* h, int index, float** dev_ptr, int64_t* per_sample) {
+    if (!h || !dev_ptr) return qfail(DQ_EINVAL, "NULL argument");
+    const QCfg& c = h->c;
+    if (index < 0 || index >= c.n_conv + c.n_fc) return qfail(DQ_EINVAL, "no such layer");
+    if (index < c.n_conv) { *dev_ptr = h->act_conv[index]; if (per_sample) *per_sample = (int64_t)c.conv[index].P * c.conv[index].filters; }
+    else { *dev_ptr = h->act_fc[index - c.n_conv]; if (per_sample) *per_sample = c.fc_out[index - c.n_conv]; }
+    return DQ_OK;
+}
+
+extern "C" int dq_adam_step(float* params, float* m, float* v, const float* grads, int64_t n, float lr, float beta1, float beta2,
+                            float eps, int64_t t, float grad_scale, dq_stream stream) {
+    if (!params || !m || !v || !grads || n < 1 || t < 1) return qfail(DQ_EINVAL, "bad argument");
+    const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t));
+    adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, m, v, grads, n, (float)lr_t, beta1, beta2, eps, grad_scale);
+    count_launch();
+    QCUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+extern "C" int dq_dqn_targets(const float* q_online_next, const float* q_target_next, const float* reward, const uint8_t* terminal,
+                              float gamma, int64_t batch, int num_actions, float* y, dq_stream stream) {
+    if (!q_online_next || !q_target_next || !reward || !terminal || !y || batch < 1) return qfail(DQ_EINVAL, "bad argument");
+    dqn_target_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(q_online_next, q_target_next, reward, terminal, gamma, batch, num_actions, y);
+    count_launch();
+    QCUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+extern "C" int dq_dqn_loss_grad(const float* q, const int32_t* actions, const float* y, int64_t batch, int num_actions, float* dq,
+                                float* stats, dq_stream stream) {
+    if (!q || !actions || !y || !dq || batch < 1) return qfail(DQ_EINVAL, "bad argument");
+    dqn_loss_grad_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(q, actions, y, batch, num_actions, dq, stats);
+    count_launch();
+    QCUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+extern "C" int dq_policy_eps_greedy(const float* q, const uint64_t* legal, int64_t n, int mask_words, int num_actions, uint32_t env_id_base,
+                                    uint64_t seed, uint32_t step_index, uint32_t* dev_step_counter, double eps, int masked_greedy,
+                                    int32_t* actions, dq_stream stream) {
+    if (!q || !legal || !actions || n < 1 || mask_words < 1 || mask_words > 3) return qfail(DQ_EINVAL, "bad argument");
+    double t = floor(eps * 4294967296.0);
+    const u32 thr = eps <= 0.0 ? 0u : (t >= 4294967295.0 ? 0xFFFFFFFFu : (u32)t);
+    eps_greedy_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(q, (const u64*)legal, (int)n, mask_words, num_actions, env_id_base,
+                                                                                      step_index, dev_step_counter, (u32)seed, (u32)(seed >> 32), thr,
+                                                                                      masked_greedy, actions);
+    count_launch();
+    QCUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+extern "C" int dq_replay_sample(const uint64_t* ring_obs, const int32_t* ring_act, const float* ring_rew, const uint8_t* ring_term,
+                                int rows, int64_t npad, int64_t n, int capacity, int head, int filled, int64_t batch, uint64_t seed,
+                                uint32_t draw_index, uint64_t* s0, uint64_t* s1, int32_t* act, float* rew, uint8_t* term,
+                                int32_t* picked, dq_stream stream) {
+    if (!ring_obs || !ring_act || !ring_rew || !ring_term || !s0 || !s1 || !act || !rew || !term) return qfail(DQ_EINVAL, "NULL argument");
+    if (filled < 1 || filled >= capacity || batch < 1) return qfail(DQ_EINVAL, "replay ring holds no complete transition yet");
+    replay_sample_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const u64*)ring_obs, ring_act, ring_rew, ring_term, rows, npad, (int)n,
+                                                                                             capacity, head, filled, batch, (u32)seed, (u32)(seed >> 32), draw_index,
+                                                                                             (u64*)s0, (u64*)s1, act, rew, term, picked);
+    count_launch();
+    QCUDA(cudaGetLastError());
+    return DQ_OK;
+}

@@ -124,6 +124,73 @@ int dq_policy_random_legal(const dq_env* env, const uint64_t* legal_mask, uint32
 int dq_policy_seek(dq_env* env, uint32_t step_index, dq_stream stream);
 int dq_policy_random_legal_next(dq_env* env, const uint64_t* legal_mask, int32_t* actions, dq_stream stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Q-network + DQN inner loop.  Replaces build_convolutional_nn + the keras-rl dueling head
+ * (EN/Function_Library.py:338-377), DQNAgent.forward/backward, the policies and SequentialMemory
+ * (keras-rl fork, call sites SPTS:109-152, 166-167).  fp32 throughout.
+ *
+ * A network input is a PACKED observation: one (2d+1)^2-cell bitmap per observation layer, PW =
+ * ceil((2d+1)^2/64) uint64 words each, stored as packed[layer*PW + word][sample] with row stride `stride`
+ * (>= batch).  Rows ROW_BM.. of the environment state matrix (dq_env_packed_obs) have exactly this
+ * form, so acting needs no byte observation at all; dq_qnet_pack_obs converts the reference's uint8
+ * board_state for callers that have only that.
+ * Parameters, gradients and Adam moments are caller-owned flat fp32 device buffers of
+ * DQ_QINFO_NUM_PARAMS elements laid out as dq_qnet_param_layout describes. */
+typedef struct dq_qnet dq_qnet;
+#define DQ_QINFO_NUM_PARAMS       0
+#define DQ_QINFO_PACKED_ROWS      1
+#define DQ_QINFO_NUM_TENSORS      2
+#define DQ_QINFO_FLOPS_PER_SAMPLE 3   /* forward, 2*MAC */
+
+/* cc_layers / ff_layers of build_convolutional_nn: conv l has filters[l] kernels[l]xkernels[l] stride strides[l]
+ * ('valid', ReLU); hidden dense i has units[i] (+ReLU, Dropout(dropout[i]) in training mode); then
+ * Dense(num_actions) linear and, if dueling, keras-rl's Dense(num_actions+1) + 'avg' combination. */
+int dq_qnet_create(dq_qnet** out, int in_channels, int in_side, int n_conv, const int* filters, const int* kernels,
+                   const int* strides, int n_dense, const int* units, const float* dropout, int num_actions,
+                   int dueling, int64_t max_batch, int device);
+int dq_qnet_destroy(dq_qnet* net);
+int dq_qnet_info(const dq_qnet* net, int what, int64_t* out);
+/* For tensor pair t (conv layers first, then dense): offsets[2t] / offsets[2t+1] = kernel / bias offset in the
+ * flat buffer, shapes[2t] x shapes[2t+1] = kernel rows (inputs) x columns (outputs).  Conv kernels are Keras
+ * HWIO flattened; rows of the first dense kernel are in (position, channel) order. */
+int dq_qnet_param_layout(const dq_qnet* net, int64_t* offsets, int64_t* shapes);
+int dq_qnet_pack_obs(dq_qnet* net, const uint8_t* obs, uint64_t* packed, int64_t stride, int64_t batch, dq_stream stream);
+/* model.predict_on_batch: Q[batch][num_actions].  train != 0 applies dropout (mask from dropout_seed) and keeps
+ * the activations for dq_qnet_backward. */
+int dq_qnet_forward(dq_qnet* net, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
+                    float* q_out, int train, uint64_t dropout_seed, dq_stream stream);
+/* Gradient of sum_b sum_a dq[b][a]*Q[b][a] for the batch of the last dq_qnet_forward call; grads is overwritten. */
+int dq_qnet_backward(dq_qnet* net, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
+                     const float* dq, float* grads, dq_stream stream);
+int dq_qnet_activation(dq_qnet* net, int index, float** dev_ptr, int64_t* per_sample);   /* tests */
+/* keras.optimizers.Adam (Keras 2): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps); g *= grad_scale first. */
+int dq_adam_step(float* params, float* m, float* v, const float* grads, int64_t n, float lr, float beta1, float beta2,
+                 float eps, int64_t t, float grad_scale, dq_stream stream);
+/* double DQN: y = r + gamma*(1-terminal)*Q_target(s', argmax_a Q_online(s', a)) */
+int dq_dqn_targets(const float* q_online_next, const float* q_target_next, const float* reward, const uint8_t* terminal,
+                   float gamma, int64_t batch, int num_actions, float* y, dq_stream stream);
+/* loss = mean_b 0.5*(y_b - Q[b][a_b])^2 (delta_clip = inf); dq = dloss/dQ; stats (optional, float[2]) += {sum of the
+ * per-sample losses, sum of max_a Q}. */
+int dq_dqn_loss_grad(const float* q, const int32_t* actions, const float* y, int64_t batch, int num_actions, float* dq,
+                     float* stats, dq_stream stream);
+/* EpsGreedyQPolicy / GreedyQPolicy with env.legal_actions (SPTS:110-115, 166-167): with probability eps uniform over
+ * the legal actions, else argmax over all actions (masked_greedy = 0) or over the legal ones (1).  Draws as in
+ * dq_policy_random_legal plus word 1 for the eps test.  dev_step_counter (optional, uint32[2] on the device) replaces
+ * step_index and is advanced by the launch, for CUDA-graph capture. */
+int dq_policy_eps_greedy(const float* q, const uint64_t* legal_mask, int64_t n, int mask_words, int num_actions,
+                         uint32_t env_id_base, uint64_t seed, uint32_t step_index, uint32_t* dev_step_counter, double eps,
+                         int masked_greedy, int32_t* actions, dq_stream stream);
+/* SequentialMemory.sample on a ring of packed observations ring_obs[slot][row][npad] with per-slot action / reward /
+ * terminal arrays [slot][n]: draws `batch` (slot, lattice) pairs uniformly over the `filled` most recent complete
+ * transitions (slot `head` holds the newest observation, whose transition is not complete yet) and gathers
+ * s, s' (= next slot), a, r, terminal.  Draw = Philox(sample index, draw_index, domain 2). */
+int dq_replay_sample(const uint64_t* ring_obs, const int32_t* ring_act, const float* ring_rew, const uint8_t* ring_term,
+                     int rows, int64_t npad, int64_t n, int capacity, int head, int filled, int64_t batch, uint64_t seed,
+                     uint32_t draw_index, uint64_t* s0, uint64_t* s1, int32_t* act, float* rew, uint8_t* term,
+                     int32_t* picked, dq_stream stream);
+/* Device pointer to the packed observation rows inside the env state (uint64 [C*PW][STATE_STRIDE]). */
+int dq_env_packed_obs(dq_env* env, uint64_t** dev_rows, int64_t* n_rows, int64_t* stride);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t dq_launch_count(void);
 
