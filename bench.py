@@ -266,6 +266,67 @@ def run_b200(args):
     h2d = n * 4
     d2h = n * (env.obs[0].numel() + 4 + 1 + 4 + 8 * env.mask_words)
 
+    # ---- DQN inner loop on the same lattices (extra evidence, not the headline metric):
+    #   act:   Q(s) for every lattice from the packed rows in the env state -> eps-greedy pick -> env step (no byte boards)
+    #   train: act + store in the replay ring + one double-DQN update (batch 4096) per iteration
+    dqn = None
+    if rank == 0 and not args.no_dqn:
+        from deepq_decoding_b200 import agents as A
+        spec = A.build_convolutional_nn([[64, 3, 2], [32, 2, 1], [32, 2, 1]], [[512, 0.2]], (7, 11, 11), env.num_actions)
+        agent = A.DQNAgent(model=spec, nb_actions=env.num_actions, memory=A.SequentialMemory(limit=64 * n), nb_steps_warmup=0,
+                           target_model_update=10 ** 9, policy=A.EpsGreedyQPolicy(eps=0.1), test_policy=A.GreedyQPolicy(masked_greedy=True),
+                           enable_dueling_network=True, batch_size=4096, seed=SEED, device=dev)
+        agent.compile(A.Adam(lr=1e-5), max_envs=n)
+        rows_ptr, nrows, stride = C.c_void_p(), C.c_int64(), C.c_int64()
+        _lib.check(L.dq_env_packed_obs(h, C.byref(rows_ptr), C.byref(nrows), C.byref(stride)))
+        from deepq_decoding_b200.qnet import device_view
+        rows_view = device_view(rows_ptr.value, (nrows.value, stride.value), "<i8", dev)
+        ring = A.ReplayRing(65, nrows.value, stride.value, n, dev)
+        st = cur()
+
+        def act_iter(i, store):
+            if store:
+                ring.push_obs(rows_view)
+            a = agent._act(env, rows_ptr.value, i, 0.1, True)
+            _lib.check(L.dq_env_step(h, vp(a), None, p_rew, p_done, p_life, p_legal, 1, cur()))
+            if store:
+                ring.push_outcome(a, env.reward, env.done)
+            return a
+
+        def timed(fn, iters):
+            for i in range(5):
+                fn(i)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(iters):
+                fn(5 + i)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) * 1e-3 / iters
+
+        t_fwd = timed(lambda i: agent.model.forward_packed(rows_ptr.value, stride.value, n), 30)
+        t_act = timed(lambda i: act_iter(i, False), 60)
+
+        def train_iter(i):
+            act_iter(i, True)
+            if ring.filled >= 1:
+                agent.train_on_ring(ring, i)
+        t_train = timed(train_iter, 40)
+        flops = agent.model.flops_per_sample
+        tf_peak = 1393.5
+        try:
+            tf_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+        except Exception:
+            pass
+        dqn = {"act_env_steps_per_s": n / t_act, "act_ms_per_iteration": t_act * 1e3,
+               "train_env_steps_per_s": n / t_train, "train_ms_per_iteration": t_train * 1e3,
+               "train_batch": 4096, "updates_per_iteration": 1,
+               "qnet_forward_ms": t_fwd * 1e3, "qnet_forward_tflops": flops * n / t_fwd / 1e12,
+               "qnet_frac_of_bf16_sustained_peak": flops * n / t_fwd / 1e12 / tf_peak,
+               "qnet_precision": "fp32 SIMT kernels (bf16 tcgen05 path not in this build)",
+               "qnet_flops_per_sample": flops, "policy": "eps-greedy 0.1 over legal actions, masked greedy"}
+
     if rank == 0:
         cb, _, _ = cpu_oracle_run(args.cpu_seconds)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
@@ -282,7 +343,7 @@ def run_b200(args):
                         "steps": ke, "api": "dq_env_step_host (pinned host actions in, all outputs to pinned host buffers)",
                         "policy": "uniform random action indices pre-generated on the host"},
                 "gpu_launches": 2 * K,
-                "roofline": roof, "cpu_baseline": cb}
+                "roofline": roof, "cpu_baseline": cb, "dqn": dqn}
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:
@@ -296,6 +357,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=64)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall budget of the cpu_baseline leg")
+    ap.add_argument("--no-dqn", action="store_true", help="skip the DQN inner-loop measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

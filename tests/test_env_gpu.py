@@ -241,3 +241,67 @@ def test_errors_are_loud():
         VecSurfaceCodeEnv(9, 0.01, 0.01, "DP", False, 3, REF.RefereeLUT(9, "DP", 1, np.zeros(4, np.uint8)), n_envs=4)
     with pytest.raises(_lib.DQError):
         VecSurfaceCodeEnv(5, 0.01, 0.01, "DP", False, 9, None, n_envs=4)          # volume_depth > 8
+
+
+def test_reference_named_adapter_matches_oracle():
+    """The N=1 class with the reference's name, ctor and attribute set, step by step against the oracle."""
+    from deepq_decoding_b200.envs import Surface_Code_Environment_Multi_Decoding_Cycles
+    rng = np.random.default_rng(8)
+    ref = random_referee(rng, 5, "DP")
+    env = Surface_Code_Environment_Multi_Decoding_Cycles(d=5, p_phys=0.03, p_meas=0.03, error_model="DP", use_Y=False,
+                                                         volume_depth=5, static_decoder=ref, seed=4, env_id=3)
+    o = O.OracleVecEnv(5, "DP", False, 5, 0.03, 0.03, 1, 4, 3)
+    o.set_referee(ref.mode, ref.lut_a, ref.lut_b)
+    assert env.observation_space.shape == (7, 11, 11) and env.action_space.n == 51
+    assert env.num_actions == 51 and env.identity_index == 50 and env.n_action_layers == 2 and env.multi_cycle
+    board = env.reset(); oobs, olegal = o.reset()
+    assert board.dtype.kind == "i" and np.array_equal(board, oobs[0])
+    ndone = 0
+    for t in range(300):
+        legal = sorted(env.legal_actions)
+        assert legal == [a for a in range(51) if (int(olegal[0, 0]) >> a) & 1]
+        a = legal[int(rng.integers(0, len(legal)))] if rng.random() > 0.2 else int(rng.integers(0, 51))
+        board, reward, done, info = env.step(a)
+        oobs, orew, odone, olife, olegal = o.step(np.array([a], np.int32), auto_reset=False)
+        st = o.get_env(0)
+        assert np.array_equal(board, oobs[0]) and board is env.board_state and info == {}
+        assert reward == float(orew[0]) and done == bool(odone[0]) and env.done == done and env.lifetime == int(olife[0])
+        assert np.array_equal(env.hidden_state, st["hidden"]) and np.array_equal(env.current_true_syndrome, st["true_syndrome"])
+        if done:
+            ndone += 1
+            board = env.reset(); oobs, olegal = o.reset()
+            assert np.array_equal(board, oobs[0]) and env.lifetime == o.get_env(0)["lifetime"] and not env.done
+    assert ndone > 0
+    text = env.render()
+    assert isinstance(text, str) and "lifetime" in text
+    # constant-layout helpers kept for API parity (notebook 3 builds its input volume with them)
+    syn = np.zeros((6, 6), int); syn[4, 1] = syn[5, 2] = 1
+    pad = env.padding_syndrome(syn)
+    assert pad.shape == (11, 11) and pad[8, 2] == 1 and pad[10, 4] == 1 and pad[0, 1] == 1 and pad[1, 3] == 1 and pad[1, 1] == 0
+    assert env.padding_actions([0] * 21 + [1] + [0] * 3)[9, 3] == 1
+    env.close()
+
+
+def test_error_rate_sweep_driver():
+    """Single_Point_Training_Script.py:187-222 on the shipped d5_dp/0.007 agent, coarse grid."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from qnet_util import REF_CC, REF_FF, golden_weights
+    from deepq_decoding_b200 import agents as A
+    from deepq_decoding_b200.envs import VecSurfaceCodeEnv
+    from deepq_decoding_b200.evaluate import test_sweep
+    conv, dense = golden_weights("dp")
+    env = VecSurfaceCodeEnv(5, 0.007, 0.007, "DP", False, 5, None, n_envs=4096, seed=77)
+    dqn = A.DQNAgent(model=A.build_convolutional_nn(REF_CC, REF_FF, env.observation_space.shape, env.num_actions), nb_actions=env.num_actions,
+                     memory=A.SequentialMemory(limit=100), policy=A.GreedyQPolicy(masked_greedy=True),
+                     test_policy=A.GreedyQPolicy(masked_greedy=True), enable_dueling_network=True)
+    dqn.compile(A.Adam(lr=1e-5), max_envs=4096)
+    dqn.model.set_keras_weights(conv, dense)
+    all_results, detailed, stats = test_sweep(dqn, env, nb_test_episodes=4096, num_to_test=4, step=0.005)
+    keys = list(all_results)
+    assert keys[0] == "0.005" and keys[1] == "0.01"
+    assert abs(all_results["0.005"] - 698.57) < 5 * max(stats["0.005"]["standard_error"], 1.0)      # BASELINE.md 1b
+    assert all_results["0.005"] > 200 > all_results["0.01"]
+    assert all_results[keys[-1]] < 1.0 / float(keys[-1]) or len(keys) == 4                       # stopped below 1/p
+    assert detailed["0.005"][-1] == pytest.approx(all_results["0.005"])
+    env.close()
