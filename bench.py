@@ -281,16 +281,16 @@ def run_b200(args):
         _lib.check(L.dq_env_packed_obs(h, C.byref(rows_ptr), C.byref(nrows), C.byref(stride)))
         from deepq_decoding_b200.qnet import device_view
         rows_view = device_view(rows_ptr.value, (nrows.value, stride.value), "<i8", dev)
-        ring = A.ReplayRing(65, nrows.value, stride.value, n, dev)
+        rring = A.ReplayRing(65, nrows.value, stride.value, n, dev)
         st = cur()
 
         def act_iter(i, store):
             if store:
-                ring.push_obs(rows_view)
+                rring.push_obs(rows_view)
             a = agent._act(env, rows_ptr.value, i, 0.1, True)
             _lib.check(L.dq_env_step(h, vp(a), None, p_rew, p_done, p_life, p_legal, 1, cur()))
             if store:
-                ring.push_outcome(a, env.reward, env.done)
+                rring.push_outcome(a, env.reward, env.done)
             return a
 
         def timed(fn, iters):
@@ -310,8 +310,8 @@ def run_b200(args):
 
         def train_iter(i):
             act_iter(i, True)
-            if ring.filled >= 1:
-                agent.train_on_ring(ring, i)
+            if rring.filled >= 1:
+                agent.train_on_ring(rring, i)
         t_train = timed(train_iter, 40)
         flops = agent.model.flops_per_sample
         tf_peak = 1393.5
