@@ -26,6 +26,7 @@
 
 #include "../../include/dq_decoding.h"
 #include "dq_lattice.cuh"
+#include "dq_ptx.cuh"
 
 namespace dq {
 
@@ -473,7 +474,9 @@ struct dq_qnet {
     float* act_fc[kMaxDense + 2]; float* dact_fc[kMaxDense + 2]; float* mask_fc[kMaxDense + 2];
     u64* pack_scratch;
     int last_train;
+    void* tc;                       // bf16 buffers of the tensor-core path (dq_qnet_tc), allocated on first use
 };
+static void tc_free(dq_qnet* h);
 
 static int grid_for(long long n, int block, int cap = 148 * 16) {
     long long g = (n + block - 1) / block;
@@ -542,6 +545,7 @@ extern "C" int dq_qnet_destroy(dq_qnet* h) {
     for (int l = 0; l < kMaxConv; ++l) { cudaFree(h->act_conv[l]); cudaFree(h->dact_conv[l]); }
     for (int i = 0; i < kMaxDense + 2; ++i) { cudaFree(h->act_fc[i]); cudaFree(h->dact_fc[i]); cudaFree(h->mask_fc[i]); }
     cudaFree(h->pack_scratch);
+    tc_free(h);
     cudaSetDevice(prev);
     delete h;
     return DQ_OK;
@@ -765,5 +769,320 @@ extern "C" int dq_replay_sample(const uint64_t* ring_obs, const int32_t* ring_ac
                                                                                              (u64*)s0, (u64*)s1, act, rew, term, picked);
     count_launch();
     QCUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+// ================================================================================================
+// bf16 tensor-core inference path (acting): tcgen05.mma with TMEM accumulators.
+//
+// Every layer after the first is Y[M][N] = act(A[M][K] * W[K][N] + b) with A rows gathered from the previous
+// channels-last activation (implicit im2col).  One CTA (128 threads) owns a 128 x BN output tile and the whole
+// K extent: the 128 A rows and BN weight rows are copied into shared memory as K-major, 128-byte-swizzled
+// tiles (one 1024-byte swizzle atom = 8 rows x 64 bf16) with 16-byte cp.async's, thread r gathering row r;
+// one thread then issues K/16 tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 -> fp32 in TMEM), commits to an
+// mbarrier, and the four warps read their 32 TMEM lanes back (tcgen05.ld 32x32b) for the fused
+// bias + ReLU + convert epilogue.  Several CTAs are resident per SM, so one CTA's copies overlap another's MMAs.
+// SASS evidence: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTCBAR (commit), LDGSTS (cp.async).
+#include <cuda_bf16.h>
+
+namespace dq {
+
+__device__ __forceinline__ void cp_async16(u32 smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ uint64_t umma_smem_desc(u32 saddr) {
+    // K-major, SWIZZLE_128B: 8-row groups 1024 B apart (SBO), LBO unused; version 1 (sm_100)
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_bf16(u32 tmem_d, uint64_t adesc, uint64_t bdesc, u32 idesc, u32 accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+struct TcArgs {
+    const __nv_bfloat16* X; Patch g;            // input activation (channels-last bf16) and its patch geometry
+    const __nv_bfloat16* Wt;                    // weights, transposed + zero-padded: [Npad][Kpad]
+    const float* bias;
+    void* Y; int ldy, out_bf16, relu;           // output rows of ldy elements
+    long long M; int N, K, Kpad;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(128)
+tc_gemm_kernel(const TcArgs a) {
+    extern __shared__ unsigned char tc_raw[];
+    __shared__ alignas(8) u64 mbar;
+    __shared__ u32 tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int KB = a.Kpad >> 6;                                     // 64-element k blocks
+    const u32 s_base = (smem_u32(tc_raw) + 1023u) & ~1023u;         // swizzle atoms need 1024-byte alignment
+    const u32 sA = s_base, sB = s_base + (u32)KB * 16384u;
+    const long long m0 = (long long)blockIdx.x * 128;
+    const int n0 = blockIdx.y * BN;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((u32)(BN < 32 ? 32 : BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) mbar_init(&mbar, 1);
+
+    // ---- A: thread r gathers row r (all k blocks); B: weight rows, spread over the CTA
+    {
+        const int r = tid;
+        const long long m = m0 + r;
+        const bool valid = m < a.M;
+        const long long rowoff = valid ? patch_row(a.g, m) : 0;
+        for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int k = kb * 64 + c * 8;
+                const u32 dst = sA + (u32)kb * 16384u + (u32)r * 128u + (u32)((c ^ (r & 7)) << 4);
+                if (valid && k < a.K) cp_async16(dst, a.X + rowoff + patch_col(a.g, k));
+                else asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+            }
+        }
+        const int total = BN * KB * 8;
+        for (int i = tid; i < total; i += 128) {
+            const int c = i & 7, n = (i >> 3) % BN, kb = (i >> 3) / BN;
+            const u32 dst = sB + (u32)kb * (u32)(BN * 128) + (u32)n * 128u + (u32)((c ^ (n & 7)) << 4);
+            cp_async16(dst, a.Wt + (size_t)(n0 + n) * a.Kpad + kb * 64 + c * 8);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        fence_proxy_async();                                        // generic-proxy writes -> visible to the MMA (async proxy)
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const u32 tmem = tmem_slot;
+
+    if (tid == 0) {
+        // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128
+        const u32 idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(BN >> 3) << 17) | ((u32)(128 >> 4) << 24);
+        for (int kb = 0; kb < KB; ++kb) {
+            const uint64_t da = umma_smem_desc(sA + (u32)kb * 16384u), db = umma_smem_desc(sB + (u32)kb * (u32)(BN * 128));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)                             // 16 bf16 = 32 bytes along the swizzled row
+                umma_bf16(tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+    }
+    mbar_wait(&mbar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 = output rows; thread = one row
+    const long long m = m0 + tid;
+    const u32 taddr = tmem + ((u32)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+        u32 v[16];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                     : "r"(taddr + (u32)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (m < a.M) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = n0 + c0 + j;
+                float x = __uint_as_float(v[j]) + ((a.bias && n < a.N) ? a.bias[n] : 0.f);
+                f[j] = a.relu ? fmaxf(x, 0.f) : x;
+            }
+            if (a.out_bf16) {
+                __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.Y) + m * a.ldy + n0 + c0;
+                if (n0 + c0 + 16 <= a.N && (a.ldy & 7) == 0) {
+                    uint4 p0, p1;
+                    __nv_bfloat162 t;
+#define DQ_PACK(dst, i) t = __floats2bfloat162_rn(f[i], f[i + 1]); dst = *reinterpret_cast<u32*>(&t);
+                    DQ_PACK(p0.x, 0) DQ_PACK(p0.y, 2) DQ_PACK(p0.z, 4) DQ_PACK(p0.w, 6)
+                    DQ_PACK(p1.x, 8) DQ_PACK(p1.y, 10) DQ_PACK(p1.z, 12) DQ_PACK(p1.w, 14)
+#undef DQ_PACK
+                    reinterpret_cast<uint4*>(y)[0] = p0; reinterpret_cast<uint4*>(y)[1] = p1;
+                } else {
+                    for (int j = 0; j < 16; ++j) if (n0 + c0 + j < a.N) y[j] = __float2bfloat16(f[j]);
+                }
+            } else {
+                float* y = reinterpret_cast<float*>(a.Y) + m * a.ldy + n0 + c0;
+                for (int j = 0; j < 16; ++j) if (n0 + c0 + j < a.N) y[j] = f[j];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((u32)(BN < 32 ? 32 : BN)) : "memory");
+}
+
+// fp32 [K][N] -> bf16 [Npad][Kpad] (transposed, zero padded)
+__global__ void prep_wt_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt, int K, int N, int Kpad, int Npad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Npad * Kpad) return;
+    const int n = i / Kpad, k = i - n * Kpad;
+    Wt[i] = __float2bfloat16((n < N && k < K) ? W[(size_t)k * N + n] : 0.f);
+}
+
+// layer 1 on packed bits with a bf16 result (same arithmetic as conv1_bits_kernel<false>, fp32 accumulation)
+__global__ void __launch_bounds__(256)
+conv1_bits_bf16_kernel(const u64* __restrict__ packed, long long stride, long long batch, ConvL L, int C, int PW, int H,
+                       const float* __restrict__ W, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+    extern __shared__ float sW[];
+    const int F = L.filters, K = L.K;
+    for (int i = threadIdx.x; i < K * F; i += blockDim.x) sW[i] = W[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const long long total = batch * L.P;
+    for (long long job = (long long)blockIdx.x * nwarp + warp; job < total; job += (long long)gridDim.x * nwarp) {
+        const long long b = job / L.P;
+        const int pos = (int)(job - b * L.P), oy = pos / L.oh, ox = pos - oy * L.oh;
+        u32 taps = 0;
+        if (lane < C) taps = layer_taps(packed, stride, b, lane, PW, H, oy * L.stride, ox * L.stride, L.ksz);
+        float acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = (lane + 32 * j < F) ? bias[lane + 32 * j] : 0.f;
+        for (int ci = 0; ci < C; ++ci) {
+            u32 m = __shfl_sync(0xffffffffu, taps, ci);
+            while (m) {
+                const int t = __ffs(m) - 1; m &= m - 1;
+                const float* wr = sW + (t * C + ci) * F;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (lane + 32 * j < F) acc[j] += wr[lane + 32 * j];
+            }
+        }
+        __nv_bfloat16* o = out + job * F;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (lane + 32 * j < F) o[lane + 32 * j] = __float2bfloat16(fmaxf(acc[j], 0.f));
+    }
+}
+
+}  // namespace dq
+
+struct dq_qnet_tc {                     // bf16 buffers of the tensor-core path, owned by the handle
+    __nv_bfloat16* act[kMaxConv + kMaxDense + 2];
+    __nv_bfloat16* wt[kMaxConv + kMaxDense + 2];
+    int kpad[kMaxConv + kMaxDense + 2], npad[kMaxConv + kMaxDense + 2], bn[kMaxConv + kMaxDense + 2];
+    int ready;
+};
+static void tc_free(dq_qnet* h) {
+    dq_qnet_tc* tc = (dq_qnet_tc*)h->tc;
+    if (!tc) return;
+    for (int i = 0; i < kMaxConv + kMaxDense + 2; ++i) { cudaFree(tc->act[i]); cudaFree(tc->wt[i]); }
+    delete tc;
+    h->tc = nullptr;
+}
+static dq_qnet_tc* tc_of(dq_qnet* h) {
+    if (h->tc) return (dq_qnet_tc*)h->tc;
+    const QCfg& c = h->c;
+    dq_qnet_tc* tc = new dq_qnet_tc();
+    memset(tc, 0, sizeof(*tc));
+    int prev = 0; cudaGetDevice(&prev); cudaSetDevice(h->device);
+    cudaError_t err = cudaMalloc(&tc->act[0], (size_t)h->max_batch * c.conv[0].P * c.conv[0].filters * sizeof(__nv_bfloat16));
+    const int n_tc = c.n_conv - 1 + c.n_hidden + 1;
+    for (int j = 0; j < n_tc && err == cudaSuccess; ++j) {
+        const int t = j + 1;
+        const int K = t < c.n_conv ? c.conv[t].K : c.fc_in[t - c.n_conv], N = t < c.n_conv ? c.conv[t].filters : c.fc_out[t - c.n_conv];
+        const long long rows = t < c.n_conv ? (long long)c.conv[t].P : 1;
+        tc->kpad[j] = (K + 63) / 64 * 64;
+        tc->bn[j] = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+        tc->npad[j] = (N + tc->bn[j] - 1) / tc->bn[j] * tc->bn[j];
+        err = cudaMalloc(&tc->wt[j], (size_t)tc->npad[j] * tc->kpad[j] * sizeof(__nv_bfloat16));
+        if (err == cudaSuccess && j + 1 < n_tc) err = cudaMalloc(&tc->act[j + 1], (size_t)h->max_batch * rows * N * sizeof(__nv_bfloat16));
+    }
+    cudaSetDevice(prev);
+    h->tc = tc;
+    if (err != cudaSuccess) { tc_free(h); return nullptr; }
+    return tc;
+}
+
+template <int BN>
+static int launch_tc(const TcArgs& a, int npad, cudaStream_t st) {
+    const size_t smem = (size_t)(128 + BN) * (a.Kpad >> 6) * 128 + 1024;
+    if (smem > 227 * 1024) return qfail(DQ_EINVAL, "tensor-core tile does not fit shared memory");
+    QCUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((a.M + 127) / 128), npad / BN);
+    tc_gemm_kernel<BN><<<grid, 128, smem, st>>>(a);
+    count_launch();
+    return DQ_OK;
+}
+
+// Q values through the bf16 tcgen05 path (inference / acting only; training stays fp32).
+// Requirements: >= 2 conv layers; every layer feeding a tensor-core layer has a channel / unit count that is a
+// multiple of 8; at least one hidden dense layer.  Shapes outside this return DQ_EINVAL (callers choose the fp32 path).
+extern "C" int dq_qnet_forward_tc(dq_qnet* h, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
+                                  float* q_out, dq_stream stream) {
+    if (!h || !params || !packed || !q_out) return qfail(DQ_EINVAL, "NULL argument");
+    if (batch < 1 || batch > h->max_batch) return qfail(DQ_EINVAL, "batch exceeds max_batch of the handle");
+    const QCfg& c = h->c;
+    if (c.n_conv < 2 || c.n_hidden < 1) return qfail(DQ_EINVAL, "tensor-core path needs >= 2 conv layers and >= 1 hidden dense layer");
+    for (int l = 0; l < c.n_conv; ++l) if (c.conv[l].filters % 8) return qfail(DQ_EINVAL, "conv filter counts must be multiples of 8 for the tensor-core path");
+    for (int i = 0; i < c.n_hidden; ++i) if (c.fc_out[i] % 8) return qfail(DQ_EINVAL, "hidden dense widths must be multiples of 8 for the tensor-core path");
+    cudaStream_t st = (cudaStream_t)stream;
+    dq_qnet_tc* tc = tc_of(h);
+    if (!tc) return qfail(DQ_ECUDA, "allocating the bf16 buffers failed");
+    const int n_tc = c.n_conv - 1 + c.n_hidden + 1;          // conv2.., hidden dense.., Dense(num_actions)
+    // weights -> bf16, transposed, padded (cheap: 193k parameters; redone per call so training can interleave)
+    for (int j = 0; j < n_tc; ++j) {
+        const int t = j + 1;                                  // tensor index in the flat layout (0 = conv1)
+        const int K = t < c.n_conv ? c.conv[t].K : c.fc_in[t - c.n_conv], N = t < c.n_conv ? c.conv[t].filters : c.fc_out[t - c.n_conv];
+        const int total = tc->npad[j] * tc->kpad[j];
+        prep_wt_kernel<<<(total + 255) / 256, 256, 0, st>>>(params + c.w_off[t], tc->wt[j], K, N, tc->kpad[j], tc->npad[j]);
+        count_launch();
+    }
+    {   // layer 1
+        const ConvL& L = c.conv[0];
+        const size_t smem = (size_t)L.K * L.filters * sizeof(float);
+        if (smem > 48 * 1024) QCUDA(cudaFuncSetAttribute(conv1_bits_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv1_bits_bf16_kernel<<<grid_for(batch * L.P, 8, 148 * 8), 256, smem, st>>>((const u64*)packed, stride, batch, L, c.C, c.PW, c.H,
+                                                                                     params + c.w_off[0], params + c.b_off[0], tc->act[0]);
+        count_launch();
+    }
+    const __nv_bfloat16* x = tc->act[0];
+    for (int j = 0; j < n_tc; ++j) {
+        const int t = j + 1;
+        TcArgs a;
+        a.X = x; a.Wt = tc->wt[j]; a.bias = params + c.b_off[t]; a.Kpad = tc->kpad[j];
+        const bool last = (j == n_tc - 1);
+        if (t < c.n_conv) { const ConvL& L = c.conv[t]; a.g = conv_patch(L); a.M = batch * L.P; a.N = L.filters; a.K = L.K; }
+        else { const int i = t - c.n_conv; a.g = dense_patch(c.fc_in[i]); a.M = batch; a.N = c.fc_out[i]; a.K = c.fc_in[i]; }
+        a.relu = last ? 0 : 1; a.out_bf16 = last ? 0 : 1; a.ldy = a.N;
+        a.Y = last ? (void*)h->act_fc[c.n_hidden] : (void*)tc->act[j + 1];
+        int rc = DQ_OK;
+        switch (tc->bn[j]) {
+            case 32: rc = launch_tc<32>(a, tc->npad[j], st); break;
+            case 64: rc = launch_tc<64>(a, tc->npad[j], st); break;
+            default: rc = launch_tc<128>(a, tc->npad[j], st); break;
+        }
+        if (rc) return rc;
+        x = tc->act[j + 1];
+    }
+    // dueling head (tiny) in fp32 on the SIMT path
+    const float* xf = h->act_fc[c.n_hidden];
+    if (c.dueling) {
+        const int i = c.n_fc - 1, K = c.fc_in[i], N = c.fc_out[i], t = c.n_conv + i;
+        dim3 grid((unsigned)((batch + TB - 1) / TB), (N + TB - 1) / TB);
+        gemm_fwd_kernel<<<grid, 256, 0, st>>>(xf, dense_patch(K), params + c.w_off[t], params + c.b_off[t], h->act_fc[i], batch, N, K, 0);
+        dueling_fwd_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(h->act_fc[i], q_out, batch, c.A);
+        count_launch(); count_launch();
+    } else {
+        QCUDA(cudaMemcpyAsync(q_out, xf, (size_t)batch * c.A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    h->last_train = 0;
+    QCUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+// bf16 activation j of the last dq_qnet_forward_tc call (0 = conv1 output, j+1 = output of tensor-core layer j); tests
+extern "C" int dq_qnet_tc_activation(dq_qnet* h, int index, void** dev_ptr, int64_t* per_sample) {
+    if (!h || !dev_ptr || !h->tc) return qfail(DQ_EINVAL, "no tensor-core forward has run on this handle");
+    const QCfg& c = h->c;
+    const int n_tc = c.n_conv - 1 + c.n_hidden + 1;
+    if (index < 0 || index >= n_tc) return qfail(DQ_EINVAL, "no such activation");
+    *dev_ptr = ((dq_qnet_tc*)h->tc)->act[index];
+    if (per_sample) {
+        if (index < c.n_conv) *per_sample = (int64_t)c.conv[index].P * c.conv[index].filters;
+        else *per_sample = c.fc_out[index - c.n_conv];
+    }
     return DQ_OK;
 }

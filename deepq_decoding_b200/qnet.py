@@ -171,14 +171,21 @@ class QNetwork:
         _lib.check(self.L.dq_qnet_pack_obs(self._h, C.c_void_p(obs_u8.data_ptr()), C.c_void_p(out.data_ptr()), B, B, self._stream()))
         return out
 
-    def forward_packed(self, packed_ptr, stride, batch, out=None, train=False, dropout_seed=0, params=None):
+    def forward_packed(self, packed_ptr, stride, batch, out=None, train=False, dropout_seed=0, params=None, precision="fp32"):
+        """precision: "fp32" (SIMT kernels, training-exact) or "bf16" (tcgen05 tensor-core path, acting only)."""
         q = self._q[:batch] if out is None else out
         p = self.params if params is None else params
+        if precision == "bf16":
+            if train:
+                raise ValueError("the bf16 tensor-core path is inference-only")
+            _lib.check(self.L.dq_qnet_forward_tc(self._h, C.c_void_p(p.data_ptr()), C.c_void_p(packed_ptr), stride, batch,
+                                                 C.c_void_p(q.data_ptr()), self._stream()))
+            return q
         _lib.check(self.L.dq_qnet_forward(self._h, C.c_void_p(p.data_ptr()), C.c_void_p(packed_ptr), stride, batch,
                                           C.c_void_p(q.data_ptr()), int(train), int(dropout_seed), self._stream()))
         return q
 
-    def forward(self, obs, train=False, dropout_seed=0):
+    def forward(self, obs, train=False, dropout_seed=0, precision="fp32"):
         """Q values for uint8/bool/int observations [B,C,H,W] (numpy or torch) -- model.predict_on_batch."""
         t = torch.as_tensor(obs)
         if t.dim() == 3:
@@ -186,7 +193,7 @@ class QNetwork:
         t = t.to(self.device).to(torch.uint8).contiguous()
         packed = self.pack(t)
         self._packed = packed
-        return self.forward_packed(packed.data_ptr(), t.shape[0], t.shape[0], train=train, dropout_seed=dropout_seed)
+        return self.forward_packed(packed.data_ptr(), t.shape[0], t.shape[0], train=train, dropout_seed=dropout_seed, precision=precision)
 
     def backward_packed(self, packed_ptr, stride, batch, dq, grads, params=None):
         p = self.params if params is None else params
@@ -199,6 +206,18 @@ class QNetwork:
         ptr, per = C.c_void_p(), C.c_int64()
         _lib.check(self.L.dq_qnet_activation(self._h, index, C.byref(ptr), C.byref(per)))
         return device_view(ptr.value, (batch, per.value), "<f4", self.device).clone()
+
+
+    def tc_activation(self, index, batch):
+        """bf16 activation `index` of the last tensor-core forward as float32 [batch, per_sample] (tests)."""
+        ptr, per = C.c_void_p(), C.c_int64()
+        _lib.check(QNetwork._L().dq_qnet_tc_activation(self._h, index, C.byref(ptr), C.byref(per)))
+        raw = device_view(ptr.value, (batch, per.value), "<i2", self.device)
+        return raw.view(torch.bfloat16).float()
+
+    @staticmethod
+    def _L():
+        return _lib.lib()
 
 
 class _RawDeviceArray:

@@ -159,6 +159,12 @@ int dq_qnet_pack_obs(dq_qnet* net, const uint8_t* obs, uint64_t* packed, int64_t
  * the activations for dq_qnet_backward. */
 int dq_qnet_forward(dq_qnet* net, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
                     float* q_out, int train, uint64_t dropout_seed, dq_stream stream);
+/* Same Q values through the bf16 tensor-core path (tcgen05.mma, fp32 accumulation in TMEM) for every layer after the
+ * first; inference / acting only.  Returns DQ_EINVAL for shapes the path does not cover (channel / unit counts must be
+ * multiples of 8, >= 2 conv layers, >= 1 hidden dense layer); there is no silent fallback. */
+int dq_qnet_forward_tc(dq_qnet* net, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
+                       float* q_out, dq_stream stream);
+int dq_qnet_tc_activation(dq_qnet* net, int index, void** dev_ptr, int64_t* per_sample);   /* tests: bf16 activations */
 /* Gradient of sum_b sum_a dq[b][a]*Q[b][a] for the batch of the last dq_qnet_forward call; grads is overwritten. */
 int dq_qnet_backward(dq_qnet* net, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
                      const float* dq, float* grads, dq_stream stream);

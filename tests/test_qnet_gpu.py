@@ -302,3 +302,37 @@ def test_fit_runs_and_learns_something():
     assert all(l % 5 == 0 for l in hist["episode_lifetimes_rolling_avg"][:1]) or True
     assert pol.value(1001) == pytest.approx(1.0 - 0.95 * 1001 / 30000)
     env.close()
+
+
+def test_tensor_core_forward_tracks_fp32():
+    """bf16 tcgen05 path (acting) against the fp32 SIMT path and torch: layer by layer, then Q and the greedy choice.
+    Tolerances: bf16 has 8 mantissa bits; activations are O(1), Q ~ 30 -> |dQ| < 0.35, argmax agreement > 97 %
+    (the shipped agent's top-2 gaps are 0.6-1.6)."""
+    import torch
+    from deepq_decoding_b200.qnet import QNetwork
+    net, conv, dense = ref_net("dp")
+    q = QNetwork(REF_CC, REF_FF, (7, 11, 11), 51, dueling=True, max_batch=4096)
+    q.set_keras_weights(conv, dense)
+    boards, _, _ = env_boards()
+    boards = boards[:3000]
+    B = len(boards)
+    want = q.forward(boards).clone()
+    got = q.forward(boards, precision="bf16")
+    # layer by layer (ours are channels-last)
+    x = torch.tensor(boards).float()
+    a1 = torch.relu(torch.nn.functional.conv2d(x, net.conv[0][0], net.conv[0][1], stride=2))
+    a2 = torch.relu(torch.nn.functional.conv2d(a1, net.conv[1][0], net.conv[1][1]))
+    a3 = torch.relu(torch.nn.functional.conv2d(a2, net.conv[2][0], net.conv[2][1]))
+    f1 = torch.relu(a3.flatten(1) @ net.dense[0][0] + net.dense[0][1])
+    cl = lambda t: t.detach().permute(0, 2, 3, 1).reshape(B, -1)
+    for idx, ref, tol in ((0, cl(a1), 0.03), (1, cl(a2), 0.06), (2, cl(a3), 0.08)):
+        mine = q.tc_activation(idx, B).cpu()
+        err = (mine - ref).abs().max().item()
+        assert err < tol * max(1.0, ref.abs().max().item()), "tensor-core activation %d: max err %g" % (idx, err)
+    mine = q.tc_activation(3, B).cpu()
+    assert (mine - f1.detach()).abs().max().item() < 0.1 * max(1.0, f1.abs().max().item())
+    d = (got - want).abs().max().item()
+    agree = (got.argmax(1) == want.argmax(1)).float().mean().item()
+    assert d < 0.35, d
+    assert agree > 0.97, agree
+    q.close()
