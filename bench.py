@@ -58,6 +58,11 @@ def cpu_oracle_run(budget_s, n=N_PER_GPU):
     import numpy as np
     from oracle import oracle as O
     from deepq_decoding_b200 import referee as REF
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except Exception:
+        ncores = os.cpu_count() or 1
+    O.lib().dqo_set_num_threads(ncores)          # torchrun exports OMP_NUM_THREADS=1: use every core we are allowed
     o = O.OracleVecEnv(D, MODEL, USE_Y, VD, P, P, n, SEED)
     ref = REF.shipped(D, MODEL)
     o.set_referee(ref.mode, ref.lut_a, ref.lut_b)
@@ -306,6 +311,9 @@ def run_b200(args):
             return a.elapsed_time(b) * 1e-3 / iters
 
         t_fwd = timed(lambda i: agent.model.forward_packed(rows_ptr.value, stride.value, n), 30)
+        t_fwd_tc = timed(lambda i: agent.model.forward_packed(rows_ptr.value, stride.value, n, precision="bf16"), 30)
+        t_act32 = timed(lambda i: act_iter(i, False), 40)
+        agent.act_precision = "bf16"
         t_act = timed(lambda i: act_iter(i, False), 60)
 
         def train_iter(i):
@@ -322,9 +330,11 @@ def run_b200(args):
         dqn = {"act_env_steps_per_s": n / t_act, "act_ms_per_iteration": t_act * 1e3,
                "train_env_steps_per_s": n / t_train, "train_ms_per_iteration": t_train * 1e3,
                "train_batch": 4096, "updates_per_iteration": 1,
-               "qnet_forward_ms": t_fwd * 1e3, "qnet_forward_tflops": flops * n / t_fwd / 1e12,
-               "qnet_frac_of_bf16_sustained_peak": flops * n / t_fwd / 1e12 / tf_peak,
-               "qnet_precision": "fp32 SIMT kernels (bf16 tcgen05 path not in this build)",
+               "act_fp32_env_steps_per_s": n / t_act32,
+               "qnet_forward_fp32_ms": t_fwd * 1e3, "qnet_forward_fp32_tflops": flops * n / t_fwd / 1e12,
+               "qnet_forward_bf16_ms": t_fwd_tc * 1e3, "qnet_forward_bf16_tflops": flops * n / t_fwd_tc / 1e12,
+               "qnet_frac_of_bf16_sustained_peak": flops * n / t_fwd_tc / 1e12 / tf_peak,
+               "qnet_precision": "acting: bf16 tcgen05 (fp32 accumulate in TMEM); updates: fp32 SIMT",
                "qnet_flops_per_sample": flops, "policy": "eps-greedy 0.1 over legal actions, masked greedy"}
 
     if rank == 0:
@@ -347,6 +357,7 @@ def run_b200(args):
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

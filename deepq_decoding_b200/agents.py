@@ -164,7 +164,7 @@ class DQNAgent:
     def __init__(self, model, nb_actions, memory, nb_steps_warmup=1000, target_model_update=10000, policy=None,
                  test_policy=None, gamma=0.99, enable_dueling_network=False, enable_double_dqn=True, batch_size=32,
                  train_interval=1, memory_interval=1, delta_clip=np.inf, dueling_type="avg", updates_per_step=1,
-                 seed=0, device="cuda:0", flush_interval=64, process_group=None):
+                 seed=0, device="cuda:0", flush_interval=64, process_group=None, act_precision="fp32"):
         if not enable_double_dqn:
             raise NotImplementedError("the reference always runs double DQN (keras-rl default)")
         if dueling_type != "avg" or delta_clip != np.inf or memory_interval != 1:
@@ -178,6 +178,7 @@ class DQNAgent:
         self.batch_size, self.train_interval, self.updates_per_step = int(batch_size), int(train_interval), int(updates_per_step)
         self.seed, self.device, self.flush_interval = int(seed), torch.device(device), int(flush_interval)
         self.process_group = process_group          # torch.distributed group for the gradient all-reduce (None = single GPU)
+        self.act_precision = act_precision          # "fp32" (SIMT) or "bf16" (tcgen05 tensor cores) for action selection; updates are always fp32
         self.optimizer = None
         self.model = None                           # QNetwork, built in compile()
         self.step, self.updates = 0, 0
@@ -228,7 +229,7 @@ class DQNAgent:
     def _act(self, v, rows_ptr, step_index, eps, masked):
         """Q(s) for all lattices from the packed rows inside the env state, then the eps-greedy pick."""
         N = v.n_envs
-        q = self.model.forward_packed(rows_ptr, v.state_stride, N)
+        q = self.model.forward_packed(rows_ptr, v.state_stride, N, precision=self.act_precision)
         if self._actions is None or self._actions.numel() != N:
             self._actions = torch.zeros(N, dtype=torch.int32, device=self.model.device)
         _lib.check(self.L.dq_policy_eps_greedy(C.c_void_p(q.data_ptr()), C.c_void_p(v.legal_mask.data_ptr()), N, v.mask_words,
@@ -270,6 +271,7 @@ class DQNAgent:
         o = self.optimizer
         _lib.check(self.L.dq_adam_step(p(m.params), p(self.adam_m), p(self.adam_v), p(self.grads), m.num_params, o.lr, o.beta_1,
                                        o.beta_2, o.epsilon, self.updates, scale, st))
+        m.params_changed()
 
     # ---- fit --------------------------------------------------------------------------------------
     def fit(self, env, nb_steps, action_repetition=1, callbacks=None, verbose=1, visualize=False, nb_max_start_steps=0,

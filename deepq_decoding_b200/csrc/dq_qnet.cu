@@ -802,19 +802,27 @@ __device__ __forceinline__ void umma_bf16(u32 tmem_d, uint64_t adesc, uint64_t b
 }
 
 struct TcArgs {
-    const __nv_bfloat16* X; Patch g;            // input activation (channels-last bf16) and its patch geometry
+    const __nv_bfloat16* X; Patch g;            // AMODE 0: input activation (channels-last bf16) and its patch geometry
+    const u64* packed; long long pstride;       // AMODE 1: packed observation rows [C*PW][pstride]
+    int C, PW, H, T;                            //          input layers, words per layer, side, taps per layer (ksz*ksz)
     const __nv_bfloat16* Wt;                    // weights, transposed + zero-padded: [Npad][Kpad]
     const float* bias;
     void* Y; int ldy, out_bf16, relu;           // output rows of ldy elements
     long long M; int N, K, Kpad;
 };
 
-template <int BN>
+// AMODE 0: A rows gathered from a bf16 activation (implicit im2col), 16-byte cp.async per chunk.
+// AMODE 1: A rows expanded from the packed binary observation: K order is (layer, tap), so a row's K bits are the
+//          per-layer tap masks concatenated; 8 bits -> 8 bf16 {0, 1.0} per 16-byte chunk.
+template <int BN, int AMODE>
 __global__ void __launch_bounds__(128)
 tc_gemm_kernel(const TcArgs a) {
     extern __shared__ unsigned char tc_raw[];
     __shared__ alignas(8) u64 mbar;
     __shared__ u32 tmem_slot;
+    __shared__ int koff[64];                                        // AMODE 0: element offset of every 8-wide k chunk
+    __shared__ float sbias[BN];
+    __shared__ u64 swords[AMODE == 1 ? 36 * 16 : 1];                // AMODE 1: packed words of the tile's samples
     const int tid = threadIdx.x, warp = tid >> 5;
     const int KB = a.Kpad >> 6;                                     // 64-element k blocks
     const u32 s_base = (smem_u32(tc_raw) + 1023u) & ~1023u;         // swizzle atoms need 1024-byte alignment
@@ -827,32 +835,77 @@ tc_gemm_kernel(const TcArgs a) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) mbar_init(&mbar, 1);
-
-    // ---- A: thread r gathers row r (all k blocks); B: weight rows, spread over the CTA
-    {
-        const int r = tid;
-        const long long m = m0 + r;
-        const bool valid = m < a.M;
-        const long long rowoff = valid ? patch_row(a.g, m) : 0;
-        for (int kb = 0; kb < KB; ++kb) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int k = kb * 64 + c * 8;
-                const u32 dst = sA + (u32)kb * 16384u + (u32)r * 128u + (u32)((c ^ (r & 7)) << 4);
-                if (valid && k < a.K) cp_async16(dst, a.X + rowoff + patch_col(a.g, k));
-                else asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
-            }
-        }
+    if (tid < BN) sbias[tid] = (a.bias && n0 + tid < a.N) ? a.bias[n0 + tid] : 0.f;
+    {   // B: weight rows, spread over the CTA (independent of A)
         const int total = BN * KB * 8;
         for (int i = tid; i < total; i += 128) {
             const int c = i & 7, n = (i >> 3) % BN, kb = (i >> 3) / BN;
             const u32 dst = sB + (u32)kb * (u32)(BN * 128) + (u32)n * 128u + (u32)((c ^ (n & 7)) << 4);
             cp_async16(dst, a.Wt + (size_t)(n0 + n) * a.Kpad + kb * 64 + c * 8);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        fence_proxy_async();                                        // generic-proxy writes -> visible to the MMA (async proxy)
     }
+    const int r = tid;
+    const long long m = m0 + r;
+    const bool valid = m < a.M;
+    if (AMODE == 0) {
+        if (tid < KB * 8) koff[tid] = (tid * 8 < a.K) ? patch_col(a.g, tid * 8) : -1;
+        const long long rowoff = valid ? patch_row(a.g, m) : 0;
+        __syncthreads();
+        for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int ko = koff[kb * 8 + c];
+                const u32 dst = sA + (u32)kb * 16384u + (u32)r * 128u + (u32)((c ^ (r & 7)) << 4);
+                if (valid && ko >= 0) cp_async16(dst, a.X + rowoff + ko);
+                else asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+            }
+        }
+    } else {
+        // stage the packed words of the samples this tile touches
+        const int P = a.g.P, rows = a.C * a.PW;
+        const long long b_lo = m0 / P;
+        const long long b_hi = min((m0 + 127) / P, (a.M - 1) / P);
+        const int ns = (int)(b_hi - b_lo + 1);
+        for (int i = tid; i < ns * rows; i += 128) {
+            const int s = i / rows, w = i - s * rows;
+            swords[s * 36 + w] = a.packed[(long long)w * a.pstride + b_lo + s];
+        }
+        __syncthreads();
+        const long long b = valid ? m / P : b_lo;
+        const int pos = valid ? (int)(m - b * P) : 0, oy = pos / a.g.oh, ox = pos - oy * a.g.oh;
+        const u64* wds = swords + (int)(b - b_lo) * 36;
+        for (int kb = 0; kb < KB; ++kb) {
+            // K bits [64 kb, 64 kb + 64): bit k = layer k / T, tap k % T
+            u64 bits = 0;
+            if (valid) {
+                for (int ci = 0; ci < a.C; ++ci) {
+                    const int lo = ci * a.T - kb * 64;
+                    if (lo >= 64 || lo + a.T <= 0) continue;
+                    u32 taps = 0;
+                    for (int ky = 0; ky < a.g.ksz; ++ky) {
+                        const int bit = (oy * a.g.stride + ky) * a.H + ox * a.g.stride, w = bit >> 6, sh = bit & 63;
+                        u64 v = wds[ci * a.PW + w] >> sh;
+                        if (sh + a.g.ksz > 64 && w + 1 < a.PW) v |= wds[ci * a.PW + w + 1] << (64 - sh);
+                        taps |= (u32)(v & ((1u << a.g.ksz) - 1)) << (ky * a.g.ksz);
+                    }
+                    bits |= lo >= 0 ? ((u64)taps << lo) : ((u64)taps >> (-lo));
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const u32 x = (u32)(bits >> (8 * c)) & 0xFFu;
+                const u32 dst = sA + (u32)kb * 16384u + (u32)r * 128u + (u32)((c ^ (r & 7)) << 4);
+                const u32 w0 = ((x & 1u) * 0x3F80u) | (((x >> 1) & 1u) * 0x3F800000u);
+                const u32 w1 = (((x >> 2) & 1u) * 0x3F80u) | (((x >> 3) & 1u) * 0x3F800000u);
+                const u32 w2 = (((x >> 4) & 1u) * 0x3F80u) | (((x >> 5) & 1u) * 0x3F800000u);
+                const u32 w3 = (((x >> 6) & 1u) * 0x3F80u) | (((x >> 7) & 1u) * 0x3F800000u);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+            }
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    fence_proxy_async();                                            // generic-proxy writes -> visible to the MMA (async proxy)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -873,8 +926,8 @@ tc_gemm_kernel(const TcArgs a) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 = output rows; thread = one row
-    const long long m = m0 + tid;
     const u32 taddr = tmem + ((u32)(warp * 32) << 16);
+    const bool vec_ok = (a.ldy & 7) == 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
         u32 v[16];
@@ -883,17 +936,16 @@ tc_gemm_kernel(const TcArgs a) {
                        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                      : "r"(taddr + (u32)c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (m < a.M) {
+        if (valid) {
             float f[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const int n = n0 + c0 + j;
-                float x = __uint_as_float(v[j]) + ((a.bias && n < a.N) ? a.bias[n] : 0.f);
+                const float x = __uint_as_float(v[j]) + sbias[c0 + j];
                 f[j] = a.relu ? fmaxf(x, 0.f) : x;
             }
             if (a.out_bf16) {
                 __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.Y) + m * a.ldy + n0 + c0;
-                if (n0 + c0 + 16 <= a.N && (a.ldy & 7) == 0) {
+                if (n0 + c0 + 16 <= a.N && vec_ok) {
                     uint4 p0, p1;
                     __nv_bfloat162 t;
 #define DQ_PACK(dst, i) t = __floats2bfloat162_rn(f[i], f[i + 1]); dst = *reinterpret_cast<u32*>(&t);
@@ -916,54 +968,59 @@ tc_gemm_kernel(const TcArgs a) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((u32)(BN < 32 ? 32 : BN)) : "memory");
 }
 
+// Fused head for the acting path: y = x W + b for the last (tiny) dense layer, then the dueling combination.
+// Thread = sample; W ([K][N], K, N <= ~150) lives in shared memory and is read as a broadcast.
+template <int MAXN>
+__global__ void __launch_bounds__(128)
+head_dueling_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                    float* __restrict__ q, long long B, int K, int N, int A, int dueling) {
+    extern __shared__ float hw[];                      // W [K][N] then bias [N]
+    for (int i = threadIdx.x; i < K * N; i += blockDim.x) hw[i] = W[i];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) hw[K * N + i] = bias[i];
+    __syncthreads();
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float y[MAXN];
+#pragma unroll
+    for (int n = 0; n < MAXN; ++n) y[n] = n < N ? hw[K * N + n] : 0.f;
+    const float* xr = x + b * K;
+    for (int k = 0; k < K; ++k) {
+        const float xv = xr[k];
+        const float* wr = hw + k * N;
+#pragma unroll
+        for (int n = 0; n < MAXN; ++n) if (n < N) y[n] = fmaf(xv, wr[n], y[n]);
+    }
+    if (dueling) {
+        float s = 0.f;
+#pragma unroll
+        for (int n = 1; n < MAXN; ++n) if (n < N) s += y[n];
+        const float base = y[0] - s / (float)A;
+#pragma unroll
+        for (int n = 1; n < MAXN; ++n) if (n < N) q[b * A + n - 1] = base + y[n];
+    } else {
+#pragma unroll
+        for (int n = 0; n < MAXN; ++n) if (n < N) q[b * A + n] = y[n];
+    }
+}
+
 // fp32 [K][N] -> bf16 [Npad][Kpad] (transposed, zero padded)
-__global__ void prep_wt_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt, int K, int N, int Kpad, int Npad) {
+// perm_C > 0 (layer 1): our K order is (layer, tap) while W's rows are (tap, layer): k' = ci*T + t  <-  k = t*C + ci
+__global__ void prep_wt_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt, int K, int N, int Kpad, int Npad, int perm_C) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Npad * Kpad) return;
     const int n = i / Kpad, k = i - n * Kpad;
-    Wt[i] = __float2bfloat16((n < N && k < K) ? W[(size_t)k * N + n] : 0.f);
-}
-
-// layer 1 on packed bits with a bf16 result (same arithmetic as conv1_bits_kernel<false>, fp32 accumulation)
-__global__ void __launch_bounds__(256)
-conv1_bits_bf16_kernel(const u64* __restrict__ packed, long long stride, long long batch, ConvL L, int C, int PW, int H,
-                       const float* __restrict__ W, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
-    extern __shared__ float sW[];
-    const int F = L.filters, K = L.K;
-    for (int i = threadIdx.x; i < K * F; i += blockDim.x) sW[i] = W[i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const long long total = batch * L.P;
-    for (long long job = (long long)blockIdx.x * nwarp + warp; job < total; job += (long long)gridDim.x * nwarp) {
-        const long long b = job / L.P;
-        const int pos = (int)(job - b * L.P), oy = pos / L.oh, ox = pos - oy * L.oh;
-        u32 taps = 0;
-        if (lane < C) taps = layer_taps(packed, stride, b, lane, PW, H, oy * L.stride, ox * L.stride, L.ksz);
-        float acc[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = (lane + 32 * j < F) ? bias[lane + 32 * j] : 0.f;
-        for (int ci = 0; ci < C; ++ci) {
-            u32 m = __shfl_sync(0xffffffffu, taps, ci);
-            while (m) {
-                const int t = __ffs(m) - 1; m &= m - 1;
-                const float* wr = sW + (t * C + ci) * F;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) if (lane + 32 * j < F) acc[j] += wr[lane + 32 * j];
-            }
-        }
-        __nv_bfloat16* o = out + job * F;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (lane + 32 * j < F) o[lane + 32 * j] = __float2bfloat16(fmaxf(acc[j], 0.f));
-    }
+    int ks = k;
+    if (perm_C > 0 && k < K) { const int T = K / perm_C, ci = k / T, t = k - ci * T; ks = t * perm_C + ci; }
+    Wt[i] = __float2bfloat16((n < N && k < K) ? W[(size_t)ks * N + n] : 0.f);
 }
 
 }  // namespace dq
 
 struct dq_qnet_tc {                     // bf16 buffers of the tensor-core path, owned by the handle
-    __nv_bfloat16* act[kMaxConv + kMaxDense + 2];
+    // tensor-core layer j = tensor j of the flat layout: conv1 .. conv_n, hidden dense .., Dense(num_actions)
+    __nv_bfloat16* act[kMaxConv + kMaxDense + 2];      // act[j] = bf16 output of layer j (not for the last one)
     __nv_bfloat16* wt[kMaxConv + kMaxDense + 2];
     int kpad[kMaxConv + kMaxDense + 2], npad[kMaxConv + kMaxDense + 2], bn[kMaxConv + kMaxDense + 2];
-    int ready;
 };
 static void tc_free(dq_qnet* h) {
     dq_qnet_tc* tc = (dq_qnet_tc*)h->tc;
@@ -972,23 +1029,27 @@ static void tc_free(dq_qnet* h) {
     delete tc;
     h->tc = nullptr;
 }
+static int tc_layers(const QCfg& c) { return c.n_conv + c.n_hidden + 1; }
+static void tc_shape(const QCfg& c, int t, int& K, int& N, long long& rows) {
+    if (t < c.n_conv) { K = c.conv[t].K; N = c.conv[t].filters; rows = c.conv[t].P; }
+    else { K = c.fc_in[t - c.n_conv]; N = c.fc_out[t - c.n_conv]; rows = 1; }
+}
 static dq_qnet_tc* tc_of(dq_qnet* h) {
     if (h->tc) return (dq_qnet_tc*)h->tc;
     const QCfg& c = h->c;
     dq_qnet_tc* tc = new dq_qnet_tc();
     memset(tc, 0, sizeof(*tc));
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(h->device);
-    cudaError_t err = cudaMalloc(&tc->act[0], (size_t)h->max_batch * c.conv[0].P * c.conv[0].filters * sizeof(__nv_bfloat16));
-    const int n_tc = c.n_conv - 1 + c.n_hidden + 1;
+    cudaError_t err = cudaSuccess;
+    const int n_tc = tc_layers(c);
     for (int j = 0; j < n_tc && err == cudaSuccess; ++j) {
-        const int t = j + 1;
-        const int K = t < c.n_conv ? c.conv[t].K : c.fc_in[t - c.n_conv], N = t < c.n_conv ? c.conv[t].filters : c.fc_out[t - c.n_conv];
-        const long long rows = t < c.n_conv ? (long long)c.conv[t].P : 1;
+        int K, N; long long rows;
+        tc_shape(c, j, K, N, rows);
         tc->kpad[j] = (K + 63) / 64 * 64;
         tc->bn[j] = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
         tc->npad[j] = (N + tc->bn[j] - 1) / tc->bn[j] * tc->bn[j];
         err = cudaMalloc(&tc->wt[j], (size_t)tc->npad[j] * tc->kpad[j] * sizeof(__nv_bfloat16));
-        if (err == cudaSuccess && j + 1 < n_tc) err = cudaMalloc(&tc->act[j + 1], (size_t)h->max_batch * rows * N * sizeof(__nv_bfloat16));
+        if (err == cudaSuccess && j + 1 < n_tc) err = cudaMalloc(&tc->act[j], (size_t)h->max_batch * rows * N * sizeof(__nv_bfloat16));
     }
     cudaSetDevice(prev);
     h->tc = tc;
@@ -996,75 +1057,97 @@ static dq_qnet_tc* tc_of(dq_qnet* h) {
     return tc;
 }
 
-template <int BN>
+template <int BN, int AMODE>
 static int launch_tc(const TcArgs& a, int npad, cudaStream_t st) {
     const size_t smem = (size_t)(128 + BN) * (a.Kpad >> 6) * 128 + 1024;
     if (smem > 227 * 1024) return qfail(DQ_EINVAL, "tensor-core tile does not fit shared memory");
-    QCUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QCUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((a.M + 127) / 128), npad / BN);
-    tc_gemm_kernel<BN><<<grid, 128, smem, st>>>(a);
+    tc_gemm_kernel<BN, AMODE><<<grid, 128, smem, st>>>(a);
     count_launch();
     return DQ_OK;
 }
+template <int AMODE>
+static int launch_tc_bn(const TcArgs& a, int bn, int npad, cudaStream_t st) {
+    switch (bn) {
+        case 32: return launch_tc<32, AMODE>(a, npad, st);
+        case 64: return launch_tc<64, AMODE>(a, npad, st);
+        default: return launch_tc<128, AMODE>(a, npad, st);
+    }
+}
 
-// Q values through the bf16 tcgen05 path (inference / acting only; training stays fp32).
-// Requirements: >= 2 conv layers; every layer feeding a tensor-core layer has a channel / unit count that is a
-// multiple of 8; at least one hidden dense layer.  Shapes outside this return DQ_EINVAL (callers choose the fp32 path).
+static int tc_check(const dq_qnet* h) {
+    const QCfg& c = h->c;
+    if (c.n_hidden < 1) return qfail(DQ_EINVAL, "tensor-core path needs >= 1 hidden dense layer");
+    for (int l = 0; l < c.n_conv; ++l) if (c.conv[l].filters % 8) return qfail(DQ_EINVAL, "conv filter counts must be multiples of 8 for the tensor-core path");
+    for (int i = 0; i < c.n_hidden; ++i) if (c.fc_out[i] % 8) return qfail(DQ_EINVAL, "hidden dense widths must be multiples of 8 for the tensor-core path");
+    if (c.C * c.PW > 36 || (128 / c.conv[0].P + 2) > 16) return qfail(DQ_EINVAL, "first layer too large for the tensor-core path");
+    return DQ_OK;
+}
+
+// bf16 copies of the weights (transposed, zero-padded, layer 1 with K in (layer, tap) order).  Call after every change of `params`.
+extern "C" int dq_qnet_prepare_tc(dq_qnet* h, const float* params, dq_stream stream) {
+    if (!h || !params) return qfail(DQ_EINVAL, "NULL argument");
+    int rc = tc_check(h);
+    if (rc) return rc;
+    const QCfg& c = h->c;
+    dq_qnet_tc* tc = tc_of(h);
+    if (!tc) return qfail(DQ_ECUDA, "allocating the bf16 buffers failed");
+    for (int j = 0; j < tc_layers(c); ++j) {
+        int K, N; long long rows;
+        tc_shape(c, j, K, N, rows);
+        const int total = tc->npad[j] * tc->kpad[j];
+        prep_wt_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params + c.w_off[j], tc->wt[j], K, N, tc->kpad[j], tc->npad[j], j == 0 ? c.C : 0);
+        count_launch();
+    }
+    QCUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+// Q values through the bf16 tcgen05 path (inference / acting only; training stays fp32).  Uses the weights staged by
+// the last dq_qnet_prepare_tc.  Shapes outside the path's coverage return DQ_EINVAL (callers choose the fp32 path).
 extern "C" int dq_qnet_forward_tc(dq_qnet* h, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
                                   float* q_out, dq_stream stream) {
     if (!h || !params || !packed || !q_out) return qfail(DQ_EINVAL, "NULL argument");
     if (batch < 1 || batch > h->max_batch) return qfail(DQ_EINVAL, "batch exceeds max_batch of the handle");
+    if (!h->tc) return qfail(DQ_ESTATE, "call dq_qnet_prepare_tc first");
     const QCfg& c = h->c;
-    if (c.n_conv < 2 || c.n_hidden < 1) return qfail(DQ_EINVAL, "tensor-core path needs >= 2 conv layers and >= 1 hidden dense layer");
-    for (int l = 0; l < c.n_conv; ++l) if (c.conv[l].filters % 8) return qfail(DQ_EINVAL, "conv filter counts must be multiples of 8 for the tensor-core path");
-    for (int i = 0; i < c.n_hidden; ++i) if (c.fc_out[i] % 8) return qfail(DQ_EINVAL, "hidden dense widths must be multiples of 8 for the tensor-core path");
     cudaStream_t st = (cudaStream_t)stream;
-    dq_qnet_tc* tc = tc_of(h);
-    if (!tc) return qfail(DQ_ECUDA, "allocating the bf16 buffers failed");
-    const int n_tc = c.n_conv - 1 + c.n_hidden + 1;          // conv2.., hidden dense.., Dense(num_actions)
-    // weights -> bf16, transposed, padded (cheap: 193k parameters; redone per call so training can interleave)
+    dq_qnet_tc* tc = (dq_qnet_tc*)h->tc;
+    const int n_tc = tc_layers(c);
     for (int j = 0; j < n_tc; ++j) {
-        const int t = j + 1;                                  // tensor index in the flat layout (0 = conv1)
-        const int K = t < c.n_conv ? c.conv[t].K : c.fc_in[t - c.n_conv], N = t < c.n_conv ? c.conv[t].filters : c.fc_out[t - c.n_conv];
-        const int total = tc->npad[j] * tc->kpad[j];
-        prep_wt_kernel<<<(total + 255) / 256, 256, 0, st>>>(params + c.w_off[t], tc->wt[j], K, N, tc->kpad[j], tc->npad[j]);
-        count_launch();
-    }
-    {   // layer 1
-        const ConvL& L = c.conv[0];
-        const size_t smem = (size_t)L.K * L.filters * sizeof(float);
-        if (smem > 48 * 1024) QCUDA(cudaFuncSetAttribute(conv1_bits_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv1_bits_bf16_kernel<<<grid_for(batch * L.P, 8, 148 * 8), 256, smem, st>>>((const u64*)packed, stride, batch, L, c.C, c.PW, c.H,
-                                                                                     params + c.w_off[0], params + c.b_off[0], tc->act[0]);
-        count_launch();
-    }
-    const __nv_bfloat16* x = tc->act[0];
-    for (int j = 0; j < n_tc; ++j) {
-        const int t = j + 1;
         TcArgs a;
-        a.X = x; a.Wt = tc->wt[j]; a.bias = params + c.b_off[t]; a.Kpad = tc->kpad[j];
+        memset(&a, 0, sizeof(a));
+        a.Wt = tc->wt[j]; a.bias = params + c.b_off[j]; a.Kpad = tc->kpad[j];
         const bool last = (j == n_tc - 1);
-        if (t < c.n_conv) { const ConvL& L = c.conv[t]; a.g = conv_patch(L); a.M = batch * L.P; a.N = L.filters; a.K = L.K; }
-        else { const int i = t - c.n_conv; a.g = dense_patch(c.fc_in[i]); a.M = batch; a.N = c.fc_out[i]; a.K = c.fc_in[i]; }
+        if (j < c.n_conv) { const ConvL& L = c.conv[j]; a.g = conv_patch(L); a.M = batch * L.P; a.N = L.filters; a.K = L.K; }
+        else { const int i = j - c.n_conv; a.g = dense_patch(c.fc_in[i]); a.M = batch; a.N = c.fc_out[i]; a.K = c.fc_in[i]; }
         a.relu = last ? 0 : 1; a.out_bf16 = last ? 0 : 1; a.ldy = a.N;
-        a.Y = last ? (void*)h->act_fc[c.n_hidden] : (void*)tc->act[j + 1];
-        int rc = DQ_OK;
-        switch (tc->bn[j]) {
-            case 32: rc = launch_tc<32>(a, tc->npad[j], st); break;
-            case 64: rc = launch_tc<64>(a, tc->npad[j], st); break;
-            default: rc = launch_tc<128>(a, tc->npad[j], st); break;
+        a.Y = last ? (void*)h->act_fc[c.n_hidden] : (void*)tc->act[j];
+        int rc;
+        if (j == 0) {
+            a.packed = (const u64*)packed; a.pstride = stride; a.C = c.C; a.PW = c.PW; a.H = c.H; a.T = c.conv[0].ksz * c.conv[0].ksz;
+            rc = launch_tc_bn<1>(a, tc->bn[j], tc->npad[j], st);
+        } else {
+            a.X = tc->act[j - 1];
+            rc = launch_tc_bn<0>(a, tc->bn[j], tc->npad[j], st);
         }
         if (rc) return rc;
-        x = tc->act[j + 1];
     }
     // dueling head (tiny) in fp32 on the SIMT path
     const float* xf = h->act_fc[c.n_hidden];
     if (c.dueling) {
         const int i = c.n_fc - 1, K = c.fc_in[i], N = c.fc_out[i], t = c.n_conv + i;
-        dim3 grid((unsigned)((batch + TB - 1) / TB), (N + TB - 1) / TB);
-        gemm_fwd_kernel<<<grid, 256, 0, st>>>(xf, dense_patch(K), params + c.w_off[t], params + c.b_off[t], h->act_fc[i], batch, N, K, 0);
-        dueling_fwd_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(h->act_fc[i], q_out, batch, c.A);
-        count_launch(); count_launch();
+        const size_t smem = (size_t)(K * N + N) * sizeof(float);
+        if (N <= 64 && smem <= 48 * 1024) {
+            head_dueling_kernel<64><<<(unsigned)((batch + 127) / 128), 128, smem, st>>>(xf, params + c.w_off[t], params + c.b_off[t], q_out, batch, K, N, c.A, 1);
+            count_launch();
+        } else {
+            dim3 grid((unsigned)((batch + TB - 1) / TB), (N + TB - 1) / TB);
+            gemm_fwd_kernel<<<grid, 256, 0, st>>>(xf, dense_patch(K), params + c.w_off[t], params + c.b_off[t], h->act_fc[i], batch, N, K, 0);
+            dueling_fwd_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(h->act_fc[i], q_out, batch, c.A);
+            count_launch(); count_launch();
+        }
     } else {
         QCUDA(cudaMemcpyAsync(q_out, xf, (size_t)batch * c.A * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
@@ -1077,7 +1160,7 @@ extern "C" int dq_qnet_forward_tc(dq_qnet* h, const float* params, const uint64_
 extern "C" int dq_qnet_tc_activation(dq_qnet* h, int index, void** dev_ptr, int64_t* per_sample) {
     if (!h || !dev_ptr || !h->tc) return qfail(DQ_EINVAL, "no tensor-core forward has run on this handle");
     const QCfg& c = h->c;
-    const int n_tc = c.n_conv - 1 + c.n_hidden + 1;
+    const int n_tc = c.n_conv + c.n_hidden;                 // layers with a bf16 output
     if (index < 0 || index >= n_tc) return qfail(DQ_EINVAL, "no such activation");
     *dev_ptr = ((dq_qnet_tc*)h->tc)->act[index];
     if (per_sample) {

@@ -54,6 +54,7 @@ class QNetwork:
         self.params = torch.zeros(self.num_params, dtype=torch.float32, device=self.device)
         self._q = torch.zeros((self.max_batch, self.num_actions), dtype=torch.float32, device=self.device)
         self._packed = None
+        self._tc_dirty = True            # bf16 weight copies of the tensor-core path are stale
         # geometry of the last conv output, for the Flatten permutation
         side, c = H, C_in
         for filt, ksz, st in self.cc_layers:
@@ -101,6 +102,7 @@ class QNetwork:
             flat[wo:wo + K * N] = k.reshape(-1)
             flat[bo:bo + N] = np.asarray(b, np.float32)
         self.params.copy_(torch.from_numpy(flat))
+        self._tc_dirty = True
 
     def get_keras_weights(self):
         flat = self.params.detach().cpu().numpy()
@@ -176,8 +178,11 @@ class QNetwork:
         q = self._q[:batch] if out is None else out
         p = self.params if params is None else params
         if precision == "bf16":
-            if train:
-                raise ValueError("the bf16 tensor-core path is inference-only")
+            if train or params is not None:
+                raise ValueError("the bf16 tensor-core path is inference-only and uses the network's own parameters")
+            if self._tc_dirty:
+                _lib.check(self.L.dq_qnet_prepare_tc(self._h, C.c_void_p(p.data_ptr()), self._stream()))
+                self._tc_dirty = False
             _lib.check(self.L.dq_qnet_forward_tc(self._h, C.c_void_p(p.data_ptr()), C.c_void_p(packed_ptr), stride, batch,
                                                  C.c_void_p(q.data_ptr()), self._stream()))
             return q
@@ -194,6 +199,10 @@ class QNetwork:
         packed = self.pack(t)
         self._packed = packed
         return self.forward_packed(packed.data_ptr(), t.shape[0], t.shape[0], train=train, dropout_seed=dropout_seed, precision=precision)
+
+    def params_changed(self):
+        """Tell the network its flat parameter buffer was modified in place (optimizer step, copy)."""
+        self._tc_dirty = True
 
     def backward_packed(self, packed_ptr, stride, batch, dq, grads, params=None):
         p = self.params if params is None else params

@@ -161,9 +161,12 @@ int dq_qnet_forward(dq_qnet* net, const float* params, const uint64_t* packed, i
                     float* q_out, int train, uint64_t dropout_seed, dq_stream stream);
 /* Same Q values through the bf16 tensor-core path (tcgen05.mma, fp32 accumulation in TMEM) for every layer after the
  * first; inference / acting only.  Returns DQ_EINVAL for shapes the path does not cover (channel / unit counts must be
- * multiples of 8, >= 2 conv layers, >= 1 hidden dense layer); there is no silent fallback. */
+ * multiples of 8, >= 1 hidden dense layer); there is no silent fallback.  The first layer expands the packed bits into
+ * a bf16 {0,1} tile in shared memory, every later layer gathers its A rows from the previous bf16 activation. */
 int dq_qnet_forward_tc(dq_qnet* net, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
                        float* q_out, dq_stream stream);
+/* Stages the bf16 weight copies dq_qnet_forward_tc multiplies with; call after every change of `params`. */
+int dq_qnet_prepare_tc(dq_qnet* net, const float* params, dq_stream stream);
 int dq_qnet_tc_activation(dq_qnet* net, int index, void** dev_ptr, int64_t* per_sample);   /* tests: bf16 activations */
 /* Gradient of sum_b sum_a dq[b][a]*Q[b][a] for the batch of the last dq_qnet_forward call; grads is overwritten. */
 int dq_qnet_backward(dq_qnet* net, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,

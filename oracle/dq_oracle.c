@@ -467,6 +467,15 @@ void dqo_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
     philox4x32_10(c0, c1, c2, c3, k0, k1, out);
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline must use the cores it reports */
+void dqo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int dqo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -42,6 +42,7 @@ def lib():
         L.dqo_stab_order.argtypes = [C.c_void_p] * 4
         L.dqo_philox.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
         L.dqo_num_threads.restype = C.c_int
+        L.dqo_set_num_threads.argtypes = [C.c_int]
         _LIB = L
     return _LIB
 

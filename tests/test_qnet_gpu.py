@@ -259,7 +259,8 @@ def test_replay_sample_gathers_consecutive_slots():
         assert a.cpu().numpy()[b] == act[ts, i]
 
 
-def test_shipped_agent_reproduces_published_lifetime():
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_shipped_agent_reproduces_published_lifetime(precision):
     """trained_models/d5_dp/0.007 at p=0.007: 270.42 cycles over 23 100 episodes (all_results.p).
     16 384 independent episodes here: standard error ~2.1 cycles, band = 3.5 SE of the two estimates combined."""
     from deepq_decoding_b200 import agents as A
@@ -268,7 +269,7 @@ def test_shipped_agent_reproduces_published_lifetime():
     env = VecSurfaceCodeEnv(5, 0.007, 0.007, "DP", False, 5, None, n_envs=16384, seed=123)
     spec = A.build_convolutional_nn(REF_CC, REF_FF, (7, 11, 11), 51)
     dqn = A.DQNAgent(model=spec, nb_actions=51, memory=A.SequentialMemory(limit=100), policy=A.GreedyQPolicy(masked_greedy=True),
-                     test_policy=A.GreedyQPolicy(masked_greedy=True), enable_dueling_network=True)
+                     test_policy=A.GreedyQPolicy(masked_greedy=True), enable_dueling_network=True, act_precision=precision)
     dqn.compile(A.Adam(lr=1e-5), max_envs=16384)
     dqn.model.set_keras_weights(conv, dense)
     h = dqn.test(env, nb_episodes=16384, verbose=0, max_iterations=20000).history
@@ -306,7 +307,7 @@ def test_fit_runs_and_learns_something():
 
 def test_tensor_core_forward_tracks_fp32():
     """bf16 tcgen05 path (acting) against the fp32 SIMT path and torch: layer by layer, then Q and the greedy choice.
-    Tolerances: bf16 has 8 mantissa bits; activations are O(1), Q ~ 30 -> |dQ| < 0.35, argmax agreement > 97 %
+    Tolerances: bf16 has 8 mantissa bits; activations are O(1), Q ~ 30 -> |dQ| < 0.5, argmax agreement > 97 %
     (the shipped agent's top-2 gaps are 0.6-1.6)."""
     import torch
     from deepq_decoding_b200.qnet import QNetwork
@@ -333,6 +334,6 @@ def test_tensor_core_forward_tracks_fp32():
     assert (mine - f1.detach()).abs().max().item() < 0.1 * max(1.0, f1.abs().max().item())
     d = (got - want).abs().max().item()
     agree = (got.argmax(1) == want.argmax(1)).float().mean().item()
-    assert d < 0.35, d
+    assert d < 0.5, d
     assert agree > 0.97, agree
     q.close()
