@@ -297,7 +297,9 @@ class DQNAgent:
         h_life = torch.zeros((K, N), dtype=torch.int32, device=dev)
         hist = History()
         ep_reward, ep_steps = np.zeros(N), np.zeros(N, np.int64)
-        lifetimes, best_avg, best_ep, episode = [], -np.inf, 0, 0
+        L_avg = max(1, int(episode_averaging_length))
+        win, win_sum, win_n = np.zeros(L_avg), 0.0, 0            # ring of the last L_avg lifetimes + running sum: O(1) rolling mean
+        best_avg, best_ep, episode = -np.inf, 0, 0
         eps_sum, eps_n = 0.0, 0
         t_start = t_last = time.time()
         it, stop = 0, False
@@ -335,8 +337,11 @@ class DQNAgent:
                 for j in range(k + 1):
                     ep_reward += rew[j]; ep_steps += 1
                     for i in np.nonzero(done[j])[0]:
-                        lifetimes.append(int(life[j, i]))
-                        rolling = float(np.mean(lifetimes[-int(episode_averaging_length):]))
+                        slot = episode % L_avg
+                        win_sum += float(life[j, i]) - win[slot]
+                        win[slot] = life[j, i]
+                        win_n = min(win_n + 1, L_avg)
+                        rolling = win_sum / win_n
                         if rolling > best_avg:
                             best_avg, best_ep = rolling, episode
                         succeeded = rolling > success_threshold
@@ -353,9 +358,9 @@ class DQNAgent:
                 for cb in (callbacks or []):
                     if hasattr(cb, "on_flush"):
                         cb.on_flush(hist.history)
-                if verbose and (it // K) % max(1, int(log_interval // max(1, K * N))) == 0 and lifetimes:
+                if verbose and (it // K) % max(1, int(log_interval // max(1, K * N))) == 0 and win_n:
                     print("step %d  episodes %d  rolling lifetime %.1f  best %.1f  eps %.3f  loss %.4g  mean_q %.3f  %.0f env-steps/s" % (
-                        self.step, episode, float(np.mean(lifetimes[-int(episode_averaging_length):])), best_avg, eps, loss, mean_q,
+                        self.step, episode, win_sum / win_n, best_avg, eps, loss, mean_q,
                         self.step / max(1e-9, now - t_start)), flush=True)
         for cb in (callbacks or []):
             if hasattr(cb, "on_flush"):
