@@ -334,6 +334,7 @@ class DQNAgent:
                 mean_eps = eps_sum / eps_n if eps_n else float("nan")
                 upd_window, eps_sum, eps_n = 0, 0.0, 0
                 now = time.time()
+                per_episode_s = (now - t_last) / max(1, int(done.sum()))
                 for j in range(k + 1):
                     ep_reward += rew[j]; ep_steps += 1
                     for i in np.nonzero(done[j])[0]:
@@ -350,7 +351,7 @@ class DQNAgent:
                                  nb_episode_steps=int(ep_steps[i]), nb_steps=int(self.step - (k - j) * N),
                                  episode_lifetimes_rolling_avg=rolling, best_rolling_avg=best_avg, best_episode=best_ep,
                                  time_since_best=episode - best_ep, has_succeeded=bool(succeeded),
-                                 stopped_improving=bool(stopped), episode=episode, duration=(now - t_last) / max(1, done[:k + 1].sum()))
+                                 stopped_improving=bool(stopped), episode=episode, duration=per_episode_s)
                         ep_reward[i], ep_steps[i] = 0.0, 0
                         episode += 1
                         stop = stop or succeeded or stopped

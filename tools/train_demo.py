@@ -34,6 +34,8 @@ ap.add_argument("--gamma", type=float, default=0.99)
 ap.add_argument("--seed", type=int, default=0)
 ap.add_argument("--act", default="bf16")
 ap.add_argument("--test-episodes", type=int, default=8192)
+ap.add_argument("--curriculum", default="", help="p:steps,p:steps,... trained in order, carrying weights and replay memory over (tex:592-609)")
+ap.add_argument("--eps-max-continue", type=float, default=0.3)
 ap.add_argument("--out", default="gpurun_out/train_demo.json")
 a = ap.parse_args()
 
@@ -44,18 +46,28 @@ dqn = A.DQNAgent(model=spec, nb_actions=env.num_actions, memory=A.SequentialMemo
                  target_model_update=int(a.target), policy=policy, test_policy=A.GreedyQPolicy(masked_greedy=True), gamma=a.gamma,
                  enable_dueling_network=True, batch_size=a.batch, updates_per_step=a.updates, seed=a.seed, act_precision=a.act)
 dqn.compile(A.Adam(lr=a.lr), max_envs=max(a.envs, a.test_episodes))
+phases = [(a.p, a.steps)] if not a.curriculum else [(float(x.split(":")[0]), float(x.split(":")[1])) for x in a.curriculum.split(",")]
 t0 = time.time()
-hist = dqn.fit(env, nb_steps=int(a.steps), verbose=1, log_interval=2e6, episode_averaging_length=5000, success_threshold=1e9,
-               stopping_patience=1e12, min_nb_steps=0).history
+curve, total_steps, hist = [], 0, None
+for ph, (p_ph, n_ph) in enumerate(phases):
+    env.p_phys = p_ph; env.p_meas = p_ph
+    if ph > 0:      # a continued run restarts its step counter and exploration schedule (Single_Point_Continue_Training_Script.py:109-136)
+        dqn.step = 0
+        dqn.policy = A.LinearAnnealedPolicy(A.EpsGreedyQPolicy(masked_greedy=False), attr="eps", value_max=a.eps_max_continue,
+                                            value_min=a.eps_min, value_test=0.0, nb_steps=min(a.eps_steps, n_ph / 3))
+    hist = dqn.fit(env, nb_steps=int(n_ph), verbose=1, log_interval=4e6, episode_averaging_length=5000, success_threshold=1e9,
+                   stopping_patience=1e12, min_nb_steps=0).history
+    steps = np.array(hist["nb_steps"]); roll = np.array(hist["episode_lifetimes_rolling_avg"])
+    idx = np.unique(np.linspace(0, len(steps) - 1, 40).astype(int))
+    curve += [{"p_phys": p_ph, "env_steps": int(total_steps + steps[i]), "rolling_lifetime": float(roll[i])} for i in idx]
+    total_steps += int(dqn.step)
 t_train = time.time() - t0
-steps = np.array(hist["nb_steps"]); roll = np.array(hist["episode_lifetimes_rolling_avg"])
-idx = np.unique(np.linspace(0, len(steps) - 1, 60).astype(int))
-curve = [{"env_steps": int(steps[i]), "rolling_lifetime": float(roll[i])} for i in idx]
+a.p = phases[-1][0]
 test_env = VecSurfaceCodeEnv(5, a.p, a.p, a.model, False, 5, None, n_envs=a.test_episodes, seed=a.seed + 1000)
 th = dqn.test(test_env, nb_episodes=a.test_episodes, verbose=1).history
 life = np.array(th["episode_lifetime"], dtype=np.float64)
-res = {"config": vars(a), "train_seconds": t_train, "env_steps": int(dqn.step), "updates": int(dqn.updates),
-       "train_env_steps_per_s": dqn.step / t_train, "episodes": len(steps), "curve": curve,
+res = {"config": vars(a), "train_seconds": t_train, "env_steps": int(total_steps), "updates": int(dqn.updates),
+       "train_env_steps_per_s": total_steps / t_train, "episodes_last_phase": len(steps), "curve": curve,
        "test_mean_lifetime": float(life.mean()), "test_se": float(life.std() / np.sqrt(len(life))),
        "test_logical_error_rate_per_cycle": float(1.0 / life.mean()), "single_qubit_lifetime_1_over_p": 1.0 / a.p,
        "final_loss": float([x for x in hist["loss"] if x == x][-1]) if any(x == x for x in hist["loss"]) else None}
