@@ -7,7 +7,8 @@
 Workload (config C3 of SURVEY.md section 8): d=5, depolarising noise, p_phys = p_meas = 0.007, volume depth 5,
 16384 lattices per GPU (weak scaling: C4 = 8 x 16384), shipped referee table, random-legal policy.
 One "step" = one vectorised env step of every lattice: the policy kernel picks an action per lattice
-from its legal mask, the env kernel advances all lattices and writes a fresh observation.
+from its legal mask, the env kernel advances all lattices and writes a fresh observation (both in one launch:
+dq_env_step_random).
 
   value     all-GPU env-steps/s with everything resident in HBM; the K steps run as CUDA-graph replays
             of 16 (policy, step) pairs, each pair writing its observations into a different slot of a
@@ -164,8 +165,9 @@ def run_b200(args):
     p_ring = [C.c_void_p(ring[s].data_ptr()) for s in range(RING)]
 
     def pair(slot, stream):
-        _lib.check(L.dq_policy_random_legal_next(h, p_legal, p_act, stream))
-        _lib.check(L.dq_env_step(h, p_act, p_ring[slot], p_rew, p_done, p_life, p_legal, 1, stream))
+        # random-legal pick + env step in ONE launch (dq_env_step_random; tests/test_env_gpu.py checks it equals
+        # dq_policy_random_legal_next followed by dq_env_step bit for bit)
+        _lib.check(L.dq_env_step_random(h, p_ring[slot], p_rew, p_done, p_life, p_legal, p_act, 1, stream))
 
     cur = lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     env.reset()
@@ -225,9 +227,8 @@ def run_b200(args):
         torch.cuda._sleep(int(25e-3 * 1.9e9))
         st = cur()
         for i in range(nprof):
-            _lib.check(L.dq_policy_random_legal_next(h, p_legal, p_act, st))
             evs[i][0].record()
-            _lib.check(L.dq_env_step(h, p_act, p_ring[i % RING], p_rew, p_done, p_life, p_legal, 1, st))
+            _lib.check(L.dq_env_step_random(h, p_ring[i % RING], p_rew, p_done, p_life, p_legal, p_act, 1, st))
             evs[i][1].record()
         torch.cuda.synchronize()
         durs = sorted(a.elapsed_time(b) * 1e-3 for a, b in evs)
@@ -346,13 +347,13 @@ def run_b200(args):
                            "l2": "each step writes its %.1f MB of observations into one of %d ring slots (%.0f MB > L2), "
                                  "so no step's writes are absorbed by the previous step's lines" % (
                                      ring[0].numel() / 1e6, RING, ring.numel() / 1e6),
-                           "launch": "CUDA graph of %d (policy, env-step) kernel pairs" % RING,
+                           "launch": "CUDA graph of %d env-step launches, each with the random-legal pick fused into its first phase" % RING,
                            "parallelism": "lattices sharded by rank, no data-path collective"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": ke, "api": "dq_env_step_host (pinned host actions in, all outputs to pinned host buffers)",
                         "policy": "uniform random action indices pre-generated on the host"},
-                "gpu_launches": 2 * K,
+                "gpu_launches": K,
                 "roofline": roof, "cpu_baseline": cb, "dqn": dqn}
         print(json.dumps(line), flush=True)
     env.close()

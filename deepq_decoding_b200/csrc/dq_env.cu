@@ -188,7 +188,7 @@ template <int D, bool RESET>
 __global__ void __launch_bounds__(kThreads, 896 / kThreads)
 env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t* __restrict__ obs,
                 float* __restrict__ reward, uint8_t* __restrict__ done_out, int32_t* __restrict__ lifetime,
-                u64* __restrict__ legal, int auto_reset) {
+                u64* __restrict__ legal, int auto_reset, u32* __restrict__ policy_ctr, int32_t* __restrict__ actions_out) {
     typedef Lat<D> L;
     constexpr u32 FULL = 0xffffffffu;
     constexpr int PW = L::PW, G = L::G, H = L::H;
@@ -229,11 +229,40 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             meta = p.state[ROW_META * np + e];
             int actbit = -1;
             if (!RESET) {
-                int a = live ? actions[e] : p.A - 1;
+                int a = (live && actions) ? actions[e] : p.A - 1;
                 xb = p.state[ROW_XB * np + e];
                 zb = p.state[ROW_ZB * np + e];
 #pragma unroll
                 for (int l = 0; l < 3; ++l) if (l < p.layers) act[l] = p.state[(ROW_ACT + l) * np + e];
+                if (policy_ctr && live) {
+                    // built-in random-legal policy (dq_env_step_random): the pick dq_policy_random_legal would make
+                    // on this lattice's current legal set, with the step index read from device memory
+                    const u32 step = *reinterpret_cast<volatile u32*>(policy_ctr);
+                    const u64 lq0 = qubits_grid_to_compact<D>(qubits_adjacent_to<D>(sum_pref) | qubits_neighbours_of<D>(act[0] | act[1] | act[2]));
+                    u64 mw[3] = {0, 0, 0};
+#pragma unroll
+                    for (int l = 0; l < 3; ++l) {
+                        if (l < p.layers) {
+                            const int o = l * L::NQ, i = o >> 6, sh = o & 63;
+                            mw[i] |= lq0 << sh;
+                            if (sh && i + 1 < 3) mw[i + 1] |= lq0 >> (64 - sh);
+                        }
+                    }
+                    const int ib = p.A - 1;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) if (i == (ib >> 6)) mw[i] |= 1ull << (ib & 63);
+                    const int cnt = popc64(mw[0]) + popc64(mw[1]) + popc64(mw[2]);
+                    const Philox4 u = philox4x32_10(p.env_id_base + (u32)e, step, 0u, 1u, p.k0, p.k1);
+                    int pick = (int)mulhi32(u.x, (u32)cnt);
+                    a = ib;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const int c = popc64(mw[i]);
+                        if (pick >= 0 && pick < c) { a = i * 64 + select64(mw[i], pick); pick = -1; }
+                        else if (pick >= 0) pick -= c;
+                    }
+                    if (actions_out) actions_out[e] = a;
+                }
                 if (a < 0 || a >= p.A) a = p.A - 1;
                 const bool ident = (a == p.A - 1);
                 const int layer = ident ? 0 : a / L::NQ, q = ident ? 0 : a % L::NQ;
@@ -408,6 +437,8 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         for (long long b = ((long long)units << 4) + tid; b < vbytes; b += kThreads)
             out[b] = (uint8_t)((bits[b >> 5] >> (b & 31)) & 1u);
     }
+    // built-in policy: the last CTA to finish advances the step index (every CTA read it in phase A, before its first barrier)
+    if (policy_ctr && tid == 0 && atomicAdd(policy_ctr + 1, 1u) == gridDim.x - 1) { policy_ctr[1] = 0; atomicAdd(policy_ctr, 1u); }
 }
 
 // Uniform pick over the sorted legal actions.  `ctr` (optional) = {step index, finished-CTA count} in
@@ -600,14 +631,14 @@ extern "C" int dq_env_set_referee_lut(dq_env* e, int mode, const void* lut_a, in
 
 template <bool RESET>
 static int launch_env(dq_env* e, const int32_t* actions, uint8_t* obs, float* reward, uint8_t* done, int32_t* lifetime,
-                      u64* legal, int auto_reset, cudaStream_t st) {
+                      u64* legal, int auto_reset, cudaStream_t st, u32* pctr = nullptr, int32_t* aout = nullptr) {
     const EnvParams& p = e->p;
     if (obs && (reinterpret_cast<uintptr_t>(obs) & 15)) return fail(DQ_EINVAL, "obs must be 16-byte aligned");
     const dim3 grid(p.npad / kEpc), block(kThreads);
     switch (p.d) {
-        case 3: env_step_kernel<3, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset); break;
-        case 5: env_step_kernel<5, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset); break;
-        case 7: env_step_kernel<7, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset); break;
+        case 3: env_step_kernel<3, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout); break;
+        case 5: env_step_kernel<5, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout); break;
+        case 7: env_step_kernel<7, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout); break;
     }
     g_launches.fetch_add(1);
     DQ_CUDA(cudaGetLastError());
@@ -626,6 +657,14 @@ extern "C" int dq_env_step(dq_env* e, const int32_t* actions, uint8_t* obs, floa
     if (e->p.ref_mode < 0) return fail(DQ_ESTATE, "no referee set: call dq_env_set_referee_lut first (the reference needs static_decoder too)");
     DeviceGuard g(e->device);
     return launch_env<false>(e, actions, obs, reward, done, lifetime, (u64*)legal, auto_reset, (cudaStream_t)stream);
+}
+
+extern "C" int dq_env_step_random(dq_env* e, uint8_t* obs, float* reward, uint8_t* done, int32_t* lifetime, uint64_t* legal,
+                                  int32_t* actions_out, int auto_reset, dq_stream stream) {
+    if (!e) return fail(DQ_EINVAL, "env is NULL");
+    if (e->p.ref_mode < 0) return fail(DQ_ESTATE, "no referee set: call dq_env_set_referee_lut first");
+    DeviceGuard g(e->device);
+    return launch_env<false>(e, nullptr, obs, reward, done, lifetime, (u64*)legal, auto_reset, (cudaStream_t)stream, e->policy_ctr, actions_out);
 }
 
 static int ensure_staging(dq_env* e) {

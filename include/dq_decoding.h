@@ -101,6 +101,12 @@ int dq_env_reset(dq_env* env, uint8_t* obs, uint64_t* legal_mask, dq_stream stre
 int dq_env_step(dq_env* env, const int32_t* actions, uint8_t* obs, float* reward, uint8_t* done,
                 int32_t* lifetime, uint64_t* legal_mask, int auto_reset, dq_stream stream);
 
+/* dq_env_step with the uniform random-legal policy built in: every lattice draws its own action exactly as
+ * dq_policy_random_legal_next would (same Philox word, step index = the handle's device-side counter, advanced by
+ * the launch), then steps.  One kernel per (policy, step) pair; actions_out (optional) receives the picks. */
+int dq_env_step_random(dq_env* env, uint8_t* obs, float* reward, uint8_t* done, int32_t* lifetime,
+                       uint64_t* legal_mask, int32_t* actions_out, int auto_reset, dq_stream stream);
+
 /* Same two calls with HOST buffers (the path bench.py's e2e number times). */
 int dq_env_reset_host(dq_env* env, uint8_t* h_obs, uint64_t* h_legal_mask);
 int dq_env_step_host(dq_env* env, const int32_t* h_actions, uint8_t* h_obs, float* h_reward,

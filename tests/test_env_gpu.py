@@ -153,6 +153,31 @@ def test_graph_capturable_policy_counter():
     env.close()
 
 
+def test_fused_random_policy_step_equals_policy_then_step():
+    """dq_env_step_random == dq_policy_random_legal_next followed by dq_env_step, bit for bit."""
+    import ctypes as C
+    import torch
+    from deepq_decoding_b200 import _lib
+    a, _ = make_pair(5, "DP", False, 5, 0.02, 1000, seed=21)
+    b, _ = make_pair(5, "DP", False, 5, 0.02, 1000, seed=21)
+    L = _lib.lib()
+    p = lambda x: C.c_void_p(x.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(a.reset(), b.reset())
+    for env in (a, b):
+        _lib.check(L.dq_policy_seek(env._h, 3, st))
+    picks = torch.zeros(1000, dtype=torch.int32, device="cuda")
+    acts = torch.zeros(1000, dtype=torch.int32, device="cuda")
+    for t in range(60):
+        _lib.check(L.dq_env_step_random(a._h, p(a.obs), p(a.reward), p(a.done), p(a.lifetime), p(a.legal_mask), p(picks), 1, st))
+        _lib.check(L.dq_policy_random_legal_next(b._h, p(b.legal_mask), p(acts), st))
+        _lib.check(L.dq_env_step(b._h, p(acts), p(b.obs), p(b.reward), p(b.done), p(b.lifetime), p(b.legal_mask), 1, st))
+        assert torch.equal(picks, acts), t
+        assert torch.equal(a.obs, b.obs) and torch.equal(a.legal_mask, b.legal_mask) and torch.equal(a.lifetime, b.lifetime), t
+        assert torch.equal(a.done, b.done) and torch.equal(a.reward, b.reward)
+    a.close(); b.close()
+
+
 def test_state_roundtrip_and_injection():
     """get_state/set_state: a restored handle continues bit-identically (checkpoint contract)."""
     import torch
