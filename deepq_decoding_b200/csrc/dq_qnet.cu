@@ -131,34 +131,39 @@ __device__ __forceinline__ int patch_col(const Patch& g, int k) {
 
 constexpr int TB = 64, TK = 16;        // 64x64 output tile, 16-deep steps, 256 threads, 4x4 per thread
 
-// Y[m][n] = act(sum_k A[m][k] W[k][n] + bias[n]);  act: 0 linear, 1 ReLU
+// Y[m][n] = act(sum_k A[m][k] W[k][n] + bias[n]);  act: 0 linear, 1 ReLU.  64 x 64 outputs per CTA, 256 threads, 4x4 per thread.
+// KS = depth of one k step: 16 for big grids (many CTAs hide each other's load latency), 64 when the grid is small and
+// every (load -> sync -> FMA -> sync) step is an exposed memory latency.
+template <int KS>
 __global__ void __launch_bounds__(256)
 gemm_fwd_kernel(const float* __restrict__ X, Patch g, const float* __restrict__ W, const float* __restrict__ bias,
                 float* __restrict__ Y, long long M, int N, int K, int act) {
-    __shared__ float As[TK][TB + 4], Bs[TK][TB + 4];
+    __shared__ float As[KS][TB + 4], Bs[KS][TB + 4];
     __shared__ long long rowoff[TB];
+    __shared__ int coloff[KS];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const long long m0 = (long long)blockIdx.x * TB;
     const int n0 = blockIdx.y * TB;
     if (tid < TB) rowoff[tid] = (m0 + tid < M) ? patch_row(g, m0 + tid) : -1;
-    __syncthreads();
     float acc[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += TK) {
+    for (int k0 = 0; k0 < K; k0 += KS) {
+        if (tid < KS) coloff[tid] = (k0 + tid < K) ? patch_col(g, k0 + tid) : -1;    // one division per k per CTA, not per element
+        __syncthreads();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {                  // A tile: 64 rows x 16 k
-            const int e = tid + i * 256, r = e >> 4, kk = e & 15, k = k0 + kk;
+        for (int i = 0; i < TB * KS / 256; ++i) {      // A tile: 64 rows x KS k
+            const int e = tid + i * 256, r = e / KS, kk = e % KS;
             float v = 0.f;
-            if (k < K && rowoff[r] >= 0) v = X[rowoff[r] + patch_col(g, k)];
+            if (coloff[kk] >= 0 && rowoff[r] >= 0) v = X[rowoff[r] + coloff[kk]];
             As[kk][r] = v;
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {                  // W tile: 16 k x 64 n
+        for (int i = 0; i < TB * KS / 256; ++i) {      // W tile: KS k x 64 n
             const int e = tid + i * 256, kk = e >> 6, c = e & 63, k = k0 + kk, n = n0 + c;
             Bs[kk][c] = (k < K && n < N) ? W[(long long)k * N + n] : 0.f;
         }
         __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < TK; ++kk) {
+#pragma unroll 16
+        for (int kk = 0; kk < KS; ++kk) {
             float a[4], b[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
@@ -190,19 +195,20 @@ gemm_dw_kernel(const float* __restrict__ X, Patch g, const float* __restrict__ d
                long long M, int N, int K, long long m_chunk) {
     __shared__ float As[TK][TB + 4], Bs[TK][TB + 4];
     __shared__ int coloff[TB];
+    __shared__ long long rowoff[TK];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int k0 = blockIdx.x * TB, n0 = blockIdx.y * TB;
     const long long mb = (long long)blockIdx.z * m_chunk, me = min(M, mb + m_chunk);
     if (tid < TB) coloff[tid] = (k0 + tid < K) ? patch_col(g, k0 + tid) : -1;
-    __syncthreads();
     float acc[4][4] = {};
     for (long long ms = mb; ms < me; ms += TK) {
+        if (tid < TK) rowoff[tid] = (ms + tid < me) ? patch_row(g, ms + tid) : -1;
+        __syncthreads();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                  // A^T tile: 16 m x 64 k
             const int e = tid + i * 256, mm = e >> 6, c = e & 63;
-            const long long m = ms + mm;
             float v = 0.f;
-            if (m < me && coloff[c] >= 0) v = X[patch_row(g, m) + coloff[c]];
+            if (rowoff[mm] >= 0 && coloff[c] >= 0) v = X[rowoff[mm] + coloff[c]];
             As[mm][c] = v;
         }
 #pragma unroll
@@ -237,10 +243,11 @@ gemm_dw_kernel(const float* __restrict__ X, Patch g, const float* __restrict__ d
 }
 
 // dX[patch(m,k)] (+)= sum_n dY[m][n] W[k][n];  overlapping patches (conv) accumulate atomically into a zeroed dX
+template <int NS>
 __global__ void __launch_bounds__(256)
 gemm_dx_kernel(const float* __restrict__ dY, const float* __restrict__ W, float* __restrict__ dX, Patch g,
                long long M, int N, int K, int overlap) {
-    __shared__ float As[TK][TB + 4], Bs[TK][TB + 4];
+    __shared__ float As[NS][TB + 4], Bs[NS][TB + 4];
     __shared__ long long rowoff[TB];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const long long m0 = (long long)blockIdx.x * TB;
@@ -248,20 +255,20 @@ gemm_dx_kernel(const float* __restrict__ dY, const float* __restrict__ W, float*
     if (tid < TB) rowoff[tid] = (m0 + tid < M) ? patch_row(g, m0 + tid) : -1;
     __syncthreads();
     float acc[4][4] = {};
-    for (int ns = 0; ns < N; ns += TK) {
+    for (int ns = 0; ns < N; ns += NS) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {                  // dY tile: 64 m x 16 n
-            const int e = tid + i * 256, r = e >> 4, nn = e & 15;
+        for (int i = 0; i < TB * NS / 256; ++i) {      // dY tile: 64 m x NS n
+            const int e = tid + i * 256, r = e / NS, nn = e % NS;
             As[nn][r] = (m0 + r < M && ns + nn < N) ? dY[(m0 + r) * N + ns + nn] : 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {                  // W^T tile: 16 n x 64 k
-            const int e = tid + i * 256, c = e >> 4, nn = e & 15;
+        for (int i = 0; i < TB * NS / 256; ++i) {      // W^T tile: NS n x 64 k
+            const int e = tid + i * 256, c = e / NS, nn = e % NS;
             Bs[nn][c] = (k0 + c < K && ns + nn < N) ? W[(long long)(k0 + c) * N + ns + nn] : 0.f;
         }
         __syncthreads();
-#pragma unroll
-        for (int nn = 0; nn < TK; ++nn) {
+#pragma unroll 16
+        for (int nn = 0; nn < NS; ++nn) {
             float a[4], b[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) { a[i] = As[nn][ty * 4 + i]; b[i] = Bs[nn][tx * 4 + i]; }
@@ -590,6 +597,22 @@ extern "C" int dq_qnet_pack_obs(dq_qnet* h, const uint8_t* obs, uint64_t* packed
     return DQ_OK;
 }
 
+static void launch_gemm_fwd(const float* X, const Patch& g, const float* W, const float* bias, float* Y, long long M, int N, int K,
+                            int act, cudaStream_t st) {
+    dim3 grid((unsigned)((M + 63) / 64), (N + 63) / 64);
+    if ((long long)grid.x * grid.y >= 2 * 148) gemm_fwd_kernel<16><<<grid, 256, 0, st>>>(X, g, W, bias, Y, M, N, K, act);
+    else gemm_fwd_kernel<64><<<grid, 256, 0, st>>>(X, g, W, bias, Y, M, N, K, act);
+    count_launch();
+}
+
+// rows per CTA of gemm_dw_kernel: enough slices of M that (k tiles x n tiles x slices) fills the GPU about four times over
+static long long dw_chunk(long long M, int K, int N) {
+    const long long tiles = (long long)((K + TB - 1) / TB) * ((N + TB - 1) / TB);
+    long long slices = std::max<long long>(1, std::min<long long>((M + 63) / 64, (592 + tiles - 1) / tiles));
+    long long chunk = (M + slices - 1) / slices;
+    return (chunk + TK - 1) / TK * TK;
+}
+
 static Patch conv_patch(const ConvL& L) { Patch g; g.P = L.P; g.oh = L.oh; g.ih = L.ih; g.cin = L.cin; g.ksz = L.ksz; g.stride = L.stride; return g; }
 static Patch dense_patch(int K) { Patch g; g.P = 1; g.oh = 1; g.ih = 1; g.cin = K; g.ksz = 1; g.stride = 1; return g; }
 
@@ -613,16 +636,12 @@ extern "C" int dq_qnet_forward(dq_qnet* h, const float* params, const uint64_t* 
     for (int l = 1; l < c.n_conv; ++l, ++t) {
         const ConvL& L = c.conv[l];
         const long long M = batch * L.P;
-        dim3 grid((unsigned)((M + TB - 1) / TB), (L.filters + TB - 1) / TB);
-        gemm_fwd_kernel<<<grid, 256, 0, st>>>(x, conv_patch(L), params + c.w_off[t], params + c.b_off[t], h->act_conv[l], M, L.filters, L.K, 1);
-        count_launch();
+        launch_gemm_fwd(x, conv_patch(L), params + c.w_off[t], params + c.b_off[t], h->act_conv[l], M, L.filters, L.K, 1, st);
         x = h->act_conv[l];
     }
     for (int i = 0; i < c.n_fc; ++i, ++t) {
         const int K = c.fc_in[i], N = c.fc_out[i];
-        dim3 grid((unsigned)((batch + TB - 1) / TB), (N + TB - 1) / TB);
-        gemm_fwd_kernel<<<grid, 256, 0, st>>>(x, dense_patch(K), params + c.w_off[t], params + c.b_off[t], h->act_fc[i], batch, N, K, i < c.n_hidden ? 1 : 0);
-        count_launch();
+        launch_gemm_fwd(x, dense_patch(K), params + c.w_off[t], params + c.b_off[t], h->act_fc[i], batch, N, K, i < c.n_hidden ? 1 : 0, st);
         if (train && c.drop[i] > 0.f) {
             const long long n = batch * N;
             dropout_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(h->act_fc[i], h->mask_fc[i], n, c.drop[i], (u32)dropout_seed, (u32)(dropout_seed >> 32), (u32)i);
@@ -666,12 +685,13 @@ extern "C" int dq_qnet_backward(dq_qnet* h, const float* params, const uint64_t*
         }
         const float* xin = i > 0 ? h->act_fc[i - 1] : h->act_conv[c.n_conv - 1];
         float* dxin = i > 0 ? h->dact_fc[i - 1] : h->dact_conv[c.n_conv - 1];
-        const long long chunk = 1024;
+        const long long chunk = dw_chunk(batch, K, N);
         dim3 gw((K + TB - 1) / TB, (N + TB - 1) / TB, (unsigned)((batch + chunk - 1) / chunk));
         gemm_dw_kernel<<<gw, 256, 0, st>>>(xin, dense_patch(K), dY, grads + c.w_off[t], batch, N, K, chunk);
         colsum_kernel<<<dim3((N + 31) / 32, (unsigned)std::min<long long>(64, (batch + 7) / 8)), 256, 0, st>>>(dY, grads + c.b_off[t], batch, N);
         dim3 gx((unsigned)((batch + TB - 1) / TB), (K + TB - 1) / TB);
-        gemm_dx_kernel<<<gx, 256, 0, st>>>(dY, params + c.w_off[t], dxin, dense_patch(K), batch, N, K, 0);
+        if ((long long)gx.x * gx.y >= 2 * 148 || N <= 16) gemm_dx_kernel<16><<<gx, 256, 0, st>>>(dY, params + c.w_off[t], dxin, dense_patch(K), batch, N, K, 0);
+        else gemm_dx_kernel<64><<<gx, 256, 0, st>>>(dY, params + c.w_off[t], dxin, dense_patch(K), batch, N, K, 0);
         count_launch(); count_launch(); count_launch();
     }
     // conv stack, last to second
@@ -680,14 +700,14 @@ extern "C" int dq_qnet_backward(dq_qnet* h, const float* params, const uint64_t*
         const long long M = batch * L.P, n = M * L.filters;
         float* dY = h->dact_conv[l];
         relu_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(dY, h->act_conv[l], nullptr, n);
-        const long long chunk = 4096;
+        const long long chunk = dw_chunk(M, L.K, L.filters);
         dim3 gw((L.K + TB - 1) / TB, (L.filters + TB - 1) / TB, (unsigned)((M + chunk - 1) / chunk));
         gemm_dw_kernel<<<gw, 256, 0, st>>>(h->act_conv[l - 1], conv_patch(L), dY, grads + c.w_off[l], M, L.filters, L.K, chunk);
         colsum_kernel<<<dim3((L.filters + 31) / 32, (unsigned)std::min<long long>(64, (M + 7) / 8)), 256, 0, st>>>(dY, grads + c.b_off[l], M, L.filters);
         const ConvL& Lp = c.conv[l - 1];
         QCUDA(cudaMemsetAsync(h->dact_conv[l - 1], 0, (size_t)batch * Lp.P * Lp.filters * sizeof(float), st));
         dim3 gx((unsigned)((M + TB - 1) / TB), (L.K + TB - 1) / TB);
-        gemm_dx_kernel<<<gx, 256, 0, st>>>(dY, params + c.w_off[l], h->dact_conv[l - 1], conv_patch(L), M, L.filters, L.K, 1);
+        gemm_dx_kernel<16><<<gx, 256, 0, st>>>(dY, params + c.w_off[l], h->dact_conv[l - 1], conv_patch(L), M, L.filters, L.K, 1);
         count_launch(); count_launch(); count_launch(); count_launch();
     }
     {   // layer 1
@@ -1143,10 +1163,9 @@ extern "C" int dq_qnet_forward_tc(dq_qnet* h, const float* params, const uint64_
             head_dueling_kernel<64><<<(unsigned)((batch + 127) / 128), 128, smem, st>>>(xf, params + c.w_off[t], params + c.b_off[t], q_out, batch, K, N, c.A, 1);
             count_launch();
         } else {
-            dim3 grid((unsigned)((batch + TB - 1) / TB), (N + TB - 1) / TB);
-            gemm_fwd_kernel<<<grid, 256, 0, st>>>(xf, dense_patch(K), params + c.w_off[t], params + c.b_off[t], h->act_fc[i], batch, N, K, 0);
+            launch_gemm_fwd(xf, dense_patch(K), params + c.w_off[t], params + c.b_off[t], h->act_fc[i], batch, N, K, 0, st);
             dueling_fwd_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(h->act_fc[i], q_out, batch, c.A);
-            count_launch(); count_launch();
+            count_launch();
         }
     } else {
         QCUDA(cudaMemcpyAsync(q_out, xf, (size_t)batch * c.A * sizeof(float), cudaMemcpyDeviceToDevice, st));
