@@ -164,7 +164,7 @@ class DQNAgent:
     def __init__(self, model, nb_actions, memory, nb_steps_warmup=1000, target_model_update=10000, policy=None,
                  test_policy=None, gamma=0.99, enable_dueling_network=False, enable_double_dqn=True, batch_size=32,
                  train_interval=1, memory_interval=1, delta_clip=np.inf, dueling_type="avg", updates_per_step=1,
-                 seed=0, device="cuda:0", flush_interval=64, process_group=None, act_precision="fp32"):
+                 seed=0, device="cuda:0", flush_interval=64, process_group=None, act_precision="fp32", target_precision="fp32"):
         if not enable_double_dqn:
             raise NotImplementedError("the reference always runs double DQN (keras-rl default)")
         if dueling_type != "avg" or delta_clip != np.inf or memory_interval != 1:
@@ -179,6 +179,7 @@ class DQNAgent:
         self.seed, self.device, self.flush_interval = int(seed), torch.device(device), int(flush_interval)
         self.process_group = process_group          # torch.distributed group for the gradient all-reduce (None = single GPU)
         self.act_precision = act_precision          # "fp32" (SIMT) or "bf16" (tcgen05 tensor cores) for action selection; updates are always fp32
+        self.target_precision = target_precision    # precision of the two no-grad forwards on s' inside an update (Q_online, Q_target)
         self.optimizer = None
         self.model = None                           # QNetwork, built in compile()
         self.step, self.updates = 0, 0
@@ -194,6 +195,11 @@ class DQNAgent:
             self.model.load_weights(s._weights_path)
         n = self.model.num_params
         self.target_params = self.model.params.clone()
+        self.target_model = None
+        if self.target_precision == "bf16":         # the target network needs its own handle for its staged bf16 weights
+            self.target_model = QNetwork(s.cc_layers, s.ff_layers, s.input_shape, s.num_actions, dueling=self.dueling,
+                                         max_batch=self.batch_size, device=self.device, seed=self.seed)
+            self.target_model.params = self.target_params
         self.grads = torch.zeros(n, dtype=torch.float32, device=self.model.device)
         self.adam_m, self.adam_v = torch.zeros_like(self.grads), torch.zeros_like(self.grads)
         B, A, rows, dev = self.batch_size, self.nb_actions, self.model.packed_rows, self.model.device
@@ -214,9 +220,30 @@ class DQNAgent:
     def load_weights(self, path):
         self.model.load_weights(path)
         self.target_params.copy_(self.model.params)
+        if getattr(self, "target_model", None) is not None:
+            self.target_model.params_changed()
 
     def save_weights(self, path, overwrite=True):
         self.model.save_weights(path, overwrite)
+
+    def save_memory(self, path=None):
+        """The reference pickles `dqn.memory` to memory.p (SPTS:156-157); here the replay ring's tensors (CPU copies).
+        Returns the snapshot dict; with `path` also torch.save()s it."""
+        snap = None if self.memory.ring is None else self.memory.ring.state_dict()
+        if path is not None and snap is not None:
+            torch.save(snap, path)
+        return snap
+
+    def load_memory(self, snap_or_path, env):
+        """Restore a replay snapshot taken with the same number of lattices and ring capacity (the continue scripts load
+        memory.p before fit, Single_Point_Continue_Training_Script.py:109-136)."""
+        snap = torch.load(snap_or_path, weights_only=False) if isinstance(snap_or_path, str) else snap_or_path
+        if snap is None:
+            return
+        v = _vec(env)
+        cap, rows, npad = snap["obs"].shape
+        self.memory.ring = ReplayRing(cap, rows, npad, v.n_envs, self.model.device)
+        self.memory.ring.load_state_dict(snap)
 
     def _st(self):
         return C.c_void_p(torch.cuda.current_stream(self.model.device).cuda_stream)
@@ -256,8 +283,12 @@ class DQNAgent:
         """backward() of keras-rl for one batch of packed transitions (all device tensors)."""
         B, A, st, m = s0.shape[1], self.nb_actions, self._st(), self.model
         p = lambda t: C.c_void_p(t.data_ptr())
-        m.forward_packed(s1.data_ptr(), B, B, out=self._qo[:B])
-        m.forward_packed(s1.data_ptr(), B, B, out=self._qt[:B], params=self.target_params)
+        if self.target_model is not None:
+            m.forward_packed(s1.data_ptr(), B, B, out=self._qo[:B], precision="bf16")
+            self.target_model.forward_packed(s1.data_ptr(), B, B, out=self._qt[:B], precision="bf16")
+        else:
+            m.forward_packed(s1.data_ptr(), B, B, out=self._qo[:B])
+            m.forward_packed(s1.data_ptr(), B, B, out=self._qt[:B], params=self.target_params)
         _lib.check(self.L.dq_dqn_targets(p(self._qo), p(self._qt), p(reward), p(terminal), self.gamma, B, A, p(self._y), st))
         self.updates += 1
         m.forward_packed(s0.data_ptr(), B, B, out=self._q[:B], train=True, dropout_seed=(self.seed << 20) ^ self.updates)
@@ -325,6 +356,8 @@ class DQNAgent:
                         upd_window += 1
             if (self.step // self.target_model_update) != ((self.step - N) // self.target_model_update):
                 self.target_params.copy_(self.model.params)
+                if self.target_model is not None:
+                    self.target_model.params_changed()
             if k == K - 1 or self.step >= nb_steps:
                 # ---- drain: episode bookkeeping on the host, in (iteration, lattice) order
                 rew, done, life = h_rew[:k + 1].cpu().numpy(), h_done[:k + 1].cpu().numpy(), h_life[:k + 1].cpu().numpy()

@@ -337,3 +337,20 @@ def test_tensor_core_forward_tracks_fp32():
     assert d < 0.5, d
     assert agree > 0.97, agree
     q.close()
+
+
+def test_curriculum_controller_and_memory_snapshot(tmp_path):
+    """Controller.py's loop in process: two error rates, two grid points each, weights + replay carried forward."""
+    import torch
+    from deepq_decoding_b200 import curriculum as CU
+    winners, carry = CU.iterative_training([0.001, 0.002], grid={"learning_rate": [1e-4, 5e-5]}, error_model="X", n_envs=512,
+                                           steps_per_point=3e5, test_episodes=256, out_dir=str(tmp_path), seed=3)
+    assert len(winners) >= 1 and winners[0]["p_phys"] == 0.001
+    assert all(set(w) >= {"p_phys", "config", "test_mean_lifetime", "test_se", "threshold", "beats_threshold"} for w in winners)
+    assert (tmp_path / "0.001" / "final_dqn_weights.h5f").exists()
+    if carry is not None:
+        assert carry["params"].numel() > 100000 and carry["memory"]["obs"].shape[1] == 12
+    # the saved weights load back into a fresh agent
+    from deepq_decoding_b200.h5lite import H5File
+    f = H5File(str(tmp_path / "0.001" / "final_dqn_weights.h5f"))
+    assert f["/conv2d_1/conv2d_1/kernel:0"].shape == (3, 3, 6, 64) and f["/dense_3/dense_3_1/kernel:0"].shape == (26, 27)
