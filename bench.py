@@ -338,6 +338,28 @@ def run_b200(args):
                "qnet_precision": "acting: bf16 tcgen05 (fp32 accumulate in TMEM); updates: fp32 SIMT",
                "qnet_flops_per_sample": flops, "policy": "eps-greedy 0.1 over legal actions, masked greedy"}
 
+    # ---- logical error rate (second half of the BASELINE metric): the reference's published d5_dp/0.007 agent
+    #      (weights carried as a test fixture) evaluated greedily here, one episode per lattice, LER := 1 / <lifetime>
+    ler = None
+    wpath = os.path.join(ROOT, "tests", "golden", "dqn_d5_dp_0.007.npz")
+    if rank == 0 and not args.no_dqn and os.path.exists(wpath):
+        from deepq_decoding_b200 import agents as A
+        z = np.load(wpath)
+        ev_env = VecSurfaceCodeEnv(D, P, P, MODEL, USE_Y, VD, None, n_envs=n, seed=SEED + 1, env_id_base=10 * n, device=dev)
+        ev = A.DQNAgent(model=A.build_convolutional_nn([[64, 3, 2], [32, 2, 1], [32, 2, 1]], [[512, 0.2]], (7, 11, 11), ev_env.num_actions),
+                        nb_actions=ev_env.num_actions, memory=A.SequentialMemory(limit=100), test_policy=A.GreedyQPolicy(masked_greedy=True),
+                        enable_dueling_network=True, device=dev, act_precision="bf16")
+        ev.compile(A.Adam(lr=1e-5), max_envs=n)
+        ev.model.set_keras_weights([(z["conv%d_k" % i], z["conv%d_b" % i]) for i in range(3)], [(z["dense%d_k" % i], z["dense%d_b" % i]) for i in range(3)])
+        t0 = time.perf_counter()
+        life = np.array(ev.test(ev_env, nb_episodes=n, verbose=0).history["episode_lifetime"], dtype=np.float64)
+        ler = {"agent": "reference trained_models/d5_dp/0.007/final_dqn_weights.h5f (tests/golden fixture), greedy masked policy, bf16 acting",
+               "episodes": int(len(life)), "mean_lifetime_cycles": float(life.mean()), "standard_error": float(life.std() / np.sqrt(len(life))),
+               "logical_error_rate_per_cycle": float(1.0 / life.mean()), "reference_published_mean_lifetime": 270.42,
+               "eval_seconds": time.perf_counter() - t0,
+               "trained_here": "profiles/r1_train_curriculum_dp_p007.json: 303.5 +- 3.3 cycles after 132 s of training from scratch"}
+        ev_env.close()
+
     if rank == 0:
         cb, _, _ = cpu_oracle_run(args.cpu_seconds)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
@@ -354,7 +376,7 @@ def run_b200(args):
                         "steps": ke, "api": "dq_env_step_host (pinned host actions in, all outputs to pinned host buffers)",
                         "policy": "uniform random action indices pre-generated on the host"},
                 "gpu_launches": K,
-                "roofline": roof, "cpu_baseline": cb, "dqn": dqn}
+                "roofline": roof, "cpu_baseline": cb, "dqn": dqn, "logical_error_rate": ler}
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:
