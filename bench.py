@@ -36,6 +36,13 @@ sys.path.insert(0, ROOT)
 
 D, VD, P, MODEL, USE_Y = 5, 5, 0.007, "DP", False
 N_PER_GPU = 16384
+# other BASELINE.json configs, selectable with --workload for the roofline report (the default, c3, is the one the metric is quoted on)
+WORKLOADS = {            # d, vd, p, model, lattices per GPU, algorithmic bytes per lattice-step
+    "c1": (3, 3, 0.05, "X", 1, 345),
+    "c2": (5, 5, 0.007, "X", 4096, 875),
+    "c3": (5, 5, 0.007, "DP", 16384, 996),
+    "c5": (7, 7, 0.011, "DP", 8192, 2310),
+}
 SEED = 2026
 RING = 16
 METRIC = "env-steps/sec at d=5 depolarising p=0.007"
@@ -237,15 +244,44 @@ def run_b200(args):
         achieved = n * BYTES_PER_STEP / mean_s / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "env_step_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and args.workload == "c3":
             try:
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roof = {"bound": "hbm", "kernel": "env_step_kernel<5,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": "env_step_kernel<%d,false>" % D, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_us_mean": mean_s * 1e6, "kernel_us_median": durs[len(durs) // 2] * 1e6,
                 "algorithmic_bytes_per_launch": n * BYTES_PER_STEP, "launches_timed": nprof}
+
+    # ---- the same kernel at larger lattice counts (extra evidence): at C3's 16 384 lattices a launch is bounded by the
+    #      latency of one CTA's dependent chain; the sweep shows where the kernel goes once a launch has enough tiles
+    scaling = None
+    if rank == 0 and not args.no_dqn:
+        scaling = []
+        peak, _ = measured_peak()
+        for nn in (16384, 65536, 262144, 1048576):
+            e2 = VecSurfaceCodeEnv(D, P, P, MODEL, USE_Y, VD, None, n_envs=nn, seed=SEED + 5, env_id_base=0, device=dev)
+            nbuf = max(2, int(300e6 // (nn * e2.obs[0].numel())) + 1)          # rotate observation buffers past the L2 size
+            bufs = [torch.zeros_like(e2.obs) for _ in range(nbuf)]
+            a2 = torch.zeros(nn, dtype=torch.int32, device=dev)
+            e2.reset()
+            args2 = (vp(e2.reward), vp(e2.done), vp(e2.lifetime), vp(e2.legal_mask), vp(a2))
+            for i in range(6):
+                _lib.check(L.dq_env_step_random(e2._h, vp(bufs[i % nbuf]), *args2, 1, cur()))
+            torch.cuda.synchronize()
+            a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 40
+            a_ev.record()
+            for i in range(reps):
+                _lib.check(L.dq_env_step_random(e2._h, vp(bufs[i % nbuf]), *args2, 1, cur()))
+            b_ev.record()
+            torch.cuda.synchronize()
+            t = a_ev.elapsed_time(b_ev) * 1e-3 / reps
+            scaling.append({"lattices": nn, "us_per_step": t * 1e6, "env_steps_per_s": nn / t,
+                            "achieved_GBps": nn * BYTES_PER_STEP / t / 1e9, "frac": nn * BYTES_PER_STEP / t / 1e9 / peak})
+            e2.close()
+            del bufs
 
     # ---- e2e: host buffers through dq_env_step_host (H2D actions, D2H every output, every step)
     ke = min(K, 64)
@@ -376,12 +412,21 @@ def run_b200(args):
                         "steps": ke, "api": "dq_env_step_host (pinned host actions in, all outputs to pinned host buffers)",
                         "policy": "uniform random action indices pre-generated on the host"},
                 "gpu_launches": K,
-                "roofline": roof, "cpu_baseline": cb, "dqn": dqn, "logical_error_rate": ler}
+                "roofline": roof, "roofline_scaling": scaling, "cpu_baseline": cb, "dqn": dqn, "logical_error_rate": ler}
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def select_workload(name):
+    global D, VD, P, MODEL, N_PER_GPU, BYTES_PER_STEP, WORKLOAD, METRIC
+    D, VD, P, MODEL, N_PER_GPU, BYTES_PER_STEP = WORKLOADS[name]
+    if name != "c3":
+        WORKLOAD = "%s: d=%d %s p_phys=p_meas=%g volume_depth=%d use_Y=False, %d lattices/GPU, random-legal policy, referee = %s" % (
+            name.upper(), D, MODEL, P, VD, N_PER_GPU, "shipped nn_d5_X_p5 tabulated" if D == 5 else "minimum-weight table")
+        METRIC = "env-steps/sec at d=%d %s p=%g" % (D, "depolarising" if MODEL == "DP" else "bit-flip", P)
 
 
 def main():
@@ -392,7 +437,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall budget of the cpu_baseline leg")
     ap.add_argument("--no-dqn", action="store_true", help="skip the DQN inner-loop measurements")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS), help="BASELINE.json config (default c3 = the metric's)")
     args = ap.parse_args()
+    select_workload(args.workload)
+    if args.workload != "c3":
+        args.no_dqn = True
     if args.impl == "reference":
         run_reference(args)
     else:

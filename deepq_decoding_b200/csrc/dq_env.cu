@@ -422,7 +422,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     if (obs) {
         const long long vbytes = (long long)nvalid * p.obs_bits;
         uint8_t* out = obs + (size_t)env0 * p.obs_bits;
-        const int units = (int)(vbytes >> 4);
+        const int units = (reinterpret_cast<uintptr_t>(obs) & 15) ? 0 : (int)(vbytes >> 4);   // unaligned caller buffer: byte stores only
 #pragma unroll 2
         for (int u = tid; u < units; u += kThreads) {
             const u32 word = bits[u >> 1];
@@ -633,7 +633,6 @@ template <bool RESET>
 static int launch_env(dq_env* e, const int32_t* actions, uint8_t* obs, float* reward, uint8_t* done, int32_t* lifetime,
                       u64* legal, int auto_reset, cudaStream_t st, u32* pctr = nullptr, int32_t* aout = nullptr) {
     const EnvParams& p = e->p;
-    if (obs && (reinterpret_cast<uintptr_t>(obs) & 15)) return fail(DQ_EINVAL, "obs must be 16-byte aligned");
     const dim3 grid(p.npad / kEpc), block(kThreads);
     switch (p.d) {
         case 3: env_step_kernel<3, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout); break;

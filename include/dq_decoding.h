@@ -21,7 +21,8 @@
  *
  * Shapes (N = n_envs, A = num_actions, C = volume_depth + action layers, H = 2d+1,
  * W = ceil(A/64)):
- *   obs        uint8  [N][C][H][H]   the reference's board_state (EN/Environments.py:91), 0/1 cells
+ *   obs        uint8  [N][C][H][H]   the reference's board_state (EN/Environments.py:91), 0/1 cells (any alignment;
+ *                                    16-byte aligned buffers get 128-bit stores)
  *   legal_mask uint64 [N][W]         bit a of word a/64 set  <=>  a in env.legal_actions
  *   actions    int32  [N]            action index as passed to env.step(); values outside [0,A) act as identity
  *   reward     float  [N]            1.0f / 0.0f   (EN/Environments.py:146-149)
