@@ -95,7 +95,7 @@ class FileLogger:
         n = len(history.get("episode", []))
         if force or self.interval is None or n - self._last >= self.interval:
             with open(self.filepath, "w") as f:
-                json.dump(history, f)
+                json.dump(history, f, default=lambda o: o.item() if hasattr(o, "item") else str(o))      # numpy scalars
             self._last = n
 
 

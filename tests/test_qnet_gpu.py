@@ -354,3 +354,37 @@ def test_curriculum_controller_and_memory_snapshot(tmp_path):
     from deepq_decoding_b200.h5lite import H5File
     f = H5File(str(tmp_path / "0.001" / "final_dqn_weights.h5f"))
     assert f["/conv2d_1/conv2d_1/kernel:0"].shape == (3, 3, 6, 64) and f["/dense_3/dense_3_1/kernel:0"].shape == (26, 27)
+
+
+def test_reference_script_shape_runs_on_single_lattice(tmp_path):
+    """The reference's own driver shape (Single_Point_Training_Script.py:92-160): the N=1 class with the reference's name,
+    build_convolutional_nn, DQNAgent(..., nb_steps_warmup, target_model_update, policy, test_policy, gamma,
+    enable_dueling_network), compile(Adam), fit(...) with the fork's keyword arguments and a FileLogger, save_weights, test."""
+    import json
+    from deepq_decoding_b200 import agents as A
+    from deepq_decoding_b200.envs import Surface_Code_Environment_Multi_Decoding_Cycles
+    env = Surface_Code_Environment_Multi_Decoding_Cycles(d=5, p_phys=0.01, p_meas=0.01, error_model="DP", use_Y=False, volume_depth=5,
+                                                         static_decoder=None)
+    model = A.build_convolutional_nn(REF_CC, REF_FF, env.observation_space.shape, env.num_actions)
+    memory = A.SequentialMemory(limit=5000, window_length=1)
+    policy = A.LinearAnnealedPolicy(A.EpsGreedyQPolicy(masked_greedy=False), attr="eps", value_max=1.0, value_min=0.02, value_test=0.0, nb_steps=300)
+    test_policy = A.GreedyQPolicy(masked_greedy=True)
+    dqn = A.DQNAgent(model=model, nb_actions=env.num_actions, memory=memory, nb_steps_warmup=100, target_model_update=200, policy=policy,
+                     test_policy=test_policy, gamma=0.99, enable_dueling_network=True)
+    dqn.compile(A.Adam(lr=1e-4))
+    log = str(tmp_path / "training_history.json")
+    history = dqn.fit(env, nb_steps=400, action_repetition=1, callbacks=[A.FileLogger(log, interval=10)], verbose=0, visualize=False,
+                      nb_max_start_steps=0, start_step_policy=None, log_interval=100, nb_max_episode_steps=None,
+                      episode_averaging_length=50, success_threshold=10000, stopping_patience=500, min_nb_steps=100, single_cycle=False)
+    assert dqn.step == 400 and dqn.updates == 300                       # one update per env step once step > nb_steps_warmup
+    logged = json.load(open(log))
+    assert set(logged) >= {"loss", "mean_q", "mean_eps", "episode_reward", "nb_episode_steps", "nb_steps", "episode_lifetimes_rolling_avg",
+                           "best_rolling_avg", "best_episode", "time_since_best", "has_succeeded", "stopped_improving", "episode", "duration"}
+    weights = str(tmp_path / "final_dqn_weights.h5f")
+    dqn.save_weights(weights, overwrite=True)
+    dqn.model.load_weights(weights)
+    env.p_phys = 0.02; env.p_meas = 0.02
+    th = dqn.test(env, nb_episodes=5, visualize=False, verbose=0, interval=10, single_cycle=False).history
+    assert len(th["episode_lifetime"]) == 5 and th["episode_lifetimes_rolling_avg"][-1] == pytest.approx(np.mean(th["episode_lifetime"]))
+    assert isinstance(dqn.forward(env.board_state), int)
+    env.close()
