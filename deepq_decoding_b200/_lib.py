@@ -60,6 +60,13 @@ _SIGNATURES = {
     "dq_dqn_loss_grad": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "dq_policy_eps_greedy": (_i, [_vp, _vp, _i64, _i, _i, _u32, _u64, _u32, _vp, _dbl, _i, _vp, _vp]),
     "dq_replay_sample": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i64, _i, _i, _i, _i64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dq_comm_create": (_i, [C.POINTER(_vp), _i, _i, _i64, _i]),
+    "dq_comm_destroy": (_i, [_vp]),
+    "dq_comm_handle": (_i, [_vp, _vp]),
+    "dq_comm_connect": (_i, [_vp, _vp]),
+    "dq_comm_next_grads": (_i, [_vp, C.POINTER(_vp)]),
+    "dq_comm_allreduce_adam": (_i, [_vp, _vp, _vp, _vp, _f, _f, _f, _f, _i64, _vp]),
+    "dq_comm_status": (_i, [_vp, C.POINTER(_i)]),
 }
 
 

@@ -164,7 +164,8 @@ class DQNAgent:
     def __init__(self, model, nb_actions, memory, nb_steps_warmup=1000, target_model_update=10000, policy=None,
                  test_policy=None, gamma=0.99, enable_dueling_network=False, enable_double_dqn=True, batch_size=32,
                  train_interval=1, memory_interval=1, delta_clip=np.inf, dueling_type="avg", updates_per_step=1,
-                 seed=0, device="cuda:0", flush_interval=64, process_group=None, act_precision="fp32", target_precision="fp32"):
+                 seed=0, device="cuda:0", flush_interval=64, process_group=None, act_precision="fp32", target_precision="fp32",
+                 collective="fused"):
         if not enable_double_dqn:
             raise NotImplementedError("the reference always runs double DQN (keras-rl default)")
         if dueling_type != "avg" or delta_clip != np.inf or memory_interval != 1:
@@ -178,6 +179,10 @@ class DQNAgent:
         self.batch_size, self.train_interval, self.updates_per_step = int(batch_size), int(train_interval), int(updates_per_step)
         self.seed, self.device, self.flush_interval = int(seed), torch.device(device), int(flush_interval)
         self.process_group = process_group          # torch.distributed group for the gradient all-reduce (None = single GPU)
+        if collective not in ("fused", "nccl"):
+            raise ValueError("collective must be 'fused' (one peer-memory all-reduce+Adam kernel) or 'nccl' (all_reduce, then Adam)")
+        self.collective = collective
+        self.comm = None
         self.act_precision = act_precision          # "fp32" (SIMT) or "bf16" (tcgen05 tensor cores) for action selection; updates are always fp32
         self.target_precision = target_precision    # precision of the two no-grad forwards on s' inside an update (Q_online, Q_target)
         self.optimizer = None
@@ -202,6 +207,11 @@ class DQNAgent:
             self.target_model.params = self.target_params
         self.grads = torch.zeros(n, dtype=torch.float32, device=self.model.device)
         self.adam_m, self.adam_v = torch.zeros_like(self.grads), torch.zeros_like(self.grads)
+        if self.process_group is not None and self.collective == "fused":
+            import torch.distributed as dist
+            if dist.get_world_size(self.process_group) > 1:
+                from .parallel import FusedAllreduceAdam
+                self.comm = FusedAllreduceAdam(n, self.model.device, self.process_group)
         B, A, rows, dev = self.batch_size, self.nb_actions, self.model.packed_rows, self.model.device
         self._s0 = torch.zeros((rows, B), dtype=torch.int64, device=dev)
         self._s1 = torch.zeros((rows, B), dtype=torch.int64, device=dev)
@@ -293,13 +303,18 @@ class DQNAgent:
         self.updates += 1
         m.forward_packed(s0.data_ptr(), B, B, out=self._q[:B], train=True, dropout_seed=(self.seed << 20) ^ self.updates)
         _lib.check(self.L.dq_dqn_loss_grad(p(self._q), p(actions), p(self._y), B, A, p(self._dq), p(self._stats), st))
+        o = self.optimizer
+        if self.comm is not None:          # gradient mean over the ranks fused with the Adam step (csrc/dq_comm.cu)
+            m.backward_packed(s0.data_ptr(), B, B, self._dq, self.comm.grads())
+            self.comm.step(m.params, self.adam_m, self.adam_v, o, self.updates, st)
+            m.params_changed()
+            return
         m.backward_packed(s0.data_ptr(), B, B, self._dq, self.grads)
         scale = 1.0
         if self.process_group is not None:
             import torch.distributed as dist
             dist.all_reduce(self.grads, group=self.process_group)
             scale = 1.0 / dist.get_world_size(self.process_group)
-        o = self.optimizer
         _lib.check(self.L.dq_adam_step(p(m.params), p(self.adam_m), p(self.adam_v), p(self.grads), m.num_params, o.lr, o.beta_1,
                                        o.beta_2, o.epsilon, self.updates, scale, st))
         m.params_changed()
@@ -388,6 +403,11 @@ class DQNAgent:
                         ep_reward[i], ep_steps[i] = 0.0, 0
                         episode += 1
                         stop = stop or succeeded or stopped
+                if self.process_group is not None:      # ranks must leave the loop together (every update is a collective)
+                    import torch.distributed as dist
+                    flag = torch.tensor([1 if stop else 0], dtype=torch.int32, device=dev)
+                    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.process_group)
+                    stop = bool(flag.item())
                 t_last = now
                 for cb in (callbacks or []):
                     if hasattr(cb, "on_flush"):
@@ -396,6 +416,8 @@ class DQNAgent:
                     print("step %d  episodes %d  rolling lifetime %.1f  best %.1f  eps %.3f  loss %.4g  mean_q %.3f  %.0f env-steps/s" % (
                         self.step, episode, win_sum / win_n, best_avg, eps, loss, mean_q,
                         self.step / max(1e-9, now - t_start)), flush=True)
+        if self.comm is not None:
+            self.comm.check()
         for cb in (callbacks or []):
             if hasattr(cb, "on_flush"):
                 cb.on_flush(hist.history, force=True)

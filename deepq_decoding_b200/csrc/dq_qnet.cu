@@ -27,6 +27,7 @@
 #include "../../include/dq_decoding.h"
 #include "dq_lattice.cuh"
 #include "dq_ptx.cuh"
+#include "dq_adam.cuh"
 
 namespace dq {
 
@@ -353,11 +354,9 @@ __global__ void dueling_bwd_kernel(const float* __restrict__ dq, float* __restri
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
                             long long n, float lr_t, float b1, float b2, float eps, float gscale) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float gi = g[i] * gscale;
-        const float mi = b1 * m[i] + (1.f - b1) * gi;
-        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi; v[i] = vi;
-        p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+        float pi = p[i], mi = m[i], vi = v[i];
+        dq::adam_update(pi, mi, vi, __fmul_rn(g[i], gscale), lr_t, b1, b2, eps);
+        p[i] = pi; m[i] = mi; v[i] = vi;
     }
 }
 // double-DQN target: y = r + gamma*(1-terminal)*Qt[argmax_a Qo[a]]   (ties -> lowest index)

@@ -6,6 +6,7 @@ GLOBAL index (`env_id_base = shard base`), so a sharded run draws exactly the no
 Acting and evaluation need no communication; training all-reduces the flat gradient buffer once per update
 (193 283 fp32 = 773 KB for the d=5 DP network) and evaluation sums (lifetime, episode) totals at the end.
 """
+import ctypes as C
 import os
 
 import torch
@@ -63,3 +64,59 @@ def reduce_lifetimes(lifetimes, group=None):
     mean = s / max(n, 1.0)
     var = max(s2 / max(n, 1.0) - mean * mean, 0.0)
     return mean, (var / max(n, 1.0)) ** 0.5, int(n)
+
+
+class FusedAllreduceAdam:
+    """Gradient mean over the ranks + Keras-2 Adam in ONE kernel per rank over NVLink peer memory (csrc/dq_comm.cu).
+
+    Replaces `dist.all_reduce(grads)` followed by `dq_adam_step`.  The 64-byte CUDA-IPC handles of the per-rank exchange
+    regions travel once through `torch.distributed` (plumbing); the data path never touches NCCL.  Usage per update:
+    `g = comm.grads()` -> backward writes this update's gradient into `g` -> `comm.step(params, m, v, optimizer, t, stream)`.
+    """
+
+    def __init__(self, n_params, device, group=None):
+        from . import _lib
+        self.L = _lib.lib()
+        self._lib = _lib
+        self.device = torch.device(device)
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n = int(n_params)
+        self._h = C.c_void_p()
+        _lib.check(self.L.dq_comm_create(C.byref(self._h), self.rank, self.world, self.n, self.device.index or 0))
+        mine = C.create_string_buffer(64)
+        _lib.check(self.L.dq_comm_handle(self._h, mine))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, bytes(mine.raw), group=group)
+        _lib.check(self.L.dq_comm_connect(self._h, C.create_string_buffer(b"".join(everyone), 64 * self.world)))
+        dist.barrier(group=group)              # every rank has mapped every region before the first signal is written
+
+    def grads(self):
+        """float32[n] view of the exchange buffer the NEXT update's gradient must be written to."""
+        from .qnet import device_view
+        ptr = C.c_void_p()
+        self._lib.check(self.L.dq_comm_next_grads(self._h, C.byref(ptr)))
+        return device_view(ptr.value, (self.n,), "<f4", self.device)
+
+    def step(self, params, m, v, optimizer, t, stream):
+        p = lambda x: C.c_void_p(x.data_ptr())
+        self._lib.check(self.L.dq_comm_allreduce_adam(self._h, p(params), p(m), p(v), optimizer.lr, optimizer.beta_1, optimizer.beta_2,
+                                                      optimizer.epsilon, int(t), stream))
+
+    def check(self):
+        """Raises if any wait on a peer timed out (the ranks fell out of step); synchronises the device."""
+        flag = C.c_int(0)
+        self._lib.check(self.L.dq_comm_status(self._h, C.byref(flag)))
+        if flag.value:
+            raise RuntimeError("fused all-reduce: a peer rank did not arrive (ranks out of step)")
+
+    def close(self):
+        if self._h:
+            self.L.dq_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

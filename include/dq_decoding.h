@@ -207,6 +207,28 @@ int dq_replay_sample(const uint64_t* ring_obs, const int32_t* ring_act, const fl
 /* Device pointer to the packed observation rows inside the env state (uint64 [C*PW][STATE_STRIDE]). */
 int dq_env_packed_obs(dq_env* env, uint64_t** dev_rows, int64_t* n_rows, int64_t* stride);
 
+/* ---- data-parallel training exchange (one process per GPU, NVLink peer memory) -------------------------------------
+ * The reference has no exchange step (one agent per process; cluster_scripts/Controller.py runs one Slurm job per
+ * hyper-parameter point).  Sharding the lattices of ONE run over the GPUs of a box adds exactly one: the mean of the
+ * flat gradient before the Adam step of DQNAgent.backward (Single_Point_Training_Script.py:119-130).  dq_comm does
+ * that mean and the Adam update in one kernel per rank, reading every rank's gradient through CUDA-IPC peer mappings.
+ *   create -> handle (64 bytes, exchange them out of band, e.g. torch.distributed.all_gather) -> connect;
+ *   per update: next_grads (where dq_qnet_backward must write this update's gradient) -> allreduce_adam.
+ * Every rank must call allreduce_adam the same number of times.  A rank whose peers do not arrive within ~20 s gives
+ * up waiting and sets the sticky flag dq_comm_status reports. */
+#define DQ_COMM_HANDLE_BYTES 64
+typedef struct dq_comm dq_comm;
+int dq_comm_create(dq_comm** out, int rank, int world, int64_t n_floats, int device);
+int dq_comm_destroy(dq_comm* comm);
+int dq_comm_handle(dq_comm* comm, void* handle64);
+int dq_comm_connect(dq_comm* comm, const void* handles /* world x 64 bytes, rank order */);
+int dq_comm_next_grads(dq_comm* comm, float** grads);
+/* params/m/v: this rank's flat buffers (n_floats, 16-byte aligned).  Same arithmetic as dq_adam_step on the rank-ordered
+ * mean of the gradients; t = 1-based update index. */
+int dq_comm_allreduce_adam(dq_comm* comm, float* params, float* m, float* v, float lr, float beta1, float beta2, float eps,
+                           int64_t t, dq_stream stream);
+int dq_comm_status(dq_comm* comm, int* timed_out);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t dq_launch_count(void);
 
