@@ -10,12 +10,14 @@ One "step" = one vectorised env step of every lattice: the policy kernel picks a
 from its legal mask, the env kernel advances all lattices and writes a fresh observation (both in one launch:
 dq_env_step_random).
 
-  value     all-GPU env-steps/s with everything resident in HBM; the K steps run as CUDA-graph replays
-            of 16 (policy, step) pairs, each pair writing its observations into a different slot of a
-            16-slot ring (222 MB > the 126 MB L2, so observation writes cannot be absorbed by L2)
-  roofline  env-step kernel only: algorithmic bytes per launch (996 B per lattice-step)
-            over its mean duration, measured with CUDA events around every launch of an eager pass
-            whose launches are queued behind a device-side delay so the events see back-to-back kernels
+  value     all-GPU env-steps/s with everything resident in HBM; the K steps run as rollout launches
+            (dq_env_rollout_random, 64 steps of every lattice per launch, bit-identical to single-step
+            launches), step s writing its observations into slot s % 16 of a 16-slot ring (222 MB > the
+            126 MB L2, so observation writes cannot be absorbed by L2) and row s of the per-step outputs;
+            `single_step_launches` repeats the K steps as one launch per step (CUDA graph of 16)
+  roofline  env-step kernel only: algorithmic bytes per launch (996 B per lattice-step x
+            lattices x steps per launch) over its mean duration, measured with CUDA events around every
+            launch of a pass queued behind a device-side delay so the events see back-to-back kernels
   e2e       the same steps through dq_env_step_host: actions come from pinned host memory, every output
             (observations, reward, done, lifetime, legal mask) is copied back to the host each step
   cpu_baseline / --impl reference
@@ -45,6 +47,7 @@ WORKLOADS = {            # d, vd, p, model, lattices per GPU, algorithmic bytes 
 }
 SEED = 2026
 RING = 16
+ROLL = 64          # env steps per rollout launch on the timed path
 METRIC = "env-steps/sec at d=5 depolarising p=0.007"
 UNIT = "env-steps/s"
 BYTES_PER_STEP = 996          # obs 847 + action 4 + reward 4 + done 1 + lifetime 4 + mask 8 + 2 x 64 state
@@ -181,7 +184,27 @@ def run_b200(args):
     _lib.check(L.dq_policy_seek(h, 0, cur()))
     torch.cuda.synchronize()
 
-    # CUDA graph of RING (policy, step) pairs
+    # ---- the timed path: multi-step rollout launches (dq_env_rollout_random, ROLL steps of every lattice per launch; bit-identical
+    #      to ROLL single-step launches, tests/test_env_gpu.py).  Step s writes its observations into ring slot (cursor+s) % RING
+    #      and row s of the per-step outputs, so every step still produces every output in HBM.
+    roll_out = [torch.empty((ROLL, n), dtype=dt, device=dev) for dt in (torch.float32, torch.uint8, torch.int32, torch.int32)]
+    roll_legal = torch.empty((ROLL, n, env.mask_words), dtype=torch.int64, device=dev)
+    state = {"cursor": 0, "launches": 0}
+
+    def rollout(steps):
+        _lib.check(L.dq_env_rollout_random(h, steps, vp(ring), RING, state["cursor"], vp(roll_out[0]), vp(roll_out[1]), vp(roll_out[2]),
+                                           vp(roll_legal), vp(roll_out[3]), 1, cur()))
+        state["cursor"] = (state["cursor"] + steps) % RING
+        state["launches"] += 1
+
+    def run_steps(k):
+        full, rest = divmod(k, ROLL)
+        for _ in range(full):
+            rollout(ROLL)
+        if rest:
+            rollout(rest)
+
+    # the older launch shape, kept as a second number: a CUDA graph of RING single-step launches
     side = torch.cuda.Stream(dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
@@ -194,7 +217,7 @@ def run_b200(args):
         for s in range(RING):
             pair(s, cur())
 
-    def run_steps(k):
+    def run_single_steps(k):
         full, rest = divmod(k, RING)
         for _ in range(full):
             graph.replay()
@@ -209,6 +232,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
+    state["launches"] = 0
     e0.record()
     run_steps(K)
     e1.record()
@@ -223,25 +247,35 @@ def run_b200(args):
     ms = float(ms.item())
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     value = world * n * K / (ms * 1e-3)
+    timed_launches = state["launches"]
+    # second number: the same K steps as single-step launches (one launch per step, replayed from a CUDA graph)
+    run_single_steps(RING)
+    torch.cuda.synchronize()
+    e0.record()
+    run_single_steps(K)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_single = e0.elapsed_time(e1)
+    single = {"value": n * K / (ms_single * 1e-3), "unit": UNIT + " on this rank", "ms_per_step": ms_single / K,
+              "launch": "CUDA graph of %d single-step launches (dq_env_step_random)" % RING}
 
-    # ---- roofline: per-launch duration of the env-step kernel, CUDA events around every launch.
+    # ---- roofline: per-launch duration of the env-step kernel, CUDA events around every rollout launch.
     # The launches are queued behind a ~25 ms device-side delay so that, when the GPU reaches them,
     # they run back to back and the event pairs bracket device time only (not Python launch gaps).
     roof = None
     if rank == 0:
-        nprof = 128
+        nprof = 24
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nprof)]
         torch.cuda._sleep(int(25e-3 * 1.9e9))
-        st = cur()
         for i in range(nprof):
             evs[i][0].record()
-            _lib.check(L.dq_env_step_random(h, p_ring[i % RING], p_rew, p_done, p_life, p_legal, p_act, 1, st))
+            rollout(ROLL)
             evs[i][1].record()
         torch.cuda.synchronize()
         durs = sorted(a.elapsed_time(b) * 1e-3 for a, b in evs)
         mean_s = sum(durs) / len(durs)
         peak, peak_src = measured_peak()
-        achieved = n * BYTES_PER_STEP / mean_s / 1e9
+        achieved = ROLL * n * BYTES_PER_STEP / mean_s / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "env_step_traffic.json")
         if os.path.exists(tpath) and args.workload == "c3":
@@ -252,7 +286,8 @@ def run_b200(args):
         roof = {"bound": "hbm", "kernel": "env_step_kernel<%d,false>" % D, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_us_mean": mean_s * 1e6, "kernel_us_median": durs[len(durs) // 2] * 1e6,
-                "algorithmic_bytes_per_launch": n * BYTES_PER_STEP, "launches_timed": nprof}
+                "algorithmic_bytes_per_launch": ROLL * n * BYTES_PER_STEP, "launches_timed": nprof, "steps_per_launch": ROLL,
+                "kernel_us_per_step": mean_s * 1e6 / ROLL}
 
     # ---- the same kernel at larger lattice counts (extra evidence): at C3's 16 384 lattices a launch is bounded by the
     #      latency of one CTA's dependent chain; the sweep shows where the kernel goes once a launch has enough tiles
@@ -262,26 +297,31 @@ def run_b200(args):
         peak, _ = measured_peak()
         for nn in (16384, 65536, 262144, 1048576):
             e2 = VecSurfaceCodeEnv(D, P, P, MODEL, USE_Y, VD, None, n_envs=nn, seed=SEED + 5, env_id_base=0, device=dev)
-            nbuf = max(2, int(300e6 // (nn * e2.obs[0].numel())) + 1)          # rotate observation buffers past the L2 size
-            bufs = [torch.zeros_like(e2.obs) for _ in range(nbuf)]
-            a2 = torch.zeros(nn, dtype=torch.int32, device=dev)
+            nbuf = max(2, int(300e6 // (nn * e2.obs[0].numel())) + 1)          # rotate observation slots past the L2 size
             e2.reset()
-            args2 = (vp(e2.reward), vp(e2.done), vp(e2.lifetime), vp(e2.legal_mask), vp(a2))
-            for i in range(6):
-                _lib.check(L.dq_env_step_random(e2._h, vp(bufs[i % nbuf]), *args2, 1, cur()))
+            ring2 = torch.zeros((nbuf,) + tuple(e2.obs.shape), dtype=torch.uint8, device=dev)
+            S2 = 16
+            o2 = [torch.empty((S2, nn), dtype=dt, device=dev) for dt in (torch.float32, torch.uint8, torch.int32, torch.int32)]
+            l2 = torch.empty((S2, nn, e2.mask_words), dtype=torch.int64, device=dev)
+
+            def roll2(i):
+                _lib.check(L.dq_env_rollout_random(e2._h, S2, vp(ring2), nbuf, (i * S2) % nbuf, vp(o2[0]), vp(o2[1]), vp(o2[2]), vp(l2),
+                                                   vp(o2[3]), 1, cur()))
+            for i in range(2):
+                roll2(i)
             torch.cuda.synchronize()
             a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 40
+            reps = 4
             a_ev.record()
             for i in range(reps):
-                _lib.check(L.dq_env_step_random(e2._h, vp(bufs[i % nbuf]), *args2, 1, cur()))
+                roll2(i)
             b_ev.record()
             torch.cuda.synchronize()
-            t = a_ev.elapsed_time(b_ev) * 1e-3 / reps
-            scaling.append({"lattices": nn, "us_per_step": t * 1e6, "env_steps_per_s": nn / t,
+            t = a_ev.elapsed_time(b_ev) * 1e-3 / (reps * S2)
+            scaling.append({"lattices": nn, "us_per_step": t * 1e6, "env_steps_per_s": nn / t, "steps_per_launch": S2,
                             "achieved_GBps": nn * BYTES_PER_STEP / t / 1e9, "frac": nn * BYTES_PER_STEP / t / 1e9 / peak})
+            del ring2, o2, l2
             e2.close()
-            del bufs
 
     # ---- e2e: host buffers through dq_env_step_host (H2D actions, D2H every output, every step)
     ke = min(K, 64)
@@ -405,13 +445,14 @@ def run_b200(args):
                            "l2": "each step writes its %.1f MB of observations into one of %d ring slots (%.0f MB > L2), "
                                  "so no step's writes are absorbed by the previous step's lines" % (
                                      ring[0].numel() / 1e6, RING, ring.numel() / 1e6),
-                           "launch": "CUDA graph of %d env-step launches, each with the random-legal pick fused into its first phase" % RING,
+                           "launch": "rollout launches of %d steps each (dq_env_rollout_random: random-legal pick + env step, every lattice "
+                                     "advanced %d steps per launch; bit-identical to single-step launches)" % (ROLL, ROLL),
                            "parallelism": "lattices sharded by rank, no data-path collective"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": ke, "api": "dq_env_step_host (pinned host actions in, all outputs to pinned host buffers)",
                         "policy": "uniform random action indices pre-generated on the host"},
-                "gpu_launches": K,
+                "gpu_launches": timed_launches, "single_step_launches": single,
                 "roofline": roof, "roofline_scaling": scaling, "cpu_baseline": cb, "dqn": dqn, "logical_error_rate": ler}
         print(json.dumps(line), flush=True)
     env.close()

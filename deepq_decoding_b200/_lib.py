@@ -36,6 +36,7 @@ _SIGNATURES = {
     "dq_env_reset": (_i, [_vp, _vp, _vp, _vp]),
     "dq_env_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "dq_env_step_random": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "dq_env_rollout_random": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "dq_env_reset_host": (_i, [_vp, _vp, _vp]),
     "dq_env_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "dq_env_get_state": (_i, [_vp, _vp, _vp]),

@@ -164,6 +164,12 @@ __device__ __forceinline__ u64 generate_volume(const EnvParams& p, u32* acc, int
     return f;
 }
 
+struct Rollout {            // multi-step launch: see env_step_kernel
+    int nsteps, slots, first_slot;
+    size_t slot_bytes;      // bytes between observation slots
+    size_t out_stride;      // elements between the per-step rows of reward / done / lifetime / actions (legal: x W)
+};
+
 struct Smem {
     u64 bm[kMaxLayers * 4][kEpc];     // freshly rendered layer bitmaps (valid where fresh[slot])
     u64 fx[kEpc], fz[kEpc], fmeta[kEpc];   // phase A -> B hand-off: frame planes, counters
@@ -186,9 +192,10 @@ template <int D> __device__ __forceinline__ u64 marker_word_rt(int i) {
 
 template <int D, bool RESET>
 __global__ void __launch_bounds__(kThreads, 896 / kThreads)
-env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t* __restrict__ obs,
-                float* __restrict__ reward, uint8_t* __restrict__ done_out, int32_t* __restrict__ lifetime,
-                u64* __restrict__ legal, int auto_reset, u32* __restrict__ policy_ctr, int32_t* __restrict__ actions_out) {
+env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t* __restrict__ obs0,
+                float* __restrict__ reward0, uint8_t* __restrict__ done0, int32_t* __restrict__ lifetime0,
+                u64* __restrict__ legal0, int auto_reset, u32* __restrict__ policy_ctr, int32_t* __restrict__ actions_out0,
+                const Rollout ro) {
     typedef Lat<D> L;
     constexpr u32 FULL = 0xffffffffu;
     constexpr int PW = L::PW, G = L::G, H = L::H;
@@ -201,6 +208,21 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     const int C = p.vd + p.layers;
     const int nvalid = min(kEpc, p.n - env0);
     const size_t np = (size_t)p.npad;
+    // built-in policy: every CTA reads the step index before its first barrier; the last CTA to finish advances it
+    const u32 step0 = policy_ctr ? *reinterpret_cast<volatile u32*>(policy_ctr) : 0u;
+
+    // A rollout (dq_env_rollout_random) runs ro.nsteps steps of this tile's lattices in one launch: lattices are independent,
+    // so a tile never waits for the slowest tile of the previous step.  Step s writes observation slot (first_slot+s) % slots
+    // and row s of the per-step outputs.  A single step is the nsteps == 1 case.
+    for (int rs = 0; rs < ro.nsteps; ++rs) {
+    uint8_t* const obs = obs0 ? obs0 + (size_t)((ro.first_slot + rs) % ro.slots) * ro.slot_bytes : nullptr;
+    const size_t oo = (size_t)rs * ro.out_stride;
+    float* const reward = reward0 ? reward0 + oo : nullptr;
+    uint8_t* const done_out = done0 ? done0 + oo : nullptr;
+    int32_t* const lifetime = lifetime0 ? lifetime0 + oo : nullptr;
+    int32_t* const actions_out = actions_out0 ? actions_out0 + oo : nullptr;
+    u64* const legal = legal0 ? legal0 + oo * p.W : nullptr;
+    if (rs) __syncthreads();            // the previous step's phase D has read the bit stream; its state stores are visible
 
     // ---- phase 0: prefetch the cached bitmap of this thread's (lattice, layer) pairs; clear scratch
     u64 bmw[kTaskIters][PW];
@@ -237,7 +259,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                 if (policy_ctr && live) {
                     // built-in random-legal policy (dq_env_step_random): the pick dq_policy_random_legal would make
                     // on this lattice's current legal set, with the step index read from device memory
-                    const u32 step = *reinterpret_cast<volatile u32*>(policy_ctr);
+                    const u32 step = step0 + (u32)rs;
                     const u64 lq0 = qubits_grid_to_compact<D>(qubits_adjacent_to<D>(sum_pref) | qubits_neighbours_of<D>(act[0] | act[1] | act[2]));
                     u64 mw[3] = {0, 0, 0};
 #pragma unroll
@@ -437,8 +459,8 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         for (long long b = ((long long)units << 4) + tid; b < vbytes; b += kThreads)
             out[b] = (uint8_t)((bits[b >> 5] >> (b & 31)) & 1u);
     }
-    // built-in policy: the last CTA to finish advances the step index (every CTA read it in phase A, before its first barrier)
-    if (policy_ctr && tid == 0 && atomicAdd(policy_ctr + 1, 1u) == gridDim.x - 1) { policy_ctr[1] = 0; atomicAdd(policy_ctr, 1u); }
+    }   // rollout step
+    if (policy_ctr && tid == 0 && atomicAdd(policy_ctr + 1, 1u) == gridDim.x - 1) { policy_ctr[1] = 0; atomicAdd(policy_ctr, (u32)ro.nsteps); }
 }
 
 // Uniform pick over the sorted legal actions.  `ctr` (optional) = {step index, finished-CTA count} in
@@ -631,13 +653,14 @@ extern "C" int dq_env_set_referee_lut(dq_env* e, int mode, const void* lut_a, in
 
 template <bool RESET>
 static int launch_env(dq_env* e, const int32_t* actions, uint8_t* obs, float* reward, uint8_t* done, int32_t* lifetime,
-                      u64* legal, int auto_reset, cudaStream_t st, u32* pctr = nullptr, int32_t* aout = nullptr) {
+                      u64* legal, int auto_reset, cudaStream_t st, u32* pctr = nullptr, int32_t* aout = nullptr,
+                      Rollout ro = Rollout{1, 1, 0, 0, 0}) {
     const EnvParams& p = e->p;
     const dim3 grid(p.npad / kEpc), block(kThreads);
     switch (p.d) {
-        case 3: env_step_kernel<3, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout); break;
-        case 5: env_step_kernel<5, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout); break;
-        case 7: env_step_kernel<7, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout); break;
+        case 3: env_step_kernel<3, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;
+        case 5: env_step_kernel<5, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;
+        case 7: env_step_kernel<7, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;
     }
     g_launches.fetch_add(1);
     DQ_CUDA(cudaGetLastError());
@@ -664,6 +687,20 @@ extern "C" int dq_env_step_random(dq_env* e, uint8_t* obs, float* reward, uint8_
     if (e->p.ref_mode < 0) return fail(DQ_ESTATE, "no referee set: call dq_env_set_referee_lut first");
     DeviceGuard g(e->device);
     return launch_env<false>(e, nullptr, obs, reward, done, lifetime, (u64*)legal, auto_reset, (cudaStream_t)stream, e->policy_ctr, actions_out);
+}
+
+extern "C" int dq_env_rollout_random(dq_env* e, int n_steps, uint8_t* obs_ring, int ring_slots, int first_slot, float* reward,
+                                     uint8_t* done, int32_t* lifetime, uint64_t* legal, int32_t* actions_out, int auto_reset,
+                                     dq_stream stream) {
+    if (!e) return fail(DQ_EINVAL, "env is NULL");
+    if (e->p.ref_mode < 0) return fail(DQ_ESTATE, "no referee set: call dq_env_set_referee_lut first");
+    if (n_steps < 1 || n_steps > 65536) return fail(DQ_EINVAL, "n_steps must be in [1, 65536]");
+    if (obs_ring && (ring_slots < 1 || first_slot < 0 || first_slot >= ring_slots)) return fail(DQ_EINVAL, "need ring_slots >= 1 and 0 <= first_slot < ring_slots");
+    DeviceGuard g(e->device);
+    Rollout ro;
+    ro.nsteps = n_steps; ro.slots = obs_ring ? ring_slots : 1; ro.first_slot = obs_ring ? first_slot : 0;
+    ro.slot_bytes = (size_t)e->p.n * e->p.obs_bits; ro.out_stride = (size_t)e->p.n;
+    return launch_env<false>(e, nullptr, obs_ring, reward, done, lifetime, (u64*)legal, auto_reset, (cudaStream_t)stream, e->policy_ctr, actions_out, ro);
 }
 
 static int ensure_staging(dq_env* e) {

@@ -166,6 +166,27 @@ class VecSurfaceCodeEnv:
                                                  _ptr(act), _stream(self.device)))
         return act
 
+    def rollout_random(self, n_steps, obs_ring=None, first_slot=0, keep=("reward", "done", "lifetime", "actions")):
+        """`n_steps` steps under the built-in uniform-random-legal policy in ONE launch (dq_env_rollout_random): the loop
+        `for _ in range(n_steps): env.step(random legal action)` of the reference, bit-identical to making the steps one by
+        one.  `obs_ring` uint8 [slots, N, C, H, H] (optional): step s fills slot (first_slot + s) % slots.  Returns a dict of
+        per-step device tensors [n_steps, N] (legal: [n_steps, N, W]) for the names in `keep`."""
+        n_steps, N, dev = int(n_steps), self.n_envs, self.device
+        mk = lambda name, shape, dt: torch.empty(shape, dtype=dt, device=dev) if name in keep else None
+        out = dict(reward=mk("reward", (n_steps, N), torch.float32), done=mk("done", (n_steps, N), torch.uint8),
+                   lifetime=mk("lifetime", (n_steps, N), torch.int32), legal=mk("legal", (n_steps, N, self.mask_words), torch.int64),
+                   actions=mk("actions", (n_steps, N), torch.int32))
+        slots = 1
+        if obs_ring is not None:
+            if obs_ring.dtype != torch.uint8 or not obs_ring.is_contiguous() or tuple(obs_ring.shape[1:]) != tuple(self.obs.shape):
+                raise ValueError("obs_ring must be a contiguous uint8 [slots, N, C, H, H] tensor")
+            slots = obs_ring.shape[0]
+        q = lambda x: C.c_void_p(0 if x is None else x.data_ptr())
+        _lib.check(self.L.dq_env_rollout_random(self._h, n_steps, q(obs_ring), slots, int(first_slot), q(out["reward"]), q(out["done"]),
+                                                q(out["lifetime"]), q(out["legal"]), q(out["actions"]), int(self.auto_reset),
+                                                _stream(self.device)))
+        return {k: v for k, v in out.items() if v is not None}
+
     # ---- host-buffer API (what the e2e benchmark times) ----
     def _host_buffers(self):
         if self._host is None:

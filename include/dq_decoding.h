@@ -107,6 +107,14 @@ int dq_env_step(dq_env* env, const int32_t* actions, uint8_t* obs, float* reward
  * the launch), then steps.  One kernel per (policy, step) pair; actions_out (optional) receives the picks. */
 int dq_env_step_random(dq_env* env, uint8_t* obs, float* reward, uint8_t* done, int32_t* lifetime,
                        uint64_t* legal_mask, int32_t* actions_out, int auto_reset, dq_stream stream);
+/* n_steps successive dq_env_step_random calls in ONE launch (bit-identical to making them one by one): lattices are
+ * independent, so each tile of lattices runs its n_steps without waiting for the slowest tile of every step.  This is
+ * the loop `for _ in range(n_steps): env.step(random legal action)` over Environments.py:118-204.
+ *   obs_ring   [ring_slots][N][C][H][H] or NULL: step s writes slot (first_slot + s) % ring_slots
+ *   reward, done, lifetime, actions_out   [n_steps][N] or NULL;  legal [n_steps][N][W] or NULL */
+int dq_env_rollout_random(dq_env* env, int n_steps, uint8_t* obs_ring, int ring_slots, int first_slot, float* reward,
+                          uint8_t* done, int32_t* lifetime, uint64_t* legal, int32_t* actions_out, int auto_reset,
+                          dq_stream stream);
 
 /* Same two calls with HOST buffers (the path bench.py's e2e number times). */
 int dq_env_reset_host(dq_env* env, uint8_t* h_obs, uint64_t* h_legal_mask);

@@ -178,6 +178,45 @@ def test_fused_random_policy_step_equals_policy_then_step():
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("d,model,n", [(5, "DP", 1000), (3, "X", 37), (7, "DP", 200)])
+def test_rollout_equals_single_steps_and_oracle(d, model, n):
+    """dq_env_rollout_random(n_steps) == n_steps x dq_env_step_random == the oracle stepping the same policy stream."""
+    import ctypes as C
+    import torch
+    from deepq_decoding_b200 import _lib
+    a, orc = make_pair(d, model, False, d, 0.03, n, seed=33)
+    b, _ = make_pair(d, model, False, d, 0.03, n, seed=33)
+    L = _lib.lib()
+    p = lambda x: C.c_void_p(x.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    obs0 = a.reset()
+    assert torch.equal(obs0, b.reset())
+    o_obs, o_legal = orc.reset()
+    assert np.array_equal(obs0.cpu().numpy(), o_obs)
+    S, slots = 23, 5
+    ring = torch.zeros((slots,) + tuple(a.obs.shape), dtype=torch.uint8, device="cuda")
+    step = 0
+    for rnd in range(2):                                     # the second rollout continues the first (policy counter, ring cursor)
+        first = (rnd * S) % slots
+        out = a.rollout_random(S, ring, first_slot=first, keep=("reward", "done", "lifetime", "actions", "legal"))
+        picks = torch.zeros(n, dtype=torch.int32, device="cuda")
+        for s in range(S):
+            _lib.check(L.dq_env_step_random(b._h, p(b.obs), p(b.reward), p(b.done), p(b.lifetime), p(b.legal_mask), p(picks), 1, st))
+            assert torch.equal(out["actions"][s], picks), (rnd, s)
+            assert torch.equal(out["reward"][s], b.reward) and torch.equal(out["done"][s], b.done) and torch.equal(out["lifetime"][s], b.lifetime)
+            assert torch.equal(out["legal"][s], b.legal_mask), (rnd, s)
+            if s >= S - slots:                               # the last `slots` steps are still in the ring
+                assert torch.equal(ring[(first + s) % slots], b.obs), (rnd, s)
+            # oracle on the same stream
+            o_act = orc.random_legal_actions(o_legal, step)
+            o_obs, o_rew, o_done, o_life, o_legal = orc.step(o_act)
+            assert np.array_equal(picks.cpu().numpy(), o_act) and np.array_equal(b.obs.cpu().numpy(), o_obs)
+            assert np.array_equal(out["lifetime"][s].cpu().numpy(), o_life) and np.array_equal(out["done"][s].cpu().numpy(), o_done)
+            step += 1
+        assert torch.equal(a.get_state_words(), b.get_state_words())
+    a.close(); b.close()
+
+
 def test_state_roundtrip_and_injection():
     """get_state/set_state: a restored handle continues bit-identically (checkpoint contract)."""
     import torch
