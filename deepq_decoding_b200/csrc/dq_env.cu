@@ -3,17 +3,19 @@
 // One CTA (4 warps) advances a tile of 16 independent lattices.  Per-lattice state is bit-packed into
 // uint64 rows of a [row][lattice] matrix that stays L2-resident between steps:
 // Pauli-frame planes, action boards, counters, AND the already-rendered (2d+1)^2-cell bitmap of every
-// observation layer, so that a step only re-renders what changed.  Phases (3 block barriers):
-//   0  every thread prefetches the cached layer bitmap of "its" (lattice, layer) pair
-//   A  warp 0, lane = lattice: apply the action to the Pauli frame, true syndrome by shifted XORs,
-//      homology label, referee table lookup, reward / done, heavy (identity | repeat) flag
+// observation layer, so that a step only re-renders what changed.  A launch runs one step (dq_env_step*) or a
+// rollout of many (dq_env_rollout_random); the tile's layer bitmaps are mirrored in shared memory for the whole
+// launch.  Per step (3 block barriers):
+//   A  warp 0, lane = lattice: (built-in random-legal pick,) apply the action to the Pauli frame, true syndrome
+//      by shifted XORs, homology label, referee table lookup, reward / done, heavy (identity | repeat) flag; a
+//      light step sets its one new cell in the action-layer bitmap
 //   B  warp per flagged lattice: draw a fresh syndrome volume (generate_volume) -- Philox4x32-10, one
 //      block per lane, fired draws folded into per-slice flip masks, warp prefix-XOR over slices --
 //      and re-render that lattice's layer bitmaps (lane per (slice, plaquette row))
-//   C  thread per (lattice, layer): OR the layer bitmap into the tile's contiguous observation bit
-//      stream in shared memory; layer-0 threads also emit the legal-move mask
-//   D  all threads: 16 stream bits -> 16 observation bytes, one aligned 128-bit store each (the tile's
-//      16 observations are one contiguous, 16-byte aligned span of HBM)
+//   C  thread per lattice: lifetime and legal-move mask
+//   D  thread per 32 bits of the tile's observation bit stream (the concatenation of its layer bitmaps): gather
+//      them from the bitmaps, expand to 32 bytes of 0/1, two aligned 128-bit stores (the tile's 16 observations
+//      are one contiguous, 16-byte aligned span of HBM)
 // Earlier variants (32-lattice tiles staged by TMA bulk copies; warp-autonomous 4/8-lattice groups) and
 // the ncu evidence that led here are summarised in profiles/README.md.
 //
@@ -40,7 +42,6 @@ constexpr int kThreads = DQ_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxVd = 8;
 constexpr int kMaxLayers = kMaxVd + 3;
-constexpr int kTaskIters = (kEpc * kMaxLayers + kThreads - 1) / kThreads;
 // The reference loops until a volume is non-trivial, forever if p_phys = p_meas = 0 on a clean frame.
 // A kernel must end: after this many attempts in one call the (trivial) volume is accepted.
 constexpr int kMaxAttemptsPerCall = 1 << 20;
@@ -56,6 +57,7 @@ struct EnvParams {
     int n, npad;                                // lattices, padded to 32
     int rounds;                                 // Philox rounds per volume attempt (B = 32*rounds)
     int obs_bits;                               // C*H*H
+    u32 ob_magic;                               // ceil(2^32 / obs_bits): g / obs_bits == umulhi(g, ob_magic) for g < 2^16
     u32 T, T1, T2, Tm;                          // thresholds (RNG contract)
     u32 k0, k1;                                 // Philox key
     u32 env_id_base;
@@ -73,16 +75,6 @@ __device__ __forceinline__ int referee_class(const EnvParams& p, u64 syn) {
     int c = lut2(p.lut_a, stabs_grid_to_type_index<D, 1>(syn)) & 1;
     if (p.model == DQ_MODEL_DP && p.lut_b) c |= (lut2(p.lut_b, stabs_grid_to_type_index<D, 0>(syn)) & 1) << 1;
     return c;
-}
-
-// OR a 64-bit value into a little-endian u32 bit stream in shared memory at a run-time bit offset
-__device__ __forceinline__ void stream_or64(u32* s, int off, u64 v) {
-    int w = off >> 5, sh = off & 31;
-    u32 v0 = (u32)v, v1 = (u32)(v >> 32);
-    u32 x0 = v0 << sh, x1 = __funnelshift_l(v0, v1, sh), x2 = __funnelshift_l(v1, 0u, sh);
-    if (x0) atomicOr(s + w, x0);
-    if (x1) atomicOr(s + w + 1, x1);
-    if (x2) atomicOr(s + w + 2, x2);
 }
 
 // A fired draw (rare: p ~ 1e-2 per draw) is folded into the per-slice flip accumulators of the warp,
@@ -171,15 +163,43 @@ struct Rollout {            // multi-step launch: see env_step_kernel
 };
 
 struct Smem {
-    u64 bm[kMaxLayers * 4][kEpc];     // freshly rendered layer bitmaps (valid where fresh[slot])
+    u64 bm[kMaxLayers * 4][kEpc];     // rendered bitmap of every observation layer of the tile's lattices (mirror of the state rows)
     u64 fx[kEpc], fz[kEpc], fmeta[kEpc];   // phase A -> B hand-off: frame planes, counters
     u64 sum[kEpc], acted[kEpc];       // OR of the volume's slices; OR of the action boards
     u32 acc[kWarps][3 * kMaxVd * 2];  // per-warp flip accumulators of generate_volume
-    int actbit[kEpc];                 // light step: (action layer << 16) | cell bit to set, else -1
     int32_t life_out[kEpc];
-    uint8_t task[kEpc], task_flags[kEpc], fresh[kEpc];
+    uint8_t task[kEpc], task_flags[kEpc];
     int ntask;
 };
+
+// 32 bits of the tile's observation bit stream starting at bit `o` of (lattice, layer): the stream is the concatenation of the
+// layer bitmaps (P bits each), lattice-major, so a 32-bit window touches at most two of them (P >= 49).
+template <int D>
+__device__ __forceinline__ u32 gather32(const Smem& sm, int lat, int layer, int o, int C) {
+    typedef Lat<D> L;
+    constexpr int PW = L::PW, P = L::P;
+    const int idx = o >> 6, sh = o & 63;
+    const u64 lo = sm.bm[layer * PW + idx][lat];
+    const u64 hi = (idx + 1 < PW) ? sm.bm[layer * PW + idx + 1][lat] : 0ull;
+    u32 v = (u32)(lo >> sh);
+    if (sh > 32) v |= (u32)(hi << (64 - sh));
+    const int n1 = P - o;                       // bits left in this layer (bits >= P of a bitmap are zero)
+    if (n1 < 32) {
+        int l2 = layer + 1, lat2 = lat;
+        if (l2 == C) { l2 = 0; lat2 = lat + 1; }
+        if (lat2 < kEpc) v |= (u32)sm.bm[l2 * PW][lat2] << n1;
+    }
+    return v;
+}
+
+__device__ __forceinline__ uint4 expand16(u32 h) {     // 16 bits -> 16 bytes of 0/1
+    uint4 v;
+    v.x = ((h & 0xFu) * 0x00204081u) & 0x01010101u;
+    v.y = (((h >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+    v.z = (((h >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+    v.w = (((h >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+    return v;
+}
 
 template <int D> __device__ __forceinline__ u64 marker_word_rt(int i) {
     switch (i) {
@@ -201,7 +221,6 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     constexpr int PW = L::PW, G = L::G, H = L::H;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-    u32* bits = reinterpret_cast<u32*>(smem_raw + ((sizeof(Smem) + 15) & ~size_t(15)));   // the tile's observation bit stream
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int env0 = blockIdx.x * kEpc;
@@ -211,35 +230,28 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     // built-in policy: every CTA reads the step index before its first barrier; the last CTA to finish advances it
     const u32 step0 = policy_ctr ? *reinterpret_cast<volatile u32*>(policy_ctr) : 0u;
 
+    // The rendered layer bitmaps and the summed syndrome of the tile's lattices live in shared memory for the whole launch
+    // (and in the state rows, kept in step): a step only re-renders what it changes.
+    for (int i = tid; i < C * PW * kEpc; i += kThreads) {
+        const int row = i / kEpc, slot = i - row * kEpc;
+        sm.bm[row][slot] = p.state[(ROW_BM + row) * np + env0 + slot];
+    }
+    if (tid < kEpc) sm.sum[tid] = p.state[ROW_SUM * np + env0 + tid];
+    __syncthreads();
+
     // A rollout (dq_env_rollout_random) runs ro.nsteps steps of this tile's lattices in one launch: lattices are independent,
     // so a tile never waits for the slowest tile of the previous step.  Step s writes observation slot (first_slot+s) % slots
     // and row s of the per-step outputs.  A single step is the nsteps == 1 case.
-    for (int rs = 0; rs < ro.nsteps; ++rs) {
-    uint8_t* const obs = obs0 ? obs0 + (size_t)((ro.first_slot + rs) % ro.slots) * ro.slot_bytes : nullptr;
-    const size_t oo = (size_t)rs * ro.out_stride;
+    int ring_slot = ro.first_slot;
+    size_t oo = 0;
+    for (int rs = 0; rs < ro.nsteps; ++rs, oo += ro.out_stride, ring_slot = (ring_slot + 1 == ro.slots) ? 0 : ring_slot + 1) {
+    uint8_t* const obs = obs0 ? obs0 + (size_t)ring_slot * ro.slot_bytes : nullptr;
     float* const reward = reward0 ? reward0 + oo : nullptr;
     uint8_t* const done_out = done0 ? done0 + oo : nullptr;
     int32_t* const lifetime = lifetime0 ? lifetime0 + oo : nullptr;
     int32_t* const actions_out = actions_out0 ? actions_out0 + oo : nullptr;
     u64* const legal = legal0 ? legal0 + oo * p.W : nullptr;
-    if (rs) __syncthreads();            // the previous step's phase D has read the bit stream; its state stores are visible
-
-    // ---- phase 0: prefetch the cached bitmap of this thread's (lattice, layer) pairs; clear scratch
-    u64 bmw[kTaskIters][PW];
-#pragma unroll
-    for (int it = 0; it < kTaskIters; ++it) {
-        const int t = it * kThreads + tid;
-#pragma unroll
-        for (int i = 0; i < PW; ++i)
-            bmw[it][i] = (t < kEpc * C) ? p.state[(ROW_BM + (t / kEpc) * PW + i) * np + env0 + t % kEpc] : 0ull;
-    }
-    const u64 sum_pref = (tid < kEpc) ? p.state[ROW_SUM * np + env0 + tid] : 0ull;
-    {
-        const int nvec = (kEpc * p.obs_bits + 31) / 32 / 4 + 1;
-        uint4* b4 = reinterpret_cast<uint4*>(bits);
-        for (int i = tid; i < nvec; i += kThreads) b4[i] = make_uint4(0, 0, 0, 0);
-        if (tid < kEpc) { sm.fresh[tid] = 0; sm.actbit[tid] = -1; }
-    }
+    if (rs) __syncthreads();            // the previous step has read the bitmaps; its state stores are visible
 
     // ---- phase A: warp 0, lane = lattice
     if (warp == 0) {
@@ -260,7 +272,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                     // built-in random-legal policy (dq_env_step_random): the pick dq_policy_random_legal would make
                     // on this lattice's current legal set, with the step index read from device memory
                     const u32 step = step0 + (u32)rs;
-                    const u64 lq0 = qubits_grid_to_compact<D>(qubits_adjacent_to<D>(sum_pref) | qubits_neighbours_of<D>(act[0] | act[1] | act[2]));
+                    const u64 lq0 = qubits_grid_to_compact<D>(qubits_adjacent_to<D>(sm.sum[lane]) | qubits_neighbours_of<D>(act[0] | act[1] | act[2]));
                     u64 mw[3] = {0, 0, 0};
 #pragma unroll
                     for (int l = 0; l < 3; ++l) {
@@ -321,13 +333,18 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                     p.state[ROW_ZB * np + e] = zb;
                     p.state[ROW_META * np + e] = meta;
                     if (!ident) p.state[(ROW_ACT + layer) * np + e] = layer == 0 ? act[0] : (layer == 1 ? act[1] : act[2]);
+                    if (actbit >= 0) {         // this step's action lights one more cell of its action layer
+                        const int pos = actbit & 0xFFFF, row = (p.vd + layer) * PW + (pos >> 6);
+                        const u64 wv = sm.bm[row][lane] | (1ull << (pos & 63));
+                        sm.bm[row][lane] = wv;
+                        p.state[(ROW_BM + row) * np + e] = wv;
+                    }
                 }
             } else if (live) {
                 flags = 2u;               // reset keeps only the attempt counter (the position in the random stream)
             }
             sm.fx[lane] = xb; sm.fz[lane] = zb; sm.fmeta[lane] = meta;
             sm.acted[lane] = act[0] | act[1] | act[2];
-            sm.actbit[lane] = flags ? -1 : actbit;
         }
         const u32 tmask = __ballot_sync(FULL, flags != 0);
         if (flags) {
@@ -363,7 +380,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             p.state[ROW_ZB * np + e] = bz;
             p.state[ROW_META * np + e] = meta_pack(life, attempts, dn);
             p.state[ROW_SUM * np + e] = summed;
-            sm.sum[slot] = summed; sm.acted[slot] = 0; sm.fresh[slot] = 1;
+            sm.sum[slot] = summed; sm.acted[slot] = 0;
             if (!RESET) sm.life_out[slot] = lo;
         }
         if (lane < p.layers) p.state[(ROW_ACT + lane) * np + e] = 0;
@@ -392,72 +409,49 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     }
     __syncthreads();
 
-    // ---- phase C: thread per (lattice, layer): layer bitmap into the tile's bit stream; legal mask
+    // ---- phase C: lifetime and legal mask (thread per lattice)
+    if (tid < nvalid) {
+        const int slot = tid;
+        if (lifetime && !RESET) lifetime[env0 + slot] = sm.life_out[slot];
+        if (legal) {
+            const u64 lq = qubits_grid_to_compact<D>(qubits_adjacent_to<D>(sm.sum[slot]) | qubits_neighbours_of<D>(sm.acted[slot]));
+            u64 mw[3] = {0, 0, 0};
 #pragma unroll
-    for (int it = 0; it < kTaskIters; ++it) {
-        const int t = it * kThreads + tid;
-        if (t >= kEpc * C) break;
-        const int slot = t % kEpc, layer = t / kEpc;
-        const bool fresh = sm.fresh[slot] != 0;
-        u64 w[PW];
-#pragma unroll
-        for (int i = 0; i < PW; ++i) w[i] = fresh ? sm.bm[layer * PW + i][slot] : bmw[it][i];
-        const int ab = sm.actbit[slot];
-        if (ab >= 0 && layer - p.vd == (ab >> 16)) {              // this step's action lights one more cell
-            const int pos = ab & 0xFFFF;
-#pragma unroll
-            for (int i = 0; i < PW; ++i)
-                if ((pos >> 6) == i) {
-                    w[i] |= 1ull << (pos & 63);
-                    p.state[(ROW_BM + layer * PW + i) * np + env0 + slot] = w[i];
+            for (int l = 0; l < 3; ++l) {
+                if (l < p.layers) {
+                    const int o = l * L::NQ, i = o >> 6, s = o & 63;
+                    mw[i] |= lq << s;
+                    if (s && i + 1 < 3) mw[i + 1] |= lq >> (64 - s);
                 }
-        }
-        const int off = slot * p.obs_bits + layer * L::P;
+            }
+            const int ib = p.A - 1;
 #pragma unroll
-        for (int i = 0; i < PW; ++i) stream_or64(bits, off + 64 * i, w[i]);
-        if (layer == 0 && slot < nvalid) {
-            if (lifetime && !RESET) lifetime[env0 + slot] = sm.life_out[slot];
-            if (legal) {
-                const u64 summed = fresh ? sm.sum[slot] : sum_pref;
-                const u64 lq = qubits_grid_to_compact<D>(qubits_adjacent_to<D>(summed) | qubits_neighbours_of<D>(sm.acted[slot]));
-                u64 mw[3] = {0, 0, 0};
-#pragma unroll
-                for (int l = 0; l < 3; ++l) {
-                    if (l < p.layers) {
-                        const int o = l * L::NQ, i = o >> 6, s = o & 63;
-                        mw[i] |= lq << s;
-                        if (s && i + 1 < 3) mw[i + 1] |= lq >> (64 - s);
-                    }
-                }
-                const int ib = p.A - 1;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    if (i == (ib >> 6)) mw[i] |= 1ull << (ib & 63);
-                    if (i < p.W) legal[(size_t)(env0 + slot) * p.W + i] = mw[i];
-                }
+            for (int i = 0; i < 3; ++i) {
+                if (i == (ib >> 6)) mw[i] |= 1ull << (ib & 63);
+                if (i < p.W) legal[(size_t)(env0 + slot) * p.W + i] = mw[i];
             }
         }
     }
-    __syncthreads();
 
-    // ---- phase D: 16 stream bits -> 16 observation bytes per 128-bit store
+    // ---- phase D: observation bytes.  Thread per 32 stream bits: gathered from the layer bitmaps, expanded to 32 bytes of 0/1,
+    //      two 128-bit stores (the tile's 16*C*H*H bytes start 16-byte aligned whenever the caller's buffer is)
     if (obs) {
-        const long long vbytes = (long long)nvalid * p.obs_bits;
+        const int vbytes = nvalid * p.obs_bits;
         uint8_t* out = obs + (size_t)env0 * p.obs_bits;
-        const int units = (reinterpret_cast<uintptr_t>(obs) & 15) ? 0 : (int)(vbytes >> 4);   // unaligned caller buffer: byte stores only
-#pragma unroll 2
-        for (int u = tid; u < units; u += kThreads) {
-            const u32 word = bits[u >> 1];
-            const u32 h = (u & 1) ? (word >> 16) : word;
-            uint4 v;
-            v.x = ((h & 0xFu) * 0x00204081u) & 0x01010101u;
-            v.y = (((h >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
-            v.z = (((h >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
-            v.w = (((h >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
-            *reinterpret_cast<uint4*>(out + ((size_t)u << 4)) = v;
+        const bool aligned = (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
+        for (int g = tid * 32; g < vbytes; g += kThreads * 32) {
+            const int lat = (int)__umulhi((u32)g, p.ob_magic);
+            const int r = g - lat * p.obs_bits;
+            const int layer = r / L::P, o = r - layer * L::P;
+            const u32 word = gather32<D>(sm, lat, layer, o, C);
+            if (aligned && g + 32 <= vbytes) {
+                *reinterpret_cast<uint4*>(out + g) = expand16(word);
+                *reinterpret_cast<uint4*>(out + g + 16) = expand16(word >> 16);
+            } else {
+                const int nb = min(32, vbytes - g);
+                for (int b = 0; b < nb; ++b) out[g + b] = (uint8_t)((word >> b) & 1u);
+            }
         }
-        for (long long b = ((long long)units << 4) + tid; b < vbytes; b += kThreads)
-            out[b] = (uint8_t)((bits[b >> 5] >> (b & 31)) & 1u);
     }
     }   // rollout step
     if (policy_ctr && tid == 0 && atomicAdd(policy_ctr + 1, 1u) == gridDim.x - 1) { policy_ctr[1] = 0; atomicAdd(policy_ctr, (u32)ro.nsteps); }
@@ -576,13 +570,14 @@ extern "C" int dq_env_create(dq_env** out, int d, int error_model, int use_Y, in
     const int items = volume_depth * (2 * d * d - 1);
     p.rounds = (items + 127) / 128;
     p.obs_bits = (volume_depth + p.layers) * (2 * d + 1) * (2 * d + 1);
+    p.ob_magic = (u32)((0x100000000ull + (u64)p.obs_bits - 1) / (u64)p.obs_bits);
     set_thresholds(p, p_phys, p_meas);
     p.k0 = (u32)seed; p.k1 = (u32)(seed >> 32);
     p.env_id_base = (u32)env_id_base;
     p.ref_mode = -1;
     e->device = device;
     e->state_rows = ROW_BM + (volume_depth + p.layers) * (((2 * d + 1) * (2 * d + 1) + 63) / 64);
-    e->smem_bytes = ((sizeof(Smem) + 15) & ~size_t(15)) + ((size_t)(kEpc * p.obs_bits + 31) / 32 / 4 + 2) * 16;
+    e->smem_bytes = (sizeof(Smem) + 15) & ~size_t(15);
     cudaError_t err = cudaMalloc(&p.state, (size_t)e->state_rows * p.npad * sizeof(u64));
     if (err != cudaSuccess) { delete e; return fail(DQ_ECUDA, std::string("cudaMalloc(state): ") + cudaGetErrorString(err)); }
     err = cudaMemset(p.state, 0, (size_t)e->state_rows * p.npad * sizeof(u64));
