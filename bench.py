@@ -11,7 +11,7 @@ from its legal mask, the env kernel advances all lattices and writes a fresh obs
 dq_env_step_random).
 
   value     all-GPU env-steps/s with everything resident in HBM; the K steps run as rollout launches
-            (dq_env_rollout_random, 64 steps of every lattice per launch, bit-identical to single-step
+            (dq_env_rollout_random, 256 steps of every lattice per launch, bit-identical to single-step
             launches), step s writing its observations into slot s % 16 of a 16-slot ring (222 MB > the
             126 MB L2, so observation writes cannot be absorbed by L2) and row s of the per-step outputs;
             `single_step_launches` repeats the K steps as one launch per step (CUDA graph of 16)
@@ -47,7 +47,7 @@ WORKLOADS = {            # d, vd, p, model, lattices per GPU, algorithmic bytes 
 }
 SEED = 2026
 RING = 16
-ROLL = 64          # env steps per rollout launch on the timed path
+ROLL = 256         # env steps per rollout launch on the timed path
 METRIC = "env-steps/sec at d=5 depolarising p=0.007"
 UNIT = "env-steps/s"
 BYTES_PER_STEP = 996          # obs 847 + action 4 + reward 4 + done 1 + lifetime 4 + mask 8 + 2 x 64 state
@@ -280,7 +280,7 @@ def run_b200(args):
         tpath = os.path.join(ROOT, "profiles", "env_step_traffic.json")
         if os.path.exists(tpath) and args.workload == "c3":
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tpath)).get("dram_bytes_per_step") * ROLL      # ncu capture of one rollout launch, per step
             except Exception:
                 traffic = None
         roof = {"bound": "hbm", "kernel": "env_step_kernel<%d,false>" % D, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -37,7 +37,13 @@ namespace dq {
 #ifndef DQ_THREADS
 #define DQ_THREADS 128
 #endif
-constexpr int kEpc = 16;                       // lattices per CTA: 16*L observation bytes are a multiple of 16 for every L
+#ifndef DQ_MIN_BLOCKS
+#define DQ_MIN_BLOCKS 7          // resident CTAs per SM the register allocation must allow
+#endif
+#ifndef DQ_EPC
+#define DQ_EPC 16
+#endif
+constexpr int kEpc = DQ_EPC;                       // lattices per CTA: 16*L observation bytes are a multiple of 16 for every L
 constexpr int kThreads = DQ_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxVd = 8;
@@ -211,7 +217,7 @@ template <int D> __device__ __forceinline__ u64 marker_word_rt(int i) {
 }
 
 template <int D, bool RESET>
-__global__ void __launch_bounds__(kThreads, 896 / kThreads)
+__global__ void __launch_bounds__(kThreads, DQ_MIN_BLOCKS)
 env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t* __restrict__ obs0,
                 float* __restrict__ reward0, uint8_t* __restrict__ done0, int32_t* __restrict__ lifetime0,
                 u64* __restrict__ legal0, int auto_reset, u32* __restrict__ policy_ctr, int32_t* __restrict__ actions_out0,

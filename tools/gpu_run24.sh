@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/pytest_all.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_all.log
+tail -5 gpurun_out/pytest_all.log
+timeout 200 python __graft_entry__.py smoke 2>&1 | tail -2
+timeout 600 python bench.py > gpurun_out/bench_v7.json 2> gpurun_out/bench_v7.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/bench_v7.json; tail -3 gpurun_out/bench_v7.err
+DQ_ONLY_ROLLOUT=64 timeout 600 ncu --set full --clock-control none --import-source on -k regex:env_step_kernel -s 4 -c 1 -o gpurun_out/r1_rollout64 python tools/prof_rollout.py > gpurun_out/ncu_ro.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/ncu_ro.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r1_launches_rollout.csv python bench.py --steps 1024 --warmup 16 --cpu-seconds 0.2 --no-dqn > gpurun_out/ncu1.log 2>&1; echo "ncu list rc=$?"
