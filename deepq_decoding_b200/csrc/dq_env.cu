@@ -174,6 +174,7 @@ struct Smem {
     u64 sum[kEpc], acted[kEpc];       // OR of the volume's slices; OR of the action boards
     u32 acc[kWarps][3 * kMaxVd * 2];  // per-warp flip accumulators of generate_volume
     int32_t life_out[kEpc];
+    int actbit[kEpc];                 // light step: (action layer << 16) | cell bit to set, else -1
     uint8_t task[kEpc], task_flags[kEpc];
     int ntask;
 };
@@ -216,6 +217,31 @@ template <int D> __device__ __forceinline__ u64 marker_word_rt(int i) {
     }
 }
 
+// Phase D: the tile's observation bytes.  Thread per 32 bits of the tile's observation bit stream: gathered from the layer
+// bitmaps, expanded to 32 bytes of 0/1, two 128-bit stores (the tile's 16*C*H*H bytes start 16-byte aligned whenever the
+// caller's buffer is).  Executed by threads [first, first + nthr) of the CTA.
+template <int D>
+__device__ __forceinline__ void write_observations(const Smem& sm, const EnvParams& p, uint8_t* obs, int env0, int nvalid, int C,
+                                                   int t, int nthr) {
+    typedef Lat<D> L;
+    const int vbytes = nvalid * p.obs_bits;
+    uint8_t* out = obs + (size_t)env0 * p.obs_bits;
+    const bool aligned = (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
+    for (int g = t * 32; g < vbytes; g += nthr * 32) {
+        const int lat = (int)__umulhi((u32)g, p.ob_magic);
+        const int r = g - lat * p.obs_bits;
+        const int layer = r / L::P, o = r - layer * L::P;
+        const u32 word = gather32<D>(sm, lat, layer, o, C);
+        if (aligned && g + 32 <= vbytes) {
+            *reinterpret_cast<uint4*>(out + g) = expand16(word);
+            *reinterpret_cast<uint4*>(out + g + 16) = expand16(word >> 16);
+        } else {
+            const int nb = min(32, vbytes - g);
+            for (int b = 0; b < nb; ++b) out[g + b] = (uint8_t)((word >> b) & 1u);
+        }
+    }
+}
+
 template <int D, bool RESET>
 __global__ void __launch_bounds__(kThreads, DQ_MIN_BLOCKS)
 env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t* __restrict__ obs0,
@@ -250,6 +276,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     // and row s of the per-step outputs.  A single step is the nsteps == 1 case.
     int ring_slot = ro.first_slot;
     size_t oo = 0;
+    uint8_t* obs_prev = nullptr;        // the previous step's observation slot: written while warp 0 runs this step's phase A
     for (int rs = 0; rs < ro.nsteps; ++rs, oo += ro.out_stride, ring_slot = (ring_slot + 1 == ro.slots) ? 0 : ring_slot + 1) {
     uint8_t* const obs = obs0 ? obs0 + (size_t)ring_slot * ro.slot_bytes : nullptr;
     float* const reward = reward0 ? reward0 + oo : nullptr;
@@ -257,10 +284,12 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     int32_t* const lifetime = lifetime0 ? lifetime0 + oo : nullptr;
     int32_t* const actions_out = actions_out0 ? actions_out0 + oo : nullptr;
     u64* const legal = legal0 ? legal0 + oo * p.W : nullptr;
-    if (rs) __syncthreads();            // the previous step has read the bitmaps; its state stores are visible
 
-    // ---- phase A: warp 0, lane = lattice
-    if (warp == 0) {
+    // ---- phase A: warp 0, lane = lattice.  Warps 1.. meanwhile write the PREVIOUS step's observations (phase D): phase A does
+    //      not touch the bitmaps -- the cell a light step adds is applied after the barrier.
+    if (warp != 0) {
+        if (obs_prev) write_observations<D>(sm, p, obs_prev, env0, nvalid, C, tid - 32, kThreads - 32);
+    } else {
         const int e = env0 + lane;
         const bool mine = lane < kEpc, live = lane < nvalid;
         u64 xb = 0, zb = 0, meta = 0, act[3] = {0, 0, 0};
@@ -339,18 +368,13 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                     p.state[ROW_ZB * np + e] = zb;
                     p.state[ROW_META * np + e] = meta;
                     if (!ident) p.state[(ROW_ACT + layer) * np + e] = layer == 0 ? act[0] : (layer == 1 ? act[1] : act[2]);
-                    if (actbit >= 0) {         // this step's action lights one more cell of its action layer
-                        const int pos = actbit & 0xFFFF, row = (p.vd + layer) * PW + (pos >> 6);
-                        const u64 wv = sm.bm[row][lane] | (1ull << (pos & 63));
-                        sm.bm[row][lane] = wv;
-                        p.state[(ROW_BM + row) * np + e] = wv;
-                    }
                 }
             } else if (live) {
                 flags = 2u;               // reset keeps only the attempt counter (the position in the random stream)
             }
             sm.fx[lane] = xb; sm.fz[lane] = zb; sm.fmeta[lane] = meta;
             sm.acted[lane] = act[0] | act[1] | act[2];
+            sm.actbit[lane] = flags ? -1 : actbit;
         }
         const u32 tmask = __ballot_sync(FULL, flags != 0);
         if (flags) {
@@ -361,6 +385,15 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     }
     __syncthreads();
 
+    if (tid < kEpc) {                          // a light step's action lights one more cell of its action layer
+        const int ab = sm.actbit[tid];
+        if (ab >= 0) {
+            const int pos = ab & 0xFFFF, row = (p.vd + (ab >> 16)) * PW + (pos >> 6);
+            const u64 wv = sm.bm[row][tid] | (1ull << (pos & 63));
+            sm.bm[row][tid] = wv;
+            p.state[(ROW_BM + row) * np + env0 + tid] = wv;
+        }
+    }
     // ---- phase B: warp per flagged lattice: fresh volume(s), then re-render its layer bitmaps
     for (int t = warp; t < sm.ntask; t += kWarps) {
         const int slot = sm.task[t], fl = sm.task_flags[t];
@@ -439,27 +472,9 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         }
     }
 
-    // ---- phase D: observation bytes.  Thread per 32 stream bits: gathered from the layer bitmaps, expanded to 32 bytes of 0/1,
-    //      two 128-bit stores (the tile's 16*C*H*H bytes start 16-byte aligned whenever the caller's buffer is)
-    if (obs) {
-        const int vbytes = nvalid * p.obs_bits;
-        uint8_t* out = obs + (size_t)env0 * p.obs_bits;
-        const bool aligned = (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
-        for (int g = tid * 32; g < vbytes; g += kThreads * 32) {
-            const int lat = (int)__umulhi((u32)g, p.ob_magic);
-            const int r = g - lat * p.obs_bits;
-            const int layer = r / L::P, o = r - layer * L::P;
-            const u32 word = gather32<D>(sm, lat, layer, o, C);
-            if (aligned && g + 32 <= vbytes) {
-                *reinterpret_cast<uint4*>(out + g) = expand16(word);
-                *reinterpret_cast<uint4*>(out + g + 16) = expand16(word >> 16);
-            } else {
-                const int nb = min(32, vbytes - g);
-                for (int b = 0; b < nb; ++b) out[g + b] = (uint8_t)((word >> b) & 1u);
-            }
-        }
-    }
+    obs_prev = obs;
     }   // rollout step
+    if (obs_prev) write_observations<D>(sm, p, obs_prev, env0, nvalid, C, tid, kThreads);     // the last step's observations
     if (policy_ctr && tid == 0 && atomicAdd(policy_ctr + 1, 1u) == gridDim.x - 1) { policy_ctr[1] = 0; atomicAdd(policy_ctr, (u32)ro.nsteps); }
 }
 
