@@ -217,6 +217,26 @@ template <int D> __device__ __forceinline__ u64 marker_word_rt(int i) {
     }
 }
 
+// Legal-move mask words of one lattice (Environments.py:238-271 in closed form): qubits touching the summed faulty syndrome
+// or next to an already acted-on qubit, in every action layer, plus the identity.
+template <int D>
+__device__ __forceinline__ void legal_words(const EnvParams& p, u64 summed, u64 acted, u64 (&mw)[3]) {
+    typedef Lat<D> L;
+    const u64 lq = qubits_grid_to_compact<D>(qubits_adjacent_to<D>(summed) | qubits_neighbours_of<D>(acted));
+    mw[0] = mw[1] = mw[2] = 0;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        if (l < p.layers) {
+            const int o = l * L::NQ, i = o >> 6, s = o & 63;
+            mw[i] |= lq << s;
+            if (s && i + 1 < 3) mw[i + 1] |= lq >> (64 - s);
+        }
+    }
+    const int ib = p.A - 1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) if (i == (ib >> 6)) mw[i] |= 1ull << (ib & 63);
+}
+
 // Phase D: the tile's observation bytes.  Thread per 32 bits of the tile's observation bit stream: gathered from the layer
 // bitmaps, expanded to 32 bytes of 0/1, two 128-bit stores (the tile's 16*C*H*H bytes start 16-byte aligned whenever the
 // caller's buffer is).  Executed by threads [first, first + nthr) of the CTA.
@@ -276,6 +296,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     // and row s of the per-step outputs.  A single step is the nsteps == 1 case.
     int ring_slot = ro.first_slot;
     size_t oo = 0;
+    u64 mw[3] = {0, 0, 0};              // warp 0, lane = lattice: legal-move mask after the latest step (phase C -> next phase A)
     uint8_t* obs_prev = nullptr;        // the previous step's observation slot: written while warp 0 runs this step's phase A
     for (int rs = 0; rs < ro.nsteps; ++rs, oo += ro.out_stride, ring_slot = (ring_slot + 1 == ro.slots) ? 0 : ring_slot + 1) {
     uint8_t* const obs = obs0 ? obs0 + (size_t)ring_slot * ro.slot_bytes : nullptr;
@@ -307,19 +328,8 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                     // built-in random-legal policy (dq_env_step_random): the pick dq_policy_random_legal would make
                     // on this lattice's current legal set, with the step index read from device memory
                     const u32 step = step0 + (u32)rs;
-                    const u64 lq0 = qubits_grid_to_compact<D>(qubits_adjacent_to<D>(sm.sum[lane]) | qubits_neighbours_of<D>(act[0] | act[1] | act[2]));
-                    u64 mw[3] = {0, 0, 0};
-#pragma unroll
-                    for (int l = 0; l < 3; ++l) {
-                        if (l < p.layers) {
-                            const int o = l * L::NQ, i = o >> 6, sh = o & 63;
-                            mw[i] |= lq0 << sh;
-                            if (sh && i + 1 < 3) mw[i + 1] |= lq0 >> (64 - sh);
-                        }
-                    }
+                    if (rs == 0) legal_words<D>(p, sm.sum[lane], act[0] | act[1] | act[2], mw);   // later steps: phase C of the previous step left it
                     const int ib = p.A - 1;
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) if (i == (ib >> 6)) mw[i] |= 1ull << (ib & 63);
                     const int cnt = popc64(mw[0]) + popc64(mw[1]) + popc64(mw[2]);
                     const Philox4 u = philox4x32_10(p.env_id_base + (u32)e, step, 0u, 1u, p.k0, p.k1);
                     int pick = (int)mulhi32(u.x, (u32)cnt);
@@ -448,30 +458,19 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     }
     __syncthreads();
 
-    // ---- phase C: lifetime and legal mask (thread per lattice)
-    if (tid < nvalid) {
+    // ---- phase C: lifetime and legal mask (warp 0, lane = lattice; the mask also feeds the next step's built-in pick)
+    if (tid < kEpc) {
         const int slot = tid;
-        if (lifetime && !RESET) lifetime[env0 + slot] = sm.life_out[slot];
-        if (legal) {
-            const u64 lq = qubits_grid_to_compact<D>(qubits_adjacent_to<D>(sm.sum[slot]) | qubits_neighbours_of<D>(sm.acted[slot]));
-            u64 mw[3] = {0, 0, 0};
+        if (lifetime && !RESET && slot < nvalid) lifetime[env0 + slot] = sm.life_out[slot];
+        if (legal || policy_ctr) {
+            legal_words<D>(p, sm.sum[slot], sm.acted[slot], mw);
+            if (legal && slot < nvalid) {
 #pragma unroll
-            for (int l = 0; l < 3; ++l) {
-                if (l < p.layers) {
-                    const int o = l * L::NQ, i = o >> 6, s = o & 63;
-                    mw[i] |= lq << s;
-                    if (s && i + 1 < 3) mw[i + 1] |= lq >> (64 - s);
-                }
-            }
-            const int ib = p.A - 1;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                if (i == (ib >> 6)) mw[i] |= 1ull << (ib & 63);
-                if (i < p.W) legal[(size_t)(env0 + slot) * p.W + i] = mw[i];
+                for (int i = 0; i < 3; ++i)
+                    if (i < p.W) legal[(size_t)(env0 + slot) * p.W + i] = mw[i];
             }
         }
     }
-
     obs_prev = obs;
     }   // rollout step
     if (obs_prev) write_observations<D>(sm, p, obs_prev, env0, nvalid, C, tid, kThreads);     // the last step's observations
