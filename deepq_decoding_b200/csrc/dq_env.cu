@@ -169,7 +169,8 @@ struct Rollout {            // multi-step launch: see env_step_kernel
 };
 
 struct Smem {
-    u64 bm[kMaxLayers * 4][kEpc];     // rendered bitmap of every observation layer of the tile's lattices (mirror of the state rows)
+    u64 bm[kEpc][kMaxLayers * 4];     // [lattice][layer*PW + word]: rendered bitmap of every observation layer (mirror of the state rows)
+    u64 lut8[256];                    // byte -> its 8 bits as 8 bytes of 0/1 (phase D)
     u64 fx[kEpc], fz[kEpc], fmeta[kEpc];   // phase A -> B hand-off: frame planes, counters
     u64 sum[kEpc], acted[kEpc];       // OR of the volume's slices; OR of the action boards
     u32 acc[kWarps][3 * kMaxVd * 2];  // per-warp flip accumulators of generate_volume
@@ -180,32 +181,28 @@ struct Smem {
 };
 
 // 32 bits of the tile's observation bit stream starting at bit `o` of (lattice, layer): the stream is the concatenation of the
-// layer bitmaps (P bits each), lattice-major, so a 32-bit window touches at most two of them (P >= 49).
+// layer bitmaps (P bits each), lattice-major, so a 32-bit window touches at most two of them (P >= 49).  A lattice's bitmap words
+// are contiguous in shared memory, read here as 32-bit words.
 template <int D>
 __device__ __forceinline__ u32 gather32(const Smem& sm, int lat, int layer, int o, int C) {
     typedef Lat<D> L;
     constexpr int PW = L::PW, P = L::P;
-    const int idx = o >> 6, sh = o & 63;
-    const u64 lo = sm.bm[layer * PW + idx][lat];
-    const u64 hi = (idx + 1 < PW) ? sm.bm[layer * PW + idx + 1][lat] : 0ull;
-    u32 v = (u32)(lo >> sh);
-    if (sh > 32) v |= (u32)(hi << (64 - sh));
-    const int n1 = P - o;                       // bits left in this layer (bits >= P of a bitmap are zero)
+    const u32* w = reinterpret_cast<const u32*>(&sm.bm[lat][layer * PW]) + (o >> 5);
+    u32 v = __funnelshift_r(w[0], w[1], o & 31);     // w[1] may belong to the next layer: those bits are masked off below
+    const int n1 = P - o;                             // bits left in this layer (bits >= P of a bitmap are zero)
     if (n1 < 32) {
+        v &= (1u << n1) - 1u;
         int l2 = layer + 1, lat2 = lat;
         if (l2 == C) { l2 = 0; lat2 = lat + 1; }
-        if (lat2 < kEpc) v |= (u32)sm.bm[l2 * PW][lat2] << n1;
+        if (lat2 < kEpc) v |= reinterpret_cast<const u32*>(&sm.bm[lat2][l2 * PW])[0] << n1;
     }
     return v;
 }
 
-__device__ __forceinline__ uint4 expand16(u32 h) {     // 16 bits -> 16 bytes of 0/1
-    uint4 v;
-    v.x = ((h & 0xFu) * 0x00204081u) & 0x01010101u;
-    v.y = (((h >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
-    v.z = (((h >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
-    v.w = (((h >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
-    return v;
+__device__ __forceinline__ uint4 expand16(const Smem& sm, u32 h) {     // low 16 bits -> 16 bytes of 0/1 (two table lookups)
+    const uint2 a = *reinterpret_cast<const uint2*>(&sm.lut8[h & 0xFFu]);
+    const uint2 b = *reinterpret_cast<const uint2*>(&sm.lut8[(h >> 8) & 0xFFu]);
+    return make_uint4(a.x, a.y, b.x, b.y);
 }
 
 template <int D> __device__ __forceinline__ u64 marker_word_rt(int i) {
@@ -244,21 +241,24 @@ template <int D>
 __device__ __forceinline__ void write_observations(const Smem& sm, const EnvParams& p, uint8_t* obs, int env0, int nvalid, int C,
                                                    int t, int nthr) {
     typedef Lat<D> L;
-    const int vbytes = nvalid * p.obs_bits;
+    const int vbytes = nvalid * p.obs_bits, OB = p.obs_bits;
     uint8_t* out = obs + (size_t)env0 * p.obs_bits;
     const bool aligned = (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
-    for (int g = t * 32; g < vbytes; g += nthr * 32) {
-        const int lat = (int)__umulhi((u32)g, p.ob_magic);
-        const int r = g - lat * p.obs_bits;
+    const int step = nthr * 32, dlat = step / OB, dr = step - dlat * OB;          // warp-uniform
+    int g = t * 32;
+    int lat = (int)__umulhi((u32)g, p.ob_magic), r = g - lat * OB;
+    for (; g < vbytes; g += step) {
         const int layer = r / L::P, o = r - layer * L::P;
         const u32 word = gather32<D>(sm, lat, layer, o, C);
         if (aligned && g + 32 <= vbytes) {
-            *reinterpret_cast<uint4*>(out + g) = expand16(word);
-            *reinterpret_cast<uint4*>(out + g + 16) = expand16(word >> 16);
+            *reinterpret_cast<uint4*>(out + g) = expand16(sm, word);
+            *reinterpret_cast<uint4*>(out + g + 16) = expand16(sm, word >> 16);
         } else {
             const int nb = min(32, vbytes - g);
             for (int b = 0; b < nb; ++b) out[g + b] = (uint8_t)((word >> b) & 1u);
         }
+        lat += dlat; r += dr;
+        if (r >= OB) { r -= OB; ++lat; }
     }
 }
 
@@ -286,9 +286,11 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     // (and in the state rows, kept in step): a step only re-renders what it changes.
     for (int i = tid; i < C * PW * kEpc; i += kThreads) {
         const int row = i / kEpc, slot = i - row * kEpc;
-        sm.bm[row][slot] = p.state[(ROW_BM + row) * np + env0 + slot];
+        sm.bm[slot][row] = p.state[(ROW_BM + row) * np + env0 + slot];
     }
     if (tid < kEpc) sm.sum[tid] = p.state[ROW_SUM * np + env0 + tid];
+    for (int i = tid; i < 256; i += kThreads)
+        sm.lut8[i] = (u64)((((u32)i & 0xFu) * 0x00204081u) & 0x01010101u) | ((u64)((((u32)i >> 4) * 0x00204081u) & 0x01010101u) << 32);
     __syncthreads();
 
     // A rollout (dq_env_rollout_random) runs ro.nsteps steps of this tile's lattices in one launch: lattices are independent,
@@ -399,8 +401,8 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         const int ab = sm.actbit[tid];
         if (ab >= 0) {
             const int pos = ab & 0xFFFF, row = (p.vd + (ab >> 16)) * PW + (pos >> 6);
-            const u64 wv = sm.bm[row][tid] | (1ull << (pos & 63));
-            sm.bm[row][tid] = wv;
+            const u64 wv = sm.bm[tid][row] | (1ull << (pos & 63));
+            sm.bm[tid][row] = wv;
             p.state[(ROW_BM + row) * np + env0 + tid] = wv;
         }
     }
@@ -434,7 +436,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         }
         if (lane < p.layers) p.state[(ROW_ACT + lane) * np + e] = 0;
         // render: markers first, then lane per (slice, plaquette row) ORs its spread row in
-        for (int i = lane; i < C * PW; i += 32) sm.bm[i][slot] = (i < p.vd * PW) ? marker_word_rt<D>(i % PW) : 0ull;
+        for (int i = lane; i < C * PW; i += 32) sm.bm[slot][i] = (i < p.vd * PW) ? marker_word_rt<D>(i % PW) : 0ull;
         __syncwarp();
         for (int base = 0; base < p.vd * G; base += 32) {
             const int idx = base + lane;
@@ -444,17 +446,17 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                 const u32 v = spread2_8((u32)(fj >> (a * G)) & ((1u << G) - 1));
                 const int off = 2 * a * H, k = off >> 5, sh = off & 31;          // 32-bit word k of the layer bitmap
                 if (v) {
-                    u32* w0 = reinterpret_cast<u32*>(&sm.bm[j * PW + (k >> 1)][slot]) + (k & 1);
+                    u32* w0 = reinterpret_cast<u32*>(&sm.bm[slot][j * PW]) + k;
                     atomicOr(w0, v << sh);
                     if (sh > 17 && (v >> (32 - sh))) {
-                        u32* w1 = reinterpret_cast<u32*>(&sm.bm[j * PW + ((k + 1) >> 1)][slot]) + ((k + 1) & 1);
+                        u32* w1 = reinterpret_cast<u32*>(&sm.bm[slot][j * PW]) + k + 1;
                         atomicOr(w1, v >> (32 - sh));
                     }
                 }
             }
         }
         __syncwarp();
-        for (int i = lane; i < C * PW; i += 32) p.state[(ROW_BM + i) * np + e] = sm.bm[i][slot];
+        for (int i = lane; i < C * PW; i += 32) p.state[(ROW_BM + i) * np + e] = sm.bm[slot][i];
     }
     __syncthreads();
 
