@@ -243,16 +243,22 @@ __device__ __forceinline__ void write_observations(const Smem& sm, const EnvPara
     typedef Lat<D> L;
     const int vbytes = nvalid * p.obs_bits, OB = p.obs_bits;
     uint8_t* out = obs + (size_t)env0 * p.obs_bits;
-    const bool aligned = (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
+    const int align = (int)(reinterpret_cast<uintptr_t>(out) & 15);               // 0: 128-bit stores, 8: 64-bit stores, else bytes
     const int step = nthr * 32, dlat = step / OB, dr = step - dlat * OB;          // warp-uniform
     int g = t * 32;
     int lat = (int)__umulhi((u32)g, p.ob_magic), r = g - lat * OB;
     for (; g < vbytes; g += step) {
         const int layer = r / L::P, o = r - layer * L::P;
         const u32 word = gather32<D>(sm, lat, layer, o, C);
-        if (aligned && g + 32 <= vbytes) {
+        if (align == 0 && g + 32 <= vbytes) {
             *reinterpret_cast<uint4*>(out + g) = expand16(sm, word);
             *reinterpret_cast<uint4*>(out + g + 16) = expand16(sm, word >> 16);
+        } else if (align == 8 && g + 32 <= vbytes) {
+            const uint4 a = expand16(sm, word), b = expand16(sm, word >> 16);
+            *reinterpret_cast<uint2*>(out + g) = make_uint2(a.x, a.y);
+            *reinterpret_cast<uint2*>(out + g + 8) = make_uint2(a.z, a.w);
+            *reinterpret_cast<uint2*>(out + g + 16) = make_uint2(b.x, b.y);
+            *reinterpret_cast<uint2*>(out + g + 24) = make_uint2(b.z, b.w);
         } else {
             const int nb = min(32, vbytes - g);
             for (int b = 0; b < nb; ++b) out[g + b] = (uint8_t)((word >> b) & 1u);

@@ -57,10 +57,58 @@ def train_point(spec_args, error_model, p, cfg, n_envs, steps, init=None, test_e
     return result, carry, dqn
 
 
+def deal(points, rank, world):
+    """Grid points of one error rate dealt round-robin to the ranks: [(grid index, config), ...] for `rank`.
+    (The reference submits one Slurm job per point, Controller.py:161-279; here a rank is a GPU of the same box.)"""
+    return [(gi, cfg) for gi, cfg in enumerate(points) if gi % world == rank]
+
+
+def pick_winner(scores):
+    """scores[r] = best greedy test lifetime rank r found at this error rate (None = it trained nothing).
+    Returns the rank whose candidate wins; ties go to the lowest rank so every rank computes the same answer."""
+    best = None
+    for r, s in enumerate(scores):
+        if s is not None and (best is None or s > scores[best]):
+            best = r
+    return best
+
+
+def broadcast_carry(carry, src, group=None, device="cpu"):
+    """The winner's hand-over state (flat parameters + replay snapshot: a dict of tensors and ints) from rank `src` to all."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    meta = [None]
+    if rank == src:
+        mem = carry.get("memory") or {}
+        meta[0] = {"params": tuple(carry["params"].shape),
+                   "tensors": {k: (tuple(v.shape), v.dtype) for k, v in mem.items() if torch.is_tensor(v)},
+                   "plain": {k: v for k, v in mem.items() if not torch.is_tensor(v)}, "has_memory": carry.get("memory") is not None}
+    dist.broadcast_object_list(meta, src=src, group=group)
+    m = meta[0]
+    params = carry["params"].to(device) if rank == src else torch.empty(m["params"], dtype=torch.float32, device=device)
+    dist.broadcast(params, src=src, group=group)
+    out = {"params": params, "memory": None}
+    if m["has_memory"]:
+        mem = dict(m["plain"])
+        for k, (shape, dt) in m["tensors"].items():
+            buf = carry["memory"][k].to(device) if rank == src else torch.empty(shape, dtype=dt, device=device)
+            dist.broadcast(buf, src=src, group=group)
+            mem[k] = buf.cpu()
+        out["memory"] = mem
+    return out
+
+
 def iterative_training(error_rates, grid=None, error_model="DP", d=5, volume_depth=5, cc_layers=((64, 3, 2), (32, 2, 1), (32, 2, 1)),
                        ff_layers=((512, 0.2),), n_envs=4096, steps_per_point=2e7, test_episodes=4096, out_dir=None, seed=0,
-                       device="cuda:0", verbose=0, max_grid_points=None):
-    """Controller.py's state machine as a function: returns the per-rate winners and the final carry (weights + memory)."""
+                       device="cuda:0", verbose=0, max_grid_points=None, process_group=None):
+    """Controller.py's state machine as a function: returns the per-rate winners and the final carry (weights + memory).
+    With `process_group` (one process per GPU) the grid points of every error rate are dealt to the ranks, the winner is
+    agreed on by an all-gather of the scores and its weights + replay memory are broadcast before the next rate."""
+    rank, world = 0, 1
+    if process_group is not None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(process_group), dist.get_world_size(process_group)
     grid = grid or default_grid()
     keys = sorted(grid)
     points = [dict(zip(keys, vals)) for vals in itertools.product(*(grid[k] for k in keys))]
@@ -70,20 +118,32 @@ def iterative_training(error_rates, grid=None, error_model="DP", d=5, volume_dep
     carry, winners = None, []
     for p in error_rates:
         best = None
-        for gi, cfg in enumerate(points):
+        for gi, cfg in deal(points, rank, world):
             res, c, dqn = train_point(spec_args, error_model, p, cfg, n_envs, steps_per_point, init=copy.copy(carry),
                                       test_episodes=test_episodes, seed=seed + gi, device=device, verbose=verbose)
             if best is None or res["test_mean_lifetime"] > best[0]["test_mean_lifetime"]:
                 best = (res, c, dqn)
             else:
                 dqn.model.close()
-        res, c, dqn = best
+        if world > 1:
+            import torch.distributed as dist
+            scores = [None] * world
+            dist.all_gather_object(scores, (best[0]["test_mean_lifetime"], best[0]) if best else None, group=process_group)
+            win = pick_winner([s[0] if s else None for s in scores])
+            res = scores[win][1]
+            c = broadcast_carry(best[1] if rank == win else None, win, process_group, device)
+            dqn = best[2] if best else None
+            if rank != win and dqn is not None:
+                dqn.model.close(); dqn = None
+        else:
+            res, c, dqn = best
         res["beats_threshold"] = res["test_mean_lifetime"] > res["threshold"]
         winners.append(res)
-        if out_dir:
+        if out_dir and dqn is not None:
             os.makedirs(os.path.join(out_dir, str(p)), exist_ok=True)
             dqn.save_weights(os.path.join(out_dir, str(p), "final_dqn_weights.h5f"))
-        dqn.model.close()
+        if dqn is not None:
+            dqn.model.close()
         if not res["beats_threshold"]:
             break                   # the reference stops the curriculum when no configuration beats 1/p (Controller.py:117-156)
         carry = c

@@ -43,3 +43,37 @@ def test_gloo_world2(tmp_path):
     assert r0["n"] == r1["n"] == len(both)
     assert r0["mean"] == pytest.approx(both.mean()) and r1["mean"] == pytest.approx(both.mean())
     assert r0["se"] == pytest.approx(both.std() / np.sqrt(len(both)))
+
+
+def test_grid_points_are_dealt_and_the_winner_is_agreed():
+    from deepq_decoding_b200 import curriculum
+    pts = [{"i": i} for i in range(7)]
+    dealt = [curriculum.deal(pts, r, 3) for r in range(3)]
+    assert sorted(gi for d in dealt for gi, _ in d) == list(range(7))
+    assert [gi for gi, _ in dealt[1]] == [1, 4]
+    assert curriculum.pick_winner([10.0, None, 30.0, 30.0]) == 2          # ties -> lowest rank, idle ranks skipped
+    assert curriculum.pick_winner([None, None]) is None
+
+
+def _carry_worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from deepq_decoding_b200 import curriculum
+    parallel.init("gloo")
+    carry = None
+    if rank == 1:                                            # rank 1 holds the winning candidate
+        carry = {"params": torch.arange(1000, dtype=torch.float32) * 0.5,
+                 "memory": {"obs": torch.arange(24, dtype=torch.int64).reshape(2, 3, 4), "act": torch.ones(2, 4, dtype=torch.int32),
+                            "head": 1, "filled": 2}}
+    got = curriculum.broadcast_carry(carry, src=1, device="cpu")
+    torch.save(got, os.path.join(out, "c%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_winner_state_reaches_every_rank(tmp_path):
+    port = 27500 + (os.getpid() % 2000)
+    mp.spawn(_carry_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in (0, 1):
+        got = torch.load(os.path.join(tmp_path, "c%d.pt" % r), weights_only=False)
+        assert torch.equal(got["params"], torch.arange(1000, dtype=torch.float32) * 0.5)
+        assert torch.equal(got["memory"]["obs"], torch.arange(24, dtype=torch.int64).reshape(2, 3, 4))
+        assert got["memory"]["act"].dtype == torch.int32 and got["memory"]["head"] == 1 and got["memory"]["filled"] == 2
