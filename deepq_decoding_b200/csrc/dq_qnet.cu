@@ -136,33 +136,55 @@ constexpr int TB = 64, TK = 16;        // 64x64 output tile, 16-deep steps, 256 
 // KS = depth of one k step: 16 for big grids (many CTAs hide each other's load latency), 64 when the grid is small and
 // every (load -> sync -> FMA -> sync) step is an exposed memory latency.
 template <int KS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 gemm_fwd_kernel(const float* __restrict__ X, Patch g, const float* __restrict__ W, const float* __restrict__ bias,
                 float* __restrict__ Y, long long M, int N, int K, int act) {
     __shared__ float As[KS][TB + 4], Bs[KS][TB + 4];
     __shared__ long long rowoff[TB];
-    __shared__ int coloff[KS];
+    __shared__ int coloff[2][KS];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const long long m0 = (long long)blockIdx.x * TB;
     const int n0 = blockIdx.y * TB;
+    constexpr int E = TB * KS / 256;                    // elements of each tile per thread
     if (tid < TB) rowoff[tid] = (m0 + tid < M) ? patch_row(g, m0 + tid) : -1;
+    if (tid < KS) coloff[0][tid] = (tid < K) ? patch_col(g, tid) : -1;       // one division per k per CTA, not per element
+    __syncthreads();
     float acc[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += KS) {
-        if (tid < KS) coloff[tid] = (k0 + tid < K) ? patch_col(g, k0 + tid) : -1;    // one division per k per CTA, not per element
-        __syncthreads();
+    float va[E], vb[E];
+    // All global loads of a k step are issued together (unconditional loads from a safe address), one step AHEAD of the
+    // math: the registers are stored to shared memory at the top of the next iteration, so the L2 round trip of step s+1
+    // hides behind the FMAs of step s.
+    auto load_tiles = [&](int k0, const int* co_tab) {
 #pragma unroll
-        for (int i = 0; i < TB * KS / 256; ++i) {      // A tile: 64 rows x KS k
+        for (int i = 0; i < E; ++i) {                   // A tile: 64 rows x KS k
             const int e = tid + i * 256, r = e / KS, kk = e % KS;
-            float v = 0.f;
-            if (coloff[kk] >= 0 && rowoff[r] >= 0) v = X[rowoff[r] + coloff[kk]];
-            As[kk][r] = v;
+            const long long ro = rowoff[r];
+            const int co = co_tab[kk];
+            const bool ok = co >= 0 && ro >= 0;
+            const float v = __ldg(X + (ok ? ro + co : 0));
+            va[i] = ok ? v : 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < TB * KS / 256; ++i) {      // W tile: KS k x 64 n
+        for (int i = 0; i < E; ++i) {                   // W tile: KS k x 64 n
             const int e = tid + i * 256, kk = e >> 6, c = e & 63, k = k0 + kk, n = n0 + c;
-            Bs[kk][c] = (k < K && n < N) ? W[(long long)k * N + n] : 0.f;
+            const bool ok = k < K && n < N;
+            const float v = __ldg(W + (ok ? (long long)k * N + n : 0));
+            vb[i] = ok ? v : 0.f;
         }
+    };
+    load_tiles(0, coloff[0]);
+    int it = 0;
+    for (int k0 = 0; k0 < K; k0 += KS, ++it) {
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const int e = tid + i * 256;
+            As[e % KS][e / KS] = va[i];
+            Bs[e >> 6][e & 63] = vb[i];
+        }
+        const bool more = k0 + KS < K;
+        if (more && tid < KS) coloff[(it + 1) & 1][tid] = (k0 + KS + tid < K) ? patch_col(g, k0 + KS + tid) : -1;
         __syncthreads();
+        if (more) load_tiles(k0 + KS, coloff[(it + 1) & 1]);
 #pragma unroll 16
         for (int kk = 0; kk < KS; ++kk) {
             float a[4], b[4];
@@ -205,18 +227,29 @@ gemm_dw_kernel(const float* __restrict__ X, Patch g, const float* __restrict__ d
     for (long long ms = mb; ms < me; ms += TK) {
         if (tid < TK) rowoff[tid] = (ms + tid < me) ? patch_row(g, ms + tid) : -1;
         __syncthreads();
+        float va[4], vb[4];                            // loads first, shared stores after (see gemm_fwd_kernel)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                  // A^T tile: 16 m x 64 k
             const int e = tid + i * 256, mm = e >> 6, c = e & 63;
-            float v = 0.f;
-            if (rowoff[mm] >= 0 && coloff[c] >= 0) v = X[rowoff[mm] + coloff[c]];
-            As[mm][c] = v;
+            const long long ro = rowoff[mm];
+            const int co = coloff[c];
+            const bool ok = ro >= 0 && co >= 0;
+            const float v = __ldg(X + (ok ? ro + co : 0));
+            va[i] = ok ? v : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                  // dY tile: 16 m x 64 n
             const int e = tid + i * 256, mm = e >> 6, c = e & 63;
             const long long m = ms + mm;
-            Bs[mm][c] = (m < me && n0 + c < N) ? dY[m * N + n0 + c] : 0.f;
+            const bool ok = m < me && n0 + c < N;
+            const float v = __ldg(dY + (ok ? m * N + n0 + c : 0));
+            vb[i] = ok ? v : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * 256;
+            As[e >> 6][e & 63] = va[i];
+            Bs[e >> 6][e & 63] = vb[i];
         }
         __syncthreads();
 #pragma unroll
@@ -253,21 +286,37 @@ gemm_dx_kernel(const float* __restrict__ dY, const float* __restrict__ W, float*
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const long long m0 = (long long)blockIdx.x * TB;
     const int k0 = blockIdx.y * TB;
+    constexpr int E = TB * NS / 256;
     if (tid < TB) rowoff[tid] = (m0 + tid < M) ? patch_row(g, m0 + tid) : -1;
     __syncthreads();
     float acc[4][4] = {};
+    float va[E], vb[E];
+    auto load_tiles = [&](int ns) {                     // one reduction step ahead of the math (see gemm_fwd_kernel)
+#pragma unroll
+        for (int i = 0; i < E; ++i) {                   // dY tile: 64 m x NS n
+            const int e = tid + i * 256, r = e / NS, nn = e % NS;
+            const bool ok = m0 + r < M && ns + nn < N;
+            const float v = __ldg(dY + (ok ? (m0 + r) * N + ns + nn : 0));
+            va[i] = ok ? v : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < E; ++i) {                   // W^T tile: NS n x 64 k
+            const int e = tid + i * 256, c = e / NS, nn = e % NS;
+            const bool ok = k0 + c < K && ns + nn < N;
+            const float v = __ldg(W + (ok ? (long long)(k0 + c) * N + ns + nn : 0));
+            vb[i] = ok ? v : 0.f;
+        }
+    };
+    load_tiles(0);
     for (int ns = 0; ns < N; ns += NS) {
 #pragma unroll
-        for (int i = 0; i < TB * NS / 256; ++i) {      // dY tile: 64 m x NS n
-            const int e = tid + i * 256, r = e / NS, nn = e % NS;
-            As[nn][r] = (m0 + r < M && ns + nn < N) ? dY[(m0 + r) * N + ns + nn] : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < TB * NS / 256; ++i) {      // W^T tile: NS n x 64 k
-            const int e = tid + i * 256, c = e / NS, nn = e % NS;
-            Bs[nn][c] = (k0 + c < K && ns + nn < N) ? W[(long long)(k0 + c) * N + ns + nn] : 0.f;
+        for (int i = 0; i < E; ++i) {
+            const int e = tid + i * 256;
+            As[e % NS][e / NS] = va[i];
+            Bs[e % NS][e / NS] = vb[i];
         }
         __syncthreads();
+        if (ns + NS < N) load_tiles(ns + NS);
 #pragma unroll 16
         for (int nn = 0; nn < NS; ++nn) {
             float a[4], b[4];
@@ -994,7 +1043,16 @@ __global__ void __launch_bounds__(128)
 head_dueling_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
                     float* __restrict__ q, long long B, int K, int N, int A, int dueling) {
     extern __shared__ float hw[];                      // W [K][N] then bias [N]
-    for (int i = threadIdx.x; i < K * N; i += blockDim.x) hw[i] = W[i];
+    for (int i0 = 0; i0 < K * N; i0 += 8 * (int)blockDim.x) {      // 8 loads in flight per thread, then the shared stores
+        float w8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w8[j] = __ldg(W + min(i0 + j * (int)blockDim.x + (int)threadIdx.x, K * N - 1));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = i0 + j * (int)blockDim.x + (int)threadIdx.x;
+            if (i < K * N) hw[i] = w8[j];
+        }
+    }
     for (int i = threadIdx.x; i < N; i += blockDim.x) hw[K * N + i] = bias[i];
     __syncthreads();
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1003,11 +1061,18 @@ head_dueling_kernel(const float* __restrict__ x, const float* __restrict__ W, co
 #pragma unroll
     for (int n = 0; n < MAXN; ++n) y[n] = n < N ? hw[K * N + n] : 0.f;
     const float* xr = x + b * K;
-    for (int k = 0; k < K; ++k) {
-        const float xv = xr[k];
-        const float* wr = hw + k * N;
+    for (int kc = 0; kc < K; kc += 16) {               // 16 independent loads in flight, then their FMAs
+        float xv[16];
 #pragma unroll
-        for (int n = 0; n < MAXN; ++n) if (n < N) y[n] = fmaf(xv, wr[n], y[n]);
+        for (int j = 0; j < 16; ++j) xv[j] = __ldg(xr + min(kc + j, K - 1));
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (kc + j < K) {
+                const float* wr = hw + (kc + j) * N;
+#pragma unroll
+                for (int n = 0; n < MAXN; ++n) if (n < N) y[n] = fmaf(xv[j], wr[n], y[n]);
+            }
+        }
     }
     if (dueling) {
         float s = 0.f;
@@ -1159,7 +1224,7 @@ extern "C" int dq_qnet_forward_tc(dq_qnet* h, const float* params, const uint64_
         const int i = c.n_fc - 1, K = c.fc_in[i], N = c.fc_out[i], t = c.n_conv + i;
         const size_t smem = (size_t)(K * N + N) * sizeof(float);
         if (N <= 64 && smem <= 48 * 1024) {
-            head_dueling_kernel<64><<<(unsigned)((batch + 127) / 128), 128, smem, st>>>(xf, params + c.w_off[t], params + c.b_off[t], q_out, batch, K, N, c.A, 1);
+            head_dueling_kernel<64><<<(unsigned)((batch + 63) / 64), 64, smem, st>>>(xf, params + c.w_off[t], params + c.b_off[t], q_out, batch, K, N, c.A, 1);
             count_launch();
         } else {
             launch_gemm_fwd(xf, dense_patch(K), params + c.w_off[t], params + c.b_off[t], h->act_fc[i], batch, N, K, 0, st);
