@@ -94,6 +94,57 @@ def cpu_oracle_run(budget_s, n=N_PER_GPU):
                        "with OpenMP over lattices" % (steps, n, el)), n * steps / el, el / steps
 
 
+def cpu_serial_dqn_loop(budget_s):
+    """The reference's training loop shape on one host core: ONE lattice, per env step one Q-network forward for
+    the eps-greedy pick and one double-DQN update on a batch of 32 (keras-rl defaults: train_interval 1, batch 32).  The env is
+    the CPU oracle and the network the torch-CPU restatement (oracle/qnet_ref.py) -- both stand-ins for the reference's numpy /
+    Keras code, which cannot travel to the GPU box; the authors' own log averages 41.6 steps/s."""
+    import copy
+    import numpy as np
+    import torch
+    from oracle import oracle as O, qnet_ref as R
+    from deepq_decoding_b200 import referee as REF
+    torch.set_num_threads(1)
+    o = O.OracleVecEnv(D, MODEL, USE_Y, VD, P, P, 1, SEED + 11)
+    ref = REF.shipped(D, MODEL)
+    o.set_referee(ref.mode, ref.lut_a, ref.lut_b)
+    rng = np.random.default_rng(SEED)
+    A_n, C_n, H = o.A, o.Cn, o.H
+    conv, dense = R.glorot_uniform_params(rng, C_n, [(64, 3, 2), (32, 2, 1), (32, 2, 1)], [512], A_n, H, dueling=True)
+    net = R.TorchQNet(conv, dense, [2, 1, 1], dueling=True)
+    target = R.TorchQNet(copy.deepcopy(conv), copy.deepcopy(dense), [2, 1, 1], dueling=True)
+    params = net.parameters()
+    m = [torch.zeros_like(x) for x in params]
+    v = [torch.zeros_like(x) for x in params]
+    obs, legal = o.reset()
+    mem_s, mem_a, mem_r, mem_t, mem_s1 = [], [], [], [], []
+    steps, updates, t0 = 0, 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        with torch.no_grad():
+            q = net.forward(obs)[0].numpy()
+        lw = legal[0]
+        legal_ids = [a for a in range(A_n) if (int(lw[a >> 6]) >> (a & 63)) & 1]
+        a = int(rng.choice(legal_ids)) if rng.random() < 0.1 else int(legal_ids[int(np.argmax(q[legal_ids]))])
+        obs1, rew, done, _, legal = o.step(np.array([a], np.int32), auto_reset=True)
+        mem_s.append(obs[0].copy()); mem_a.append(a); mem_r.append(float(rew[0])); mem_t.append(float(done[0])); mem_s1.append(obs1[0].copy())
+        obs = obs1
+        steps += 1
+        if len(mem_a) >= 32:
+            idx = rng.integers(0, len(mem_a), size=32)
+            s0 = np.stack([mem_s[i] for i in idx]); s1 = np.stack([mem_s1[i] for i in idx])
+            with torch.no_grad():
+                y = R.dqn_targets(net.forward(s1), target.forward(s1), torch.tensor([mem_r[i] for i in idx]),
+                                  torch.tensor([mem_t[i] for i in idx]), 0.99)
+            loss = R.dqn_loss(net.forward(s0), torch.tensor([mem_a[i] for i in idx]), y)
+            grads = torch.autograd.grad(loss, params)
+            updates += 1
+            R.keras_adam_step(params, grads, m, v, updates, 1e-4)
+    el = time.perf_counter() - t0
+    return {"env_steps_per_s": steps / el, "updates": updates, "seconds": el, "cores": 1,
+            "what": "one lattice, forward + eps-greedy + oracle env step + one batch-32 double-DQN update per step, torch-CPU fp32 "
+                    "(the reference's loop shape; its own log: 41.6 steps/s)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -411,6 +462,7 @@ def run_b200(args):
                "qnet_forward_fp32_ms": t_fwd * 1e3, "qnet_forward_fp32_tflops": flops * n / t_fwd / 1e12,
                "qnet_forward_bf16_ms": t_fwd_tc * 1e3, "qnet_forward_bf16_tflops": flops * n / t_fwd_tc / 1e12,
                "qnet_frac_of_bf16_sustained_peak": flops * n / t_fwd_tc / 1e12 / tf_peak,
+               "cpu_serial_loop": cpu_serial_dqn_loop(min(6.0, max(0.5, args.cpu_seconds / 2))),
                "qnet_precision": "acting: bf16 tcgen05 (fp32 accumulate in TMEM); updates: fp32 SIMT",
                "qnet_flops_per_sample": flops, "policy": "eps-greedy 0.1 over legal actions, masked greedy"}
 

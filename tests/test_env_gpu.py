@@ -217,6 +217,28 @@ def test_rollout_equals_single_steps_and_oracle(d, model, n):
     a.close(); b.close()
 
 
+def test_rollout_without_auto_reset_matches_single_steps():
+    """auto_reset = 0: finished lattices stay finished inside a rollout exactly as across single-step calls."""
+    import ctypes as C
+    import torch
+    from deepq_decoding_b200 import _lib
+    a, _ = make_pair(5, "X", False, 5, 0.05, 300, seed=44, auto_reset=False)
+    b, _ = make_pair(5, "X", False, 5, 0.05, 300, seed=44, auto_reset=False)
+    L = _lib.lib()
+    p = lambda x: C.c_void_p(x.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(a.reset(), b.reset())
+    S = 40
+    out = a.rollout_random(S, None, keep=("reward", "done", "lifetime", "actions"))
+    picks = torch.zeros(300, dtype=torch.int32, device="cuda")
+    for s in range(S):
+        _lib.check(L.dq_env_step_random(b._h, None, p(b.reward), p(b.done), p(b.lifetime), p(b.legal_mask), p(picks), 0, st))
+        assert torch.equal(out["actions"][s], picks) and torch.equal(out["done"][s], b.done) and torch.equal(out["lifetime"][s], b.lifetime), s
+    assert int(out["done"][-1].sum()) > 0                     # some lattices did finish, and stayed so
+    assert torch.equal(a.get_state_words(), b.get_state_words())
+    a.close(); b.close()
+
+
 def test_state_roundtrip_and_injection():
     """get_state/set_state: a restored handle continues bit-identically (checkpoint contract)."""
     import torch
