@@ -1037,56 +1037,78 @@ tc_gemm_kernel(const TcArgs a) {
 }
 
 // Fused head for the acting path: y = x W + b for the last (tiny) dense layer, then the dueling combination.
-// Thread = sample; W ([K][N], K, N <= ~150) lives in shared memory and is read as a broadcast.
+// 4 adjacent lanes share a sample, each owning a quarter of the N outputs; W ([K][N], N <= 64) and the CTA's 32 input rows
+// are staged in shared memory with all their global loads in flight together.
+constexpr int kHeadSamples = 32;
 template <int MAXN>
 __global__ void __launch_bounds__(128)
 head_dueling_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
                     float* __restrict__ q, long long B, int K, int N, int A, int dueling) {
-    extern __shared__ float hw[];                      // W [K][N] then bias [N]
-    for (int i0 = 0; i0 < K * N; i0 += 8 * (int)blockDim.x) {      // 8 loads in flight per thread, then the shared stores
+    extern __shared__ float hw[];                      // W [K][N], bias [N], x tile [32][K]
+    float* hb = hw + K * N;
+    float* hx = hb + N;
+    const int tid = threadIdx.x;
+    const long long b0 = (long long)blockIdx.x * kHeadSamples;
+    const int nrow = (int)min((long long)kHeadSamples, B - b0);
+    for (int i0 = 0; i0 < K * N; i0 += 8 * 128) {      // 8 loads in flight per thread, then the shared stores
         float w8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w8[j] = __ldg(W + min(i0 + j * (int)blockDim.x + (int)threadIdx.x, K * N - 1));
+        for (int j = 0; j < 8; ++j) w8[j] = __ldg(W + min(i0 + j * 128 + tid, K * N - 1));
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int i = i0 + j * (int)blockDim.x + (int)threadIdx.x;
+            const int i = i0 + j * 128 + tid;
             if (i < K * N) hw[i] = w8[j];
         }
     }
-    for (int i = threadIdx.x; i < N; i += blockDim.x) hw[K * N + i] = bias[i];
-    __syncthreads();
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    float y[MAXN];
+    for (int i = tid; i < N; i += 128) hb[i] = bias[i];
+    {
+        const int tot = nrow * K;                      // the CTA's rows are contiguous in x
+        const float* xs = x + b0 * K;
+        for (int i0 = 0; i0 < tot; i0 += 8 * 128) {
+            float x8[8];
 #pragma unroll
-    for (int n = 0; n < MAXN; ++n) y[n] = n < N ? hw[K * N + n] : 0.f;
-    const float* xr = x + b * K;
-    for (int kc = 0; kc < K; kc += 16) {               // 16 independent loads in flight, then their FMAs
-        float xv[16];
+            for (int j = 0; j < 8; ++j) x8[j] = __ldg(xs + min(i0 + j * 128 + tid, tot - 1));
 #pragma unroll
-        for (int j = 0; j < 16; ++j) xv[j] = __ldg(xr + min(kc + j, K - 1));
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            if (kc + j < K) {
-                const float* wr = hw + (kc + j) * N;
-#pragma unroll
-                for (int n = 0; n < MAXN; ++n) if (n < N) y[n] = fmaf(xv[j], wr[n], y[n]);
+            for (int j = 0; j < 8; ++j) {
+                const int i = i0 + j * 128 + tid;
+                if (i < tot) hx[i] = x8[j];
             }
         }
     }
+    __syncthreads();
+    constexpr int NP = MAXN / 4;                       // outputs per lane
+    const int s = tid >> 2, part = tid & 3, np = (N + 3) >> 2, nbeg = part * np;
+    const bool live = s < nrow;
+    float y[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) y[j] = (j < np && nbeg + j < N) ? hb[nbeg + j] : 0.f;
+    if (live) {
+        const float* xr = hx + s * K;
+        for (int k = 0; k < K; ++k) {
+            const float xv = xr[k];
+            const float* wr = hw + k * N + nbeg;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) if (j < np && nbeg + j < N) y[j] = fmaf(xv, wr[j], y[j]);
+        }
+    }
+    const long long b = b0 + s;
     if (dueling) {
-        float s = 0.f;
+        float sum = 0.f;                               // advantages are outputs 1..N-1, the state value is output 0
 #pragma unroll
-        for (int n = 1; n < MAXN; ++n) if (n < N) s += y[n];
-        const float base = y[0] - s / (float)A;
+        for (int j = 0; j < NP; ++j) if (j < np && nbeg + j < N && nbeg + j > 0) sum += y[j];
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const float v0 = __shfl_sync(0xffffffffu, y[0], (tid & 31) & ~3);
+        const float base = v0 - sum / (float)A;
+        if (live) {
 #pragma unroll
-        for (int n = 1; n < MAXN; ++n) if (n < N) q[b * A + n - 1] = base + y[n];
-    } else {
+            for (int j = 0; j < NP; ++j) if (j < np && nbeg + j < N && nbeg + j > 0) q[b * A + nbeg + j - 1] = base + y[j];
+        }
+    } else if (live) {
 #pragma unroll
-        for (int n = 0; n < MAXN; ++n) if (n < N) q[b * A + n] = y[n];
+        for (int j = 0; j < NP; ++j) if (j < np && nbeg + j < N) q[b * A + nbeg + j] = y[j];
     }
 }
-
 // fp32 [K][N] -> bf16 [Npad][Kpad] (transposed, zero padded)
 // perm_C > 0 (layer 1): our K order is (layer, tap) while W's rows are (tap, layer): k' = ci*T + t  <-  k = t*C + ci
 __global__ void prep_wt_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt, int K, int N, int Kpad, int Npad, int perm_C) {
@@ -1222,9 +1244,9 @@ extern "C" int dq_qnet_forward_tc(dq_qnet* h, const float* params, const uint64_
     const float* xf = h->act_fc[c.n_hidden];
     if (c.dueling) {
         const int i = c.n_fc - 1, K = c.fc_in[i], N = c.fc_out[i], t = c.n_conv + i;
-        const size_t smem = (size_t)(K * N + N) * sizeof(float);
+        const size_t smem = (size_t)(K * N + N + kHeadSamples * K) * sizeof(float);
         if (N <= 64 && smem <= 48 * 1024) {
-            head_dueling_kernel<64><<<(unsigned)((batch + 63) / 64), 64, smem, st>>>(xf, params + c.w_off[t], params + c.b_off[t], q_out, batch, K, N, c.A, 1);
+            head_dueling_kernel<64><<<(unsigned)((batch + kHeadSamples - 1) / kHeadSamples), 128, smem, st>>>(xf, params + c.w_off[t], params + c.b_off[t], q_out, batch, K, N, c.A, 1);
             count_launch();
         } else {
             launch_gemm_fwd(xf, dense_patch(K), params + c.w_off[t], params + c.b_off[t], h->act_fc[i], batch, N, K, 0, st);
