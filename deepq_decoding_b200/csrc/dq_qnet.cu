@@ -879,6 +879,47 @@ struct TcArgs {
     long long M; int N, K, Kpad;
 };
 
+// Epilogue of a 128 x BN accumulator tile: warp w owns TMEM lanes 32w..32w+31 = output rows; thread = one row.
+template <int BN>
+__device__ __forceinline__ void tc_epilogue(const TcArgs& a, u32 tmem, int warp, long long m, bool valid, int n0, const float* sbias) {
+    const u32 taddr = tmem + ((u32)(warp * 32) << 16);
+    const bool vec_ok = (a.ldy & 7) == 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+        u32 v[16];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                     : "r"(taddr + (u32)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (valid) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float x = __uint_as_float(v[j]) + sbias[c0 + j];
+                f[j] = a.relu ? fmaxf(x, 0.f) : x;
+            }
+            if (a.out_bf16) {
+                __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.Y) + m * a.ldy + n0 + c0;
+                if (n0 + c0 + 16 <= a.N && vec_ok) {
+                    uint4 p0, p1;
+                    __nv_bfloat162 t;
+#define DQ_PACK(dst, i) t = __floats2bfloat162_rn(f[i], f[i + 1]); dst = *reinterpret_cast<u32*>(&t);
+                    DQ_PACK(p0.x, 0) DQ_PACK(p0.y, 2) DQ_PACK(p0.z, 4) DQ_PACK(p0.w, 6)
+                    DQ_PACK(p1.x, 8) DQ_PACK(p1.y, 10) DQ_PACK(p1.z, 12) DQ_PACK(p1.w, 14)
+#undef DQ_PACK
+                    reinterpret_cast<uint4*>(y)[0] = p0; reinterpret_cast<uint4*>(y)[1] = p1;
+                } else {
+                    for (int j = 0; j < 16; ++j) if (n0 + c0 + j < a.N) y[j] = __float2bfloat16(f[j]);
+                }
+            } else {
+                float* y = reinterpret_cast<float*>(a.Y) + m * a.ldy + n0 + c0;
+                for (int j = 0; j < 16; ++j) if (n0 + c0 + j < a.N) y[j] = f[j];
+            }
+        }
+    }
+}
+
 // AMODE 0: A rows gathered from a bf16 activation (implicit im2col), 16-byte cp.async per chunk.
 // AMODE 1: A rows expanded from the packed binary observation: K order is (layer, tap), so a row's K bits are the
 //          per-layer tap masks concatenated; 8 bits -> 8 bf16 {0, 1.0} per 16-byte chunk.
@@ -993,43 +1034,106 @@ tc_gemm_kernel(const TcArgs a) {
     mbar_wait(&mbar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 = output rows; thread = one row
-    const u32 taddr = tmem + ((u32)(warp * 32) << 16);
-    const bool vec_ok = (a.ldy & 7) == 0;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-        u32 v[16];
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                     : "r"(taddr + (u32)c0));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (valid) {
-            float f[16];
+    tc_epilogue<BN>(a, tmem, warp, m, valid, n0, sbias);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((u32)(BN < 32 ? 32 : BN)) : "memory");
+}
+
+// AMODE 0 with K > 64: the same tile, but K is streamed through a two-stage ring of 64-wide chunks (A chunk 128 x 128 B +
+// W chunk BN x 128 B per stage): the cp.async copies of chunk k+1 are in flight while the MMAs of chunk k run, a stage is
+// recycled when the tcgen05.commit of the MMAs that read it has arrived on its mbarrier, and the small footprint
+// (40-64 KB instead of 83-198 KB) keeps 3-5 CTAs resident per SM.
+__device__ __forceinline__ void mbar_wait_or_trap(u64* bar, u32 parity) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < 4000000000ll) {             // ~2 s of SM clocks
+        u32 ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();                                           // a lost arrival must fail the launch, not hang the GPU
+}
+
+template <int BN>
+__global__ void __launch_bounds__(128)
+tc_gemm_pipe_kernel(const TcArgs a) {
+    constexpr int S = 2;
+    constexpr u32 STAGE = 16384u + (u32)BN * 128u;
+    extern __shared__ unsigned char tc_raw[];
+    __shared__ alignas(8) u64 mbar_free[S];
+    __shared__ u32 tmem_slot;
+    __shared__ int koff[64];
+    __shared__ long long rowoff_s[128];
+    __shared__ float sbias[BN];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int KB = a.Kpad >> 6;
+    const u32 s_base = (smem_u32(tc_raw) + 1023u) & ~1023u;
+    const long long m0 = (long long)blockIdx.x * 128;
+    const int n0 = blockIdx.y * BN;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((u32)(BN < 32 ? 32 : BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) { mbar_init(&mbar_free[0], 1); mbar_init(&mbar_free[1], 1); }
+    if (tid < BN) sbias[tid] = (a.bias && n0 + tid < a.N) ? a.bias[n0 + tid] : 0.f;
+    if (tid < KB * 8) koff[tid] = (tid * 8 < a.K) ? patch_col(a.g, tid * 8) : -1;
+    const int r = tid;
+    const long long m = m0 + r;
+    const bool valid = m < a.M;
+    rowoff_s[r] = valid ? patch_row(a.g, m) : -1;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const u32 tmem = tmem_slot;
+    const u32 idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(BN >> 3) << 17) | ((u32)(128 >> 4) << 24);
+
+    auto load_chunk = [&](int kb) {
+        const u32 sA = s_base + (u32)(kb % S) * STAGE, sB = sA + 16384u;
+        // 8 consecutive lanes copy the 8 x 16 B of one row's chunk (one full 128-byte line per row), 4 rows per warp instruction
+        const int c = tid & 7, ko = koff[kb * 8 + c];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float x = __uint_as_float(v[j]) + sbias[c0 + j];
-                f[j] = a.relu ? fmaxf(x, 0.f) : x;
-            }
-            if (a.out_bf16) {
-                __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.Y) + m * a.ldy + n0 + c0;
-                if (n0 + c0 + 16 <= a.N && vec_ok) {
-                    uint4 p0, p1;
-                    __nv_bfloat162 t;
-#define DQ_PACK(dst, i) t = __floats2bfloat162_rn(f[i], f[i + 1]); dst = *reinterpret_cast<u32*>(&t);
-                    DQ_PACK(p0.x, 0) DQ_PACK(p0.y, 2) DQ_PACK(p0.z, 4) DQ_PACK(p0.w, 6)
-                    DQ_PACK(p1.x, 8) DQ_PACK(p1.y, 10) DQ_PACK(p1.z, 12) DQ_PACK(p1.w, 14)
-#undef DQ_PACK
-                    reinterpret_cast<uint4*>(y)[0] = p0; reinterpret_cast<uint4*>(y)[1] = p1;
-                } else {
-                    for (int j = 0; j < 16; ++j) if (n0 + c0 + j < a.N) y[j] = __float2bfloat16(f[j]);
-                }
-            } else {
-                float* y = reinterpret_cast<float*>(a.Y) + m * a.ldy + n0 + c0;
-                for (int j = 0; j < 16; ++j) if (n0 + c0 + j < a.N) y[j] = f[j];
-            }
+        for (int j = 0; j < 8; ++j) {
+            const int rr = (tid >> 3) + 16 * j;
+            const long long ro = rowoff_s[rr];
+            const u32 dst = sA + (u32)rr * 128u + (u32)((c ^ (rr & 7)) << 4);
+            if (ro >= 0 && ko >= 0) cp_async16(dst, a.X + ro + ko);
+            else asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+        }
+        for (int i = tid; i < BN * 8; i += 128) {
+            const int c = i & 7, n = i >> 3;
+            cp_async16(sB + (u32)n * 128u + (u32)((c ^ (n & 7)) << 4), a.Wt + (size_t)(n0 + n) * a.Kpad + kb * 64 + c * 8);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    load_chunk(0);
+    for (int kb = 0; kb < KB; ++kb) {
+        if (kb + 1 < KB) {
+            if (kb + 1 >= S) mbar_wait_or_trap(&mbar_free[(kb + 1) % S], (u32)(((kb + 1) / S - 1) & 1));   // its previous readers are done
+            load_chunk(kb + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        fence_proxy_async();                                        // generic-proxy writes -> visible to the MMA (async proxy)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const u32 sA = s_base + (u32)(kb % S) * STAGE;
+            const uint64_t da = umma_smem_desc(sA), db = umma_smem_desc(sA + 16384u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar_free[kb % S])) : "memory");
         }
     }
+    mbar_wait_or_trap(&mbar_free[(KB - 1) % S], (u32)(((KB - 1) / S) & 1));      // the last commit covers every MMA
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_epilogue<BN>(a, tmem, warp, m, valid, n0, sbias);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
@@ -1163,8 +1267,20 @@ static dq_qnet_tc* tc_of(dq_qnet* h) {
     return tc;
 }
 
+static bool tc_pipe_enabled() {
+    static const bool on = [] { const char* e = getenv("DQ_TC_PIPE"); return !(e && e[0] == '0'); }();
+    return on;
+}
 template <int BN, int AMODE>
 static int launch_tc(const TcArgs& a, int npad, cudaStream_t st) {
+    if (AMODE == 0 && (a.Kpad >> 6) >= 2 && tc_pipe_enabled()) {
+        const size_t smem = 2 * (16384 + (size_t)BN * 128) + 1024;
+        QCUDA(cudaFuncSetAttribute(tc_gemm_pipe_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)((a.M + 127) / 128), npad / BN);
+        tc_gemm_pipe_kernel<BN><<<grid, 128, smem, st>>>(a);
+        count_launch();
+        return DQ_OK;
+    }
     const size_t smem = (size_t)(128 + BN) * (a.Kpad >> 6) * 128 + 1024;
     if (smem > 227 * 1024) return qfail(DQ_EINVAL, "tensor-core tile does not fit shared memory");
     QCUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
