@@ -881,9 +881,18 @@ struct TcArgs {
 
 // Epilogue of a 128 x BN accumulator tile: warp w owns TMEM lanes 32w..32w+31 = output rows; thread = one row.
 template <int BN>
-__device__ __forceinline__ void tc_epilogue(const TcArgs& a, u32 tmem, int warp, long long m, bool valid, int n0, const float* sbias) {
+__device__ __forceinline__ void tc_epilogue(const TcArgs& a, u32 tmem, int warp, long long m, bool valid, int n0, const float* sbias,
+                                            u32 stage_smem) {
     const u32 taddr = tmem + ((u32)(warp * 32) << 16);
     const bool vec_ok = (a.ldy & 7) == 0;
+    const int lane = threadIdx.x & 31;
+    // bf16 full-width tiles: a thread owns a ROW, so direct stores would touch 32 lines per warp instruction.  The warp's
+    // 32 x BN tile goes through shared memory (the operand stages are free once the MMAs have completed; 16-byte pieces
+    // XOR-swizzled by row) and leaves as full lines: BN/8 consecutive lanes write one row.
+    const bool staged = a.out_bf16 && vec_ok && n0 + BN <= a.N;
+    constexpr int PR = BN / 8;                          // 16-byte pieces per row
+    constexpr int SW = (PR < 8 ? PR : 8) - 1;
+    const u32 wbase = stage_smem + (u32)warp * (u32)(32 * BN * 2);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
         u32 v[16];
@@ -892,7 +901,7 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, u32 tmem, int warp,
                        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                      : "r"(taddr + (u32)c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (valid) {
+        if (valid || staged) {
             float f[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -908,7 +917,15 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, u32 tmem, int warp,
                     DQ_PACK(p0.x, 0) DQ_PACK(p0.y, 2) DQ_PACK(p0.z, 4) DQ_PACK(p0.w, 6)
                     DQ_PACK(p1.x, 8) DQ_PACK(p1.y, 10) DQ_PACK(p1.z, 12) DQ_PACK(p1.w, 14)
 #undef DQ_PACK
-                    reinterpret_cast<uint4*>(y)[0] = p0; reinterpret_cast<uint4*>(y)[1] = p1;
+                    if (staged) {
+                        const int q0 = c0 >> 3;
+                        const u32 d0 = wbase + (u32)lane * (u32)(BN * 2) + (u32)(((q0) ^ (lane & SW)) << 4);
+                        const u32 d1 = wbase + (u32)lane * (u32)(BN * 2) + (u32)(((q0 + 1) ^ (lane & SW)) << 4);
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(d0), "r"(p0.x), "r"(p0.y), "r"(p0.z), "r"(p0.w) : "memory");
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(d1), "r"(p1.x), "r"(p1.y), "r"(p1.z), "r"(p1.w) : "memory");
+                    } else {
+                        reinterpret_cast<uint4*>(y)[0] = p0; reinterpret_cast<uint4*>(y)[1] = p1;
+                    }
                 } else {
                     for (int j = 0; j < 16; ++j) if (n0 + c0 + j < a.N) y[j] = __float2bfloat16(f[j]);
                 }
@@ -916,6 +933,19 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, u32 tmem, int warp,
                 float* y = reinterpret_cast<float*>(a.Y) + m * a.ldy + n0 + c0;
                 for (int j = 0; j < 16; ++j) if (n0 + c0 + j < a.N) y[j] = f[j];
             }
+        }
+    }
+    if (staged) {
+        __syncwarp();
+        const long long mw = m - lane;                  // first row of this warp
+        __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(a.Y);
+#pragma unroll
+        for (int it = 0; it < PR; ++it) {
+            const int idx = it * 32 + lane, row = idx / PR, q = idx % PR;
+            uint4 val;
+            const u32 src = wbase + (u32)row * (u32)(BN * 2) + (u32)((q ^ (row & SW)) << 4);
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(src));
+            if (mw + row < a.M) *reinterpret_cast<uint4*>(yb + (mw + row) * a.ldy + n0 + q * 8) = val;
         }
     }
 }
@@ -983,31 +1013,40 @@ tc_gemm_kernel(const TcArgs a) {
         const long long b = valid ? m / P : b_lo;
         const int pos = valid ? (int)(m - b * P) : 0, oy = pos / a.g.oh, ox = pos - oy * a.g.oh;
         const u64* wds = swords + (int)(b - b_lo) * 36;
-        for (int kb = 0; kb < KB; ++kb) {
-            // K bits [64 kb, 64 kb + 64): bit k = layer k / T, tap k % T
-            u64 bits = 0;
-            if (valid) {
-                for (int ci = 0; ci < a.C; ++ci) {
-                    const int lo = ci * a.T - kb * 64;
-                    if (lo >= 64 || lo + a.T <= 0) continue;
-                    u32 taps = 0;
-                    for (int ky = 0; ky < a.g.ksz; ++ky) {
-                        const int bit = (oy * a.g.stride + ky) * a.H + ox * a.g.stride, w = bit >> 6, sh = bit & 63;
-                        u64 v = wds[ci * a.PW + w] >> sh;
-                        if (sh + a.g.ksz > 64 && w + 1 < a.PW) v |= wds[ci * a.PW + w + 1] << (64 - sh);
-                        taps |= (u32)(v & ((1u << a.g.ksz) - 1)) << (ky * a.g.ksz);
-                    }
-                    bits |= lo >= 0 ? ((u64)taps << lo) : ((u64)taps >> (-lo));
+        // this row's K bits: bit k = (layer k / T, tap k % T); per layer the ksz row segments of the patch are cut out of the
+        // layer bitmap with one funnel shift each (32-bit view: a segment never needs bits of a third word)
+        u64 kbits[3] = {0, 0, 0};
+        if (valid) {
+            const u32* w32 = reinterpret_cast<const u32*>(wds);
+            const int ksz = a.g.ksz, b0 = oy * a.g.stride * a.H + ox * a.g.stride;
+            const u32 kmask = (1u << ksz) - 1u;
+            for (int ci = 0; ci < a.C; ++ci) {
+                const u32* lw = w32 + ci * a.PW * 2;
+                u32 taps = 0;
+#pragma unroll 4
+                for (int ky = 0; ky < ksz; ++ky) {
+                    const int bit = b0 + ky * a.H, wi = bit >> 5;
+                    taps |= (__funnelshift_r(lw[wi], lw[wi + 1], bit & 31) & kmask) << (ky * ksz);
+                }
+                const int pos = ci * a.T, wq = pos >> 6, sh = pos & 63;
+                const u64 tv = (u64)taps;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    if (q == wq) kbits[q] |= tv << sh;
+                    if (q == wq + 1 && sh) kbits[q] |= tv >> (64 - sh);
                 }
             }
+        }
+        for (int kb = 0; kb < KB; ++kb) {
+            const u64 bits = kb == 0 ? kbits[0] : (kb == 1 ? kbits[1] : kbits[2]);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const u32 x = (u32)(bits >> (8 * c)) & 0xFFu;
                 const u32 dst = sA + (u32)kb * 16384u + (u32)r * 128u + (u32)((c ^ (r & 7)) << 4);
-                const u32 w0 = ((x & 1u) * 0x3F80u) | (((x >> 1) & 1u) * 0x3F800000u);
-                const u32 w1 = (((x >> 2) & 1u) * 0x3F80u) | (((x >> 3) & 1u) * 0x3F800000u);
-                const u32 w2 = (((x >> 4) & 1u) * 0x3F80u) | (((x >> 5) & 1u) * 0x3F800000u);
-                const u32 w3 = (((x >> 6) & 1u) * 0x3F80u) | (((x >> 7) & 1u) * 0x3F800000u);
+                const u32 w0 = ((x & 1u) * 0x3F80u) | ((x & 2u) * 0x1FC00000u);          // bf16 1.0 = 0x3F80
+                const u32 w1 = (((x >> 2) & 1u) * 0x3F80u) | (((x >> 2) & 2u) * 0x1FC00000u);
+                const u32 w2 = (((x >> 4) & 1u) * 0x3F80u) | (((x >> 4) & 2u) * 0x1FC00000u);
+                const u32 w3 = (((x >> 6) & 1u) * 0x3F80u) | (((x >> 6) & 2u) * 0x1FC00000u);
                 asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
             }
         }
@@ -1034,7 +1073,7 @@ tc_gemm_kernel(const TcArgs a) {
     mbar_wait(&mbar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    tc_epilogue<BN>(a, tmem, warp, m, valid, n0, sbias);
+    tc_epilogue<BN>(a, tmem, warp, m, valid, n0, sbias, s_base);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
@@ -1133,7 +1172,7 @@ tc_gemm_pipe_kernel(const TcArgs a) {
     }
     mbar_wait_or_trap(&mbar_free[(KB - 1) % S], (u32)(((KB - 1) / S) & 1));      // the last commit covers every MMA
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    tc_epilogue<BN>(a, tmem, warp, m, valid, n0, sbias);
+    tc_epilogue<BN>(a, tmem, warp, m, valid, n0, sbias, s_base);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
