@@ -485,7 +485,7 @@ def run_b200(args):
                "episodes": int(len(life)), "mean_lifetime_cycles": float(life.mean()), "standard_error": float(life.std() / np.sqrt(len(life))),
                "logical_error_rate_per_cycle": float(1.0 / life.mean()), "reference_published_mean_lifetime": 270.42,
                "eval_seconds": time.perf_counter() - t0,
-               "trained_here": "profiles/r1_train_curriculum_dp_p007.json: 303.5 +- 3.3 cycles after 132 s of training from scratch"}
+               "trained_here": "profiles/r1_train_curriculum_dp_p007.json: 342.9 +- 3.7 cycles after 109 s of training from scratch"}
         ev_env.close()
 
     if rank == 0:
