@@ -959,7 +959,7 @@ tc_gemm_kernel(const TcArgs a) {
     extern __shared__ unsigned char tc_raw[];
     __shared__ alignas(8) u64 mbar;
     __shared__ u32 tmem_slot;
-    __shared__ int koff[64];                                        // AMODE 0: element offset of every 8-wide k chunk
+    __shared__ int koff[128];                                       // AMODE 0: element offset of every 8-wide k chunk (K <= 1024)
     __shared__ float sbias[BN];
     __shared__ u64 swords[AMODE == 1 ? 36 * 16 : 1];                // AMODE 1: packed words of the tile's samples
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -1103,7 +1103,7 @@ tc_gemm_pipe_kernel(const TcArgs a) {
     extern __shared__ unsigned char tc_raw[];
     __shared__ alignas(8) u64 mbar_free[S];
     __shared__ u32 tmem_slot;
-    __shared__ int koff[64];
+    __shared__ int koff[128];                                       // element offset of every 8-wide k chunk (K <= 1024)
     __shared__ long long rowoff_s[128];
     __shared__ float sbias[BN];
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -1180,76 +1180,100 @@ tc_gemm_pipe_kernel(const TcArgs a) {
 }
 
 // Fused head for the acting path: y = x W + b for the last (tiny) dense layer, then the dueling combination.
-// 4 adjacent lanes share a sample, each owning a quarter of the N outputs; W ([K][N], N <= 64) and the CTA's 32 input rows
-// are staged in shared memory with all their global loads in flight together.
+// 4 adjacent lanes share a sample; lane p owns the 4-column groups p, p+4, p+8, ... of the N outputs, so every weight read is
+// one 128-bit shared load shared by all samples of the warp.  W (rows padded to a multiple of 4), the bias and the CTA's 32
+// input rows are staged in shared memory with all their global loads in flight together.
 constexpr int kHeadSamples = 32;
-template <int MAXN>
+template <int MAXG>                                     // 4-column groups per lane: N <= 16 * MAXG
 __global__ void __launch_bounds__(128)
 head_dueling_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
                     float* __restrict__ q, long long B, int K, int N, int A, int dueling) {
-    extern __shared__ float hw[];                      // W [K][N], bias [N], x tile [32][K]
-    float* hb = hw + K * N;
-    float* hx = hb + N;
+    extern __shared__ __align__(16) float hw[];         // W [K][N4], bias [N4], x tile [32][K]
+    const int N4 = (N + 3) & ~3, G = N4 >> 2;
+    float* hb = hw + K * N4;
+    float* hx = hb + N4;
     const int tid = threadIdx.x;
     const long long b0 = (long long)blockIdx.x * kHeadSamples;
     const int nrow = (int)min((long long)kHeadSamples, B - b0);
-    for (int i0 = 0; i0 < K * N; i0 += 8 * 128) {      // 8 loads in flight per thread, then the shared stores
-        float w8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) w8[j] = __ldg(W + min(i0 + j * 128 + tid, K * N - 1));
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int i = i0 + j * 128 + tid;
-            if (i < K * N) hw[i] = w8[j];
-        }
-    }
-    for (int i = tid; i < N; i += 128) hb[i] = bias[i];
     {
-        const int tot = nrow * K;                      // the CTA's rows are contiguous in x
+        const int nw = K * N, tot = nrow * K;
         const float* xs = x + b0 * K;
-        for (int i0 = 0; i0 < tot; i0 += 8 * 128) {
-            float x8[8];
+        for (int i0 = 0; i0 < nw; i0 += 16 * 128) {     // 16 loads in flight per thread, then the shared stores
+            float w16[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x8[j] = __ldg(xs + min(i0 + j * 128 + tid, tot - 1));
+            for (int j = 0; j < 16; ++j) w16[j] = __ldg(W + min(i0 + j * 128 + tid, nw - 1));
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 const int i = i0 + j * 128 + tid;
-                if (i < tot) hx[i] = x8[j];
+                if (i < nw) { const int k = i / N; hw[k * N4 + (i - k * N)] = w16[j]; }
+            }
+        }
+        if (N4 != N) for (int k = tid; k < K; k += 128) for (int c = N; c < N4; ++c) hw[k * N4 + c] = 0.f;
+        for (int i = tid; i < N4; i += 128) hb[i] = i < N ? bias[i] : 0.f;
+        for (int i0 = 0; i0 < tot; i0 += 16 * 128) {
+            float x16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x16[j] = __ldg(xs + min(i0 + j * 128 + tid, tot - 1));
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int i = i0 + j * 128 + tid;
+                if (i < tot) hx[i] = x16[j];
             }
         }
     }
     __syncthreads();
-    constexpr int NP = MAXN / 4;                       // outputs per lane
-    const int s = tid >> 2, part = tid & 3, np = (N + 3) >> 2, nbeg = part * np;
+    const int s = tid >> 2, part = tid & 3;
     const bool live = s < nrow;
-    float y[NP];
+    const int cnt = (G - part + 3) >> 2;                // groups part, part+4, ... < G
+    float4 y[MAXG];
 #pragma unroll
-    for (int j = 0; j < NP; ++j) y[j] = (j < np && nbeg + j < N) ? hb[nbeg + j] : 0.f;
+    for (int i = 0; i < MAXG; ++i) y[i] = (i < cnt) ? reinterpret_cast<const float4*>(hb)[part + 4 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) {
         const float* xr = hx + s * K;
         for (int k = 0; k < K; ++k) {
             const float xv = xr[k];
-            const float* wr = hw + k * N + nbeg;
+            const float4* wr = reinterpret_cast<const float4*>(hw + k * N4) + part;
 #pragma unroll
-            for (int j = 0; j < NP; ++j) if (j < np && nbeg + j < N) y[j] = fmaf(xv, wr[j], y[j]);
+            for (int i = 0; i < MAXG; ++i) {
+                if (i < cnt) {
+                    const float4 w = wr[4 * i];
+                    y[i].x = fmaf(xv, w.x, y[i].x); y[i].y = fmaf(xv, w.y, y[i].y);
+                    y[i].z = fmaf(xv, w.z, y[i].z); y[i].w = fmaf(xv, w.w, y[i].w);
+                }
+            }
         }
     }
     const long long b = b0 + s;
     if (dueling) {
-        float sum = 0.f;                               // advantages are outputs 1..N-1, the state value is output 0
+        float sum = 0.f;                                // advantages are outputs 1..N-1, the state value is output 0
 #pragma unroll
-        for (int j = 0; j < NP; ++j) if (j < np && nbeg + j < N && nbeg + j > 0) sum += y[j];
+        for (int i = 0; i < MAXG; ++i) {
+            const int c0 = 4 * (part + 4 * i);
+            const float e[4] = {y[i].x, y[i].y, y[i].z, y[i].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (i < cnt && c0 + u >= 1 && c0 + u < N) sum += e[u];
+        }
         sum += __shfl_xor_sync(0xffffffffu, sum, 1);
         sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        const float v0 = __shfl_sync(0xffffffffu, y[0], (tid & 31) & ~3);
+        const float v0 = __shfl_sync(0xffffffffu, y[0].x, (tid & 31) & ~3);
         const float base = v0 - sum / (float)A;
         if (live) {
 #pragma unroll
-            for (int j = 0; j < NP; ++j) if (j < np && nbeg + j < N && nbeg + j > 0) q[b * A + nbeg + j - 1] = base + y[j];
+            for (int i = 0; i < MAXG; ++i) {
+                const int c0 = 4 * (part + 4 * i);
+                const float e[4] = {y[i].x, y[i].y, y[i].z, y[i].w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (i < cnt && c0 + u >= 1 && c0 + u < N) q[b * A + c0 + u - 1] = base + e[u];
+            }
         }
     } else if (live) {
 #pragma unroll
-        for (int j = 0; j < NP; ++j) if (j < np && nbeg + j < N) q[b * A + nbeg + j] = y[j];
+        for (int i = 0; i < MAXG; ++i) {
+            const int c0 = 4 * (part + 4 * i);
+            const float e[4] = {y[i].x, y[i].y, y[i].z, y[i].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (i < cnt && c0 + u < N) q[b * A + c0 + u] = e[u];
+        }
     }
 }
 // fp32 [K][N] -> bf16 [Npad][Kpad] (transposed, zero padded)
@@ -1343,6 +1367,10 @@ static int tc_check(const dq_qnet* h) {
     for (int l = 0; l < c.n_conv; ++l) if (c.conv[l].filters % 8) return qfail(DQ_EINVAL, "conv filter counts must be multiples of 8 for the tensor-core path");
     for (int i = 0; i < c.n_hidden; ++i) if (c.fc_out[i] % 8) return qfail(DQ_EINVAL, "hidden dense widths must be multiples of 8 for the tensor-core path");
     if (c.C * c.PW > 36 || (128 / c.conv[0].P + 2) > 16) return qfail(DQ_EINVAL, "first layer too large for the tensor-core path");
+    for (int l = 1; l < c.n_conv; ++l)
+        if (c.conv[l].ksz * c.conv[l].ksz * c.conv[l - 1].filters > 1024) return qfail(DQ_EINVAL, "conv layer K > 1024 is not supported on the tensor-core path");
+    for (int i = 0; i < c.n_hidden + 1 && i < c.n_fc; ++i)
+        if (c.fc_in[i] > 1024) return qfail(DQ_EINVAL, "dense layer K > 1024 is not supported on the tensor-core path");
     return DQ_OK;
 }
 
@@ -1399,9 +1427,15 @@ extern "C" int dq_qnet_forward_tc(dq_qnet* h, const float* params, const uint64_
     const float* xf = h->act_fc[c.n_hidden];
     if (c.dueling) {
         const int i = c.n_fc - 1, K = c.fc_in[i], N = c.fc_out[i], t = c.n_conv + i;
-        const size_t smem = (size_t)(K * N + N + kHeadSamples * K) * sizeof(float);
+        const int N4 = (N + 3) & ~3;
+        const size_t smem = (size_t)(K * N4 + N4 + kHeadSamples * K) * sizeof(float);
+        const unsigned hgrid = (unsigned)((batch + kHeadSamples - 1) / kHeadSamples);
         if (N <= 64 && smem <= 48 * 1024) {
-            head_dueling_kernel<64><<<(unsigned)((batch + kHeadSamples - 1) / kHeadSamples), 128, smem, st>>>(xf, params + c.w_off[t], params + c.b_off[t], q_out, batch, K, N, c.A, 1);
+            head_dueling_kernel<4><<<hgrid, 128, smem, st>>>(xf, params + c.w_off[t], params + c.b_off[t], q_out, batch, K, N, c.A, 1);
+            count_launch();
+        } else if (N <= 128 && smem <= 200 * 1024) {
+            QCUDA(cudaFuncSetAttribute(head_dueling_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            head_dueling_kernel<8><<<hgrid, 128, smem, st>>>(xf, params + c.w_off[t], params + c.b_off[t], q_out, batch, K, N, c.A, 1);
             count_launch();
         } else {
             launch_gemm_fwd(xf, dense_patch(K), params + c.w_off[t], params + c.b_off[t], h->act_fc[i], batch, N, K, 0, st);

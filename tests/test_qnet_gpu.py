@@ -339,6 +339,24 @@ def test_tensor_core_forward_tracks_fp32():
     q.close()
 
 
+@pytest.mark.parametrize("shape,actions", [((6, 11, 11), 26), ((9, 15, 15), 99), ((4, 7, 7), 10)])
+def test_tensor_core_forward_other_geometries(shape, actions):
+    """The bf16 path on the other BASELINE geometries (d=5 X, d=7 DP: 4 words per layer and K > 64 in layer 1, d=3 X) with
+    Glorot weights: Q within 2 % of the fp32 path's scale on a ragged batch."""
+    import torch
+    from deepq_decoding_b200.qnet import QNetwork
+    cc = REF_CC if shape[1] >= 11 else [[64, 3, 2], [32, 2, 1]]
+    q = QNetwork(cc, REF_FF, shape, actions, dueling=True, max_batch=2048, seed=5)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    boards = (torch.rand((1337,) + shape, generator=g) < 0.15).to(torch.uint8).cuda()
+    want = q.forward(boards).clone()
+    got = q.forward(boards, precision="bf16")
+    scale = want.abs().max().item()
+    assert scale > 1e-3
+    assert (got - want).abs().max().item() < 0.02 * scale + 1e-3, ((got - want).abs().max().item(), scale)
+    q.close()
+
+
 def test_curriculum_controller_and_memory_snapshot(tmp_path):
     """Controller.py's loop in process: two error rates, two grid points each, weights + replay carried forward."""
     import torch
