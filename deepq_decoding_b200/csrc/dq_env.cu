@@ -290,9 +290,18 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
 
     // The rendered layer bitmaps and the summed syndrome of the tile's lattices live in shared memory for the whole launch
     // (and in the state rows, kept in step): a step only re-renders what it changes.
-    for (int i = tid; i < C * PW * kEpc; i += kThreads) {
-        const int row = i / kEpc, slot = i - row * kEpc;
-        sm.bm[slot][row] = p.state[(ROW_BM + row) * np + env0 + slot];
+    for (int i0 = 0; i0 < C * PW * kEpc; i0 += 6 * kThreads) {        // the loads of a batch are in flight together
+        u64 w6[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int i = min(i0 + j * kThreads + tid, C * PW * kEpc - 1), row = i / kEpc;
+            w6[j] = p.state[(ROW_BM + row) * np + env0 + (i - row * kEpc)];
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int i = i0 + j * kThreads + tid, row = i / kEpc;
+            if (i < C * PW * kEpc) sm.bm[i - row * kEpc][row] = w6[j];
+        }
     }
     if (tid < kEpc) sm.sum[tid] = p.state[ROW_SUM * np + env0 + tid];
     for (int i = tid; i < 256; i += kThreads)

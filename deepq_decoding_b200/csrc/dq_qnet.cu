@@ -69,7 +69,21 @@ conv1_bits_kernel(const u64* __restrict__ packed, long long stride, long long ba
                   const float* __restrict__ dY, float* __restrict__ dW) {
     extern __shared__ float sW[];                      // forward: W [K][F]; backward: dW accumulator [K][F]
     const int F = L.filters, K = L.K;
-    for (int i = threadIdx.x; i < K * F; i += blockDim.x) sW[i] = BACKWARD ? 0.f : W[i];
+    if (BACKWARD) {
+        for (int i = threadIdx.x; i < K * F; i += blockDim.x) sW[i] = 0.f;
+    } else {
+        const int n = K * F, bd = blockDim.x;           // 8 loads in flight per thread, then the shared stores
+        for (int i0 = 0; i0 < n; i0 += 8 * bd) {
+            float w8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w8[j] = __ldg(W + min(i0 + j * bd + (int)threadIdx.x, n - 1));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = i0 + j * bd + (int)threadIdx.x;
+                if (i < n) sW[i] = w8[j];
+            }
+        }
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const long long total = batch * L.P;
