@@ -35,6 +35,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION, from the environment or
+# /etc/nccl.conf) off it
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 D, VD, P, MODEL, USE_Y = 5, 5, 0.007, "DP", False
 N_PER_GPU = 16384
