@@ -305,6 +305,28 @@ def test_fit_runs_and_learns_something():
     env.close()
 
 
+def test_fit_and_test_run_on_the_d7_workload():
+    """BASELINE config C5's geometry end to end: d=7 depolarising lattices (9 x 15 x 15 observations, 99 actions, min-weight
+    referee), bf16 acting, bf16 no-grad forwards, fp32 gradients; then a greedy evaluation."""
+    from deepq_decoding_b200 import agents as A
+    from deepq_decoding_b200.envs import VecSurfaceCodeEnv
+    env = VecSurfaceCodeEnv(7, 0.004, 0.004, "DP", False, 7, None, n_envs=256, seed=4)
+    assert env.observation_space.shape == (9, 15, 15) and env.num_actions == 99
+    spec = A.build_convolutional_nn(REF_CC, REF_FF, env.observation_space.shape, env.num_actions)
+    pol = A.LinearAnnealedPolicy(A.EpsGreedyQPolicy(masked_greedy=False), attr="eps", value_max=1.0, value_min=0.05, value_test=0.0, nb_steps=20000)
+    dqn = A.DQNAgent(model=spec, nb_actions=99, memory=A.SequentialMemory(limit=100000), nb_steps_warmup=2000, target_model_update=5000,
+                     policy=pol, test_policy=A.GreedyQPolicy(masked_greedy=True), gamma=0.99, enable_dueling_network=True, batch_size=256,
+                     act_precision="bf16", target_precision="bf16")
+    dqn.compile(A.Adam(lr=1e-4), max_envs=256)
+    before = dqn.model.params.clone()
+    hist = dqn.fit(env, nb_steps=30000, verbose=0, episode_averaging_length=200, success_threshold=1e9, stopping_patience=1e9, min_nb_steps=0).history
+    assert len(hist["episode"]) > 20 and any(x == x for x in hist["loss"]) and np.isfinite([x for x in hist["loss"] if x == x]).all()
+    assert float((dqn.model.params - before).abs().max()) > 1e-5 and bool(np.isfinite(dqn.model.params.cpu().numpy()).all())
+    th = dqn.test(env, nb_episodes=256, verbose=0).history
+    assert len(th["episode_lifetime"]) == 256 and min(th["episode_lifetime"]) >= 7 and all(l % 7 == 0 for l in th["episode_lifetime"])
+    env.close()
+
+
 def test_tensor_core_forward_tracks_fp32():
     """bf16 tcgen05 path (acting) against the fp32 SIMT path and torch: layer by layer, then Q and the greedy choice.
     Tolerances: bf16 has 8 mantissa bits; activations are O(1), Q ~ 30 -> |dQ| < 0.5, argmax agreement > 97 %
