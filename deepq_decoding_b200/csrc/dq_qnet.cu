@@ -904,9 +904,11 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, u32 tmem, int warp,
     // 32 x BN tile goes through shared memory (the operand stages are free once the MMAs have completed; 16-byte pieces
     // XOR-swizzled by row) and leaves as full lines: BN/8 consecutive lanes write one row.
     const bool staged = a.out_bf16 && vec_ok && n0 + BN <= a.N;
+    // fp32 output whose rows are dense (ldy == N, one N tile, e.g. the Dense -> num_actions layer): staged the same way
+    const bool dense32 = !a.out_bf16 && a.ldy == a.N && a.N <= BN && gridDim.y == 1;
+    const u32 wbase = stage_smem + (u32)warp * (u32)(32 * BN * (dense32 ? 4 : 2));      // this warp's 32-row staging tile
     constexpr int PR = BN / 8;                          // 16-byte pieces per row
     constexpr int SW = (PR < 8 ? PR : 8) - 1;
-    const u32 wbase = stage_smem + (u32)warp * (u32)(32 * BN * 2);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
         u32 v[16];
@@ -915,7 +917,7 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, u32 tmem, int warp,
                        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                      : "r"(taddr + (u32)c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (valid || staged) {
+        if (valid || staged || dense32) {
             float f[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -943,10 +945,26 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, u32 tmem, int warp,
                 } else {
                     for (int j = 0; j < 16; ++j) if (n0 + c0 + j < a.N) y[j] = __float2bfloat16(f[j]);
                 }
+            } else if (dense32) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < a.N) asm volatile("st.shared.f32 [%0], %1;" ::"r"(wbase + (u32)((lane * a.N + c0 + j) * 4)), "f"(f[j]) : "memory");
             } else {
                 float* y = reinterpret_cast<float*>(a.Y) + m * a.ldy + n0 + c0;
                 for (int j = 0; j < 16; ++j) if (n0 + c0 + j < a.N) y[j] = f[j];
             }
+        }
+    }
+    if (dense32) {                                      // the warp's 32 rows are one contiguous span of the fp32 output
+        __syncwarp();
+        const long long mw = m - lane;
+        const long long rows = min(32ll, a.M - mw);
+        float* yb = reinterpret_cast<float*>(a.Y) + mw * a.N;
+        const int tot = rows > 0 ? (int)rows * a.N : 0;
+        for (int i = lane; i < tot; i += 32) {
+            float val;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(wbase + (u32)(i * 4)));
+            yb[i] = val;
         }
     }
     if (staged) {
@@ -1109,10 +1127,9 @@ __device__ __forceinline__ void mbar_wait_or_trap(u64* bar, u32 parity) {
     __trap();                                           // a lost arrival must fail the launch, not hang the GPU
 }
 
-template <int BN>
+template <int BN, int S>
 __global__ void __launch_bounds__(128)
 tc_gemm_pipe_kernel(const TcArgs a) {
-    constexpr int S = 2;
     constexpr u32 STAGE = 16384u + (u32)BN * 128u;
     extern __shared__ unsigned char tc_raw[];
     __shared__ alignas(8) u64 mbar_free[S];
@@ -1130,7 +1147,7 @@ tc_gemm_pipe_kernel(const TcArgs a) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((u32)(BN < 32 ? 32 : BN)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 0) { mbar_init(&mbar_free[0], 1); mbar_init(&mbar_free[1], 1); }
+    if (tid == 0) for (int s = 0; s < S; ++s) mbar_init(&mbar_free[s], 1);
     if (tid < BN) sbias[tid] = (a.bias && n0 + tid < a.N) ? a.bias[n0 + tid] : 0.f;
     if (tid < KB * 8) koff[tid] = (tid * 8 < a.K) ? patch_col(a.g, tid * 8) : -1;
     const int r = tid;
@@ -1162,15 +1179,21 @@ tc_gemm_pipe_kernel(const TcArgs a) {
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    load_chunk(0);
+    // S - 1 chunks ahead of the math; one cp.async group is committed per iteration (possibly empty) so that
+    // "all but the newest S - 1 groups have landed" always means "chunk kb has landed"
+    for (int kb = 0; kb < S - 1; ++kb) {
+        if (kb < KB) load_chunk(kb);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     for (int kb = 0; kb < KB; ++kb) {
-        if (kb + 1 < KB) {
-            if (kb + 1 >= S) mbar_wait_or_trap(&mbar_free[(kb + 1) % S], (u32)(((kb + 1) / S - 1) & 1));   // its previous readers are done
-            load_chunk(kb + 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        const int nk = kb + S - 1;                                  // the chunk to prefetch now
+        if (nk < KB) {
+            if (nk >= S) mbar_wait_or_trap(&mbar_free[nk % S], (u32)((nk / S - 1) & 1));   // its stage's previous readers are done
+            load_chunk(nk);
         } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
+        asm volatile("cp.async.wait_group %0;" ::"n"(S - 1) : "memory");
         fence_proxy_async();                                        // generic-proxy writes -> visible to the MMA (async proxy)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -1351,10 +1374,18 @@ static bool tc_pipe_enabled() {
 template <int BN, int AMODE>
 static int launch_tc(const TcArgs& a, int npad, cudaStream_t st) {
     if (AMODE == 0 && (a.Kpad >> 6) >= 2 && tc_pipe_enabled()) {
-        const size_t smem = 2 * (16384 + (size_t)BN * 128) + 1024;
-        QCUDA(cudaFuncSetAttribute(tc_gemm_pipe_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((unsigned)((a.M + 127) / 128), npad / BN);
-        tc_gemm_pipe_kernel<BN><<<grid, 128, smem, st>>>(a);
+        // few tiles (at most ~2 per SM) and a long K: four stages keep three chunks in flight per CTA; otherwise two stages
+        // and more CTAs per SM
+        const bool deep = (long long)grid.x * grid.y <= 2 * 148 && (a.Kpad >> 6) >= 4;
+        const size_t smem = (deep ? 4 : 2) * (16384 + (size_t)BN * 128) + 1024;
+        if (deep) {
+            QCUDA(cudaFuncSetAttribute(tc_gemm_pipe_kernel<BN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tc_gemm_pipe_kernel<BN, 4><<<grid, 128, smem, st>>>(a);
+        } else {
+            QCUDA(cudaFuncSetAttribute(tc_gemm_pipe_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tc_gemm_pipe_kernel<BN, 2><<<grid, 128, smem, st>>>(a);
+        }
         count_launch();
         return DQ_OK;
     }
