@@ -316,6 +316,46 @@ def test_full_size_properties():
     env.close()
 
 
+def test_full_size_c5_rollout_properties():
+    """BASELINE config 5 per-GPU shape (d=7 DP p=0.011, 8192 lattices, min-weight referee): a 40-step rollout launch equals 40
+    single-step launches on every lattice, and the size-independent invariants hold on its outputs."""
+    import ctypes as C
+    import torch
+    from deepq_decoding_b200 import _lib
+    from deepq_decoding_b200.envs import VecSurfaceCodeEnv
+    n, S, slots = 8192, 40, 3
+    a = VecSurfaceCodeEnv(7, 0.011, 0.011, "DP", False, 7, None, n_envs=n, seed=9)
+    b = VecSurfaceCodeEnv(7, 0.011, 0.011, "DP", False, 7, None, n_envs=n, seed=9)
+    L = _lib.lib()
+    p = lambda x: C.c_void_p(x.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    obs0 = a.reset().clone()
+    assert torch.equal(obs0, b.reset())
+    marker = obs0[0, 0].clone(); marker[::2, ::2] = 0
+    legal_before = a.legal_mask.clone()
+    ring = torch.zeros((slots,) + tuple(a.obs.shape), dtype=torch.uint8, device="cuda")
+    out = a.rollout_random(S, ring, keep=("reward", "done", "lifetime", "actions", "legal"))
+    ident = a.num_actions - 1
+    picks = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for s in range(S):
+        _lib.check(L.dq_env_step_random(b._h, p(b.obs), p(b.reward), p(b.done), p(b.lifetime), p(b.legal_mask), p(picks), 1, st))
+        assert torch.equal(out["actions"][s], picks) and torch.equal(out["done"][s], b.done) and torch.equal(out["lifetime"][s], b.lifetime), s
+        # the pick is a legal action of the mask the previous step published; identity is always legal
+        act = out["actions"][s].long()
+        word = torch.gather(legal_before, 1, (act >> 6)[:, None])[:, 0]
+        assert bool(((word >> (act & 63)) & 1).all()), s
+        legal_before = out["legal"][s]
+        assert bool(((legal_before[:, ident >> 6] >> (ident & 63)) & 1).all())
+        assert bool((out["lifetime"][s] % 7 == 0).all())
+        assert not bool(((out["reward"][s] == 1.0) & (out["done"][s] != 0)).any())
+    assert torch.equal(a.get_state_words(), b.get_state_words())
+    last = ring[(S - 1) % slots]
+    assert torch.equal(last, b.obs) and int(last.max()) <= 1
+    m = last[:, :7].clone(); m[:, :, ::2, ::2] = 0
+    assert bool((m == marker).all())
+    a.close(); b.close()
+
+
 def test_errors_are_loud():
     from deepq_decoding_b200 import _lib
     from deepq_decoding_b200.envs import VecSurfaceCodeEnv
