@@ -1235,7 +1235,26 @@ head_dueling_kernel(const float* __restrict__ x, const float* __restrict__ W, co
     {
         const int nw = K * N, tot = nrow * K;
         const float* xs = x + b0 * K;
-        for (int i0 = 0; i0 < nw; i0 += 16 * 128) {     // 16 loads in flight per thread, then the shared stores
+        // one L2 round trip for the whole prologue: every load (24 of W, 16 of the row tile per thread) is issued before the
+        // first shared store; anything beyond 3072 weights / 2048 inputs goes through the batched loops below
+        float w24[24], x16[16];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) w24[j] = __ldg(W + min(j * 128 + tid, nw - 1));
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x16[j] = __ldg(xs + min(j * 128 + tid, tot - 1));
+        const float bv = tid < N ? __ldg(bias + tid) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {
+            const int i = j * 128 + tid;
+            if (i < nw) { const int k = i / N; hw[k * N4 + (i - k * N)] = w24[j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int i = j * 128 + tid;
+            if (i < tot) hx[i] = x16[j];
+        }
+        if (tid < N4) hb[tid] = bv;
+        for (int i0 = 24 * 128; i0 < nw; i0 += 16 * 128) {
             float w16[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) w16[j] = __ldg(W + min(i0 + j * 128 + tid, nw - 1));
@@ -1246,15 +1265,14 @@ head_dueling_kernel(const float* __restrict__ x, const float* __restrict__ W, co
             }
         }
         if (N4 != N) for (int k = tid; k < K; k += 128) for (int c = N; c < N4; ++c) hw[k * N4 + c] = 0.f;
-        for (int i = tid; i < N4; i += 128) hb[i] = i < N ? bias[i] : 0.f;
-        for (int i0 = 0; i0 < tot; i0 += 16 * 128) {
-            float x16[16];
+        for (int i0 = 16 * 128; i0 < tot; i0 += 16 * 128) {
+            float y16[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) x16[j] = __ldg(xs + min(i0 + j * 128 + tid, tot - 1));
+            for (int j = 0; j < 16; ++j) y16[j] = __ldg(xs + min(i0 + j * 128 + tid, tot - 1));
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int i = i0 + j * 128 + tid;
-                if (i < tot) hx[i] = x16[j];
+                if (i < tot) hx[i] = y16[j];
             }
         }
     }
