@@ -919,10 +919,16 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, u32 tmem, int warp,
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (valid || staged || dense32) {
             float f[16];
+            const float4* sb4 = reinterpret_cast<const float4*>(sbias + c0);       // four 128-bit broadcast loads
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float x = __uint_as_float(v[j]) + sbias[c0 + j];
-                f[j] = a.relu ? fmaxf(x, 0.f) : x;
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 bq = sb4[j4];
+                const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float x = __uint_as_float(v[4 * j4 + u]) + bb[u];
+                    f[4 * j4 + u] = a.relu ? fmaxf(x, 0.f) : x;
+                }
             }
             if (a.out_bf16) {
                 __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.Y) + m * a.ldy + n0 + c0;
@@ -992,8 +998,9 @@ tc_gemm_kernel(const TcArgs a) {
     __shared__ alignas(8) u64 mbar;
     __shared__ u32 tmem_slot;
     __shared__ int koff[128];                                       // AMODE 0: element offset of every 8-wide k chunk (K <= 1024)
-    __shared__ float sbias[BN];
+    __shared__ alignas(16) float sbias[BN];
     __shared__ u64 swords[AMODE == 1 ? 36 * 16 : 1];                // AMODE 1: packed words of the tile's samples
+    __shared__ alignas(16) uint4 bf16lut[AMODE == 1 ? 256 : 1];     // AMODE 1: byte -> its 8 bits as 8 bf16 {0, 1.0}
     const int tid = threadIdx.x, warp = tid >> 5;
     const int KB = a.Kpad >> 6;                                     // 64-element k blocks
     const u32 s_base = (smem_u32(tc_raw) + 1023u) & ~1023u;         // swizzle atoms need 1024-byte alignment
@@ -1032,6 +1039,9 @@ tc_gemm_kernel(const TcArgs a) {
             }
         }
     } else {
+        for (int x = tid; x < 256; x += 128)
+            bf16lut[x] = make_uint4(((x & 1u) * 0x3F80u) | ((x & 2u) * 0x1FC00000u), (((x >> 2) & 1u) * 0x3F80u) | (((x >> 2) & 2u) * 0x1FC00000u),
+                                    (((x >> 4) & 1u) * 0x3F80u) | (((x >> 4) & 2u) * 0x1FC00000u), (((x >> 6) & 1u) * 0x3F80u) | (((x >> 6) & 2u) * 0x1FC00000u));
         // stage the packed words of the samples this tile touches
         const int P = a.g.P, rows = a.C * a.PW;
         const long long b_lo = m0 / P;
@@ -1075,11 +1085,8 @@ tc_gemm_kernel(const TcArgs a) {
             for (int c = 0; c < 8; ++c) {
                 const u32 x = (u32)(bits >> (8 * c)) & 0xFFu;
                 const u32 dst = sA + (u32)kb * 16384u + (u32)r * 128u + (u32)((c ^ (r & 7)) << 4);
-                const u32 w0 = ((x & 1u) * 0x3F80u) | ((x & 2u) * 0x1FC00000u);          // bf16 1.0 = 0x3F80
-                const u32 w1 = (((x >> 2) & 1u) * 0x3F80u) | (((x >> 2) & 2u) * 0x1FC00000u);
-                const u32 w2 = (((x >> 4) & 1u) * 0x3F80u) | (((x >> 4) & 2u) * 0x1FC00000u);
-                const u32 w3 = (((x >> 6) & 1u) * 0x3F80u) | (((x >> 6) & 2u) * 0x1FC00000u);
-                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+                const uint4 w = bf16lut[x];                                              // bf16 1.0 = 0x3F80
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
             }
         }
     }
@@ -1136,7 +1143,7 @@ tc_gemm_pipe_kernel(const TcArgs a) {
     __shared__ u32 tmem_slot;
     __shared__ int koff[128];                                       // element offset of every 8-wide k chunk (K <= 1024)
     __shared__ long long rowoff_s[128];
-    __shared__ float sbias[BN];
+    __shared__ alignas(16) float sbias[BN];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int KB = a.Kpad >> 6;
     const u32 s_base = (smem_u32(tc_raw) + 1023u) & ~1023u;
