@@ -82,6 +82,7 @@ class FusedAllreduceAdam:
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.n = int(n_params)
+        self._views = {}
         self._h = C.c_void_p()
         _lib.check(self.L.dq_comm_create(C.byref(self._h), self.rank, self.world, self.n, self.device.index or 0))
         mine = C.create_string_buffer(64)
@@ -96,7 +97,10 @@ class FusedAllreduceAdam:
         from .qnet import device_view
         ptr = C.c_void_p()
         self._lib.check(self.L.dq_comm_next_grads(self._h, C.byref(ptr)))
-        return device_view(ptr.value, (self.n,), "<f4", self.device)
+        view = self._views.get(ptr.value)                 # two buffers (update parity): wrap each once
+        if view is None:
+            view = self._views[ptr.value] = device_view(ptr.value, (self.n,), "<f4", self.device)
+        return view
 
     def step(self, params, m, v, optimizer, t, stream):
         p = lambda x: C.c_void_p(x.data_ptr())
