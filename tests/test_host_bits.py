@@ -166,3 +166,38 @@ def test_philox_extract_select(hb):
         pos = [i for i in range(64) if (x >> i) & 1]
         k = int(rng.integers(0, len(pos)))
         assert hb.hb_select64(x, k) == pos[k]
+
+
+def test_survey_structural_kats(hb):
+    """The structural known answers SURVEY.md section 8(c) extracted from the imported reference, asserted on BOTH the oracle
+    and the device helpers: d=3 centre-qubit syndromes, the d=5 plaquette-type map, logical operators, 8-neighbourhoods."""
+    # d = 3, centre qubit (1,1): X -> {(1,2),(2,1)}, Z -> {(1,1),(2,2)}, Y -> all four
+    o3 = O.OracleVecEnv(3, "DP", True, 3, 0.01, 0.01, 1, 0)
+    want = {1: {(1, 2), (2, 1)}, 3: {(1, 1), (2, 2)}, 2: {(1, 1), (2, 2), (1, 2), (2, 1)}}
+    for pauli, cells in want.items():
+        hidden = np.zeros((3, 3), np.int8); hidden[1, 1] = pauli
+        syn, _ = o3.syndrome_of(hidden)
+        assert {tuple(x) for x in np.argwhere(syn)} == cells
+        xb = to_word((hidden == 1) | (hidden == 2), 4); zb = to_word((hidden == 3) | (hidden == 2), 4)
+        got = from_word(hb.hb_true_syndrome(3, xb, zb), 4, 4, 4)
+        assert {tuple(x) for x in np.argwhere(got)} == cells
+    # d = 5 plaquette types (1 = flips on Z/Y, 3 = flips on X/Y, 0 = absent)
+    o5 = O.OracleVecEnv(5, "DP", False, 5, 0.01, 0.01, 1, 0)
+    a, b, ty = o5.stab_order()
+    tmap = np.zeros((6, 6), int); tmap[a, b] = ty
+    assert tmap.tolist() == [[0, 3, 0, 3, 0, 0], [0, 1, 3, 1, 3, 1], [1, 3, 1, 3, 1, 0], [0, 1, 3, 1, 3, 1], [1, 3, 1, 3, 1, 0], [0, 0, 3, 0, 3, 0]]
+    t1 = from_word(hb.hb_masks(5, 1), 6, 6, 6); t3 = from_word(hb.hb_masks(5, 2), 6, 6, 6)
+    assert np.array_equal(t1 * 1 + t3 * 3, tmap)
+    # logical operators: a full row of X has zero syndrome and label index 1, a full column of Z label index 2
+    row_x = np.zeros((5, 5), np.int8); row_x[2, :] = 1
+    col_z = np.zeros((5, 5), np.int8); col_z[:, 3] = 3
+    for hidden, label in ((row_x, 1), (col_z, 2)):
+        syn, lab = o5.syndrome_of(hidden)
+        assert not syn.any() and lab == label
+        xb = to_word((hidden == 1) | (hidden == 2), 6); zb = to_word((hidden == 3) | (hidden == 2), 6)
+        assert hb.hb_true_syndrome(5, xb, zb) == 0 and hb.hb_label(5, xb, zb) == label
+    # qubit_neighbours[0] = [1, 5, 6]; centre qubit 12 -> [11, 13, 7, 6, 8, 17, 16, 18]
+    for q, nb in ((0, {1, 5, 6}), (12, {11, 13, 7, 6, 8, 17, 16, 18})):
+        board = np.zeros((5, 5), np.int8); board[q // 5, q % 5] = 1
+        got = from_word(hb.hb_neighbours(5, to_word(board, 6)), 6, 5, 5)
+        assert {int(r * 5 + c) for r, c in np.argwhere(got)} == nb
