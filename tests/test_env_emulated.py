@@ -1,0 +1,161 @@
+"""CPU check of the CUDA environment kernel's SOURCE: `dq_env.cu` compiled by g++ under `tests/host/cuda_emu.h`
+(every CUDA thread a fiber, warp primitives and barriers as rendez-vous) and driven through the same C ABI,
+compared bit for bit with the oracle.
+
+This does not replace the `-m gpu` parity tests (those run the sm_100a build on a B200); it is what lets a
+kernel change be validated in this GPU-less container before GPU minutes are spent on it.  Cases mirror
+tests/test_env_gpu.py at sizes the fibers finish in seconds.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+import emu_env as E
+
+JOINT, SPLIT = 0, 1
+
+
+def random_luts(rng, d, model):
+    ns = d * d - 1
+    if model == "X" or d == 7:
+        la = rng.integers(0, 256, size=(1 << (ns // 2)) // 4 + 1, dtype=np.uint8) & 0x55
+        lb = rng.integers(0, 256, size=(1 << (ns // 2)) // 4 + 1, dtype=np.uint8) & 0x55
+        return SPLIT, la, (lb if model == "DP" else None)
+    return JOINT, rng.integers(0, 256, size=(1 << ns) // 4 + 1, dtype=np.uint8), None
+
+
+def make_pair(d, model, use_Y, vd, p, n, seed, base=0):
+    rng = np.random.default_rng(1000 * d + vd)
+    mode, la, lb = random_luts(rng, d, model)
+    env = E.EmuVecEnv(d, model, use_Y, vd, p, p, n, seed, base)
+    o = O.OracleVecEnv(d, model, use_Y, vd, p, p, n, seed, base)
+    env.set_referee(mode, la, lb)
+    o.set_referee(mode, la, lb)
+    return env, o
+
+
+def grid_to_pauli(xw, zw, d):
+    g = d + 1
+    out = np.zeros((d, d), np.int8)
+    for r in range(d):
+        for c in range(d):
+            x, z = (int(xw) >> (r * g + c)) & 1, (int(zw) >> (r * g + c)) & 1
+            out[r, c] = 2 if (x and z) else (1 if x else (3 if z else 0))
+    return out
+
+
+def compare_state(env, o, idx):
+    w = env.state_words()
+    for i in idx:
+        ost = o.get_env(int(i))
+        meta = int(w[E.ROW_META, i])
+        assert np.array_equal(grid_to_pauli(w[E.ROW_XB, i], w[E.ROW_ZB, i], env.d), ost["hidden"])
+        assert (meta & 0xFFFFFFFF) == ost["lifetime"] and ((meta >> 32) & 0x7FFFFFFF) == ost["attempts"]
+        assert bool(meta >> 63) == ost["done"]
+
+
+CASES = [(3, "X", False, 3, 0.05, 1),
+         (3, "X", False, 3, 0.05, 100),
+         (5, "X", False, 5, 0.02, 45),        # ragged tail CTA
+         (5, "DP", False, 5, 0.02, 64),
+         (5, "DP", True, 3, 0.03, 33),
+         (7, "DP", False, 7, 0.011, 40),
+         (7, "DP", True, 8, 0.02, 17),        # deepest volume, three mask words
+         (3, "DP", True, 2, 0.08, 48)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "d%d_%s_y%d_vd%d_n%d" % (c[0], c[1], c[2], c[3], c[5]))
+def test_emulated_kernel_trajectory_parity(case):
+    d, model, use_Y, vd, p, n = case
+    env, o = make_pair(d, model, use_Y, vd, p, n, seed=42, base=5)
+    rng = np.random.default_rng(d + n)
+    obs, legal = env.reset()
+    oobs, olegal = o.reset()
+    assert np.array_equal(obs, oobs) and np.array_equal(legal, olegal)
+    ndone = 0
+    for t in range(60):
+        acts = env.random_legal_actions(legal, t)
+        assert np.array_equal(acts, o.random_legal_actions(olegal, t)), "random-legal policy"
+        arb = rng.random(n) < 0.2
+        acts[arb] = rng.integers(-1, o.A + 1, size=int(arb.sum()))      # includes out-of-range -> identity
+        oacts = np.where((acts < 0) | (acts >= o.A), o.A - 1, acts).astype(np.int32)
+        obs, rew, done, life, legal = env.step(acts)
+        oobs, orew, odone, olife, olegal = o.step(oacts, auto_reset=True)
+        assert np.array_equal(obs, oobs), "obs t=%d" % t
+        assert np.array_equal(rew, orew) and np.array_equal(done, odone), "reward / done t=%d" % t
+        assert np.array_equal(life, olife), "lifetime t=%d" % t
+        assert np.array_equal(legal, olegal), "legal t=%d" % t
+        ndone += int(odone.sum())
+        if t % 20 == 0:
+            compare_state(env, o, rng.integers(0, n, size=min(n, 4)))
+    if n >= 40:
+        assert ndone > 0, "the trajectory should contain finished episodes"
+
+
+@pytest.mark.parametrize("d,model,n,auto_reset", [(5, "DP", 50, True), (3, "X", 37, True), (7, "DP", 20, True), (5, "X", 30, False)])
+def test_emulated_rollout_equals_single_steps_and_oracle(d, model, n, auto_reset):
+    """dq_env_rollout_random (one launch, many steps, observation ring) == dq_env_step_random launches == oracle."""
+    vd, p, steps, slots = d, 0.03, 24, 5
+    a, o = make_pair(d, model, False, vd, p, n, seed=7, base=3)
+    b, _ = make_pair(d, model, False, vd, p, n, seed=7, base=3)
+    _, olegal = o.reset()
+    a.reset(); b.reset()
+    a.policy_seek(11); b.policy_seek(11)
+    ring, rew, done, life, legal, acts = a.rollout_random(steps, slots, first_slot=2, auto_reset=auto_reset)
+    for s in range(steps):
+        oacts = o.random_legal_actions(olegal, 11 + s)
+        oobs, orew, odone, olife, olegal = o.step(oacts, auto_reset=auto_reset)
+        sobs, srew, sdone, slife, slegal, sacts = b.step_random(auto_reset=auto_reset)
+        assert np.array_equal(acts[s], oacts) and np.array_equal(sacts, oacts), "actions s=%d" % s
+        assert np.array_equal(rew[s], orew) and np.array_equal(srew, orew)
+        assert np.array_equal(done[s], odone) and np.array_equal(sdone, odone)
+        assert np.array_equal(life[s], olife) and np.array_equal(slife, olife)
+        assert np.array_equal(legal[s], olegal) and np.array_equal(slegal, olegal)
+        assert np.array_equal(sobs, oobs), "single-step obs s=%d" % s
+        if s >= steps - slots:                         # the ring keeps the last `slots` observations
+            assert np.array_equal(ring[(2 + s) % slots], oobs), "ring obs s=%d" % s
+    assert np.array_equal(a.state_words(), b.state_words())
+    # the device-side step counter advanced by the number of steps on both
+    nxt_a = a.step_random(auto_reset=auto_reset)[5]
+    assert np.array_equal(nxt_a, o.random_legal_actions(olegal, 11 + steps))
+
+
+def test_emulated_host_entry_points_and_unaligned_observation_buffers():
+    """dq_env_step_host, and observation pointers at 8-byte / odd alignment (the 64-bit and byte store paths of phase D)."""
+    d, model, n = 5, "DP", 21
+    env, o = make_pair(d, model, False, 5, 0.03, n, seed=3)
+    obs, legal = env.reset()
+    oobs, olegal = o.reset()
+    assert np.array_equal(obs, oobs)
+    for t in range(6):
+        acts = o.random_legal_actions(olegal, t)
+        got = env.step_host(acts)
+        want = o.step(acts, auto_reset=True)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
+        olegal = want[4]
+    import ctypes as C
+    for off in (8, 3):
+        acts = o.random_legal_actions(olegal, 100 + off)
+        nbytes = n * env.Cn * env.H * env.H
+        raw = np.zeros(nbytes + 64, np.uint8)
+        base = raw.ctypes.data
+        start = (-base) % 16 + off
+        view = raw[start:start + nbytes]
+        reward, done, life, legal2, _ = env._outs()
+        env._check(env.L.dq_env_step(env.h, E._p(acts), C.c_void_p(base + start), E._p(reward), E._p(done), E._p(life),
+                                     E._p(legal2), 1, None))
+        want = o.step(acts, auto_reset=True)
+        assert np.array_equal(view.reshape(want[0].shape), want[0]), "observation at alignment %d" % off
+        assert not raw[:start].any() and not raw[start + nbytes:].any(), "bytes outside the buffer were written"
+        olegal = want[4]
+
+
+def test_emulator_reports_deadlock_free_run_of_every_geometry():
+    """Reset alone (RESET=true instantiation) on every supported distance, single lattice and ragged tile."""
+    for d in (3, 5, 7):
+        for n in (1, 19):
+            env, o = make_pair(d, "DP", False, d, 0.05, n, seed=1)
+            obs, legal = env.reset()
+            oobs, olegal = o.reset()
+            assert np.array_equal(obs, oobs) and np.array_equal(legal, olegal)
