@@ -47,8 +47,11 @@ namespace dq {
 constexpr int kEpc = DQ_EPC;                       // lattices per CTA: 16*L observation bytes are a multiple of 16 for every L
 constexpr int kThreads = DQ_THREADS;
 constexpr int kWarps = kThreads / 32;
+constexpr int kPickGroup = (kThreads - 32) / kEpc;   // rollout steps whose policy words warps 1.. draw in one go (thread = (step, lattice))
+static_assert(kPickGroup >= 1, "warps 1.. must cover at least one step of the tile");
 constexpr int kMaxVd = 8;
 constexpr int kMaxLayers = kMaxVd + 3;
+constexpr int kStreamWords = (kEpc * kMaxLayers * 15 * 15 + 31) / 32 + 1;   // d = 7 at the deepest volume
 // The reference loops until a volume is non-trivial, forever if p_phys = p_meas = 0 on a clean frame.
 // A kernel must end: after this many attempts in one call the (trivial) volume is accepted.
 constexpr int kMaxAttemptsPerCall = 1 << 20;
@@ -66,6 +69,7 @@ struct EnvParams {
     int obs_bits;                               // C*H*H
     u32 ob_magic;                               // ceil(2^32 / obs_bits): g / obs_bits == umulhi(g, ob_magic) for g < 2^16
     u32 T, T1, T2, Tm;                          // thresholds (RNG contract)
+    u32 Tmx;                                    // max(T, Tm): the one-compare screen of generate_volume
     u32 k0, k1;                                 // Philox key
     u32 env_id_base;
     int ref_mode;
@@ -122,17 +126,32 @@ __device__ __forceinline__ u64 generate_volume(const EnvParams& p, u32* acc, int
         bool evq = false;
         for (int r = 0; r < R; r += 2) {
             const Philox4 u0 = philox4x32_10(env_id, attempts, (u32)(r * 32 + lane), 0u, p.k0, p.k1);
-            const Philox4 u1 = philox4x32_10(env_id, attempts, (u32)(r * 32 + 32 + lane), 0u, p.k0, p.k1);
+            Philox4 u1;
+            u1.x = u1.y = u1.z = u1.w = 0xffffffffu;                      // an odd R has no second round: words that can never fire
+            if (r + 1 < R) u1 = philox4x32_10(env_id, attempts, (u32)(r * 32 + 32 + lane), 0u, p.k0, p.k1);
             const u32 uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+            // Screen the lane's eight draws against the larger threshold with one predicate chain; only a lane that may have
+            // fired (p ~ 1e-2 per draw) walks its candidates, one per set bit, and applies the exact per-item threshold.
+            bool any = false;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const int rr = r + (w >> 2);
-                const int item = ((w & 3) * R + rr) * 32 + lane;      // = word*B + block
-                const u32 thr = (item < nq_items) ? p.T : p.Tm;
-                if (rr < R && uu[w] < thr) {
-                    record_event<D>(acc, item, uu[w], nq_items, n_items, p.T1, p.T2, dp);
-                    evq |= item < nq_items;
-                }
+            for (int w = 0; w < 8; ++w) any |= uu[w] < p.Tmx;
+            if (any) {
+                u32 hits = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) hits |= (uu[w] < p.Tmx ? 1u : 0u) << w;
+                do {
+                    const int w = __ffs((int)hits) - 1;
+                    hits &= hits - 1;
+                    const u32 lo4 = (w & 2) ? ((w & 1) ? uu[3] : uu[2]) : ((w & 1) ? uu[1] : uu[0]);
+                    const u32 hi4 = (w & 2) ? ((w & 1) ? uu[7] : uu[6]) : ((w & 1) ? uu[5] : uu[4]);
+                    const u32 uv = (w & 4) ? hi4 : lo4;
+                    const int item = ((w & 3) * R + r + (w >> 2)) * 32 + lane;      // = word*B + block
+                    const u32 thr = (item < nq_items) ? p.T : p.Tm;
+                    if (uv < thr) {
+                        record_event<D>(acc, item, uv, nq_items, n_items, p.T1, p.T2, dp);
+                        evq |= item < nq_items;
+                    }
+                } while (hits);
             }
         }
         const bool anyq = __any_sync(FULL, evq);
@@ -171,10 +190,14 @@ struct Rollout {            // multi-step launch: see env_step_kernel
 
 struct Smem {
     u64 bm[kEpc][kMaxLayers * 4];     // [lattice][layer*PW + word]: rendered bitmap of every observation layer (mirror of the state rows)
+    u32 stream[kStreamWords];         // the tile's observation bit stream: lattice-major concatenation of the layer bitmaps, P bits each,
+                                      // no padding = byte i of the tile's observations is bit i; kept in step with bm, so phase D is a
+                                      // straight expansion of consecutive words
     u64 lut8[256];                    // byte -> its 8 bits as 8 bytes of 0/1 (phase D)
     u64 fx[kEpc], fz[kEpc], fmeta[kEpc];   // phase A -> B hand-off: frame planes, counters
     u64 sum[kEpc], acted[kEpc];       // OR of the volume's slices; OR of the action boards
     u32 acc[kWarps][3 * kMaxVd * 2];  // per-warp flip accumulators of generate_volume
+    u32 pick_u[2][kPickGroup][kEpc];  // built-in policy: word 0 of the (lattice, step) policy block, drawn a group of steps ahead, double-buffered
     int32_t life_out[kEpc];
     int actbit[kEpc];                 // light step: (action layer << 16) | cell bit to set, else -1
     uint8_t task[kEpc], task_flags[kEpc];
@@ -198,6 +221,15 @@ __device__ __forceinline__ u32 gather32(const Smem& sm, int lat, int layer, int 
         if (lat2 < kEpc) v |= reinterpret_cast<const u32*>(&sm.bm[lat2][l2 * PW])[0] << n1;
     }
     return v;
+}
+
+// word `wi` of the tile's observation bit stream, gathered from the layer bitmaps
+template <int D>
+__device__ __forceinline__ u32 stream_word(const Smem& sm, const EnvParams& p, int wi, int C) {
+    const int g = wi * 32;
+    const int lat = (int)__umulhi((u32)g, p.ob_magic), r = g - lat * p.obs_bits;
+    const int layer = r / Lat<D>::P, o = r - layer * Lat<D>::P;
+    return lat < kEpc ? gather32<D>(sm, lat, layer, o, C) : 0u;
 }
 
 __device__ __forceinline__ uint4 expand16(const Smem& sm, u32 h) {     // low 16 bits -> 16 bytes of 0/1 (two table lookups)
@@ -235,37 +267,43 @@ __device__ __forceinline__ void legal_words(const EnvParams& p, u64 summed, u64 
     for (int i = 0; i < 3; ++i) if (i == (ib >> 6)) mw[i] |= 1ull << (ib & 63);
 }
 
-// Phase D: the tile's observation bytes.  Thread per 32 bits of the tile's observation bit stream: gathered from the layer
-// bitmaps, expanded to 32 bytes of 0/1, two 128-bit stores (the tile's 16*C*H*H bytes start 16-byte aligned whenever the
-// caller's buffer is).  Executed by threads [first, first + nthr) of the CTA.
-template <int D>
-__device__ __forceinline__ void write_observations(const Smem& sm, const EnvParams& p, uint8_t* obs, int env0, int nvalid, int C,
-                                                   int t, int nthr) {
-    typedef Lat<D> L;
-    const int vbytes = nvalid * p.obs_bits, OB = p.obs_bits;
-    uint8_t* out = obs + (size_t)env0 * p.obs_bits;
-    const int align = (int)(reinterpret_cast<uintptr_t>(out) & 15);               // 0: 128-bit stores, 8: 64-bit stores, else bytes
-    const int step = nthr * 32, dlat = step / OB, dr = step - dlat * OB;          // warp-uniform
-    int g = t * 32;
-    int lat = (int)__umulhi((u32)g, p.ob_magic), r = g - lat * OB;
-    for (; g < vbytes; g += step) {
-        const int layer = r / L::P, o = r - layer * L::P;
-        const u32 word = gather32<D>(sm, lat, layer, o, C);
-        if (align == 0 && g + 32 <= vbytes) {
-            *reinterpret_cast<uint4*>(out + g) = expand16(sm, word);
-            *reinterpret_cast<uint4*>(out + g + 16) = expand16(sm, word >> 16);
-        } else if (align == 8 && g + 32 <= vbytes) {
+// Phase D: the tile's observation bytes.  Thread per 32-bit word of the tile's observation bit stream: expanded to 32 bytes of
+// 0/1, two 128-bit stores (the tile's 16*C*H*H bytes start 16-byte aligned whenever the caller's buffer is).  Executed by
+// threads [first, first + nthr) of the CTA.
+__device__ __noinline__ void write_observations_unaligned(const Smem& sm, uint8_t* out, int full, int align, int t, int nthr) {
+    for (int g = t * 32; g < full; g += nthr * 32) {        // rare: 64-bit stores at 8-byte alignment, else bytes
+        const u32 word = sm.stream[g >> 5];
+        if (align == 8) {
             const uint4 a = expand16(sm, word), b = expand16(sm, word >> 16);
             *reinterpret_cast<uint2*>(out + g) = make_uint2(a.x, a.y);
             *reinterpret_cast<uint2*>(out + g + 8) = make_uint2(a.z, a.w);
             *reinterpret_cast<uint2*>(out + g + 16) = make_uint2(b.x, b.y);
             *reinterpret_cast<uint2*>(out + g + 24) = make_uint2(b.z, b.w);
         } else {
-            const int nb = min(32, vbytes - g);
-            for (int b = 0; b < nb; ++b) out[g + b] = (uint8_t)((word >> b) & 1u);
+#pragma unroll 4
+            for (int b = 0; b < 32; ++b) out[g + b] = (uint8_t)((word >> b) & 1u);
         }
-        lat += dlat; r += dr;
-        if (r >= OB) { r -= OB; ++lat; }
+    }
+}
+__device__ __forceinline__ void write_observations(const Smem& sm, const EnvParams& p, uint8_t* obs, int env0, int nvalid,
+                                                   int t, int nthr) {
+    const int vbytes = nvalid * p.obs_bits;
+    uint8_t* out = obs + (size_t)env0 * p.obs_bits;
+    const int align = (int)(reinterpret_cast<uintptr_t>(out) & 15);
+    const int full = vbytes & ~31;                                                // whole 32-byte groups
+    if (align == 0) {
+#pragma unroll 2
+        for (int g = t * 32; g < full; g += nthr * 32) {
+            const u32 word = sm.stream[g >> 5];
+            *reinterpret_cast<uint4*>(out + g) = expand16(sm, word);
+            *reinterpret_cast<uint4*>(out + g + 16) = expand16(sm, word >> 16);
+        }
+    } else {
+        write_observations_unaligned(sm, out, full, align, t, nthr);
+    }
+    if (t == 0 && full < vbytes) {                                                 // the tile's last, partial group
+        const u32 word = sm.stream[full >> 5];
+        for (int b = 0; b < vbytes - full; ++b) out[full + b] = (uint8_t)((word >> b) & 1u);
     }
 }
 
@@ -288,7 +326,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int env0 = blockIdx.x * kEpc;
     const int C = p.vd + p.layers;
-    const int nvalid = min(kEpc, p.n - env0);
+    const int nvalid = max(0, min(kEpc, p.n - env0));      // a tile past the last lattice (n padded to 32) has none
     const size_t np = (size_t)p.npad;
     // built-in policy: every CTA reads the step index before its first barrier; the last CTA to finish advances it
     const u32 step0 = policy_ctr ? *reinterpret_cast<volatile u32*>(policy_ctr) : 0u;
@@ -309,8 +347,18 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         }
     }
     if (tid < kEpc) sm.sum[tid] = p.state[ROW_SUM * np + env0 + tid];
+    // built-in policy: the random word of a pick depends only on (lattice, step index), so it never has to sit on the
+    // step's dependent chain: the words of the first kPickGroup steps are drawn here, those of every later group by warps 1..
+    // one group ahead (below), into the buffer warp 0 is not reading
+    if (!RESET && policy_ctr && tid < kPickGroup * kEpc) {
+        const int ahead = tid / kEpc, lat = tid - ahead * kEpc;
+        if (ahead < ro.nsteps)
+            sm.pick_u[0][ahead][lat] = philox4x32_10(p.env_id_base + (u32)(env0 + lat), step0 + (u32)ahead, 0u, 1u, p.k0, p.k1).x;
+    }
     for (int i = tid; i < 256; i += kThreads)
         sm.lut8[i] = (u64)((((u32)i & 0xFu) * 0x00204081u) & 0x01010101u) | ((u64)((((u32)i >> 4) * 0x00204081u) & 0x01010101u) << 32);
+    __syncthreads();
+    for (int wi = tid; wi < (kEpc * p.obs_bits + 31) >> 5; wi += kThreads) sm.stream[wi] = stream_word<D>(sm, p, wi, C);
     __syncthreads();
 
     // A rollout (dq_env_rollout_random) runs ro.nsteps steps of this tile's lattices in one launch: lattices are independent,
@@ -320,6 +368,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     size_t oo = 0;
     u64 mw[3] = {0, 0, 0};              // warp 0, lane = lattice: legal-move mask after the latest step (phase C -> next phase A)
     uint8_t* obs_prev = nullptr;        // the previous step's observation slot: written while warp 0 runs this step's phase A
+    int gphase = 0, gbuf = 0;           // rs % kPickGroup, (rs / kPickGroup) & 1
     for (int rs = 0; rs < ro.nsteps; ++rs, oo += ro.out_stride, ring_slot = (ring_slot + 1 == ro.slots) ? 0 : ring_slot + 1) {
     uint8_t* const obs = obs0 ? obs0 + (size_t)ring_slot * ro.slot_bytes : nullptr;
     float* const reward = reward0 ? reward0 + oo : nullptr;
@@ -331,7 +380,13 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     // ---- phase A: warp 0, lane = lattice.  Warps 1.. meanwhile write the PREVIOUS step's observations (phase D): phase A does
     //      not touch the bitmaps -- the cell a light step adds is applied after the barrier.
     if (warp != 0) {
-        if (obs_prev) write_observations<D>(sm, p, obs_prev, env0, nvalid, C, tid - 32, kThreads - 32);
+        if (!RESET && policy_ctr && gphase == 0 && rs + kPickGroup < ro.nsteps && tid - 32 < kPickGroup * kEpc) {
+            // policy words of the NEXT group of steps -> the other buffer (last read two barriers ago, next read after this step's barriers)
+            const int ahead = (tid - 32) / kEpc, lat = (tid - 32) - ahead * kEpc, s = rs + kPickGroup + ahead;
+            if (s < ro.nsteps)
+                sm.pick_u[gbuf ^ 1][ahead][lat] = philox4x32_10(p.env_id_base + (u32)(env0 + lat), step0 + (u32)s, 0u, 1u, p.k0, p.k1).x;
+        }
+        if (obs_prev) write_observations(sm, p, obs_prev, env0, nvalid, tid - 32, kThreads - 32);
     } else {
         const int e = env0 + lane;
         const bool mine = lane < kEpc, live = lane < nvalid;
@@ -349,19 +404,16 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                 if (policy_ctr && live) {
                     // built-in random-legal policy (dq_env_step_random): the pick dq_policy_random_legal would make
                     // on this lattice's current legal set, with the step index read from device memory
-                    const u32 step = step0 + (u32)rs;
                     if (rs == 0) legal_words<D>(p, sm.sum[lane], act[0] | act[1] | act[2], mw);   // later steps: phase C of the previous step left it
                     const int ib = p.A - 1;
                     const int cnt = popc64(mw[0]) + popc64(mw[1]) + popc64(mw[2]);
-                    const Philox4 u = philox4x32_10(p.env_id_base + (u32)e, step, 0u, 1u, p.k0, p.k1);
-                    int pick = (int)mulhi32(u.x, (u32)cnt);
-                    a = ib;
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const int c = popc64(mw[i]);
-                        if (pick >= 0 && pick < c) { a = i * 64 + select64(mw[i], pick); pick = -1; }
-                        else if (pick >= 0) pick -= c;
-                    }
+                    int pick = (int)mulhi32(sm.pick_u[gbuf][gphase][lane], (u32)cnt);              // < cnt (cnt >= 1: the identity is always legal)
+                    const int c0 = popc64(mw[0]), c1 = popc64(mw[1]);
+                    u64 word = mw[0];
+                    int wbase = 0;
+                    if (pick >= c0 + c1) { pick -= c0 + c1; word = mw[2]; wbase = 128; }
+                    else if (pick >= c0) { pick -= c0; word = mw[1]; wbase = 64; }
+                    a = cnt > 0 ? wbase + select64(word, pick) : ib;
                     if (actions_out) actions_out[e] = a;
                 }
                 if (a < 0 || a >= p.A) a = p.A - 1;
@@ -424,6 +476,8 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             const u64 wv = sm.bm[tid][row] | (1ull << (pos & 63));
             sm.bm[tid][row] = wv;
             p.state[(ROW_BM + row) * np + env0 + tid] = wv;
+            const int sb = tid * p.obs_bits + (p.vd + (ab >> 16)) * L::P + pos;
+            atomicOr(&sm.stream[sb >> 5], 1u << (sb & 31));
         }
     }
     // ---- phase B: warp per flagged lattice: fresh volume(s), then re-render its layer bitmaps
@@ -477,6 +531,18 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         }
         __syncwarp();
         for (int i = lane; i < C * PW; i += 32) p.state[(ROW_BM + i) * np + e] = sm.bm[slot][i];
+        // this lattice's span of the tile's bit stream; its first and last word are shared with the neighbouring lattices, which
+        // other warps may be re-rendering right now: only this lattice's bits of those are replaced, atomically
+        {
+            const int b0 = slot * p.obs_bits, b1 = b0 + p.obs_bits;
+            for (int wi = (b0 >> 5) + lane; wi <= ((b1 - 1) >> 5); wi += 32) {
+                const int lo = max(b0 - wi * 32, 0), hi = min(b1 - wi * 32, 32);          // bits [lo, hi) of the word are this lattice's
+                const u32 mask = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                const u32 v = stream_word<D>(sm, p, wi, C);
+                if (mask == 0xffffffffu) sm.stream[wi] = v;
+                else { atomicAnd(&sm.stream[wi], ~mask); atomicOr(&sm.stream[wi], v & mask); }
+            }
+        }
     }
     __syncthreads();
 
@@ -494,8 +560,9 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         }
     }
     obs_prev = obs;
+    if (++gphase == kPickGroup) { gphase = 0; gbuf ^= 1; }
     }   // rollout step
-    if (obs_prev) write_observations<D>(sm, p, obs_prev, env0, nvalid, C, tid, kThreads);     // the last step's observations
+    if (obs_prev) write_observations(sm, p, obs_prev, env0, nvalid, tid, kThreads);           // the last step's observations
     if (policy_ctr && tid == 0 && atomicAdd(policy_ctr + 1, 1u) == gridDim.x - 1) { policy_ctr[1] = 0; atomicAdd(policy_ctr, (u32)ro.nsteps); }
 }
 
@@ -580,6 +647,7 @@ static u32 threshold_u32(double p) {
 static void set_thresholds(EnvParams& p, double p_phys, double p_meas) {
     p.T = threshold_u32(p_phys); p.Tm = threshold_u32(p_meas);
     p.T1 = p.T / 3; p.T2 = (u32)((2ull * p.T) / 3);
+    p.Tmx = p.T > p.Tm ? p.T : p.Tm;
 }
 
 extern "C" const char* dq_last_error(void) { return dq::g_err_q.c_str(); }

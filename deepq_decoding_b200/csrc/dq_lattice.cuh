@@ -256,14 +256,26 @@ DQ_HD u64 extract_bits(const u32* s, int off, int n) {
     return n >= 64 ? v : (v & ((1ull << n) - 1));
 }
 
-// position of the k-th (0-based) set bit
-DQ_HD int select64(u64 x, int k) {
-    for (int i = 0; i < k; ++i) x &= x - 1;
+// position of the k-th (0-based) set bit, k < popcount(x): binary search over popcounts, branch-free (clearing the
+// lowest set bit k times made a warp's dependent chain as long as its largest k)
+DQ_HD int popc32(u32 x) {
 #if defined(__CUDA_ARCH__)
-    return __ffsll((long long)x) - 1;
+    return __popc(x);
 #else
-    return __builtin_ctzll(x);
+    return __builtin_popcount(x);
 #endif
+}
+DQ_HD int select64(u64 x, int k) {
+    u32 w = (u32)x;
+    int base = 0;
+    const int c0 = popc32(w);
+    if (k >= c0) { k -= c0; w = (u32)(x >> 32); base = 32; }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const int c = popc32(w & ((1u << s) - 1u));
+        if (k >= c) { k -= c; w >>= s; base += s; }
+    }
+    return base;
 }
 
 }  // namespace dq

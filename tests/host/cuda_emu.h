@@ -123,6 +123,9 @@ inline void block_barrier() {
     }
 }
 
+inline int sched_mode() { static int m = -1; if (m < 0) { const char* e = getenv("DQ_EMU_SCHED"); m = e ? atoi(e) : 0; } return m; }
+inline unsigned sched_rand() { static unsigned s = 0; if (!s) s = 2654435761u * (unsigned)(sched_mode() + 1); s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; }
+
 inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {
     static Cta* c = nullptr;
     if (!c) {
@@ -152,13 +155,21 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
             makecontext(&f.ctx, (void (*)())entry, 0);
         }
         int idle_passes = 0;
+        const int nwarps = (nthreads + 31) / 32;
         while (c->ndone < nthreads) {
             const long before = c->progress;
-            for (int i = 0; i < nthreads; ++i) {
-                if (c->th[i].done) continue;
-                c->cur = i;
-                swapcontext(&c->sched, &c->th[i].ctx);
-            }
+            // warps of a CTA run in no particular order on the GPU: DQ_EMU_SCHED = 0 ascending (default), 1 descending,
+            // >= 2 a fresh pseudo-random warp order every pass (the value seeds it)
+            int order[kMaxThreads / 32];
+            for (int w = 0; w < nwarps; ++w) order[w] = sched_mode() == 1 ? nwarps - 1 - w : w;
+            if (sched_mode() >= 2)
+                for (int w = nwarps - 1; w > 0; --w) { const int j = (int)(sched_rand() % (unsigned)(w + 1)); const int t = order[w]; order[w] = order[j]; order[j] = t; }
+            for (int wi = 0; wi < nwarps; ++wi)
+                for (int i = order[wi] * 32; i < nthreads && i < order[wi] * 32 + 32; ++i) {
+                    if (c->th[i].done) continue;
+                    c->cur = i;
+                    swapcontext(&c->sched, &c->th[i].ctx);
+                }
             idle_passes = (c->progress == before) ? idle_passes + 1 : 0;
             if (idle_passes > 2) {
                 fprintf(stderr, "dq_emu: deadlock in block (%u,%u,%u): %d of %d threads finished, the rest wait at a barrier or warp "

@@ -159,3 +159,21 @@ def test_emulator_reports_deadlock_free_run_of_every_geometry():
             obs, legal = env.reset()
             oobs, olegal = o.reset()
             assert np.array_equal(obs, oobs) and np.array_equal(legal, olegal)
+
+
+@pytest.mark.parametrize("p_phys,p_meas", [(0.01, 0.08), (0.08, 0.01), (0.0, 0.05), (0.05, 0.0)])
+def test_emulated_distinct_measurement_rate(p_phys, p_meas):
+    """p_meas != p_phys: data-qubit and measurement draws use different thresholds (the screen uses the larger one)."""
+    d, model, n = 5, "DP", 40
+    env, o = make_pair(d, model, False, 4, 0.03, n, seed=11)
+    env.set_noise(p_phys, p_meas); o.set_noise(p_phys, p_meas)
+    obs, legal = env.reset()
+    oobs, olegal = o.reset()
+    assert np.array_equal(obs, oobs) and np.array_equal(legal, olegal)
+    for t in range(25):
+        acts = o.random_legal_actions(olegal, t)
+        got = env.step(acts)
+        want = o.step(acts, auto_reset=True)
+        for k, (g, w) in enumerate(zip(got, want)):
+            assert np.array_equal(g, w), "output %d at t=%d" % (k, t)
+        olegal = want[4]
