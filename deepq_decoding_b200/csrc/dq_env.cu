@@ -238,15 +238,6 @@ __device__ __forceinline__ uint4 expand16(const Smem& sm, u32 h) {     // low 16
     return make_uint4(a.x, a.y, b.x, b.y);
 }
 
-template <int D> __device__ __forceinline__ u64 marker_word_rt(int i) {
-    switch (i) {
-        case 0: return Lat<D>::marker_word(0);
-        case 1: return Lat<D>::marker_word(1);
-        case 2: return Lat<D>::marker_word(2);
-        default: return Lat<D>::marker_word(3);
-    }
-}
-
 // Legal-move mask words of one lattice (Environments.py:238-271 in closed form): qubits touching the summed faulty syndrome
 // or next to an already acted-on qubit, in every action layer, plus the identity.
 template <int D>
@@ -490,11 +481,15 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         u32 life = (u32)bm0, attempts = (u32)(bm0 >> 32) & 0x7FFFFFFFu, dn = (u32)(bm0 >> 63);
         u64 f = 0;
         int32_t lo = (int32_t)life;
-        for (int pass = 0; pass < 2; ++pass) {          // pass 0: heavy step, pass 1: restart of a finished lattice
-            if (!(fl & (1 << pass))) continue;
-            if (pass == 1) { bx = 0; bz = 0; life = 0; dn = 0; }
+        // bit 0 of fl: heavy step (volume on the current frame), bit 1: restart of a finished lattice (volume on a clean frame), in
+        // that order; one copy of the generator serves both
+#pragma unroll 1
+        for (int todo = fl; todo; ) {
+            const bool restart = !(todo & 1);
+            if (restart) { bx = 0; bz = 0; life = 0; dn = 0; }
             f = generate_volume<D>(p, sm.acc[warp], lane, env_id, bx, bz, life, attempts);
-            if (pass == 0) lo = (int32_t)life;
+            if (!restart) lo = (int32_t)life;
+            todo = restart ? 0 : (todo & 2);
         }
         u64 summed = f;                                 // lanes >= vd hold 0
         summed |= __shfl_xor_sync(FULL, summed, 1);
@@ -509,28 +504,18 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             if (!RESET) sm.life_out[slot] = lo;
         }
         if (lane < p.layers) p.state[(ROW_ACT + lane) * np + e] = 0;
-        // render: markers first, then lane per (slice, plaquette row) ORs its spread row in
-        for (int i = lane; i < C * PW; i += 32) sm.bm[slot][i] = (i < p.vd * PW) ? marker_word_rt<D>(i % PW) : 0ull;
-        __syncwarp();
-        for (int base = 0; base < p.vd * G; base += 32) {
-            const int idx = base + lane;
-            const int j = min(idx / G, p.vd - 1), a = idx - (idx / G) * G;
-            const u64 fj = __shfl_sync(FULL, f, j);
-            if (idx < p.vd * G) {
-                const u32 v = spread2_8((u32)(fj >> (a * G)) & ((1u << G) - 1));
-                const int off = 2 * a * H, k = off >> 5, sh = off & 31;          // 32-bit word k of the layer bitmap
-                if (v) {
-                    u32* w0 = reinterpret_cast<u32*>(&sm.bm[slot][j * PW]) + k;
-                    atomicOr(w0, v << sh);
-                    if (sh > 17 && (v >> (32 - sh))) {
-                        u32* w1 = reinterpret_cast<u32*>(&sm.bm[slot][j * PW]) + k + 1;
-                        atomicOr(w1, v >> (32 - sh));
-                    }
-                }
+        // render: lane j < vd holds slice j and builds that layer's bitmap in registers; lanes vd..C-1 clear the action layers
+        if (lane < C) {
+            u64 w[PW];
+            syndrome_layer_bitmap<D>(f, w);
+#pragma unroll
+            for (int i = 0; i < PW; ++i) {
+                const u64 v = lane < p.vd ? w[i] : 0ull;
+                sm.bm[slot][lane * PW + i] = v;
+                p.state[(ROW_BM + lane * PW + i) * np + e] = v;
             }
         }
         __syncwarp();
-        for (int i = lane; i < C * PW; i += 32) p.state[(ROW_BM + i) * np + e] = sm.bm[slot][i];
         // this lattice's span of the tile's bit stream; its first and last word are shared with the neighbouring lattices, which
         // other warps may be re-rendering right now: only this lattice's bits of those are replaced, atomically
         {
