@@ -70,6 +70,7 @@ struct EnvParams {
     u32 ob_magic;                               // ceil(2^32 / obs_bits): g / obs_bits == umulhi(g, ob_magic) for g < 2^16
     u32 T, T1, T2, Tm;                          // thresholds (RNG contract)
     u32 Tmx;                                    // max(T, Tm): the one-compare screen of generate_volume
+    u64 idw[3];                                 // legal-mask words with only the identity action (A-1) set
     u32 k0, k1;                                 // Philox key
     u32 env_id_base;
     int ref_mode;
@@ -244,7 +245,7 @@ template <int D>
 __device__ __forceinline__ void legal_words(const EnvParams& p, u64 summed, u64 acted, u64 (&mw)[3]) {
     typedef Lat<D> L;
     const u64 lq = qubits_grid_to_compact<D>(qubits_adjacent_to<D>(summed) | qubits_neighbours_of<D>(acted));
-    mw[0] = mw[1] = mw[2] = 0;
+    mw[0] = p.idw[0]; mw[1] = p.idw[1]; mw[2] = p.idw[2];      // the identity (a run-time index here would push mw into local memory)
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
         if (l < p.layers) {
@@ -253,9 +254,6 @@ __device__ __forceinline__ void legal_words(const EnvParams& p, u64 summed, u64 
             if (s && i + 1 < 3) mw[i + 1] |= lq >> (64 - s);
         }
     }
-    const int ib = p.A - 1;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) if (i == (ib >> 6)) mw[i] |= 1ull << (ib & 63);
 }
 
 // Phase D: the tile's observation bytes.  Thread per 32-bit word of the tile's observation bit stream: expanded to 32 bytes of
@@ -661,6 +659,7 @@ extern "C" int dq_env_create(dq_env** out, int d, int error_model, int use_Y, in
     p.layers = error_model == DQ_MODEL_X ? 1 : (use_Y ? 3 : 2);
     p.A = p.layers * d * d + 1;
     p.W = (p.A + 63) / 64;
+    p.idw[(p.A - 1) >> 6] = 1ull << ((p.A - 1) & 63);
     p.n = (int)n_envs; p.npad = (int)((n_envs + 31) / 32 * 32);
     const int items = volume_depth * (2 * d * d - 1);
     p.rounds = (items + 127) / 128;
