@@ -47,6 +47,15 @@ namespace dq {
 constexpr int kEpc = DQ_EPC;                       // lattices per CTA: 16*L observation bytes are a multiple of 16 for every L
 constexpr int kThreads = DQ_THREADS;
 constexpr int kWarps = kThreads / 32;
+#ifndef DQ_PREFETCH
+#define DQ_PREFETCH 0            // rollouts: warps 1.. draw the flip masks of every lattice's next volume attempt ahead of time
+#endif
+#ifndef DQ_REFILL
+#define DQ_REFILL 2              // ... at most this many lattices per warp and step
+#endif
+constexpr bool kPrefetch = DQ_PREFETCH != 0;
+constexpr int kRefill = DQ_REFILL;
+constexpr u32 kNoAttempt = 0xffffffffu;              // attempt indices have 31 bits
 constexpr int kPickGroup = (kThreads - 32) / kEpc;   // rollout steps whose policy words warps 1.. draw in one go (thread = (step, lattice))
 static_assert(kPickGroup >= 1, "warps 1.. must cover at least one step of the tile");
 constexpr int kMaxVd = 8;
@@ -105,61 +114,76 @@ __device__ __noinline__ void record_event(u32* acc, int item, u32 uv, int nq_ite
     }
 }
 
-// One volume (Environments.py:158-176 / :216-235) for one lattice, executed by a full warp.
-// A volume attempt = R rounds of one Philox4x32-10 block per lane (draw i = word i/B of block i%B),
-// issued two rounds at a time so two Philox chains overlap.  Every lane thresholds its own draws;
-// the few that fire are XOR-ed into shared-memory accumulators (record_event).  Lane j < vd then owns
-// slice j: a warp prefix-XOR gives the frame after every slice, one shifted-XOR syndrome per lane the
-// faulty slices.  Updates xb, zb (frame), life, attempts (all warp-uniform); returns this lane's slice.
+// The draws of ONE volume attempt of one lattice, executed by a full warp: R rounds of one Philox4x32-10 block per lane
+// (draw i = word i/B of block i%B), issued two rounds at a time so two Philox chains overlap.  Every lane thresholds its own
+// draws; the few that fire are XOR-ed into the accumulators acc[kind][slice] (record_event).  They depend on (lattice, attempt
+// index) only -- not on the lattice's state -- which is what lets warps 1.. draw them ahead of time (DQ_PREFETCH).
+// Returns (warp-uniform) whether a data-qubit draw fired.
 template <int D>
-__device__ __forceinline__ u64 generate_volume(const EnvParams& p, u32* acc, int lane, u32 env_id,
-                                               u64& xb, u64& zb, u32& life, u32& attempts) {
+__device__ __forceinline__ bool draw_flip_masks(const EnvParams& p, u32* acc, int lane, u32 env_id, u32 attempt) {
     typedef Lat<D> L;
     constexpr u32 FULL = 0xffffffffu;
     const int vd = p.vd, R = p.rounds, nq_items = vd * L::NQ, n_items = vd * (L::NQ + L::NS);
     const int dp = p.model == DQ_MODEL_DP;
+    if (lane < 3 * kMaxVd) { acc[2 * lane] = 0; acc[2 * lane + 1] = 0; }
+    __syncwarp();
+    bool evq = false;
+    for (int r = 0; r < R; r += 2) {
+        const Philox4 u0 = philox4x32_10(env_id, attempt, (u32)(r * 32 + lane), 0u, p.k0, p.k1);
+        Philox4 u1;
+        u1.x = u1.y = u1.z = u1.w = 0xffffffffu;                      // an odd R has no second round: words that can never fire
+        if (r + 1 < R) u1 = philox4x32_10(env_id, attempt, (u32)(r * 32 + 32 + lane), 0u, p.k0, p.k1);
+        const u32 uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+        // Screen the lane's eight draws against the larger threshold with one predicate chain; only a lane that may have
+        // fired (p ~ 1e-2 per draw) walks its candidates, one per set bit, and applies the exact per-item threshold.
+        bool any = false;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) any |= uu[w] < p.Tmx;
+        if (any) {
+            u32 hits = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) hits |= (uu[w] < p.Tmx ? 1u : 0u) << w;
+            do {
+                const int w = __ffs((int)hits) - 1;
+                hits &= hits - 1;
+                const u32 lo4 = (w & 2) ? ((w & 1) ? uu[3] : uu[2]) : ((w & 1) ? uu[1] : uu[0]);
+                const u32 hi4 = (w & 2) ? ((w & 1) ? uu[7] : uu[6]) : ((w & 1) ? uu[5] : uu[4]);
+                const u32 uv = (w & 4) ? hi4 : lo4;
+                const int item = ((w & 3) * R + r + (w >> 2)) * 32 + lane;      // = word*B + block
+                const u32 thr = (item < nq_items) ? p.T : p.Tm;
+                if (uv < thr) {
+                    record_event<D>(acc, item, uv, nq_items, n_items, p.T1, p.T2, dp);
+                    evq |= item < nq_items;
+                }
+            } while (hits);
+        }
+    }
+    const bool anyq = __any_sync(FULL, evq);
+    __syncwarp();
+    return anyq;
+}
+
+// One volume (Environments.py:158-176 / :216-235) for one lattice, executed by a full warp: attempts until one is
+// non-trivial.  An attempt's flip masks come from `pre` when they were drawn ahead for exactly this attempt index (pre_att),
+// else they are drawn now into `acc`.  Lane j < vd then owns slice j: a warp prefix-XOR gives the frame after every slice, one
+// shifted-XOR syndrome per lane the faulty slices.  Updates xb, zb (frame), life, attempts (all warp-uniform); returns this
+// lane's slice.
+template <int D>
+__device__ __forceinline__ u64 generate_volume(const EnvParams& p, u32* acc, const u32* pre, u32 pre_att, bool pre_anyq,
+                                               int lane, u32 env_id, u64& xb, u64& zb, u32& life, u32& attempts) {
+    constexpr u32 FULL = 0xffffffffu;
+    const int vd = p.vd;
     bool nontrivial;
     u64 f = 0;
     int guard = 0;
     do {
-        if (lane < 3 * kMaxVd) { acc[2 * lane] = 0; acc[2 * lane + 1] = 0; }
-        __syncwarp();
-        bool evq = false;
-        for (int r = 0; r < R; r += 2) {
-            const Philox4 u0 = philox4x32_10(env_id, attempts, (u32)(r * 32 + lane), 0u, p.k0, p.k1);
-            Philox4 u1;
-            u1.x = u1.y = u1.z = u1.w = 0xffffffffu;                      // an odd R has no second round: words that can never fire
-            if (r + 1 < R) u1 = philox4x32_10(env_id, attempts, (u32)(r * 32 + 32 + lane), 0u, p.k0, p.k1);
-            const u32 uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-            // Screen the lane's eight draws against the larger threshold with one predicate chain; only a lane that may have
-            // fired (p ~ 1e-2 per draw) walks its candidates, one per set bit, and applies the exact per-item threshold.
-            bool any = false;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) any |= uu[w] < p.Tmx;
-            if (any) {
-                u32 hits = 0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) hits |= (uu[w] < p.Tmx ? 1u : 0u) << w;
-                do {
-                    const int w = __ffs((int)hits) - 1;
-                    hits &= hits - 1;
-                    const u32 lo4 = (w & 2) ? ((w & 1) ? uu[3] : uu[2]) : ((w & 1) ? uu[1] : uu[0]);
-                    const u32 hi4 = (w & 2) ? ((w & 1) ? uu[7] : uu[6]) : ((w & 1) ? uu[5] : uu[4]);
-                    const u32 uv = (w & 4) ? hi4 : lo4;
-                    const int item = ((w & 3) * R + r + (w >> 2)) * 32 + lane;      // = word*B + block
-                    const u32 thr = (item < nq_items) ? p.T : p.Tm;
-                    if (uv < thr) {
-                        record_event<D>(acc, item, uv, nq_items, n_items, p.T1, p.T2, dp);
-                        evq |= item < nq_items;
-                    }
-                } while (hits);
-            }
-        }
-        const bool anyq = __any_sync(FULL, evq);
-        __syncwarp();
+        const u32* masks = acc;
+        bool anyq;
+        if (pre_att == attempts) { masks = pre; anyq = pre_anyq; }
+        else anyq = draw_flip_masks<D>(p, acc, lane, env_id, attempts);
         u64 ex = 0, ez = 0, m = 0;
         if (lane < vd) {
-            const u64* a64 = reinterpret_cast<const u64*>(acc);
+            const u64* a64 = reinterpret_cast<const u64*>(masks);
             ex = a64[0 * kMaxVd + lane]; ez = a64[1 * kMaxVd + lane]; m = a64[2 * kMaxVd + lane];
         }
         __syncwarp();
@@ -198,6 +222,9 @@ struct Smem {
     u64 fx[kEpc], fz[kEpc], fmeta[kEpc];   // phase A -> B hand-off: frame planes, counters
     u64 sum[kEpc], acted[kEpc];       // OR of the volume's slices; OR of the action boards
     u32 acc[kWarps][3 * kMaxVd * 2];  // per-warp flip accumulators of generate_volume
+    u32 pre[kPrefetch ? kEpc : 1][3 * kMaxVd * 2];   // DQ_PREFETCH: flip masks of attempt pre_att[lattice] of each lattice, drawn ahead
+    u32 pre_att[kEpc], att[kEpc];     // ... the attempt index they belong to; the lattice's current attempt counter
+    uint8_t pre_anyq[kEpc];
     u32 pick_u[2][kPickGroup][kEpc];  // built-in policy: word 0 of the (lattice, step) policy block, drawn a group of steps ahead, double-buffered
     int32_t life_out[kEpc];
     int actbit[kEpc];                 // light step: (action layer << 16) | cell bit to set, else -1
@@ -304,7 +331,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                 const Rollout ro) {
     typedef Lat<D> L;
     constexpr u32 FULL = 0xffffffffu;
-    constexpr int PW = L::PW, G = L::G, H = L::H;
+    constexpr int PW = L::PW, H = L::H;
 #ifdef DQ_EMU
     unsigned char* const smem_raw = DQ_EMU_DYNAMIC_SMEM;
 #else
@@ -335,7 +362,11 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             if (i < C * PW * kEpc) sm.bm[i - row * kEpc][row] = w6[j];
         }
     }
-    if (tid < kEpc) sm.sum[tid] = p.state[ROW_SUM * np + env0 + tid];
+    if (tid < kEpc) {
+        sm.sum[tid] = p.state[ROW_SUM * np + env0 + tid];
+        sm.pre_att[tid] = kNoAttempt;
+        if (kPrefetch) sm.att[tid] = (u32)(p.state[ROW_META * np + env0 + tid] >> 32) & 0x7FFFFFFFu;
+    }
     // built-in policy: the random word of a pick depends only on (lattice, step index), so it never has to sit on the
     // step's dependent chain: the words of the first kPickGroup steps are drawn here, those of every later group by warps 1..
     // one group ahead (below), into the buffer warp 0 is not reading
@@ -376,6 +407,18 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                 sm.pick_u[gbuf ^ 1][ahead][lat] = philox4x32_10(p.env_id_base + (u32)(env0 + lat), step0 + (u32)s, 0u, 1u, p.k0, p.k1).x;
         }
         if (obs_prev) write_observations(sm, p, obs_prev, env0, nvalid, tid - 32, kThreads - 32);
+        if (kPrefetch && !RESET && ro.nsteps > 1) {
+            // draw ahead: lattices whose prepared masks are not those of their next attempt (consumed, or never drawn).  This
+            // window (warp 0 runs phase C and A) is separated from phase B, which reads them, by the block barriers.
+            int done = 0;
+            for (int lat = warp - 1; lat < nvalid && done < kRefill; lat += kWarps - 1) {
+                const u32 want = sm.att[lat];
+                if (sm.pre_att[lat] == want) continue;                     // warp-uniform
+                const bool anyq = draw_flip_masks<D>(p, sm.pre[lat], lane, p.env_id_base + (u32)(env0 + lat), want);
+                if (lane == 0) { sm.pre_att[lat] = want; sm.pre_anyq[lat] = anyq ? 1 : 0; }
+                ++done;
+            }
+        }
     } else {
         const int e = env0 + lane;
         const bool mine = lane < kEpc, live = lane < nvalid;
@@ -485,7 +528,8 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         for (int todo = fl; todo; ) {
             const bool restart = !(todo & 1);
             if (restart) { bx = 0; bz = 0; life = 0; dn = 0; }
-            f = generate_volume<D>(p, sm.acc[warp], lane, env_id, bx, bz, life, attempts);
+            f = generate_volume<D>(p, sm.acc[warp], sm.pre[kPrefetch ? slot : 0], sm.pre_att[slot], sm.pre_anyq[slot] != 0,
+                                   lane, env_id, bx, bz, life, attempts);
             if (!restart) lo = (int32_t)life;
             todo = restart ? 0 : (todo & 2);
         }
@@ -499,6 +543,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             p.state[ROW_META * np + e] = meta_pack(life, attempts, dn);
             p.state[ROW_SUM * np + e] = summed;
             sm.sum[slot] = summed; sm.acted[slot] = 0;
+            if (kPrefetch) sm.att[slot] = attempts;
             if (!RESET) sm.life_out[slot] = lo;
         }
         if (lane < p.layers) p.state[(ROW_ACT + lane) * np + e] = 0;

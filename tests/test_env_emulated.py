@@ -177,3 +177,42 @@ def test_emulated_distinct_measurement_rate(p_phys, p_meas):
         for k, (g, w) in enumerate(zip(got, want)):
             assert np.array_equal(g, w), "output %d at t=%d" % (k, t)
         olegal = want[4]
+
+
+VARIANTS = [("prefetch", ["-DDQ_PREFETCH=1"]),
+            ("prefetch_refill1", ["-DDQ_PREFETCH=1", "-DDQ_REFILL=1"]),
+            ("tile32x256", ["-DDQ_EPC=32", "-DDQ_THREADS=256"]),
+            ("tile8x64_prefetch", ["-DDQ_EPC=8", "-DDQ_THREADS=64", "-DDQ_PREFETCH=1"])]
+
+
+@pytest.mark.parametrize("name,flags", VARIANTS, ids=[v[0] for v in VARIANTS])
+def test_emulated_build_variants(name, flags):
+    """The tuning builds of tools/build_variants.sh (tile shape, flip masks drawn ahead by warps 1..) are the same function:
+    reset, a single-step launch, a long and a short rollout, then the packed state, all against the oracle."""
+    import os
+    path = E.build(flags, out=os.path.join(E.HERE, "host", "libdq_env_emu_%s.so" % name))
+    for d, model, n, p, ar in [(5, "DP", 50, 0.03, True), (3, "X", 37, 0.05, True), (7, "DP", 20, 0.02, True),
+                               (5, "X", 30, 0.03, False), (5, "DP", 16, 0.007, True)]:
+        mode, la, lb = random_luts(np.random.default_rng(d), d, model)
+        a = E.EmuVecEnv(d, model, False, d, p, p, n, 7, 3, lib_path=path)
+        o = O.OracleVecEnv(d, model, False, d, p, p, n, 7, 3)
+        a.set_referee(mode, la, lb); o.set_referee(mode, la, lb)
+        obs, _ = a.reset()
+        oobs, olegal = o.reset()
+        assert np.array_equal(obs, oobs)
+        a.policy_seek(0)
+        t = 0
+        for S in (1, 30, 7):
+            if S == 1:
+                ring, (rew, done, life, legal, acts) = None, [x[None] for x in a.step_random(ar)[1:]]
+            else:
+                ring, rew, done, life, legal, acts = a.rollout_random(S, 4, 0, ar)
+            for s in range(S):
+                oa = o.random_legal_actions(olegal, t)
+                oobs, orew, odone, olife, olegal = o.step(oa, auto_reset=ar)
+                t += 1
+                assert np.array_equal(acts[s], oa) and np.array_equal(rew[s], orew) and np.array_equal(done[s], odone)
+                assert np.array_equal(life[s], olife) and np.array_equal(legal[s], olegal)
+                if ring is not None and s >= S - 4:
+                    assert np.array_equal(ring[s % 4], oobs)
+        compare_state(a, o, range(min(n, 8)))
