@@ -319,12 +319,7 @@ __device__ __forceinline__ void write_observations(const Smem& sm, const EnvPara
     }
     if (t == 0 && full < vbytes) {                                                 // the tile's last, partial group
         const u32 word = sm.stream[full >> 5];
-        int b = 0;
-        if (align == 0 && vbytes - full >= 16) {                                   // a full tile ends on 16 bytes: one more 128-bit store
-            *reinterpret_cast<uint4*>(out + full) = expand16(sm, word);
-            b = 16;
-        }
-        for (; b < vbytes - full; ++b) out[full + b] = (uint8_t)((word >> b) & 1u);
+        for (int b = 0; b < vbytes - full; ++b) out[full + b] = (uint8_t)((word >> b) & 1u);
     }
 }
 
@@ -564,31 +559,16 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             }
         }
         __syncwarp();
-        // this lattice's span of the tile's bit stream.  Pass 1 clears it (its first and last word are shared with the neighbouring
-        // lattices, which other warps may be re-rendering right now: only this lattice's bits of those are cleared, atomically);
-        // pass 2: lane j < vd shifts its layer's P bits to the layer's offset in the stream and ORs the words in (a layer's first
-        // and last word are shared with the neighbouring layers, i.e. with other lanes: atomics again).
+        // this lattice's span of the tile's bit stream; its first and last word are shared with the neighbouring lattices, which
+        // other warps may be re-rendering right now: only this lattice's bits of those are replaced, atomically
         {
             const int b0 = slot * p.obs_bits, b1 = b0 + p.obs_bits;
             for (int wi = (b0 >> 5) + lane; wi <= ((b1 - 1) >> 5); wi += 32) {
                 const int lo = max(b0 - wi * 32, 0), hi = min(b1 - wi * 32, 32);          // bits [lo, hi) of the word are this lattice's
                 const u32 mask = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-                if (mask == 0xffffffffu) sm.stream[wi] = 0u;
-                else atomicAnd(&sm.stream[wi], ~mask);
-            }
-            __syncwarp();
-            if (lane < p.vd) {
-                constexpr int NW = (L::P + 62) / 32;                   // words a P-bit field can touch at any bit offset
-                const int off = b0 + lane * L::P, k0 = off >> 5, sh = off & 31;
-                const u32* v32 = reinterpret_cast<const u32*>(&sm.bm[slot][lane * PW]);     // this lane's layer, as written above
-                u32 prev = 0;
-#pragma unroll
-                for (int i = 0; i < NW; ++i) {
-                    const u32 cur = i < 2 * PW ? v32[i] : 0u;
-                    const u32 o = __funnelshift_l(prev, cur, sh);      // (cur << sh) | (prev >> (32 - sh)); sh = 0: cur
-                    if (o) atomicOr(&sm.stream[k0 + i], o);
-                    prev = cur;
-                }
+                const u32 v = stream_word<D>(sm, p, wi, C);
+                if (mask == 0xffffffffu) sm.stream[wi] = v;
+                else { atomicAnd(&sm.stream[wi], ~mask); atomicOr(&sm.stream[wi], v & mask); }
             }
         }
     }
