@@ -4,18 +4,22 @@
 // uint64 rows of a [row][lattice] matrix that stays L2-resident between steps:
 // Pauli-frame planes, action boards, counters, AND the already-rendered (2d+1)^2-cell bitmap of every
 // observation layer, so that a step only re-renders what changed.  A launch runs one step (dq_env_step*) or a
-// rollout of many (dq_env_rollout_random); the tile's layer bitmaps are mirrored in shared memory for the whole
-// launch.  Per step (3 block barriers):
+// rollout of many (dq_env_rollout_random).  For the whole launch the tile's layer bitmaps are mirrored in shared
+// memory, together with the tile's observation BIT STREAM in its final layout (lattice-major concatenation of the
+// layer bitmaps, no padding: byte i of the tile's observations is bit i of the stream).  Per step (2 block barriers):
 //   A  warp 0, lane = lattice: (built-in random-legal pick,) apply the action to the Pauli frame, true syndrome
-//      by shifted XORs, homology label, referee table lookup, reward / done, heavy (identity | repeat) flag; a
-//      light step sets its one new cell in the action-layer bitmap
+//      by shifted XORs, homology label, referee table lookup, reward / done, heavy (identity | repeat) flag.
+//      Meanwhile warps 1.. write the PREVIOUS step's observations (D) and, once per group of steps, draw the
+//      policy's random words of the next group (they depend on (lattice, step index) only)
+//   -- barrier; a light step sets its one new cell in the action-layer bitmap and in the stream
 //   B  warp per flagged lattice: draw a fresh syndrome volume (generate_volume) -- Philox4x32-10, one
-//      block per lane, fired draws folded into per-slice flip masks, warp prefix-XOR over slices --
-//      and re-render that lattice's layer bitmaps (lane per (slice, plaquette row))
-//   C  thread per lattice: lifetime and legal-move mask
-//   D  thread per 32 bits of the tile's observation bit stream (the concatenation of its layer bitmaps): gather
-//      them from the bitmaps, expand to 32 bytes of 0/1, two aligned 128-bit stores (the tile's 16 observations
-//      are one contiguous, 16-byte aligned span of HBM)
+//      block per lane, draws screened by one min-reduce, fired draws folded into per-slice flip masks, warp
+//      prefix-XOR over slices -- then the lane that owns a slice builds its layer bitmap in registers and the
+//      lattice's span of the stream is re-gathered
+//   -- barrier
+//   C  warp 0, lane = lattice: lifetime and legal-move mask (kept in registers for the next step's pick)
+//   D  thread per 32-bit word of the stream: expand to 32 bytes of 0/1 through a 256-entry table, two aligned
+//      128-bit stores (the tile's 16 observations are one contiguous, 16-byte aligned span of HBM)
 // Earlier variants (32-lattice tiles staged by TMA bulk copies; warp-autonomous 4/8-lattice groups) and
 // the ncu evidence that led here are summarised in profiles/README.md.
 //
