@@ -20,6 +20,9 @@ dq_env_step_random).
             launch of a pass queued behind a device-side delay so the events see back-to-back kernels
   e2e       the same steps through dq_env_step_host: actions come from pinned host memory, every output
             (observations, reward, done, lifetime, legal mask) is copied back to the host each step
+  e2e_packed
+            the e2e loop with dq_env_step_host_packed: observations cross PCIe as the bit-packed rows the Q-network
+            consumes (7.5x fewer bytes); reported beside e2e, which stays the byte-observation number
   cpu_baseline / --impl reference
             the CPU oracle (oracle/dq_oracle.c, a C restatement of the reference env; the Python
             reference itself cannot travel to the GPU box) on all host cores, same workload
@@ -403,6 +406,32 @@ def run_b200(args):
     h2d = n * 4
     d2h = n * (env.obs[0].numel() + 4 + 1 + 4 + 8 * env.mask_words)
 
+    # ---- the same loop with the observations returned PACKED (one bit per cell, the rows the Q-network consumes):
+    #      an extra line of evidence next to e2e, never a replacement for it; a failure here must not cost the bench line
+    e2e_packed = None
+    try:
+        pk = env._packed_host_buffer()
+
+        def host_step_packed(i):
+            _lib.check(L.dq_env_step_host_packed(h, C.c_void_p(host_actions[i].data_ptr()), hp(pk), hp(hb["reward"]),
+                                                 hp(hb["done"]), hp(hb["lifetime"]), hp(hb["legal"]), 1))
+        for i in range(3):
+            host_step_packed(i)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(3, ke + 3):
+            host_step_packed(i)
+        dtp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
+        e2e_packed = {"value": world * n * ke / float(dtp.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": int(pk.numel() * 8 + n * (4 + 1 + 4 + 8 * env.mask_words)), "steps": ke,
+                      "api": "dq_env_step_host_packed (observations as bit-packed rows uint64 [C*PW][stride]; "
+                             "envs.unpack_observations expands them on the host when a caller needs bytes)"}
+    except Exception as ex:      # noqa: BLE001 -- reported, not fatal
+        e2e_packed = {"error": "%s: %s" % (type(ex).__name__, ex)}
+
     # ---- DQN inner loop on the same lattices (extra evidence, not the headline metric):
     #   act:   Q(s) for every lattice from the packed rows in the env state -> eps-greedy pick -> env step (no byte boards)
     #   train: act + store in the replay ring + one double-DQN update (batch 4096) per iteration
@@ -508,6 +537,7 @@ def run_b200(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": ke, "api": "dq_env_step_host (pinned host actions in, all outputs to pinned host buffers)",
                         "policy": "uniform random action indices pre-generated on the host"},
+                "e2e_packed": e2e_packed,
                 "gpu_launches": timed_launches, "single_step_launches": single,
                 "roofline": roof, "roofline_scaling": scaling, "cpu_baseline": cb, "dqn": dqn, "logical_error_rate": ler}
         print(json.dumps(line), flush=True)

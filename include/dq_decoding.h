@@ -120,6 +120,13 @@ int dq_env_rollout_random(dq_env* env, int n_steps, uint8_t* obs_ring, int ring_
 int dq_env_reset_host(dq_env* env, uint8_t* h_obs, uint64_t* h_legal_mask);
 int dq_env_step_host(dq_env* env, const int32_t* h_actions, uint8_t* h_obs, float* h_reward,
                      uint8_t* h_done, int32_t* h_lifetime, uint64_t* h_legal_mask, int auto_reset);
+/* The same two calls returning the observations PACKED -- uint64 h_packed[C*PW][STATE_STRIDE], bit x*H+y of the PW-word
+ * bitmap of layer l of lattice i in h_packed[l*PW + word][i], i.e. the rows dq_env_packed_obs exposes and the Q-network
+ * consumes -- instead of one byte per cell: 7.5x fewer bytes over PCIe at d = 5.  (The reference returns board_state as an
+ * int64 array, EN/Environments.py:204; deepq_decoding_b200.envs.unpack_observations restores that form on the host.) */
+int dq_env_reset_host_packed(dq_env* env, uint64_t* h_packed, uint64_t* h_legal_mask);
+int dq_env_step_host_packed(dq_env* env, const int32_t* h_actions, uint64_t* h_packed, float* h_reward, uint8_t* h_done,
+                            int32_t* h_lifetime, uint64_t* h_legal_mask, int auto_reset);
 
 /* Packed per-lattice state, uint64 [STATE_WORDS][STATE_STRIDE] on the device (layout in
  * DESIGN.md section 2): what env.hidden_state / completed_actions / lifetime / done hold in the

@@ -56,6 +56,8 @@ def lib(path=None):
     L.dq_policy_seek.argtypes = [vp, C.c_uint32, vp]
     L.dq_env_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32]
     L.dq_env_reset_host.argtypes = [vp, vp, vp]
+    L.dq_env_reset_host_packed.argtypes = [vp, vp, vp]
+    L.dq_env_step_host_packed.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32]
     _LIB[path] = L
     return L
 
@@ -150,3 +152,16 @@ class EmuVecEnv:
         reward, done, life, legal, _ = self._outs()
         self._check(self.L.dq_env_step_host(self.h, _p(actions), _p(obs), _p(reward), _p(done), _p(life), _p(legal), int(auto_reset)))
         return obs, reward, done, life, legal
+
+    def step_host_packed(self, actions, auto_reset=True):
+        actions = np.ascontiguousarray(actions, dtype=np.int32)
+        packed = np.zeros((self.state_rows - ROW_BM, self.stride), np.uint64)
+        reward, done, life, legal, _ = self._outs()
+        self._check(self.L.dq_env_step_host_packed(self.h, _p(actions), _p(packed), _p(reward), _p(done), _p(life), _p(legal), int(auto_reset)))
+        return packed, reward, done, life, legal
+
+    def reset_host_packed(self):
+        packed = np.zeros((self.state_rows - ROW_BM, self.stride), np.uint64)
+        legal = np.zeros((self.n, self.W), np.uint64)
+        self._check(self.L.dq_env_reset_host_packed(self.h, _p(packed), _p(legal)))
+        return packed, legal

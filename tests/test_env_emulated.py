@@ -216,3 +216,23 @@ def test_emulated_build_variants(name, flags):
                 if ring is not None and s >= S - 4:
                     assert np.array_equal(ring[s % 4], oobs)
         compare_state(a, o, range(min(n, 8)))
+
+
+@pytest.mark.parametrize("d,model,use_Y,vd,n", [(5, "DP", False, 5, 45), (7, "DP", True, 4, 19), (3, "X", False, 3, 33)])
+def test_emulated_packed_host_calls(d, model, use_Y, vd, n):
+    """dq_env_reset_host_packed / dq_env_step_host_packed: the bit-packed observation rows, expanded on the host by
+    deepq_decoding_b200.envs.unpack_observations, are the oracle's byte observations; every other output as usual."""
+    from deepq_decoding_b200.envs import unpack_observations
+    env, o = make_pair(d, model, use_Y, vd, 0.03, n, seed=5)
+    packed, legal = env.reset_host_packed()
+    oobs, olegal = o.reset()
+    assert packed.shape == (env.Cn * ((env.H * env.H + 63) // 64), env.stride)
+    assert np.array_equal(unpack_observations(packed, n, d, env.Cn), oobs) and np.array_equal(legal, olegal)
+    for t in range(30):
+        acts = o.random_legal_actions(olegal, t)
+        packed, rew, done, life, legal = env.step_host_packed(acts)
+        oobs, orew, odone, olife, olegal = o.step(acts, auto_reset=True)
+        assert np.array_equal(unpack_observations(packed, n, d, env.Cn), oobs), "packed obs t=%d" % t
+        assert np.array_equal(rew, orew) and np.array_equal(done, odone) and np.array_equal(life, olife)
+        assert np.array_equal(legal, olegal)
+        assert not packed[:, n:].any(), "padding lattices stay empty"
