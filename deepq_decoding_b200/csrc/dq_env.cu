@@ -57,7 +57,12 @@ constexpr int kWarps = kThreads / 32;
 #ifndef DQ_REFILL
 #define DQ_REFILL 2              // ... at most this many lattices per warp and step
 #endif
+#ifndef DQ_BATCHB
+#define DQ_BATCHB 0              // phase B in two stages: masks drawn warp per lattice, then applied / rendered lane per (lattice, slice)
+#endif
 constexpr bool kPrefetch = DQ_PREFETCH != 0;
+constexpr bool kBatchB = DQ_BATCHB != 0;
+static_assert(!(kPrefetch && kBatchB), "DQ_PREFETCH and DQ_BATCHB both use the prepared-mask buffers");
 constexpr int kRefill = DQ_REFILL;
 constexpr u32 kNoAttempt = 0xffffffffu;              // attempt indices have 31 bits
 constexpr int kPickGroup = (kThreads - 32) / kEpc;   // rollout steps whose policy words warps 1.. draw in one go (thread = (step, lattice))
@@ -226,7 +231,7 @@ struct Smem {
     u64 fx[kEpc], fz[kEpc], fmeta[kEpc];   // phase A -> B hand-off: frame planes, counters
     u64 sum[kEpc], acted[kEpc];       // OR of the volume's slices; OR of the action boards
     u32 acc[kWarps][3 * kMaxVd * 2];  // per-warp flip accumulators of generate_volume
-    u32 pre[kPrefetch ? kEpc : 1][3 * kMaxVd * 2];   // DQ_PREFETCH: flip masks of attempt pre_att[lattice] of each lattice, drawn ahead
+    u32 pre[(kPrefetch || kBatchB) ? kEpc : 1][3 * kMaxVd * 2];   // DQ_PREFETCH: flip masks of attempt pre_att[lattice] of each lattice, drawn ahead
     u32 pre_att[kEpc], att[kEpc];     // ... the attempt index they belong to; the lattice's current attempt counter
     uint8_t pre_anyq[kEpc];
     u32 pick_u[2][kPickGroup][kEpc];  // built-in policy: word 0 of the (lattice, step) policy block, drawn a group of steps ahead, double-buffered
@@ -234,6 +239,7 @@ struct Smem {
     int actbit[kEpc];                 // light step: (action layer << 16) | cell bit to set, else -1
     uint8_t task[kEpc], task_flags[kEpc];
     int ntask;
+    int npending[2];                  // DQ_BATCHB: lattices that still need a volume attempt after a round (by round parity)
 };
 
 // 32 bits of the tile's observation bit stream starting at bit `o` of (lattice, layer): the stream is the concatenation of the
@@ -516,67 +522,183 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             atomicOr(&sm.stream[sb >> 5], 1u << (sb & 31));
         }
     }
-    // ---- phase B: warp per flagged lattice: fresh volume(s), then re-render its layer bitmaps
-    for (int t = warp; t < sm.ntask; t += kWarps) {
-        const int slot = sm.task[t], fl = sm.task_flags[t];
-        const u32 env_id = p.env_id_base + (u32)(env0 + slot);
-        const int e = env0 + slot;
-        u64 bx = sm.fx[slot], bz = sm.fz[slot];
-        const u64 bm0 = sm.fmeta[slot];
-        u32 life = (u32)bm0, attempts = (u32)(bm0 >> 32) & 0x7FFFFFFFu, dn = (u32)(bm0 >> 63);
-        u64 f = 0;
-        int32_t lo = (int32_t)life;
-        // bit 0 of fl: heavy step (volume on the current frame), bit 1: restart of a finished lattice (volume on a clean frame), in
-        // that order; one copy of the generator serves both
-#pragma unroll 1
-        for (int todo = fl; todo; ) {
-            const bool restart = !(todo & 1);
-            if (restart) { bx = 0; bz = 0; life = 0; dn = 0; }
-            f = generate_volume<D>(p, sm.acc[warp], sm.pre[kPrefetch ? slot : 0], sm.pre_att[slot], sm.pre_anyq[slot] != 0,
-                                   lane, env_id, bx, bz, life, attempts);
-            if (!restart) lo = (int32_t)life;
-            todo = restart ? 0 : (todo & 2);
+    // ---- phase B: fresh volume(s) for the flagged lattices, then their layer bitmaps and stream spans
+    if constexpr (!kBatchB) {
+    // warp per flagged lattice
+        for (int t = warp; t < sm.ntask; t += kWarps) {
+            const int slot = sm.task[t], fl = sm.task_flags[t];
+            const u32 env_id = p.env_id_base + (u32)(env0 + slot);
+            const int e = env0 + slot;
+            u64 bx = sm.fx[slot], bz = sm.fz[slot];
+            const u64 bm0 = sm.fmeta[slot];
+            u32 life = (u32)bm0, attempts = (u32)(bm0 >> 32) & 0x7FFFFFFFu, dn = (u32)(bm0 >> 63);
+            u64 f = 0;
+            int32_t lo = (int32_t)life;
+            // bit 0 of fl: heavy step (volume on the current frame), bit 1: restart of a finished lattice (volume on a clean frame), in
+            // that order; one copy of the generator serves both
+    #pragma unroll 1
+            for (int todo = fl; todo; ) {
+                const bool restart = !(todo & 1);
+                if (restart) { bx = 0; bz = 0; life = 0; dn = 0; }
+                f = generate_volume<D>(p, sm.acc[warp], sm.pre[kPrefetch ? slot : 0], sm.pre_att[slot], sm.pre_anyq[slot] != 0,
+                                       lane, env_id, bx, bz, life, attempts);
+                if (!restart) lo = (int32_t)life;
+                todo = restart ? 0 : (todo & 2);
+            }
+            u64 summed = f;                                 // lanes >= vd hold 0
+            summed |= __shfl_xor_sync(FULL, summed, 1);
+            summed |= __shfl_xor_sync(FULL, summed, 2);
+            summed |= __shfl_xor_sync(FULL, summed, 4);
+            if (lane == 0) {
+                p.state[ROW_XB * np + e] = bx;
+                p.state[ROW_ZB * np + e] = bz;
+                p.state[ROW_META * np + e] = meta_pack(life, attempts, dn);
+                p.state[ROW_SUM * np + e] = summed;
+                sm.sum[slot] = summed; sm.acted[slot] = 0;
+                if (kPrefetch) sm.att[slot] = attempts;
+                if (!RESET) sm.life_out[slot] = lo;
+            }
+            if (lane < p.layers) p.state[(ROW_ACT + lane) * np + e] = 0;
+            // render: lane j < vd holds slice j and builds that layer's bitmap in registers; lanes vd..C-1 clear the action layers
+            if (lane < C) {
+                u64 w[PW];
+                syndrome_layer_bitmap<D>(f, w);
+    #pragma unroll
+                for (int i = 0; i < PW; ++i) {
+                    const u64 v = lane < p.vd ? w[i] : 0ull;
+                    sm.bm[slot][lane * PW + i] = v;
+                    p.state[(ROW_BM + lane * PW + i) * np + e] = v;
+                }
+            }
+            __syncwarp();
+            // this lattice's span of the tile's bit stream; its first and last word are shared with the neighbouring lattices, which
+            // other warps may be re-rendering right now: only this lattice's bits of those are replaced, atomically
+            {
+                const int b0 = slot * p.obs_bits, b1 = b0 + p.obs_bits;
+                for (int wi = (b0 >> 5) + lane; wi <= ((b1 - 1) >> 5); wi += 32) {
+                    const int lo = max(b0 - wi * 32, 0), hi = min(b1 - wi * 32, 32);          // bits [lo, hi) of the word are this lattice's
+                    const u32 mask = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                    const u32 v = stream_word<D>(sm, p, wi, C);
+                    if (mask == 0xffffffffu) sm.stream[wi] = v;
+                    else { atomicAnd(&sm.stream[wi], ~mask); atomicOr(&sm.stream[wi], v & mask); }
+                }
+            }
         }
-        u64 summed = f;                                 // lanes >= vd hold 0
-        summed |= __shfl_xor_sync(FULL, summed, 1);
-        summed |= __shfl_xor_sync(FULL, summed, 2);
-        summed |= __shfl_xor_sync(FULL, summed, 4);
-        if (lane == 0) {
-            p.state[ROW_XB * np + e] = bx;
-            p.state[ROW_ZB * np + e] = bz;
-            p.state[ROW_META * np + e] = meta_pack(life, attempts, dn);
-            p.state[ROW_SUM * np + e] = summed;
-            sm.sum[slot] = summed; sm.acted[slot] = 0;
-            if (kPrefetch) sm.att[slot] = attempts;
-            if (!RESET) sm.life_out[slot] = lo;
+    } else {
+    // DQ_BATCHB.  Everything after the draws of a volume attempt is a few lanes' work per lattice, so a warp per lattice runs it at
+    // 5-8 active lanes.  Here a round is two stages: (1) the flip masks of ONE attempt of every lattice that still needs a volume,
+    // warp per lattice (all lanes busy: Philox + thresholds); (2) after a block barrier, lane = (lattice of a group of four,
+    // slice): prefix-XOR, syndromes, triviality test, and for the lattices whose volume is complete the state, the layer bitmaps
+    // and the stream spans -- one pass for up to four lattices.  Task flags: bit 0 heavy volume pending, bit 1 restart pending,
+    // bit 2 restart in progress (its frame was reset).  Rounds repeat while a lattice drew an all-trivial volume or still has
+    // its restart to do (block-uniform: counted in npending[round parity]).
+    for (int round = 0;; ++round) {
+        for (int t = warp; t < sm.ntask; t += kWarps) {
+            if (!sm.task_flags[t]) continue;
+            const int slot = sm.task[t];
+            const u32 att = (u32)(sm.fmeta[slot] >> 32) & 0x7FFFFFFFu;
+            const bool anyq = draw_flip_masks<D>(p, sm.pre[slot], lane, p.env_id_base + (u32)(env0 + slot), att);
+            if (lane == 0) sm.pre_anyq[slot] = anyq ? 1 : 0;
         }
-        if (lane < p.layers) p.state[(ROW_ACT + lane) * np + e] = 0;
-        // render: lane j < vd holds slice j and builds that layer's bitmap in registers; lanes vd..C-1 clear the action layers
-        if (lane < C) {
-            u64 w[PW];
-            syndrome_layer_bitmap<D>(f, w);
+        if (tid == 0) sm.npending[round & 1] = 0;
+        __syncthreads();
+        const int ntask = sm.ntask;
+        for (int c = warp; c * 4 < ntask; c += kWarps) {
+            const int j = lane >> 3, sl = lane & 7, t = c * 4 + j;
+            int fl = t < ntask ? sm.task_flags[t] : 0;
+            const bool act = fl != 0;
+            const int slot = t < ntask ? sm.task[t] : 0;
+            const int e = env0 + slot;
+            u64 xb = sm.fx[slot], zb = sm.fz[slot];
+            const u64 bm0 = sm.fmeta[slot];
+            u32 life = (u32)bm0, attempts = (u32)(bm0 >> 32) & 0x7FFFFFFFu, dn = (u32)(bm0 >> 63);
+            const bool heavy = (fl & 1) != 0;
+            if (act && !heavy && (fl & 2)) { xb = 0; zb = 0; life = 0; dn = 0; fl = 4; }      // the restart begins on a clean frame
+            u64 ex = 0, ez = 0, m = 0;
+            if (act && sl < p.vd) {
+                const u64* a64 = reinterpret_cast<const u64*>(sm.pre[slot]);
+                ex = a64[0 * kMaxVd + sl]; ez = a64[1 * kMaxVd + sl]; m = a64[2 * kMaxVd + sl];
+            }
 #pragma unroll
-            for (int i = 0; i < PW; ++i) {
-                const u64 v = lane < p.vd ? w[i] : 0ull;
-                sm.bm[slot][lane * PW + i] = v;
-                p.state[(ROW_BM + lane * PW + i) * np + e] = v;
+            for (int off = 1; off < kMaxVd; off <<= 1) {          // inclusive prefix XOR over the slices of each 8-lane group
+                const u64 tx = __shfl_up_sync(FULL, ex, off, 8), tz = __shfl_up_sync(FULL, ez, off, 8);
+                if (sl >= off) { ex ^= tx; ez ^= tz; }
+            }
+            const u64 fx = xb ^ ex, fz = zb ^ ez;
+            const u64 f = (act && sl < p.vd) ? (true_syndrome<D>(fx, fz) ^ m) : 0ull;
+            const u32 bal = __ballot_sync(FULL, f != 0);
+            const bool nontrivial = ((bal >> (j * 8)) & 0xFFu) != 0 || round >= kMaxAttemptsPerCall - 1;
+            xb = __shfl_sync(FULL, fx, p.vd - 1, 8);
+            zb = __shfl_sync(FULL, fz, p.vd - 1, 8);
+            life += (u32)p.vd;
+            attempts += 1;
+            bool complete = false, heavy_done = false;
+            if (act && nontrivial) {
+                if (heavy) { heavy_done = true; fl &= ~1; complete = fl == 0; }
+                else { fl = 0; complete = true; }
+            }
+            u64 summed = f;
+            summed |= __shfl_xor_sync(FULL, summed, 1, 8);
+            summed |= __shfl_xor_sync(FULL, summed, 2, 8);
+            summed |= __shfl_xor_sync(FULL, summed, 4, 8);
+            if (act && sl == 0) {
+                sm.fx[slot] = xb; sm.fz[slot] = zb; sm.fmeta[slot] = meta_pack(life, attempts, dn);
+                sm.task_flags[t] = (uint8_t)fl;
+                if (fl) atomicAdd(&sm.npending[round & 1], 1);
+                if (heavy_done && !RESET) sm.life_out[slot] = (int32_t)life;
+                if (complete) {
+                    p.state[ROW_XB * np + e] = xb;
+                    p.state[ROW_ZB * np + e] = zb;
+                    p.state[ROW_META * np + e] = meta_pack(life, attempts, dn);
+                    p.state[ROW_SUM * np + e] = summed;
+                    sm.sum[slot] = summed; sm.acted[slot] = 0;
+                }
+            }
+            if (complete) {
+                u64 w[PW];
+                syndrome_layer_bitmap<D>(f, w);
+                if (sl < p.vd) {
+#pragma unroll
+                    for (int i = 0; i < PW; ++i) {
+                        sm.bm[slot][sl * PW + i] = w[i];
+                        p.state[(ROW_BM + sl * PW + i) * np + e] = w[i];
+                    }
+                }
+                if (sl < p.layers) {                           // the action boards and their layers are cleared
+                    p.state[(ROW_ACT + sl) * np + e] = 0;
+#pragma unroll
+                    for (int i = 0; i < PW; ++i) {
+                        sm.bm[slot][(p.vd + sl) * PW + i] = 0ull;
+                        p.state[(ROW_BM + (p.vd + sl) * PW + i) * np + e] = 0ull;
+                    }
+                }
+            }
+            __syncwarp();
+            // stream spans of the completed lattices of this group of four, as one list of (lattice, word) pairs over the lanes
+            // (a span's first / last word is shared with the neighbouring lattices: atomics)
+            {
+                const u32 cmask = __ballot_sync(FULL, complete && sl == 0);
+                const int nws = ((p.obs_bits + 31) >> 5) + 1;             // words a lattice's span can touch
+                for (int base = 0; base < 4 * nws; base += 32) {
+                    const int idx = base + lane;
+                    const int jj = (idx >= nws) + (idx >= 2 * nws) + (idx >= 3 * nws), k = idx - jj * nws;
+                    const int sj = __shfl_sync(FULL, slot, (jj & 3) * 8);
+                    const int b0 = sj * p.obs_bits, b1 = b0 + p.obs_bits, wi = (b0 >> 5) + k;
+                    if (idx < 4 * nws && ((cmask >> (jj * 8)) & 1u) && wi <= ((b1 - 1) >> 5)) {
+                        const int lo = max(b0 - wi * 32, 0), hi = min(b1 - wi * 32, 32);
+                        const u32 mask = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                        const u32 v = stream_word<D>(sm, p, wi, C);
+                        if (mask == 0xffffffffu) sm.stream[wi] = v;
+                        else { atomicAnd(&sm.stream[wi], ~mask); atomicOr(&sm.stream[wi], v & mask); }
+                    }
+                }
             }
         }
-        __syncwarp();
-        // this lattice's span of the tile's bit stream; its first and last word are shared with the neighbouring lattices, which
-        // other warps may be re-rendering right now: only this lattice's bits of those are replaced, atomically
-        {
-            const int b0 = slot * p.obs_bits, b1 = b0 + p.obs_bits;
-            for (int wi = (b0 >> 5) + lane; wi <= ((b1 - 1) >> 5); wi += 32) {
-                const int lo = max(b0 - wi * 32, 0), hi = min(b1 - wi * 32, 32);          // bits [lo, hi) of the word are this lattice's
-                const u32 mask = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-                const u32 v = stream_word<D>(sm, p, wi, C);
-                if (mask == 0xffffffffu) sm.stream[wi] = v;
-                else { atomicAnd(&sm.stream[wi], ~mask); atomicOr(&sm.stream[wi], v & mask); }
-            }
-        }
+        __syncthreads();
+        if (sm.npending[round & 1] == 0) break;
     }
-    __syncthreads();
+    }
+    if constexpr (!kBatchB) __syncthreads();
 
     // ---- phase C: lifetime and legal mask (warp 0, lane = lattice; the mask also feeds the next step's built-in pick)
     if (tid < kEpc) {

@@ -18,6 +18,9 @@ variant() {   # name, extra flags
     rm -f $OUT/dq_env_$name.o
     echo "built $OUT/libdq_$name.so"
 }
+variant bb         -DDQ_BATCHB=1
+variant bbmb8      -DDQ_BATCHB=1 -DDQ_MIN_BLOCKS=8
+variant pf1        -DDQ_PREFETCH=1 -DDQ_REFILL=1
 variant pf2        -DDQ_PREFETCH=1
 variant pf3        -DDQ_PREFETCH=1 -DDQ_REFILL=3
 variant pf2mb8     -DDQ_PREFETCH=1 -DDQ_MIN_BLOCKS=8
