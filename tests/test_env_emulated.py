@@ -238,3 +238,53 @@ def test_emulated_packed_host_calls(d, model, use_Y, vd, n):
         assert np.array_equal(rew, orew) and np.array_equal(done, odone) and np.array_equal(life, olife)
         assert np.array_equal(legal, olegal)
         assert not packed[:, n:].any(), "padding lattices stay empty"
+
+
+@pytest.mark.parametrize("seed0", [100, 200, 300])
+def test_emulated_random_configurations(seed0):
+    """Randomised sweep over the whole parameter space of the C ABI (d, noise model, use_Y, volume depth 1..8, lattice count,
+    stream id base, p_phys / p_meas from 0 to 0.2, auto-reset on or off): explicit actions (30 % arbitrary, some out of range),
+    single-step launches and rollouts of random length into rings of random size, then the packed state -- all against the oracle."""
+    lut_cache = {}
+    for it in range(6):
+        rng = np.random.default_rng(seed0 + it)
+        d = int(rng.choice([3, 5, 7])); model = str(rng.choice(["X", "DP"])); use_Y = bool(rng.integers(0, 2)) and model == "DP"
+        vd = int(rng.integers(1, 9)); n = int(rng.integers(1, 70)); base = int(rng.integers(0, 1000)); seed = int(rng.integers(0, 2 ** 62))
+        pp = float(rng.choice([0.0, 0.002, 0.01, 0.05, 0.2])); pm = float(rng.choice([0.0, 0.002, 0.01, 0.05, 0.2]))
+        if pp == 0.0 and pm == 0.0:
+            pm = 0.01
+        ar = bool(rng.integers(0, 2))
+        cfg = dict(d=d, model=model, use_Y=use_Y, vd=vd, n=n, base=base, seed=seed, p_phys=pp, p_meas=pm, auto_reset=ar)
+        if (d, model) not in lut_cache:
+            lut_cache[(d, model)] = random_luts(np.random.default_rng(d * 7 + len(model)), d, model)
+        mode, la, lb = lut_cache[(d, model)]
+        env = E.EmuVecEnv(d, model, use_Y, vd, pp, pm, n, seed, base)
+        o = O.OracleVecEnv(d, model, use_Y, vd, pp, pm, n, seed, base)
+        env.set_referee(mode, la, lb); o.set_referee(mode, la, lb)
+        obs, legal = env.reset()
+        oobs, olegal = o.reset()
+        assert np.array_equal(obs, oobs) and np.array_equal(legal, olegal), cfg
+        t = 0
+        for _ in range(3):
+            if int(rng.integers(0, 3)) == 0:
+                for _ in range(6):
+                    acts = o.random_legal_actions(olegal, t)
+                    arb = rng.random(n) < 0.3
+                    acts[arb] = rng.integers(-2, o.A + 2, size=int(arb.sum()))
+                    oacts = np.where((acts < 0) | (acts >= o.A), o.A - 1, acts).astype(np.int32)
+                    got, want = env.step(acts, auto_reset=ar), o.step(oacts, auto_reset=ar)
+                    olegal = want[4]; t += 1
+                    assert all(np.array_equal(g, w) for g, w in zip(got, want)), cfg
+            else:
+                S, slots = int(rng.integers(1, 14)), int(rng.integers(1, 5))
+                fs = int(rng.integers(0, slots))
+                env.policy_seek(t)
+                ring, rew, done, life, legal2, acts = env.rollout_random(S, slots, fs, ar)
+                for s in range(S):
+                    oa = o.random_legal_actions(olegal, t)
+                    oobs, orew, odone, olife, olegal = o.step(oa, auto_reset=ar); t += 1
+                    assert np.array_equal(acts[s], oa) and np.array_equal(rew[s], orew) and np.array_equal(done[s], odone), cfg
+                    assert np.array_equal(life[s], olife) and np.array_equal(legal2[s], olegal), cfg
+                    if s >= S - slots:
+                        assert np.array_equal(ring[(fs + s) % slots], oobs), cfg
+        compare_state(env, o, range(min(n, 6)))
