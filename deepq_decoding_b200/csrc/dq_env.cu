@@ -25,9 +25,7 @@
 //
 // Replaces (reference paths relative to example_notebooks/): Environments.py:99-115 (reset),
 // :118-204 (step), :206-235, :238-314 and the Function_Library.py helpers they call.
-#ifndef DQ_EMU                    // DQ_EMU: tests/host/cuda_emu.h runs this same source on the CPU (test infrastructure only)
 #include <cuda_runtime.h>
-#endif
 #include <stdint.h>
 #include <string.h>
 #include <math.h>
@@ -342,11 +340,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     typedef Lat<D> L;
     constexpr u32 FULL = 0xffffffffu;
     constexpr int PW = L::PW, H = L::H;
-#ifdef DQ_EMU
-    unsigned char* const smem_raw = DQ_EMU_DYNAMIC_SMEM;
-#else
     extern __shared__ __align__(128) unsigned char smem_raw[];
-#endif
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -917,17 +911,11 @@ static int launch_env(dq_env* e, const int32_t* actions, uint8_t* obs, float* re
                       Rollout ro = Rollout{1, 1, 0, 0, 0}) {
     const EnvParams& p = e->p;
     const dim3 grid(p.npad / kEpc), block(kThreads);
-#ifdef DQ_EMU
-#define DQ_ENV_LAUNCH(D) dq_emu::launch(grid, block, e->smem_bytes, [&]() { env_step_kernel<D, RESET>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); })
-#else
-#define DQ_ENV_LAUNCH(D) env_step_kernel<D, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro)
-#endif
     switch (p.d) {
-        case 3: DQ_ENV_LAUNCH(3); break;
-        case 5: DQ_ENV_LAUNCH(5); break;
-        case 7: DQ_ENV_LAUNCH(7); break;
+        case 3: env_step_kernel<3, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;
+        case 5: env_step_kernel<5, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;
+        case 7: env_step_kernel<7, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;
     }
-#undef DQ_ENV_LAUNCH
     g_launches.fetch_add(1);
     DQ_CUDA(cudaGetLastError());
     return DQ_OK;
@@ -1081,12 +1069,8 @@ extern "C" int dq_env_set_state(dq_env* e, const uint64_t* dev_words, dq_stream 
 
 static int launch_policy(const dq_env* e, const uint64_t* legal, u32 step, u32* ctr, int32_t* actions, cudaStream_t st) {
     const EnvParams& p = e->p;
-#ifdef DQ_EMU
-    dq_emu::launch((p.n + 127) / 128, 128, 0, [&]() { policy_random_legal_kernel((const u64*)legal, p.n, p.W, p.A, p.env_id_base, step, ctr, p.k0, p.k1, actions); });
-#else
     policy_random_legal_kernel<<<(p.n + 127) / 128, 128, 0, st>>>((const u64*)legal, p.n, p.W, p.A, p.env_id_base, step, ctr,
                                                                   p.k0, p.k1, actions);
-#endif
     g_launches.fetch_add(1);
     DQ_CUDA(cudaGetLastError());
     return DQ_OK;
@@ -1101,11 +1085,7 @@ extern "C" int dq_policy_random_legal(const dq_env* e, const uint64_t* legal, ui
 extern "C" int dq_policy_seek(dq_env* e, uint32_t step, dq_stream stream) {
     if (!e) return fail(DQ_EINVAL, "env is NULL");
     DeviceGuard g(e->device);
-#ifdef DQ_EMU
-    dq_emu::launch(1, 1, 0, [&]() { set_u32_kernel(e->policy_ctr, step); });
-#else
     set_u32_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(e->policy_ctr, step);
-#endif
     g_launches.fetch_add(1);
     DQ_CUDA(cudaGetLastError());
     return DQ_OK;

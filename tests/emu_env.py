@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE: the environment's C ABI served by the CUDA kernel source executed on the CPU.
 
-`tests/host/cuda_emu.h` compiles `deepq_decoding_b200/csrc/dq_env.cu` itself (same templates, same shared-memory
-struct, same warp primitives and barriers) into `tests/host/libdq_env_emu.so`; "device pointers" are numpy
+`tests/host/cuda_emu.h` + `tests/host/emu_build.py` compile `deepq_decoding_b200/csrc/dq_env.cu` itself (same templates, same
+shared-memory struct, same warp primitives and barriers; only the `<<<...>>>` launch syntax and the dynamic shared-memory
+declaration are rewritten, in a generated copy) into `tests/host/libdq_env_emu.so`; "device pointers" are numpy
 buffers.  `EmuVecEnv` is the thin numpy caller the tests use to compare that build with the oracle when no
 GPU is present, so a kernel change can be checked bit for bit before it ever reaches a B200.  Nothing under
 `deepq_decoding_b200/` imports this, and nothing here is a fallback: the product raises without a GPU.
@@ -22,13 +23,10 @@ ROW_XB, ROW_ZB, ROW_META, ROW_ACT, ROW_SUM, ROW_BM = 0, 1, 2, 3, 6, 7
 
 
 def build(extra_flags=(), out=OUT):
-    deps = [SRC, SHIM, os.path.join(os.path.dirname(SRC), "dq_lattice.cuh"), os.path.join(ROOT, "include", "dq_decoding.h")]
-    if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(f) for f in deps):
-        return out
-    cmd = ["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-DDQ_EMU", "-include", SHIM, *extra_flags,
-           "-x", "c++", SRC, "-o", out]
-    subprocess.check_call(cmd)
-    return out
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "host"))
+    import emu_build
+    return emu_build.build(out, [SRC], extra_flags=tuple(extra_flags))
 
 
 _LIB = {}

@@ -1,7 +1,9 @@
-// cuda_emu.h -- TEST INFRASTRUCTURE: runs the CUDA source of the environment kernel on the CPU.
+// cuda_emu.h -- TEST INFRASTRUCTURE: runs the CUDA source of the product's SIMT kernels on the CPU.
 //
-// `g++ -DDQ_EMU -include tests/host/cuda_emu.h -x c++ deepq_decoding_b200/csrc/dq_env.cu` compiles the SAME kernel
-// source the GPU runs (templates, shared-memory struct, warp shuffles, ballots, barriers) into a host library whose
+// tests/host/emu_build.py copies a product source (csrc/dq_env.cu, the fp32 half of csrc/dq_qnet.cu), rewrites only the
+// `<<<...>>>` launch syntax and the dynamic shared-memory declaration, and compiles the copy with
+// `g++ -include tests/host/cuda_emu.h`: the SAME kernel code the GPU runs (templates, shared-memory structs, warp shuffles,
+// ballots, barriers) becomes a host library whose
 // "device pointers" are host pointers.  Every CUDA thread of a CTA is a cooperative fiber (ucontext); a warp-level
 // primitive (__shfl*_sync, __ballot_sync, __any_sync, __syncwarp) or __syncthreads parks the fiber until every
 // participating lane / thread has arrived, exactly the rendez-vous the hardware performs, so the kernel's control

@@ -1,7 +1,6 @@
 """TEST INFRASTRUCTURE: turns CUDA sources of the product into host C++ for the CPU execution harness (cuda_emu.h).
 
-`dq_env.cu` carries its own `#ifdef DQ_EMU` hooks.  Other sources are left untouched in the product tree and rewritten
-here, textually, into a generated .cpp:
+The product sources carry no emulation hooks: they are rewritten here, textually, into a generated .cpp:
 
   * `kernel<<<grid, block, smem, stream>>>(args);`  ->  `dq_emu::launch(grid, block, smem, [&]() { kernel(args); });`
   * `extern __shared__ T name[];`                   ->  `T* name = reinterpret_cast<T*>(DQ_EMU_DYNAMIC_SMEM);`
@@ -38,10 +37,10 @@ def _match(text, i, open_ch, close_ch):
 def _split_top(s):
     """split on commas that are not nested in (), <>, [] or {}"""
     out, depth, cur = [], 0, ""
-    for ch in s:
+    for k, ch in enumerate(s):
         if ch in "([{<":
             depth += 1
-        elif ch in ")]}>":
+        elif ch in ")]}>" and not (ch == ">" and k > 0 and s[k - 1] == "-"):        # `->` is not a bracket
             depth -= 1
         if ch == "," and depth == 0:
             out.append(cur.strip()); cur = ""
@@ -92,13 +91,13 @@ def transform(path, cut_marker=None, tail=""):
         text = text[:text.index(cut_marker)] + "\n" + tail + "\n"
     text = re.sub(r'#include\s+"dq_ptx\.cuh"', "", text)
     text = text.replace('"../../include/dq_decoding.h"', '"%s"' % os.path.join(ROOT, "include", "dq_decoding.h"))
-    text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([A-Za-z_][\w:]*)\s+(\w+)\[\];",
+    text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?((?:unsigned\s+)?[A-Za-z_][\w:]*)\s+(\w+)\[\];",
                   r"\1* \2 = reinterpret_cast<\1*>(DQ_EMU_DYNAMIC_SMEM);", text)
     return rewrite_launches(text)
 
 
 def build(out, sources, extra_flags=(), deps=()):
-    """sources: list of (path, cut_marker, tail) or plain paths (compiled as they are, e.g. dq_env.cu)."""
+    """sources: list of (path, cut_marker, tail) tuples, or plain paths for sources that need no cut."""
     os.makedirs(GEN, exist_ok=True)
     all_deps = [SHIM, os.path.abspath(__file__), os.path.join(ROOT, "include", "dq_decoding.h"),
                 os.path.join(CSRC, "dq_lattice.cuh"), os.path.join(CSRC, "dq_adam.cuh"), *deps]
@@ -109,10 +108,7 @@ def build(out, sources, extra_flags=(), deps=()):
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(f) for f in all_deps):
         return out
     for s in sources:
-        if isinstance(s, str):
-            files.append(s)
-            continue
-        path, cut, tail = s
+        path, cut, tail = (s, None, "") if isinstance(s, str) else s
         gen = os.path.join(GEN, os.path.basename(path).replace(".cu", "_emu.cpp"))
         with open(gen, "w") as f:
             f.write('#line 1 "%s"\n' % path)
