@@ -530,7 +530,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             int32_t lo = (int32_t)life;
             // bit 0 of fl: heavy step (volume on the current frame), bit 1: restart of a finished lattice (volume on a clean frame), in
             // that order; one copy of the generator serves both
-    #pragma unroll 1
+#pragma unroll 1
             for (int todo = fl; todo; ) {
                 const bool restart = !(todo & 1);
                 if (restart) { bx = 0; bz = 0; life = 0; dn = 0; }
@@ -557,7 +557,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             if (lane < C) {
                 u64 w[PW];
                 syndrome_layer_bitmap<D>(f, w);
-    #pragma unroll
+#pragma unroll
                 for (int i = 0; i < PW; ++i) {
                     const u64 v = lane < p.vd ? w[i] : 0ull;
                     sm.bm[slot][lane * PW + i] = v;
