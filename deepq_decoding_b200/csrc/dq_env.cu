@@ -56,8 +56,8 @@ constexpr int kWarps = kThreads / 32;
 #define DQ_REFILL 2              // ... at most this many lattices per warp and step
 #endif
 #ifndef DQ_BATCHB
-#define DQ_BATCHB 0              // phase B in two stages: masks drawn warp per lattice, then applied / rendered lane per (lattice, slice)
-#endif
+#define DQ_BATCHB 0              // 1: phase B in rounds of two stages: masks drawn warp per lattice, then applied / rendered lane per (lattice, slice)
+#endif                           // 2: volumes warp per lattice as in the default build, only their finalisation (state, bitmaps, stream) batched
 constexpr bool kPrefetch = DQ_PREFETCH != 0;
 constexpr bool kBatchB = DQ_BATCHB != 0;
 static_assert(!(kPrefetch && kBatchB), "DQ_PREFETCH and DQ_BATCHB both use the prepared-mask buffers");
@@ -238,6 +238,7 @@ struct Smem {
     uint8_t task[kEpc], task_flags[kEpc];
     int ntask;
     int npending[2];                  // DQ_BATCHB: lattices that still need a volume attempt after a round (by round parity)
+    u64 fsl[DQ_BATCHB == 2 ? kEpc : 1][kMaxVd];   // DQ_BATCHB=2: the slices of a finished volume, handed from its warp to the batched finalisation
 };
 
 // 32 bits of the tile's observation bit stream starting at bit `o` of (lattice, layer): the stream is the concatenation of the
@@ -578,8 +579,94 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                 }
             }
         }
+    } else if constexpr (DQ_BATCHB == 2) {
+    // DQ_BATCHB=2.  Stage 1, warp per flagged lattice: the volume(s) exactly as in the default build (attempts retried inside the
+    // warp, no block barrier), but nothing of the few-lane work that follows: the finished slices, frame and counters are left in
+    // shared memory.  Stage 2, after one block barrier, lane = (lattice of a group of four, slice): state rows, layer bitmaps,
+    // action boards and stream spans of four lattices in one pass.
+    for (int t = warp; t < sm.ntask; t += kWarps) {
+        const int slot = sm.task[t], fl = sm.task_flags[t];
+        const u32 env_id = p.env_id_base + (u32)(env0 + slot);
+        u64 bx = sm.fx[slot], bz = sm.fz[slot];
+        const u64 bm0 = sm.fmeta[slot];
+        u32 life = (u32)bm0, attempts = (u32)(bm0 >> 32) & 0x7FFFFFFFu, dn = (u32)(bm0 >> 63);
+        u64 f = 0;
+        int32_t lo = (int32_t)life;
+#pragma unroll 1
+        for (int todo = fl; todo; ) {
+            const bool restart = !(todo & 1);
+            if (restart) { bx = 0; bz = 0; life = 0; dn = 0; }
+            f = generate_volume<D>(p, sm.acc[warp], sm.pre[0], kNoAttempt, false, lane, env_id, bx, bz, life, attempts);
+            if (!restart) lo = (int32_t)life;
+            todo = restart ? 0 : (todo & 2);
+        }
+        if (lane < kMaxVd) sm.fsl[slot][lane] = f;               // lanes >= vd hold 0
+        if (lane == 0) {
+            sm.fx[slot] = bx; sm.fz[slot] = bz; sm.fmeta[slot] = meta_pack(life, attempts, dn);
+            if (!RESET) sm.life_out[slot] = lo;
+        }
+    }
+    __syncthreads();
+    {
+        const int ntask = sm.ntask;
+        for (int c = warp; c * 4 < ntask; c += kWarps) {
+            const int j = lane >> 3, sl = lane & 7, t = c * 4 + j;
+            const bool complete = t < ntask;
+            const int slot = complete ? sm.task[t] : 0;
+            const int e = env0 + slot;
+            const u64 f = complete ? sm.fsl[slot][sl] : 0ull;
+            u64 summed = f;
+            summed |= __shfl_xor_sync(FULL, summed, 1, 8);
+            summed |= __shfl_xor_sync(FULL, summed, 2, 8);
+            summed |= __shfl_xor_sync(FULL, summed, 4, 8);
+            if (complete) {
+                if (sl == 0) {
+                    p.state[ROW_XB * np + e] = sm.fx[slot];
+                    p.state[ROW_ZB * np + e] = sm.fz[slot];
+                    p.state[ROW_META * np + e] = sm.fmeta[slot];
+                    p.state[ROW_SUM * np + e] = summed;
+                    sm.sum[slot] = summed; sm.acted[slot] = 0;
+                }
+                u64 w[PW];
+                syndrome_layer_bitmap<D>(f, w);
+                if (sl < p.vd) {
+#pragma unroll
+                    for (int i = 0; i < PW; ++i) {
+                        sm.bm[slot][sl * PW + i] = w[i];
+                        p.state[(ROW_BM + sl * PW + i) * np + e] = w[i];
+                    }
+                }
+                if (sl < p.layers) {                           // the action boards and their layers are cleared
+                    p.state[(ROW_ACT + sl) * np + e] = 0;
+#pragma unroll
+                    for (int i = 0; i < PW; ++i) {
+                        sm.bm[slot][(p.vd + sl) * PW + i] = 0ull;
+                        p.state[(ROW_BM + (p.vd + sl) * PW + i) * np + e] = 0ull;
+                    }
+                }
+            }
+            __syncwarp();
+            // stream spans of the group's lattices as one list of (lattice, word) pairs over the lanes
+            const u32 cmask = __ballot_sync(FULL, complete && sl == 0);
+            const int nws = ((p.obs_bits + 31) >> 5) + 1;
+            for (int base = 0; base < 4 * nws; base += 32) {
+                const int idx = base + lane;
+                const int jj = (idx >= nws) + (idx >= 2 * nws) + (idx >= 3 * nws), k = idx - jj * nws;
+                const int sj = __shfl_sync(FULL, slot, (jj & 3) * 8);
+                const int b0 = sj * p.obs_bits, b1 = b0 + p.obs_bits, wi = (b0 >> 5) + k;
+                if (idx < 4 * nws && ((cmask >> (jj * 8)) & 1u) && wi <= ((b1 - 1) >> 5)) {
+                    const int lo = max(b0 - wi * 32, 0), hi = min(b1 - wi * 32, 32);
+                    const u32 mask = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                    const u32 v = stream_word<D>(sm, p, wi, C);
+                    if (mask == 0xffffffffu) sm.stream[wi] = v;
+                    else { atomicAnd(&sm.stream[wi], ~mask); atomicOr(&sm.stream[wi], v & mask); }
+                }
+            }
+        }
+    }
+    __syncthreads();
     } else {
-    // DQ_BATCHB.  Everything after the draws of a volume attempt is a few lanes' work per lattice, so a warp per lattice runs it at
+    // DQ_BATCHB=1.  Everything after the draws of a volume attempt is a few lanes' work per lattice, so a warp per lattice runs it at
     // 5-8 active lanes.  Here a round is two stages: (1) the flip masks of ONE attempt of every lattice that still needs a volume,
     // warp per lattice (all lanes busy: Philox + thresholds); (2) after a block barrier, lane = (lattice of a group of four,
     // slice): prefix-XOR, syndromes, triviality test, and for the lattices whose volume is complete the state, the layer bitmaps

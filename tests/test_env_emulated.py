@@ -182,6 +182,7 @@ def test_emulated_distinct_measurement_rate(p_phys, p_meas):
 VARIANTS = [("prefetch", ["-DDQ_PREFETCH=1"]),
             ("prefetch_refill1", ["-DDQ_PREFETCH=1", "-DDQ_REFILL=1"]),
             ("batched_phase_b", ["-DDQ_BATCHB=1"]),
+            ("batched_finalisation", ["-DDQ_BATCHB=2"]),
             ("batched_phase_b_tile32x256", ["-DDQ_BATCHB=1", "-DDQ_EPC=32", "-DDQ_THREADS=256"]),
             ("tile32x256", ["-DDQ_EPC=32", "-DDQ_THREADS=256"]),
             ("tile8x64_prefetch", ["-DDQ_EPC=8", "-DDQ_THREADS=64", "-DDQ_PREFETCH=1"])]

@@ -18,6 +18,7 @@ variant() {   # name, extra flags
     rm -f $OUT/dq_env_$name.o
     echo "built $OUT/libdq_$name.so"
 }
+variant bb2        -DDQ_BATCHB=2
 variant bb         -DDQ_BATCHB=1
 variant bbmb8      -DDQ_BATCHB=1 -DDQ_MIN_BLOCKS=8
 variant pf1        -DDQ_PREFETCH=1 -DDQ_REFILL=1
