@@ -28,6 +28,8 @@ variant pf2mb8     -DDQ_PREFETCH=1 -DDQ_MIN_BLOCKS=8
 variant mb8        -DDQ_MIN_BLOCKS=8
 variant mb10       -DDQ_MIN_BLOCKS=10
 variant e8t64mb14  -DDQ_EPC=8  -DDQ_THREADS=64  -DDQ_MIN_BLOCKS=14
+variant e16t96     -DDQ_EPC=16 -DDQ_THREADS=96  -DDQ_MIN_BLOCKS=7
+variant bb2t96     -DDQ_BATCHB=2 -DDQ_THREADS=96 -DDQ_MIN_BLOCKS=7
 variant e32t256mb4 -DDQ_EPC=32 -DDQ_THREADS=256 -DDQ_MIN_BLOCKS=4
 variant e16t256mb4 -DDQ_EPC=16 -DDQ_THREADS=256 -DDQ_MIN_BLOCKS=4
 if [ -n "$OLD_REV" ]; then    # control: the env kernel of an earlier commit, built in a scratch copy

@@ -45,7 +45,7 @@ unset DQ_DECODING_LIB
 [ "$BEST" != "new" ] && run bench_default 90 python bench.py --cpu-seconds 3 --no-dqn
 run pytest_rest 90 python -m pytest tests -m gpu -x -q --deselect tests/test_env_gpu.py
 run smoke 40 python __graft_entry__.py smoke
-for v in e16t256mb4 mb10; do
+for v in e16t96 bb2t96 pf2 e8t64mb14; do
     DQ_ONLY_ROLLOUT=256 DQ_DECODING_LIB=build/variants/libdq_$v.so run ab_$v 25 python tools/prof_rollout.py
 done
 for f in gpurun_out/${TAG}_ab_*.out; do echo "$f $(cut -c1-300 $f)"; done
