@@ -408,29 +408,34 @@ def run_b200(args):
 
     # ---- the same loop with the observations returned PACKED (one bit per cell, the rows the Q-network consumes):
     #      an extra line of evidence next to e2e, never a replacement for it; a failure here must not cost the bench line
-    e2e_packed = None
-    try:
+    e2e_packed, packed_err, packed_dt, packed_bytes = None, None, -1.0, 0
+    if world > 1:
+        dist.barrier()
+    try:                         # no collective inside: a failure on one rank must not leave the others waiting
         pk = env._packed_host_buffer()
+        packed_bytes = int(pk.numel() * 8 + n * (4 + 1 + 4 + 8 * env.mask_words))
 
         def host_step_packed(i):
             _lib.check(L.dq_env_step_host_packed(h, C.c_void_p(host_actions[i].data_ptr()), hp(pk), hp(hb["reward"]),
                                                  hp(hb["done"]), hp(hb["lifetime"]), hp(hb["legal"]), 1))
         for i in range(3):
             host_step_packed(i)
-        if world > 1:
-            dist.barrier()
         t0 = time.perf_counter()
         for i in range(3, ke + 3):
             host_step_packed(i)
-        dtp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
-        e2e_packed = {"value": world * n * ke / float(dtp.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                      "d2h_bytes_per_step": int(pk.numel() * 8 + n * (4 + 1 + 4 + 8 * env.mask_words)), "steps": ke,
+        packed_dt = time.perf_counter() - t0
+    except Exception as ex:      # noqa: BLE001 -- reported, not fatal
+        packed_err = "%s: %s" % (type(ex).__name__, ex)
+    dtp = torch.tensor([packed_dt, -packed_dt], dtype=torch.float64, device=dev)       # max over ranks of (dt, -dt): slowest, and any failure (-1)
+    if world > 1:
+        dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
+    if packed_err is None and float(dtp[1].item()) < 0:
+        e2e_packed = {"value": world * n * ke / float(dtp[0].item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": packed_bytes, "steps": ke,
                       "api": "dq_env_step_host_packed (observations as bit-packed rows uint64 [C*PW][stride]; "
                              "envs.unpack_observations expands them on the host when a caller needs bytes)"}
-    except Exception as ex:      # noqa: BLE001 -- reported, not fatal
-        e2e_packed = {"error": "%s: %s" % (type(ex).__name__, ex)}
+    else:
+        e2e_packed = {"error": packed_err or "failed on another rank"}
 
     # ---- DQN inner loop on the same lattices (extra evidence, not the headline metric):
     #   act:   Q(s) for every lattice from the packed rows in the env state -> eps-greedy pick -> env step (no byte boards)
