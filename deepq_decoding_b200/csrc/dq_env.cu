@@ -58,9 +58,19 @@ constexpr int kWarps = kThreads / 32;
 #ifndef DQ_BATCHB
 #define DQ_BATCHB 0              // 1: phase B in rounds of two stages: masks drawn warp per lattice, then applied / rendered lane per (lattice, slice)
 #endif                           // 2: volumes warp per lattice as in the default build, only their finalisation (state, bitmaps, stream) batched
+#ifndef DQ_DEFER
+#define DQ_DEFER 0               // 1: work that nothing on the step's dependent chain waits for leaves the chain: the frame / counters / action
+#endif                           //    boards of the tile are mirrored in shared memory (phase A reads no global state), and a re-rendered
+                                 //    lattice's span of the bit stream is refreshed by the threads that expand it (phase D), not by phase B
+#ifndef DQ_STREAM_OBS
+#define DQ_STREAM_OBS 0          // 1: observation bytes leave with evict-first stores (STG.E.EF.128): they are never read back by this
+#endif                           //    kernel, and a ring of them streaming through L2 otherwise evicts lines of the 4 MB joint referee
+                                 //    table (the v8 capture reads 150 KB of DRAM per step, and warp 0 waits ~1000 cycles per step on that lookup)
 constexpr bool kPrefetch = DQ_PREFETCH != 0;
 constexpr bool kBatchB = DQ_BATCHB != 0;
+constexpr bool kDefer = DQ_DEFER != 0;
 static_assert(!(kPrefetch && kBatchB), "DQ_PREFETCH and DQ_BATCHB both use the prepared-mask buffers");
+static_assert(!(kDefer && kBatchB), "DQ_DEFER restructures the default phase B");
 constexpr int kRefill = DQ_REFILL;
 constexpr u32 kNoAttempt = 0xffffffffu;              // attempt indices have 31 bits
 constexpr int kPickGroup = (kThreads - 32) / kEpc;   // rollout steps whose policy words warps 1.. draw in one go (thread = (step, lattice))
@@ -239,6 +249,10 @@ struct Smem {
     int ntask;
     int npending[2];                  // DQ_BATCHB: lattices that still need a volume attempt after a round (by round parity)
     u64 fsl[DQ_BATCHB == 2 ? kEpc : 1][kMaxVd];   // DQ_BATCHB=2: the slices of a finished volume, handed from its warp to the batched finalisation
+#if DQ_DEFER
+    u64 cx[kEpc], cz[kEpc], cmeta[kEpc], cact[3][kEpc];   // the tile's frame planes, counters and action boards (mirror of the state rows)
+    u32 dirty[2];                     // by step parity: lattices (bit = slot) whose span of `stream` is older than their bitmaps
+#endif
 };
 
 // 32 bits of the tile's observation bit stream starting at bit `o` of (lattice, layer): the stream is the concatenation of the
@@ -275,6 +289,32 @@ __device__ __forceinline__ uint4 expand16(const Smem& sm, u32 h) {     // low 16
     return make_uint4(a.x, a.y, b.x, b.y);
 }
 
+__device__ __forceinline__ void store_obs16(uint8_t* dst, const uint4 v) {
+#if DQ_STREAM_OBS
+    __stcs(reinterpret_cast<uint4*>(dst), v);
+#else
+    *reinterpret_cast<uint4*>(dst) = v;
+#endif
+}
+
+#if DQ_DEFER
+// DQ_DEFER: word `wi` of the bit stream as phase D needs it.  Phase B no longer refreshes the span of a lattice it re-rendered; it
+// sets the lattice's bit in the step's dirty mask `dm`, and the thread that expands a word overlapping such a lattice gathers
+// it from the bitmaps here and puts it back (every word has one owner per pass; the bitmaps are not written during phase D).
+template <int D>
+__device__ __forceinline__ u32 fresh_word(Smem& sm, const EnvParams& p, int wi, u32 dm, int C) {
+    if (dm) {
+        const u32 la = __umulhi((u32)(wi * 32), p.ob_magic), lb = min(__umulhi((u32)(wi * 32 + 31), p.ob_magic), (u32)(kEpc - 1));
+        if (((dm >> la) | (dm >> lb)) & 1u) {       // la <= lb < kEpc: the word's bits past the tile's last lattice are zero either way
+            const u32 v = stream_word<D>(sm, p, wi, C);
+            sm.stream[wi] = v;
+            return v;
+        }
+    }
+    return sm.stream[wi];
+}
+#endif
+
 // Legal-move mask words of one lattice (Environments.py:238-271 in closed form): qubits touching the summed faulty syndrome
 // or next to an already acted-on qubit, in every action layer, plus the identity.
 template <int D>
@@ -310,6 +350,7 @@ __device__ __noinline__ void write_observations_unaligned(const Smem& sm, uint8_
         }
     }
 }
+#if !DQ_DEFER
 __device__ __forceinline__ void write_observations(const Smem& sm, const EnvParams& p, uint8_t* obs, int env0, int nvalid,
                                                    int t, int nthr) {
     const int vbytes = nvalid * p.obs_bits;
@@ -320,8 +361,8 @@ __device__ __forceinline__ void write_observations(const Smem& sm, const EnvPara
 #pragma unroll 2
         for (int g = t * 32; g < full; g += nthr * 32) {
             const u32 word = sm.stream[g >> 5];
-            *reinterpret_cast<uint4*>(out + g) = expand16(sm, word);
-            *reinterpret_cast<uint4*>(out + g + 16) = expand16(sm, word >> 16);
+            store_obs16(out + g, expand16(sm, word));
+            store_obs16(out + g + 16, expand16(sm, word >> 16));
         }
     } else {
         write_observations_unaligned(sm, out, full, align, t, nthr);
@@ -331,6 +372,33 @@ __device__ __forceinline__ void write_observations(const Smem& sm, const EnvPara
         for (int b = 0; b < vbytes - full; ++b) out[full + b] = (uint8_t)((word >> b) & 1u);
     }
 }
+#else
+// DQ_DEFER form: the same expansion, every word read through fresh_word (dm = the dirty mask of the step being written)
+template <int D>
+__device__ __forceinline__ void write_observations(Smem& sm, const EnvParams& p, uint8_t* obs, int env0, int nvalid,
+                                                   int t, int nthr, u32 dm, int C) {
+    const int vbytes = nvalid * p.obs_bits;
+    uint8_t* out = obs + (size_t)env0 * p.obs_bits;
+    const int align = (int)(reinterpret_cast<uintptr_t>(out) & 15);
+    const int full = vbytes & ~31;                                                // whole 32-byte groups
+    if (align == 0) {
+#pragma unroll 2
+        for (int g = t * 32; g < full; g += nthr * 32) {
+            const u32 word = fresh_word<D>(sm, p, g >> 5, dm, C);
+            store_obs16(out + g, expand16(sm, word));
+            store_obs16(out + g + 16, expand16(sm, word >> 16));
+        }
+    } else {
+        if (dm)                                                                   // same word ownership as the copy loop below
+            for (int g = t * 32; g < full; g += nthr * 32) fresh_word<D>(sm, p, g >> 5, dm, C);
+        write_observations_unaligned(sm, out, full, align, t, nthr);
+    }
+    if (t == 0 && full < vbytes) {                                                 // the tile's last, partial group
+        const u32 word = fresh_word<D>(sm, p, full >> 5, dm, C);
+        for (int b = 0; b < vbytes - full; ++b) out[full + b] = (uint8_t)((word >> b) & 1u);
+    }
+}
+#endif
 
 template <int D, bool RESET>
 __global__ void __launch_bounds__(kThreads, DQ_MIN_BLOCKS)
@@ -371,6 +439,16 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         sm.sum[tid] = p.state[ROW_SUM * np + env0 + tid];
         sm.pre_att[tid] = kNoAttempt;
         if (kPrefetch) sm.att[tid] = (u32)(p.state[ROW_META * np + env0 + tid] >> 32) & 0x7FFFFFFFu;
+#if DQ_DEFER
+        if (!RESET) {
+            sm.cx[tid] = p.state[ROW_XB * np + env0 + tid];
+            sm.cz[tid] = p.state[ROW_ZB * np + env0 + tid];
+            sm.cmeta[tid] = p.state[ROW_META * np + env0 + tid];
+#pragma unroll
+            for (int l = 0; l < 3; ++l) sm.cact[l][tid] = l < p.layers ? p.state[(ROW_ACT + l) * np + env0 + tid] : 0ull;
+        }
+        if (tid < 2) sm.dirty[tid] = 0;
+#endif
     }
     // built-in policy: the random word of a pick depends only on (lattice, step index), so it never has to sit on the
     // step's dependent chain: the words of the first kPickGroup steps are drawn here, those of every later group by warps 1..
@@ -411,7 +489,11 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             if (s < ro.nsteps)
                 sm.pick_u[gbuf ^ 1][ahead][lat] = philox4x32_10(p.env_id_base + (u32)(env0 + lat), step0 + (u32)s, 0u, 1u, p.k0, p.k1).x;
         }
+#if !DQ_DEFER
         if (obs_prev) write_observations(sm, p, obs_prev, env0, nvalid, tid - 32, kThreads - 32);
+#else
+        if (obs_prev) write_observations<D>(sm, p, obs_prev, env0, nvalid, tid - 32, kThreads - 32, sm.dirty[(rs & 1) ^ 1], C);
+#endif
         if (kPrefetch && !RESET && ro.nsteps > 1) {
             // draw ahead: lattices whose prepared masks are not those of their next attempt (consumed, or never drawn).  This
             // window (warp 0 runs phase C and A) is separated from phase B, which reads them, by the block barriers.
@@ -430,14 +512,25 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         u64 xb = 0, zb = 0, meta = 0, act[3] = {0, 0, 0};
         u32 flags = 0;
         if (mine) {
+#if !DQ_DEFER
             meta = p.state[ROW_META * np + e];
+#else
+            meta = RESET ? p.state[ROW_META * np + e] : sm.cmeta[lane];
+#endif
             int actbit = -1;
             if (!RESET) {
                 int a = (live && actions) ? actions[e] : p.A - 1;
+#if !DQ_DEFER
                 xb = p.state[ROW_XB * np + e];
                 zb = p.state[ROW_ZB * np + e];
 #pragma unroll
                 for (int l = 0; l < 3; ++l) if (l < p.layers) act[l] = p.state[(ROW_ACT + l) * np + e];
+#else
+                xb = sm.cx[lane];
+                zb = sm.cz[lane];
+#pragma unroll
+                for (int l = 0; l < 3; ++l) act[l] = sm.cact[l][lane];
+#endif
                 if (policy_ctr && live) {
                     // built-in random-legal policy (dq_env_step_random): the pick dq_policy_random_legal would make
                     // on this lattice's current legal set, with the step index read from device memory
@@ -489,6 +582,10 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                     p.state[ROW_ZB * np + e] = zb;
                     p.state[ROW_META * np + e] = meta;
                     if (!ident) p.state[(ROW_ACT + layer) * np + e] = layer == 0 ? act[0] : (layer == 1 ? act[1] : act[2]);
+#if DQ_DEFER
+                    sm.cx[lane] = xb; sm.cz[lane] = zb; sm.cmeta[lane] = meta;
+                    sm.cact[0][lane] = act[0]; sm.cact[1][lane] = act[1]; sm.cact[2][lane] = act[2];
+#endif
                 }
             } else if (live) {
                 flags = 2u;               // reset keeps only the attempt counter (the position in the random stream)
@@ -506,6 +603,9 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     }
     __syncthreads();
 
+#if DQ_DEFER
+    if (tid == 0) sm.dirty[(rs & 1) ^ 1] = 0;  // the previous step's mask: phase D consumed it before the barrier above
+#endif
     if (tid < kEpc) {                          // a light step's action lights one more cell of its action layer
         const int ab = sm.actbit[tid];
         if (ab >= 0) {
@@ -552,6 +652,13 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                 sm.sum[slot] = summed; sm.acted[slot] = 0;
                 if (kPrefetch) sm.att[slot] = attempts;
                 if (!RESET) sm.life_out[slot] = lo;
+#if DQ_DEFER
+                if (!RESET) {
+                    sm.cx[slot] = bx; sm.cz[slot] = bz; sm.cmeta[slot] = meta_pack(life, attempts, dn);
+                    sm.cact[0][slot] = 0; sm.cact[1][slot] = 0; sm.cact[2][slot] = 0;
+                }
+                atomicOr(&sm.dirty[rs & 1], 1u << slot);
+#endif
             }
             if (lane < p.layers) p.state[(ROW_ACT + lane) * np + e] = 0;
             // render: lane j < vd holds slice j and builds that layer's bitmap in registers; lanes vd..C-1 clear the action layers
@@ -568,7 +675,8 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             __syncwarp();
             // this lattice's span of the tile's bit stream; its first and last word are shared with the neighbouring lattices, which
             // other warps may be re-rendering right now: only this lattice's bits of those are replaced, atomically
-            {
+            // (DQ_DEFER: left to phase D, see fresh_word)
+            if constexpr (!kDefer) {
                 const int b0 = slot * p.obs_bits, b1 = b0 + p.obs_bits;
                 for (int wi = (b0 >> 5) + lane; wi <= ((b1 - 1) >> 5); wi += 32) {
                     const int lo = max(b0 - wi * 32, 0), hi = min(b1 - wi * 32, 32);          // bits [lo, hi) of the word are this lattice's
@@ -797,7 +905,11 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     obs_prev = obs;
     if (++gphase == kPickGroup) { gphase = 0; gbuf ^= 1; }
     }   // rollout step
+#if !DQ_DEFER
     if (obs_prev) write_observations(sm, p, obs_prev, env0, nvalid, tid, kThreads);           // the last step's observations
+#else
+    if (obs_prev) write_observations<D>(sm, p, obs_prev, env0, nvalid, tid, kThreads, sm.dirty[(ro.nsteps - 1) & 1], C);
+#endif
     if (policy_ctr && tid == 0 && atomicAdd(policy_ctr + 1, 1u) == gridDim.x - 1) { policy_ctr[1] = 0; atomicAdd(policy_ctr, (u32)ro.nsteps); }
 }
 

@@ -23,7 +23,14 @@ ROW_XB, ROW_ZB, ROW_META, ROW_ACT, ROW_SUM, ROW_BM = 0, 1, 2, 3, 6, 7
 
 
 def build(extra_flags=(), out=OUT):
+    """DQ_EMU_FLAGS="-DDQ_DEFER=1 ..." in the environment points the DEFAULT emulated library (every test that does not name a
+    variant) at a tuning build, so the whole suite can be run against it before it is ever timed on a GPU."""
     import sys
+    env_flags = os.environ.get("DQ_EMU_FLAGS", "").split()
+    if env_flags and not extra_flags and out == OUT:
+        import hashlib
+        extra_flags = tuple(env_flags)
+        out = OUT[:-3] + "_" + hashlib.md5(" ".join(env_flags).encode()).hexdigest()[:8] + ".so"
     sys.path.insert(0, os.path.join(HERE, "host"))
     import emu_build
     return emu_build.build(out, [SRC], extra_flags=tuple(extra_flags))

@@ -258,6 +258,7 @@ static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t s) {
     return r;
 }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+template <typename T> static inline void __stcs(T* p, const T v) { *p = v; }      // cache hint only
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline long long min(long long a, long long b) { return a < b ? a : b; }

@@ -185,7 +185,11 @@ VARIANTS = [("prefetch", ["-DDQ_PREFETCH=1"]),
             ("batched_finalisation", ["-DDQ_BATCHB=2"]),
             ("batched_phase_b_tile32x256", ["-DDQ_BATCHB=1", "-DDQ_EPC=32", "-DDQ_THREADS=256"]),
             ("tile32x256", ["-DDQ_EPC=32", "-DDQ_THREADS=256"]),
-            ("tile8x64_prefetch", ["-DDQ_EPC=8", "-DDQ_THREADS=64", "-DDQ_PREFETCH=1"])]
+            ("tile8x64_prefetch", ["-DDQ_EPC=8", "-DDQ_THREADS=64", "-DDQ_PREFETCH=1"]),
+            ("deferred", ["-DDQ_DEFER=1"]),
+            ("deferred_prefetch_refill1", ["-DDQ_DEFER=1", "-DDQ_PREFETCH=1", "-DDQ_REFILL=1"]),
+            ("deferred_tile32x256", ["-DDQ_DEFER=1", "-DDQ_EPC=32", "-DDQ_THREADS=256"]),
+            ("deferred_streaming_stores", ["-DDQ_DEFER=1", "-DDQ_STREAM_OBS=1"])]
 
 
 @pytest.mark.parametrize("name,flags", VARIANTS, ids=[v[0] for v in VARIANTS])

@@ -18,6 +18,11 @@ variant() {   # name, extra flags
     rm -f $OUT/dq_env_$name.o
     echo "built $OUT/libdq_$name.so"
 }
+variant df         -DDQ_DEFER=1
+variant so         -DDQ_STREAM_OBS=1
+variant dfso       -DDQ_DEFER=1 -DDQ_STREAM_OBS=1
+variant dfsopf1    -DDQ_DEFER=1 -DDQ_STREAM_OBS=1 -DDQ_PREFETCH=1 -DDQ_REFILL=1
+variant bb2so      -DDQ_BATCHB=2 -DDQ_STREAM_OBS=1
 variant bb2        -DDQ_BATCHB=2
 variant bb         -DDQ_BATCHB=1
 variant bbmb8      -DDQ_BATCHB=1 -DDQ_MIN_BLOCKS=8

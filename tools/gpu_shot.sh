@@ -15,7 +15,7 @@ run pytest_env 90 python -m pytest tests/test_env_gpu.py -x -q
 tail -2 gpurun_out/${TAG}_pytest_env.out
 run ab_new 40 python tools/prof_rollout.py
 DQ_DECODING_LIB=build/variants/libdq_old.so run ab_old 40 python tools/prof_rollout.py
-for v in bb2 bb pf1 bbmb8 mb8 e32t256mb4; do
+for v in so df dfso dfsopf1 bb2 bb2so bb pf1 bbmb8 mb8; do
     DQ_ONLY_ROLLOUT=256 DQ_DECODING_LIB=build/variants/libdq_$v.so run ab_$v 25 python tools/prof_rollout.py
 done
 BEST=$(python - "$TAG" <<'PY'
@@ -45,7 +45,7 @@ unset DQ_DECODING_LIB
 [ "$BEST" != "new" ] && run bench_default 90 python bench.py --cpu-seconds 3 --no-dqn
 run pytest_rest 90 python -m pytest tests -m gpu -x -q --deselect tests/test_env_gpu.py
 run smoke 40 python __graft_entry__.py smoke
-for v in e16t96 bb2t96 pf2 e8t64mb14; do
+for v in e16t96 bb2t96 pf2 e8t64mb14 e32t256mb4; do
     DQ_ONLY_ROLLOUT=256 DQ_DECODING_LIB=build/variants/libdq_$v.so run ab_$v 25 python tools/prof_rollout.py
 done
 for f in gpurun_out/${TAG}_ab_*.out; do echo "$f $(cut -c1-300 $f)"; done
