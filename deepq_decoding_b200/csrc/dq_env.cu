@@ -62,6 +62,8 @@ constexpr int kWarps = kThreads / 32;
 #define DQ_DEFER 0               // 1: work that nothing on the step's dependent chain waits for leaves the chain: the frame / counters / action
 #endif                           //    boards of the tile are mirrored in shared memory (phase A reads no global state), and a re-rendered
                                  //    lattice's span of the bit stream is refreshed by the threads that expand it (phase D), not by phase B
+                                 // 2: ... and so do the layer bitmaps of a fresh volume: phase B leaves the slices in shared memory, the threads
+                                 //    of the next window render them (thread = (lattice, layer)) before they expand the stream
 #ifndef DQ_STREAM_OBS
 #define DQ_STREAM_OBS 0          // 1: observation bytes leave with evict-first stores (STG.E.EF.128): they are never read back by this
 #endif                           //    kernel, and a ring of them streaming through L2 otherwise evicts lines of the 4 MB joint referee
@@ -248,7 +250,7 @@ struct Smem {
     uint8_t task[kEpc], task_flags[kEpc];
     int ntask;
     int npending[2];                  // DQ_BATCHB: lattices that still need a volume attempt after a round (by round parity)
-    u64 fsl[DQ_BATCHB == 2 ? kEpc : 1][kMaxVd];   // DQ_BATCHB=2: the slices of a finished volume, handed from its warp to the batched finalisation
+    u64 fsl[(DQ_BATCHB == 2 || DQ_DEFER == 2) ? kEpc : 1][kMaxVd];   // DQ_BATCHB=2: the slices of a finished volume, handed from its warp to the batched finalisation
 #if DQ_DEFER
     u64 cx[kEpc], cz[kEpc], cmeta[kEpc], cact[3][kEpc];   // the tile's frame planes, counters and action boards (mirror of the state rows)
     u32 dirty[2];                     // by step parity: lattices (bit = slot) whose span of `stream` is older than their bitmaps
@@ -296,6 +298,41 @@ __device__ __forceinline__ void store_obs16(uint8_t* dst, const uint4 v) {
     *reinterpret_cast<uint4*>(dst) = v;
 #endif
 }
+
+#if DQ_DEFER == 2
+// Barrier over the `count` threads of the CTA that name barrier `id` (1..15; 0 is __syncthreads).
+__device__ __forceinline__ void named_barrier(int id, int count) {
+#ifdef DQ_EMU_DYNAMIC_SMEM
+    dq_emu::named_barrier(id, count);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+
+// DQ_DEFER=2: the layer bitmaps of the lattices in dirty mask `dm` (fresh volumes of the step being written), one (lattice, layer)
+// pair per thread: syndrome layers from the slices phase B left in fsl, action layers cleared.  Executed by threads
+// [0, nthr) of the caller's group; the caller synchronises the group before anyone reads the bitmaps.
+template <int D>
+__device__ __forceinline__ void render_dirty(Smem& sm, const EnvParams& p, u32 dm, int t, int nthr, int env0, int C) {
+    typedef Lat<D> L;
+    constexpr int PW = L::PW;
+    const size_t np = (size_t)p.npad;
+    const int items = __popc(dm) * C;
+    for (int i = t; i < items; i += nthr) {
+        const int k = i / C, c = i - k * C;
+        const int slot = select64((u64)dm, k);
+        const int e = env0 + slot;
+        u64 w[PW];
+        syndrome_layer_bitmap<D>(sm.fsl[slot][min(c, kMaxVd - 1)], w);
+#pragma unroll
+        for (int j = 0; j < PW; ++j) {
+            const u64 v = c < p.vd ? w[j] : 0ull;               // an action layer has no marker cells
+            sm.bm[slot][c * PW + j] = v;
+            p.state[(ROW_BM + c * PW + j) * np + e] = v;
+        }
+    }
+}
+#endif
 
 #if DQ_DEFER
 // DQ_DEFER: word `wi` of the bit stream as phase D needs it.  Phase B no longer refreshes the span of a lattice it re-rendered; it
@@ -492,7 +529,16 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
 #if !DQ_DEFER
         if (obs_prev) write_observations(sm, p, obs_prev, env0, nvalid, tid - 32, kThreads - 32);
 #else
-        if (obs_prev) write_observations<D>(sm, p, obs_prev, env0, nvalid, tid - 32, kThreads - 32, sm.dirty[(rs & 1) ^ 1], C);
+        {
+            const u32 dm = sm.dirty[(rs & 1) ^ 1];           // the previous step's fresh volumes (0 at the first step)
+#if DQ_DEFER == 2
+            if (dm) {               // block-uniform
+                render_dirty<D>(sm, p, dm, tid - 32, kThreads - 32, env0, C);
+                if (obs_prev) named_barrier(1, kThreads - 32);
+            }
+#endif
+            if (obs_prev) write_observations<D>(sm, p, obs_prev, env0, nvalid, tid - 32, kThreads - 32, dm, C);
+        }
 #endif
         if (kPrefetch && !RESET && ro.nsteps > 1) {
             // draw ahead: lattices whose prepared masks are not those of their next attempt (consumed, or never drawn).  This
@@ -660,9 +706,12 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                 atomicOr(&sm.dirty[rs & 1], 1u << slot);
 #endif
             }
-            if (lane < p.layers) p.state[(ROW_ACT + lane) * np + e] = 0;
+#if DQ_DEFER == 2
+            if (lane < kMaxVd) sm.fsl[slot][lane] = f;          // lanes >= vd hold 0; rendered in the next window (render_dirty)
+#endif
+            if (lane < p.layers) p.state[(ROW_ACT + lane) * np + e] = 0;     // not deferred: phase A of the next step may write this row
             // render: lane j < vd holds slice j and builds that layer's bitmap in registers; lanes vd..C-1 clear the action layers
-            if (lane < C) {
+            if (DQ_DEFER != 2 && lane < C) {
                 u64 w[PW];
                 syndrome_layer_bitmap<D>(f, w);
 #pragma unroll
@@ -908,7 +957,14 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
 #if !DQ_DEFER
     if (obs_prev) write_observations(sm, p, obs_prev, env0, nvalid, tid, kThreads);           // the last step's observations
 #else
-    if (obs_prev) write_observations<D>(sm, p, obs_prev, env0, nvalid, tid, kThreads, sm.dirty[(ro.nsteps - 1) & 1], C);
+    {
+        const u32 dm = sm.dirty[(ro.nsteps - 1) & 1];
+#if DQ_DEFER == 2
+        render_dirty<D>(sm, p, dm, tid, kThreads, env0, C);        // the last phase B lies behind barrier 2
+        if (obs_prev) __syncthreads();                             // block-uniform
+#endif
+        if (obs_prev) write_observations<D>(sm, p, obs_prev, env0, nvalid, tid, kThreads, dm, C);
+    }
 #endif
     if (policy_ctr && tid == 0 && atomicAdd(policy_ctr + 1, 1u) == gridDim.x - 1) { policy_ctr[1] = 0; atomicAdd(policy_ctr, (u32)ro.nsteps); }
 }

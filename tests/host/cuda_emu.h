@@ -70,6 +70,7 @@ struct Cta {
     ucontext_t sched;
     int nthreads, ndone, cur;
     int bar_count, bar_gen;
+    int nbar_count[16], nbar_gen[16];      // named barriers (bar.sync id, count)
     long progress;
     dim3 bid, bdim, gdim;
     unsigned char* smem;
@@ -125,6 +126,15 @@ inline void block_barrier() {
     }
 }
 
+// bar.sync id, count: the barrier completes when `count` threads have arrived
+inline void named_barrier(int id, int count) {
+    Cta& c = *cta();
+    if (id < 1 || id > 15 || count % 32) { fprintf(stderr, "dq_emu: bad named barrier (%d, %d)\n", id, count); abort(); }
+    const int gen = c.nbar_gen[id];
+    if (++c.nbar_count[id] >= count) { c.nbar_count[id] = 0; c.nbar_gen[id]++; c.progress++; return; }
+    while (c.nbar_gen[id] == gen) yield();
+}
+
 inline int sched_mode() { static int m = -1; if (m < 0) { const char* e = getenv("DQ_EMU_SCHED"); m = e ? atoi(e) : 0; } return m; }
 inline unsigned sched_rand() { static unsigned s = 0; if (!s) s = 2654435761u * (unsigned)(sched_mode() + 1); s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; }
 
@@ -144,6 +154,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
     for (unsigned bz = 0; bz < grid.z; ++bz) for (unsigned by = 0; by < grid.y; ++by) for (unsigned bx = 0; bx < grid.x; ++bx) {
         c->bid = dim3(bx, by, bz);
         c->nthreads = nthreads; c->ndone = 0; c->bar_count = 0; c->bar_gen = 0; c->progress = 0;
+        memset(c->nbar_count, 0, sizeof(c->nbar_count)); memset(c->nbar_gen, 0, sizeof(c->nbar_gen));
         memset(c->warps, 0, sizeof(c->warps));
         memset(c->smem, 0xA5, smem_bytes);           // shared memory starts undefined on the GPU: poison it
         for (int i = 0; i < nthreads; ++i) {
