@@ -178,9 +178,10 @@ def test_fused_random_policy_step_equals_policy_then_step():
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("d,model,n", [(5, "DP", 1000), (3, "X", 37), (7, "DP", 200)])
+@pytest.mark.parametrize("d,model,n", [(5, "DP", 1000), (3, "X", 37), (7, "DP", 200), (5, "DP", 16384), (7, "DP", 8192)])
 def test_rollout_equals_single_steps_and_oracle(d, model, n):
-    """dq_env_rollout_random(n_steps) == n_steps x dq_env_step_random == the oracle stepping the same policy stream."""
+    """dq_env_rollout_random(n_steps) == n_steps x dq_env_step_random == the oracle stepping the same policy stream.
+    The last two cases are the full per-GPU lattice counts of BASELINE configs C3 and C5, bit for bit against the oracle."""
     import ctypes as C
     import torch
     from deepq_decoding_b200 import _lib
