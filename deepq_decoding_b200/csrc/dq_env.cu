@@ -107,7 +107,20 @@ struct EnvParams {
     u64* state;                                 // [STATE_WORDS][npad]
 };
 
+#ifndef DQ_LUT_KEEP
+#define DQ_LUT_KEEP 0            // 1: referee-table loads carry an L2 evict-last policy (the table competes with the observation stream for L2)
+#endif
+#if DQ_LUT_KEEP && !defined(DQ_EMU_DYNAMIC_SMEM)
+__device__ __forceinline__ int lut2(const uint8_t* lut, u32 idx) {
+    u64 pol;
+    u32 v;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(lut + (idx >> 2)), "l"(pol));
+    return (int)((v >> ((idx & 3) * 2)) & 3u);
+}
+#else
 __device__ __forceinline__ int lut2(const uint8_t* lut, u32 idx) { return (__ldg(lut + (idx >> 2)) >> ((idx & 3) * 2)) & 3; }
+#endif
 
 template <int D>
 __device__ __forceinline__ int referee_class(const EnvParams& p, u64 syn) {

@@ -23,6 +23,8 @@ variant so         -DDQ_STREAM_OBS=1
 variant dfso       -DDQ_DEFER=1 -DDQ_STREAM_OBS=1
 variant df2        -DDQ_DEFER=2
 variant df2so      -DDQ_DEFER=2 -DDQ_STREAM_OBS=1
+variant df2solk    -DDQ_DEFER=2 -DDQ_STREAM_OBS=1 -DDQ_LUT_KEEP=1
+variant lk         -DDQ_LUT_KEEP=1
 variant df2sopf1   -DDQ_DEFER=2 -DDQ_STREAM_OBS=1 -DDQ_PREFETCH=1 -DDQ_REFILL=1
 variant dfsopf1    -DDQ_DEFER=1 -DDQ_STREAM_OBS=1 -DDQ_PREFETCH=1 -DDQ_REFILL=1
 variant bb2so      -DDQ_BATCHB=2 -DDQ_STREAM_OBS=1
