@@ -16,7 +16,7 @@ tail -2 gpurun_out/${TAG}_pytest_env.out
 run ab_new 40 python tools/prof_rollout.py
 DQ_DECODING_LIB=build/variants/libdq_old.so run ab_old 40 python tools/prof_rollout.py
 for v in so lk df dfso df2 df2so df2solk df2sopf1 dfsopf1 bb2 bb2so bb pf1 mb8; do
-    DQ_ONLY_ROLLOUT=256 DQ_DECODING_LIB=build/variants/libdq_$v.so run ab_$v 25 python tools/prof_rollout.py
+    DQ_CALLS=12 DQ_ONLY_ROLLOUT=256 DQ_DECODING_LIB=build/variants/libdq_$v.so run ab_$v 25 python tools/prof_rollout.py
 done
 BEST=$(python - "$TAG" <<'PY'
 import glob, json, sys
@@ -38,6 +38,7 @@ if [ "$BEST" != "new" ]; then
     run pytest_env_best 60 python -m pytest tests/test_env_gpu.py -x -q
     tail -2 gpurun_out/${TAG}_pytest_env_best.out
 fi
+DQ_CALLS=6 DQ_ONLY_ROLLOUT=64 DQ_N=262144 run big_best 40 python tools/prof_rollout.py      # the same build with every SM fully loaded
 run bench_best 90 python bench.py --cpu-seconds 3 --no-dqn
 run ncu_list 60 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_launches_rollout.csv python bench.py --steps 1024 --warmup 16 --cpu-seconds 0.2 --no-dqn
 DQ_ONLY_ROLLOUT=64 run ncu_full 60 ncu --set full --clock-control none --import-source on -k regex:env_step_kernel -s 4 -c 1 -f -o gpurun_out/${TAG}_rollout64 python tools/prof_rollout.py

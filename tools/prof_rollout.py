@@ -53,7 +53,7 @@ for S in ((ONLY,) if ONLY else (4, 16, 64, 256)):
     def roll(i, S=S):
         _lib.check(L.dq_env_rollout_random(env._h, S, p(ring), SLOTS, (i * S) % SLOTS, p(rew), p(done), p(life), p(legal), p(acts), 1, st))
 
-    us = timed(roll, S, 2 if ONLY else max(4, 1024 // S))
+    us = timed(roll, S, int(os.environ.get("DQ_CALLS", "2")) if ONLY else max(4, 1024 // S))     # DQ_CALLS: A/B runs time more launches than an ncu capture needs
     res["rollout_%d_us_per_step" % S] = us
     res["rollout_%d_env_steps_per_s" % S] = N / us * 1e6
 print(json.dumps(res))
