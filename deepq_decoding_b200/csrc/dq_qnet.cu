@@ -854,6 +854,43 @@ extern "C" int dq_replay_sample(const uint64_t* ring_obs, const int32_t* ring_ac
     return DQ_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ folded head (acting)
+// The layers after the last hidden dense layer are all linear: Dense(K -> A) (Function_Library.py:338-377), keras-rl's dueling
+// Dense(A -> A+1) and the 'avg' combine Q_a = y_0 + y_{a+1} - mean_a' y_{a'+1}.  For inference they are ONE affine map
+// Q = h * Wf + bf.  Thread r < K builds row r of Wf [K][A]; thread r == K builds bf.
+namespace dq {
+__global__ void fold_head_kernel(const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ W3,
+                                 const float* __restrict__ b3, int K, int A, float* __restrict__ Wf, float* __restrict__ bf) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > K) return;
+    const float* x = r < K ? W2 + (size_t)r * A : b2;          // the row of Dense(K -> A) this thread pushes through the head
+    float* out = r < K ? Wf + (size_t)r * A : bf;
+    float y0 = r < K ? 0.f : b3[0], mean = 0.f;
+    for (int m = 0; m < A; ++m) y0 += x[m] * W3[(size_t)m * (A + 1)];
+    for (int a = 0; a < A; ++a) {
+        float y = r < K ? 0.f : b3[1 + a];
+        for (int m = 0; m < A; ++m) y += x[m] * W3[(size_t)m * (A + 1) + 1 + a];
+        out[a] = y;
+        mean += y;
+    }
+    mean /= (float)A;
+    for (int a = 0; a < A; ++a) out[a] = y0 + out[a] - mean;
+}
+}  // namespace dq
+
+extern "C" int dq_qnet_fold_head(const dq_qnet* h, const float* params, float* w_out, float* b_out, dq_stream stream) {
+    if (!h || !params || !w_out || !b_out) return qfail(DQ_EINVAL, "NULL argument");
+    const QCfg& c = h->c;
+    if (!c.dueling || c.n_fc < 2) return qfail(DQ_EINVAL, "the network has no dueling head to fold");
+    const int i2 = c.n_fc - 2, i3 = c.n_fc - 1, t2 = c.n_conv + i2, t3 = c.n_conv + i3, K = c.fc_in[i2];
+    if (c.fc_out[i2] != c.A || c.fc_in[i3] != c.A || c.fc_out[i3] != c.A + 1) return qfail(DQ_EINVAL, "unexpected head shape");
+    fold_head_kernel<<<(unsigned)((K + 1 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(params + c.w_off[t2], params + c.b_off[t2], params + c.w_off[t3],
+                                                                                      params + c.b_off[t3], K, c.A, w_out, b_out);
+    count_launch();
+    QCUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
 // ================================================================================================
 // bf16 tensor-core inference path (acting): tcgen05.mma with TMEM accumulators.
 //
@@ -1356,11 +1393,19 @@ struct dq_qnet_tc {                     // bf16 buffers of the tensor-core path,
     __nv_bfloat16* act[kMaxConv + kMaxDense + 2];      // act[j] = bf16 output of layer j (not for the last one)
     __nv_bfloat16* wt[kMaxConv + kMaxDense + 2];
     int kpad[kMaxConv + kMaxDense + 2], npad[kMaxConv + kMaxDense + 2], bn[kMaxConv + kMaxDense + 2];
+    // DQ_QNET_FOLD_HEAD=1 (opt-in): Dense(num_actions) + dueling head folded into one affine map (dq_qnet_fold_head); the last
+    // tensor-core layer then multiplies with fold_wt / fold_b and writes Q itself
+    float* fold_w; float* fold_b; __nv_bfloat16* fold_wt; int folded;
 };
+static bool tc_fold_enabled() {
+    static const bool on = [] { const char* e = getenv("DQ_QNET_FOLD_HEAD"); return e && e[0] == '1'; }();
+    return on;
+}
 static void tc_free(dq_qnet* h) {
     dq_qnet_tc* tc = (dq_qnet_tc*)h->tc;
     if (!tc) return;
     for (int i = 0; i < kMaxConv + kMaxDense + 2; ++i) { cudaFree(tc->act[i]); cudaFree(tc->wt[i]); }
+    cudaFree(tc->fold_w); cudaFree(tc->fold_b); cudaFree(tc->fold_wt);
     delete tc;
     h->tc = nullptr;
 }
@@ -1385,6 +1430,13 @@ static dq_qnet_tc* tc_of(dq_qnet* h) {
         tc->npad[j] = (N + tc->bn[j] - 1) / tc->bn[j] * tc->bn[j];
         err = cudaMalloc(&tc->wt[j], (size_t)tc->npad[j] * tc->kpad[j] * sizeof(__nv_bfloat16));
         if (err == cudaSuccess && j + 1 < n_tc) err = cudaMalloc(&tc->act[j], (size_t)h->max_batch * rows * N * sizeof(__nv_bfloat16));
+    }
+    if (err == cudaSuccess && tc_fold_enabled() && c.dueling && c.n_fc >= 2) {
+        const int j = n_tc - 1, K = c.fc_in[c.n_fc - 2];
+        err = cudaMalloc(&tc->fold_w, (size_t)K * c.A * sizeof(float));
+        if (err == cudaSuccess) err = cudaMalloc(&tc->fold_b, (size_t)c.A * sizeof(float));
+        if (err == cudaSuccess) err = cudaMalloc(&tc->fold_wt, (size_t)tc->npad[j] * tc->kpad[j] * sizeof(__nv_bfloat16));
+        tc->folded = err == cudaSuccess;
     }
     cudaSetDevice(prev);
     h->tc = tc;
@@ -1459,6 +1511,16 @@ extern "C" int dq_qnet_prepare_tc(dq_qnet* h, const float* params, dq_stream str
         prep_wt_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params + c.w_off[j], tc->wt[j], K, N, tc->kpad[j], tc->npad[j], j == 0 ? c.C : 0);
         count_launch();
     }
+    if (tc->folded) {
+        const int j = tc_layers(c) - 1;
+        int K, N; long long rows;
+        tc_shape(c, j, K, N, rows);
+        rc = dq_qnet_fold_head(h, params, tc->fold_w, tc->fold_b, stream);
+        if (rc) return rc;
+        const int total = tc->npad[j] * tc->kpad[j];
+        prep_wt_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tc->fold_w, tc->fold_wt, K, N, tc->kpad[j], tc->npad[j], 0);
+        count_launch();
+    }
     QCUDA(cudaGetLastError());
     return DQ_OK;
 }
@@ -1483,6 +1545,7 @@ extern "C" int dq_qnet_forward_tc(dq_qnet* h, const float* params, const uint64_
         else { const int i = j - c.n_conv; a.g = dense_patch(c.fc_in[i]); a.M = batch; a.N = c.fc_out[i]; a.K = c.fc_in[i]; }
         a.relu = last ? 0 : 1; a.out_bf16 = last ? 0 : 1; a.ldy = a.N;
         a.Y = last ? (void*)h->act_fc[c.n_hidden] : (void*)tc->act[j];
+        if (last && tc->folded) { a.Wt = tc->fold_wt; a.bias = tc->fold_b; a.Y = q_out; }      // N = num_actions: the rows are Q itself
         int rc;
         if (j == 0) {
             a.packed = (const u64*)packed; a.pstride = stride; a.C = c.C; a.PW = c.PW; a.H = c.H; a.T = c.conv[0].ksz * c.conv[0].ksz;
@@ -1493,6 +1556,7 @@ extern "C" int dq_qnet_forward_tc(dq_qnet* h, const float* params, const uint64_
         }
         if (rc) return rc;
     }
+    if (tc->folded) { h->last_train = 0; QCUDA(cudaGetLastError()); return DQ_OK; }
     // dueling head (tiny) in fp32 on the SIMT path
     const float* xf = h->act_fc[c.n_hidden];
     if (c.dueling) {

@@ -35,6 +35,7 @@ def lib():
         L.dq_qnet_pack_obs.argtypes = [vp, vp, vp, i64, i64, vp]
         L.dq_qnet_forward.argtypes = [vp, vp, vp, i64, i64, vp, i, u64, vp]
         L.dq_qnet_backward.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp]
+        L.dq_qnet_fold_head.argtypes = [vp, vp, vp, vp, vp]
         L.dq_qnet_activation.argtypes = [vp, i, C.POINTER(vp), C.POINTER(i64)]
         L.dq_adam_step.argtypes = [vp, vp, vp, vp, i64, f, f, f, f, i64, f, vp]
         L.dq_dqn_targets.argtypes = [vp, vp, vp, vp, f, i64, i, vp, vp]
@@ -136,6 +137,13 @@ class EmuQNet:
         q = np.zeros((b, self.A), np.float32)
         check(self.L.dq_qnet_forward(self.h, _p(self.params), _p(packed), b, b, _p(q), int(train), dropout_seed, None))
         return q, packed
+
+    def fold_head(self):
+        """(w [K][A], b [A]) with Q = h @ w + b for the output h of the last hidden dense layer (dq_qnet_fold_head)."""
+        K = self.layout[-2][2]
+        w, b = np.zeros((K, self.A), np.float32), np.zeros(self.A, np.float32)
+        check(self.L.dq_qnet_fold_head(self.h, _p(self.params), _p(w), _p(b), None))
+        return w, b
 
     def backward(self, packed, dq):
         b = packed.shape[1]

@@ -149,3 +149,21 @@ def test_emulated_replay_sample_gathers_consecutive_slots():
         ts, i = picked[b]
         assert np.array_equal(s0[:, b], obs[ts, :, i]) and np.array_equal(s1[:, b], obs[(ts + 1) % cap, :, i])
         assert a[b] == act[ts, i] and r[b] == rew[ts, i] and t[b] == term[ts, i]
+
+
+@pytest.mark.parametrize("which,A", [("dp", 51), ("x", 26)])
+def test_emulated_folded_head_is_the_networks_head(which, A):
+    """dq_qnet_fold_head: Dense(A) -> dueling Dense(A+1) -> 'avg' combine as one affine map, on the reference's published
+    weights: h @ w + b reproduces the head applied to a hidden activation h (float64 restatement)."""
+    conv, dense = golden_weights(which)
+    C_in = 7 if which == "dp" else 6
+    q = EQ.EmuQNet(REF_CC, [[512, 0.2]], (C_in, 11, 11), A, max_batch=64)
+    q.set_keras_weights(conv, dense)
+    w, b = q.fold_head()
+    (w2, b2), (w3, b3) = dense[-2], dense[-1]
+    rng = np.random.default_rng(3)
+    h = np.maximum(rng.standard_normal((64, w2.shape[0])), 0).astype(np.float64)
+    y = (h @ w2.astype(np.float64) + b2) @ w3.astype(np.float64) + b3
+    want = y[:, :1] + y[:, 1:] - y[:, 1:].mean(axis=1, keepdims=True)
+    got = h @ w.astype(np.float64) + b
+    assert np.abs(got - want).max() < 1e-4 * max(1.0, np.abs(want).max())
