@@ -405,6 +405,14 @@ def run_b200(args):
     e2e_value = world * n * ke / float(dt.item())
     h2d = n * 4
     d2h = n * (env.obs[0].numel() + 4 + 1 + 4 + 8 * env.mask_words)
+    host_expand = False
+    try:                         # DQ_HOST_EXPAND=1 (opt-in): same call, observations cross PCIe bit-packed and are expanded by host threads
+        he = C.c_int64(0)
+        if L.dq_env_info(h, 10, C.byref(he)) == 0 and he.value == 1:
+            host_expand = True
+            d2h = int((env.state_words - 7) * env.state_stride * 8 + n * (4 + 1 + 4 + 8 * env.mask_words))
+    except Exception:            # noqa: BLE001
+        pass
 
     # ---- the same loop with the observations returned PACKED (one bit per cell, the rows the Q-network consumes):
     #      an extra line of evidence next to e2e, never a replacement for it; a failure here must not cost the bench line
@@ -541,6 +549,7 @@ def run_b200(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": ke, "api": "dq_env_step_host (pinned host actions in, all outputs to pinned host buffers)",
+                        "host_expand": host_expand,
                         "policy": "uniform random action indices pre-generated on the host"},
                 "e2e_packed": e2e_packed,
                 "gpu_launches": timed_launches, "single_step_launches": single,

@@ -29,8 +29,15 @@
 #include <stdint.h>
 #include <string.h>
 #include <math.h>
+#include <stdlib.h>
+#include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/dq_decoding.h"
 #include "dq_lattice.cuh"
@@ -1029,6 +1036,7 @@ struct dq_env {
     cudaStream_t hstream;
     u32* policy_ctr;             // {step index, finished-CTA count} for dq_policy_random_legal_next
     int32_t* s_actions; uint8_t* s_obs; float* s_reward; uint8_t* s_done; int32_t* s_life; u64* s_legal;
+    u64* h_packed;               // DQ_HOST_EXPAND: pinned landing buffer of the bit-packed observation rows
 };
 
 static std::atomic<long long> g_launches{0};
@@ -1038,6 +1046,7 @@ void count_launch() { g_launches.fetch_add(1); }
 }
 
 static int fail(int code, const std::string& msg) { dq::g_err_q = msg; return code; }
+static bool host_expand_enabled();
 #define DQ_CUDA(expr)                                                                       \
     do {                                                                                    \
         cudaError_t _e = (expr);                                                            \
@@ -1122,6 +1131,7 @@ extern "C" int dq_env_destroy(dq_env* e) {
     if (e->hstream) {
         cudaStreamSynchronize(e->hstream);
         cudaFree(e->s_actions); cudaFree(e->s_obs); cudaFree(e->s_reward); cudaFree(e->s_done); cudaFree(e->s_life); cudaFree(e->s_legal);
+        if (e->h_packed) cudaFreeHost(e->h_packed);
         cudaStreamDestroy(e->hstream);
     }
     cudaFree(e->p.state);
@@ -1144,6 +1154,7 @@ extern "C" int dq_env_info(const dq_env* e, int what, int64_t* out) {
         case DQ_INFO_N_TYPE3: *out = (p.d * p.d - 1) / 2; break;
         case DQ_INFO_N_TYPE1: *out = (p.d * p.d - 1) / 2; break;
         case DQ_INFO_RNG_BLOCKS: *out = 32 * p.rounds; break;
+        case DQ_INFO_HOST_EXPAND: *out = host_expand_enabled() ? 1 : 0; break;
         default: return fail(DQ_EINVAL, "unknown info selector");
     }
     return DQ_OK;
@@ -1238,6 +1249,101 @@ static int ensure_staging(dq_env* e) {
     return DQ_OK;
 }
 
+// ---- DQ_HOST_EXPAND=1 (opt-in, read once per process): the *_host entry points keep their interface (byte observations in the
+// caller's host buffer) but move the observations over PCIe as the bit-packed rows of the state matrix (7.5x fewer bytes, the
+// kernel's byte-expanding phase skipped) and expand them here, on a small pool of host threads.
+static bool host_expand_enabled() {
+    static const bool on = [] { const char* v = getenv("DQ_HOST_EXPAND"); return v && v[0] == '1'; }();
+    return on;
+}
+
+namespace {
+struct HostPool {                 // persistent workers: blocks of a job are claimed from an atomic counter
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv_job, cv_done;
+    const std::function<void(int)>* job = nullptr;
+    int nblocks = 0, generation = 0, active = 0;
+    std::atomic<int> next{0};
+    explicit HostPool(int n) {
+        for (int i = 0; i < n; ++i) th.emplace_back([this] { run(); });
+        for (auto& t : th) t.detach();            // the pool lives as long as the process
+    }
+    void run() {
+        int seen = 0;
+        for (;;) {
+            const std::function<void(int)>* f;
+            int nb;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv_job.wait(lk, [&] { return generation != seen; });
+                seen = generation; f = job; nb = nblocks;
+            }
+            for (int b; (b = next.fetch_add(1)) < nb;) (*f)(b);
+            {
+                std::lock_guard<std::mutex> lk(m);
+                if (--active == 0) cv_done.notify_one();
+            }
+        }
+    }
+    void parallel_for(int nb, const std::function<void(int)>& f) {      // the caller works too
+        {
+            std::lock_guard<std::mutex> lk(m);
+            job = &f; nblocks = nb; next.store(0); active = (int)th.size(); ++generation;
+        }
+        cv_job.notify_all();
+        for (int b; (b = next.fetch_add(1)) < nb;) f(b);
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return active == 0; });
+    }
+};
+
+HostPool& host_pool() {
+    static HostPool* pool = [] {
+        int n = (int)std::thread::hardware_concurrency();
+        if (const char* v = getenv("DQ_HOST_THREADS")) n = atoi(v);
+        return new HostPool(std::max(0, std::min(n, 32) - 1));
+    }();
+    return *pool;
+}
+
+// byte -> its 8 bits as 8 bytes of 0/1 (little-endian: bit 0 first)
+const u64* byte_lut() {
+    static const u64* t = [] {
+        u64* x = new u64[256];
+        for (int i = 0; i < 256; ++i) { u64 v = 0; for (int b = 0; b < 8; ++b) v |= (u64)((i >> b) & 1) << (8 * b); x[i] = v; }
+        return x;
+    }();
+    return t;
+}
+}  // namespace
+
+// packed rows [C*PW][npad] (bit i of layer c of lattice e = bit i%64 of row c*PW + i/64, column e) -> obs [n][C][P] bytes of 0/1
+static void expand_packed_host(const u64* packed, size_t npad, int n, int C, int PW, int P, uint8_t* obs) {
+    const u64* lut = byte_lut();
+    const int per = 256, nb = (n + per - 1) / per;
+    const std::function<void(int)> block = [&](int b) {
+        const int e1 = std::min(n, (b + 1) * per);
+        for (int e = b * per; e < e1; ++e) {
+            uint8_t* out = obs + (size_t)e * C * P;
+            for (int c = 0; c < C; ++c, out += P)
+                for (int w = 0; w < PW; ++w) {
+                    u64 v = packed[(size_t)(c * PW + w) * npad + e];
+                    const int bits = std::min(64, P - 64 * w);
+                    uint8_t* o = out + 64 * w;
+                    int i = 0;
+                    for (; i + 8 <= bits; i += 8, v >>= 8) memcpy(o + i, &lut[v & 0xFF], 8);
+                    for (; i < bits; ++i, v >>= 1) o[i] = (uint8_t)(v & 1);
+                }
+        }
+    };
+    host_pool().parallel_for(nb, block);
+}
+
+static int copy_packed(dq_env* e, uint64_t* h_packed);
+// the tail of a *_host call under DQ_HOST_EXPAND: packed rows to the pinned landing buffer, the small outputs, one synchronise, expand
+static int copy_out_expanding(dq_env* e, uint8_t* h_obs, float* h_reward, uint8_t* h_done, int32_t* h_life, uint64_t* h_legal);
+
 static int copy_out(dq_env* e, uint8_t* h_obs, float* h_reward, uint8_t* h_done, int32_t* h_life, uint64_t* h_legal) {
     const EnvParams& p = e->p;
     cudaStream_t s = e->hstream;
@@ -1255,8 +1361,10 @@ extern "C" int dq_env_reset_host(dq_env* e, uint8_t* h_obs, uint64_t* h_legal) {
     DeviceGuard g(e->device);
     int rc = ensure_staging(e);
     if (rc) return rc;
-    rc = launch_env<true>(e, nullptr, h_obs ? e->s_obs : nullptr, nullptr, nullptr, nullptr, h_legal ? e->s_legal : nullptr, 1, e->hstream);
+    const bool expand = h_obs && host_expand_enabled();
+    rc = launch_env<true>(e, nullptr, (h_obs && !expand) ? e->s_obs : nullptr, nullptr, nullptr, nullptr, h_legal ? e->s_legal : nullptr, 1, e->hstream);
     if (rc) return rc;
+    if (expand) return copy_out_expanding(e, h_obs, nullptr, nullptr, nullptr, h_legal);
     return copy_out(e, h_obs, nullptr, nullptr, nullptr, h_legal);
 }
 
@@ -1268,10 +1376,12 @@ extern "C" int dq_env_step_host(dq_env* e, const int32_t* h_actions, uint8_t* h_
     int rc = ensure_staging(e);
     if (rc) return rc;
     DQ_CUDA(cudaMemcpyAsync(e->s_actions, h_actions, (size_t)e->p.n * 4, cudaMemcpyHostToDevice, e->hstream));
-    rc = launch_env<false>(e, e->s_actions, h_obs ? e->s_obs : nullptr, h_reward ? e->s_reward : nullptr,
+    const bool expand = h_obs && host_expand_enabled();
+    rc = launch_env<false>(e, e->s_actions, (h_obs && !expand) ? e->s_obs : nullptr, h_reward ? e->s_reward : nullptr,
                            h_done ? e->s_done : nullptr, h_life ? e->s_life : nullptr, h_legal ? e->s_legal : nullptr,
                            auto_reset, e->hstream);
     if (rc) return rc;
+    if (expand) return copy_out_expanding(e, h_obs, h_reward, h_done, h_life, h_legal);
     return copy_out(e, h_obs, h_reward, h_done, h_life, h_legal);
 }
 
@@ -1282,6 +1392,19 @@ static int copy_packed(dq_env* e, uint64_t* h_packed) {
     if (!h_packed) return DQ_OK;
     const size_t words = (size_t)(e->state_rows - ROW_BM) * e->p.npad;
     DQ_CUDA(cudaMemcpyAsync(h_packed, e->p.state + (size_t)ROW_BM * e->p.npad, words * sizeof(u64), cudaMemcpyDeviceToHost, e->hstream));
+    return DQ_OK;
+}
+
+static int copy_out_expanding(dq_env* e, uint8_t* h_obs, float* h_reward, uint8_t* h_done, int32_t* h_life, uint64_t* h_legal) {
+    const EnvParams& p = e->p;
+    const size_t words = (size_t)(e->state_rows - ROW_BM) * p.npad;
+    if (!e->h_packed) DQ_CUDA(cudaMallocHost(&e->h_packed, words * sizeof(u64)));
+    int rc = copy_packed(e, e->h_packed);
+    if (rc) return rc;
+    rc = copy_out(e, nullptr, h_reward, h_done, h_life, h_legal);          // synchronises the stream
+    if (rc) return rc;
+    const int side = 2 * p.d + 1, P = side * side;
+    expand_packed_host(e->h_packed, (size_t)p.npad, p.n, p.vd + p.layers, (P + 63) / 64, P, h_obs);
     return DQ_OK;
 }
 

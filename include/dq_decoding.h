@@ -60,6 +60,7 @@ extern "C" {
 #define DQ_INFO_N_TYPE3       7
 #define DQ_INFO_N_TYPE1       8
 #define DQ_INFO_RNG_BLOCKS    9   /* Philox blocks per volume attempt (B of the RNG contract) */
+#define DQ_INFO_HOST_EXPAND  10   /* 1 if the *_host calls move observations bit-packed and expand them on the host (DQ_HOST_EXPAND=1) */
 
 typedef struct dq_env dq_env;
 typedef void* dq_stream;

@@ -165,6 +165,12 @@ class EmuVecEnv:
         self._check(self.L.dq_env_step_host_packed(self.h, _p(actions), _p(packed), _p(reward), _p(done), _p(life), _p(legal), int(auto_reset)))
         return packed, reward, done, life, legal
 
+    def reset_host(self):
+        obs = np.zeros((self.n, self.Cn, self.H, self.H), np.uint8)
+        legal = np.zeros((self.n, self.W), np.uint64)
+        self._check(self.L.dq_env_reset_host(self.h, _p(obs), _p(legal)))
+        return obs, legal
+
     def reset_host_packed(self):
         packed = np.zeros((self.state_rows - ROW_BM, self.stride), np.uint64)
         legal = np.zeros((self.n, self.W), np.uint64)

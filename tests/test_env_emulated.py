@@ -151,6 +151,34 @@ def test_emulated_host_entry_points_and_unaligned_observation_buffers():
         olegal = want[4]
 
 
+def test_emulated_host_calls_with_host_side_expansion():
+    """DQ_HOST_EXPAND=1 (opt-in, read once per process, hence the child process): dq_env_reset_host / dq_env_step_host return the
+    same byte observations, moved as bit-packed rows and expanded by the library's host threads."""
+    import os, subprocess, sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import emu_env as E\n"
+        "from test_env_emulated import make_pair\n"
+        "for d, model, use_Y, vd, n in ((5, 'DP', False, 5, 300), (7, 'DP', True, 4, 19), (3, 'X', False, 3, 257)):\n"
+        "    env, o = make_pair(d, model, use_Y, vd, 0.03, n, seed=3)\n"
+        "    assert env._info(10) == 1\n"
+        "    obs, legal = env.reset_host()\n"
+        "    oobs, olegal = o.reset()\n"
+        "    assert np.array_equal(obs, oobs) and np.array_equal(legal, olegal)\n"
+        "    for t in range(12):\n"
+        "        acts = o.random_legal_actions(olegal, t)\n"
+        "        got, want = env.step_host(acts), o.step(acts, auto_reset=True)\n"
+        "        assert all(np.array_equal(g, w) for g, w in zip(got, want)), (d, t)\n"
+        "        olegal = want[4]\n"
+        "print('ok')\n"
+    ) % os.path.dirname(os.path.abspath(__file__))
+    for threads in ("1", "5"):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DQ_HOST_EXPAND="1", DQ_HOST_THREADS=threads),
+                             capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
 def test_emulator_reports_deadlock_free_run_of_every_geometry():
     """Reset alone (RESET=true instantiation) on every supported distance, single lattice and ragged tile."""
     for d in (3, 5, 7):

@@ -46,6 +46,8 @@ unset DQ_DECODING_LIB
 [ "$BEST" != "new" ] && run bench_default 90 python bench.py --cpu-seconds 3 --no-dqn
 run pytest_rest 90 python -m pytest tests -m gpu -x -q --deselect tests/test_env_gpu.py
 run smoke 40 python __graft_entry__.py smoke
+DQ_HOST_EXPAND=1 run bench_host_expand 90 python bench.py --cpu-seconds 3 --no-dqn      # e2e with observations moved bit-packed + expanded on the host
+DQ_HOST_EXPAND=1 run pytest_host_expand 60 python -m pytest tests/test_env_gpu.py -x -q -k "host_buffer"
 run fold_head 90 python tools/check_fold_head.py      # opt-in folded head of the bf16 acting path: Q against unfolded / fp32, forward time
 for v in e16t96 bb2t96 pf2 e8t64mb14 e32t256mb4; do
     DQ_ONLY_ROLLOUT=256 DQ_DECODING_LIB=build/variants/libdq_$v.so run ab_$v 25 python tools/prof_rollout.py
