@@ -30,6 +30,9 @@
 #include <string.h>
 #include <math.h>
 #include <stdlib.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -1318,12 +1321,50 @@ const u64* byte_lut() {
 }
 }  // namespace
 
+#if defined(__x86_64__)
+// 32 bits -> 32 bytes of 0/1 in one store
+__attribute__((target("avx2"))) static inline void expand32_avx2(uint32_t word, uint8_t* out) {
+    __m256i v = _mm256_set1_epi32((int)word);
+    const __m256i shuf = _mm256_setr_epi64x(0x0000000000000000LL, 0x0101010101010101LL, 0x0202020202020202LL, 0x0303030303030303LL);
+    v = _mm256_shuffle_epi8(v, shuf);                                      // byte k of the word over bytes 8k .. 8k+7
+    const __m256i bitm = _mm256_set1_epi64x((long long)0x8040201008040201ULL);
+    v = _mm256_and_si256(_mm256_cmpeq_epi8(_mm256_and_si256(v, bitm), bitm), _mm256_set1_epi8(1));
+    _mm256_storeu_si256(reinterpret_cast<__m256i*>(out), v);
+}
+__attribute__((target("avx2"))) static void expand_lattices_avx2(const u64* packed, size_t npad, int e0, int e1, int C, int PW, int P, uint8_t* obs) {
+    // a layer's last cells leave as one more 32-byte store that ends exactly at the layer's end (it overlaps the previous store with
+    // the same values): no write past the layer, no partial copy through a temporary
+    const int t0 = P - 32, tw = t0 >> 6, ts = t0 & 63;
+    for (int e = e0; e < e1; ++e) {
+        uint8_t* out = obs + (size_t)e * C * P;
+        for (int c = 0; c < C; ++c, out += P) {
+            const u64* col = packed + (size_t)(c * PW) * npad + e;
+            int i = 0;
+            for (; i + 32 <= P; i += 32) expand32_avx2((uint32_t)(col[(size_t)(i >> 6) * npad] >> (i & 63)), out + i);
+            if (i < P) {
+                u64 lo = col[(size_t)tw * npad] >> ts;
+                if (ts > 32) lo |= col[(size_t)(tw + 1) * npad] << (64 - ts);
+                expand32_avx2((uint32_t)lo, out + t0);
+            }
+        }
+    }
+}
+#endif
+
 // packed rows [C*PW][npad] (bit i of layer c of lattice e = bit i%64 of row c*PW + i/64, column e) -> obs [n][C][P] bytes of 0/1
 static void expand_packed_host(const u64* packed, size_t npad, int n, int C, int PW, int P, uint8_t* obs) {
     const u64* lut = byte_lut();
     const int per = 256, nb = (n + per - 1) / per;
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("DQ_HOST_NO_AVX2");
+#else
+    const bool avx2 = false;
+#endif
     const std::function<void(int)> block = [&](int b) {
         const int e1 = std::min(n, (b + 1) * per);
+#if defined(__x86_64__)
+        if (avx2 && P >= 32) { expand_lattices_avx2(packed, npad, b * per, e1, C, PW, P, obs); return; }
+#endif
         for (int e = b * per; e < e1; ++e) {
             uint8_t* out = obs + (size_t)e * C * P;
             for (int c = 0; c < C; ++c, out += P)

@@ -20,6 +20,9 @@
 #include <string.h>
 #include <math.h>
 #include <ucontext.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>

@@ -173,8 +173,8 @@ def test_emulated_host_calls_with_host_side_expansion():
         "        olegal = want[4]\n"
         "print('ok')\n"
     ) % os.path.dirname(os.path.abspath(__file__))
-    for threads in ("1", "5"):
-        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DQ_HOST_EXPAND="1", DQ_HOST_THREADS=threads),
+    for threads, extra in (("1", {}), ("5", {}), ("3", {"DQ_HOST_NO_AVX2": "1"})):      # AVX2 expansion where the host has it, and the table walk
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DQ_HOST_EXPAND="1", DQ_HOST_THREADS=threads, **extra),
                              capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
 
