@@ -220,7 +220,8 @@ VARIANTS = [("prefetch", ["-DDQ_PREFETCH=1"]),
             ("deferred_streaming_stores", ["-DDQ_DEFER=1", "-DDQ_STREAM_OBS=1"]),
             ("deferred_render", ["-DDQ_DEFER=2"]),
             ("deferred_render_prefetch_refill1", ["-DDQ_DEFER=2", "-DDQ_PREFETCH=1", "-DDQ_REFILL=1"]),
-            ("deferred_render_tile8x64", ["-DDQ_DEFER=2", "-DDQ_EPC=8", "-DDQ_THREADS=64"])]
+            ("deferred_render_tile8x64", ["-DDQ_DEFER=2", "-DDQ_EPC=8", "-DDQ_THREADS=64"]),
+            ("deferred_render_5warps", ["-DDQ_DEFER=2", "-DDQ_THREADS=160"])]
 
 
 @pytest.mark.parametrize("name,flags", VARIANTS, ids=[v[0] for v in VARIANTS])
