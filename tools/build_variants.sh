@@ -27,6 +27,7 @@ variant df2solk    -DDQ_DEFER=2 -DDQ_STREAM_OBS=1 -DDQ_LUT_KEEP=1
 variant df2sot160  -DDQ_DEFER=2 -DDQ_STREAM_OBS=1 -DDQ_THREADS=160 -DDQ_MIN_BLOCKS=7      # five warps: one more for phase B and the helpers; 56 registers, ~100 B of spills
 variant lk         -DDQ_LUT_KEEP=1
 variant df2sopf1   -DDQ_DEFER=2 -DDQ_STREAM_OBS=1 -DDQ_PREFETCH=1 -DDQ_REFILL=1
+variant df2sopf2   -DDQ_DEFER=2 -DDQ_STREAM_OBS=1 -DDQ_PREFETCH=1 -DDQ_REFILL=2
 variant dfsopf1    -DDQ_DEFER=1 -DDQ_STREAM_OBS=1 -DDQ_PREFETCH=1 -DDQ_REFILL=1
 variant bb2so      -DDQ_BATCHB=2 -DDQ_STREAM_OBS=1
 variant bb2        -DDQ_BATCHB=2
