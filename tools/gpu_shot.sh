@@ -2,6 +2,7 @@
 # One short GPU call for a rebuilt env kernel: parity first, then a same-box A/B of the default build against the previous
 # kernel and the tuning variants (tools/build_variants.sh), parity of the fastest build, the bench line and the ncu launch
 # list on it, then whatever else fits.  Usage (under gpurun): bash tools/gpu_shot.sh <tag> <seconds available>
+# (SKIP_AB=1 skips the first A/B loop: a second call can then spend its time on the later steps)
 TAG=${1:-shot}; BUDGET=${2:-220}; T0=$(date +%s)
 left() { echo $(( BUDGET - ($(date +%s) - T0) )); }
 run() {   # name, max seconds, command...: skipped when less than 10 s remain
@@ -15,7 +16,7 @@ run pytest_env 90 python -m pytest tests/test_env_gpu.py -x -q
 tail -2 gpurun_out/${TAG}_pytest_env.out
 run ab_new 40 python tools/prof_rollout.py
 DQ_DECODING_LIB=build/variants/libdq_old.so run ab_old 40 python tools/prof_rollout.py
-for v in so lk df dfso df2 df2so df2solk df2sopf1 df2sopf2 df2sot160 dfsopf1 bb2 bb2so bb bbso bbe32 pf1 mb8; do
+[ -n "$SKIP_AB" ] || for v in so lk df dfso df2 df2so df2solk df2sopf1 df2sopf2 df2sot160 dfsopf1 bb2 bb2so bb bbso bbe32 pf1 mb8; do
     DQ_CALLS=12 DQ_ONLY_ROLLOUT=256 DQ_DECODING_LIB=build/variants/libdq_$v.so run ab_$v 25 python tools/prof_rollout.py
 done
 BEST=$(python - "$TAG" <<'PY'
