@@ -80,6 +80,12 @@ constexpr int kWarps = kThreads / 32;
                                  //    table (the v8 capture reads 150 KB of DRAM per step, and warp 0 waits ~1000 cycles per step on that lookup)
 constexpr bool kPrefetch = DQ_PREFETCH != 0;
 constexpr bool kBatchB = DQ_BATCHB != 0;
+#ifndef DQ_MIRROR
+#define DQ_MIRROR (DQ_DEFER != 0)   // the shared-memory mirror of the frame / counters / action boards alone (part of DQ_DEFER; also combines with DQ_BATCHB)
+#endif
+#if DQ_DEFER && !DQ_MIRROR
+#error "DQ_DEFER needs DQ_MIRROR"
+#endif
 constexpr bool kDefer = DQ_DEFER != 0;
 static_assert(!(kPrefetch && kBatchB), "DQ_PREFETCH and DQ_BATCHB both use the prepared-mask buffers");
 static_assert(!(kDefer && kBatchB), "DQ_DEFER restructures the default phase B");
@@ -274,8 +280,10 @@ struct Smem {
     int ntask;
     int npending[2];                  // DQ_BATCHB: lattices that still need a volume attempt after a round (by round parity)
     u64 fsl[(DQ_BATCHB == 2 || DQ_DEFER == 2) ? kEpc : 1][kMaxVd];   // DQ_BATCHB=2: the slices of a finished volume, handed from its warp to the batched finalisation
-#if DQ_DEFER
+#if DQ_MIRROR
     u64 cx[kEpc], cz[kEpc], cmeta[kEpc], cact[3][kEpc];   // the tile's frame planes, counters and action boards (mirror of the state rows)
+#endif
+#if DQ_DEFER
     u32 dirty[2];                     // by step parity: lattices (bit = slot) whose span of `stream` is older than their bitmaps
 #endif
 };
@@ -499,7 +507,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         sm.sum[tid] = p.state[ROW_SUM * np + env0 + tid];
         sm.pre_att[tid] = kNoAttempt;
         if (kPrefetch) sm.att[tid] = (u32)(p.state[ROW_META * np + env0 + tid] >> 32) & 0x7FFFFFFFu;
-#if DQ_DEFER
+#if DQ_MIRROR
         if (!RESET) {
             sm.cx[tid] = p.state[ROW_XB * np + env0 + tid];
             sm.cz[tid] = p.state[ROW_ZB * np + env0 + tid];
@@ -507,6 +515,8 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
 #pragma unroll
             for (int l = 0; l < 3; ++l) sm.cact[l][tid] = l < p.layers ? p.state[(ROW_ACT + l) * np + env0 + tid] : 0ull;
         }
+#endif
+#if DQ_DEFER
         if (tid < 2) sm.dirty[tid] = 0;
 #endif
     }
@@ -581,7 +591,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         u64 xb = 0, zb = 0, meta = 0, act[3] = {0, 0, 0};
         u32 flags = 0;
         if (mine) {
-#if !DQ_DEFER
+#if !DQ_MIRROR
             meta = p.state[ROW_META * np + e];
 #else
             meta = RESET ? p.state[ROW_META * np + e] : sm.cmeta[lane];
@@ -589,7 +599,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             int actbit = -1;
             if (!RESET) {
                 int a = (live && actions) ? actions[e] : p.A - 1;
-#if !DQ_DEFER
+#if !DQ_MIRROR
                 xb = p.state[ROW_XB * np + e];
                 zb = p.state[ROW_ZB * np + e];
 #pragma unroll
@@ -651,7 +661,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                     p.state[ROW_ZB * np + e] = zb;
                     p.state[ROW_META * np + e] = meta;
                     if (!ident) p.state[(ROW_ACT + layer) * np + e] = layer == 0 ? act[0] : (layer == 1 ? act[1] : act[2]);
-#if DQ_DEFER
+#if DQ_MIRROR
                     sm.cx[lane] = xb; sm.cz[lane] = zb; sm.cmeta[lane] = meta;
                     sm.cact[0][lane] = act[0]; sm.cact[1][lane] = act[1]; sm.cact[2][lane] = act[2];
 #endif
@@ -721,11 +731,13 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                 sm.sum[slot] = summed; sm.acted[slot] = 0;
                 if (kPrefetch) sm.att[slot] = attempts;
                 if (!RESET) sm.life_out[slot] = lo;
-#if DQ_DEFER
+#if DQ_MIRROR
                 if (!RESET) {
                     sm.cx[slot] = bx; sm.cz[slot] = bz; sm.cmeta[slot] = meta_pack(life, attempts, dn);
                     sm.cact[0][slot] = 0; sm.cact[1][slot] = 0; sm.cact[2][slot] = 0;
                 }
+#endif
+#if DQ_DEFER
                 atomicOr(&sm.dirty[rs & 1], 1u << slot);
 #endif
             }
@@ -806,6 +818,12 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                     p.state[ROW_META * np + e] = sm.fmeta[slot];
                     p.state[ROW_SUM * np + e] = summed;
                     sm.sum[slot] = summed; sm.acted[slot] = 0;
+#if DQ_MIRROR
+                    if (!RESET) {
+                        sm.cx[slot] = sm.fx[slot]; sm.cz[slot] = sm.fz[slot]; sm.cmeta[slot] = sm.fmeta[slot];
+                        sm.cact[0][slot] = 0; sm.cact[1][slot] = 0; sm.cact[2][slot] = 0;
+                    }
+#endif
                 }
                 u64 w[PW];
                 syndrome_layer_bitmap<D>(f, w);
@@ -913,6 +931,12 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                     p.state[ROW_META * np + e] = meta_pack(life, attempts, dn);
                     p.state[ROW_SUM * np + e] = summed;
                     sm.sum[slot] = summed; sm.acted[slot] = 0;
+#if DQ_MIRROR
+                    if (!RESET) {
+                        sm.cx[slot] = xb; sm.cz[slot] = zb; sm.cmeta[slot] = meta_pack(life, attempts, dn);
+                        sm.cact[0][slot] = 0; sm.cact[1][slot] = 0; sm.cact[2][slot] = 0;
+                    }
+#endif
                 }
             }
             if (complete) {

@@ -221,7 +221,9 @@ VARIANTS = [("prefetch", ["-DDQ_PREFETCH=1"]),
             ("deferred_render", ["-DDQ_DEFER=2"]),
             ("deferred_render_prefetch_refill1", ["-DDQ_DEFER=2", "-DDQ_PREFETCH=1", "-DDQ_REFILL=1"]),
             ("deferred_render_tile8x64", ["-DDQ_DEFER=2", "-DDQ_EPC=8", "-DDQ_THREADS=64"]),
-            ("deferred_render_5warps", ["-DDQ_DEFER=2", "-DDQ_THREADS=160"])]
+            ("deferred_render_5warps", ["-DDQ_DEFER=2", "-DDQ_THREADS=160"]),
+            ("batched_phase_b_mirror", ["-DDQ_BATCHB=1", "-DDQ_MIRROR=1"]),
+            ("batched_finalisation_mirror_tile32x256", ["-DDQ_BATCHB=2", "-DDQ_MIRROR=1", "-DDQ_EPC=32", "-DDQ_THREADS=256"])]
 
 
 @pytest.mark.parametrize("name,flags", VARIANTS, ids=[v[0] for v in VARIANTS])

@@ -35,6 +35,8 @@ variant bb         -DDQ_BATCHB=1
 variant bbmb8      -DDQ_BATCHB=1 -DDQ_MIN_BLOCKS=8
 variant bbe32      -DDQ_BATCHB=1 -DDQ_EPC=32 -DDQ_THREADS=256 -DDQ_MIN_BLOCKS=4 -DDQ_STREAM_OBS=1     # fewest instructions per lattice-step of all builds
 variant bbso       -DDQ_BATCHB=1 -DDQ_STREAM_OBS=1
+variant bbsomi     -DDQ_BATCHB=1 -DDQ_STREAM_OBS=1 -DDQ_MIRROR=1      # + frame / counters / action boards read from shared memory in phase A
+variant bb2somi    -DDQ_BATCHB=2 -DDQ_STREAM_OBS=1 -DDQ_MIRROR=1
 variant pf1        -DDQ_PREFETCH=1 -DDQ_REFILL=1
 variant pf2        -DDQ_PREFETCH=1
 variant pf3        -DDQ_PREFETCH=1 -DDQ_REFILL=3

@@ -16,7 +16,7 @@ run pytest_env 90 python -m pytest tests/test_env_gpu.py -x -q
 tail -2 gpurun_out/${TAG}_pytest_env.out
 run ab_new 40 python tools/prof_rollout.py
 DQ_DECODING_LIB=build/variants/libdq_old.so run ab_old 40 python tools/prof_rollout.py
-[ -n "$SKIP_AB" ] || for v in so lk df dfso df2 df2so df2solk df2sopf1 df2sopf2 df2sot160 dfsopf1 bb2 bb2so bb bbso bbe32 pf1 mb8; do
+[ -n "$SKIP_AB" ] || for v in so lk df dfso df2 df2so df2solk df2sopf1 df2sopf2 df2sot160 dfsopf1 bb2 bb2so bb2somi bb bbso bbsomi bbe32 pf1 mb8; do
     DQ_CALLS=12 DQ_ONLY_ROLLOUT=256 DQ_DECODING_LIB=build/variants/libdq_$v.so run ab_$v 25 python tools/prof_rollout.py
 done
 BEST=$(python - "$TAG" <<'PY'
