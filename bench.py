@@ -534,6 +534,13 @@ def run_b200(args):
                "trained_here": "profiles/r1_train_curriculum_dp_p007.json: 342.9 +- 3.7 cycles after 109 s of training from scratch"}
         ev_env.close()
 
+    experiments = None
+    if rank == 0 and world == 1 and args.workload == "c3" and not args.no_experiments:
+        try:
+            torch.cuda.synchronize()
+            experiments = run_experiments()
+        except Exception as ex:      # noqa: BLE001
+            experiments = {"error": str(ex)[:200]}
     if rank == 0:
         cb, _, _ = cpu_oracle_run(args.cpu_seconds)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
@@ -553,12 +560,108 @@ def run_b200(args):
                         "policy": "uniform random action indices pre-generated on the host"},
                 "e2e_packed": e2e_packed,
                 "gpu_launches": timed_launches, "single_step_launches": single,
-                "roofline": roof, "roofline_scaling": scaling, "cpu_baseline": cb, "dqn": dqn, "logical_error_rate": ler}
+                "roofline": roof, "roofline_scaling": scaling, "cpu_baseline": cb, "dqn": dqn, "logical_error_rate": ler,
+                "experiments": experiments}
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------- opt-in builds, timed beside the default
+def experiment_child(args):
+    """One opt-in build / mode in its own process (the library and the DQ_* switches are chosen per process): a fixed seeded
+    rollout whose outputs are folded into a checksum (must equal the default build's), then the rollout and host-buffer rates."""
+    import numpy as np
+    import torch
+    from deepq_decoding_b200 import _lib
+    from deepq_decoding_b200.envs import VecSurfaceCodeEnv
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    L = _lib.lib()
+    n = N_PER_GPU
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    cur = lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    env = VecSurfaceCodeEnv(D, P, P, MODEL, USE_Y, VD, None, n_envs=n, seed=SEED + 77, env_id_base=0, device=dev)
+    ring = torch.zeros((RING,) + tuple(env.obs.shape), dtype=torch.uint8, device=dev)
+    S = 64
+    out = [torch.empty((S, n), dtype=dt, device=dev) for dt in (torch.float32, torch.uint8, torch.int32, torch.int32)]
+    legal = torch.empty((S, n, env.mask_words), dtype=torch.int64, device=dev)
+    env.reset()
+    _lib.check(L.dq_policy_seek(env._h, 0, cur()))
+
+    def roll(i):
+        _lib.check(L.dq_env_rollout_random(env._h, S, vp(ring), RING, (i * S) % RING, vp(out[0]), vp(out[1]), vp(out[2]), vp(legal), vp(out[3]), 1, cur()))
+    roll(0)
+    torch.cuda.synchronize()
+    mix = lambda t: int((t.to(torch.int64).flatten() * (torch.arange(t.numel(), device=dev, dtype=torch.int64) % 1000003 + 1)).sum().item())
+    checksum = [mix(out[0]), mix(out[1]), mix(out[2]), mix(out[3]), mix(legal), mix(ring.view(torch.uint8)), mix(env.get_state_words())]
+    for i in range(1, 4):
+        roll(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 24
+    a.record()
+    for i in range(reps):
+        roll(4 + i)
+    b.record()
+    torch.cuda.synchronize()
+    us = a.elapsed_time(b) * 1e3 / (reps * S)
+    res = {"checksum": checksum, "rollout_us_per_step": us, "env_steps_per_s": n / us * 1e6, "steps_per_launch": S}
+    # host-buffer rate (dq_env_step_host), as the e2e leg does it
+    rng = np.random.default_rng(SEED)
+    ke = 24
+    host_actions = torch.from_numpy(rng.integers(0, env.num_actions, size=(ke + 3, n), dtype=np.int32)).pin_memory()
+    hb = env._host_buffers()
+    hp = lambda t: C.c_void_p(t.data_ptr())
+    def host_step(i):
+        _lib.check(L.dq_env_step_host(env._h, C.c_void_p(host_actions[i].data_ptr()), hp(hb["obs"]), hp(hb["reward"]),
+                                      hp(hb["done"]), hp(hb["lifetime"]), hp(hb["legal"]), 1))
+    for i in range(3):
+        host_step(i)
+    t0 = time.perf_counter()
+    for i in range(3, ke + 3):
+        host_step(i)
+    dt = time.perf_counter() - t0
+    res["host_env_steps_per_s"] = n * ke / dt
+    res["host_obs_checksum"] = mix(hb["obs"].to(dev))
+    he = C.c_int64(0)
+    res["host_expand"] = bool(L.dq_env_info(env._h, 10, C.byref(he)) == 0 and he.value == 1)
+    env.close()
+    print("EXPERIMENT " + json.dumps(res), flush=True)
+
+
+def run_experiments():
+    """Times the opt-in builds that were written without GPU access next to the default build, each in a child process with a
+    time limit; nothing here feeds `value` / `e2e`.  A child that fails or is missing its library is reported, not fatal."""
+    arms = [("default", {}),
+            ("stream_obs", {"DQ_DECODING_LIB": os.path.join(ROOT, "build", "variants", "libdq_so.so")}),
+            ("defer1_stream_obs", {"DQ_DECODING_LIB": os.path.join(ROOT, "build", "variants", "libdq_dfso.so")}),
+            ("host_expand", {"DQ_HOST_EXPAND": "1"})]
+    res, t_start = {}, time.perf_counter()
+    for name, extra in arms:
+        if time.perf_counter() - t_start > 150:          # the whole leg stays within a few minutes whatever happens
+            res[name] = {"skipped": "time budget of the experiments leg spent"}
+            continue
+        libp = extra.get("DQ_DECODING_LIB")
+        if libp and not os.path.exists(libp):
+            res[name] = {"skipped": "library not built"}
+            continue
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--experiment-child"], env=dict(os.environ, **extra),
+                                 capture_output=True, text=True, timeout=60)
+            line = [l for l in out.stdout.splitlines() if l.startswith("EXPERIMENT ")]
+            res[name] = json.loads(line[-1][len("EXPERIMENT "):]) if line else {"error": (out.stderr or out.stdout)[-300:]}
+        except Exception as ex:      # noqa: BLE001 -- reported, not fatal
+            res[name] = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+    ref = res.get("default", {})
+    for name, r in res.items():
+        if "checksum" in r and "checksum" in ref:
+            r["identical_to_default_build"] = r["checksum"] == ref["checksum"] and r["host_obs_checksum"] == ref["host_obs_checksum"]
+    for r in res.values():
+        r.pop("checksum", None)
+    return res
 
 
 def select_workload(name):
@@ -579,8 +682,12 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall budget of the cpu_baseline leg")
     ap.add_argument("--no-dqn", action="store_true", help="skip the DQN inner-loop measurements")
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS), help="BASELINE.json config (default c3 = the metric's)")
+    ap.add_argument("--experiment-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-experiments", action="store_true", help="skip the child processes that time the opt-in builds")
     args = ap.parse_args()
     select_workload(args.workload)
+    if args.experiment_child:
+        return experiment_child(args)
     if args.workload != "c3":
         args.no_dqn = True
     if args.impl == "reference":

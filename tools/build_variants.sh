@@ -11,8 +11,9 @@ FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompil
 mkdir -p $OUT
 [ -f $OUT/dq_qnet.o ] && [ $OUT/dq_qnet.o -nt $CS/dq_qnet.cu ] || $NVCC $FLAGS -c -o $OUT/dq_qnet.o $CS/dq_qnet.cu
 [ -f $OUT/dq_comm.o ] && [ $OUT/dq_comm.o -nt $CS/dq_comm.cu ] || $NVCC $FLAGS -c -o $OUT/dq_comm.o $CS/dq_comm.cu
-variant() {   # name, extra flags
+variant() {   # name, extra flags; DQ_VARIANTS="so dfso" restricts the build to the named ones
     name=$1; shift
+    if [ -n "$DQ_VARIANTS" ]; then case " $DQ_VARIANTS " in *" $name "*) ;; *) return 0;; esac; fi
     $NVCC $FLAGS "$@" -c -o $OUT/dq_env_$name.o $CS/dq_env.cu
     $NVCC -shared -o $OUT/libdq_$name.so $OUT/dq_env_$name.o $OUT/dq_qnet.o $OUT/dq_comm.o -lcudart
     rm -f $OUT/dq_env_$name.o

@@ -40,14 +40,14 @@ if [ "$BEST" != "new" ]; then
     tail -2 gpurun_out/${TAG}_pytest_env_best.out
 fi
 DQ_CALLS=6 DQ_ONLY_ROLLOUT=64 DQ_N=262144 run big_best 40 python tools/prof_rollout.py      # the same build with every SM fully loaded
-run bench_best 90 python bench.py --cpu-seconds 3 --no-dqn
-run ncu_list 60 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_launches_rollout.csv python bench.py --steps 1024 --warmup 16 --cpu-seconds 0.2 --no-dqn
+run bench_best 90 python bench.py --cpu-seconds 3 --no-dqn --no-experiments
+run ncu_list 60 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_launches_rollout.csv python bench.py --steps 1024 --warmup 16 --cpu-seconds 0.2 --no-dqn --no-experiments
 DQ_ONLY_ROLLOUT=64 run ncu_full 60 ncu --set full --clock-control none --import-source on -k regex:env_step_kernel -s 4 -c 1 -f -o gpurun_out/${TAG}_rollout64 python tools/prof_rollout.py
 unset DQ_DECODING_LIB
-[ "$BEST" != "new" ] && run bench_default 90 python bench.py --cpu-seconds 3 --no-dqn
+[ "$BEST" != "new" ] && run bench_default 90 python bench.py --cpu-seconds 3 --no-dqn --no-experiments
 run pytest_rest 90 python -m pytest tests -m gpu -x -q --deselect tests/test_env_gpu.py
 run smoke 40 python __graft_entry__.py smoke
-DQ_HOST_EXPAND=1 run bench_host_expand 90 python bench.py --cpu-seconds 3 --no-dqn      # e2e with observations moved bit-packed + expanded on the host
+DQ_HOST_EXPAND=1 run bench_host_expand 90 python bench.py --cpu-seconds 3 --no-dqn --no-experiments      # e2e with observations moved bit-packed + expanded on the host
 DQ_HOST_EXPAND=1 run pytest_host_expand 60 python -m pytest tests/test_env_gpu.py -x -q -k "host_buffer"
 run fold_head 90 python tools/check_fold_head.py      # opt-in folded head of the bf16 acting path: Q against unfolded / fp32, forward time
 for v in e16t96 bb2t96 pf2 e8t64mb14 e32t256mb4; do
