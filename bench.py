@@ -638,7 +638,8 @@ def run_experiments():
     arms = [("default", {}),
             ("stream_obs", {"DQ_DECODING_LIB": os.path.join(ROOT, "build", "variants", "libdq_so.so")}),
             ("defer1_stream_obs", {"DQ_DECODING_LIB": os.path.join(ROOT, "build", "variants", "libdq_dfso.so")}),
-            ("host_expand", {"DQ_HOST_EXPAND": "1"})]
+            ("host_expand", {"DQ_HOST_EXPAND": "1"}),
+            ("defer2_stream_obs", {"DQ_DECODING_LIB": os.path.join(ROOT, "build", "variants", "libdq_df2so.so")})]    # last: the one with a new barrier
     res, t_start = {}, time.perf_counter()
     for name, extra in arms:
         if time.perf_counter() - t_start > 150:          # the whole leg stays within a few minutes whatever happens
