@@ -67,17 +67,54 @@ def owner(f, l):
     return "%s:%d" % (f, l)
 
 
-# source-line ranges of dq_env.cu / dq_lattice.cuh at commit af650fa (the v8 kernel the round-1 captures were taken from);
-# a library built from a later source needs these ranges moved with it
-OWNERS = [(98, 106, "referee table lookup"), (108, 122, "record_event (fired draws)"), (124, 171, "draw_flip_masks (screen + walk)"),
-          (173, 215, "generate_volume after the draws"), (244, 270, "stream gather"), (272, 276, "expand16"),
-          (278, 293, "legal_words"), (295, 333, "write_observations"), (335, 403, "loop control / prologue"),
-          (405, 426, "helpers: policy words, D call"), (428, 506, "phase A body (warp 0)"), (507, 519, "barrier 1 / light cell"),
-          (520, 581, "phase B task body"), (782, 802, "phase C / tail")]
-LATTICE = [(34, 41, "popc64"), (42, 112, "Lat<D> geometry"), (113, 120, "true_syndrome"), (121, 125, "homology_label"),
-           (126, 139, "qubit grid <-> compact"), (140, 160, "stabilizer grid <-> compact"), (161, 171, "joint referee index"),
-           (172, 180, "split referee index"), (181, 192, "adjacent / neighbour qubits"), (193, 215, "syndrome_layer_bitmap"),
-           (216, 227, "action_layer_bitmap"), (228, 250, "philox4x32_10"), (251, 267, "extract / popc32"), (268, 290, "select64")]
+# Owners of source lines.  FIXED_* are the ranges at commit af650fa (the v8 kernel the round-1 captures were taken from); for a library
+# built from a later source pass --source <dir of that source> and the ranges are derived from the function signatures and the
+# phase comments of dq_env.cu / dq_lattice.cuh themselves (derive_owners).
+FIXED_OWNERS = [(98, 106, "referee table lookup"), (108, 122, "record_event (fired draws)"), (124, 171, "draw_flip_masks (screen + walk)"),
+                (173, 215, "generate_volume after the draws"), (244, 270, "stream gather"), (272, 276, "expand16"),
+                (278, 293, "legal_words"), (295, 333, "write_observations"), (335, 403, "loop control / prologue"),
+                (405, 426, "helpers: policy words, D call"), (428, 506, "phase A body (warp 0)"), (507, 519, "barrier 1 / light cell"),
+                (520, 581, "phase B task body"), (782, 802, "phase C / tail")]
+FIXED_LATTICE = [(34, 41, "popc64"), (42, 112, "Lat<D> geometry"), (113, 120, "true_syndrome"), (121, 125, "homology_label"),
+                 (126, 139, "qubit grid <-> compact"), (140, 160, "stabilizer grid <-> compact"), (161, 171, "joint referee index"),
+                 (172, 180, "split referee index"), (181, 192, "adjacent / neighbour qubits"), (193, 215, "syndrome_layer_bitmap"),
+                 (216, 227, "action_layer_bitmap"), (228, 250, "philox4x32_10"), (251, 267, "extract / popc32"), (268, 290, "select64")]
+OWNERS, LATTICE = FIXED_OWNERS, FIXED_LATTICE
+
+ENV_MARKS = [("int lut2(", "referee table lookup"), ("void record_event(", "record_event (fired draws)"),
+             ("bool draw_flip_masks(", "draw_flip_masks (screen + walk)"), ("u64 generate_volume(", "generate_volume after the draws"),
+             ("struct Rollout", None), ("u32 gather32(", "stream gather"), ("uint4 expand16(", "expand16"), ("void store_obs16(", "write_observations"),
+             ("void named_barrier(", "render_dirty (deferred bitmaps)"), ("u32 fresh_word(", "fresh_word (deferred stream spans)"),
+             ("void legal_words(", "legal_words"), ("void write_observations_unaligned(", "write_observations"),
+             ("env_step_kernel(const EnvParams p", "loop control / prologue"), ("// ---- phase A", "helpers: policy words, D call"),
+             ("        const int e = env0 + lane;", "phase A body (warp 0)"), ("a light step's action lights", "barrier 1 / light cell"),
+             ("// ---- phase B", "phase B task body"), ("} else if constexpr (DQ_BATCHB == 2)", "phase B (batched finalisation)"),
+             ("// DQ_BATCHB=1.  Everything after the draws", "phase B (batched)"), ("// ---- phase C", "phase C / tail"),
+             ("__global__ void policy_random_legal_kernel(", None)]
+LAT_MARKS = [("int popc64(", "popc64"), ("struct Lat", "Lat<D> geometry"), ("u64 plaquette_parity(", "true_syndrome"), ("int homology_label(", "homology_label"),
+             ("u64 qubits_compact_to_grid(", "qubit grid <-> compact"), ("u64 stabs_grid_to_compact(", "stabilizer grid <-> compact"),
+             ("u32 stabs_grid_to_joint_index(", "joint referee index"), ("u32 stabs_grid_to_type_index(", "split referee index"),
+             ("u64 qubits_adjacent_to(", "adjacent / neighbour qubits"), ("u32 spread2_8(", "syndrome_layer_bitmap"),
+             ("void action_layer_bitmap(", "action_layer_bitmap"), ("u32 mulhi32(", "philox4x32_10"), ("u64 extract_bits(", "extract / popc32"),
+             ("int select64(", "select64")]
+
+
+def derive_owners(path, marks):
+    """[(first line, last line, owner)] from the first line that contains each marker, in file order; a None owner ends a range."""
+    lines = open(path).read().splitlines()
+    found = []
+    for text, name in marks:
+        for i, ln in enumerate(lines, 1):
+            if text in ln and (not found or i > found[-1][0]):
+                found.append((i, name))
+                break
+    found.sort()
+    out = []
+    for k, (i, name) in enumerate(found):
+        end = found[k + 1][0] - 1 if k + 1 < len(found) else len(lines)
+        if name:
+            out.append((i, end, name))
+    return out
 
 
 def main():
@@ -87,7 +124,12 @@ def main():
     ap.add_argument("--tiles", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--kernel", default=KERNEL)
+    ap.add_argument("--source", default=None, help="directory of the dq_env.cu / dq_lattice.cuh the library was built from (default: the af650fa line ranges)")
     a = ap.parse_args()
+    if a.source:
+        global OWNERS, LATTICE
+        OWNERS = derive_owners(os.path.join(a.source, "dq_env.cu"), ENV_MARKS)
+        LATTICE = derive_owners(os.path.join(a.source, "dq_lattice.cuh"), LAT_MARKS)
     seq = line_table(a.lib, a.kernel)
     hdr, data = source_page(a.rep)
     assert len(seq) == len(data), "capture and library are different builds (%d vs %d instructions)" % (len(data), len(seq))
