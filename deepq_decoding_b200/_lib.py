@@ -32,6 +32,7 @@ _SIGNATURES = {
     "dq_env_destroy": (_i, [_vp]),
     "dq_env_info": (_i, [_vp, _i, C.POINTER(_i64)]),
     "dq_env_set_noise": (_i, [_vp, _dbl, _dbl]),
+    "dq_env_set_max_attempts": (_i, [_vp, _i]),
     "dq_env_set_referee_lut": (_i, [_vp, _i, _vp, _i64, _vp, _i64]),
     "dq_env_reset": (_i, [_vp, _vp, _vp, _vp]),
     "dq_env_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),

@@ -23,6 +23,7 @@ import torch
 
 from . import _lib
 from .envs import VecSurfaceCodeEnv, Surface_Code_Environment_Multi_Decoding_Cycles
+from .episodes import EpisodeBook
 from .qnet import QNetwork
 
 
@@ -188,6 +189,7 @@ class DQNAgent:
         self.optimizer = None
         self.model = None                           # QNetwork, built in compile()
         self.step, self.updates = 0, 0
+        self.policy_step = 0        # iterations acted so far over ALL fit / test calls: the step index of the policy's Philox stream
         self.L = _lib.lib()
 
     # ---- reference API ----
@@ -261,7 +263,7 @@ class DQNAgent:
     def _policy_params(self, policy, training):
         if isinstance(policy, LinearAnnealedPolicy):
             return policy.value(self.step, training), policy.masked_greedy
-        return (policy.eps if training or isinstance(policy, GreedyQPolicy) else 0.0), policy.masked_greedy
+        return policy.eps, policy.masked_greedy          # GreedyQPolicy: 0; an EpsGreedyQPolicy handed in as test policy keeps its own eps
 
     def _act(self, v, rows_ptr, step_index, eps, masked):
         """Q(s) for all lattices from the packed rows inside the env state, then the eps-greedy pick."""
@@ -326,10 +328,18 @@ class DQNAgent:
         if action_repetition != 1 or nb_max_start_steps != 0 or single_cycle:
             raise NotImplementedError("only the settings the reference uses (action_repetition=1, no start steps, multi-cycle)")
         v = _vec(env)
-        v.auto_reset = True
         N, dev = v.n_envs, self.model.device
         if N > self.model.max_batch:
             raise ValueError("compile(max_envs=...) must cover the environment's %d lattices" % N)
+        # Data-parallel fit: warm-up, the target period, train_interval and termination must fall on the same iteration on every
+        # rank (every update is a collective), so all ranks count the LARGEST shard's transitions per iteration.
+        step_inc = N
+        if self.process_group is not None:
+            import torch.distributed as dist
+            if dist.get_world_size(self.process_group) > 1:
+                t = torch.tensor([N], dtype=torch.int64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.process_group)
+                step_inc = int(t.item())
         rows_ptr, nrows, stride = C.c_void_p(), C.c_int64(), C.c_int64()
         _lib.check(self.L.dq_env_packed_obs(v._h, C.byref(rows_ptr), C.byref(nrows), C.byref(stride)))
         from .qnet import device_view
@@ -337,15 +347,18 @@ class DQNAgent:
         if self.memory.ring is None:
             self.memory.ring = ReplayRing(max(2, -(-self.memory.limit // N) + 1), nrows.value, stride.value, N, dev)
         ring = self.memory.ring
+        if ring.pushed > 0:
+            # resumed ring (an earlier fit, or load_memory): its newest slot holds (s, a, r) of a transition whose s' was never
+            # stored.  The first observation of this fit takes that slot over, so the sampler can never pair it with this episode.
+            ring.pushed -= 1
+        self.step = 0               # keras-rl's Agent.fit restarts the step counter (warm-up and the eps schedule with it)
         K = self.flush_interval
         h_rew = torch.zeros((K, N), dtype=torch.float32, device=dev)
         h_done = torch.zeros((K, N), dtype=torch.uint8, device=dev)
         h_life = torch.zeros((K, N), dtype=torch.int32, device=dev)
         hist = History()
         ep_reward, ep_steps = np.zeros(N), np.zeros(N, np.int64)
-        L_avg = max(1, int(episode_averaging_length))
-        win, win_sum, win_n = np.zeros(L_avg), 0.0, 0            # ring of the last L_avg lifetimes + running sum: O(1) rolling mean
-        best_avg, best_ep, episode = -np.inf, 0, 0
+        book = EpisodeBook(episode_averaging_length, success_threshold, stopping_patience, min_nb_steps)
         eps_sum, eps_n = 0.0, 0
         t_start = t_last = time.time()
         it, stop = 0, False
@@ -356,12 +369,13 @@ class DQNAgent:
         while self.step < nb_steps and not stop:
             eps, masked = self._policy_params(self.policy, True)
             ring.push_obs(rows_view)
-            actions = self._act(v, rows_ptr.value, it, eps, masked)
+            actions = self._act(v, rows_ptr.value, self.policy_step, eps, masked)
+            self.policy_step += 1
             _lib.check(self.L.dq_env_step(v._h, p(actions), None, p(v.reward), p(v.done), p(v.lifetime), p(v.legal_mask), 1, self._st()))
             ring.push_outcome(actions, v.reward, v.done)
             k = it % K
             h_rew[k].copy_(v.reward, non_blocking=True); h_done[k].copy_(v.done, non_blocking=True); h_life[k].copy_(v.lifetime, non_blocking=True)
-            self.step += N
+            self.step += step_inc
             it += 1
             if self.step > self.nb_steps_warmup:
                 eps_sum += eps; eps_n += 1
@@ -369,7 +383,7 @@ class DQNAgent:
                     for _ in range(self.updates_per_step):
                         self.train_on_ring(ring, self.updates)
                         upd_window += 1
-            if (self.step // self.target_model_update) != ((self.step - N) // self.target_model_update):
+            if (self.step // self.target_model_update) != ((self.step - step_inc) // self.target_model_update):
                 self.target_params.copy_(self.model.params)
                 if self.target_model is not None:
                     self.target_model.params_changed()
@@ -385,24 +399,15 @@ class DQNAgent:
                 per_episode_s = (now - t_last) / max(1, int(done.sum()))
                 for j in range(k + 1):
                     ep_reward += rew[j]; ep_steps += 1
+                    nb = int(self.step - (k - j) * step_inc)
                     for i in np.nonzero(done[j])[0]:
-                        slot = episode % L_avg
-                        win_sum += float(life[j, i]) - win[slot]
-                        win[slot] = life[j, i]
-                        win_n = min(win_n + 1, L_avg)
-                        rolling = win_sum / win_n
-                        if rolling > best_avg:
-                            best_avg, best_ep = rolling, episode
-                        succeeded = rolling > success_threshold
-                        stopped = (episode - best_ep > stopping_patience) and self.step >= min_nb_steps
+                        entry = book.finish_episode(life[j, i], nb)       # rolling / best / stop rules: episodes.py
                         hist.add(loss=loss, mean_q=mean_q, mean_eps=mean_eps, episode_reward=float(ep_reward[i]),
-                                 nb_episode_steps=int(ep_steps[i]), nb_steps=int(self.step - (k - j) * N),
-                                 episode_lifetimes_rolling_avg=rolling, best_rolling_avg=best_avg, best_episode=best_ep,
-                                 time_since_best=episode - best_ep, has_succeeded=bool(succeeded),
-                                 stopped_improving=bool(stopped), episode=episode, duration=per_episode_s)
+                                 nb_episode_steps=int(ep_steps[i]), nb_steps=nb, duration=per_episode_s, **entry)
                         ep_reward[i], ep_steps[i] = 0.0, 0
-                        episode += 1
-                        stop = stop or succeeded or stopped
+                stop = stop or book.stop
+                if self.comm is not None:
+                    self.comm.check()                   # a peer that never arrived: abort here, not after the run
                 if self.process_group is not None:      # ranks must leave the loop together (every update is a collective)
                     import torch.distributed as dist
                     flag = torch.tensor([1 if stop else 0], dtype=torch.int32, device=dev)
@@ -412,9 +417,9 @@ class DQNAgent:
                 for cb in (callbacks or []):
                     if hasattr(cb, "on_flush"):
                         cb.on_flush(hist.history)
-                if verbose and (it // K) % max(1, int(log_interval // max(1, K * N))) == 0 and win_n:
+                if verbose and (it // K) % max(1, int(log_interval // max(1, K * N))) == 0 and book.win_n:
                     print("step %d  episodes %d  rolling lifetime %.1f  best %.1f  eps %.3f  loss %.4g  mean_q %.3f  %.0f env-steps/s" % (
-                        self.step, episode, win_sum / win_n, best_avg, eps, loss, mean_q,
+                        self.step, book.episode, book.rolling, book.best_avg, eps, loss, mean_q,
                         self.step / max(1e-9, now - t_start)), flush=True)
         if self.comm is not None:
             self.comm.check()
@@ -431,7 +436,6 @@ class DQNAgent:
         ones); the first nb_episodes records in lattice-major order are returned.  History keys as in the fork:
         'episode_lifetime', 'episode_lifetimes_rolling_avg' (cumulative mean), 'episode_reward', 'nb_steps'."""
         v = _vec(env)
-        v.auto_reset = True
         N, dev = v.n_envs, self.model.device
         quota = -(-int(nb_episodes) // N)
         rows_ptr, nrows, stride = C.c_void_p(), C.c_int64(), C.c_int64()
@@ -448,7 +452,8 @@ class DQNAgent:
         lane = torch.arange(N, device=dev)
         it = 0
         while True:
-            actions = self._act(v, rows_ptr.value, it, eps, masked)
+            actions = self._act(v, rows_ptr.value, self.policy_step, eps, masked)
+            self.policy_step += 1
             _lib.check(self.L.dq_env_step(v._h, p(actions), None, p(v.reward), p(v.done), p(v.lifetime), p(v.legal_mask), 1, self._st()))
             it += 1
             done = v.done.bool()

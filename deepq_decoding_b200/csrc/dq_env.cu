@@ -1,27 +1,30 @@
 // dq_env.cu -- sm_100a environment-step kernel + C ABI (include/dq_decoding.h).
 //
-// One CTA (4 warps) advances a tile of 16 independent lattices.  Per-lattice state is bit-packed into
-// uint64 rows of a [row][lattice] matrix that stays L2-resident between steps:
-// Pauli-frame planes, action boards, counters, AND the already-rendered (2d+1)^2-cell bitmap of every
-// observation layer, so that a step only re-renders what changed.  A launch runs one step (dq_env_step*) or a
-// rollout of many (dq_env_rollout_random).  For the whole launch the tile's layer bitmaps are mirrored in shared
-// memory, together with the tile's observation BIT STREAM in its final layout (lattice-major concatenation of the
-// layer bitmaps, no padding: byte i of the tile's observations is bit i of the stream).  Per step (2 block barriers):
-//   A  warp 0, lane = lattice: (built-in random-legal pick,) apply the action to the Pauli frame, true syndrome
-//      by shifted XORs, homology label, referee table lookup, reward / done, heavy (identity | repeat) flag.
-//      Meanwhile warps 1.. write the PREVIOUS step's observations (D) and, once per group of steps, draw the
-//      policy's random words of the next group (they depend on (lattice, step index) only)
-//   -- barrier; a light step sets its one new cell in the action-layer bitmap and in the stream
-//   B  warp per flagged lattice: draw a fresh syndrome volume (generate_volume) -- Philox4x32-10, one
-//      block per lane, draws screened by one min-reduce, fired draws folded into per-slice flip masks, warp
-//      prefix-XOR over slices -- then the lane that owns a slice builds its layer bitmap in registers and the
-//      lattice's span of the stream is re-gathered
-//   -- barrier
-//   C  warp 0, lane = lattice: lifetime and legal-move mask (kept in registers for the next step's pick)
-//   D  thread per 32-bit word of the stream: expand to 32 bytes of 0/1 through a 256-entry table, two aligned
-//      128-bit stores (the tile's 16 observations are one contiguous, 16-byte aligned span of HBM)
-// Earlier variants (32-lattice tiles staged by TMA bulk copies; warp-autonomous 4/8-lattice groups) and
-// the ncu evidence that led here are summarised in profiles/README.md.
+// One CTA advances a tile of 32 independent lattices with three kinds of warps that never meet at a block barrier
+// inside the step loop (a launch runs one step -- dq_env_step* -- or a rollout of many -- dq_env_rollout_random):
+//
+//   PHYSICS (warp 0, lane = lattice, the lattice's frame / counters / action boards / legal mask live in registers for the
+//     whole launch): (built-in random-legal pick,) action -> Pauli frame, true syndrome by shifted XORs, homology label,
+//     referee table lookup, reward / done; a step that needs a fresh syndrome volume (identity | repeat | restart of a
+//     finished lattice) POPS it from the lattice's volume queue; then lifetime, legal-move mask, the small outputs.
+//   GENERATORS (warps 1+W..): keep every lattice's volume queue full.  A volume attempt is drawn from
+//     Philox(lattice, attempt index) alone, and the syndrome map is XOR-linear, so everything about attempt t can be
+//     computed without the lattice's state:  g_j = syndrome(e_0 ^ .. ^ e_j) ^ m_j  (e_j / m_j: the data-qubit and measurement
+//     flips of slice j) and the frame delta E = e_0 ^ .. ^ e_{vd-1}.  Popping it on frame F is then
+//     f_j = g_j ^ syndrome(F), F ^= E -- a handful of XORs per lattice -- and the attempt is all-trivial iff every f_j == 0.
+//     The attempt index is a monotone per-lattice counter, so a queued attempt is always consumed eventually, by a heavy
+//     step or by a restart alike: nothing is speculative.  The queue (DQ_QDEPTH attempts per lattice) persists in
+//     device memory between launches.
+//   WRITERS (warps 1..W): own the tile's rendered (2d+1)^2-cell layer bitmaps and the tile's observation BIT STREAM in its final
+//     layout (lattice-major concatenation of the layer bitmaps, no padding: byte i of the tile's observations is bit i).
+//     Per step they take the physics warp's record (one new action cell, or the slices of a fresh volume), re-render
+//     what changed, and expand the stream to bytes: thread per 32-bit word, 256-entry table, two 128-bit stores (the tile's 32
+//     observations are one contiguous, 32-byte aligned span of HBM).
+//
+// Hand-offs: physics -> writers through a two-slot record ring guarded by named barriers (bar.arrive / bar.sync, full and
+// empty per slot); physics <-> generators through per-lattice head / tail counters in shared memory (release / acquire by
+// __threadfence_block + volatile accesses).
+// Earlier kernels (barrier-phased 16-lattice tiles, v1-v8) and the ncu evidence that led here: profiles/README.md.
 //
 // Replaces (reference paths relative to example_notebooks/): Environments.py:99-115 (reset),
 // :118-204 (step), :206-235, :238-314 and the Function_Library.py helpers they call.
@@ -47,57 +50,34 @@
 
 namespace dq {
 
-#ifndef DQ_THREADS
-#define DQ_THREADS 128
+#ifndef DQ_WRITERS
+#define DQ_WRITERS 3             // observation-writer warps per CTA
+#endif
+#ifndef DQ_GENS
+#define DQ_GENS 4                // volume-generator warps per CTA
+#endif
+#ifndef DQ_QDEPTH
+#define DQ_QDEPTH 4              // queued volume attempts per lattice (power of two)
 #endif
 #ifndef DQ_MIN_BLOCKS
-#define DQ_MIN_BLOCKS 7          // resident CTAs per SM the register allocation must allow
+#define DQ_MIN_BLOCKS 4          // resident CTAs per SM the register allocation must allow (16 384 lattices = 512 tiles = 3.5 per SM)
 #endif
-#ifndef DQ_EPC
-#define DQ_EPC 16
-#endif
-constexpr int kEpc = DQ_EPC;                       // lattices per CTA: 16*L observation bytes are a multiple of 16 for every L
-constexpr int kThreads = DQ_THREADS;
-constexpr int kWarps = kThreads / 32;
-#ifndef DQ_PREFETCH
-#define DQ_PREFETCH 0            // rollouts: warps 1.. draw the flip masks of every lattice's next volume attempt ahead of time
-#endif
-#ifndef DQ_REFILL
-#define DQ_REFILL 2              // ... at most this many lattices per warp and step
-#endif
-#ifndef DQ_BATCHB
-#define DQ_BATCHB 0              // 1: phase B in rounds of two stages: masks drawn warp per lattice, then applied / rendered lane per (lattice, slice)
-#endif                           // 2: volumes warp per lattice as in the default build, only their finalisation (state, bitmaps, stream) batched
-#ifndef DQ_DEFER
-#define DQ_DEFER 0               // 1: work that nothing on the step's dependent chain waits for leaves the chain: the frame / counters / action
-#endif                           //    boards of the tile are mirrored in shared memory (phase A reads no global state), and a re-rendered
-                                 //    lattice's span of the bit stream is refreshed by the threads that expand it (phase D), not by phase B
-                                 // 2: ... and so do the layer bitmaps of a fresh volume: phase B leaves the slices in shared memory, the threads
-                                 //    of the next window render them (thread = (lattice, layer)) before they expand the stream
-#ifndef DQ_STREAM_OBS
-#define DQ_STREAM_OBS 0          // 1: observation bytes leave with evict-first stores (STG.E.EF.128): they are never read back by this
-#endif                           //    kernel, and a ring of them streaming through L2 otherwise evicts lines of the 4 MB joint referee
-                                 //    table (the v8 capture reads 150 KB of DRAM per step, and warp 0 waits ~1000 cycles per step on that lookup)
-constexpr bool kPrefetch = DQ_PREFETCH != 0;
-constexpr bool kBatchB = DQ_BATCHB != 0;
-#ifndef DQ_MIRROR
-#define DQ_MIRROR (DQ_DEFER != 0)   // the shared-memory mirror of the frame / counters / action boards alone (part of DQ_DEFER; also combines with DQ_BATCHB)
-#endif
-#if DQ_DEFER && !DQ_MIRROR
-#error "DQ_DEFER needs DQ_MIRROR"
-#endif
-constexpr bool kDefer = DQ_DEFER != 0;
-static_assert(!(kPrefetch && kBatchB), "DQ_PREFETCH and DQ_BATCHB both use the prepared-mask buffers");
-static_assert(!(kDefer && kBatchB), "DQ_DEFER restructures the default phase B");
-constexpr int kRefill = DQ_REFILL;
-constexpr u32 kNoAttempt = 0xffffffffu;              // attempt indices have 31 bits
-constexpr int kPickGroup = (kThreads - 32) / kEpc;   // rollout steps whose policy words warps 1.. draw in one go (thread = (step, lattice))
-static_assert(kPickGroup >= 1, "warps 1.. must cover at least one step of the tile");
+constexpr int kLpc = 32;                             // lattices per CTA = lanes of the physics warp
+constexpr int kWriters = DQ_WRITERS, kGens = DQ_GENS, kQ = DQ_QDEPTH;
+constexpr int kThreads = 32 * (1 + kWriters + kGens);
+constexpr int kWriterThreads = 32 * kWriters;
+constexpr int kOwned = (kLpc + kGens - 1) / kGens;   // lattices a generator warp serves: l = i*kGens + g
+static_assert((kQ & (kQ - 1)) == 0 && kQ >= 2, "queue depth must be a power of two");
+static_assert(kWriters >= 1 && kGens >= 1 && kThreads <= 1024, "warp roles");
 constexpr int kMaxVd = 8;
 constexpr int kMaxLayers = kMaxVd + 3;
-constexpr int kStreamWords = (kEpc * kMaxLayers * 15 * 15 + 31) / 32 + 1;   // d = 7 at the deepest volume
+constexpr int kQW = kMaxVd + 2;                      // words of a queued attempt: g_0..g_{vd-1}, EX, EZ
+constexpr int kRing = 2;                             // record slots between the physics warp and the writers
+constexpr int kBmWords = kMaxLayers * 4;             // u64 words of a lattice's layer bitmaps at d = 7, deepest volume
+constexpr int kStreamWords = kLpc * kMaxLayers * 15 * 15 / 32 + 1;
+constexpr int BAR_FULL = 1, BAR_EMPTY = BAR_FULL + kRing, BAR_WRITERS = BAR_EMPTY + kRing;    // named barriers (0 = __syncthreads)
 // The reference loops until a volume is non-trivial, forever if p_phys = p_meas = 0 on a clean frame.
-// A kernel must end: after this many attempts in one call the (trivial) volume is accepted.
+// A kernel must end: after this many attempts on one volume the (trivial) volume is accepted.
 constexpr int kMaxAttemptsPerCall = 1 << 20;
 
 // rows of the packed state matrix: frame planes, counters, action boards, OR of the volume's slices,
@@ -111,32 +91,23 @@ struct EnvParams {
     int n, npad;                                // lattices, padded to 32
     int rounds;                                 // Philox rounds per volume attempt (B = 32*rounds)
     int obs_bits;                               // C*H*H
-    u32 ob_magic;                               // ceil(2^32 / obs_bits): g / obs_bits == umulhi(g, ob_magic) for g < 2^16
+    u32 ob_magic;                               // ceil(2^32 / obs_bits): g / obs_bits == umulhi(g, ob_magic) for g * obs_bits < 2^32
     u32 T, T1, T2, Tm;                          // thresholds (RNG contract)
-    u32 Tmx;                                    // max(T, Tm): the one-compare screen of generate_volume
+    u32 Tmx;                                    // max(T, Tm): the one-compare screen of draw_flip_masks
     u64 idw[3];                                 // legal-mask words with only the identity action (A-1) set
     u32 k0, k1;                                 // Philox key
     u32 env_id_base;
     int ref_mode;
+    int q_reset;                                // the queued attempts were drawn under other noise rates: discard them
+    int max_attempts;                           // all-trivial attempts after which a volume is accepted as it is (default 2^20)
     const uint8_t* lut_a;
     const uint8_t* lut_b;
     u64* state;                                 // [STATE_WORDS][npad]
+    u64* queue;                                 // [tile][kQ][kQW][kLpc]: attempt t of a lattice sits in slot t % kQ
+    u32* qtail;                                 // [npad]: first attempt index NOT yet queued
 };
 
-#ifndef DQ_LUT_KEEP
-#define DQ_LUT_KEEP 0            // 1: referee-table loads carry an L2 evict-last policy (the table competes with the observation stream for L2)
-#endif
-#if DQ_LUT_KEEP && !defined(DQ_EMU_DYNAMIC_SMEM)
-__device__ __forceinline__ int lut2(const uint8_t* lut, u32 idx) {
-    u64 pol;
-    u32 v;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(lut + (idx >> 2)), "l"(pol));
-    return (int)((v >> ((idx & 3) * 2)) & 3u);
-}
-#else
 __device__ __forceinline__ int lut2(const uint8_t* lut, u32 idx) { return (__ldg(lut + (idx >> 2)) >> ((idx & 3) * 2)) & 3; }
-#endif
 
 template <int D>
 __device__ __forceinline__ int referee_class(const EnvParams& p, u64 syn) {
@@ -144,6 +115,29 @@ __device__ __forceinline__ int referee_class(const EnvParams& p, u64 syn) {
     int c = lut2(p.lut_a, stabs_grid_to_type_index<D, 1>(syn)) & 1;
     if (p.model == DQ_MODEL_DP && p.lut_b) c |= (lut2(p.lut_b, stabs_grid_to_type_index<D, 0>(syn)) & 1) << 1;
     return c;
+}
+
+// ---- the three synchronisation primitives of the warp-specialised CTA (tests/host/cuda_emu.h serves them on the CPU) ----
+__device__ __forceinline__ void bar_sync_named(int id, int count) {          // wait until `count` threads have arrived at barrier `id`
+#ifdef DQ_EMU
+    dq_emu::named_barrier(id, count);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+__device__ __forceinline__ void bar_arrive_named(int id, int count) {        // arrive without waiting
+#ifdef DQ_EMU
+    dq_emu::named_barrier_arrive(id, count);
+#else
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+__device__ __forceinline__ void spin_pause() {
+#ifdef DQ_EMU
+    dq_emu::yield();
+#else
+    __nanosleep(20);
+#endif
 }
 
 // A fired draw (rare: p ~ 1e-2 per draw) is folded into the per-slice flip accumulators of the warp,
@@ -164,18 +158,14 @@ __device__ __noinline__ void record_event(u32* acc, int item, u32 uv, int nq_ite
 
 // The draws of ONE volume attempt of one lattice, executed by a full warp: R rounds of one Philox4x32-10 block per lane
 // (draw i = word i/B of block i%B), issued two rounds at a time so two Philox chains overlap.  Every lane thresholds its own
-// draws; the few that fire are XOR-ed into the accumulators acc[kind][slice] (record_event).  They depend on (lattice, attempt
-// index) only -- not on the lattice's state -- which is what lets warps 1.. draw them ahead of time (DQ_PREFETCH).
-// Returns (warp-uniform) whether a data-qubit draw fired.
+// draws; the few that fire are XOR-ed into the accumulators acc[kind][slice] (record_event).
 template <int D>
-__device__ __forceinline__ bool draw_flip_masks(const EnvParams& p, u32* acc, int lane, u32 env_id, u32 attempt) {
+__device__ __forceinline__ void draw_flip_masks(const EnvParams& p, u32* acc, int lane, u32 env_id, u32 attempt) {
     typedef Lat<D> L;
-    constexpr u32 FULL = 0xffffffffu;
     const int vd = p.vd, R = p.rounds, nq_items = vd * L::NQ, n_items = vd * (L::NQ + L::NS);
     const int dp = p.model == DQ_MODEL_DP;
     if (lane < 3 * kMaxVd) { acc[2 * lane] = 0; acc[2 * lane + 1] = 0; }
     __syncwarp();
-    bool evq = false;
     for (int r = 0; r < R; r += 2) {
         const Philox4 u0 = philox4x32_10(env_id, attempt, (u32)(r * 32 + lane), 0u, p.k0, p.k1);
         Philox4 u1;
@@ -199,60 +189,34 @@ __device__ __forceinline__ bool draw_flip_masks(const EnvParams& p, u32* acc, in
                 const u32 uv = (w & 4) ? hi4 : lo4;
                 const int item = ((w & 3) * R + r + (w >> 2)) * 32 + lane;      // = word*B + block
                 const u32 thr = (item < nq_items) ? p.T : p.Tm;
-                if (uv < thr) {
-                    record_event<D>(acc, item, uv, nq_items, n_items, p.T1, p.T2, dp);
-                    evq |= item < nq_items;
-                }
+                if (uv < thr) record_event<D>(acc, item, uv, nq_items, n_items, p.T1, p.T2, dp);
             } while (hits);
         }
     }
-    const bool anyq = __any_sync(FULL, evq);
     __syncwarp();
-    return anyq;
 }
 
-// One volume (Environments.py:158-176 / :216-235) for one lattice, executed by a full warp: attempts until one is
-// non-trivial.  An attempt's flip masks come from `pre` when they were drawn ahead for exactly this attempt index (pre_att),
-// else they are drawn now into `acc`.  Lane j < vd then owns slice j: a warp prefix-XOR gives the frame after every slice, one
-// shifted-XOR syndrome per lane the faulty slices.  Updates xb, zb (frame), life, attempts (all warp-uniform); returns this
-// lane's slice.
+// One volume attempt (the body of the loop at Environments.py:158-170 / :216-230) in its state-free form, executed by a
+// full warp into queue slot `dst` (word w of the entry at dst[w * kLpc]): lane j < vd owns slice j -- a warp prefix-XOR gives
+// the accumulated data-qubit flips after every slice, one shifted-XOR syndrome per lane the slice's g_j.
 template <int D>
-__device__ __forceinline__ u64 generate_volume(const EnvParams& p, u32* acc, const u32* pre, u32 pre_att, bool pre_anyq,
-                                               int lane, u32 env_id, u64& xb, u64& zb, u32& life, u32& attempts) {
+__device__ __forceinline__ void generate_attempt(const EnvParams& p, u32* acc, int lane, u32 env_id, u32 attempt, volatile u64* dst) {
     constexpr u32 FULL = 0xffffffffu;
     const int vd = p.vd;
-    bool nontrivial;
-    u64 f = 0;
-    int guard = 0;
-    do {
-        const u32* masks = acc;
-        bool anyq;
-        if (pre_att == attempts) { masks = pre; anyq = pre_anyq; }
-        else anyq = draw_flip_masks<D>(p, acc, lane, env_id, attempts);
-        u64 ex = 0, ez = 0, m = 0;
-        if (lane < vd) {
-            const u64* a64 = reinterpret_cast<const u64*>(masks);
-            ex = a64[0 * kMaxVd + lane]; ez = a64[1 * kMaxVd + lane]; m = a64[2 * kMaxVd + lane];
-        }
-        __syncwarp();
-        if (anyq) {                           // inclusive prefix XOR over slices: frame delta after slice `lane`
+    draw_flip_masks<D>(p, acc, lane, env_id, attempt);
+    u64 ex = 0, ez = 0, m = 0;
+    if (lane < vd) {
+        const u64* a64 = reinterpret_cast<const u64*>(acc);
+        ex = a64[0 * kMaxVd + lane]; ez = a64[1 * kMaxVd + lane]; m = a64[2 * kMaxVd + lane];
+    }
 #pragma unroll
-            for (int off = 1; off < kMaxVd; off <<= 1) {
-                const u64 tx = __shfl_up_sync(FULL, ex, off), tz = __shfl_up_sync(FULL, ez, off);
-                if (lane >= off) { ex ^= tx; ez ^= tz; }
-            }
-        }
-        const u64 fx = xb ^ ex, fz = zb ^ ez;
-        f = (lane < vd) ? (true_syndrome<D>(fx, fz) ^ m) : 0ull;
-        nontrivial = __any_sync(FULL, f != 0);
-        if (anyq) {
-            xb = __shfl_sync(FULL, fx, vd - 1);
-            zb = __shfl_sync(FULL, fz, vd - 1);
-        }
-        life += (u32)vd;
-        attempts += 1;
-    } while (!nontrivial && ++guard < kMaxAttemptsPerCall);
-    return f;
+    for (int off = 1; off < kMaxVd; off <<= 1) {      // inclusive prefix XOR over slices
+        const u64 tx = __shfl_up_sync(FULL, ex, off), tz = __shfl_up_sync(FULL, ez, off);
+        if (lane >= off) { ex ^= tx; ez ^= tz; }
+    }
+    if (lane < vd) dst[lane * kLpc] = true_syndrome<D>(ex, ez) ^ m;
+    if (lane == vd - 1) { dst[kMaxVd * kLpc] = ex; dst[(kMaxVd + 1) * kLpc] = ez; }
+    __syncwarp();                                      // acc is rewritten by the next attempt
 }
 
 struct Rollout {            // multi-step launch: see env_step_kernel
@@ -262,30 +226,19 @@ struct Rollout {            // multi-step launch: see env_step_kernel
 };
 
 struct Smem {
-    u64 bm[kEpc][kMaxLayers * 4];     // [lattice][layer*PW + word]: rendered bitmap of every observation layer (mirror of the state rows)
+    u64 bm[kLpc][kBmWords];           // [lattice][layer*PW + word]: rendered bitmap of every observation layer (mirror of the state rows)
     u32 stream[kStreamWords];         // the tile's observation bit stream: lattice-major concatenation of the layer bitmaps, P bits each,
-                                      // no padding = byte i of the tile's observations is bit i; kept in step with bm, so phase D is a
-                                      // straight expansion of consecutive words
-    u64 lut8[256];                    // byte -> its 8 bits as 8 bytes of 0/1 (phase D)
-    u64 fx[kEpc], fz[kEpc], fmeta[kEpc];   // phase A -> B hand-off: frame planes, counters
-    u64 sum[kEpc], acted[kEpc];       // OR of the volume's slices; OR of the action boards
-    u32 acc[kWarps][3 * kMaxVd * 2];  // per-warp flip accumulators of generate_volume
-    u32 pre[(kPrefetch || kBatchB) ? kEpc : 1][3 * kMaxVd * 2];   // DQ_PREFETCH: flip masks of attempt pre_att[lattice] of each lattice, drawn ahead
-    u32 pre_att[kEpc], att[kEpc];     // ... the attempt index they belong to; the lattice's current attempt counter
-    uint8_t pre_anyq[kEpc];
-    u32 pick_u[2][kPickGroup][kEpc];  // built-in policy: word 0 of the (lattice, step) policy block, drawn a group of steps ahead, double-buffered
-    int32_t life_out[kEpc];
-    int actbit[kEpc];                 // light step: (action layer << 16) | cell bit to set, else -1
-    uint8_t task[kEpc], task_flags[kEpc];
-    int ntask;
-    int npending[2];                  // DQ_BATCHB: lattices that still need a volume attempt after a round (by round parity)
-    u64 fsl[(DQ_BATCHB == 2 || DQ_DEFER == 2) ? kEpc : 1][kMaxVd];   // DQ_BATCHB=2: the slices of a finished volume, handed from its warp to the batched finalisation
-#if DQ_MIRROR
-    u64 cx[kEpc], cz[kEpc], cmeta[kEpc], cact[3][kEpc];   // the tile's frame planes, counters and action boards (mirror of the state rows)
-#endif
-#if DQ_DEFER
-    u32 dirty[2];                     // by step parity: lattices (bit = slot) whose span of `stream` is older than their bitmaps
-#endif
+                                      // no padding = byte i of the tile's observations is bit i; kept in step with bm
+    u64 lut8[256];                    // byte -> its 8 bits as 8 bytes of 0/1
+    // physics -> writers, slot = step & 1
+    u64 rec_f[kRing][kMaxVd][kLpc];   // the slices of a lattice's fresh volume
+    int rec_actbit[kRing][kLpc];      // light step: (action layer << 16) | cell bit to set, else -1
+    u32 rec_volmask[kRing];           // lattices (bit = lane) that drew a fresh volume
+    // physics <-> generators
+    u64 q[kQ][kQW][kLpc];             // rollouts: the tile's volume queues (a single-step launch works on the device-memory copy)
+    u32 head[kLpc], tail[kLpc];       // attempt indices: next to pop (= the lattice's attempt counter) / first not yet queued
+    u32 quit;                         // the physics warp has popped its last volume of the launch
+    __align__(16) u32 acc[kGens][3 * kMaxVd * 2];   // per-generator-warp flip accumulators (read back as 64-bit words)
 };
 
 // 32 bits of the tile's observation bit stream starting at bit `o` of (lattice, layer): the stream is the concatenation of the
@@ -302,7 +255,7 @@ __device__ __forceinline__ u32 gather32(const Smem& sm, int lat, int layer, int 
         v &= (1u << n1) - 1u;
         int l2 = layer + 1, lat2 = lat;
         if (l2 == C) { l2 = 0; lat2 = lat + 1; }
-        if (lat2 < kEpc) v |= reinterpret_cast<const u32*>(&sm.bm[lat2][l2 * PW])[0] << n1;
+        if (lat2 < kLpc) v |= reinterpret_cast<const u32*>(&sm.bm[lat2][l2 * PW])[0] << n1;
     }
     return v;
 }
@@ -313,7 +266,7 @@ __device__ __forceinline__ u32 stream_word(const Smem& sm, const EnvParams& p, i
     const int g = wi * 32;
     const int lat = (int)__umulhi((u32)g, p.ob_magic), r = g - lat * p.obs_bits;
     const int layer = r / Lat<D>::P, o = r - layer * Lat<D>::P;
-    return lat < kEpc ? gather32<D>(sm, lat, layer, o, C) : 0u;
+    return lat < kLpc ? gather32<D>(sm, lat, layer, o, C) : 0u;
 }
 
 __device__ __forceinline__ uint4 expand16(const Smem& sm, u32 h) {     // low 16 bits -> 16 bytes of 0/1 (two table lookups)
@@ -322,58 +275,18 @@ __device__ __forceinline__ uint4 expand16(const Smem& sm, u32 h) {     // low 16
     return make_uint4(a.x, a.y, b.x, b.y);
 }
 
-__device__ __forceinline__ void store_obs16(uint8_t* dst, const uint4 v) {
-#if DQ_STREAM_OBS
-    __stcs(reinterpret_cast<uint4*>(dst), v);
-#else
-    *reinterpret_cast<uint4*>(dst) = v;
-#endif
-}
+// Observation bytes are never read back by this kernel: evict-first stores (STG.E.EF.128) keep the ring of them that streams
+// through L2 from evicting the 4 MB joint referee table.
+__device__ __forceinline__ void store_obs16(uint8_t* dst, const uint4 v) { __stcs(reinterpret_cast<uint4*>(dst), v); }
 
-#if DQ_DEFER == 2
-// Barrier over the `count` threads of the CTA that name barrier `id` (1..15; 0 is __syncthreads).
-__device__ __forceinline__ void named_barrier(int id, int count) {
-#ifdef DQ_EMU_DYNAMIC_SMEM
-    dq_emu::named_barrier(id, count);
-#else
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-#endif
-}
-
-// DQ_DEFER=2: the layer bitmaps of the lattices in dirty mask `dm` (fresh volumes of the step being written), one (lattice, layer)
-// pair per thread: syndrome layers from the slices phase B left in fsl, action layers cleared.  Executed by threads
-// [0, nthr) of the caller's group; the caller synchronises the group before anyone reads the bitmaps.
-template <int D>
-__device__ __forceinline__ void render_dirty(Smem& sm, const EnvParams& p, u32 dm, int t, int nthr, int env0, int C) {
-    typedef Lat<D> L;
-    constexpr int PW = L::PW;
-    const size_t np = (size_t)p.npad;
-    const int items = __popc(dm) * C;
-    for (int i = t; i < items; i += nthr) {
-        const int k = i / C, c = i - k * C;
-        const int slot = select64((u64)dm, k);
-        const int e = env0 + slot;
-        u64 w[PW];
-        syndrome_layer_bitmap<D>(sm.fsl[slot][min(c, kMaxVd - 1)], w);
-#pragma unroll
-        for (int j = 0; j < PW; ++j) {
-            const u64 v = c < p.vd ? w[j] : 0ull;               // an action layer has no marker cells
-            sm.bm[slot][c * PW + j] = v;
-            p.state[(ROW_BM + c * PW + j) * np + e] = v;
-        }
-    }
-}
-#endif
-
-#if DQ_DEFER
-// DQ_DEFER: word `wi` of the bit stream as phase D needs it.  Phase B no longer refreshes the span of a lattice it re-rendered; it
-// sets the lattice's bit in the step's dirty mask `dm`, and the thread that expands a word overlapping such a lattice gathers
-// it from the bitmaps here and puts it back (every word has one owner per pass; the bitmaps are not written during phase D).
+// Word `wi` of the bit stream as the expansion needs it.  A lattice whose bitmaps changed (bit set in `dm`: fresh volume) has a
+// stale span; the thread that expands a word overlapping such a lattice gathers it from the bitmaps and puts it back (every word
+// has one owner per pass; the bitmaps are not written during the pass).
 template <int D>
 __device__ __forceinline__ u32 fresh_word(Smem& sm, const EnvParams& p, int wi, u32 dm, int C) {
     if (dm) {
-        const u32 la = __umulhi((u32)(wi * 32), p.ob_magic), lb = min(__umulhi((u32)(wi * 32 + 31), p.ob_magic), (u32)(kEpc - 1));
-        if (((dm >> la) | (dm >> lb)) & 1u) {       // la <= lb < kEpc: the word's bits past the tile's last lattice are zero either way
+        const u32 la = __umulhi((u32)(wi * 32), p.ob_magic), lb = min(__umulhi((u32)(wi * 32 + 31), p.ob_magic), (u32)(kLpc - 1));
+        if (((dm >> la) | (dm >> lb)) & 1u) {       // la <= lb < kLpc
             const u32 v = stream_word<D>(sm, p, wi, C);
             sm.stream[wi] = v;
             return v;
@@ -381,7 +294,6 @@ __device__ __forceinline__ u32 fresh_word(Smem& sm, const EnvParams& p, int wi, 
     }
     return sm.stream[wi];
 }
-#endif
 
 // Legal-move mask words of one lattice (Environments.py:238-271 in closed form): qubits touching the summed faulty syndrome
 // or next to an already acted-on qubit, in every action layer, plus the identity.
@@ -400,9 +312,9 @@ __device__ __forceinline__ void legal_words(const EnvParams& p, u64 summed, u64 
     }
 }
 
-// Phase D: the tile's observation bytes.  Thread per 32-bit word of the tile's observation bit stream: expanded to 32 bytes of
-// 0/1, two 128-bit stores (the tile's 16*C*H*H bytes start 16-byte aligned whenever the caller's buffer is).  Executed by
-// threads [first, first + nthr) of the CTA.
+// The tile's observation bytes.  Thread per 32-bit word of the tile's observation bit stream: expanded to 32 bytes of
+// 0/1, two 128-bit stores (the tile's 32*C*H*H bytes start 16-byte aligned whenever the caller's buffer is).  Executed by
+// `nthr` threads, t = 0..nthr-1.
 __device__ __noinline__ void write_observations_unaligned(const Smem& sm, uint8_t* out, int full, int align, int t, int nthr) {
     for (int g = t * 32; g < full; g += nthr * 32) {        // rare: 64-bit stores at 8-byte alignment, else bytes
         const u32 word = sm.stream[g >> 5];
@@ -418,30 +330,6 @@ __device__ __noinline__ void write_observations_unaligned(const Smem& sm, uint8_
         }
     }
 }
-#if !DQ_DEFER
-__device__ __forceinline__ void write_observations(const Smem& sm, const EnvParams& p, uint8_t* obs, int env0, int nvalid,
-                                                   int t, int nthr) {
-    const int vbytes = nvalid * p.obs_bits;
-    uint8_t* out = obs + (size_t)env0 * p.obs_bits;
-    const int align = (int)(reinterpret_cast<uintptr_t>(out) & 15);
-    const int full = vbytes & ~31;                                                // whole 32-byte groups
-    if (align == 0) {
-#pragma unroll 2
-        for (int g = t * 32; g < full; g += nthr * 32) {
-            const u32 word = sm.stream[g >> 5];
-            store_obs16(out + g, expand16(sm, word));
-            store_obs16(out + g + 16, expand16(sm, word >> 16));
-        }
-    } else {
-        write_observations_unaligned(sm, out, full, align, t, nthr);
-    }
-    if (t == 0 && full < vbytes) {                                                 // the tile's last, partial group
-        const u32 word = sm.stream[full >> 5];
-        for (int b = 0; b < vbytes - full; ++b) out[full + b] = (uint8_t)((word >> b) & 1u);
-    }
-}
-#else
-// DQ_DEFER form: the same expansion, every word read through fresh_word (dm = the dirty mask of the step being written)
 template <int D>
 __device__ __forceinline__ void write_observations(Smem& sm, const EnvParams& p, uint8_t* obs, int env0, int nvalid,
                                                    int t, int nthr, u32 dm, int C) {
@@ -466,7 +354,6 @@ __device__ __forceinline__ void write_observations(Smem& sm, const EnvParams& p,
         for (int b = 0; b < vbytes - full; ++b) out[full + b] = (uint8_t)((word >> b) & 1u);
     }
 }
-#endif
 
 template <int D, bool RESET>
 __global__ void __launch_bounds__(kThreads, DQ_MIN_BLOCKS)
@@ -481,149 +368,82 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int env0 = blockIdx.x * kEpc;
+    const int env0 = blockIdx.x * kLpc;
     const int C = p.vd + p.layers;
-    const int nvalid = max(0, min(kEpc, p.n - env0));      // a tile past the last lattice (n padded to 32) has none
+    const int nvalid = max(0, min(kLpc, p.n - env0));
     const size_t np = (size_t)p.npad;
     // built-in policy: every CTA reads the step index before its first barrier; the last CTA to finish advances it
     const u32 step0 = policy_ctr ? *reinterpret_cast<volatile u32*>(policy_ctr) : 0u;
+    // A rollout keeps the tile's volume queues in shared memory for the launch; a single step pops and refills the device-memory copy in place.
+    const bool q_in_smem = ro.nsteps > 1;
+    u64* const gq = p.queue + (size_t)blockIdx.x * (kQ * kQW * kLpc);
+    volatile u64* const qp = q_in_smem ? &sm.q[0][0][0] : gq;
 
-    // The rendered layer bitmaps and the summed syndrome of the tile's lattices live in shared memory for the whole launch
-    // (and in the state rows, kept in step): a step only re-renders what it changes.
-    for (int i0 = 0; i0 < C * PW * kEpc; i0 += 6 * kThreads) {        // the loads of a batch are in flight together
-        u64 w6[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            const int i = min(i0 + j * kThreads + tid, C * PW * kEpc - 1), row = i / kEpc;
-            w6[j] = p.state[(ROW_BM + row) * np + env0 + (i - row * kEpc)];
-        }
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            const int i = i0 + j * kThreads + tid, row = i / kEpc;
-            if (i < C * PW * kEpc) sm.bm[i - row * kEpc][row] = w6[j];
-        }
-    }
-    if (tid < kEpc) {
-        sm.sum[tid] = p.state[ROW_SUM * np + env0 + tid];
-        sm.pre_att[tid] = kNoAttempt;
-        if (kPrefetch) sm.att[tid] = (u32)(p.state[ROW_META * np + env0 + tid] >> 32) & 0x7FFFFFFFu;
-#if DQ_MIRROR
-        if (!RESET) {
-            sm.cx[tid] = p.state[ROW_XB * np + env0 + tid];
-            sm.cz[tid] = p.state[ROW_ZB * np + env0 + tid];
-            sm.cmeta[tid] = p.state[ROW_META * np + env0 + tid];
-#pragma unroll
-            for (int l = 0; l < 3; ++l) sm.cact[l][tid] = l < p.layers ? p.state[(ROW_ACT + l) * np + env0 + tid] : 0ull;
-        }
-#endif
-#if DQ_DEFER
-        if (tid < 2) sm.dirty[tid] = 0;
-#endif
-    }
-    // built-in policy: the random word of a pick depends only on (lattice, step index), so it never has to sit on the
-    // step's dependent chain: the words of the first kPickGroup steps are drawn here, those of every later group by warps 1..
-    // one group ahead (below), into the buffer warp 0 is not reading
-    if (!RESET && policy_ctr && tid < kPickGroup * kEpc) {
-        const int ahead = tid / kEpc, lat = tid - ahead * kEpc;
-        if (ahead < ro.nsteps)
-            sm.pick_u[0][ahead][lat] = philox4x32_10(p.env_id_base + (u32)(env0 + lat), step0 + (u32)ahead, 0u, 1u, p.k0, p.k1).x;
+    // ---- prologue: layer bitmaps, expansion table, queue and its counters
+    for (int i = tid; i < C * PW * kLpc; i += kThreads) {
+        const int row = i / kLpc, l = i - row * kLpc;
+        sm.bm[l][row] = p.state[(ROW_BM + row) * np + env0 + l];
     }
     for (int i = tid; i < 256; i += kThreads)
         sm.lut8[i] = (u64)((((u32)i & 0xFu) * 0x00204081u) & 0x01010101u) | ((u64)((((u32)i >> 4) * 0x00204081u) & 0x01010101u) << 32);
-    __syncthreads();
-    for (int wi = tid; wi < (kEpc * p.obs_bits + 31) >> 5; wi += kThreads) sm.stream[wi] = stream_word<D>(sm, p, wi, C);
+    if (q_in_smem) {
+        u64* sq = &sm.q[0][0][0];
+        for (int i = tid; i < kQ * kQW * kLpc; i += kThreads) sq[i] = gq[i];
+    }
+    if (tid < kLpc) {
+        const u32 head = (u32)(p.state[ROW_META * np + env0 + tid] >> 32) & 0x7FFFFFFFu;
+        u32 tail = p.qtail[env0 + tid];
+        if (p.q_reset || tail - head > (u32)kQ) tail = head;      // nothing usable queued (first launch, injected state, new noise rates)
+        sm.head[tid] = head; sm.tail[tid] = tail;
+        if (tid == 0) sm.quit = 0;
+    }
     __syncthreads();
 
-    // A rollout (dq_env_rollout_random) runs ro.nsteps steps of this tile's lattices in one launch: lattices are independent,
-    // so a tile never waits for the slowest tile of the previous step.  Step s writes observation slot (first_slot+s) % slots
-    // and row s of the per-step outputs.  A single step is the nsteps == 1 case.
-    int ring_slot = ro.first_slot;
-    size_t oo = 0;
-    u64 mw[3] = {0, 0, 0};              // warp 0, lane = lattice: legal-move mask after the latest step (phase C -> next phase A)
-    uint8_t* obs_prev = nullptr;        // the previous step's observation slot: written while warp 0 runs this step's phase A
-    int gphase = 0, gbuf = 0;           // rs % kPickGroup, (rs / kPickGroup) & 1
-    for (int rs = 0; rs < ro.nsteps; ++rs, oo += ro.out_stride, ring_slot = (ring_slot + 1 == ro.slots) ? 0 : ring_slot + 1) {
-    uint8_t* const obs = obs0 ? obs0 + (size_t)ring_slot * ro.slot_bytes : nullptr;
-    float* const reward = reward0 ? reward0 + oo : nullptr;
-    uint8_t* const done_out = done0 ? done0 + oo : nullptr;
-    int32_t* const lifetime = lifetime0 ? lifetime0 + oo : nullptr;
-    int32_t* const actions_out = actions_out0 ? actions_out0 + oo : nullptr;
-    u64* const legal = legal0 ? legal0 + oo * p.W : nullptr;
-
-    // ---- phase A: warp 0, lane = lattice.  Warps 1.. meanwhile write the PREVIOUS step's observations (phase D): phase A does
-    //      not touch the bitmaps -- the cell a light step adds is applied after the barrier.
-    if (warp != 0) {
-        if (!RESET && policy_ctr && gphase == 0 && rs + kPickGroup < ro.nsteps && tid - 32 < kPickGroup * kEpc) {
-            // policy words of the NEXT group of steps -> the other buffer (last read two barriers ago, next read after this step's barriers)
-            const int ahead = (tid - 32) / kEpc, lat = (tid - 32) - ahead * kEpc, s = rs + kPickGroup + ahead;
-            if (s < ro.nsteps)
-                sm.pick_u[gbuf ^ 1][ahead][lat] = philox4x32_10(p.env_id_base + (u32)(env0 + lat), step0 + (u32)s, 0u, 1u, p.k0, p.k1).x;
-        }
-#if !DQ_DEFER
-        if (obs_prev) write_observations(sm, p, obs_prev, env0, nvalid, tid - 32, kThreads - 32);
-#else
-        {
-            const u32 dm = sm.dirty[(rs & 1) ^ 1];           // the previous step's fresh volumes (0 at the first step)
-#if DQ_DEFER == 2
-            if (dm) {               // block-uniform
-                render_dirty<D>(sm, p, dm, tid - 32, kThreads - 32, env0, C);
-                if (obs_prev) named_barrier(1, kThreads - 32);
-            }
-#endif
-            if (obs_prev) write_observations<D>(sm, p, obs_prev, env0, nvalid, tid - 32, kThreads - 32, dm, C);
-        }
-#endif
-        if (kPrefetch && !RESET && ro.nsteps > 1) {
-            // draw ahead: lattices whose prepared masks are not those of their next attempt (consumed, or never drawn).  This
-            // window (warp 0 runs phase C and A) is separated from phase B, which reads them, by the block barriers.
-            int done = 0;
-            for (int lat = warp - 1; lat < nvalid && done < kRefill; lat += kWarps - 1) {
-                const u32 want = sm.att[lat];
-                if (sm.pre_att[lat] == want) continue;                     // warp-uniform
-                const bool anyq = draw_flip_masks<D>(p, sm.pre[lat], lane, p.env_id_base + (u32)(env0 + lat), want);
-                if (lane == 0) { sm.pre_att[lat] = want; sm.pre_anyq[lat] = anyq ? 1 : 0; }
-                ++done;
-            }
-        }
-    } else {
+    if (warp == 0) {
+        // ================================================================== PHYSICS: lane = lattice
         const int e = env0 + lane;
-        const bool mine = lane < kEpc, live = lane < nvalid;
-        u64 xb = 0, zb = 0, meta = 0, act[3] = {0, 0, 0};
-        u32 flags = 0;
-        if (mine) {
-#if !DQ_MIRROR
-            meta = p.state[ROW_META * np + e];
-#else
-            meta = RESET ? p.state[ROW_META * np + e] : sm.cmeta[lane];
-#endif
+        const bool live = lane < nvalid;
+        const u32 env_id = p.env_id_base + (u32)e;
+        volatile u32* const vtail = sm.tail;
+        volatile u32* const vhead = sm.head;
+        u64 xb = 0, zb = 0, act[3] = {0, 0, 0};
+        const u64 meta0 = p.state[ROW_META * np + e];
+        u64 summed = p.state[ROW_SUM * np + e];
+        u32 life = (u32)meta0, attempts = (u32)(meta0 >> 32) & 0x7FFFFFFFu, dn = (u32)(meta0 >> 63);
+        if (!RESET) {
+            xb = p.state[ROW_XB * np + e];
+            zb = p.state[ROW_ZB * np + e];
+#pragma unroll
+            for (int l = 0; l < 3; ++l) if (l < p.layers) act[l] = p.state[(ROW_ACT + l) * np + e];
+        }
+        u64 mw[3] = {0, 0, 0};              // legal-move mask after the latest step (feeds the next built-in pick)
+        if (!RESET && policy_ctr) legal_words<D>(p, summed, act[0] | act[1] | act[2], mw);
+        // built-in policy: the random word of a pick depends only on (lattice, step index); the next step's word is drawn
+        // beside this step's dependent chain
+        u32 pick_u = (!RESET && policy_ctr) ? philox4x32_10(env_id, step0, 0u, 1u, p.k0, p.k1).x : 0u;
+
+        size_t oo = 0;
+        for (int rs = 0; rs < ro.nsteps; ++rs, oo += ro.out_stride) {
+            const int r = rs & (kRing - 1);
+            u32 pick_next = 0;
+            if (!RESET && policy_ctr && rs + 1 < ro.nsteps) pick_next = philox4x32_10(env_id, step0 + (u32)rs + 1u, 0u, 1u, p.k0, p.k1).x;
+            u32 flags = 0, dn_out = 0;
             int actbit = -1;
+            float rw = 0.f;
             if (!RESET) {
                 int a = (live && actions) ? actions[e] : p.A - 1;
-#if !DQ_MIRROR
-                xb = p.state[ROW_XB * np + e];
-                zb = p.state[ROW_ZB * np + e];
-#pragma unroll
-                for (int l = 0; l < 3; ++l) if (l < p.layers) act[l] = p.state[(ROW_ACT + l) * np + e];
-#else
-                xb = sm.cx[lane];
-                zb = sm.cz[lane];
-#pragma unroll
-                for (int l = 0; l < 3; ++l) act[l] = sm.cact[l][lane];
-#endif
                 if (policy_ctr && live) {
-                    // built-in random-legal policy (dq_env_step_random): the pick dq_policy_random_legal would make
-                    // on this lattice's current legal set, with the step index read from device memory
-                    if (rs == 0) legal_words<D>(p, sm.sum[lane], act[0] | act[1] | act[2], mw);   // later steps: phase C of the previous step left it
+                    // built-in random-legal policy: the pick dq_policy_random_legal would make on this lattice's current legal set
                     const int ib = p.A - 1;
-                    const int cnt = popc64(mw[0]) + popc64(mw[1]) + popc64(mw[2]);
-                    int pick = (int)mulhi32(sm.pick_u[gbuf][gphase][lane], (u32)cnt);              // < cnt (cnt >= 1: the identity is always legal)
                     const int c0 = popc64(mw[0]), c1 = popc64(mw[1]);
+                    const int cnt = c0 + c1 + popc64(mw[2]);
+                    int pick = (int)mulhi32(pick_u, (u32)cnt);              // < cnt (cnt >= 1: the identity is always legal)
                     u64 word = mw[0];
                     int wbase = 0;
                     if (pick >= c0 + c1) { pick -= c0 + c1; word = mw[2]; wbase = 128; }
                     else if (pick >= c0) { pick -= c0; word = mw[1]; wbase = 64; }
                     a = cnt > 0 ? wbase + select64(word, pick) : ib;
-                    if (actions_out) actions_out[e] = a;
+                    if (actions_out0) actions_out0[oo + e] = a;
                 }
                 if (a < 0 || a >= p.A) a = p.A - 1;
                 const bool ident = (a == p.A - 1);
@@ -641,378 +461,180 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                 if (fz) zb ^= bit;
                 const u64 syn = true_syndrome<D>(xb, zb);
                 const int label = homology_label<D>(xb, zb);
-                u32 dn = (u32)(meta >> 63);
-                float rw = 0.f;
                 if (label == 0 && syn == 0) rw = 1.f;
                 else if (live && referee_class<D>(p, syn) != label) dn = 1;
                 if (!heavy) {
                     if (layer == 0) act[0] |= bit; else if (layer == 1) act[1] |= bit; else act[2] |= bit;
                     actbit = (layer << 16) | ((2 * qr + 1) * H + 2 * qc + 1);
                 }
-                meta = (meta & ~(1ull << 63)) | ((u64)dn << 63);
-                if (live) {
-                    if (reward) reward[e] = rw;
-                    if (done_out) done_out[e] = (uint8_t)dn;
-                    flags = (heavy ? 1u : 0u) | ((dn && auto_reset) ? 2u : 0u);   // padding lattices never draw volumes
-                }
-                sm.life_out[lane] = (int32_t)(u32)meta;
-                if (!flags) {                  // light step: the frame and the touched action board go back now
-                    p.state[ROW_XB * np + e] = xb;
-                    p.state[ROW_ZB * np + e] = zb;
-                    p.state[ROW_META * np + e] = meta;
-                    if (!ident) p.state[(ROW_ACT + layer) * np + e] = layer == 0 ? act[0] : (layer == 1 ? act[1] : act[2]);
-#if DQ_MIRROR
-                    sm.cx[lane] = xb; sm.cz[lane] = zb; sm.cmeta[lane] = meta;
-                    sm.cact[0][lane] = act[0]; sm.cact[1][lane] = act[1]; sm.cact[2][lane] = act[2];
-#endif
-                }
+                dn_out = dn;
+                if (live) flags = (heavy ? 1u : 0u) | ((dn && auto_reset) ? 2u : 0u);     // padding lattices never draw volumes
             } else if (live) {
                 flags = 2u;               // reset keeps only the attempt counter (the position in the random stream)
             }
-            sm.fx[lane] = xb; sm.fz[lane] = zb; sm.fmeta[lane] = meta;
-            sm.acted[lane] = act[0] | act[1] | act[2];
-            sm.actbit[lane] = flags ? -1 : actbit;
-        }
-        const u32 tmask = __ballot_sync(FULL, flags != 0);
-        if (flags) {
-            const int pos = __popc(tmask & ((1u << lane) - 1));
-            sm.task[pos] = (uint8_t)lane; sm.task_flags[pos] = (uint8_t)flags;
-        }
-        if (lane == 0) sm.ntask = __popc(tmask);
-    }
-    __syncthreads();
+            int32_t life_out = (int32_t)life;
 
-#if DQ_DEFER
-    if (tid == 0) sm.dirty[(rs & 1) ^ 1] = 0;  // the previous step's mask: phase D consumed it before the barrier above
-#endif
-    if (tid < kEpc) {                          // a light step's action lights one more cell of its action layer
-        const int ab = sm.actbit[tid];
-        if (ab >= 0) {
-            const int pos = ab & 0xFFFF, row = (p.vd + (ab >> 16)) * PW + (pos >> 6);
-            const u64 wv = sm.bm[tid][row] | (1ull << (pos & 63));
-            sm.bm[tid][row] = wv;
-            p.state[(ROW_BM + row) * np + env0 + tid] = wv;
-            const int sb = tid * p.obs_bits + (p.vd + (ab >> 16)) * L::P + pos;
-            atomicOr(&sm.stream[sb >> 5], 1u << (sb & 31));
-        }
-    }
-    // ---- phase B: fresh volume(s) for the flagged lattices, then their layer bitmaps and stream spans
-    if constexpr (!kBatchB) {
-    // warp per flagged lattice
-        for (int t = warp; t < sm.ntask; t += kWarps) {
-            const int slot = sm.task[t], fl = sm.task_flags[t];
-            const u32 env_id = p.env_id_base + (u32)(env0 + slot);
-            const int e = env0 + slot;
-            u64 bx = sm.fx[slot], bz = sm.fz[slot];
-            const u64 bm0 = sm.fmeta[slot];
-            u32 life = (u32)bm0, attempts = (u32)(bm0 >> 32) & 0x7FFFFFFFu, dn = (u32)(bm0 >> 63);
-            u64 f = 0;
-            int32_t lo = (int32_t)life;
-            // bit 0 of fl: heavy step (volume on the current frame), bit 1: restart of a finished lattice (volume on a clean frame), in
-            // that order; one copy of the generator serves both
-#pragma unroll 1
-            for (int todo = fl; todo; ) {
-                const bool restart = !(todo & 1);
-                if (restart) { bx = 0; bz = 0; life = 0; dn = 0; }
-                f = generate_volume<D>(p, sm.acc[warp], sm.pre[kPrefetch ? slot : 0], sm.pre_att[slot], sm.pre_anyq[slot] != 0,
-                                       lane, env_id, bx, bz, life, attempts);
-                if (!restart) lo = (int32_t)life;
-                todo = restart ? 0 : (todo & 2);
+            // the record slot of this step must have been read by the writers (they run at most kRing steps behind)
+            if (rs >= kRing) bar_sync_named(BAR_EMPTY + r, 32 + kWriterThreads);
+
+            // ---- fresh volume(s): bit 0 of todo = heavy step (volume on the current frame), bit 1 = restart of a finished lattice
+            // (volume on a clean frame), in that order.  Each pass pops one queued attempt for every lane that still needs one.
+            u32 todo = flags;
+            int guard = 0;
+            u64 sum_new = 0;
+            if (todo == 2u) { xb = 0; zb = 0; life = 0; dn = 0; }
+            while (__any_sync(FULL, todo != 0)) {
+                if (todo) {
+                    while (vtail[lane] == attempts) spin_pause();         // (rare) the generators have not queued this attempt yet
+                    __threadfence_block();
+                    volatile u64* const ent = qp + (size_t)(attempts & (u32)(kQ - 1)) * (kQW * kLpc) + lane;
+                    const u64 s0 = true_syndrome<D>(xb, zb);
+                    u64 nz = 0;
+#pragma unroll
+                    for (int j = 0; j < kMaxVd; ++j) {
+                        if (j < p.vd) {
+                            const u64 fj = ent[j * kLpc] ^ s0;
+                            nz |= fj;
+                            sm.rec_f[r][j][lane] = fj;
+                        }
+                    }
+                    xb ^= ent[kMaxVd * kLpc];
+                    zb ^= ent[(kMaxVd + 1) * kLpc];
+                    life += (u32)p.vd;
+                    attempts += 1;
+                    if (nz != 0 || ++guard >= p.max_attempts) {
+                        sum_new = nz;
+                        guard = 0;
+                        if (todo & 1u) {
+                            life_out = (int32_t)life;
+                            todo &= ~1u;
+                            if (todo) { xb = 0; zb = 0; life = 0; dn = 0; }
+                        } else todo = 0;
+                    }
+                    __threadfence_block();                                // the entry has been read before its slot is offered for refill
+                    vhead[lane] = attempts;
+                }
             }
-            u64 summed = f;                                 // lanes >= vd hold 0
-            summed |= __shfl_xor_sync(FULL, summed, 1);
-            summed |= __shfl_xor_sync(FULL, summed, 2);
-            summed |= __shfl_xor_sync(FULL, summed, 4);
-            if (lane == 0) {
-                p.state[ROW_XB * np + e] = bx;
-                p.state[ROW_ZB * np + e] = bz;
-                p.state[ROW_META * np + e] = meta_pack(life, attempts, dn);
-                p.state[ROW_SUM * np + e] = summed;
-                sm.sum[slot] = summed; sm.acted[slot] = 0;
-                if (kPrefetch) sm.att[slot] = attempts;
-                if (!RESET) sm.life_out[slot] = lo;
-#if DQ_MIRROR
+            const bool vol = flags != 0;
+            if (vol) { act[0] = 0; act[1] = 0; act[2] = 0; summed = sum_new; }
+            sm.rec_actbit[r][lane] = vol ? -1 : actbit;
+            const u32 vm = __ballot_sync(FULL, vol);
+            if (lane == 0) sm.rec_volmask[r] = vm;
+            __threadfence_block();
+            bar_arrive_named(BAR_FULL + r, 32 + kWriterThreads);
+
+            // ---- lifetime, legal mask, the small outputs
+            if (live) {
                 if (!RESET) {
-                    sm.cx[slot] = bx; sm.cz[slot] = bz; sm.cmeta[slot] = meta_pack(life, attempts, dn);
-                    sm.cact[0][slot] = 0; sm.cact[1][slot] = 0; sm.cact[2][slot] = 0;
+                    if (reward0) reward0[oo + e] = rw;
+                    if (done0) done0[oo + e] = (uint8_t)dn_out;
+                    if (lifetime0) lifetime0[oo + e] = life_out;
                 }
-#endif
-#if DQ_DEFER
-                atomicOr(&sm.dirty[rs & 1], 1u << slot);
-#endif
             }
-#if DQ_DEFER == 2
-            if (lane < kMaxVd) sm.fsl[slot][lane] = f;          // lanes >= vd hold 0; rendered in the next window (render_dirty)
-#endif
-            if (lane < p.layers) p.state[(ROW_ACT + lane) * np + e] = 0;     // not deferred: phase A of the next step may write this row
-            // render: lane j < vd holds slice j and builds that layer's bitmap in registers; lanes vd..C-1 clear the action layers
-            if (DQ_DEFER != 2 && lane < C) {
-                u64 w[PW];
-                syndrome_layer_bitmap<D>(f, w);
+            if (legal0 || policy_ctr) {
+                legal_words<D>(p, summed, act[0] | act[1] | act[2], mw);
+                if (legal0 && live) {
 #pragma unroll
-                for (int i = 0; i < PW; ++i) {
-                    const u64 v = lane < p.vd ? w[i] : 0ull;
-                    sm.bm[slot][lane * PW + i] = v;
-                    p.state[(ROW_BM + lane * PW + i) * np + e] = v;
+                    for (int i = 0; i < 3; ++i)
+                        if (i < p.W) legal0[(oo + e) * p.W + i] = mw[i];
                 }
             }
-            __syncwarp();
-            // this lattice's span of the tile's bit stream; its first and last word are shared with the neighbouring lattices, which
-            // other warps may be re-rendering right now: only this lattice's bits of those are replaced, atomically
-            // (DQ_DEFER: left to phase D, see fresh_word)
-            if constexpr (!kDefer) {
-                const int b0 = slot * p.obs_bits, b1 = b0 + p.obs_bits;
-                for (int wi = (b0 >> 5) + lane; wi <= ((b1 - 1) >> 5); wi += 32) {
-                    const int lo = max(b0 - wi * 32, 0), hi = min(b1 - wi * 32, 32);          // bits [lo, hi) of the word are this lattice's
-                    const u32 mask = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-                    const u32 v = stream_word<D>(sm, p, wi, C);
-                    if (mask == 0xffffffffu) sm.stream[wi] = v;
-                    else { atomicAnd(&sm.stream[wi], ~mask); atomicOr(&sm.stream[wi], v & mask); }
-                }
-            }
+            pick_u = pick_next;
         }
-    } else if constexpr (DQ_BATCHB == 2) {
-    // DQ_BATCHB=2.  Stage 1, warp per flagged lattice: the volume(s) exactly as in the default build (attempts retried inside the
-    // warp, no block barrier), but nothing of the few-lane work that follows: the finished slices, frame and counters are left in
-    // shared memory.  Stage 2, after one block barrier, lane = (lattice of a group of four, slice): state rows, layer bitmaps,
-    // action boards and stream spans of four lattices in one pass.
-    for (int t = warp; t < sm.ntask; t += kWarps) {
-        const int slot = sm.task[t], fl = sm.task_flags[t];
-        const u32 env_id = p.env_id_base + (u32)(env0 + slot);
-        u64 bx = sm.fx[slot], bz = sm.fz[slot];
-        const u64 bm0 = sm.fmeta[slot];
-        u32 life = (u32)bm0, attempts = (u32)(bm0 >> 32) & 0x7FFFFFFFu, dn = (u32)(bm0 >> 63);
-        u64 f = 0;
-        int32_t lo = (int32_t)life;
-#pragma unroll 1
-        for (int todo = fl; todo; ) {
-            const bool restart = !(todo & 1);
-            if (restart) { bx = 0; bz = 0; life = 0; dn = 0; }
-            f = generate_volume<D>(p, sm.acc[warp], sm.pre[0], kNoAttempt, false, lane, env_id, bx, bz, life, attempts);
-            if (!restart) lo = (int32_t)life;
-            todo = restart ? 0 : (todo & 2);
-        }
-        if (lane < kMaxVd) sm.fsl[slot][lane] = f;               // lanes >= vd hold 0
-        if (lane == 0) {
-            sm.fx[slot] = bx; sm.fz[slot] = bz; sm.fmeta[slot] = meta_pack(life, attempts, dn);
-            if (!RESET) sm.life_out[slot] = lo;
-        }
-    }
-    __syncthreads();
-    {
-        const int ntask = sm.ntask;
-        for (int c = warp; c * 4 < ntask; c += kWarps) {
-            const int j = lane >> 3, sl = lane & 7, t = c * 4 + j;
-            const bool complete = t < ntask;
-            const int slot = complete ? sm.task[t] : 0;
-            const int e = env0 + slot;
-            const u64 f = complete ? sm.fsl[slot][sl] : 0ull;
-            u64 summed = f;
-            summed |= __shfl_xor_sync(FULL, summed, 1, 8);
-            summed |= __shfl_xor_sync(FULL, summed, 2, 8);
-            summed |= __shfl_xor_sync(FULL, summed, 4, 8);
-            if (complete) {
-                if (sl == 0) {
-                    p.state[ROW_XB * np + e] = sm.fx[slot];
-                    p.state[ROW_ZB * np + e] = sm.fz[slot];
-                    p.state[ROW_META * np + e] = sm.fmeta[slot];
-                    p.state[ROW_SUM * np + e] = summed;
-                    sm.sum[slot] = summed; sm.acted[slot] = 0;
-#if DQ_MIRROR
-                    if (!RESET) {
-                        sm.cx[slot] = sm.fx[slot]; sm.cz[slot] = sm.fz[slot]; sm.cmeta[slot] = sm.fmeta[slot];
-                        sm.cact[0][slot] = 0; sm.cact[1][slot] = 0; sm.cact[2][slot] = 0;
-                    }
-#endif
-                }
-                u64 w[PW];
-                syndrome_layer_bitmap<D>(f, w);
-                if (sl < p.vd) {
+        // the lattice's state goes back to its rows
+        p.state[ROW_XB * np + e] = xb;
+        p.state[ROW_ZB * np + e] = zb;
+        p.state[ROW_META * np + e] = meta_pack(life, attempts, dn);
+        p.state[ROW_SUM * np + e] = summed;
 #pragma unroll
-                    for (int i = 0; i < PW; ++i) {
-                        sm.bm[slot][sl * PW + i] = w[i];
-                        p.state[(ROW_BM + sl * PW + i) * np + e] = w[i];
-                    }
-                }
-                if (sl < p.layers) {                           // the action boards and their layers are cleared
-                    p.state[(ROW_ACT + sl) * np + e] = 0;
-#pragma unroll
-                    for (int i = 0; i < PW; ++i) {
-                        sm.bm[slot][(p.vd + sl) * PW + i] = 0ull;
-                        p.state[(ROW_BM + (p.vd + sl) * PW + i) * np + e] = 0ull;
-                    }
-                }
-            }
-            __syncwarp();
-            // stream spans of the group's lattices as one list of (lattice, word) pairs over the lanes
-            const u32 cmask = __ballot_sync(FULL, complete && sl == 0);
-            const int nws = ((p.obs_bits + 31) >> 5) + 1;
-            for (int base = 0; base < 4 * nws; base += 32) {
-                const int idx = base + lane;
-                const int jj = (idx >= nws) + (idx >= 2 * nws) + (idx >= 3 * nws), k = idx - jj * nws;
-                const int sj = __shfl_sync(FULL, slot, (jj & 3) * 8);
-                const int b0 = sj * p.obs_bits, b1 = b0 + p.obs_bits, wi = (b0 >> 5) + k;
-                if (idx < 4 * nws && ((cmask >> (jj * 8)) & 1u) && wi <= ((b1 - 1) >> 5)) {
-                    const int lo = max(b0 - wi * 32, 0), hi = min(b1 - wi * 32, 32);
-                    const u32 mask = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-                    const u32 v = stream_word<D>(sm, p, wi, C);
-                    if (mask == 0xffffffffu) sm.stream[wi] = v;
-                    else { atomicAnd(&sm.stream[wi], ~mask); atomicOr(&sm.stream[wi], v & mask); }
-                }
-            }
-        }
-    }
-    __syncthreads();
-    } else {
-    // DQ_BATCHB=1.  Everything after the draws of a volume attempt is a few lanes' work per lattice, so a warp per lattice runs it at
-    // 5-8 active lanes.  Here a round is two stages: (1) the flip masks of ONE attempt of every lattice that still needs a volume,
-    // warp per lattice (all lanes busy: Philox + thresholds); (2) after a block barrier, lane = (lattice of a group of four,
-    // slice): prefix-XOR, syndromes, triviality test, and for the lattices whose volume is complete the state, the layer bitmaps
-    // and the stream spans -- one pass for up to four lattices.  Task flags: bit 0 heavy volume pending, bit 1 restart pending,
-    // bit 2 restart in progress (its frame was reset).  Rounds repeat while a lattice drew an all-trivial volume or still has
-    // its restart to do (block-uniform: counted in npending[round parity]).
-    for (int round = 0;; ++round) {
-        for (int t = warp; t < sm.ntask; t += kWarps) {
-            if (!sm.task_flags[t]) continue;
-            const int slot = sm.task[t];
-            const u32 att = (u32)(sm.fmeta[slot] >> 32) & 0x7FFFFFFFu;
-            const bool anyq = draw_flip_masks<D>(p, sm.pre[slot], lane, p.env_id_base + (u32)(env0 + slot), att);
-            if (lane == 0) sm.pre_anyq[slot] = anyq ? 1 : 0;
-        }
-        if (tid == 0) sm.npending[round & 1] = 0;
-        __syncthreads();
-        const int ntask = sm.ntask;
-        for (int c = warp; c * 4 < ntask; c += kWarps) {
-            const int j = lane >> 3, sl = lane & 7, t = c * 4 + j;
-            int fl = t < ntask ? sm.task_flags[t] : 0;
-            const bool act = fl != 0;
-            const int slot = t < ntask ? sm.task[t] : 0;
-            const int e = env0 + slot;
-            u64 xb = sm.fx[slot], zb = sm.fz[slot];
-            const u64 bm0 = sm.fmeta[slot];
-            u32 life = (u32)bm0, attempts = (u32)(bm0 >> 32) & 0x7FFFFFFFu, dn = (u32)(bm0 >> 63);
-            const bool heavy = (fl & 1) != 0;
-            if (act && !heavy && (fl & 2)) { xb = 0; zb = 0; life = 0; dn = 0; fl = 4; }      // the restart begins on a clean frame
-            u64 ex = 0, ez = 0, m = 0;
-            if (act && sl < p.vd) {
-                const u64* a64 = reinterpret_cast<const u64*>(sm.pre[slot]);
-                ex = a64[0 * kMaxVd + sl]; ez = a64[1 * kMaxVd + sl]; m = a64[2 * kMaxVd + sl];
-            }
-#pragma unroll
-            for (int off = 1; off < kMaxVd; off <<= 1) {          // inclusive prefix XOR over the slices of each 8-lane group
-                const u64 tx = __shfl_up_sync(FULL, ex, off, 8), tz = __shfl_up_sync(FULL, ez, off, 8);
-                if (sl >= off) { ex ^= tx; ez ^= tz; }
-            }
-            const u64 fx = xb ^ ex, fz = zb ^ ez;
-            const u64 f = (act && sl < p.vd) ? (true_syndrome<D>(fx, fz) ^ m) : 0ull;
-            const u32 bal = __ballot_sync(FULL, f != 0);
-            const bool nontrivial = ((bal >> (j * 8)) & 0xFFu) != 0 || round >= kMaxAttemptsPerCall - 1;
-            xb = __shfl_sync(FULL, fx, p.vd - 1, 8);
-            zb = __shfl_sync(FULL, fz, p.vd - 1, 8);
-            life += (u32)p.vd;
-            attempts += 1;
-            bool complete = false, heavy_done = false;
-            if (act && nontrivial) {
-                if (heavy) { heavy_done = true; fl &= ~1; complete = fl == 0; }
-                else { fl = 0; complete = true; }
-            }
-            u64 summed = f;
-            summed |= __shfl_xor_sync(FULL, summed, 1, 8);
-            summed |= __shfl_xor_sync(FULL, summed, 2, 8);
-            summed |= __shfl_xor_sync(FULL, summed, 4, 8);
-            if (act && sl == 0) {
-                sm.fx[slot] = xb; sm.fz[slot] = zb; sm.fmeta[slot] = meta_pack(life, attempts, dn);
-                sm.task_flags[t] = (uint8_t)fl;
-                if (fl) atomicAdd(&sm.npending[round & 1], 1);
-                if (heavy_done && !RESET) sm.life_out[slot] = (int32_t)life;
-                if (complete) {
-                    p.state[ROW_XB * np + e] = xb;
-                    p.state[ROW_ZB * np + e] = zb;
-                    p.state[ROW_META * np + e] = meta_pack(life, attempts, dn);
-                    p.state[ROW_SUM * np + e] = summed;
-                    sm.sum[slot] = summed; sm.acted[slot] = 0;
-#if DQ_MIRROR
-                    if (!RESET) {
-                        sm.cx[slot] = xb; sm.cz[slot] = zb; sm.cmeta[slot] = meta_pack(life, attempts, dn);
-                        sm.cact[0][slot] = 0; sm.cact[1][slot] = 0; sm.cact[2][slot] = 0;
-                    }
-#endif
-                }
-            }
-            if (complete) {
-                u64 w[PW];
-                syndrome_layer_bitmap<D>(f, w);
-                if (sl < p.vd) {
-#pragma unroll
-                    for (int i = 0; i < PW; ++i) {
-                        sm.bm[slot][sl * PW + i] = w[i];
-                        p.state[(ROW_BM + sl * PW + i) * np + e] = w[i];
-                    }
-                }
-                if (sl < p.layers) {                           // the action boards and their layers are cleared
-                    p.state[(ROW_ACT + sl) * np + e] = 0;
-#pragma unroll
-                    for (int i = 0; i < PW; ++i) {
-                        sm.bm[slot][(p.vd + sl) * PW + i] = 0ull;
-                        p.state[(ROW_BM + (p.vd + sl) * PW + i) * np + e] = 0ull;
+        for (int l = 0; l < 3; ++l) if (l < p.layers) p.state[(ROW_ACT + l) * np + e] = act[l];
+        __threadfence_block();
+        if (lane == 0) *reinterpret_cast<volatile u32*>(&sm.quit) = 1u;
+    } else if (warp <= kWriters) {
+        // ================================================================== WRITERS
+        const int t = tid - 32;
+        int ring_slot = ro.first_slot;
+        for (int rs = 0; rs < ro.nsteps; ++rs) {
+            const int r = rs & (kRing - 1);
+            uint8_t* const obs = obs0 ? obs0 + (size_t)ring_slot * ro.slot_bytes : nullptr;
+            bar_sync_named(BAR_FULL + r, 32 + kWriterThreads);
+            const u32 vm = sm.rec_volmask[r];
+            // (1) apply the step's record to the bitmaps (and their state rows): a light step lights one more cell of its action layer ...
+            if (t < kLpc) {
+                const int ab = sm.rec_actbit[r][t];
+                if (ab >= 0) {
+                    const int pos = ab & 0xFFFF, row = (p.vd + (ab >> 16)) * PW + (pos >> 6);
+                    const u64 wv = sm.bm[t][row] | (1ull << (pos & 63));
+                    sm.bm[t][row] = wv;
+                    p.state[(ROW_BM + row) * np + env0 + t] = wv;
+                    if (obs0 && rs > 0) {                     // (the first pass of a launch gathers the whole stream)
+                        const int sb = t * p.obs_bits + (p.vd + (ab >> 16)) * L::P + pos;
+                        atomicOr(&sm.stream[sb >> 5], 1u << (sb & 31));
                     }
                 }
             }
-            __syncwarp();
-            // stream spans of the completed lattices of this group of four, as one list of (lattice, word) pairs over the lanes
-            // (a span's first / last word is shared with the neighbouring lattices: atomics)
+            // ... a fresh volume re-renders the lattice: thread = (lattice, layer); action layers are cleared
             {
-                const u32 cmask = __ballot_sync(FULL, complete && sl == 0);
-                const int nws = ((p.obs_bits + 31) >> 5) + 1;             // words a lattice's span can touch
-                for (int base = 0; base < 4 * nws; base += 32) {
-                    const int idx = base + lane;
-                    const int jj = (idx >= nws) + (idx >= 2 * nws) + (idx >= 3 * nws), k = idx - jj * nws;
-                    const int sj = __shfl_sync(FULL, slot, (jj & 3) * 8);
-                    const int b0 = sj * p.obs_bits, b1 = b0 + p.obs_bits, wi = (b0 >> 5) + k;
-                    if (idx < 4 * nws && ((cmask >> (jj * 8)) & 1u) && wi <= ((b1 - 1) >> 5)) {
-                        const int lo = max(b0 - wi * 32, 0), hi = min(b1 - wi * 32, 32);
-                        const u32 mask = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-                        const u32 v = stream_word<D>(sm, p, wi, C);
-                        if (mask == 0xffffffffu) sm.stream[wi] = v;
-                        else { atomicAnd(&sm.stream[wi], ~mask); atomicOr(&sm.stream[wi], v & mask); }
+                const int items = __popc(vm) * C;
+                for (int i = t; i < items; i += kWriterThreads) {
+                    const int k = i / C, c = i - k * C;
+                    const int slot = select64((u64)vm, k);
+                    u64 w[PW];
+                    syndrome_layer_bitmap<D>(sm.rec_f[r][min(c, kMaxVd - 1)][slot], w);
+#pragma unroll
+                    for (int j = 0; j < PW; ++j) {
+                        const u64 v = c < p.vd ? w[j] : 0ull;               // an action layer has no marker cells
+                        sm.bm[slot][c * PW + j] = v;
+                        p.state[(ROW_BM + c * PW + j) * np + env0 + slot] = v;
                     }
                 }
             }
+            if (rs + kRing < ro.nsteps) bar_arrive_named(BAR_EMPTY + r, 32 + kWriterThreads);     // this thread is done with the record
+            bar_sync_named(BAR_WRITERS, kWriterThreads);
+            // (2) the tile's observation bytes
+            if (obs) write_observations<D>(sm, p, obs, env0, nvalid, t, kWriterThreads, rs == 0 ? FULL : vm, C);
+            ring_slot = (ring_slot + 1 == ro.slots) ? 0 : ring_slot + 1;
         }
-        __syncthreads();
-        if (sm.npending[round & 1] == 0) break;
-    }
-    }
-    if constexpr (!kBatchB) __syncthreads();
-
-    // ---- phase C: lifetime and legal mask (warp 0, lane = lattice; the mask also feeds the next step's built-in pick)
-    if (tid < kEpc) {
-        const int slot = tid;
-        if (lifetime && !RESET && slot < nvalid) lifetime[env0 + slot] = sm.life_out[slot];
-        if (legal || policy_ctr) {
-            legal_words<D>(p, sm.sum[slot], sm.acted[slot], mw);
-            if (legal && slot < nvalid) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-                    if (i < p.W) legal[(size_t)(env0 + slot) * p.W + i] = mw[i];
+    } else {
+        // ================================================================== GENERATORS
+        const int g = warp - 1 - kWriters;
+        u32* const acc = sm.acc[g];
+        volatile u32* const vtail = sm.tail;
+        volatile u32* const vhead = sm.head;
+        const int mine = lane * kGens + g;                        // lanes < kOwned look at one owned lattice each
+        for (;;) {
+            u32 quit = *reinterpret_cast<volatile u32*>(&sm.quit);
+            __threadfence_block();                                 // quit is read BEFORE the heads it was published after
+            quit = __shfl_sync(FULL, quit, 0);                     // one value for the warp: the lanes leave the loop together
+            u32 key = 0;                                           // (emptiness << 8) | (255 - lane): the emptiest queue first, then the lowest lattice
+            if (lane < kOwned && mine < nvalid) {
+                const u32 fill = vtail[mine] - vhead[mine];
+                if (fill < (u32)kQ) key = (((u32)kQ - fill) << 8) | (u32)(255 - lane);
             }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) key = max(key, __shfl_xor_sync(FULL, key, off));
+            if (key == 0) {
+                if (quit) break;
+                spin_pause();
+                continue;
+            }
+            const int l = (255 - (int)(key & 0xFFu)) * kGens + g;
+            const u32 t = vtail[l];
+            generate_attempt<D>(p, acc, lane, p.env_id_base + (u32)(env0 + l), t,
+                                qp + (size_t)(t & (u32)(kQ - 1)) * (kQW * kLpc) + l);
+            __threadfence_block();
+            __syncwarp();                                          // every lane's words of the entry are written ...
+            if (lane == 0) vtail[l] = t + 1u;                      // ... before the entry is offered
+            __syncwarp();                                          // and no lane samples the counters of the next pass before that
         }
     }
-    obs_prev = obs;
-    if (++gphase == kPickGroup) { gphase = 0; gbuf ^= 1; }
-    }   // rollout step
-#if !DQ_DEFER
-    if (obs_prev) write_observations(sm, p, obs_prev, env0, nvalid, tid, kThreads);           // the last step's observations
-#else
-    {
-        const u32 dm = sm.dirty[(ro.nsteps - 1) & 1];
-#if DQ_DEFER == 2
-        render_dirty<D>(sm, p, dm, tid, kThreads, env0, C);        // the last phase B lies behind barrier 2
-        if (obs_prev) __syncthreads();                             // block-uniform
-#endif
-        if (obs_prev) write_observations<D>(sm, p, obs_prev, env0, nvalid, tid, kThreads, dm, C);
+    __syncthreads();
+    // ---- epilogue: the queues and their fill counters persist between launches
+    if (q_in_smem) {
+        const u64* sq = &sm.q[0][0][0];
+        for (int i = tid; i < kQ * kQW * kLpc; i += kThreads) gq[i] = sq[i];
     }
-#endif
+    if (tid < kLpc) p.qtail[env0 + tid] = sm.tail[tid];
     if (policy_ctr && tid == 0 && atomicAdd(policy_ctr + 1, 1u) == gridDim.x - 1) { policy_ctr[1] = 0; atomicAdd(policy_ctr, (u32)ro.nsteps); }
 }
 
@@ -1063,7 +685,8 @@ struct dq_env {
     cudaStream_t hstream;
     u32* policy_ctr;             // {step index, finished-CTA count} for dq_policy_random_legal_next
     int32_t* s_actions; uint8_t* s_obs; float* s_reward; uint8_t* s_done; int32_t* s_life; u64* s_legal;
-    u64* h_packed;               // DQ_HOST_EXPAND: pinned landing buffer of the bit-packed observation rows
+    u64* h_packed;               // pinned landing buffer of the bit-packed observation rows (host-side expansion)
+    bool q_reset;                // the next launch must discard the queued volume attempts (noise rates changed)
 };
 
 static std::atomic<long long> g_launches{0};
@@ -1148,6 +771,17 @@ extern "C" int dq_env_create(dq_env** out, int d, int error_model, int use_Y, in
     err = cudaMalloc(&e->policy_ctr, 2 * sizeof(u32));
     if (err == cudaSuccess) err = cudaMemset(e->policy_ctr, 0, 2 * sizeof(u32));
     if (err != cudaSuccess) { cudaFree(p.state); delete e; return fail(DQ_ECUDA, std::string("cudaMalloc(policy_ctr): ") + cudaGetErrorString(err)); }
+    // volume queues: kQ state-free attempts per lattice, tile-major; qtail = 0 with attempt counters at 0 means "empty"
+    const size_t qwords = (size_t)(p.npad / kLpc) * kQ * kQW * kLpc;
+    err = cudaMalloc(&p.queue, qwords * sizeof(u64));
+    if (err == cudaSuccess) err = cudaMemset(p.queue, 0, qwords * sizeof(u64));
+    if (err == cudaSuccess) err = cudaMalloc(&p.qtail, (size_t)p.npad * sizeof(u32));
+    if (err == cudaSuccess) err = cudaMemset(p.qtail, 0, (size_t)p.npad * sizeof(u32));
+    if (err != cudaSuccess) {
+        cudaFree(p.queue); cudaFree(p.qtail); cudaFree(e->policy_ctr); cudaFree(p.state); delete e;
+        return fail(DQ_ECUDA, std::string("cudaMalloc(volume queues): ") + cudaGetErrorString(err));
+    }
+    p.max_attempts = kMaxAttemptsPerCall;
     *out = e;
     return DQ_OK;
 }
@@ -1162,6 +796,8 @@ extern "C" int dq_env_destroy(dq_env* e) {
         cudaStreamDestroy(e->hstream);
     }
     cudaFree(e->p.state);
+    cudaFree(e->p.queue);
+    cudaFree(e->p.qtail);
     cudaFree(e->policy_ctr);
     delete e;
     return DQ_OK;
@@ -1191,6 +827,14 @@ extern "C" int dq_env_set_noise(dq_env* e, double p_phys, double p_meas) {
     if (!e) return fail(DQ_EINVAL, "env is NULL");
     if (!(p_phys >= 0.0) || !(p_meas >= 0.0)) return fail(DQ_EINVAL, "probabilities must be >= 0");
     set_thresholds(e->p, p_phys, p_meas);
+    e->q_reset = true;            // queued attempts were thresholded with the old rates
+    return DQ_OK;
+}
+
+extern "C" int dq_env_set_max_attempts(dq_env* e, int max_attempts) {
+    if (!e) return fail(DQ_EINVAL, "env is NULL");
+    if (max_attempts < 1 || max_attempts > kMaxAttemptsPerCall) return fail(DQ_EINVAL, "max_attempts must be in [1, 2^20]");
+    e->p.max_attempts = max_attempts;
     return DQ_OK;
 }
 
@@ -1215,8 +859,10 @@ template <bool RESET>
 static int launch_env(dq_env* e, const int32_t* actions, uint8_t* obs, float* reward, uint8_t* done, int32_t* lifetime,
                       u64* legal, int auto_reset, cudaStream_t st, u32* pctr = nullptr, int32_t* aout = nullptr,
                       Rollout ro = Rollout{1, 1, 0, 0, 0}) {
-    const EnvParams& p = e->p;
-    const dim3 grid(p.npad / kEpc), block(kThreads);
+    EnvParams p = e->p;
+    p.q_reset = e->q_reset ? 1 : 0;
+    e->q_reset = false;
+    const dim3 grid(p.npad / kLpc), block(kThreads);
     switch (p.d) {
         case 3: env_step_kernel<3, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;
         case 5: env_step_kernel<5, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;

@@ -80,6 +80,10 @@ int dq_env_info(const dq_env* env, int what, int64_t* out);
 
 /* env.p_phys / env.p_meas are assignable in the reference (SPTS:200-201). */
 int dq_env_set_noise(dq_env* env, double p_phys, double p_meas);
+/* Documented deviation: the reference redraws an all-trivial syndrome volume forever (EN/Environments.py:158-170 never
+ * returns at p_phys = p_meas = 0 on a clean frame); a kernel must end, so after max_attempts all-trivial attempts on one
+ * volume the trivial volume is accepted.  Default 2^20; range [1, 2^20].  Tests lower it to exercise the branch. */
+int dq_env_set_max_attempts(dq_env* env, int max_attempts);
 
 /* Replaces the duck-typed static_decoder.predict + argmax (EN/Environments.py:144,150) by
  * table lookups.  Tables are DEVICE pointers, 2 bits per entry, 4 entries per byte, entry i

@@ -109,6 +109,8 @@ typedef struct {
     int n3, n1;                           /* #type-3 / #type-1 stabilizers         */
     int joint_a[MAXG * MAXG], joint_b[MAXG * MAXG];   /* joint-table bit order       */
     int ref_mode;                         /* -1 none, 0 joint, 1 split             */
+    int max_attempts;                     /* 0 = the reference's behaviour (redraw for ever); n > 0 = the product's documented
+                                             deviation: after n all-trivial attempts the trivial volume is accepted       */
     const uint8_t* lut_a;                 /* joint table, or X-class table         */
     const uint8_t* lut_b;                 /* Z-class table (split, DP only)        */
     env_t* envs;
@@ -215,7 +217,7 @@ static inline uint32_t noise_word(const oracle_t* o, const env_t* e, uint32_t at
  * vd noisy slices until the summed faulty syndrome is non-trivial.  Rejected
  * volumes keep their errors in the hidden frame and still advance lifetime.    */
 static void new_volume(const oracle_t* o, env_t* e) {
-    int d = o->d, g = d + 1;
+    int d = o->d, g = d + 1, tries = 0;
     for (;;) {
         uint32_t attempt = e->attempts++;
         uint32_t cache[4]; int cb = -1;
@@ -241,7 +243,7 @@ static void new_volume(const oracle_t* o, env_t* e) {
             e->lifetime += 1;
         }
         (void)g;
-        if (any) break;
+        if (any || (o->max_attempts > 0 && ++tries >= o->max_attempts)) break;
     }
 }
 
@@ -362,6 +364,8 @@ void* dqo_create(int d, int model, int use_Y, int vd, double p_phys, double p_me
 }
 
 void dqo_destroy(void* h) { oracle_t* o = (oracle_t*)h; if (o) { free(o->envs); free(o); } }
+
+void dqo_set_max_attempts(void* h, int n) { ((oracle_t*)h)->max_attempts = n; }
 
 void dqo_set_noise(void* h, double p_phys, double p_meas) {
     oracle_t* o = (oracle_t*)h;

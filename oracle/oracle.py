@@ -31,6 +31,7 @@ def lib():
                                  C.c_int64, C.c_uint64, C.c_int64]
         L.dqo_destroy.argtypes = [C.c_void_p]
         L.dqo_set_noise.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.dqo_set_max_attempts.argtypes = [C.c_void_p, C.c_int]
         L.dqo_set_referee.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.dqo_info.argtypes = [C.c_void_p, C.c_int]
         L.dqo_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -78,6 +79,10 @@ class OracleVecEnv:
         if getattr(self, "h", None):
             self.L.dqo_destroy(self.h)
             self.h = None
+
+    def set_max_attempts(self, n):
+        """0 = redraw an all-trivial volume for ever (the reference); n > 0 = accept it after n attempts (the product's deviation)."""
+        self.L.dqo_set_max_attempts(self.h, int(n))
 
     def set_noise(self, p_phys, p_meas):
         self.L.dqo_set_noise(self.h, float(p_phys), float(p_meas))

@@ -50,6 +50,7 @@ def lib(path=None):
     L.dq_env_destroy.argtypes = [vp]
     L.dq_env_info.argtypes = [vp, i32, C.POINTER(i64)]
     L.dq_env_set_noise.argtypes = [vp, f64, f64]
+    L.dq_env_set_max_attempts.argtypes = [vp, i32]
     L.dq_env_set_referee_lut.argtypes = [vp, i32, vp, i64, vp, i64]
     L.dq_env_reset.argtypes = [vp, vp, vp, vp]
     L.dq_env_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp]
@@ -99,6 +100,9 @@ class EmuVecEnv:
 
     def set_noise(self, p_phys, p_meas):
         self._check(self.L.dq_env_set_noise(self.h, float(p_phys), float(p_meas)))
+
+    def set_max_attempts(self, n):
+        self._check(self.L.dq_env_set_max_attempts(self.h, int(n)))
 
     def set_referee(self, mode, lut_a, lut_b=None):
         lut_a = np.ascontiguousarray(lut_a, dtype=np.uint8)

@@ -142,6 +142,15 @@ inline void named_barrier(int id, int count) {
     while (c.nbar_gen[id] == gen) yield();
 }
 
+// bar.arrive id, count: arrive at the barrier without waiting for it
+inline void named_barrier_arrive(int id, int count) {
+    Cta& c = *cta();
+    if (id < 1 || id > 15 || count % 32) { fprintf(stderr, "dq_emu: bad named barrier (%d, %d)\n", id, count); abort(); }
+    if (++c.nbar_count[id] >= count) { c.nbar_count[id] = 0; c.nbar_gen[id]++; }
+    c.progress++;
+}
+
+inline int idle_limit() { static int m = -1; if (m < 0) { const char* e = getenv("DQ_EMU_IDLE"); m = e ? atoi(e) : 2; } return m; }
 inline int sched_mode() { static int m = -1; if (m < 0) { const char* e = getenv("DQ_EMU_SCHED"); m = e ? atoi(e) : 0; } return m; }
 inline unsigned sched_rand() { static unsigned s = 0; if (!s) s = 2654435761u * (unsigned)(sched_mode() + 1); s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; }
 
@@ -191,7 +200,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
                     swapcontext(&c->sched, &c->th[i].ctx);
                 }
             idle_passes = (c->progress == before) ? idle_passes + 1 : 0;
-            if (idle_passes > 2) {
+            if (idle_passes > idle_limit()) {
                 fprintf(stderr, "dq_emu: deadlock in block (%u,%u,%u): %d of %d threads finished, the rest wait at a barrier or warp "
                                 "primitive that can never complete\n", bx, by, bz, c->ndone, nthreads);
                 abort();
@@ -217,6 +226,8 @@ inline dim3 thread_idx() {
 
 // ---- warp / block primitives ----------------------------------------------------------------------------------
 static inline void __syncthreads() { dq_emu::block_barrier(); }
+static inline void __threadfence_block() {}          // fibers of one OS thread: program order is memory order
+static inline void __nanosleep(unsigned) { dq_emu::yield(); }
 static inline void __syncwarp(uint32_t mask = 0xffffffffu) { dq_emu::warp_collect(mask, 0); }
 static inline uint32_t __ballot_sync(uint32_t mask, int pred) {
     const uint64_t* v = dq_emu::warp_collect(mask, pred ? 1 : 0);

@@ -207,28 +207,18 @@ def test_emulated_distinct_measurement_rate(p_phys, p_meas):
         olegal = want[4]
 
 
-VARIANTS = [("prefetch", ["-DDQ_PREFETCH=1"]),
-            ("prefetch_refill1", ["-DDQ_PREFETCH=1", "-DDQ_REFILL=1"]),
-            ("batched_phase_b", ["-DDQ_BATCHB=1"]),
-            ("batched_finalisation", ["-DDQ_BATCHB=2"]),
-            ("batched_phase_b_tile32x256", ["-DDQ_BATCHB=1", "-DDQ_EPC=32", "-DDQ_THREADS=256"]),
-            ("tile32x256", ["-DDQ_EPC=32", "-DDQ_THREADS=256"]),
-            ("tile8x64_prefetch", ["-DDQ_EPC=8", "-DDQ_THREADS=64", "-DDQ_PREFETCH=1"]),
-            ("deferred", ["-DDQ_DEFER=1"]),
-            ("deferred_prefetch_refill1", ["-DDQ_DEFER=1", "-DDQ_PREFETCH=1", "-DDQ_REFILL=1"]),
-            ("deferred_tile32x256", ["-DDQ_DEFER=1", "-DDQ_EPC=32", "-DDQ_THREADS=256"]),
-            ("deferred_streaming_stores", ["-DDQ_DEFER=1", "-DDQ_STREAM_OBS=1"]),
-            ("deferred_render", ["-DDQ_DEFER=2"]),
-            ("deferred_render_prefetch_refill1", ["-DDQ_DEFER=2", "-DDQ_PREFETCH=1", "-DDQ_REFILL=1"]),
-            ("deferred_render_tile8x64", ["-DDQ_DEFER=2", "-DDQ_EPC=8", "-DDQ_THREADS=64"]),
-            ("deferred_render_5warps", ["-DDQ_DEFER=2", "-DDQ_THREADS=160"]),
-            ("batched_phase_b_mirror", ["-DDQ_BATCHB=1", "-DDQ_MIRROR=1"]),
-            ("batched_finalisation_mirror_tile32x256", ["-DDQ_BATCHB=2", "-DDQ_MIRROR=1", "-DDQ_EPC=32", "-DDQ_THREADS=256"])]
+VARIANTS = [("w1g1", ["-DDQ_WRITERS=1", "-DDQ_GENS=1"]),
+            ("w2g3", ["-DDQ_WRITERS=2", "-DDQ_GENS=3"]),
+            ("w2g5", ["-DDQ_WRITERS=2", "-DDQ_GENS=5"]),
+            ("w4g3", ["-DDQ_WRITERS=4", "-DDQ_GENS=3"]),
+            ("w3g6", ["-DDQ_WRITERS=3", "-DDQ_GENS=6"]),
+            ("q2", ["-DDQ_QDEPTH=2"]),
+            ("q8", ["-DDQ_QDEPTH=8"])]
 
 
 @pytest.mark.parametrize("name,flags", VARIANTS, ids=[v[0] for v in VARIANTS])
 def test_emulated_build_variants(name, flags):
-    """The tuning builds of tools/build_variants.sh (tile shape, flip masks drawn ahead by warps 1..) are the same function:
+    """The tuning builds of tools/build_variants.sh (writer / generator warps per CTA, depth of the volume queues) are the same function:
     reset, a single-step launch, a long and a short rollout, then the packed state, all against the oracle."""
     import os
     path = E.build(flags, out=os.path.join(E.HERE, "host", "libdq_env_emu_%s.so" % name))
@@ -257,6 +247,84 @@ def test_emulated_build_variants(name, flags):
                 if ring is not None and s >= S - 4:
                     assert np.array_equal(ring[s % 4], oobs)
         compare_state(a, o, range(min(n, 8)))
+
+
+def test_emulated_noise_change_discards_queued_volumes():
+    """env.p_phys / env.p_meas are assignable between steps (SPTS:200-201): volume attempts queued ahead under the old rates must not
+    be served afterwards -- single steps and a rollout either side of two changes, against the oracle."""
+    d, model, n = 5, "DP", 40
+    env, o = make_pair(d, model, False, 5, 0.02, n, seed=21)
+    _, olegal = o.reset()
+    env.reset()
+    t = 0
+    for pp, pm in ((0.05, 0.01), (0.004, 0.03)):
+        for _ in range(5):
+            acts = o.random_legal_actions(olegal, t)
+            got, want = env.step(acts), o.step(acts, auto_reset=True)
+            assert all(np.array_equal(g, w) for g, w in zip(got, want)), "before the change, t=%d" % t
+            olegal = want[4]; t += 1
+        env.set_noise(pp, pm); o.set_noise(pp, pm)
+        env.policy_seek(t)
+        ring, rew, done, life, legal, acts = env.rollout_random(9, 3, 0, True)
+        for s in range(9):
+            oa = o.random_legal_actions(olegal, t)
+            oobs, orew, odone, olife, olegal = o.step(oa, auto_reset=True); t += 1
+            assert np.array_equal(acts[s], oa) and np.array_equal(rew[s], orew) and np.array_equal(done[s], odone), "after the change, s=%d" % s
+            assert np.array_equal(life[s], olife) and np.array_equal(legal[s], olegal)
+            if s >= 6:
+                assert np.array_equal(ring[s % 3], oobs)
+    compare_state(env, o, range(8))
+
+
+def test_emulated_injected_state_revalidates_queues():
+    """dq_env_set_state (checkpoint restore / parity injection): a handle that receives another trajectory's state continues that
+    trajectory bit for bit, whatever volume attempts its own queues held (their fill counters no longer match the attempt counters)."""
+    d, model, n = 5, "DP", 37
+    a, o = make_pair(d, model, False, 5, 0.03, n, seed=13, base=2)
+    b, _ = make_pair(d, model, False, 5, 0.03, n, seed=13, base=2)
+    _, olegal = o.reset()
+    a.reset(); b.reset()
+    t = 0
+    for _ in range(7):                       # only `a` (and the oracle) advance: b's queues stay at the reset position
+        acts = o.random_legal_actions(olegal, t)
+        a.step(acts); olegal = o.step(acts, auto_reset=True)[4]; t += 1
+    w = a.state_words()
+    b._check(b.L.dq_env_set_state(b.h, E._p(w), None))
+    for _ in range(8):
+        acts = o.random_legal_actions(olegal, t)
+        got, want = b.step(acts), o.step(acts, auto_reset=True)
+        assert all(np.array_equal(g, x) for g, x in zip(got, want)), "restored handle, t=%d" % t
+        olegal = want[4]; t += 1
+    # and back in time: the first handle receives an EARLIER state than the one its queues were filled for
+    c, o2 = make_pair(d, model, False, 5, 0.03, n, seed=13, base=2)
+    _, ol2 = o2.reset(); c.reset()
+    w0 = c.state_words().copy()
+    b._check(b.L.dq_env_set_state(b.h, E._p(w0), None))
+    for t2 in range(6):
+        acts = o2.random_legal_actions(ol2, t2)
+        got, want = b.step(acts), o2.step(acts, auto_reset=True)
+        assert all(np.array_equal(g, x) for g, x in zip(got, want)), "rewound handle, t=%d" % t2
+        ol2 = want[4]
+
+
+@pytest.mark.parametrize("cap", [1, 3])
+def test_emulated_attempt_cap_accepts_a_trivial_volume(cap):
+    """Documented deviation (include/dq_decoding.h, dq_env_set_max_attempts): at p_phys = p_meas = 0 the reference would redraw the
+    all-trivial volume for ever; after `cap` attempts the kernel accepts it.  The oracle restates the same rule when told to."""
+    d, model, n = 3, "DP", 9
+    env, o = make_pair(d, model, False, 3, 0.0, n, seed=4)
+    env.set_max_attempts(cap); o.set_max_attempts(cap)
+    obs, legal = env.reset()
+    oobs, olegal = o.reset()
+    assert np.array_equal(obs, oobs) and np.array_equal(legal, olegal)
+    assert not obs[:, :, ::2, ::2].any(), "an all-trivial volume shows no syndrome"
+    for t in range(4):
+        acts = o.random_legal_actions(olegal, t)          # only the identity is legal: every step draws a volume
+        got, want = env.step(acts), o.step(acts, auto_reset=True)
+        assert all(np.array_equal(g, w) for g, w in zip(got, want)), "t=%d" % t
+        assert (want[3] == (t + 2) * cap * 3).all(), "lifetime counts every attempt's slices"
+        olegal = want[4]
+    compare_state(env, o, range(n))
 
 
 @pytest.mark.parametrize("d,model,use_Y,vd,n", [(5, "DP", False, 5, 45), (7, "DP", True, 4, 19), (3, "X", False, 3, 33)])

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Alternative builds of the C-ABI library for kernel tuning on the GPU box (selected with DQ_DECODING_LIB, see _lib.py):
-# tile shapes / occupancy targets of the env kernel, plus the previous round's env kernel as a same-box control.
+# warp-role splits / queue depths of the env kernel, plus (OLD_REV=<git rev>) an earlier revision's env kernel as a same-box control.
 # The Q-network and exchange objects are compiled once and linked into every variant.
 set -e
 cd "$(dirname "$0")/.."
@@ -11,7 +11,7 @@ FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompil
 mkdir -p $OUT
 [ -f $OUT/dq_qnet.o ] && [ $OUT/dq_qnet.o -nt $CS/dq_qnet.cu ] || $NVCC $FLAGS -c -o $OUT/dq_qnet.o $CS/dq_qnet.cu
 [ -f $OUT/dq_comm.o ] && [ $OUT/dq_comm.o -nt $CS/dq_comm.cu ] || $NVCC $FLAGS -c -o $OUT/dq_comm.o $CS/dq_comm.cu
-variant() {   # name, extra flags; DQ_VARIANTS="so dfso" restricts the build to the named ones
+variant() {   # name, extra flags; DQ_VARIANTS="w2g3 q8" restricts the build to the named ones
     name=$1; shift
     if [ -n "$DQ_VARIANTS" ]; then case " $DQ_VARIANTS " in *" $name "*) ;; *) return 0;; esac; fi
     $NVCC $FLAGS "$@" -c -o $OUT/dq_env_$name.o $CS/dq_env.cu
@@ -19,43 +19,21 @@ variant() {   # name, extra flags; DQ_VARIANTS="so dfso" restricts the build to 
     rm -f $OUT/dq_env_$name.o
     echo "built $OUT/libdq_$name.so"
 }
-variant df         -DDQ_DEFER=1
-variant so         -DDQ_STREAM_OBS=1
-variant dfso       -DDQ_DEFER=1 -DDQ_STREAM_OBS=1
-variant df2        -DDQ_DEFER=2
-variant df2so      -DDQ_DEFER=2 -DDQ_STREAM_OBS=1
-variant df2solk    -DDQ_DEFER=2 -DDQ_STREAM_OBS=1 -DDQ_LUT_KEEP=1
-variant df2sot160  -DDQ_DEFER=2 -DDQ_STREAM_OBS=1 -DDQ_THREADS=160 -DDQ_MIN_BLOCKS=7      # five warps: one more for phase B and the helpers; 56 registers, ~100 B of spills
-variant lk         -DDQ_LUT_KEEP=1
-variant df2sopf1   -DDQ_DEFER=2 -DDQ_STREAM_OBS=1 -DDQ_PREFETCH=1 -DDQ_REFILL=1
-variant df2sopf2   -DDQ_DEFER=2 -DDQ_STREAM_OBS=1 -DDQ_PREFETCH=1 -DDQ_REFILL=2
-variant dfsopf1    -DDQ_DEFER=1 -DDQ_STREAM_OBS=1 -DDQ_PREFETCH=1 -DDQ_REFILL=1
-variant bb2so      -DDQ_BATCHB=2 -DDQ_STREAM_OBS=1
-variant bb2        -DDQ_BATCHB=2
-variant bb         -DDQ_BATCHB=1
-variant bbmb8      -DDQ_BATCHB=1 -DDQ_MIN_BLOCKS=8
-variant bbe32      -DDQ_BATCHB=1 -DDQ_EPC=32 -DDQ_THREADS=256 -DDQ_MIN_BLOCKS=4 -DDQ_STREAM_OBS=1     # fewest instructions per lattice-step of all builds
-variant bbso       -DDQ_BATCHB=1 -DDQ_STREAM_OBS=1
-variant bbsomi     -DDQ_BATCHB=1 -DDQ_STREAM_OBS=1 -DDQ_MIRROR=1      # + frame / counters / action boards read from shared memory in phase A
-variant bb2somi    -DDQ_BATCHB=2 -DDQ_STREAM_OBS=1 -DDQ_MIRROR=1
-variant pf1        -DDQ_PREFETCH=1 -DDQ_REFILL=1
-variant pf2        -DDQ_PREFETCH=1
-variant pf3        -DDQ_PREFETCH=1 -DDQ_REFILL=3
-variant pf2mb8     -DDQ_PREFETCH=1 -DDQ_MIN_BLOCKS=8
-variant mb8        -DDQ_MIN_BLOCKS=8
-variant mb10       -DDQ_MIN_BLOCKS=10
-variant e8t64mb14  -DDQ_EPC=8  -DDQ_THREADS=64  -DDQ_MIN_BLOCKS=14
-variant e16t96     -DDQ_EPC=16 -DDQ_THREADS=96  -DDQ_MIN_BLOCKS=7
-variant bb2t96     -DDQ_BATCHB=2 -DDQ_THREADS=96 -DDQ_MIN_BLOCKS=7
-variant e32t256mb4 -DDQ_EPC=32 -DDQ_THREADS=256 -DDQ_MIN_BLOCKS=4
-variant e16t256mb4 -DDQ_EPC=16 -DDQ_THREADS=256 -DDQ_MIN_BLOCKS=4
-if [ -n "$OLD_REV" ]; then    # control: the env kernel of an earlier commit, built in a scratch copy
-    T=$(mktemp -d)
-    mkdir -p $T/deepq_decoding_b200/csrc $T/include
-    for f in dq_env.cu dq_lattice.cuh dq_ptx.cuh; do git show $OLD_REV:$CS/$f > $T/$CS/$f; done
-    git show $OLD_REV:include/dq_decoding.h > $T/include/dq_decoding.h
-    $NVCC $FLAGS -c -o $OUT/dq_env_old.o $T/$CS/dq_env.cu
+variant w2g3   -DDQ_WRITERS=2 -DDQ_GENS=3
+variant w2g5   -DDQ_WRITERS=2 -DDQ_GENS=5
+variant w3g3   -DDQ_WRITERS=3 -DDQ_GENS=3
+variant w4g3   -DDQ_WRITERS=4 -DDQ_GENS=3
+variant w3g6   -DDQ_WRITERS=3 -DDQ_GENS=6 -DDQ_MIN_BLOCKS=4
+variant q2     -DDQ_QDEPTH=2
+variant q8     -DDQ_QDEPTH=8
+variant mb5    -DDQ_MIN_BLOCKS=5
+if [ -n "$OLD_REV" ]; then      # same-box control: the env kernel of an earlier revision
+    mkdir -p $OUT/old && git show $OLD_REV:$CS/dq_env.cu > $OUT/old/dq_env.cu && git show $OLD_REV:$CS/dq_lattice.cuh > $OUT/old/dq_lattice.cuh
+    git show $OLD_REV:include/dq_decoding.h > $OUT/old/dq_decoding.h
+    sed -i 's#"../../include/dq_decoding.h"#"dq_decoding.h"#' $OUT/old/dq_env.cu
+    grep -q dq_env_set_max_attempts $OUT/old/dq_env.cu || echo 'extern "C" int dq_env_set_max_attempts(dq_env*, int) { return 0; }' >> $OUT/old/dq_env.cu      # entry points added since
+    $NVCC $FLAGS -c -o $OUT/dq_env_old.o $OUT/old/dq_env.cu
     $NVCC -shared -o $OUT/libdq_old.so $OUT/dq_env_old.o $OUT/dq_qnet.o $OUT/dq_comm.o -lcudart
-    rm -rf $T $OUT/dq_env_old.o
-    echo "built $OUT/libdq_old.so ($OLD_REV)"
+    rm -f $OUT/dq_env_old.o
+    echo "built $OUT/libdq_old.so"
 fi
