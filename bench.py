@@ -38,11 +38,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION, from the environment or
-# /etc/nccl.conf) off it
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
-
 D, VD, P, MODEL, USE_Y = 5, 5, 0.007, "DP", False
 N_PER_GPU = 16384
 # other BASELINE.json configs, selectable with --workload for the roofline report (the default, c3, is the one the metric is quoted on)
@@ -71,9 +66,10 @@ def measured_peak():
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
-def cpu_oracle_run(budget_s, n=N_PER_GPU):
-    """Times the oracle on all host cores: random-legal policy + step, like the GPU loop."""
+def cpu_oracle_run(budget_s, n=None):
+    """Times the oracle on all host cores: random-legal policy + step, like the GPU loop (n = lattices of the selected workload)."""
     import numpy as np
+    n = N_PER_GPU if n is None else n
     from oracle import oracle as O
     from deepq_decoding_b200 import referee as REF
     try:
@@ -96,9 +92,27 @@ def cpu_oracle_run(budget_s, n=N_PER_GPU):
         el = time.perf_counter() - t0
         if el >= budget_s:
             break
-    return dict(value=n * steps / el, unit=UNIT, cores=cores, kind="port",
-                sample="%d vectorised steps of %d lattices (%.1f s wall) of the same workload, oracle/dq_oracle.c "
-                       "with OpenMP over lattices" % (steps, n, el)), n * steps / el, el / steps
+    cb = dict(value=n * steps / el, unit=UNIT, cores=cores, kind="port",
+              sample="%d vectorised steps of %d lattices (%.1f s wall) of the same workload, oracle/dq_oracle.c "
+                     "with OpenMP over lattices" % (steps, n, el))
+    rp = reference_python_result()
+    if rp is not None:
+        cb["reference_python"] = rp
+    return cb, n * steps / el, el / steps
+
+
+def reference_python_result():
+    """The UNMODIFIED Python reference timed on host cores (tools/time_reference_cpu.py).  It needs /root/reference, which exists
+    only in the build container, so the committed result of that run is reported next to the live C-port number."""
+    path = os.path.join(ROOT, "profiles", "reference_cpu_build_container.json")
+    try:
+        r = json.load(open(path))
+        return {"value": r["env_steps_per_s_aggregate"], "unit": UNIT, "cores": r["processes"], "per_core": r["env_steps_per_s_per_process_mean"],
+                "seconds_per_process": r["seconds_per_process"], "host_cpu": r["host"]["cpu"],
+                "source": "profiles/reference_cpu_build_container.json (tools/time_reference_cpu.py, build container; not timed in this run)",
+                "what": r["what"]}
+    except Exception:
+        return None
 
 
 def cpu_serial_dqn_loop(budget_s):
@@ -204,6 +218,228 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+def e2e_legs(L, _lib, torch, np, dist, dev, world, rank, n, K):
+    """Host-buffer throughput: every step copies the actions in from pinned host memory and every output back to pinned host
+    memory.  The policy is the same random-legal pick as on the device path, computed on the host from the legal masks that came
+    back (dq_policy_random_legal_host), so the workload mix equals the resident loop's and the CPU arm's."""
+    from deepq_decoding_b200.envs import VecSurfaceCodeEnv
+    ke = min(K, 64)
+    half = n // 2
+    envs = [VecSurfaceCodeEnv(D, P, P, MODEL, USE_Y, VD, None, n_envs=cnt, seed=SEED + 3, env_id_base=rank * n + base, device=dev)
+            for base, cnt in ((0, half), (half, n - half))]
+    whole = VecSurfaceCodeEnv(D, P, P, MODEL, USE_Y, VD, None, n_envs=n, seed=SEED + 3, env_id_base=rank * n, device=dev)
+    he = C.c_int64(0)
+    host_expand = bool(L.dq_env_info(whole._h, 10, C.byref(he)) == 0 and he.value == 1)
+    small = 4 + 1 + 4 + 8 * whole.mask_words
+    packed_bytes = int((whole.state_words - 7) * whole.state_stride * 8)
+    obs_bytes = int(whole.obs[0].numel())
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def rate(seconds):
+        t = torch.tensor([seconds], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * n * ke / float(t.item())
+
+    # (a) two handles of n/2 lattices, split calls: begin(A) begin(B) end(A) policy(A) begin(A) end(B) policy(B) begin(B) ...
+    for e in envs:
+        e.reset_host()
+    step = [0, 0]
+
+    def begin(k):
+        envs[k].random_legal_actions_host(step[k])
+        envs[k].step_host_begin()
+        step[k] += 1
+    for k in (0, 1):
+        begin(k)
+    for _ in range(3):
+        for k in (0, 1):
+            envs[k].step_host_end(); begin(k)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        for k in (0, 1):
+            envs[k].step_host_end(); begin(k)
+    dt = time.perf_counter() - t0
+    for k in (0, 1):
+        envs[k].step_host_end()
+    e2e = {"value": rate(dt), "unit": UNIT, "h2d_bytes_per_step": n * 4,
+           "d2h_bytes_per_step": n * small + (packed_bytes if host_expand else n * obs_bytes), "steps": ke,
+           "host_bytes_delivered_per_step": n * (obs_bytes + small),
+           "api": "VecSurfaceCodeEnv.step_host_begin / step_host_end (dq_env_step_host_begin / _end) on two handles of %d lattices driven alternately, "
+                  "random_legal_actions_host (dq_policy_random_legal_host) in between; uint8 observations [N,C,H,H], reward, done, lifetime and "
+                  "legal masks land in pinned host memory every step" % half,
+           "host_expand": host_expand,
+           "how": "the bitmap rows cross PCIe bit-packed and the library's host threads expand them into the byte observations inside _end, while "
+                  "the other handle's kernel and copies run" if host_expand else "the kernel writes bytes; all of them are copied back",
+           "policy": "uniform random-legal, computed on the host from the returned legal masks"}
+    # (b) the one-piece call on one handle of n lattices (no overlap between the GPU and the host side)
+    whole.reset_host()
+    for i in range(3):
+        whole.random_legal_actions_host(i); whole.step_host_begin(); whole.step_host_end()
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(ke):
+        whole.random_legal_actions_host(3 + i); whole.step_host_begin(); whole.step_host_end()
+    e2e["one_handle_sync"] = {"value": rate(time.perf_counter() - t0), "unit": UNIT,
+                              "api": "dq_env_step_host on one handle of %d lattices, same policy" % n}
+    # (c) observations returned PACKED (one bit per cell, the rows the Q-network consumes): nothing to expand anywhere
+    e2e_packed = None
+    try:
+        hb, pk = whole._host_buffers(), whole._packed_host_buffer()
+        hp = lambda t: C.c_void_p(t.data_ptr())
+
+        def packed_step(i):
+            whole.random_legal_actions_host(100 + i)
+            _lib.check(L.dq_env_step_host_packed(whole._h, hp(hb["actions"]), hp(pk), hp(hb["reward"]), hp(hb["done"]), hp(hb["lifetime"]), hp(hb["legal"]), 1))
+        for i in range(3):
+            packed_step(i)
+        sync_all()
+        t0 = time.perf_counter()
+        for i in range(ke):
+            packed_step(3 + i)
+        e2e_packed = {"value": rate(time.perf_counter() - t0), "unit": UNIT, "h2d_bytes_per_step": n * 4,
+                      "d2h_bytes_per_step": packed_bytes + n * small, "steps": ke,
+                      "api": "dq_env_step_host_packed (observations as bit-packed rows uint64 [C*PW][stride]; envs.unpack_observations expands "
+                             "them when a caller needs bytes), same policy"}
+    except Exception as ex:      # noqa: BLE001 -- reported, not fatal (no collective between here and the next barrier on the success path either)
+        e2e_packed = {"error": "%s: %s" % (type(ex).__name__, ex)}
+    for e in envs + [whole]:
+        e.close()
+    return e2e, e2e_packed
+
+
+def dqn_data_parallel_leg(L, _lib, torch, np, dist, dev, world, rank, n):
+    """The one collective of the path: data-parallel DQN updates over the sharded lattices, on EVERY rank.
+      * per-update device time of the gradient exchange + Adam: the fused peer-memory kernel (csrc/dq_comm.cu) vs NCCL all-reduce + Adam kernel;
+      * a short sharded `DQNAgent.fit` (C4 shape: n lattices per GPU) through collective='fused' and through 'nccl': parameters must stay
+        bit-identical across the ranks, and the two collectives must agree at world 2 (one fp32 add either way);
+      * sharded greedy evaluation of the reference's published d5_dp/0.007 agent, merged with parallel.reduce_lifetimes: LER at N GPUs."""
+    from deepq_decoding_b200 import agents as A, parallel
+    from deepq_decoding_b200.envs import VecSurfaceCodeEnv
+    out = {"world": world, "lattices_per_gpu": n}
+    st = lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    group = dist.group.WORLD if world > 1 else None
+    nparams = 193283 if (D, MODEL) == (5, "DP") else None
+    # ---- (1) exchange + Adam per update, device time, max over ranks
+    opt = A.Adam(lr=1e-5)
+
+    def timed(fn, iters=200, warm=20):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) * 1e3
+    npar = nparams or 193283
+    params, m, v, g = torch.randn(npar, device=dev), torch.zeros(npar, device=dev), torch.zeros(npar, device=dev), torch.randn(npar, device=dev)
+    tcount = [0]
+    if world > 1:
+        comm = parallel.FusedAllreduceAdam(npar, dev, group)
+
+        def fused():
+            tcount[0] += 1
+            comm.grads()
+            comm.step(params, m, v, opt, tcount[0], st())
+
+        def nccl():
+            tcount[0] += 1
+            dist.all_reduce(g)
+            _lib.check(L.dq_adam_step(p(params), p(m), p(v), p(g), npar, opt.lr, opt.beta_1, opt.beta_2, opt.epsilon, tcount[0], 1.0 / world, st()))
+        out["fused_us"], out["nccl_us"] = timed(fused), timed(nccl)
+        comm.check(); comm.close()
+    else:
+        # one GPU: the same kernel with itself as only peer (world 1) against the stand-alone Adam kernel
+        h = C.c_void_p()
+        _lib.check(L.dq_comm_create(C.byref(h), 0, 1, npar, dev.index or 0))
+
+        def fused():
+            tcount[0] += 1
+            gp = C.c_void_p()
+            _lib.check(L.dq_comm_next_grads(h, C.byref(gp)))
+            _lib.check(L.dq_comm_allreduce_adam(h, p(params), p(m), p(v), opt.lr, opt.beta_1, opt.beta_2, opt.epsilon, tcount[0], st()))
+
+        def adam_only():
+            tcount[0] += 1
+            _lib.check(L.dq_adam_step(p(params), p(m), p(v), p(g), npar, opt.lr, opt.beta_1, opt.beta_2, opt.epsilon, tcount[0], 1.0, st()))
+        out["fused_us"], out["nccl_us"] = timed(fused), None
+        out["adam_kernel_only_us"] = timed(adam_only)
+        flag = C.c_int(0)
+        _lib.check(L.dq_comm_status(h, C.byref(flag)))
+        out["note"] = "one GPU: dq_comm_allreduce_adam with world = 1 (its own region as only peer); there is nothing for NCCL to do"
+        L.dq_comm_destroy(h)
+    # ---- (2) short sharded fit through both collectives
+    spec_args = ([[64, 3, 2], [32, 2, 1], [32, 2, 1]], [[512, 0.2]])
+
+    def short_fit(collective):
+        env = VecSurfaceCodeEnv(D, P, P, MODEL, USE_Y, VD, None, n_envs=n, seed=SEED + 21, env_id_base=rank * n, device=dev)
+        spec = A.build_convolutional_nn(spec_args[0], spec_args[1], env.observation_space.shape, env.num_actions)
+        pol = A.LinearAnnealedPolicy(A.EpsGreedyQPolicy(masked_greedy=False), attr="eps", value_max=1.0, value_min=0.05, value_test=0.0, nb_steps=20 * n)
+        dqn = A.DQNAgent(model=spec, nb_actions=env.num_actions, memory=A.SequentialMemory(limit=16 * n), nb_steps_warmup=4 * n,
+                         target_model_update=10 * n, policy=pol, test_policy=A.GreedyQPolicy(masked_greedy=True), gamma=0.99,
+                         enable_dueling_network=True, batch_size=1024, seed=0, device=dev, process_group=group, collective=collective,
+                         act_precision="bf16")
+        dqn.compile(A.Adam(lr=1e-4), max_envs=n)
+        if world > 1:
+            parallel.broadcast_params_(dqn.model.params)
+            dqn.target_params.copy_(dqn.model.params)
+        t0 = time.perf_counter()
+        dqn.fit(env, nb_steps=24 * n, verbose=0, episode_averaging_length=1000, success_threshold=1e9, stopping_patience=1e12)
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+        params = dqn.model.params.clone()
+        env.close()
+        return params, dqn.updates, secs
+    pf, upd, secs = short_fit("fused")
+    pn, _, _ = short_fit("nccl")
+    ident = True
+    if world > 1:
+        lo, hi = pf.clone(), pf.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ident = bool(torch.equal(lo.view(torch.int32), hi.view(torch.int32)))
+        lo, hi = pn.clone(), pn.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ident = ident and bool(torch.equal(lo.view(torch.int32), hi.view(torch.int32)))
+    out.update({"identical": ident, "fit_updates": upd, "fit_env_steps": 24 * n * world, "fit_seconds_fused": secs,
+                "fit_finite": bool(torch.isfinite(pf).all()),
+                "fused_vs_nccl_max_abs_diff": float((pf - pn).abs().max()),
+                "fit": "DQNAgent.fit on %d lattices per rank, batch 1024 per rank, one update per iteration after a warm-up of 4 iterations, 24 iterations" % n})
+    # ---- (3) sharded greedy evaluation of the published agent
+    wpath = os.path.join(ROOT, "tests", "golden", "dqn_d5_dp_0.007.npz")
+    if os.path.exists(wpath) and (D, MODEL) == (5, "DP"):
+        z = np.load(wpath)
+        ev_env = VecSurfaceCodeEnv(D, P, P, MODEL, USE_Y, VD, None, n_envs=n, seed=SEED + 1, env_id_base=(10 + rank) * n, device=dev)
+        ev = A.DQNAgent(model=A.build_convolutional_nn(spec_args[0], spec_args[1], (7, 11, 11), ev_env.num_actions),
+                        nb_actions=ev_env.num_actions, memory=A.SequentialMemory(limit=100), test_policy=A.GreedyQPolicy(masked_greedy=True),
+                        enable_dueling_network=True, device=dev, act_precision="bf16")
+        ev.compile(A.Adam(lr=1e-5), max_envs=n)
+        ev.model.set_keras_weights([(z["conv%d_k" % i], z["conv%d_b" % i]) for i in range(3)], [(z["dense%d_k" % i], z["dense%d_b" % i]) for i in range(3)])
+        t0 = time.perf_counter()
+        life = np.array(ev.test(ev_env, nb_episodes=n, verbose=0).history["episode_lifetime"], dtype=np.float64)
+        mean, se, episodes = parallel.reduce_lifetimes(life, group)
+        out["logical_error_rate"] = {"agent": "reference trained_models/d5_dp/0.007/final_dqn_weights.h5f (tests/golden fixture), greedy masked policy, bf16 acting",
+                                     "episodes": episodes, "mean_lifetime_cycles": mean, "standard_error": se,
+                                     "logical_error_rate_per_cycle": 1.0 / mean, "reference_published_mean_lifetime": 270.42,
+                                     "within_3_se_of_published": bool(abs(mean - 270.42) <= 3 * se),
+                                     "eval_seconds": time.perf_counter() - t0, "merged_with": "parallel.reduce_lifetimes over %d rank(s)" % world}
+        ev_env.close()
+    return out
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -218,6 +454,9 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # The CPU baseline runs BEFORE the ranks meet: the other ranks wait for rank 0 in the rendezvous (blocked on a socket), not in an
+    # NCCL barrier that spins on the host cores the baseline is being timed on.
+    cb = cpu_oracle_run(args.cpu_seconds)[0] if rank == 0 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, Wm = args.steps, max(args.warmup, 3)
@@ -242,8 +481,8 @@ def run_b200(args):
     _lib.check(L.dq_policy_seek(h, 0, cur()))
     torch.cuda.synchronize()
 
-    # ---- the timed path: multi-step rollout launches (dq_env_rollout_random, ROLL steps of every lattice per launch; bit-identical
-    #      to ROLL single-step launches, tests/test_env_gpu.py).  Step s writes its observations into ring slot (cursor+s) % RING
+    # ---- the timed path: multi-step rollout launches (dq_env_rollout_random, up to ROLL steps of every lattice per launch; bit-identical
+    #      to single-step launches, tests/test_env_gpu.py).  Step s writes its observations into ring slot (cursor+s) % RING
     #      and row s of the per-step outputs, so every step still produces every output in HBM.
     roll_out = [torch.empty((ROLL, n), dtype=dt, device=dev) for dt in (torch.float32, torch.uint8, torch.int32, torch.int32)]
     roll_legal = torch.empty((ROLL, n, env.mask_words), dtype=torch.int64, device=dev)
@@ -262,7 +501,7 @@ def run_b200(args):
         if rest:
             rollout(rest)
 
-    # the older launch shape, kept as a second number: a CUDA graph of RING single-step launches
+    # the other launch shape, kept as a second number: a CUDA graph of RING single-step launches
     side = torch.cuda.Stream(dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
@@ -282,8 +521,10 @@ def run_b200(args):
         for s in range(rest):
             pair(s, cur())
 
+    delay = lambda ms_: torch.cuda._sleep(int(ms_ * 1e-3 * 1.9e9))     # device-side spin: what is queued behind it starts back to back
     sampler = ClockSampler(local) if rank == 0 else None
     run_steps(Wm)
+    run_steps(min(K, ROLL))                      # the launch shape of the timed region once more (its first launch of a given length is not a cold one)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -291,6 +532,7 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     state["launches"] = 0
+    delay(2.0)                                   # the K steps are queued while the device still spins: e0 -> e1 is device time, not host launch latency
     e0.record()
     run_steps(K)
     e1.record()
@@ -309,6 +551,7 @@ def run_b200(args):
     # second number: the same K steps as single-step launches (one launch per step, replayed from a CUDA graph)
     run_single_steps(RING)
     torch.cuda.synchronize()
+    delay(2.0)
     e0.record()
     run_single_steps(K)
     e1.record()
@@ -317,14 +560,14 @@ def run_b200(args):
     single = {"value": n * K / (ms_single * 1e-3), "unit": UNIT + " on this rank", "ms_per_step": ms_single / K,
               "launch": "CUDA graph of %d single-step launches (dq_env_step_random)" % RING}
 
-    # ---- roofline: per-launch duration of the env-step kernel, CUDA events around every rollout launch.
+    # ---- roofline: per-launch duration of the env-step kernel, CUDA events around every rollout launch of ROLL steps.
     # The launches are queued behind a ~25 ms device-side delay so that, when the GPU reaches them,
     # they run back to back and the event pairs bracket device time only (not Python launch gaps).
     roof = None
     if rank == 0:
         nprof = 24
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nprof)]
-        torch.cuda._sleep(int(25e-3 * 1.9e9))
+        delay(25.0)
         for i in range(nprof):
             evs[i][0].record()
             rollout(ROLL)
@@ -334,116 +577,76 @@ def run_b200(args):
         mean_s = sum(durs) / len(durs)
         peak, peak_src = measured_peak()
         achieved = ROLL * n * BYTES_PER_STEP / mean_s / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "env_step_traffic.json")
         if os.path.exists(tpath) and args.workload == "c3":
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_step") * ROLL      # ncu capture of one rollout launch, per step
+                tj = json.load(open(tpath))
+                traffic = tj.get("dram_bytes_per_step") * ROLL
+                traffic_src = "stored ncu capture (%s): dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch, per step, x %d; not measured in this run" % (
+                    tj.get("capture", "profiles/env_step_traffic.json"), ROLL)
             except Exception:
                 traffic = None
         roof = {"bound": "hbm", "kernel": "env_step_kernel<%d,false>" % D, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel_us_mean": mean_s * 1e6, "kernel_us_median": durs[len(durs) // 2] * 1e6,
                 "algorithmic_bytes_per_launch": ROLL * n * BYTES_PER_STEP, "launches_timed": nprof, "steps_per_launch": ROLL,
-                "kernel_us_per_step": mean_s * 1e6 / ROLL}
+                "kernel_us_per_step": mean_s * 1e6 / ROLL, "value_over_kernel_rate": (value / world) / (n / (mean_s / ROLL))}
 
-    # ---- the same kernel at larger lattice counts (extra evidence): at C3's 16 384 lattices a launch is bounded by the
-    #      latency of one CTA's dependent chain; the sweep shows where the kernel goes once a launch has enough tiles
-    scaling = None
+    def rollout_rate(e2, nn, S2, reps):
+        nbuf = max(2, int(300e6 // (nn * e2.obs[0].numel())) + 1)          # rotate observation slots past the L2 size
+        e2.reset()
+        ring2 = torch.zeros((nbuf,) + tuple(e2.obs.shape), dtype=torch.uint8, device=dev)
+        o2 = [torch.empty((S2, nn), dtype=dt, device=dev) for dt in (torch.float32, torch.uint8, torch.int32, torch.int32)]
+        l2 = torch.empty((S2, nn, e2.mask_words), dtype=torch.int64, device=dev)
+
+        def roll2(i):
+            _lib.check(L.dq_env_rollout_random(e2._h, S2, vp(ring2), nbuf, (i * S2) % nbuf, vp(o2[0]), vp(o2[1]), vp(o2[2]), vp(l2),
+                                               vp(o2[3]), 1, cur()))
+        for i in range(2):
+            roll2(i)
+        torch.cuda.synchronize()
+        a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        delay(2.0)
+        a_ev.record()
+        for i in range(reps):
+            roll2(i)
+        b_ev.record()
+        torch.cuda.synchronize()
+        return a_ev.elapsed_time(b_ev) * 1e-3 / (reps * S2)
+
+    # ---- the same kernel at larger lattice counts, and on the other BASELINE configs (extra evidence on rank 0)
+    scaling, others = None, None
     if rank == 0 and not args.no_dqn:
         scaling = []
         peak, _ = measured_peak()
         for nn in (16384, 65536, 262144, 1048576):
             e2 = VecSurfaceCodeEnv(D, P, P, MODEL, USE_Y, VD, None, n_envs=nn, seed=SEED + 5, env_id_base=0, device=dev)
-            nbuf = max(2, int(300e6 // (nn * e2.obs[0].numel())) + 1)          # rotate observation slots past the L2 size
-            e2.reset()
-            ring2 = torch.zeros((nbuf,) + tuple(e2.obs.shape), dtype=torch.uint8, device=dev)
-            S2 = 16
-            o2 = [torch.empty((S2, nn), dtype=dt, device=dev) for dt in (torch.float32, torch.uint8, torch.int32, torch.int32)]
-            l2 = torch.empty((S2, nn, e2.mask_words), dtype=torch.int64, device=dev)
-
-            def roll2(i):
-                _lib.check(L.dq_env_rollout_random(e2._h, S2, vp(ring2), nbuf, (i * S2) % nbuf, vp(o2[0]), vp(o2[1]), vp(o2[2]), vp(l2),
-                                                   vp(o2[3]), 1, cur()))
-            for i in range(2):
-                roll2(i)
-            torch.cuda.synchronize()
-            a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 4
-            a_ev.record()
-            for i in range(reps):
-                roll2(i)
-            b_ev.record()
-            torch.cuda.synchronize()
-            t = a_ev.elapsed_time(b_ev) * 1e-3 / (reps * S2)
-            scaling.append({"lattices": nn, "us_per_step": t * 1e6, "env_steps_per_s": nn / t, "steps_per_launch": S2,
+            t = rollout_rate(e2, nn, 16, 4)
+            scaling.append({"lattices": nn, "us_per_step": t * 1e6, "env_steps_per_s": nn / t, "steps_per_launch": 16,
                             "achieved_GBps": nn * BYTES_PER_STEP / t / 1e9, "frac": nn * BYTES_PER_STEP / t / 1e9 / peak})
-            del ring2, o2, l2
             e2.close()
+        if args.workload == "c3":
+            others = {}
+            for name in ("c5", "c2"):
+                d_, vd_, p_, model_, nn, bytes_ = WORKLOADS[name]
+                e2 = VecSurfaceCodeEnv(d_, p_, p_, model_, False, vd_, None, n_envs=nn, seed=SEED + 6, env_id_base=0, device=dev)
+                t = rollout_rate(e2, nn, 256, 4)
+                others[name] = {"workload": "d=%d %s p=%g volume_depth=%d, %d lattices per GPU" % (d_, model_, p_, vd_, nn),
+                                "us_per_step": t * 1e6, "env_steps_per_s": nn / t, "steps_per_launch": 256,
+                                "algorithmic_bytes_per_lattice_step": bytes_, "achieved_GBps": nn * bytes_ / t / 1e9, "frac": nn * bytes_ / t / 1e9 / peak}
+                e2.close()
 
-    # ---- e2e: host buffers through dq_env_step_host (H2D actions, D2H every output, every step)
-    ke = min(K, 64)
-    rng = np.random.default_rng(SEED + rank)
-    host_actions = torch.from_numpy(rng.integers(0, env.num_actions, size=(ke + 3, n), dtype=np.int32)).pin_memory()
-    hb = env._host_buffers()
-    hp = lambda t: C.c_void_p(t.data_ptr())
-    torch.cuda.synchronize()
+    # ---- e2e: host buffers in and out, every step
+    e2e, e2e_packed = e2e_legs(L, _lib, torch, np, dist, dev, world, rank, n, K)
 
-    def host_step(i):
-        _lib.check(L.dq_env_step_host(h, C.c_void_p(host_actions[i].data_ptr()), hp(hb["obs"]), hp(hb["reward"]),
-                                      hp(hb["done"]), hp(hb["lifetime"]), hp(hb["legal"]), 1))
-    for i in range(3):
-        host_step(i)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(3, ke + 3):
-        host_step(i)
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * ke / float(dt.item())
-    h2d = n * 4
-    d2h = n * (env.obs[0].numel() + 4 + 1 + 4 + 8 * env.mask_words)
-    host_expand = False
-    try:                         # DQ_HOST_EXPAND=1 (opt-in): same call, observations cross PCIe bit-packed and are expanded by host threads
-        he = C.c_int64(0)
-        if L.dq_env_info(h, 10, C.byref(he)) == 0 and he.value == 1:
-            host_expand = True
-            d2h = int((env.state_words - 7) * env.state_stride * 8 + n * (4 + 1 + 4 + 8 * env.mask_words))
-    except Exception:            # noqa: BLE001
-        pass
-
-    # ---- the same loop with the observations returned PACKED (one bit per cell, the rows the Q-network consumes):
-    #      an extra line of evidence next to e2e, never a replacement for it; a failure here must not cost the bench line
-    e2e_packed, packed_err, packed_dt, packed_bytes = None, None, -1.0, 0
-    if world > 1:
-        dist.barrier()
-    try:                         # no collective inside: a failure on one rank must not leave the others waiting
-        pk = env._packed_host_buffer()
-        packed_bytes = int(pk.numel() * 8 + n * (4 + 1 + 4 + 8 * env.mask_words))
-
-        def host_step_packed(i):
-            _lib.check(L.dq_env_step_host_packed(h, C.c_void_p(host_actions[i].data_ptr()), hp(pk), hp(hb["reward"]),
-                                                 hp(hb["done"]), hp(hb["lifetime"]), hp(hb["legal"]), 1))
-        for i in range(3):
-            host_step_packed(i)
-        t0 = time.perf_counter()
-        for i in range(3, ke + 3):
-            host_step_packed(i)
-        packed_dt = time.perf_counter() - t0
-    except Exception as ex:      # noqa: BLE001 -- reported, not fatal
-        packed_err = "%s: %s" % (type(ex).__name__, ex)
-    dtp = torch.tensor([packed_dt, -packed_dt], dtype=torch.float64, device=dev)       # max over ranks of (dt, -dt): slowest, and any failure (-1)
-    if world > 1:
-        dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
-    if packed_err is None and float(dtp[1].item()) < 0:
-        e2e_packed = {"value": world * n * ke / float(dtp[0].item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                      "d2h_bytes_per_step": packed_bytes, "steps": ke,
-                      "api": "dq_env_step_host_packed (observations as bit-packed rows uint64 [C*PW][stride]; "
-                             "envs.unpack_observations expands them on the host when a caller needs bytes)"}
-    else:
-        e2e_packed = {"error": packed_err or "failed on another rank"}
+    # ---- the data-parallel DQN update on every rank (the path's one collective) + sharded evaluation of the published agent
+    dqn_dp = None
+    if not args.no_dqn and args.workload == "c3":
+        try:
+            dqn_dp = dqn_data_parallel_leg(L, _lib, torch, np, dist, dev, world, rank, n)
+        except Exception as ex:      # noqa: BLE001 -- reported: the leg is the same code on every rank, so a failure is one on all of them
+            dqn_dp = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:300])}
 
     # ---- DQN inner loop on the same lattices (extra evidence, not the headline metric):
     #   act:   Q(s) for every lattice from the packed rows in the env state -> eps-greedy pick -> env step (no byte boards)
@@ -461,7 +664,6 @@ def run_b200(args):
         from deepq_decoding_b200.qnet import device_view
         rows_view = device_view(rows_ptr.value, (nrows.value, stride.value), "<i8", dev)
         rring = A.ReplayRing(65, nrows.value, stride.value, n, dev)
-        st = cur()
 
         def act_iter(i, store):
             if store:
@@ -486,6 +688,7 @@ def run_b200(args):
 
         t_fwd = timed(lambda i: agent.model.forward_packed(rows_ptr.value, stride.value, n), 30)
         t_fwd_tc = timed(lambda i: agent.model.forward_packed(rows_ptr.value, stride.value, n, precision="bf16"), 30)
+        t_env = timed(lambda i: _lib.check(L.dq_env_step(h, p_act, None, p_rew, p_done, p_life, p_legal, 1, cur())), 60)
         t_act32 = timed(lambda i: act_iter(i, False), 40)
         agent.act_precision = "bf16"
         t_act = timed(lambda i: act_iter(i, False), 60)
@@ -505,6 +708,7 @@ def run_b200(args):
                "train_env_steps_per_s": n / t_train, "train_ms_per_iteration": t_train * 1e3,
                "train_batch": 4096, "updates_per_iteration": 1,
                "act_fp32_env_steps_per_s": n / t_act32,
+               "env_step_external_actions_us": t_env * 1e6,
                "qnet_forward_fp32_ms": t_fwd * 1e3, "qnet_forward_fp32_tflops": flops * n / t_fwd / 1e12,
                "qnet_forward_bf16_ms": t_fwd_tc * 1e3, "qnet_forward_bf16_tflops": flops * n / t_fwd_tc / 1e12,
                "qnet_frac_of_bf16_sustained_peak": flops * n / t_fwd_tc / 1e12 / tf_peak,
@@ -512,37 +716,8 @@ def run_b200(args):
                "qnet_precision": "acting: bf16 tcgen05 (fp32 accumulate in TMEM); updates: fp32 SIMT",
                "qnet_flops_per_sample": flops, "policy": "eps-greedy 0.1 over legal actions, masked greedy"}
 
-    # ---- logical error rate (second half of the BASELINE metric): the reference's published d5_dp/0.007 agent
-    #      (weights carried as a test fixture) evaluated greedily here, one episode per lattice, LER := 1 / <lifetime>
-    ler = None
-    wpath = os.path.join(ROOT, "tests", "golden", "dqn_d5_dp_0.007.npz")
-    if rank == 0 and not args.no_dqn and os.path.exists(wpath):
-        from deepq_decoding_b200 import agents as A
-        z = np.load(wpath)
-        ev_env = VecSurfaceCodeEnv(D, P, P, MODEL, USE_Y, VD, None, n_envs=n, seed=SEED + 1, env_id_base=10 * n, device=dev)
-        ev = A.DQNAgent(model=A.build_convolutional_nn([[64, 3, 2], [32, 2, 1], [32, 2, 1]], [[512, 0.2]], (7, 11, 11), ev_env.num_actions),
-                        nb_actions=ev_env.num_actions, memory=A.SequentialMemory(limit=100), test_policy=A.GreedyQPolicy(masked_greedy=True),
-                        enable_dueling_network=True, device=dev, act_precision="bf16")
-        ev.compile(A.Adam(lr=1e-5), max_envs=n)
-        ev.model.set_keras_weights([(z["conv%d_k" % i], z["conv%d_b" % i]) for i in range(3)], [(z["dense%d_k" % i], z["dense%d_b" % i]) for i in range(3)])
-        t0 = time.perf_counter()
-        life = np.array(ev.test(ev_env, nb_episodes=n, verbose=0).history["episode_lifetime"], dtype=np.float64)
-        ler = {"agent": "reference trained_models/d5_dp/0.007/final_dqn_weights.h5f (tests/golden fixture), greedy masked policy, bf16 acting",
-               "episodes": int(len(life)), "mean_lifetime_cycles": float(life.mean()), "standard_error": float(life.std() / np.sqrt(len(life))),
-               "logical_error_rate_per_cycle": float(1.0 / life.mean()), "reference_published_mean_lifetime": 270.42,
-               "eval_seconds": time.perf_counter() - t0,
-               "trained_here": "profiles/r1_train_curriculum_dp_p007.json: 342.9 +- 3.7 cycles after 109 s of training from scratch"}
-        ev_env.close()
-
-    experiments = None
-    if rank == 0 and world == 1 and args.workload == "c3" and not args.no_experiments:
-        try:
-            torch.cuda.synchronize()
-            experiments = run_experiments()
-        except Exception as ex:      # noqa: BLE001
-            experiments = {"error": str(ex)[:200]}
     if rank == 0:
-        cb, _, _ = cpu_oracle_run(args.cpu_seconds)
+        full, rest = divmod(K, ROLL)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic",
@@ -550,119 +725,19 @@ def run_b200(args):
                            "l2": "each step writes its %.1f MB of observations into one of %d ring slots (%.0f MB > L2), "
                                  "so no step's writes are absorbed by the previous step's lines" % (
                                      ring[0].numel() / 1e6, RING, ring.numel() / 1e6),
-                           "launch": "rollout launches of %d steps each (dq_env_rollout_random: random-legal pick + env step, every lattice "
-                                     "advanced %d steps per launch; bit-identical to single-step launches)" % (ROLL, ROLL),
-                           "parallelism": "lattices sharded by rank, no data-path collective"},
-                "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": ke, "api": "dq_env_step_host (pinned host actions in, all outputs to pinned host buffers)",
-                        "host_expand": host_expand,
-                        "policy": "uniform random action indices pre-generated on the host"},
-                "e2e_packed": e2e_packed,
+                           "launch": "the %d timed steps ran as %d dq_env_rollout_random launch(es): %d of %d steps%s (random-legal pick + env step of every "
+                                     "lattice per step; bit-identical to single-step launches), queued behind a 2 ms device-side delay so the event pair "
+                                     "brackets device time" % (K, timed_launches, full, ROLL, (" and one of %d" % rest) if rest else ""),
+                           "parallelism": "lattices sharded by rank, no data-path collective (the gradient exchange of training is measured in dqn_dp)"},
+                "clocks": clocks, "e2e": e2e, "e2e_packed": e2e_packed,
                 "gpu_launches": timed_launches, "single_step_launches": single,
-                "roofline": roof, "roofline_scaling": scaling, "cpu_baseline": cb, "dqn": dqn, "logical_error_rate": ler,
-                "experiments": experiments}
+                "roofline": roof, "roofline_scaling": scaling, "other_workloads": others, "cpu_baseline": cb, "dqn_dp": dqn_dp, "dqn": dqn,
+                "logical_error_rate": (dqn_dp or {}).get("logical_error_rate")}
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-
-
-# --------------------------------------------------------------------------------------------- opt-in builds, timed beside the default
-def experiment_child(args):
-    """One opt-in build / mode in its own process (the library and the DQ_* switches are chosen per process): a fixed seeded
-    rollout whose outputs are folded into a checksum (must equal the default build's), then the rollout and host-buffer rates."""
-    import numpy as np
-    import torch
-    from deepq_decoding_b200 import _lib
-    from deepq_decoding_b200.envs import VecSurfaceCodeEnv
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
-    L = _lib.lib()
-    n = N_PER_GPU
-    vp = lambda t: C.c_void_p(t.data_ptr())
-    cur = lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    env = VecSurfaceCodeEnv(D, P, P, MODEL, USE_Y, VD, None, n_envs=n, seed=SEED + 77, env_id_base=0, device=dev)
-    ring = torch.zeros((RING,) + tuple(env.obs.shape), dtype=torch.uint8, device=dev)
-    S = 64
-    out = [torch.empty((S, n), dtype=dt, device=dev) for dt in (torch.float32, torch.uint8, torch.int32, torch.int32)]
-    legal = torch.empty((S, n, env.mask_words), dtype=torch.int64, device=dev)
-    env.reset()
-    _lib.check(L.dq_policy_seek(env._h, 0, cur()))
-
-    def roll(i):
-        _lib.check(L.dq_env_rollout_random(env._h, S, vp(ring), RING, (i * S) % RING, vp(out[0]), vp(out[1]), vp(out[2]), vp(legal), vp(out[3]), 1, cur()))
-    roll(0)
-    torch.cuda.synchronize()
-    mix = lambda t: int((t.to(torch.int64).flatten() * (torch.arange(t.numel(), device=dev, dtype=torch.int64) % 1000003 + 1)).sum().item())
-    checksum = [mix(out[0]), mix(out[1]), mix(out[2]), mix(out[3]), mix(legal), mix(ring.view(torch.uint8)), mix(env.get_state_words())]
-    for i in range(1, 4):
-        roll(i)
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 24
-    a.record()
-    for i in range(reps):
-        roll(4 + i)
-    b.record()
-    torch.cuda.synchronize()
-    us = a.elapsed_time(b) * 1e3 / (reps * S)
-    res = {"checksum": checksum, "rollout_us_per_step": us, "env_steps_per_s": n / us * 1e6, "steps_per_launch": S}
-    # host-buffer rate (dq_env_step_host), as the e2e leg does it
-    rng = np.random.default_rng(SEED)
-    ke = 24
-    host_actions = torch.from_numpy(rng.integers(0, env.num_actions, size=(ke + 3, n), dtype=np.int32)).pin_memory()
-    hb = env._host_buffers()
-    hp = lambda t: C.c_void_p(t.data_ptr())
-    def host_step(i):
-        _lib.check(L.dq_env_step_host(env._h, C.c_void_p(host_actions[i].data_ptr()), hp(hb["obs"]), hp(hb["reward"]),
-                                      hp(hb["done"]), hp(hb["lifetime"]), hp(hb["legal"]), 1))
-    for i in range(3):
-        host_step(i)
-    t0 = time.perf_counter()
-    for i in range(3, ke + 3):
-        host_step(i)
-    dt = time.perf_counter() - t0
-    res["host_env_steps_per_s"] = n * ke / dt
-    res["host_obs_checksum"] = mix(hb["obs"].to(dev))
-    he = C.c_int64(0)
-    res["host_expand"] = bool(L.dq_env_info(env._h, 10, C.byref(he)) == 0 and he.value == 1)
-    env.close()
-    print("EXPERIMENT " + json.dumps(res), flush=True)
-
-
-def run_experiments():
-    """Times the opt-in builds that were written without GPU access next to the default build, each in a child process with a
-    time limit; nothing here feeds `value` / `e2e`.  A child that fails or is missing its library is reported, not fatal."""
-    arms = [("default", {}),
-            ("stream_obs", {"DQ_DECODING_LIB": os.path.join(ROOT, "build", "variants", "libdq_so.so")}),
-            ("defer1_stream_obs", {"DQ_DECODING_LIB": os.path.join(ROOT, "build", "variants", "libdq_dfso.so")}),
-            ("host_expand", {"DQ_HOST_EXPAND": "1"}),
-            ("defer2_stream_obs", {"DQ_DECODING_LIB": os.path.join(ROOT, "build", "variants", "libdq_df2so.so")})]    # last: the one with a new barrier
-    res, t_start = {}, time.perf_counter()
-    for name, extra in arms:
-        if time.perf_counter() - t_start > 150:          # the whole leg stays within a few minutes whatever happens
-            res[name] = {"skipped": "time budget of the experiments leg spent"}
-            continue
-        libp = extra.get("DQ_DECODING_LIB")
-        if libp and not os.path.exists(libp):
-            res[name] = {"skipped": "library not built"}
-            continue
-        try:
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--experiment-child"], env=dict(os.environ, **extra),
-                                 capture_output=True, text=True, timeout=60)
-            line = [l for l in out.stdout.splitlines() if l.startswith("EXPERIMENT ")]
-            res[name] = json.loads(line[-1][len("EXPERIMENT "):]) if line else {"error": (out.stderr or out.stdout)[-300:]}
-        except Exception as ex:      # noqa: BLE001 -- reported, not fatal
-            res[name] = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
-    ref = res.get("default", {})
-    for name, r in res.items():
-        if "checksum" in r and "checksum" in ref:
-            r["identical_to_default_build"] = r["checksum"] == ref["checksum"] and r["host_obs_checksum"] == ref["host_obs_checksum"]
-    for r in res.values():
-        r.pop("checksum", None)
-    return res
 
 
 def select_workload(name):
@@ -683,12 +758,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall budget of the cpu_baseline leg")
     ap.add_argument("--no-dqn", action="store_true", help="skip the DQN inner-loop measurements")
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS), help="BASELINE.json config (default c3 = the metric's)")
-    ap.add_argument("--experiment-child", action="store_true", help=argparse.SUPPRESS)
-    ap.add_argument("--no-experiments", action="store_true", help="skip the child processes that time the opt-in builds")
+    ap.add_argument("--no-experiments", action="store_true", help=argparse.SUPPRESS)      # accepted for older command lines; there is no such leg any more
     args = ap.parse_args()
     select_workload(args.workload)
-    if args.experiment_child:
-        return experiment_child(args)
     if args.workload != "c3":
         args.no_dqn = True
     if args.impl == "reference":

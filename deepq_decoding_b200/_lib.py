@@ -40,6 +40,9 @@ _SIGNATURES = {
     "dq_env_rollout_random": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "dq_env_reset_host": (_i, [_vp, _vp, _vp]),
     "dq_env_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "dq_env_step_host_begin": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "dq_env_step_host_end": (_i, [_vp]),
+    "dq_policy_random_legal_host": (_i, [_vp, _vp, _u32, _vp]),
     "dq_env_reset_host_packed": (_i, [_vp, _vp, _vp]),
     "dq_env_step_host_packed": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "dq_env_get_state": (_i, [_vp, _vp, _vp]),

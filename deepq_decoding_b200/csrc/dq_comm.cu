@@ -16,8 +16,8 @@
 // Double buffering by update parity makes the single barrier sufficient: a rank writes buffer (e+1)&1 only after its
 // update-e kernel returned, and that kernel waited for every peer's "ready e", which a peer sends only after its
 // update-(e-1) kernel (the last reader of that buffer) has finished in stream order.
-// A peer that never arrives cannot hang the GPU: the wait gives up after kSpinLimit clocks and raises a sticky
-// status flag that the host reads with dq_comm_status.
+// A peer that never arrives cannot hang the GPU: the wait gives up after kSpinLimit clocks, raises a sticky
+// status flag that the host reads with dq_comm_status, and the update is skipped (no Adam step on stale gradients).
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -65,15 +65,19 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(Peers peers, int ra
     // ---- 1. "my gradient of this update is complete" -> every rank; wait for theirs -------------------------------
     if (blockIdx.x == 0 && threadIdx.x < world)
         st_release_sys(reinterpret_cast<uint32_t*>(peers.base[threadIdx.x]) + rank, epoch);
+    __shared__ int s_timed_out;
+    if (threadIdx.x == 0) s_timed_out = 0;
+    __syncthreads();
     if (threadIdx.x < world) {
         const uint32_t* f = reinterpret_cast<const uint32_t*>(peers.base[rank]) + threadIdx.x;
         const long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-            if (clock64() - t0 > kSpinLimit) { atomicExch(status, 1); break; }
+            if (clock64() - t0 > kSpinLimit) { atomicExch(status, 1); s_timed_out = 1; break; }
             __nanosleep(64);
         }
     }
     __syncthreads();
+    if (s_timed_out) return;          // a peer never arrived: its gradient is stale or incomplete, so no update is applied (the host sees status)
     // ---- 2. sum in rank order, mean, Adam ------------------------------------------------------------------------------
     const long long n4 = (n + 3) >> 2;                  // the exchange buffers are padded to a multiple of 4 floats (zeros)
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {

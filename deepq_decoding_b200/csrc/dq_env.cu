@@ -72,8 +72,18 @@ static_assert(kWriters >= 1 && kGens >= 1 && kThreads <= 1024, "warp roles");
 constexpr int kMaxVd = 8;
 constexpr int kMaxLayers = kMaxVd + 3;
 constexpr int kQW = kMaxVd + 2;                      // words of a queued attempt: g_0..g_{vd-1}, EX, EZ
-constexpr int kRing = 2;                             // record slots between the physics warp and the writers
-constexpr int kBmWords = kMaxLayers * 4;             // u64 words of a lattice's layer bitmaps at d = 7, deepest volume
+constexpr int kMaxSms = 1024;
+constexpr long long kSpinTrapClocks = 4000000000ll;   // ~2 s of SM clocks: far beyond any legitimate wait for a generator warp
+#ifndef DQ_ROTATE
+#define DQ_ROTATE 0               // 1: rotate the warp roles of the CTAs that share an SM (see env_step_kernel; measured: no gain)
+#endif
+#ifndef DQ_PHYS_LAST
+#define DQ_PHYS_LAST 0            // 1: the physics role on the CTA's last warp instead of its first
+#endif
+#ifndef DQ_RING
+#define DQ_RING 4                // record slots between the physics warp and the writers (power of two)
+#endif
+constexpr int kRing = DQ_RING;
 constexpr int kStreamWords = kLpc * kMaxLayers * 15 * 15 / 32 + 1;
 constexpr int BAR_FULL = 1, BAR_EMPTY = BAR_FULL + kRing, BAR_WRITERS = BAR_EMPTY + kRing;    // named barriers (0 = __syncthreads)
 // The reference loops until a volume is non-trivial, forever if p_phys = p_meas = 0 on a clean frame.
@@ -105,6 +115,7 @@ struct EnvParams {
     u64* state;                                 // [STATE_WORDS][npad]
     u64* queue;                                 // [tile][kQ][kQW][kLpc]: attempt t of a lattice sits in slot t % kQ
     u32* qtail;                                 // [npad]: first attempt index NOT yet queued
+    u32* sm_arrivals;                           // [kMaxSms]: CTAs that have started on each SM, ever (role rotation, see env_step_kernel)
 };
 
 __device__ __forceinline__ int lut2(const uint8_t* lut, u32 idx) { return (__ldg(lut + (idx >> 2)) >> ((idx & 3) * 2)) & 3; }
@@ -132,11 +143,21 @@ __device__ __forceinline__ void bar_arrive_named(int id, int count) {        // 
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 #endif
 }
-__device__ __forceinline__ void spin_pause() {
+__device__ __forceinline__ void spin_pause(unsigned ns = 20) {
 #ifdef DQ_EMU
+    (void)ns;
     dq_emu::yield();
 #else
-    __nanosleep(20);
+    __nanosleep(ns);
+#endif
+}
+__device__ __forceinline__ u32 sm_id() {
+#ifdef DQ_EMU
+    return blockIdx.x;
+#else
+    u32 r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
 #endif
 }
 
@@ -226,9 +247,8 @@ struct Rollout {            // multi-step launch: see env_step_kernel
 };
 
 struct Smem {
-    u64 bm[kLpc][kBmWords];           // [lattice][layer*PW + word]: rendered bitmap of every observation layer (mirror of the state rows)
     u32 stream[kStreamWords];         // the tile's observation bit stream: lattice-major concatenation of the layer bitmaps, P bits each,
-                                      // no padding = byte i of the tile's observations is bit i; kept in step with bm
+                                      // no padding = byte i of the tile's observations is bit i; kept in step with the state's bitmap rows
     u64 lut8[256];                    // byte -> its 8 bits as 8 bytes of 0/1
     // physics -> writers, slot = step & 1
     u64 rec_f[kRing][kMaxVd][kLpc];   // the slices of a lattice's fresh volume
@@ -238,35 +258,35 @@ struct Smem {
     u64 q[kQ][kQW][kLpc];             // rollouts: the tile's volume queues (a single-step launch works on the device-memory copy)
     u32 head[kLpc], tail[kLpc];       // attempt indices: next to pop (= the lattice's attempt counter) / first not yet queued
     u32 quit;                         // the physics warp has popped its last volume of the launch
+    u32 door;                         // bumped by the physics warp with every pop: idle generators watch it
+    u32 rot;                          // warp-role rotation of this CTA
     __align__(16) u32 acc[kGens][3 * kMaxVd * 2];   // per-generator-warp flip accumulators (read back as 64-bit words)
 };
 
-// 32 bits of the tile's observation bit stream starting at bit `o` of (lattice, layer): the stream is the concatenation of the
-// layer bitmaps (P bits each), lattice-major, so a 32-bit window touches at most two of them (P >= 49).  A lattice's bitmap words
-// are contiguous in shared memory, read here as 32-bit words.
+// Layer bitmap w (P bits in PW u64 words, bits >= P zero) -> its place in the tile's bit stream: bits [off, off + P), at any alignment.
+// Whole stream words are stored; the two end words are shared with the neighbouring layers, which other threads may be placing right
+// now, so there only this layer's bits are replaced, atomically.
 template <int D>
-__device__ __forceinline__ u32 gather32(const Smem& sm, int lat, int layer, int o, int C) {
-    typedef Lat<D> L;
-    constexpr int PW = L::PW, P = L::P;
-    const u32* w = reinterpret_cast<const u32*>(&sm.bm[lat][layer * PW]) + (o >> 5);
-    u32 v = __funnelshift_r(w[0], w[1], o & 31);     // w[1] may belong to the next layer: those bits are masked off below
-    const int n1 = P - o;                             // bits left in this layer (bits >= P of a bitmap are zero)
-    if (n1 < 32) {
-        v &= (1u << n1) - 1u;
-        int l2 = layer + 1, lat2 = lat;
-        if (l2 == C) { l2 = 0; lat2 = lat + 1; }
-        if (lat2 < kLpc) v |= reinterpret_cast<const u32*>(&sm.bm[lat2][l2 * PW])[0] << n1;
+__device__ __forceinline__ void place_layer(u32* stream, int off, const u64 (&w)[Lat<D>::PW]) {
+    constexpr int P = Lat<D>::P, PW = Lat<D>::PW, NV = 2 * PW, JMAX = (P + 62) / 32;
+    u32 v[NV];
+#pragma unroll
+    for (int i = 0; i < PW; ++i) { v[2 * i] = (u32)w[i]; v[2 * i + 1] = (u32)(w[i] >> 32); }
+    const int k0 = off >> 5, sh = off & 31, end = sh + P;            // the layer occupies bits [sh, end) counted from word k0
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j) {
+        if (j * 32 < end) {
+            const u32 lo = (j >= 1 && j - 1 < NV) ? v[j >= 1 ? j - 1 : 0] : 0u, hi = j < NV ? v[j < NV ? j : 0] : 0u;
+            const u32 slice = __funnelshift_l(lo, hi, sh);            // (hi << sh) | (lo >> (32 - sh))
+            const int b0 = j == 0 ? sh : 0, b1 = min(end - j * 32, 32);
+            if (b0 == 0 && b1 == 32) stream[k0 + j] = slice;
+            else {
+                const u32 mask = (b1 == 32 ? 0xffffffffu : ((1u << b1) - 1u)) & ~((1u << b0) - 1u);
+                atomicAnd(&stream[k0 + j], ~mask);
+                atomicOr(&stream[k0 + j], slice & mask);
+            }
+        }
     }
-    return v;
-}
-
-// word `wi` of the tile's observation bit stream, gathered from the layer bitmaps
-template <int D>
-__device__ __forceinline__ u32 stream_word(const Smem& sm, const EnvParams& p, int wi, int C) {
-    const int g = wi * 32;
-    const int lat = (int)__umulhi((u32)g, p.ob_magic), r = g - lat * p.obs_bits;
-    const int layer = r / Lat<D>::P, o = r - layer * Lat<D>::P;
-    return lat < kLpc ? gather32<D>(sm, lat, layer, o, C) : 0u;
 }
 
 __device__ __forceinline__ uint4 expand16(const Smem& sm, u32 h) {     // low 16 bits -> 16 bytes of 0/1 (two table lookups)
@@ -278,22 +298,6 @@ __device__ __forceinline__ uint4 expand16(const Smem& sm, u32 h) {     // low 16
 // Observation bytes are never read back by this kernel: evict-first stores (STG.E.EF.128) keep the ring of them that streams
 // through L2 from evicting the 4 MB joint referee table.
 __device__ __forceinline__ void store_obs16(uint8_t* dst, const uint4 v) { __stcs(reinterpret_cast<uint4*>(dst), v); }
-
-// Word `wi` of the bit stream as the expansion needs it.  A lattice whose bitmaps changed (bit set in `dm`: fresh volume) has a
-// stale span; the thread that expands a word overlapping such a lattice gathers it from the bitmaps and puts it back (every word
-// has one owner per pass; the bitmaps are not written during the pass).
-template <int D>
-__device__ __forceinline__ u32 fresh_word(Smem& sm, const EnvParams& p, int wi, u32 dm, int C) {
-    if (dm) {
-        const u32 la = __umulhi((u32)(wi * 32), p.ob_magic), lb = min(__umulhi((u32)(wi * 32 + 31), p.ob_magic), (u32)(kLpc - 1));
-        if (((dm >> la) | (dm >> lb)) & 1u) {       // la <= lb < kLpc
-            const u32 v = stream_word<D>(sm, p, wi, C);
-            sm.stream[wi] = v;
-            return v;
-        }
-    }
-    return sm.stream[wi];
-}
 
 // Legal-move mask words of one lattice (Environments.py:238-271 in closed form): qubits touching the summed faulty syndrome
 // or next to an already acted-on qubit, in every action layer, plus the identity.
@@ -330,9 +334,7 @@ __device__ __noinline__ void write_observations_unaligned(const Smem& sm, uint8_
         }
     }
 }
-template <int D>
-__device__ __forceinline__ void write_observations(Smem& sm, const EnvParams& p, uint8_t* obs, int env0, int nvalid,
-                                                   int t, int nthr, u32 dm, int C) {
+__device__ __forceinline__ void write_observations(const Smem& sm, const EnvParams& p, uint8_t* obs, int env0, int nvalid, int t, int nthr) {
     const int vbytes = nvalid * p.obs_bits;
     uint8_t* out = obs + (size_t)env0 * p.obs_bits;
     const int align = (int)(reinterpret_cast<uintptr_t>(out) & 15);
@@ -340,17 +342,15 @@ __device__ __forceinline__ void write_observations(Smem& sm, const EnvParams& p,
     if (align == 0) {
 #pragma unroll 2
         for (int g = t * 32; g < full; g += nthr * 32) {
-            const u32 word = fresh_word<D>(sm, p, g >> 5, dm, C);
+            const u32 word = sm.stream[g >> 5];
             store_obs16(out + g, expand16(sm, word));
             store_obs16(out + g + 16, expand16(sm, word >> 16));
         }
     } else {
-        if (dm)                                                                   // same word ownership as the copy loop below
-            for (int g = t * 32; g < full; g += nthr * 32) fresh_word<D>(sm, p, g >> 5, dm, C);
         write_observations_unaligned(sm, out, full, align, t, nthr);
     }
     if (t == 0 && full < vbytes) {                                                 // the tile's last, partial group
-        const u32 word = fresh_word<D>(sm, p, full >> 5, dm, C);
+        const u32 word = sm.stream[full >> 5];
         for (int b = 0; b < vbytes - full; ++b) out[full + b] = (uint8_t)((word >> b) & 1u);
     }
 }
@@ -377,13 +377,9 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     // A rollout keeps the tile's volume queues in shared memory for the launch; a single step pops and refills the device-memory copy in place.
     const bool q_in_smem = ro.nsteps > 1;
     u64* const gq = p.queue + (size_t)blockIdx.x * (kQ * kQW * kLpc);
-    volatile u64* const qp = q_in_smem ? &sm.q[0][0][0] : gq;
+    volatile u64* const qp = q_in_smem ? &sm.q[0][0][0] : gq;             // (the generators' stores go through this generic pointer)
 
     // ---- prologue: layer bitmaps, expansion table, queue and its counters
-    for (int i = tid; i < C * PW * kLpc; i += kThreads) {
-        const int row = i / kLpc, l = i - row * kLpc;
-        sm.bm[l][row] = p.state[(ROW_BM + row) * np + env0 + l];
-    }
     for (int i = tid; i < 256; i += kThreads)
         sm.lut8[i] = (u64)((((u32)i & 0xFu) * 0x00204081u) & 0x01010101u) | ((u64)((((u32)i >> 4) * 0x00204081u) & 0x01010101u) << 32);
     if (q_in_smem) {
@@ -395,14 +391,30 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         u32 tail = p.qtail[env0 + tid];
         if (p.q_reset || tail - head > (u32)kQ) tail = head;      // nothing usable queued (first launch, injected state, new noise rates)
         sm.head[tid] = head; sm.tail[tid] = tail;
-        if (tid == 0) sm.quit = 0;
+        if (tid == 0) {
+            sm.quit = 0; sm.door = 0;
+            // Warp w of a CTA runs on scheduler (w mod 4) of its SM when CTAs are multiples of four warps, so without a rotation
+            // every physics warp of an SM -- the one dependent chain that sets the step time -- would share ONE scheduler with
+            // its siblings of the co-resident CTAs.  The k-th CTA to start on an SM rotates its roles by k.
+#if DQ_ROTATE
+            sm.rot = atomicAdd(&p.sm_arrivals[sm_id() % kMaxSms], 1u) % (u32)(kThreads / 32);
+#else
+            sm.rot = 0;
+#endif
+        }
     }
     __syncthreads();
+#if DQ_PHYS_LAST
+    const int role = (kThreads / 32) - 1 - warp;                                   // the physics warp is the CTA's last warp
+#else
+    const int role = (warp + (kThreads / 32) - (int)sm.rot) % (kThreads / 32);     // 0 physics, 1..kWriters writers, then generators
+#endif
 
-    if (warp == 0) {
+    if (role == 0) {
         // ================================================================== PHYSICS: lane = lattice
         const int e = env0 + lane;
         const bool live = lane < nvalid;
+        const bool policy = !RESET && policy_ctr != nullptr;
         const u32 env_id = p.env_id_base + (u32)e;
         volatile u32* const vtail = sm.tail;
         volatile u32* const vhead = sm.head;
@@ -417,105 +429,149 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             for (int l = 0; l < 3; ++l) if (l < p.layers) act[l] = p.state[(ROW_ACT + l) * np + e];
         }
         u64 mw[3] = {0, 0, 0};              // legal-move mask after the latest step (feeds the next built-in pick)
-        if (!RESET && policy_ctr) legal_words<D>(p, summed, act[0] | act[1] | act[2], mw);
-        // built-in policy: the random word of a pick depends only on (lattice, step index); the next step's word is drawn
-        // beside this step's dependent chain
-        u32 pick_u = (!RESET && policy_ctr) ? philox4x32_10(env_id, step0, 0u, 1u, p.k0, p.k1).x : 0u;
+        if (policy) legal_words<D>(p, summed, act[0] | act[1] | act[2], mw);
+
+        // ---- the first half of a step (Environments.py:131-150): action -> Pauli frame, true syndrome, homology label, and the
+        // referee's class -- a table gather whose L2 latency is the longest single wait of the chain.  With the built-in policy the
+        // next step's pick only needs this step's legal mask, so this half runs at the END of the previous iteration and the
+        // gather is in flight while that iteration stores its outputs and the next one pops its heavy volumes; its result
+        // (a_cls) is first looked at when `done` is decided.
+        bool a_heavy = false;
+        int a_actbit = -1, a_label = 0, a_cls = 0;
+        float a_rw = 0.f;
+        auto first_half = [&](int a) {
+            if (a < 0 || a >= p.A) a = p.A - 1;
+            const bool ident = (a == p.A - 1);
+            const int layer = ident ? 0 : a / L::NQ, q = ident ? 0 : a % L::NQ;
+            const int qr = q / D, qc = q - qr * D;
+            const u64 bit = ident ? 0ull : (1ull << (q + qr));
+            const u64 cur = layer == 0 ? act[0] : (layer == 1 ? act[1] : act[2]);
+            a_heavy = ident || (cur & bit) != 0;
+            // Pauli applied by this action layer (Function_Library.py:253-304)
+            bool fx, fz;
+            if (p.model == DQ_MODEL_X) { fx = true; fz = false; }
+            else if (p.use_y) { fx = layer <= 1; fz = layer >= 1; }
+            else { fx = layer == 0; fz = layer == 1; }
+            if (fx) xb ^= bit;
+            if (fz) zb ^= bit;
+            const u64 syn = true_syndrome<D>(xb, zb);
+            a_label = homology_label<D>(xb, zb);
+            a_rw = (a_label == 0 && syn == 0) ? 1.f : 0.f;
+            a_cls = a_label;
+            if (a_rw == 0.f && live) a_cls = referee_class<D>(p, syn);
+            a_actbit = -1;
+            if (!a_heavy) {
+                if (layer == 0) act[0] |= bit; else if (layer == 1) act[1] |= bit; else act[2] |= bit;
+                a_actbit = (layer << 16) | ((2 * qr + 1) * H + 2 * qc + 1);
+            }
+        };
+        // built-in random-legal policy: the pick dq_policy_random_legal would make on this lattice's current legal set
+        auto pick_action = [&](u32 word_u) {
+            const int c0 = popc64(mw[0]), c1 = popc64(mw[1]);
+            const int cnt = c0 + c1 + popc64(mw[2]);
+            int pick = (int)mulhi32(word_u, (u32)cnt);              // < cnt (cnt >= 1: the identity is always legal)
+            u64 word = mw[0];
+            int wbase = 0;
+            if (pick >= c0 + c1) { pick -= c0 + c1; word = mw[2]; wbase = 128; }
+            else if (pick >= c0) { pick -= c0; word = mw[1]; wbase = 64; }
+            return cnt > 0 ? wbase + select64(word, pick) : p.A - 1;
+        };
+        if (policy) {
+            const int a = live ? pick_action(philox4x32_10(env_id, step0, 0u, 1u, p.k0, p.k1).x) : p.A - 1;
+            if (actions_out0 && live) actions_out0[e] = a;
+            first_half(a);
+        }
+
+        // one pass of the volume loop (Environments.py:158-170): every lane that still needs a volume pops one queued attempt
+        u32 todo = 0;
+        int guard = 0;
+        bool restarted = false;
+        u64 sum_new = 0;
+        int32_t life_out = 0;
+        auto pop_pass = [&](int r) {
+            if (todo) {
+                if (todo == 2u && !restarted) { xb = 0; zb = 0; life = 0; dn = 0; restarted = true; }     // a restart begins on a clean frame
+                if (vtail[lane] == attempts) {                        // (rare) the generators have not queued this attempt yet
+                    const long long t0 = clock64();
+                    while (vtail[lane] == attempts) {
+                        spin_pause();
+                        if (clock64() - t0 > kSpinTrapClocks) __trap();   // a lost hand-off must end the launch with an error, not hang the GPU
+                    }
+                }
+                __threadfence_block();
+                const int slot = (int)(attempts & (u32)(kQ - 1));
+                const u64 s0 = true_syndrome<D>(xb, zb);
+                u64 g[kMaxVd], ex, ez;
+                if (q_in_smem) {                                      // rollout: plain shared-memory loads
+#pragma unroll
+                    for (int j = 0; j < kMaxVd; ++j) g[j] = j < p.vd ? sm.q[slot][j][lane] : 0ull;
+                    ex = sm.q[slot][kMaxVd][lane]; ez = sm.q[slot][kMaxVd + 1][lane];
+                } else {                                              // single step: the device-memory copy, refilled in place by this CTA's generators
+                    const volatile u64* const ent = gq + (size_t)slot * (kQW * kLpc) + lane;
+#pragma unroll
+                    for (int j = 0; j < kMaxVd; ++j) g[j] = j < p.vd ? ent[j * kLpc] : 0ull;
+                    ex = ent[kMaxVd * kLpc]; ez = ent[(kMaxVd + 1) * kLpc];
+                }
+                u64 nz = 0;
+#pragma unroll
+                for (int j = 0; j < kMaxVd; ++j) {
+                    if (j < p.vd) {
+                        const u64 fj = g[j] ^ s0;
+                        nz |= fj;
+                        sm.rec_f[r][j][lane] = fj;
+                    }
+                }
+                xb ^= ex;
+                zb ^= ez;
+                life += (u32)p.vd;
+                attempts += 1;
+                if (nz != 0 || ++guard >= p.max_attempts) {
+                    sum_new = nz;
+                    guard = 0;
+                    if (todo & 1u) { life_out = (int32_t)life; todo &= ~1u; }
+                    else todo = 0;
+                }
+                __threadfence_block();                                // the entry has been read before its slot is offered for refill
+                vhead[lane] = attempts;
+                __threadfence_block();
+                atomicAdd(&sm.door, 1u);                              // wake idle generators NOW: this lane may need the refill within this very step
+            }
+        };
 
         size_t oo = 0;
         for (int rs = 0; rs < ro.nsteps; ++rs, oo += ro.out_stride) {
             const int r = rs & (kRing - 1);
+            // the next pick's random word depends on (lattice, step index) only: drawn beside this step's dependent chain
             u32 pick_next = 0;
-            if (!RESET && policy_ctr && rs + 1 < ro.nsteps) pick_next = philox4x32_10(env_id, step0 + (u32)rs + 1u, 0u, 1u, p.k0, p.k1).x;
-            u32 flags = 0, dn_out = 0;
-            int actbit = -1;
-            float rw = 0.f;
-            if (!RESET) {
-                int a = (live && actions) ? actions[e] : p.A - 1;
-                if (policy_ctr && live) {
-                    // built-in random-legal policy: the pick dq_policy_random_legal would make on this lattice's current legal set
-                    const int ib = p.A - 1;
-                    const int c0 = popc64(mw[0]), c1 = popc64(mw[1]);
-                    const int cnt = c0 + c1 + popc64(mw[2]);
-                    int pick = (int)mulhi32(pick_u, (u32)cnt);              // < cnt (cnt >= 1: the identity is always legal)
-                    u64 word = mw[0];
-                    int wbase = 0;
-                    if (pick >= c0 + c1) { pick -= c0 + c1; word = mw[2]; wbase = 128; }
-                    else if (pick >= c0) { pick -= c0; word = mw[1]; wbase = 64; }
-                    a = cnt > 0 ? wbase + select64(word, pick) : ib;
-                    if (actions_out0) actions_out0[oo + e] = a;
-                }
-                if (a < 0 || a >= p.A) a = p.A - 1;
-                const bool ident = (a == p.A - 1);
-                const int layer = ident ? 0 : a / L::NQ, q = ident ? 0 : a % L::NQ;
-                const int qr = q / D, qc = q - qr * D;
-                const u64 bit = ident ? 0ull : (1ull << (q + qr));
-                const u64 cur = layer == 0 ? act[0] : (layer == 1 ? act[1] : act[2]);
-                const bool heavy = ident || (cur & bit) != 0;
-                // Pauli applied by this action layer (Function_Library.py:253-304)
-                bool fx, fz;
-                if (p.model == DQ_MODEL_X) { fx = true; fz = false; }
-                else if (p.use_y) { fx = layer <= 1; fz = layer >= 1; }
-                else { fx = layer == 0; fz = layer == 1; }
-                if (fx) xb ^= bit;
-                if (fz) zb ^= bit;
-                const u64 syn = true_syndrome<D>(xb, zb);
-                const int label = homology_label<D>(xb, zb);
-                if (label == 0 && syn == 0) rw = 1.f;
-                else if (live && referee_class<D>(p, syn) != label) dn = 1;
-                if (!heavy) {
-                    if (layer == 0) act[0] |= bit; else if (layer == 1) act[1] |= bit; else act[2] |= bit;
-                    actbit = (layer << 16) | ((2 * qr + 1) * H + 2 * qc + 1);
-                }
-                dn_out = dn;
-                if (live) flags = (heavy ? 1u : 0u) | ((dn && auto_reset) ? 2u : 0u);     // padding lattices never draw volumes
-            } else if (live) {
-                flags = 2u;               // reset keeps only the attempt counter (the position in the random stream)
-            }
-            int32_t life_out = (int32_t)life;
+            if (policy && rs + 1 < ro.nsteps) pick_next = philox4x32_10(env_id, step0 + (u32)rs + 1u, 0u, 1u, p.k0, p.k1).x;
+            if (!RESET && !policy) first_half((live && actions) ? actions[e] : p.A - 1);
 
             // the record slot of this step must have been read by the writers (they run at most kRing steps behind)
             if (rs >= kRing) bar_sync_named(BAR_EMPTY + r, 32 + kWriterThreads);
 
             // ---- fresh volume(s): bit 0 of todo = heavy step (volume on the current frame), bit 1 = restart of a finished lattice
-            // (volume on a clean frame), in that order.  Each pass pops one queued attempt for every lane that still needs one.
-            u32 todo = flags;
-            int guard = 0;
-            u64 sum_new = 0;
-            if (todo == 2u) { xb = 0; zb = 0; life = 0; dn = 0; }
-            while (__any_sync(FULL, todo != 0)) {
-                if (todo) {
-                    while (vtail[lane] == attempts) spin_pause();         // (rare) the generators have not queued this attempt yet
-                    __threadfence_block();
-                    volatile u64* const ent = qp + (size_t)(attempts & (u32)(kQ - 1)) * (kQW * kLpc) + lane;
-                    const u64 s0 = true_syndrome<D>(xb, zb);
-                    u64 nz = 0;
-#pragma unroll
-                    for (int j = 0; j < kMaxVd; ++j) {
-                        if (j < p.vd) {
-                            const u64 fj = ent[j * kLpc] ^ s0;
-                            nz |= fj;
-                            sm.rec_f[r][j][lane] = fj;
-                        }
-                    }
-                    xb ^= ent[kMaxVd * kLpc];
-                    zb ^= ent[(kMaxVd + 1) * kLpc];
-                    life += (u32)p.vd;
-                    attempts += 1;
-                    if (nz != 0 || ++guard >= p.max_attempts) {
-                        sum_new = nz;
-                        guard = 0;
-                        if (todo & 1u) {
-                            life_out = (int32_t)life;
-                            todo &= ~1u;
-                            if (todo) { xb = 0; zb = 0; life = 0; dn = 0; }
-                        } else todo = 0;
-                    }
-                    __threadfence_block();                                // the entry has been read before its slot is offered for refill
-                    vhead[lane] = attempts;
-                }
+            // (volume on a clean frame), in that order.  The heavy volumes do not depend on the referee, so their first pass runs
+            // before `done` is decided.
+            life_out = (int32_t)life;
+            restarted = false;
+            guard = 0;
+            u32 dn_out = 0;
+            float rw = 0.f;
+            int actbit = -1;
+            bool heavy = false;
+            if (!RESET) {
+                heavy = live && a_heavy;
+                rw = a_rw; actbit = a_actbit;
+                todo = heavy ? 1u : 0u;
+                if (__any_sync(FULL, todo != 0)) pop_pass(r);
+                if (live && a_cls != a_label) dn = 1;                    // Environments.py:150 (a rewarded step cannot end the episode: a_cls == a_label there)
+                dn_out = dn;
+                if (live && dn && auto_reset) todo |= 2u;
+            } else {
+                todo = live ? 2u : 0u;    // reset keeps only the attempt counter (the position in the random stream)
             }
-            const bool vol = flags != 0;
+            const bool vol = heavy || todo != 0;
+            while (__any_sync(FULL, todo != 0)) pop_pass(r);
             if (vol) { act[0] = 0; act[1] = 0; act[2] = 0; summed = sum_new; }
             sm.rec_actbit[r][lane] = vol ? -1 : actbit;
             const u32 vm = __ballot_sync(FULL, vol);
@@ -523,23 +579,28 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             __threadfence_block();
             bar_arrive_named(BAR_FULL + r, 32 + kWriterThreads);
 
-            // ---- lifetime, legal mask, the small outputs
+            // ---- legal mask; with the built-in policy the next step's pick and first half (its referee gather goes out here)
+            if (legal0 || policy) legal_words<D>(p, summed, act[0] | act[1] | act[2], mw);
+            const int32_t life_now = life_out;
+            u64 lw0 = mw[0], lw1 = mw[1], lw2 = mw[2];
+            if (policy && rs + 1 < ro.nsteps) {
+                const int a = live ? pick_action(pick_next) : p.A - 1;
+                if (actions_out0 && live) actions_out0[oo + ro.out_stride + e] = a;
+                first_half(a);
+            }
+            // ---- the small outputs of this step
             if (live) {
                 if (!RESET) {
                     if (reward0) reward0[oo + e] = rw;
                     if (done0) done0[oo + e] = (uint8_t)dn_out;
-                    if (lifetime0) lifetime0[oo + e] = life_out;
+                    if (lifetime0) lifetime0[oo + e] = life_now;
+                }
+                if (legal0) {
+                    legal0[(oo + e) * p.W] = lw0;
+                    if (p.W > 1) legal0[(oo + e) * p.W + 1] = lw1;
+                    if (p.W > 2) legal0[(oo + e) * p.W + 2] = lw2;
                 }
             }
-            if (legal0 || policy_ctr) {
-                legal_words<D>(p, summed, act[0] | act[1] | act[2], mw);
-                if (legal0 && live) {
-#pragma unroll
-                    for (int i = 0; i < 3; ++i)
-                        if (i < p.W) legal0[(oo + e) * p.W + i] = mw[i];
-                }
-            }
-            pick_u = pick_next;
         }
         // the lattice's state goes back to its rows
         p.state[ROW_XB * np + e] = xb;
@@ -550,24 +611,33 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         for (int l = 0; l < 3; ++l) if (l < p.layers) p.state[(ROW_ACT + l) * np + e] = act[l];
         __threadfence_block();
         if (lane == 0) *reinterpret_cast<volatile u32*>(&sm.quit) = 1u;
-    } else if (warp <= kWriters) {
+    } else if (role <= kWriters) {
         // ================================================================== WRITERS
-        const int t = tid - 32;
+        const int t = (role - 1) * 32 + lane;
         int ring_slot = ro.first_slot;
+        // the stream as the state stands at launch: every (lattice, layer) bitmap row into its place (while the physics warp runs step 0)
+        if (obs0) {
+            for (int i = t; i < kLpc * C; i += kWriterThreads) {
+                const int l = i / C, c = i - l * C;
+                u64 w[PW];
+#pragma unroll
+                for (int j = 0; j < PW; ++j) w[j] = p.state[(ROW_BM + c * PW + j) * np + env0 + l];
+                place_layer<D>(sm.stream, l * p.obs_bits + c * L::P, w);
+            }
+        }
+        bar_sync_named(BAR_WRITERS, kWriterThreads);
         for (int rs = 0; rs < ro.nsteps; ++rs) {
             const int r = rs & (kRing - 1);
             uint8_t* const obs = obs0 ? obs0 + (size_t)ring_slot * ro.slot_bytes : nullptr;
             bar_sync_named(BAR_FULL + r, 32 + kWriterThreads);
             const u32 vm = sm.rec_volmask[r];
-            // (1) apply the step's record to the bitmaps (and their state rows): a light step lights one more cell of its action layer ...
+            // (1) apply the step's record to the state's bitmap rows and to the stream: a light step lights one more cell of its action layer ...
             if (t < kLpc) {
                 const int ab = sm.rec_actbit[r][t];
                 if (ab >= 0) {
                     const int pos = ab & 0xFFFF, row = (p.vd + (ab >> 16)) * PW + (pos >> 6);
-                    const u64 wv = sm.bm[t][row] | (1ull << (pos & 63));
-                    sm.bm[t][row] = wv;
-                    p.state[(ROW_BM + row) * np + env0 + t] = wv;
-                    if (obs0 && rs > 0) {                     // (the first pass of a launch gathers the whole stream)
+                    atomicOr(reinterpret_cast<unsigned long long*>(&p.state[(ROW_BM + row) * np + env0 + t]), 1ull << (pos & 63));
+                    if (obs0) {
                         const int sb = t * p.obs_bits + (p.vd + (ab >> 16)) * L::P + pos;
                         atomicOr(&sm.stream[sb >> 5], 1u << (sb & 31));
                     }
@@ -583,29 +653,31 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                     syndrome_layer_bitmap<D>(sm.rec_f[r][min(c, kMaxVd - 1)][slot], w);
 #pragma unroll
                     for (int j = 0; j < PW; ++j) {
-                        const u64 v = c < p.vd ? w[j] : 0ull;               // an action layer has no marker cells
-                        sm.bm[slot][c * PW + j] = v;
-                        p.state[(ROW_BM + c * PW + j) * np + env0 + slot] = v;
+                        if (c >= p.vd) w[j] = 0ull;                          // an action layer has no marker cells
+                        p.state[(ROW_BM + c * PW + j) * np + env0 + slot] = w[j];
                     }
+                    if (obs0) place_layer<D>(sm.stream, slot * p.obs_bits + c * L::P, w);
                 }
             }
             if (rs + kRing < ro.nsteps) bar_arrive_named(BAR_EMPTY + r, 32 + kWriterThreads);     // this thread is done with the record
             bar_sync_named(BAR_WRITERS, kWriterThreads);
             // (2) the tile's observation bytes
-            if (obs) write_observations<D>(sm, p, obs, env0, nvalid, t, kWriterThreads, rs == 0 ? FULL : vm, C);
+            if (obs) write_observations(sm, p, obs, env0, nvalid, t, kWriterThreads);
             ring_slot = (ring_slot + 1 == ro.slots) ? 0 : ring_slot + 1;
         }
     } else {
         // ================================================================== GENERATORS
-        const int g = warp - 1 - kWriters;
+        const int g = role - 1 - kWriters;
         u32* const acc = sm.acc[g];
         volatile u32* const vtail = sm.tail;
         volatile u32* const vhead = sm.head;
         const int mine = lane * kGens + g;                        // lanes < kOwned look at one owned lattice each
         for (;;) {
             u32 quit = *reinterpret_cast<volatile u32*>(&sm.quit);
-            __threadfence_block();                                 // quit is read BEFORE the heads it was published after
+            u32 door = *reinterpret_cast<volatile u32*>(&sm.door);
+            __threadfence_block();                                 // quit / door are read BEFORE the heads they were published after
             quit = __shfl_sync(FULL, quit, 0);                     // one value for the warp: the lanes leave the loop together
+            door = __shfl_sync(FULL, door, 0);
             u32 key = 0;                                           // (emptiness << 8) | (255 - lane): the emptiest queue first, then the lowest lattice
             if (lane < kOwned && mine < nvalid) {
                 const u32 fill = vtail[mine] - vhead[mine];
@@ -613,9 +685,14 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             }
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) key = max(key, __shfl_xor_sync(FULL, key, off));
-            if (key == 0) {
+            if (key == 0) {                                        // every queue of this warp is full
                 if (quit) break;
-                spin_pause();
+                for (;;) {                                         // sleep until the physics warp pops again (or ends): one shared-memory word to watch
+                    u32 d = *reinterpret_cast<volatile u32*>(&sm.door) ^ door;
+                    d |= *reinterpret_cast<volatile u32*>(&sm.quit);
+                    if (__shfl_sync(FULL, d, 0)) break;
+                    spin_pause(200);
+                }
                 continue;
             }
             const int l = (255 - (int)(key & 0xFFu)) * kGens + g;
@@ -676,6 +753,13 @@ __global__ void set_u32_kernel(u32* p, u32 v) { p[0] = v; p[1] = 0; }
 // ======================================================================== host side / C ABI
 using namespace dq;
 
+constexpr int kHostChunks = 4;
+struct HostCall {                // outputs of a host-buffer call between its begin and its end
+    uint8_t* obs; float* reward; uint8_t* done; int32_t* life; uint64_t* legal;
+    int chunks, first[kHostChunks], last[kHostChunks];
+    bool pending;
+};
+
 struct dq_env {
     EnvParams p;
     int device;
@@ -687,6 +771,8 @@ struct dq_env {
     int32_t* s_actions; uint8_t* s_obs; float* s_reward; uint8_t* s_done; int32_t* s_life; u64* s_legal;
     u64* h_packed;               // pinned landing buffer of the bit-packed observation rows (host-side expansion)
     bool q_reset;                // the next launch must discard the queued volume attempts (noise rates changed)
+    cudaEvent_t h_ev[kHostChunks];   // "this lattice range of the rows has landed"
+    HostCall hc;                 // the host-buffer call in flight (dq_env_step_host_begin .. _end)
 };
 
 static std::atomic<long long> g_launches{0};
@@ -777,8 +863,10 @@ extern "C" int dq_env_create(dq_env** out, int d, int error_model, int use_Y, in
     if (err == cudaSuccess) err = cudaMemset(p.queue, 0, qwords * sizeof(u64));
     if (err == cudaSuccess) err = cudaMalloc(&p.qtail, (size_t)p.npad * sizeof(u32));
     if (err == cudaSuccess) err = cudaMemset(p.qtail, 0, (size_t)p.npad * sizeof(u32));
+    if (err == cudaSuccess) err = cudaMalloc(&p.sm_arrivals, kMaxSms * sizeof(u32));
+    if (err == cudaSuccess) err = cudaMemset(p.sm_arrivals, 0, kMaxSms * sizeof(u32));
     if (err != cudaSuccess) {
-        cudaFree(p.queue); cudaFree(p.qtail); cudaFree(e->policy_ctr); cudaFree(p.state); delete e;
+        cudaFree(p.queue); cudaFree(p.qtail); cudaFree(p.sm_arrivals); cudaFree(e->policy_ctr); cudaFree(p.state); delete e;
         return fail(DQ_ECUDA, std::string("cudaMalloc(volume queues): ") + cudaGetErrorString(err));
     }
     p.max_attempts = kMaxAttemptsPerCall;
@@ -793,11 +881,13 @@ extern "C" int dq_env_destroy(dq_env* e) {
         cudaStreamSynchronize(e->hstream);
         cudaFree(e->s_actions); cudaFree(e->s_obs); cudaFree(e->s_reward); cudaFree(e->s_done); cudaFree(e->s_life); cudaFree(e->s_legal);
         if (e->h_packed) cudaFreeHost(e->h_packed);
+        for (int c = 0; c < kHostChunks; ++c) if (e->h_ev[c]) cudaEventDestroy(e->h_ev[c]);
         cudaStreamDestroy(e->hstream);
     }
     cudaFree(e->p.state);
     cudaFree(e->p.queue);
     cudaFree(e->p.qtail);
+    cudaFree(e->p.sm_arrivals);
     cudaFree(e->policy_ctr);
     delete e;
     return DQ_OK;
@@ -914,60 +1004,67 @@ static int ensure_staging(dq_env* e) {
     const EnvParams& p = e->p;
     DQ_CUDA(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
     DQ_CUDA(cudaMalloc(&e->s_actions, (size_t)p.n * 4));
-    DQ_CUDA(cudaMalloc(&e->s_obs, (size_t)p.n * p.obs_bits));
     DQ_CUDA(cudaMalloc(&e->s_reward, (size_t)p.n * 4));
     DQ_CUDA(cudaMalloc(&e->s_done, (size_t)p.n));
     DQ_CUDA(cudaMalloc(&e->s_life, (size_t)p.n * 4));
     DQ_CUDA(cudaMalloc(&e->s_legal, (size_t)p.n * p.W * 8));
+    for (int c = 0; c < kHostChunks; ++c) DQ_CUDA(cudaEventCreateWithFlags(&e->h_ev[c], cudaEventDisableTiming));
     return DQ_OK;
 }
 
-// ---- DQ_HOST_EXPAND=1 (opt-in, read once per process): the *_host entry points keep their interface (byte observations in the
-// caller's host buffer) but move the observations over PCIe as the bit-packed rows of the state matrix (7.5x fewer bytes, the
-// kernel's byte-expanding phase skipped) and expand them here, on a small pool of host threads.
+// ---- The *_host entry points return byte observations in the caller's host buffer, but what crosses PCIe are the bit-packed
+// bitmap rows of the state matrix (7.5x fewer bytes at d = 5; the kernel's byte-expanding writers have nothing to do): they land in
+// a pinned buffer chunk by chunk and are expanded to 0/1 bytes by a pool of host threads while the next chunk is still in flight.
+// DQ_HOST_EXPAND=0 in the environment selects the plain form instead (the kernel writes bytes, all of them are copied back).
 static bool host_expand_enabled() {
-    static const bool on = [] { const char* v = getenv("DQ_HOST_EXPAND"); return v && v[0] == '1'; }();
+    static const bool on = [] { const char* v = getenv("DQ_HOST_EXPAND"); return !(v && v[0] == '0'); }();
     return on;
 }
 
 namespace {
 struct HostPool {                 // persistent workers: blocks of a job are claimed from an atomic counter
     std::vector<std::thread> th;
-    std::mutex m;
-    std::condition_variable cv_job, cv_done;
+    std::mutex m, run_m;
+    std::condition_variable cv_job;
     const std::function<void(int)>* job = nullptr;
-    int nblocks = 0, generation = 0, active = 0;
-    std::atomic<int> next{0};
+    int nblocks = 0;
+    std::atomic<int> generation{0}, next{0}, active{0};
     explicit HostPool(int n) {
         for (int i = 0; i < n; ++i) th.emplace_back([this] { run(); });
         for (auto& t : th) t.detach();            // the pool lives as long as the process
     }
+    static void relax() {
+#if defined(__x86_64__)
+        _mm_pause();
+#endif
+    }
     void run() {
         int seen = 0;
         for (;;) {
-            const std::function<void(int)>* f;
-            int nb;
-            {
+            // a step arrives every ~100 us while a host-buffer loop runs: spin briefly for the next job, then sleep
+            int spins = 0;
+            while (generation.load(std::memory_order_acquire) == seen) {
+                if (++spins < 20000) { relax(); continue; }
                 std::unique_lock<std::mutex> lk(m);
-                cv_job.wait(lk, [&] { return generation != seen; });
-                seen = generation; f = job; nb = nblocks;
+                cv_job.wait(lk, [&] { return generation.load(std::memory_order_acquire) != seen; });
             }
+            seen = generation.load(std::memory_order_acquire);
+            const std::function<void(int)>* f = job;
+            const int nb = nblocks;
             for (int b; (b = next.fetch_add(1)) < nb;) (*f)(b);
-            {
-                std::lock_guard<std::mutex> lk(m);
-                if (--active == 0) cv_done.notify_one();
-            }
+            active.fetch_sub(1, std::memory_order_acq_rel);
         }
     }
-    void parallel_for(int nb, const std::function<void(int)>& f) {      // the caller works too
+    void parallel_for(int nb, const std::function<void(int)>& f) {      // the caller works too; one job at a time
+        std::lock_guard<std::mutex> serial(run_m);
+        job = &f; nblocks = nb; next.store(0); active.store((int)th.size());
         {
             std::lock_guard<std::mutex> lk(m);
-            job = &f; nblocks = nb; next.store(0); active = (int)th.size(); ++generation;
+            generation.fetch_add(1, std::memory_order_acq_rel);
         }
         cv_job.notify_all();
         for (int b; (b = next.fetch_add(1)) < nb;) f(b);
-        std::unique_lock<std::mutex> lk(m);
-        cv_done.wait(lk, [&] { return active == 0; });
+        while (active.load(std::memory_order_acquire) != 0) relax();
     }
 };
 
@@ -1021,21 +1118,22 @@ __attribute__((target("avx2"))) static void expand_lattices_avx2(const u64* pack
 }
 #endif
 
-// packed rows [C*PW][npad] (bit i of layer c of lattice e = bit i%64 of row c*PW + i/64, column e) -> obs [n][C][P] bytes of 0/1
-static void expand_packed_host(const u64* packed, size_t npad, int n, int C, int PW, int P, uint8_t* obs) {
+// packed rows [C*PW][npad] (bit i of layer c of lattice e = bit i%64 of row c*PW + i/64, column e) -> obs [n][C][P] bytes of 0/1,
+// for the lattices [first, last)
+static void expand_packed_host(const u64* packed, size_t npad, int first, int last, int C, int PW, int P, uint8_t* obs) {
     const u64* lut = byte_lut();
-    const int per = 256, nb = (n + per - 1) / per;
+    const int per = 128, nb = (last - first + per - 1) / per;
 #if defined(__x86_64__)
     static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("DQ_HOST_NO_AVX2");
 #else
     const bool avx2 = false;
 #endif
     const std::function<void(int)> block = [&](int b) {
-        const int e1 = std::min(n, (b + 1) * per);
+        const int e0 = first + b * per, e1 = std::min(last, e0 + per);
 #if defined(__x86_64__)
-        if (avx2 && P >= 32) { expand_lattices_avx2(packed, npad, b * per, e1, C, PW, P, obs); return; }
+        if (avx2 && P >= 32) { expand_lattices_avx2(packed, npad, e0, e1, C, PW, P, obs); return; }
 #endif
-        for (int e = b * per; e < e1; ++e) {
+        for (int e = e0; e < e1; ++e) {
             uint8_t* out = obs + (size_t)e * C * P;
             for (int c = 0; c < C; ++c, out += P)
                 for (int w = 0; w < PW; ++w) {
@@ -1051,100 +1149,143 @@ static void expand_packed_host(const u64* packed, size_t npad, int n, int C, int
     host_pool().parallel_for(nb, block);
 }
 
-static int copy_packed(dq_env* e, uint64_t* h_packed);
-// the tail of a *_host call under DQ_HOST_EXPAND: packed rows to the pinned landing buffer, the small outputs, one synchronise, expand
-static int copy_out_expanding(dq_env* e, uint8_t* h_obs, float* h_reward, uint8_t* h_done, int32_t* h_life, uint64_t* h_legal);
+// Uniform pick over the sorted legal actions on the HOST (same draw as dq_policy_random_legal): for callers that drive the
+// *_host entry points and hold the legal masks in host memory.
+extern "C" int dq_policy_random_legal_host(const dq_env* e, const uint64_t* h_legal, uint32_t step_index, int32_t* h_actions) {
+    if (!e || !h_legal || !h_actions) return fail(DQ_EINVAL, "NULL argument");
+    const EnvParams& p = e->p;
+    const int per = 512, nb = (p.n + per - 1) / per;
+    const std::function<void(int)> block = [&](int b) {
+        const int e1 = std::min(p.n, (b + 1) * per);
+        for (int i = b * per; i < e1; ++i) {
+            const u64* m = h_legal + (size_t)i * p.W;
+            int cnt = 0;
+            for (int w = 0; w < p.W; ++w) cnt += popc64(m[w]);
+            const Philox4 u = philox4x32_10(p.env_id_base + (u32)i, step_index, 0u, 1u, p.k0, p.k1);
+            int pick = (int)mulhi32(u.x, (u32)cnt), act = p.A - 1;
+            for (int w = 0; w < p.W; ++w) {
+                const int c = popc64(m[w]);
+                if (pick < c) { act = w * 64 + select64(m[w], pick); break; }
+                pick -= c;
+            }
+            h_actions[i] = act;
+        }
+    };
+    host_pool().parallel_for(nb, block);
+    return DQ_OK;
+}
 
-static int copy_out(dq_env* e, uint8_t* h_obs, float* h_reward, uint8_t* h_done, int32_t* h_life, uint64_t* h_legal) {
+// ---- host-buffer calls in two halves: *_begin queues the copy-in, the launch and every copy-out on the handle's own stream and
+// returns; *_end waits for the results and (host-side expansion) turns the landed bitmap rows into bytes.  Two handles driven
+// begin(A) begin(B) end(A) begin(A) end(B) ... overlap one handle's kernel and copies with the other's expansion on the host.
+static int queue_outputs(dq_env* e, bool bytes_on_device, uint64_t* h_packed_user) {
     const EnvParams& p = e->p;
     cudaStream_t s = e->hstream;
-    if (h_obs) DQ_CUDA(cudaMemcpyAsync(h_obs, e->s_obs, (size_t)p.n * p.obs_bits, cudaMemcpyDeviceToHost, s));
-    if (h_reward) DQ_CUDA(cudaMemcpyAsync(h_reward, e->s_reward, (size_t)p.n * 4, cudaMemcpyDeviceToHost, s));
-    if (h_done) DQ_CUDA(cudaMemcpyAsync(h_done, e->s_done, (size_t)p.n, cudaMemcpyDeviceToHost, s));
-    if (h_life) DQ_CUDA(cudaMemcpyAsync(h_life, e->s_life, (size_t)p.n * 4, cudaMemcpyDeviceToHost, s));
-    if (h_legal) DQ_CUDA(cudaMemcpyAsync(h_legal, e->s_legal, (size_t)p.n * p.W * 8, cudaMemcpyDeviceToHost, s));
-    DQ_CUDA(cudaStreamSynchronize(s));
+    HostCall& hc = e->hc;
+    if (hc.reward) DQ_CUDA(cudaMemcpyAsync(hc.reward, e->s_reward, (size_t)p.n * 4, cudaMemcpyDeviceToHost, s));
+    if (hc.done) DQ_CUDA(cudaMemcpyAsync(hc.done, e->s_done, (size_t)p.n, cudaMemcpyDeviceToHost, s));
+    if (hc.life) DQ_CUDA(cudaMemcpyAsync(hc.life, e->s_life, (size_t)p.n * 4, cudaMemcpyDeviceToHost, s));
+    if (hc.legal) DQ_CUDA(cudaMemcpyAsync(hc.legal, e->s_legal, (size_t)p.n * p.W * 8, cudaMemcpyDeviceToHost, s));
+    const size_t rows = (size_t)(e->state_rows - ROW_BM), words = rows * p.npad;
+    const u64* src = p.state + (size_t)ROW_BM * p.npad;
+    hc.chunks = 0;
+    if (h_packed_user) {
+        DQ_CUDA(cudaMemcpyAsync(h_packed_user, src, words * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    } else if (hc.obs && bytes_on_device) {
+        DQ_CUDA(cudaMemcpyAsync(hc.obs, e->s_obs, (size_t)p.n * p.obs_bits, cudaMemcpyDeviceToHost, s));
+    } else if (hc.obs) {
+        if (!e->h_packed) DQ_CUDA(cudaMallocHost(&e->h_packed, words * sizeof(u64)));
+        // lattice ranges of the rows, one event each: the first range is being expanded while the others are still on the bus
+        const int nch = p.n >= 4096 ? kHostChunks : 1;
+        const int per = ((p.npad / nch) + 31) / 32 * 32;
+        for (int c = 0, first = 0; c < nch && first < p.n; ++c, first += per) {
+            const int cnt = std::min(per, p.npad - first);
+            DQ_CUDA(cudaMemcpy2DAsync(e->h_packed + first, (size_t)p.npad * 8, src + first, (size_t)p.npad * 8, (size_t)cnt * 8, rows,
+                                      cudaMemcpyDeviceToHost, s));
+            DQ_CUDA(cudaEventRecord(e->h_ev[c], s));
+            hc.first[c] = first; hc.last[c] = std::min(p.n, first + cnt);
+            hc.chunks = c + 1;
+        }
+    }
+    hc.pending = true;
     return DQ_OK;
+}
+
+static int host_begin(dq_env* e, bool reset, const int32_t* h_actions, uint8_t* h_obs, uint64_t* h_packed_user, float* h_reward, uint8_t* h_done,
+                      int32_t* h_life, uint64_t* h_legal, int auto_reset) {
+    if (e->hc.pending) return fail(DQ_ESTATE, "a host-buffer call is already in flight on this handle: call dq_env_step_host_end first");
+    DeviceGuard g(e->device);
+    int rc = ensure_staging(e);
+    if (rc) return rc;
+    const EnvParams& p = e->p;
+    const bool bytes_on_device = h_obs && !host_expand_enabled();
+    if (bytes_on_device && !e->s_obs) DQ_CUDA(cudaMalloc(&e->s_obs, (size_t)p.n * p.obs_bits));
+    e->hc = HostCall{};
+    e->hc.obs = h_obs; e->hc.reward = h_reward; e->hc.done = h_done; e->hc.life = h_life; e->hc.legal = h_legal;
+    if (reset) {
+        rc = launch_env<true>(e, nullptr, bytes_on_device ? e->s_obs : nullptr, nullptr, nullptr, nullptr, h_legal ? e->s_legal : nullptr, 1, e->hstream);
+    } else {
+        DQ_CUDA(cudaMemcpyAsync(e->s_actions, h_actions, (size_t)p.n * 4, cudaMemcpyHostToDevice, e->hstream));
+        rc = launch_env<false>(e, e->s_actions, bytes_on_device ? e->s_obs : nullptr, h_reward ? e->s_reward : nullptr,
+                               h_done ? e->s_done : nullptr, h_life ? e->s_life : nullptr, h_legal ? e->s_legal : nullptr, auto_reset, e->hstream);
+    }
+    if (rc) return rc;
+    return queue_outputs(e, bytes_on_device, h_packed_user);
+}
+
+static int host_end(dq_env* e) {
+    if (!e->hc.pending) return fail(DQ_ESTATE, "no host-buffer call in flight on this handle");
+    DeviceGuard g(e->device);
+    const EnvParams& p = e->p;
+    HostCall& hc = e->hc;
+    hc.pending = false;
+    const int side = 2 * p.d + 1, P = side * side;
+    for (int c = 0; c < hc.chunks; ++c) {
+        DQ_CUDA(cudaEventSynchronize(e->h_ev[c]));
+        expand_packed_host(e->h_packed, (size_t)p.npad, hc.first[c], hc.last[c], p.vd + p.layers, (P + 63) / 64, P, hc.obs);
+    }
+    DQ_CUDA(cudaStreamSynchronize(e->hstream));
+    return DQ_OK;
+}
+
+extern "C" int dq_env_step_host_begin(dq_env* e, const int32_t* h_actions, uint8_t* h_obs, float* h_reward, uint8_t* h_done,
+                                      int32_t* h_life, uint64_t* h_legal, int auto_reset) {
+    if (!e || !h_actions) return fail(DQ_EINVAL, "env / actions is NULL");
+    if (e->p.ref_mode < 0) return fail(DQ_ESTATE, "no referee set: call dq_env_set_referee_lut first");
+    return host_begin(e, false, h_actions, h_obs, nullptr, h_reward, h_done, h_life, h_legal, auto_reset);
+}
+
+extern "C" int dq_env_step_host_end(dq_env* e) {
+    if (!e) return fail(DQ_EINVAL, "env is NULL");
+    return host_end(e);
 }
 
 extern "C" int dq_env_reset_host(dq_env* e, uint8_t* h_obs, uint64_t* h_legal) {
     if (!e) return fail(DQ_EINVAL, "env is NULL");
-    DeviceGuard g(e->device);
-    int rc = ensure_staging(e);
-    if (rc) return rc;
-    const bool expand = h_obs && host_expand_enabled();
-    rc = launch_env<true>(e, nullptr, (h_obs && !expand) ? e->s_obs : nullptr, nullptr, nullptr, nullptr, h_legal ? e->s_legal : nullptr, 1, e->hstream);
-    if (rc) return rc;
-    if (expand) return copy_out_expanding(e, h_obs, nullptr, nullptr, nullptr, h_legal);
-    return copy_out(e, h_obs, nullptr, nullptr, nullptr, h_legal);
+    const int rc = host_begin(e, true, nullptr, h_obs, nullptr, nullptr, nullptr, nullptr, h_legal, 1);
+    return rc ? rc : host_end(e);
 }
 
 extern "C" int dq_env_step_host(dq_env* e, const int32_t* h_actions, uint8_t* h_obs, float* h_reward, uint8_t* h_done,
                                 int32_t* h_life, uint64_t* h_legal, int auto_reset) {
-    if (!e || !h_actions) return fail(DQ_EINVAL, "env / actions is NULL");
-    if (e->p.ref_mode < 0) return fail(DQ_ESTATE, "no referee set: call dq_env_set_referee_lut first");
-    DeviceGuard g(e->device);
-    int rc = ensure_staging(e);
-    if (rc) return rc;
-    DQ_CUDA(cudaMemcpyAsync(e->s_actions, h_actions, (size_t)e->p.n * 4, cudaMemcpyHostToDevice, e->hstream));
-    const bool expand = h_obs && host_expand_enabled();
-    rc = launch_env<false>(e, e->s_actions, (h_obs && !expand) ? e->s_obs : nullptr, h_reward ? e->s_reward : nullptr,
-                           h_done ? e->s_done : nullptr, h_life ? e->s_life : nullptr, h_legal ? e->s_legal : nullptr,
-                           auto_reset, e->hstream);
-    if (rc) return rc;
-    if (expand) return copy_out_expanding(e, h_obs, h_reward, h_done, h_life, h_legal);
-    return copy_out(e, h_obs, h_reward, h_done, h_life, h_legal);
+    const int rc = dq_env_step_host_begin(e, h_actions, h_obs, h_reward, h_done, h_life, h_legal, auto_reset);
+    return rc ? rc : host_end(e);
 }
 
 // Host-buffer calls that return the observations PACKED (the rows the Q-network and the replay ring consume: one bit per
-// cell, uint64 [C*PW][STATE_STRIDE]) instead of one byte per cell: 7.5x fewer bytes over PCIe, and the byte-expanding phase of
-// the kernel is skipped altogether.
-static int copy_packed(dq_env* e, uint64_t* h_packed) {
-    if (!h_packed) return DQ_OK;
-    const size_t words = (size_t)(e->state_rows - ROW_BM) * e->p.npad;
-    DQ_CUDA(cudaMemcpyAsync(h_packed, e->p.state + (size_t)ROW_BM * e->p.npad, words * sizeof(u64), cudaMemcpyDeviceToHost, e->hstream));
-    return DQ_OK;
-}
-
-static int copy_out_expanding(dq_env* e, uint8_t* h_obs, float* h_reward, uint8_t* h_done, int32_t* h_life, uint64_t* h_legal) {
-    const EnvParams& p = e->p;
-    const size_t words = (size_t)(e->state_rows - ROW_BM) * p.npad;
-    if (!e->h_packed) DQ_CUDA(cudaMallocHost(&e->h_packed, words * sizeof(u64)));
-    int rc = copy_packed(e, e->h_packed);
-    if (rc) return rc;
-    rc = copy_out(e, nullptr, h_reward, h_done, h_life, h_legal);          // synchronises the stream
-    if (rc) return rc;
-    const int side = 2 * p.d + 1, P = side * side;
-    expand_packed_host(e->h_packed, (size_t)p.npad, p.n, p.vd + p.layers, (P + 63) / 64, P, h_obs);
-    return DQ_OK;
-}
-
+// cell, uint64 [C*PW][STATE_STRIDE]) instead of one byte per cell: nothing to expand on either side.
 extern "C" int dq_env_reset_host_packed(dq_env* e, uint64_t* h_packed, uint64_t* h_legal) {
     if (!e) return fail(DQ_EINVAL, "env is NULL");
-    DeviceGuard g(e->device);
-    int rc = ensure_staging(e);
-    if (rc) return rc;
-    rc = launch_env<true>(e, nullptr, nullptr, nullptr, nullptr, nullptr, h_legal ? e->s_legal : nullptr, 1, e->hstream);
-    if (rc) return rc;
-    rc = copy_packed(e, h_packed);
-    if (rc) return rc;
-    return copy_out(e, nullptr, nullptr, nullptr, nullptr, h_legal);
+    const int rc = host_begin(e, true, nullptr, nullptr, h_packed, nullptr, nullptr, nullptr, h_legal, 1);
+    return rc ? rc : host_end(e);
 }
 
 extern "C" int dq_env_step_host_packed(dq_env* e, const int32_t* h_actions, uint64_t* h_packed, float* h_reward, uint8_t* h_done,
                                        int32_t* h_life, uint64_t* h_legal, int auto_reset) {
     if (!e || !h_actions) return fail(DQ_EINVAL, "env / actions is NULL");
     if (e->p.ref_mode < 0) return fail(DQ_ESTATE, "no referee set: call dq_env_set_referee_lut first");
-    DeviceGuard g(e->device);
-    int rc = ensure_staging(e);
-    if (rc) return rc;
-    DQ_CUDA(cudaMemcpyAsync(e->s_actions, h_actions, (size_t)e->p.n * 4, cudaMemcpyHostToDevice, e->hstream));
-    rc = launch_env<false>(e, e->s_actions, nullptr, h_reward ? e->s_reward : nullptr, h_done ? e->s_done : nullptr,
-                           h_life ? e->s_life : nullptr, h_legal ? e->s_legal : nullptr, auto_reset, e->hstream);
-    if (rc) return rc;
-    rc = copy_packed(e, h_packed);
-    if (rc) return rc;
-    return copy_out(e, nullptr, h_reward, h_done, h_life, h_legal);
+    const int rc = host_begin(e, false, h_actions, nullptr, h_packed, h_reward, h_done, h_life, h_legal, auto_reset);
+    return rc ? rc : host_end(e);
 }
 
 extern "C" int dq_env_packed_obs(dq_env* e, uint64_t** dev_rows, int64_t* n_rows, int64_t* stride) {

@@ -228,6 +228,29 @@ class VecSurfaceCodeEnv:
         return (hb["obs"].numpy(), hb["reward"].numpy(), hb["done"].numpy().astype(bool),
                 {"lifetime": hb["lifetime"].numpy(), "legal_mask": hb["legal"].numpy().view(np.uint64)})
 
+    def step_host_begin(self, actions=None):
+        """First half of `step_host` (dq_env_step_host_begin): queues the copy-in, the launch and the copy-outs and returns at once.
+        `actions=None` uses what is already in the pinned action buffer (e.g. written by `random_legal_actions_host`).  Two
+        environments stepped begin(A) begin(B) end(A) begin(A) end(B) ... overlap one's GPU work with the other's host-side work."""
+        hb = self._host_buffers()
+        if actions is not None:
+            hb["actions"].numpy()[:] = np.asarray(actions, dtype=np.int32)
+        _lib.check(self.L.dq_env_step_host_begin(self._h, _ptr(hb["actions"]), _ptr(hb["obs"]), _ptr(hb["reward"]),
+                                                 _ptr(hb["done"]), _ptr(hb["lifetime"]), _ptr(hb["legal"]), int(self.auto_reset)))
+
+    def step_host_end(self):
+        hb = self._host_buffers()
+        _lib.check(self.L.dq_env_step_host_end(self._h))
+        return (hb["obs"].numpy(), hb["reward"].numpy(), hb["done"].numpy().astype(bool),
+                {"lifetime": hb["lifetime"].numpy(), "legal_mask": hb["legal"].numpy().view(np.uint64)})
+
+    def random_legal_actions_host(self, step_index):
+        """The random-legal policy on the host (dq_policy_random_legal_host): picks from the legal masks of the latest host-buffer
+        call into the pinned action buffer, which is returned (and is what `step_host_begin()` sends)."""
+        hb = self._host_buffers()
+        _lib.check(self.L.dq_policy_random_legal_host(self._h, _ptr(hb["legal"]), int(step_index) & 0xFFFFFFFF, _ptr(hb["actions"])))
+        return hb["actions"].numpy()
+
     # ---- packed state (parity tests, checkpoints) ----
     def get_state_words(self):
         w = torch.empty((self.state_words, self.state_stride), dtype=torch.int64, device=self.device)

@@ -17,6 +17,7 @@ import struct
 import numpy as np
 
 _UNDEF = 0xFFFFFFFFFFFFFFFF
+_H5HL_FREE_NULL = 1
 
 
 class H5File:
@@ -339,7 +340,9 @@ def _write_group(w, children, attrs):
         heap_data += b"\0" * (16 - len(heap_data))
     w.align(8)
     hd_addr = w.write(bytes(heap_data))
-    heap_addr = w.write(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), _UNDEF & 0xFFFFFFFFFFFFFFFF, hd_addr))
+    # free-list head: libhdf5 (H5HL prefix decode) accepts H5HL_FREE_NULL (= 1, "no free block") or an offset inside the data
+    # segment; the undefined address is rejected ("bad heap free list").  The segment above has no free block.
+    heap_addr = w.write(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), _H5HL_FREE_NULL, hd_addr))
     # symbol nodes: up to 2K=8 entries per SNOD (group leaf node K = 4)
     K = 4
     snods = []

@@ -60,7 +60,7 @@ extern "C" {
 #define DQ_INFO_N_TYPE3       7
 #define DQ_INFO_N_TYPE1       8
 #define DQ_INFO_RNG_BLOCKS    9   /* Philox blocks per volume attempt (B of the RNG contract) */
-#define DQ_INFO_HOST_EXPAND  10   /* 1 if the *_host calls move observations bit-packed and expand them on the host (DQ_HOST_EXPAND=1) */
+#define DQ_INFO_HOST_EXPAND  10   /* 1 if the *_host calls move observations bit-packed and expand them on the host (default; DQ_HOST_EXPAND=0 turns it off) */
 
 typedef struct dq_env dq_env;
 typedef void* dq_stream;
@@ -125,6 +125,19 @@ int dq_env_rollout_random(dq_env* env, int n_steps, uint8_t* obs_ring, int ring_
 int dq_env_reset_host(dq_env* env, uint8_t* h_obs, uint64_t* h_legal_mask);
 int dq_env_step_host(dq_env* env, const int32_t* h_actions, uint8_t* h_obs, float* h_reward,
                      uint8_t* h_done, int32_t* h_lifetime, uint64_t* h_legal_mask, int auto_reset);
+/* dq_env_step_host in two halves.  _begin queues the copy-in of the actions, the launch and every copy-out on the handle's own
+ * stream and returns at once (the buffers must stay valid, and pinned for the copies to be asynchronous); _end waits for the results
+ * and finishes the observations.  One call may be in flight per handle; two handles driven begin(A) begin(B) end(A) begin(A) end(B) ...
+ * overlap one handle's kernel and PCIe traffic with the other's host-side work.
+ * What crosses PCIe for h_obs are the bit-packed bitmap rows (7.5x fewer bytes at d = 5); host threads of the library expand them
+ * into the caller's byte buffer in _end, range by range while the later ranges are still in flight (DQ_HOST_THREADS caps the
+ * threads; DQ_HOST_EXPAND=0 makes the kernel write bytes and copies all of them back instead). */
+int dq_env_step_host_begin(dq_env* env, const int32_t* h_actions, uint8_t* h_obs, float* h_reward, uint8_t* h_done,
+                           int32_t* h_lifetime, uint64_t* h_legal_mask, int auto_reset);
+int dq_env_step_host_end(dq_env* env);
+/* The uniform pick over the sorted legal actions (dq_policy_random_legal, same Philox word) computed on the host from host-resident
+ * legal masks: the policy of the env-only benchmark for callers that live on the host side of the *_host calls. */
+int dq_policy_random_legal_host(const dq_env* env, const uint64_t* h_legal_mask, uint32_t step_index, int32_t* h_actions);
 /* The same two calls returning the observations PACKED -- uint64 h_packed[C*PW][STATE_STRIDE], bit x*H+y of the PW-word
  * bitmap of layer l of lattice i in h_packed[l*PW + word][i], i.e. the rows dq_env_packed_obs exposes and the Q-network
  * consumes -- instead of one byte per cell: 7.5x fewer bytes over PCIe at d = 5.  (The reference returns board_state as an

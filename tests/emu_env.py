@@ -62,6 +62,9 @@ def lib(path=None):
     L.dq_policy_seek.argtypes = [vp, C.c_uint32, vp]
     L.dq_env_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32]
     L.dq_env_reset_host.argtypes = [vp, vp, vp]
+    L.dq_env_step_host_begin.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32]
+    L.dq_env_step_host_end.argtypes = [vp]
+    L.dq_policy_random_legal_host.argtypes = [vp, vp, C.c_uint32, vp]
     L.dq_env_reset_host_packed.argtypes = [vp, vp, vp]
     L.dq_env_step_host_packed.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32]
     _LIB[path] = L
@@ -161,6 +164,23 @@ class EmuVecEnv:
         reward, done, life, legal, _ = self._outs()
         self._check(self.L.dq_env_step_host(self.h, _p(actions), _p(obs), _p(reward), _p(done), _p(life), _p(legal), int(auto_reset)))
         return obs, reward, done, life, legal
+
+    def step_host_begin(self, actions, auto_reset=True):
+        actions = np.ascontiguousarray(actions, dtype=np.int32)
+        obs = np.zeros((self.n, self.Cn, self.H, self.H), np.uint8)
+        reward, done, life, legal, _ = self._outs()
+        self._check(self.L.dq_env_step_host_begin(self.h, _p(actions), _p(obs), _p(reward), _p(done), _p(life), _p(legal), int(auto_reset)))
+        self._pending_actions, self._pending = actions, (obs, reward, done, life, legal)      # kept alive until step_host_end (a refused call keeps the earlier ones)
+
+    def step_host_end(self):
+        self._check(self.L.dq_env_step_host_end(self.h))
+        return self._pending
+
+    def random_legal_actions_host(self, legal, step):
+        legal = np.ascontiguousarray(legal, dtype=np.uint64)
+        acts = np.zeros(self.n, np.int32)
+        self._check(self.L.dq_policy_random_legal_host(self.h, _p(legal), step, _p(acts)))
+        return acts
 
     def step_host_packed(self, actions, auto_reset=True):
         actions = np.ascontiguousarray(actions, dtype=np.int32)

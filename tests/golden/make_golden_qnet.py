@@ -12,13 +12,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import qnet_ref as Q  # noqa
 
-for tag, sub in (("dp", "d5_dp"), ("x", "d5_x")):
-    w = Q.load_keras_dqn_weights("/root/reference/trained_models/%s/0.007/final_dqn_weights.h5f" % sub)
+# d5_dp/0.005: the agent the reference's controller hands to the 0.007 runs as initial weights (Controller.py:187-270)
+for tag, sub, rate in (("dp", "d5_dp", "0.007"), ("x", "d5_x", "0.007"), ("dp", "d5_dp", "0.005")):
+    w = Q.load_keras_dqn_weights("/root/reference/trained_models/%s/%s/final_dqn_weights.h5f" % (sub, rate))
     arrays = {}
     for i, (k, b) in enumerate(w["conv"]):
         arrays["conv%d_k" % i], arrays["conv%d_b" % i] = k, b
     for i, (k, b) in enumerate(w["dense"]):
         arrays["dense%d_k" % i], arrays["dense%d_b" % i] = k, b
-    out = os.path.join(HERE, "dqn_d5_%s_0.007.npz" % tag)
+    out = os.path.join(HERE, "dqn_d5_%s_%s.npz" % (tag, rate))
     np.savez_compressed(out, **arrays)
     print(out, os.path.getsize(out))

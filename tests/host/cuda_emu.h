@@ -228,6 +228,8 @@ inline dim3 thread_idx() {
 static inline void __syncthreads() { dq_emu::block_barrier(); }
 static inline void __threadfence_block() {}          // fibers of one OS thread: program order is memory order
 static inline void __nanosleep(unsigned) { dq_emu::yield(); }
+static inline long long clock64() { static long long t = 0; return t += 1000; }          // 4e6 polls of a spin loop trip the kernel's watchdog
+static inline void __trap() { fprintf(stderr, "dq_emu: __trap() (a spin-wait watchdog of the kernel fired)\n"); abort(); }
 static inline void __syncwarp(uint32_t mask = 0xffffffffu) { dq_emu::warp_collect(mask, 0); }
 static inline uint32_t __ballot_sync(uint32_t mask, int pred) {
     const uint64_t* v = dq_emu::warp_collect(mask, pred ? 1 : 0);
@@ -330,3 +332,13 @@ template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFunc
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)malloc(1); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+typedef struct dq_emu_event* cudaEvent_t;
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)malloc(1); return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t) {
+    for (size_t r = 0; r < height; ++r) memmove((char*)d + r * dpitch, (const char*)s + r * spitch, width);
+    return cudaSuccess;
+}

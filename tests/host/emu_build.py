@@ -115,7 +115,7 @@ def build(out, sources, extra_flags=(), deps=()):
             f.write(transform(path, cut, tail))
         files.append(gen)
     cmd = ["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-DDQ_EMU", "-include", SHIM,
-           "-fsanitize=alignment", "-fno-sanitize-recover=alignment",      # x86 forgives misaligned loads, the GPU does not
+           "-fsanitize=alignment", "-fno-sanitize-recover=alignment", *(["-fsanitize=address"] if os.environ.get("DQ_EMU_ASAN") else []),      # x86 forgives misaligned loads, the GPU does not
            
            "-I", STUBS, "-I", CSRC, *extra_flags]
     for f in files:

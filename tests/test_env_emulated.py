@@ -151,9 +151,10 @@ def test_emulated_host_entry_points_and_unaligned_observation_buffers():
         olegal = want[4]
 
 
-def test_emulated_host_calls_with_host_side_expansion():
-    """DQ_HOST_EXPAND=1 (opt-in, read once per process, hence the child process): dq_env_reset_host / dq_env_step_host return the
-    same byte observations, moved as bit-packed rows and expanded by the library's host threads."""
+def test_emulated_host_calls_plain_and_threaded_expansion():
+    """dq_env_reset_host / dq_env_step_host return the same byte observations whether the library moves bit-packed rows and expands
+    them with its host threads (the default; any thread count; AVX2 or the table walk) or lets the kernel write bytes and copies all
+    of them back (DQ_HOST_EXPAND=0).  The switches are read once per process, hence the child processes."""
     import os, subprocess, sys
     code = (
         "import sys, numpy as np\n"
@@ -162,7 +163,7 @@ def test_emulated_host_calls_with_host_side_expansion():
         "from test_env_emulated import make_pair\n"
         "for d, model, use_Y, vd, n in ((5, 'DP', False, 5, 300), (7, 'DP', True, 4, 19), (3, 'X', False, 3, 257)):\n"
         "    env, o = make_pair(d, model, use_Y, vd, 0.03, n, seed=3)\n"
-        "    assert env._info(10) == 1\n"
+        "    assert env._info(10) == int(sys.argv[1])\n"
         "    obs, legal = env.reset_host()\n"
         "    oobs, olegal = o.reset()\n"
         "    assert np.array_equal(obs, oobs) and np.array_equal(legal, olegal)\n"
@@ -173,10 +174,38 @@ def test_emulated_host_calls_with_host_side_expansion():
         "        olegal = want[4]\n"
         "print('ok')\n"
     ) % os.path.dirname(os.path.abspath(__file__))
-    for threads, extra in (("1", {}), ("5", {}), ("3", {"DQ_HOST_NO_AVX2": "1"})):      # AVX2 expansion where the host has it, and the table walk
-        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DQ_HOST_EXPAND="1", DQ_HOST_THREADS=threads, **extra),
+    for expand, threads, extra in (("1", "1", {}), ("1", "5", {}), ("1", "3", {"DQ_HOST_NO_AVX2": "1"}), ("0", "2", {})):
+        out = subprocess.run([sys.executable, "-c", code, expand], env=dict(os.environ, DQ_HOST_EXPAND=expand, DQ_HOST_THREADS=threads, **extra),
                              capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_emulated_split_host_call_and_host_policy():
+    """dq_env_step_host_begin / _end on two handles driven alternately (the overlap pattern of the e2e benchmark) and the host-side
+    random-legal policy: same picks as the device policy and the oracle, same outputs as the one-piece call."""
+    d, model, n = 5, "DP", 4100                       # >= 4096 lattices: the bitmap rows cross in several lattice ranges
+    a, oa = make_pair(d, model, False, 5, 0.03, n, seed=8, base=0)
+    b, ob = make_pair(d, model, False, 5, 0.03, n, seed=8, base=n)
+    la, lb = oa.reset()[1], ob.reset()[1]
+    assert np.array_equal(a.reset_host()[1], la) and np.array_equal(b.reset_host()[1], lb)
+    for t in range(4):
+        acts_a, acts_b = a.random_legal_actions_host(la, t), b.random_legal_actions_host(lb, t)
+        assert np.array_equal(acts_a, oa.random_legal_actions(la, t)) and np.array_equal(acts_b, ob.random_legal_actions(lb, t))
+        assert np.array_equal(acts_a, a.random_legal_actions(la, t)), "host policy == device policy"
+        a.step_host_begin(acts_a)
+        b.step_host_begin(acts_b)
+        got_a = a.step_host_end()
+        want_a = oa.step(acts_a, auto_reset=True)
+        got_b = b.step_host_end()
+        want_b = ob.step(acts_b, auto_reset=True)
+        assert all(np.array_equal(g, w) for g, w in zip(got_a, want_a)) and all(np.array_equal(g, w) for g, w in zip(got_b, want_b)), t
+        la, lb = want_a[4], want_b[4]
+    with pytest.raises(RuntimeError):
+        a.step_host_end()                              # nothing in flight
+    a.step_host_begin(oa.random_legal_actions(la, 9))
+    with pytest.raises(RuntimeError):
+        a.step_host_begin(oa.random_legal_actions(la, 9))      # one call per handle at a time
+    a.step_host_end()
 
 
 def test_emulator_reports_deadlock_free_run_of_every_geometry():
@@ -305,6 +334,38 @@ def test_emulated_injected_state_revalidates_queues():
         got, want = b.step(acts), o2.step(acts, auto_reset=True)
         assert all(np.array_equal(g, x) for g, x in zip(got, want)), "rewound handle, t=%d" % t2
         ol2 = want[4]
+
+
+@pytest.mark.parametrize("variant", [None, "q2"])
+def test_emulated_many_trivial_attempts_in_one_step(variant):
+    """Low noise on a small code: most volume attempts are all-trivial, so one step pops many more attempts than a queue holds --
+    the physics warp must be able to wake idle generator warps from inside a step (a doorbell rung only after the step deadlocks)."""
+    import os
+    path = None if variant is None else E.build(dict(VARIANTS)[variant], out=os.path.join(E.HERE, "host", "libdq_env_emu_%s.so" % variant))
+    for d, model, vd, p in ((3, "X", 1, 0.004), (3, "DP", 2, 0.002), (5, "X", 2, 0.0015)):
+        n = 45
+        mode, la, lb = random_luts(np.random.default_rng(d), d, model)
+        env = E.EmuVecEnv(d, model, False, vd, p, p, n, 77, 0, lib_path=path)
+        o = O.OracleVecEnv(d, model, False, vd, p, p, n, 77, 0)
+        env.set_referee(mode, la, lb); o.set_referee(mode, la, lb)
+        obs, legal = env.reset()
+        oobs, olegal = o.reset()
+        assert np.array_equal(obs, oobs) and np.array_equal(legal, olegal)
+        attempts0 = sum(o.get_env(i)["attempts"] for i in range(n))
+        assert attempts0 > 4 * n, "the reset alone should need several attempts per lattice"
+        for t in range(6):
+            acts = o.random_legal_actions(olegal, t)
+            got, want = env.step(acts), o.step(acts, auto_reset=True)
+            assert all(np.array_equal(g, w) for g, w in zip(got, want)), (d, t)
+            olegal = want[4]
+        env.policy_seek(6)
+        ring, rew, done, life, legal2, acts = env.rollout_random(10, 2, 0, True)
+        for s_ in range(10):
+            oa = o.random_legal_actions(olegal, 6 + s_)
+            oobs, orew, odone, olife, olegal = o.step(oa, auto_reset=True)
+            assert np.array_equal(acts[s_], oa) and np.array_equal(life[s_], olife) and np.array_equal(legal2[s_], olegal)
+        assert np.array_equal(ring[1], oobs)
+        compare_state(env, o, range(6))
 
 
 @pytest.mark.parametrize("cap", [1, 3])

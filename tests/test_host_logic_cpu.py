@@ -65,6 +65,40 @@ def test_h5_subset_round_trip(tmp_path):
         bad = tmp_path / "bad.h5"
         bad.write_bytes(b"not hdf5 at all")
         h5lite.H5File(str(bad))
+    # structural checks libhdf5 applies when it opens a group (no h5py in this image to open the file with): every local heap
+    # (H5HL prefix) must carry a free-list head that is H5HL_FREE_NULL (= 1) or an offset inside its data segment, and a data
+    # segment that lies inside the file
+    heaps = _local_heaps(open(path, "rb").read())
+    assert len(heaps) == 5                     # root, conv2d_1, conv2d_1/conv2d_1, dense_1, dense_1/dense_1_1
+    for size, free_head, seg_addr, file_len in heaps:
+        assert free_head == 1 or free_head < size, "libhdf5: 'bad heap free list'"
+        assert size >= 16 and size % 8 == 0 and seg_addr + size <= file_len
+
+
+def _local_heaps(buf):
+    """(data segment size, free-list head, data segment address, file length) of every local heap in an HDF5 image."""
+    import struct
+    out, pos = [], buf.find(b"HEAP")
+    while pos >= 0:
+        if pos % 8 == 0 and buf[pos + 4] == 0:
+            size, free_head, seg = struct.unpack_from("<QQQ", buf, pos + 8)
+            out.append((size, free_head, seg, len(buf)))
+        pos = buf.find(b"HEAP", pos + 4)
+    return out
+
+
+@pytest.mark.reference
+def test_reference_written_heaps_satisfy_the_same_rule():
+    """The check above, applied to files h5py wrote (the reference's shipped weights): validates the check itself."""
+    import glob
+    files = glob.glob("/root/reference/trained_models/d5_dp/0.007/final_dqn_weights.h5f") + glob.glob("/root/reference/example_notebooks/referee_decoders/nn_d5_X_p5")
+    assert files
+    for f in files:
+        heaps = _local_heaps(open(f, "rb").read())
+        assert heaps
+        for size, free_head, seg_addr, file_len in heaps:
+            assert free_head == 1 or free_head < size
+            assert seg_addr + size <= file_len
 
 
 @pytest.mark.parametrize("d,model", [(3, "X"), (3, "DP"), (5, "X")])

@@ -14,6 +14,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/${TAG}_gpu.txt
 run pytest_env 150 python -m pytest tests/test_env_gpu.py -x -q
 tail -3 gpurun_out/${TAG}_pytest_env.out
+grep -q " passed" gpurun_out/${TAG}_pytest_env.out && ! grep -q "failed" gpurun_out/${TAG}_pytest_env.out || { echo "env parity failed: stopping"; exit 1; }
 run ab_new 60 python tools/prof_rollout.py
 [ -f build/variants/libdq_old.so ] && DQ_DECODING_LIB=build/variants/libdq_old.so run ab_old 60 python tools/prof_rollout.py
 [ -n "$SKIP_AB" ] || for v in $(ls build/variants/ | sed -n 's/^libdq_\(.*\)\.so$/\1/p' | grep -v '^old$'); do
@@ -21,8 +22,10 @@ run ab_new 60 python tools/prof_rollout.py
 done
 DQ_CALLS=6 DQ_ONLY_ROLLOUT=64 DQ_N=262144 run big 40 python tools/prof_rollout.py      # every SM fully loaded
 DQ_D=7 DQ_N=8192 run d7 40 python tools/prof_rollout.py
-run bench 150 python bench.py --cpu-seconds 3 --no-dqn --no-experiments
-run ncu_list 90 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_launches_rollout.csv python bench.py --steps 1024 --warmup 16 --cpu-seconds 0.2 --no-dqn --no-experiments
+run bench 150 python bench.py --cpu-seconds 3 --no-dqn
+run bench20 100 python bench.py --cpu-seconds 1 --no-dqn --steps 20 --warmup 3
+run bench_full 300 python bench.py --cpu-seconds 3
+run ncu_list 90 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_launches_rollout.csv python bench.py --steps 1024 --warmup 16 --cpu-seconds 0.2 --no-dqn
 DQ_ONLY_ROLLOUT=64 run ncu_full 90 ncu --set full --clock-control none --import-source on -k regex:env_step_kernel -s 4 -c 1 -f -o gpurun_out/${TAG}_rollout64 python tools/prof_rollout.py
 run pytest_rest 240 python -m pytest tests -m gpu -x -q --deselect tests/test_env_gpu.py
 run smoke 60 python __graft_entry__.py smoke
