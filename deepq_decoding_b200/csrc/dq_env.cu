@@ -50,11 +50,21 @@
 
 namespace dq {
 
+// Warp roles per CTA: 1 physics warp + writer warps + generator warps.  The physics warp is the one dependent chain that sets the
+// step time, and every other resident warp competes with it for issue slots, so the roles are sized to keep up and no larger:
+// at d <= 5 one writer warp (847 stream words per tile-step) and three generator warps; at d = 7 the observation is 2.4x larger and a
+// volume attempt draws three times the Philox blocks.
 #ifndef DQ_WRITERS
-#define DQ_WRITERS 3             // observation-writer warps per CTA
+#define DQ_WRITERS 1             // observation-writer warps per CTA, d <= 5
 #endif
 #ifndef DQ_GENS
-#define DQ_GENS 4                // volume-generator warps per CTA
+#define DQ_GENS 3                // volume-generator warps per CTA, d <= 5
+#endif
+#ifndef DQ_WRITERS_D7
+#define DQ_WRITERS_D7 3
+#endif
+#ifndef DQ_GENS_D7
+#define DQ_GENS_D7 4
 #endif
 #ifndef DQ_QDEPTH
 #define DQ_QDEPTH 4              // queued volume attempts per lattice (power of two)
@@ -63,12 +73,16 @@ namespace dq {
 #define DQ_MIN_BLOCKS 4          // resident CTAs per SM the register allocation must allow (16 384 lattices = 512 tiles = 3.5 per SM)
 #endif
 constexpr int kLpc = 32;                             // lattices per CTA = lanes of the physics warp
-constexpr int kWriters = DQ_WRITERS, kGens = DQ_GENS, kQ = DQ_QDEPTH;
-constexpr int kThreads = 32 * (1 + kWriters + kGens);
-constexpr int kWriterThreads = 32 * kWriters;
-constexpr int kOwned = (kLpc + kGens - 1) / kGens;   // lattices a generator warp serves: l = i*kGens + g
+constexpr int kQ = DQ_QDEPTH;
+template <int D> struct Roles {
+    static constexpr int kWriters = D >= 7 ? DQ_WRITERS_D7 : DQ_WRITERS, kGens = D >= 7 ? DQ_GENS_D7 : DQ_GENS;
+    static constexpr int kThreads = 32 * (1 + kWriters + kGens);
+    static constexpr int kWriterThreads = 32 * kWriters;
+    static constexpr int kOwned = (kLpc + kGens - 1) / kGens;   // lattices a generator warp serves: l = i*kGens + g
+    static_assert(kWriters >= 1 && kGens >= 1 && kThreads <= 1024, "warp roles");
+};
+constexpr int kMaxGens = 6;                          // shared-memory arrays and doorbell barriers are sized for this many generator warps
 static_assert((kQ & (kQ - 1)) == 0 && kQ >= 2, "queue depth must be a power of two");
-static_assert(kWriters >= 1 && kGens >= 1 && kThreads <= 1024, "warp roles");
 constexpr int kMaxVd = 8;
 constexpr int kMaxLayers = kMaxVd + 3;
 constexpr int kQW = kMaxVd + 2;                      // words of a queued attempt: g_0..g_{vd-1}, EX, EZ
@@ -85,7 +99,9 @@ constexpr long long kSpinTrapClocks = 4000000000ll;   // ~2 s of SM clocks: far 
 #endif
 constexpr int kRing = DQ_RING;
 constexpr int kStreamWords = kLpc * kMaxLayers * 15 * 15 / 32 + 1;
-constexpr int BAR_FULL = 1, BAR_EMPTY = BAR_FULL + kRing, BAR_WRITERS = BAR_EMPTY + kRing;    // named barriers (0 = __syncthreads)
+constexpr int BAR_FULL = 1, BAR_EMPTY = BAR_FULL + kRing, BAR_WRITERS = BAR_EMPTY + kRing, BAR_DOOR = BAR_WRITERS + 1;    // named barriers (0 = __syncthreads)
+static_assert(BAR_DOOR + kMaxGens <= 16, "the hardware has 16 named barriers per CTA");
+static_assert(Roles<3>::kGens <= kMaxGens && Roles<7>::kGens <= kMaxGens, "generator warps");
 // The reference loops until a volume is non-trivial, forever if p_phys = p_meas = 0 on a clean frame.
 // A kernel must end: after this many attempts on one volume the (trivial) volume is accepted.
 constexpr int kMaxAttemptsPerCall = 1 << 20;
@@ -161,16 +177,20 @@ __device__ __forceinline__ u32 sm_id() {
 #endif
 }
 
-// A fired draw (rare: p ~ 1e-2 per draw) is folded into the per-slice flip accumulators of the warp,
-// acc[kind][slice] as two 32-bit halves, kind 0 = data-qubit X flips, 1 = Z flips, 2 = measurement flips.
+// A fired draw (rare: p ~ 1e-2 per draw) is folded into the per-slice accumulators of the warp, acc[kind][slice] as two 32-bit
+// halves: kind 0 / 1 = the X / Z flips of the data qubits ACCUMULATED up to and including that slice (a flip in slice j is XOR-ed
+// into every slice j' >= j: the frame keeps it), kind 2 = the slice's measurement flips.
 template <int D>
-__device__ __noinline__ void record_event(u32* acc, int item, u32 uv, int nq_items, int n_items, u32 T1, u32 T2, int dp) {
+__device__ __noinline__ void record_event(u32* acc, int item, u32 uv, int nq_items, int n_items, u32 T1, u32 T2, int dp, int vd) {
     typedef Lat<D> L;
     if (item < nq_items) {
         const int j = item / L::NQ, q = item - j * L::NQ, pos = q + q / D;
         const u32 bit = 1u << (pos & 31);
-        if (!dp || uv < T2) atomicXor(&acc[((0 * kMaxVd + j) << 1) + (pos >> 5)], bit);     // X or Y
-        if (dp && uv >= T1) atomicXor(&acc[((1 * kMaxVd + j) << 1) + (pos >> 5)], bit);     // Y or Z
+        const bool fx = !dp || uv < T2, fz = dp && uv >= T1;                                  // X or Y / Y or Z
+        for (int jj = j; jj < vd; ++jj) {
+            if (fx) atomicXor(&acc[((0 * kMaxVd + jj) << 1) + (pos >> 5)], bit);
+            if (fz) atomicXor(&acc[((1 * kMaxVd + jj) << 1) + (pos >> 5)], bit);
+        }
     } else if (item < n_items) {
         const int mi = item - nq_items, j = mi / L::NS, k = mi - j * L::NS, pos = L::stab_pos(k);
         atomicXor(&acc[((2 * kMaxVd + j) << 1) + (pos >> 5)], 1u << (pos & 31));
@@ -210,7 +230,7 @@ __device__ __forceinline__ void draw_flip_masks(const EnvParams& p, u32* acc, in
                 const u32 uv = (w & 4) ? hi4 : lo4;
                 const int item = ((w & 3) * R + r + (w >> 2)) * 32 + lane;      // = word*B + block
                 const u32 thr = (item < nq_items) ? p.T : p.Tm;
-                if (uv < thr) record_event<D>(acc, item, uv, nq_items, n_items, p.T1, p.T2, dp);
+                if (uv < thr) record_event<D>(acc, item, uv, nq_items, n_items, p.T1, p.T2, dp, vd);
             } while (hits);
         }
     }
@@ -218,25 +238,18 @@ __device__ __forceinline__ void draw_flip_masks(const EnvParams& p, u32* acc, in
 }
 
 // One volume attempt (the body of the loop at Environments.py:158-170 / :216-230) in its state-free form, executed by a
-// full warp into queue slot `dst` (word w of the entry at dst[w * kLpc]): lane j < vd owns slice j -- a warp prefix-XOR gives
-// the accumulated data-qubit flips after every slice, one shifted-XOR syndrome per lane the slice's g_j.
+// full warp into queue slot `dst` (word w of the entry at dst[w * kLpc]): lane j < vd owns slice j -- the accumulators hold the
+// data-qubit flips accumulated up to every slice, one shifted-XOR syndrome per lane gives the slice's g_j.
 template <int D>
 __device__ __forceinline__ void generate_attempt(const EnvParams& p, u32* acc, int lane, u32 env_id, u32 attempt, volatile u64* dst) {
-    constexpr u32 FULL = 0xffffffffu;
     const int vd = p.vd;
     draw_flip_masks<D>(p, acc, lane, env_id, attempt);
-    u64 ex = 0, ez = 0, m = 0;
     if (lane < vd) {
         const u64* a64 = reinterpret_cast<const u64*>(acc);
-        ex = a64[0 * kMaxVd + lane]; ez = a64[1 * kMaxVd + lane]; m = a64[2 * kMaxVd + lane];
+        const u64 ex = a64[0 * kMaxVd + lane], ez = a64[1 * kMaxVd + lane], m = a64[2 * kMaxVd + lane];
+        dst[lane * kLpc] = true_syndrome<D>(ex, ez) ^ m;
+        if (lane == vd - 1) { dst[kMaxVd * kLpc] = ex; dst[(kMaxVd + 1) * kLpc] = ez; }
     }
-#pragma unroll
-    for (int off = 1; off < kMaxVd; off <<= 1) {      // inclusive prefix XOR over slices
-        const u64 tx = __shfl_up_sync(FULL, ex, off), tz = __shfl_up_sync(FULL, ez, off);
-        if (lane >= off) { ex ^= tx; ez ^= tz; }
-    }
-    if (lane < vd) dst[lane * kLpc] = true_syndrome<D>(ex, ez) ^ m;
-    if (lane == vd - 1) { dst[kMaxVd * kLpc] = ex; dst[(kMaxVd + 1) * kLpc] = ez; }
     __syncwarp();                                      // acc is rewritten by the next attempt
 }
 
@@ -258,9 +271,9 @@ struct Smem {
     u64 q[kQ][kQW][kLpc];             // rollouts: the tile's volume queues (a single-step launch works on the device-memory copy)
     u32 head[kLpc], tail[kLpc];       // attempt indices: next to pop (= the lattice's attempt counter) / first not yet queued
     u32 quit;                         // the physics warp has popped its last volume of the launch
-    u32 door;                         // bumped by the physics warp with every pop: idle generators watch it
+    u32 gsleep[kMaxGens];                // 1: generator warp g found all its queues full and is about to sleep (or sleeps) at its doorbell
     u32 rot;                          // warp-role rotation of this CTA
-    __align__(16) u32 acc[kGens][3 * kMaxVd * 2];   // per-generator-warp flip accumulators (read back as 64-bit words)
+    __align__(16) u32 acc[kMaxGens][3 * kMaxVd * 2];   // per-generator-warp flip accumulators (read back as 64-bit words)
 };
 
 // Layer bitmap w (P bits in PW u64 words, bits >= P zero) -> its place in the tile's bit stream: bits [off, off + P), at any alignment.
@@ -356,7 +369,7 @@ __device__ __forceinline__ void write_observations(const Smem& sm, const EnvPara
 }
 
 template <int D, bool RESET>
-__global__ void __launch_bounds__(kThreads, DQ_MIN_BLOCKS)
+__global__ void __launch_bounds__(Roles<D>::kThreads, DQ_MIN_BLOCKS)
 env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t* __restrict__ obs0,
                 float* __restrict__ reward0, uint8_t* __restrict__ done0, int32_t* __restrict__ lifetime0,
                 u64* __restrict__ legal0, int auto_reset, u32* __restrict__ policy_ctr, int32_t* __restrict__ actions_out0,
@@ -364,6 +377,8 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     typedef Lat<D> L;
     constexpr u32 FULL = 0xffffffffu;
     constexpr int PW = L::PW, H = L::H;
+    constexpr int kWriters = Roles<D>::kWriters, kGens = Roles<D>::kGens, kThreads = Roles<D>::kThreads;
+    constexpr int kWriterThreads = Roles<D>::kWriterThreads, kOwned = Roles<D>::kOwned;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -392,7 +407,8 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         if (p.q_reset || tail - head > (u32)kQ) tail = head;      // nothing usable queued (first launch, injected state, new noise rates)
         sm.head[tid] = head; sm.tail[tid] = tail;
         if (tid == 0) {
-            sm.quit = 0; sm.door = 0;
+            sm.quit = 0;
+            for (int gg = 0; gg < kGens; ++gg) sm.gsleep[gg] = 0;
             // Warp w of a CTA runs on scheduler (w mod 4) of its SM when CTAs are multiples of four warps, so without a rotation
             // every physics warp of an SM -- the one dependent chain that sets the step time -- would share ONE scheduler with
             // its siblings of the co-resident CTAs.  The k-th CTA to start on an SM rotates its roles by k.
@@ -501,25 +517,28 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                 __threadfence_block();
                 const int slot = (int)(attempts & (u32)(kQ - 1));
                 const u64 s0 = true_syndrome<D>(xb, zb);
-                u64 g[kMaxVd], ex, ez;
+                u64 nz = 0, ex, ez;
                 if (q_in_smem) {                                      // rollout: plain shared-memory loads
 #pragma unroll
-                    for (int j = 0; j < kMaxVd; ++j) g[j] = j < p.vd ? sm.q[slot][j][lane] : 0ull;
+                    for (int j = 0; j < kMaxVd; ++j) {
+                        if (j < p.vd) {
+                            const u64 fj = sm.q[slot][j][lane] ^ s0;
+                            nz |= fj;
+                            sm.rec_f[r][j][lane] = fj;
+                        }
+                    }
                     ex = sm.q[slot][kMaxVd][lane]; ez = sm.q[slot][kMaxVd + 1][lane];
                 } else {                                              // single step: the device-memory copy, refilled in place by this CTA's generators
                     const volatile u64* const ent = gq + (size_t)slot * (kQW * kLpc) + lane;
 #pragma unroll
-                    for (int j = 0; j < kMaxVd; ++j) g[j] = j < p.vd ? ent[j * kLpc] : 0ull;
-                    ex = ent[kMaxVd * kLpc]; ez = ent[(kMaxVd + 1) * kLpc];
-                }
-                u64 nz = 0;
-#pragma unroll
-                for (int j = 0; j < kMaxVd; ++j) {
-                    if (j < p.vd) {
-                        const u64 fj = g[j] ^ s0;
-                        nz |= fj;
-                        sm.rec_f[r][j][lane] = fj;
+                    for (int j = 0; j < kMaxVd; ++j) {
+                        if (j < p.vd) {
+                            const u64 fj = ent[j * kLpc] ^ s0;
+                            nz |= fj;
+                            sm.rec_f[r][j][lane] = fj;
+                        }
                     }
+                    ex = ent[kMaxVd * kLpc]; ez = ent[(kMaxVd + 1) * kLpc];
                 }
                 xb ^= ex;
                 zb ^= ez;
@@ -533,8 +552,20 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                 }
                 __threadfence_block();                                // the entry has been read before its slot is offered for refill
                 vhead[lane] = attempts;
-                __threadfence_block();
-                atomicAdd(&sm.door, 1u);                              // wake idle generators NOW: this lane may need the refill within this very step
+            }
+        };
+        // Doorbells: a generator warp that finds all its queues full announces it (gsleep[g] = 1), looks once more, and sleeps in
+        // `bar.sync BAR_DOOR+g, 64`.  The physics warp rings after EVERY pass that popped (a lane may need the refill within this very
+        // step): whoever clears gsleep[g] decides -- if the physics warp does, it arrives (32 threads) and the generator's sync completes,
+        // now or when it gets there; if the generator does (it found work on its second look), nobody arrives and it does not sync.
+        // Arrivals and syncs therefore pair one to one, and a pop made after the generator's last look always finds the flag set.
+        auto ring_doorbells = [&]() {
+            __threadfence_block();
+#pragma unroll
+            for (int gg = 0; gg < kGens; ++gg) {
+                u32 was = 0;
+                if (lane == 0) was = atomicCAS(&sm.gsleep[gg], 1u, 0u);
+                if (__shfl_sync(FULL, was, 0)) bar_arrive_named(BAR_DOOR + gg, 64);
             }
         };
 
@@ -563,7 +594,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                 heavy = live && a_heavy;
                 rw = a_rw; actbit = a_actbit;
                 todo = heavy ? 1u : 0u;
-                if (__any_sync(FULL, todo != 0)) pop_pass(r);
+                if (__any_sync(FULL, todo != 0)) { pop_pass(r); ring_doorbells(); }
                 if (live && a_cls != a_label) dn = 1;                    // Environments.py:150 (a rewarded step cannot end the episode: a_cls == a_label there)
                 dn_out = dn;
                 if (live && dn && auto_reset) todo |= 2u;
@@ -571,7 +602,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                 todo = live ? 2u : 0u;    // reset keeps only the attempt counter (the position in the random stream)
             }
             const bool vol = heavy || todo != 0;
-            while (__any_sync(FULL, todo != 0)) pop_pass(r);
+            while (__any_sync(FULL, todo != 0)) { pop_pass(r); ring_doorbells(); }
             if (vol) { act[0] = 0; act[1] = 0; act[2] = 0; summed = sum_new; }
             sm.rec_actbit[r][lane] = vol ? -1 : actbit;
             const u32 vm = __ballot_sync(FULL, vol);
@@ -611,6 +642,8 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         for (int l = 0; l < 3; ++l) if (l < p.layers) p.state[(ROW_ACT + l) * np + e] = act[l];
         __threadfence_block();
         if (lane == 0) *reinterpret_cast<volatile u32*>(&sm.quit) = 1u;
+        __syncwarp();
+        ring_doorbells();                    // sleeping generators wake up and leave
     } else if (role <= kWriters) {
         // ================================================================== WRITERS
         const int t = (role - 1) * 32 + lane;
@@ -672,28 +705,38 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         volatile u32* const vtail = sm.tail;
         volatile u32* const vhead = sm.head;
         const int mine = lane * kGens + g;                        // lanes < kOwned look at one owned lattice each
+        bool announced = false;
         for (;;) {
             u32 quit = *reinterpret_cast<volatile u32*>(&sm.quit);
-            u32 door = *reinterpret_cast<volatile u32*>(&sm.door);
-            __threadfence_block();                                 // quit / door are read BEFORE the heads they were published after
+            __threadfence_block();                                 // quit is read BEFORE the heads it was published after
             quit = __shfl_sync(FULL, quit, 0);                     // one value for the warp: the lanes leave the loop together
-            door = __shfl_sync(FULL, door, 0);
+            // The launch ends with the physics warp: queues that are not full stay that way until the next launch, whose generators
+            // fill them beside its physics warp (DQ_QDEPTH attempts of slack per lattice).  Topping them up here instead would make
+            // every single-step launch wait for the generator warp with the most pops to replace.
+            if (quit) break;
             u32 key = 0;                                           // (emptiness << 8) | (255 - lane): the emptiest queue first, then the lowest lattice
             if (lane < kOwned && mine < nvalid) {
                 const u32 fill = vtail[mine] - vhead[mine];
                 if (fill < (u32)kQ) key = (((u32)kQ - fill) << 8) | (u32)(255 - lane);
             }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) key = max(key, __shfl_xor_sync(FULL, key, off));
+            key = __reduce_max_sync(FULL, key);                    // one REDUX instruction
             if (key == 0) {                                        // every queue of this warp is full
-                if (quit) break;
-                for (;;) {                                         // sleep until the physics warp pops again (or ends): one shared-memory word to watch
-                    u32 d = *reinterpret_cast<volatile u32*>(&sm.door) ^ door;
-                    d |= *reinterpret_cast<volatile u32*>(&sm.quit);
-                    if (__shfl_sync(FULL, d, 0)) break;
-                    spin_pause(200);
+                if (!announced) {                                  // announce, then look once more (a pop may have slipped in between)
+                    if (lane == 0) *reinterpret_cast<volatile u32*>(&sm.gsleep[g]) = 1u;
+                    __threadfence_block();
+                    __syncwarp();
+                    announced = true;
+                    continue;
                 }
+                bar_sync_named(BAR_DOOR + g, 64);                  // sleep until the physics warp pops again (or ends); it cleared the flag
+                announced = false;
                 continue;
+            }
+            if (announced) {                                       // work turned up on the second look: take the announcement back ...
+                u32 was = 0;
+                if (lane == 0) was = atomicCAS(&sm.gsleep[g], 1u, 0u);
+                if (!__shfl_sync(FULL, was, 0)) bar_sync_named(BAR_DOOR + g, 64);      // ... unless the physics warp already answered it: take its arrival
+                announced = false;
             }
             const int l = (255 - (int)(key & 0xFFu)) * kGens + g;
             const u32 t = vtail[l];
@@ -768,10 +811,12 @@ struct dq_env {
     // staging for the *_host entry points
     cudaStream_t hstream;
     u32* policy_ctr;             // {step index, finished-CTA count} for dq_policy_random_legal_next
-    int32_t* s_actions; uint8_t* s_obs; float* s_reward; uint8_t* s_done; int32_t* s_life; u64* s_legal;
+    int32_t* s_actions; uint8_t* s_obs; float* s_reward; uint8_t* s_done; int32_t* s_life; u64* s_legal;      // s_reward .. s_legal point into s_small
+    uint8_t* s_small; uint8_t* h_small; size_t small_bytes;
     u64* h_packed;               // pinned landing buffer of the bit-packed observation rows (host-side expansion)
     bool q_reset;                // the next launch must discard the queued volume attempts (noise rates changed)
     cudaEvent_t h_ev[kHostChunks];   // "this lattice range of the rows has landed"
+    cudaEvent_t h_ev_small;          // "the small outputs have landed"
     HostCall hc;                 // the host-buffer call in flight (dq_env_step_host_begin .. _end)
 };
 
@@ -879,9 +924,11 @@ extern "C" int dq_env_destroy(dq_env* e) {
     DeviceGuard g(e->device);
     if (e->hstream) {
         cudaStreamSynchronize(e->hstream);
-        cudaFree(e->s_actions); cudaFree(e->s_obs); cudaFree(e->s_reward); cudaFree(e->s_done); cudaFree(e->s_life); cudaFree(e->s_legal);
+        cudaFree(e->s_actions); cudaFree(e->s_obs); cudaFree(e->s_small);
+        if (e->h_small) cudaFreeHost(e->h_small);
         if (e->h_packed) cudaFreeHost(e->h_packed);
         for (int c = 0; c < kHostChunks; ++c) if (e->h_ev[c]) cudaEventDestroy(e->h_ev[c]);
+        if (e->h_ev_small) cudaEventDestroy(e->h_ev_small);
         cudaStreamDestroy(e->hstream);
     }
     cudaFree(e->p.state);
@@ -952,11 +999,11 @@ static int launch_env(dq_env* e, const int32_t* actions, uint8_t* obs, float* re
     EnvParams p = e->p;
     p.q_reset = e->q_reset ? 1 : 0;
     e->q_reset = false;
-    const dim3 grid(p.npad / kLpc), block(kThreads);
+    const dim3 grid(p.npad / kLpc);
     switch (p.d) {
-        case 3: env_step_kernel<3, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;
-        case 5: env_step_kernel<5, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;
-        case 7: env_step_kernel<7, RESET><<<grid, block, e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;
+        case 3: env_step_kernel<3, RESET><<<grid, dim3(Roles<3>::kThreads), e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;
+        case 5: env_step_kernel<5, RESET><<<grid, dim3(Roles<5>::kThreads), e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;
+        case 7: env_step_kernel<7, RESET><<<grid, dim3(Roles<7>::kThreads), e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;
     }
     g_launches.fetch_add(1);
     DQ_CUDA(cudaGetLastError());
@@ -1004,11 +1051,17 @@ static int ensure_staging(dq_env* e) {
     const EnvParams& p = e->p;
     DQ_CUDA(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
     DQ_CUDA(cudaMalloc(&e->s_actions, (size_t)p.n * 4));
-    DQ_CUDA(cudaMalloc(&e->s_reward, (size_t)p.n * 4));
-    DQ_CUDA(cudaMalloc(&e->s_done, (size_t)p.n));
-    DQ_CUDA(cudaMalloc(&e->s_life, (size_t)p.n * 4));
-    DQ_CUDA(cudaMalloc(&e->s_legal, (size_t)p.n * p.W * 8));
+    // the small outputs of a step sit in ONE device block [legal | reward | lifetime | done] so that one copy brings them all back
+    const size_t n = (size_t)p.n;
+    e->small_bytes = n * p.W * 8 + n * 4 + n * 4 + n;
+    DQ_CUDA(cudaMalloc(&e->s_small, e->small_bytes));
+    DQ_CUDA(cudaMallocHost(&e->h_small, e->small_bytes));
+    e->s_legal = reinterpret_cast<u64*>(e->s_small);
+    e->s_reward = reinterpret_cast<float*>(e->s_small + n * p.W * 8);
+    e->s_life = reinterpret_cast<int32_t*>(e->s_small + n * p.W * 8 + n * 4);
+    e->s_done = reinterpret_cast<uint8_t*>(e->s_small + n * p.W * 8 + n * 8);
     for (int c = 0; c < kHostChunks; ++c) DQ_CUDA(cudaEventCreateWithFlags(&e->h_ev[c], cudaEventDisableTiming));
+    DQ_CUDA(cudaEventCreateWithFlags(&e->h_ev_small, cudaEventDisableTiming));
     return DQ_OK;
 }
 
@@ -1149,26 +1202,99 @@ static void expand_packed_host(const u64* packed, size_t npad, int first, int la
     host_pool().parallel_for(nb, block);
 }
 
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static inline void mulhilo_x8(__m256i m, __m256i x, __m256i& hi, __m256i& lo) {      // 8 x (32 x 32 -> 64)
+    const __m256i pe = _mm256_mul_epu32(m, x);                                   // even lanes: 64-bit products
+    const __m256i po = _mm256_mul_epu32(m, _mm256_srli_epi64(x, 32));            // odd lanes
+    lo = _mm256_blend_epi32(pe, _mm256_slli_epi64(po, 32), 0xAA);
+    hi = _mm256_blend_epi32(_mm256_srli_epi64(pe, 32), po, 0xAA);
+}
+// word 0 of Philox4x32-10(counter = (id0 + lane, c1, 0, 1), key) for 8 consecutive stream ids: the policy draw of 8 lattices at once
+__attribute__((target("avx2"))) static inline void philox_word0_x8(uint32_t id0, uint32_t c1, uint32_t k0, uint32_t k1, uint32_t* out8) {
+    const __m256i M0 = _mm256_set1_epi32((int)0xD2511F53u), M1 = _mm256_set1_epi32((int)0xCD9E8D57u);
+    __m256i a = _mm256_add_epi32(_mm256_set1_epi32((int)id0), _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7));
+    __m256i b = _mm256_set1_epi32((int)c1), c = _mm256_setzero_si256(), d = _mm256_set1_epi32(1);
+    for (int r = 0; r < 10; ++r) {
+        __m256i h0, l0, h1, l1;
+        mulhilo_x8(M0, a, h0, l0);
+        mulhilo_x8(M1, c, h1, l1);
+        const __m256i n0 = _mm256_xor_si256(_mm256_xor_si256(h1, b), _mm256_set1_epi32((int)k0));
+        const __m256i n2 = _mm256_xor_si256(_mm256_xor_si256(h0, d), _mm256_set1_epi32((int)k1));
+        a = n0; b = l1; c = n2; d = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    _mm256_storeu_si256(reinterpret_cast<__m256i*>(out8), a);
+}
+#endif
+
+// The pick itself, compiled with the POPCNT instruction where the host has it (the generic build calls libgcc's table popcount:
+// ~10 of them per pick were the whole cost of the host policy).
+#if defined(__x86_64__)
+#define DQ_HOST_POPCNT __attribute__((target("popcnt")))
+#else
+#define DQ_HOST_POPCNT
+#endif
+static inline int generic_pick(const u64* m, int W, int A, u32 ux) {      // the same pick with the portable helpers
+    int cnt = 0;
+    for (int w = 0; w < W; ++w) cnt += popc64(m[w]);
+    int pick = (int)mulhi32(ux, (u32)cnt);
+    for (int w = 0; w < W; ++w) {
+        const int c = popc64(m[w]);
+        if (pick < c) return w * 64 + select64(m[w], pick);
+        pick -= c;
+    }
+    return A - 1;
+}
+DQ_HOST_POPCNT static inline int host_select64(u64 x, int k) {      // position of the k-th set bit (k < popcount)
+    u32 w = (u32)x;
+    int base = 0;
+    const int c0 = __builtin_popcount(w);
+    if (k >= c0) { k -= c0; w = (u32)(x >> 32); base = 32; }
+    for (int sft = 16; sft >= 1; sft >>= 1) {
+        const int c = __builtin_popcount(w & ((1u << sft) - 1u));
+        if (k >= c) { k -= c; w >>= sft; base += sft; }
+    }
+    return base;
+}
+DQ_HOST_POPCNT static inline int host_pick(const u64* m, int W, int A, u32 ux) {
+    int cnt = 0;
+    for (int w = 0; w < W; ++w) cnt += __builtin_popcountll(m[w]);
+    int pick = (int)(((u64)ux * (u32)cnt) >> 32);
+    for (int w = 0; w < W; ++w) {
+        const int c = __builtin_popcountll(m[w]);
+        if (pick < c) return w * 64 + host_select64(m[w], pick);
+        pick -= c;
+    }
+    return A - 1;
+}
+
 // Uniform pick over the sorted legal actions on the HOST (same draw as dq_policy_random_legal): for callers that drive the
 // *_host entry points and hold the legal masks in host memory.
 extern "C" int dq_policy_random_legal_host(const dq_env* e, const uint64_t* h_legal, uint32_t step_index, int32_t* h_actions) {
     if (!e || !h_legal || !h_actions) return fail(DQ_EINVAL, "NULL argument");
     const EnvParams& p = e->p;
     const int per = 512, nb = (p.n + per - 1) / per;
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("DQ_HOST_NO_AVX2");
+    static const bool have_popcnt = __builtin_cpu_supports("popcnt") && !getenv("DQ_HOST_NO_AVX2");
+#else
+    const bool avx2 = false, have_popcnt = false;
+#endif
     const std::function<void(int)> block = [&](int b) {
         const int e1 = std::min(p.n, (b + 1) * per);
+        uint32_t u8[8];
         for (int i = b * per; i < e1; ++i) {
-            const u64* m = h_legal + (size_t)i * p.W;
-            int cnt = 0;
-            for (int w = 0; w < p.W; ++w) cnt += popc64(m[w]);
-            const Philox4 u = philox4x32_10(p.env_id_base + (u32)i, step_index, 0u, 1u, p.k0, p.k1);
-            int pick = (int)mulhi32(u.x, (u32)cnt), act = p.A - 1;
-            for (int w = 0; w < p.W; ++w) {
-                const int c = popc64(m[w]);
-                if (pick < c) { act = w * 64 + select64(m[w], pick); break; }
-                pick -= c;
-            }
-            h_actions[i] = act;
+            u32 ux;
+            const int k = (i - b * per) & 7;
+#if defined(__x86_64__)
+            if (avx2) {
+                if (k == 0) philox_word0_x8(p.env_id_base + (u32)i, step_index, p.k0, p.k1, u8);
+                ux = u8[k];
+            } else
+#endif
+            ux = philox4x32_10(p.env_id_base + (u32)i, step_index, 0u, 1u, p.k0, p.k1).x;
+            (void)k;
+            h_actions[i] = have_popcnt ? host_pick(h_legal + (size_t)i * p.W, p.W, p.A, ux) : generic_pick(h_legal + (size_t)i * p.W, p.W, p.A, ux);
         }
     };
     host_pool().parallel_for(nb, block);
@@ -1178,14 +1304,18 @@ extern "C" int dq_policy_random_legal_host(const dq_env* e, const uint64_t* h_le
 // ---- host-buffer calls in two halves: *_begin queues the copy-in, the launch and every copy-out on the handle's own stream and
 // returns; *_end waits for the results and (host-side expansion) turns the landed bitmap rows into bytes.  Two handles driven
 // begin(A) begin(B) end(A) begin(A) end(B) ... overlap one handle's kernel and copies with the other's expansion on the host.
+static int host_chunks() {          // lattice ranges the bitmap rows cross PCIe in (each one costs two driver calls; DQ_HOST_CHUNKS, default 2)
+    static const int n = [] { const char* v = getenv("DQ_HOST_CHUNKS"); const int c = v ? atoi(v) : 2; return std::max(1, std::min(c, kHostChunks)); }();
+    return n;
+}
+
 static int queue_outputs(dq_env* e, bool bytes_on_device, uint64_t* h_packed_user) {
     const EnvParams& p = e->p;
     cudaStream_t s = e->hstream;
     HostCall& hc = e->hc;
-    if (hc.reward) DQ_CUDA(cudaMemcpyAsync(hc.reward, e->s_reward, (size_t)p.n * 4, cudaMemcpyDeviceToHost, s));
-    if (hc.done) DQ_CUDA(cudaMemcpyAsync(hc.done, e->s_done, (size_t)p.n, cudaMemcpyDeviceToHost, s));
-    if (hc.life) DQ_CUDA(cudaMemcpyAsync(hc.life, e->s_life, (size_t)p.n * 4, cudaMemcpyDeviceToHost, s));
-    if (hc.legal) DQ_CUDA(cudaMemcpyAsync(hc.legal, e->s_legal, (size_t)p.n * p.W * 8, cudaMemcpyDeviceToHost, s));
+    if (hc.reward || hc.done || hc.life) DQ_CUDA(cudaMemcpyAsync(e->h_small, e->s_small, e->small_bytes, cudaMemcpyDeviceToHost, s));
+    else if (hc.legal) DQ_CUDA(cudaMemcpyAsync(e->h_small, e->s_small, (size_t)p.n * p.W * 8, cudaMemcpyDeviceToHost, s));
+    DQ_CUDA(cudaEventRecord(e->h_ev_small, s));
     const size_t rows = (size_t)(e->state_rows - ROW_BM), words = rows * p.npad;
     const u64* src = p.state + (size_t)ROW_BM * p.npad;
     hc.chunks = 0;
@@ -1196,7 +1326,7 @@ static int queue_outputs(dq_env* e, bool bytes_on_device, uint64_t* h_packed_use
     } else if (hc.obs) {
         if (!e->h_packed) DQ_CUDA(cudaMallocHost(&e->h_packed, words * sizeof(u64)));
         // lattice ranges of the rows, one event each: the first range is being expanded while the others are still on the bus
-        const int nch = p.n >= 4096 ? kHostChunks : 1;
+        const int nch = p.n >= 4096 ? host_chunks() : 1;
         const int per = ((p.npad / nch) + 31) / 32 * 32;
         for (int c = 0, first = 0; c < nch && first < p.n; ++c, first += per) {
             const int cnt = std::min(per, p.npad - first);
@@ -1240,6 +1370,14 @@ static int host_end(dq_env* e) {
     HostCall& hc = e->hc;
     hc.pending = false;
     const int side = 2 * p.d + 1, P = side * side;
+    DQ_CUDA(cudaEventSynchronize(e->h_ev_small));
+    {
+        const size_t n = (size_t)p.n;
+        if (hc.legal) memcpy(hc.legal, e->h_small, n * p.W * 8);
+        if (hc.reward) memcpy(hc.reward, e->h_small + n * p.W * 8, n * 4);
+        if (hc.life) memcpy(hc.life, e->h_small + n * p.W * 8 + n * 4, n * 4);
+        if (hc.done) memcpy(hc.done, e->h_small + n * p.W * 8 + n * 8, n);
+    }
     for (int c = 0; c < hc.chunks; ++c) {
         DQ_CUDA(cudaEventSynchronize(e->h_ev[c]));
         expand_packed_host(e->h_packed, (size_t)p.npad, hc.first[c], hc.last[c], p.vd + p.layers, (P + 63) / 64, P, hc.obs);

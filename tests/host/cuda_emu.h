@@ -133,22 +133,30 @@ inline void block_barrier() {
     }
 }
 
-// bar.sync id, count: the barrier completes when `count` threads have arrived
-inline void named_barrier(int id, int count) {
+// bar.sync id, count / bar.arrive id, count.  The hardware executes barrier instructions per WARP, as if all its threads were active:
+// a warp arrives as one unit of 32.  The fibers of a warp therefore first meet (a warp-wide rendez-vous), one of them adds the warp's
+// 32 arrivals, and -- for bar.sync -- all of them wait for the phase to complete.  Callers must be warp-converged, as on the GPU.
+inline void named_barrier_impl(int id, int count, bool wait) {
     Cta& c = *cta();
     if (id < 1 || id > 15 || count % 32) { fprintf(stderr, "dq_emu: bad named barrier (%d, %d)\n", id, count); abort(); }
-    const int gen = c.nbar_gen[id];
-    if (++c.nbar_count[id] >= count) { c.nbar_count[id] = 0; c.nbar_gen[id]++; c.progress++; return; }
-    while (c.nbar_gen[id] == gen) yield();
+    const int w = c.cur >> 5, lane = c.cur & 31;
+    const uint32_t lanes = lanes_of_warp(c, w);
+    int gen = c.nbar_gen[id];
+    const uint64_t* v = warp_collect(lanes, (uint64_t)(unsigned)gen);       // every lane sees the phase the warp's LOWEST lane sampled
+    int low = 0;
+    while (!((lanes >> low) & 1u)) ++low;
+    gen = (int)v[low];
+    if (lane == low) {
+        c.nbar_count[id] += 32;
+        if (c.nbar_count[id] >= count) { c.nbar_count[id] = 0; c.nbar_gen[id]++; }
+        c.progress++;
+    }
+    warp_collect(lanes, 0);                                                 // the arrival is registered before any lane moves on
+    if (wait)
+        while (c.nbar_gen[id] == gen) yield();
 }
-
-// bar.arrive id, count: arrive at the barrier without waiting for it
-inline void named_barrier_arrive(int id, int count) {
-    Cta& c = *cta();
-    if (id < 1 || id > 15 || count % 32) { fprintf(stderr, "dq_emu: bad named barrier (%d, %d)\n", id, count); abort(); }
-    if (++c.nbar_count[id] >= count) { c.nbar_count[id] = 0; c.nbar_gen[id]++; }
-    c.progress++;
-}
+inline void named_barrier(int id, int count) { named_barrier_impl(id, count, true); }
+inline void named_barrier_arrive(int id, int count) { named_barrier_impl(id, count, false); }
 
 inline int idle_limit() { static int m = -1; if (m < 0) { const char* e = getenv("DQ_EMU_IDLE"); m = e ? atoi(e) : 2; } return m; }
 inline int sched_mode() { static int m = -1; if (m < 0) { const char* e = getenv("DQ_EMU_SCHED"); m = e ? atoi(e) : 0; } return m; }
@@ -239,6 +247,14 @@ static inline uint32_t __ballot_sync(uint32_t mask, int pred) {
     for (int i = 0; i < 32; ++i) if (((mask >> i) & 1u) && v[i]) b |= 1u << i;
     return b;
 }
+static inline uint32_t __reduce_max_sync(uint32_t mask, uint32_t v) {
+    const uint64_t* a = dq_emu::warp_collect(mask, v);
+    const dq_emu::Cta& c = *dq_emu::cta();
+    mask &= dq_emu::lanes_of_warp(c, c.cur >> 5);
+    uint32_t m = 0;
+    for (int i = 0; i < 32; ++i) if ((mask >> i) & 1u) m = std::max(m, (uint32_t)a[i]);
+    return m;
+}
 static inline int __any_sync(uint32_t mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 static inline int __all_sync(uint32_t mask, int pred) { return __ballot_sync(mask, !pred) == 0; }
 
@@ -308,6 +324,7 @@ template <typename T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + 
 template <typename T> static inline T atomicXor(T* p, T v) { T o = *p; *p = o ^ v; return o; }
 template <typename T> static inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
 template <typename T> static inline T atomicAnd(T* p, T v) { T o = *p; *p = o & v; return o; }
+template <typename T> static inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 
 // ---- the slice of the runtime API the host side of dq_env.cu uses: "device memory" is host memory ------------
 typedef int cudaError_t;

@@ -281,6 +281,73 @@ def test_single_error_syndrome_kat():
     env.close()
 
 
+def test_c3_exact_parameters_bit_exact_against_the_oracle():
+    """BASELINE config C3 at its exact parameters -- d=5 depolarising, p_phys = p_meas = 0.007, volume depth 5, 16 384 lattices, the
+    SHIPPED referee (the reference's nn_d5_DP_p5 as a table) -- bit for bit against the oracle: explicit-action steps (random-legal picks
+    with 10 % arbitrary, possibly illegal or repeated actions), then a rollout under the built-in policy, every output of every step."""
+    import ctypes as C
+    import torch
+    from deepq_decoding_b200 import _lib, referee as R
+    n = 16384
+    env, o = make_pair(5, "DP", False, 5, 0.007, n, seed=2026, base=0, referee=R.shipped(5, "DP"))
+    obs = env.reset().cpu().numpy()
+    oobs, olegal = o.reset()
+    assert np.array_equal(obs, oobs)
+    rng = np.random.default_rng(7)
+    ndone = 0
+    for t in range(12):
+        acts = o.random_legal_actions(olegal, t)
+        arb = rng.random(n) < 0.1
+        acts[arb] = rng.integers(0, o.A, size=int(arb.sum()))
+        obs, rew, done, info = env.step(torch.from_numpy(acts).cuda())
+        oobs, orew, odone, olife, olegal = o.step(acts, auto_reset=True)
+        assert np.array_equal(obs.cpu().numpy(), oobs), "obs t=%d" % t
+        assert np.array_equal(rew.cpu().numpy(), orew) and np.array_equal(done.cpu().numpy(), odone.astype(bool)), "reward / done t=%d" % t
+        assert np.array_equal(info["lifetime"].cpu().numpy(), olife) and np.array_equal(info["legal_mask"].cpu().numpy().view(np.uint64), olegal)
+        ndone += int(odone.sum())
+    L = _lib.lib()
+    p = lambda x: C.c_void_p(x.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    S, slots = 40, 3
+    ring = torch.zeros((slots,) + tuple(env.obs.shape), dtype=torch.uint8, device="cuda")
+    rew = torch.zeros((S, n), dtype=torch.float32, device="cuda"); done = torch.zeros((S, n), dtype=torch.uint8, device="cuda")
+    life = torch.zeros((S, n), dtype=torch.int32, device="cuda"); acts_out = torch.zeros((S, n), dtype=torch.int32, device="cuda")
+    legal = torch.zeros((S, n, env.mask_words), dtype=torch.int64, device="cuda")
+    _lib.check(L.dq_policy_seek(env._h, 100, st))
+    _lib.check(L.dq_env_rollout_random(env._h, S, p(ring), slots, 1, p(rew), p(done), p(life), p(legal), p(acts_out), 1, st))
+    torch.cuda.synchronize()
+    for s_ in range(S):
+        oa = o.random_legal_actions(olegal, 100 + s_)
+        oobs, orew, odone, olife, olegal = o.step(oa, auto_reset=True)
+        assert np.array_equal(acts_out[s_].cpu().numpy(), oa), "pick s=%d" % s_
+        assert np.array_equal(rew[s_].cpu().numpy(), orew) and np.array_equal(done[s_].cpu().numpy(), odone) and np.array_equal(life[s_].cpu().numpy(), olife)
+        assert np.array_equal(legal[s_].cpu().numpy().view(np.uint64), olegal)
+        ndone += int(odone.sum())
+        if s_ >= S - slots:
+            assert np.array_equal(ring[(1 + s_) % slots].cpu().numpy(), oobs), "ring obs s=%d" % s_
+    assert ndone > 1000, "the run must contain finished episodes (referee decisions)"
+    compare_state(env, o, rng.integers(0, n, size=16))
+    env.close()
+
+
+def test_attempt_cap_accepts_a_trivial_volume():
+    """Documented deviation (dq_env_set_max_attempts): at p = 0 the reference would redraw the all-trivial volume for ever."""
+    from deepq_decoding_b200 import _lib
+    env, o = make_pair(3, "DP", False, 3, 0.0, 40, seed=4)
+    _lib.check(_lib.lib().dq_env_set_max_attempts(env._h, 3)); o.set_max_attempts(3)
+    obs = env.reset().cpu().numpy()
+    oobs, olegal = o.reset()
+    assert np.array_equal(obs, oobs) and not obs[:, :, ::2, ::2].any()
+    for t in range(3):
+        acts = o.random_legal_actions(olegal, t)
+        import torch
+        obs, rew, done, info = env.step(torch.from_numpy(acts).cuda())
+        oobs, orew, odone, olife, olegal = o.step(acts, auto_reset=True)
+        assert np.array_equal(obs.cpu().numpy(), oobs) and np.array_equal(info["lifetime"].cpu().numpy(), olife)
+        assert (olife == (t + 2) * 9).all()
+    env.close()
+
+
 def test_full_size_properties():
     """BASELINE config 3 shape (d=5 DP p=0.007, 16384 lattices): size-independent invariants."""
     import torch

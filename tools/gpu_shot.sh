@@ -22,11 +22,15 @@ run ab_new 60 python tools/prof_rollout.py
 done
 DQ_CALLS=6 DQ_ONLY_ROLLOUT=64 DQ_N=262144 run big 40 python tools/prof_rollout.py      # every SM fully loaded
 DQ_D=7 DQ_N=8192 run d7 40 python tools/prof_rollout.py
+for v in d7w2g4 d7w2g5 d7w4g3; do DQ_CALLS=12 DQ_ONLY_ROLLOUT=256 DQ_D=7 DQ_N=8192 DQ_DECODING_LIB=build/variants/libdq_$v.so run d7_$v 30 python tools/prof_rollout.py; done
+run hostprof 200 python tools/prof_host_path.py
 run bench 150 python bench.py --cpu-seconds 3 --no-dqn
 run bench20 100 python bench.py --cpu-seconds 1 --no-dqn --steps 20 --warmup 3
 run bench_full 300 python bench.py --cpu-seconds 3
 run ncu_list 90 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_launches_rollout.csv python bench.py --steps 1024 --warmup 16 --cpu-seconds 0.2 --no-dqn
 DQ_ONLY_ROLLOUT=64 run ncu_full 90 ncu --set full --clock-control none --import-source on -k regex:env_step_kernel -s 4 -c 1 -f -o gpurun_out/${TAG}_rollout64 python tools/prof_rollout.py
+run ncu_full_single 90 ncu --set full --clock-control none --import-source on -k regex:env_step_kernel -s 30 -c 1 -f -o gpurun_out/${TAG}_single python tools/prof_rollout.py
+run fold_head 90 python tools/check_fold_head.py
 run pytest_rest 240 python -m pytest tests -m gpu -x -q --deselect tests/test_env_gpu.py
 run smoke 60 python __graft_entry__.py smoke
-for f in gpurun_out/${TAG}_ab_*.out gpurun_out/${TAG}_big.out gpurun_out/${TAG}_d7.out; do echo "$f $(cut -c1-400 $f)"; done
+for f in gpurun_out/${TAG}_ab_*.out gpurun_out/${TAG}_big.out gpurun_out/${TAG}_d7*.out; do echo "$f $(cut -c1-400 $f)"; done
