@@ -245,48 +245,51 @@ def e2e_legs(L, _lib, torch, np, dist, dev, world, rank, n, K):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return world * n * ke / float(t.item())
 
-    # (a) two handles of n/2 lattices, split calls: begin(A) begin(B) end(A) policy(A) begin(A) end(B) policy(B) begin(B) ...
-    for e in envs:
-        e.reset_host()
-    step = [0, 0]
-
-    def begin(k):
-        envs[k].random_legal_actions_host(step[k])
-        envs[k].step_host_begin()
-        step[k] += 1
-    for k in (0, 1):
-        begin(k)
-    for _ in range(3):
-        for k in (0, 1):
-            envs[k].step_host_end(); begin(k)
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(ke):
-        for k in (0, 1):
-            envs[k].step_host_end(); begin(k)
-    dt = time.perf_counter() - t0
-    for k in (0, 1):
-        envs[k].step_host_end()
-    e2e = {"value": rate(dt), "unit": UNIT, "h2d_bytes_per_step": n * 4,
-           "d2h_bytes_per_step": n * small + (packed_bytes if host_expand else n * obs_bytes), "steps": ke,
-           "host_bytes_delivered_per_step": n * (obs_bytes + small),
-           "api": "VecSurfaceCodeEnv.step_host_begin / step_host_end (dq_env_step_host_begin / _end) on two handles of %d lattices driven alternately, "
-                  "random_legal_actions_host (dq_policy_random_legal_host) in between; uint8 observations [N,C,H,H], reward, done, lifetime and "
-                  "legal masks land in pinned host memory every step" % half,
-           "host_expand": host_expand,
-           "how": "the bitmap rows cross PCIe bit-packed and the library's host threads expand them into the byte observations inside _end, while "
-                  "the other handle's kernel and copies run" if host_expand else "the kernel writes bytes; all of them are copied back",
-           "policy": "uniform random-legal, computed on the host from the returned legal masks"}
-    # (b) the one-piece call on one handle of n lattices (no overlap between the GPU and the host side)
+    # (a) the public call on one handle of n lattices: random-legal pick on the host, dq_env_step_host, every output landed -- per step
     whole.reset_host()
-    for i in range(3):
+    for i in range(4):
         whole.random_legal_actions_host(i); whole.step_host_begin(); whole.step_host_end()
     sync_all()
     t0 = time.perf_counter()
     for i in range(ke):
-        whole.random_legal_actions_host(3 + i); whole.step_host_begin(); whole.step_host_end()
-    e2e["one_handle_sync"] = {"value": rate(time.perf_counter() - t0), "unit": UNIT,
-                              "api": "dq_env_step_host on one handle of %d lattices, same policy" % n}
+        whole.random_legal_actions_host(4 + i); whole.step_host_begin(); whole.step_host_end()
+    dt = time.perf_counter() - t0
+    e2e = {"value": rate(dt), "unit": UNIT, "h2d_bytes_per_step": n * 4,
+           "d2h_bytes_per_step": n * small + (packed_bytes if host_expand else n * obs_bytes), "steps": ke,
+           "host_bytes_delivered_per_step": n * (obs_bytes + small),
+           "api": "VecSurfaceCodeEnv.random_legal_actions_host + step_host_begin / step_host_end (dq_policy_random_legal_host, dq_env_step_host) on one "
+                  "handle of %d lattices: uint8 observations [N,C,H,H], reward, done, lifetime and legal masks land in pinned host memory every step" % n,
+           "host_expand": host_expand,
+           "how": "the bitmap rows cross PCIe bit-packed and the library's host threads expand them into the byte observations"
+                  if host_expand else "the kernel writes bytes; all of them are copied back",
+           "policy": "uniform random-legal, computed on the host from the returned legal masks (same picks as the device policy)"}
+    # (b) two handles of n/2 lattices driven alternately -- begin(A) begin(B) end(A) policy(A) begin(A) end(B) ... -- so that one handle's
+    #     kernel and copies run under the other's host-side work
+    try:
+        for e in envs:
+            e.reset_host()
+        step = [0, 0]
+
+        def begin(k):
+            envs[k].random_legal_actions_host(step[k])
+            envs[k].step_host_begin()
+            step[k] += 1
+        for k in (0, 1):
+            begin(k)
+        for _ in range(8):
+            for k in (0, 1):
+                envs[k].step_host_end(); begin(k)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            for k in (0, 1):
+                envs[k].step_host_end(); begin(k)
+        dt2 = time.perf_counter() - t0
+        for k in (0, 1):
+            envs[k].step_host_end()
+        e2e["two_handles"] = {"value": rate(dt2), "unit": UNIT, "api": "the same calls on two handles of %d lattices, split begin / end, driven alternately" % half}
+    except Exception as ex:      # noqa: BLE001
+        e2e["two_handles"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
     # (c) observations returned PACKED (one bit per cell, the rows the Q-network consumes): nothing to expand anywhere
     e2e_packed = None
     try:
@@ -688,7 +691,10 @@ def run_b200(args):
 
         t_fwd = timed(lambda i: agent.model.forward_packed(rows_ptr.value, stride.value, n), 30)
         t_fwd_tc = timed(lambda i: agent.model.forward_packed(rows_ptr.value, stride.value, n, precision="bf16"), 30)
-        t_env = timed(lambda i: _lib.check(L.dq_env_step(h, p_act, None, p_rew, p_done, p_life, p_legal, 1, cur())), 60)
+        def ext_step(i):      # the launch every real policy uses: actions from a device buffer, packed observations only (obs = NULL)
+            _lib.check(L.dq_policy_random_legal_next(h, p_legal, p_act, cur()))
+            _lib.check(L.dq_env_step(h, p_act, None, p_rew, p_done, p_life, p_legal, 1, cur()))
+        t_env = timed(ext_step, 100)
         t_act32 = timed(lambda i: act_iter(i, False), 40)
         agent.act_precision = "bf16"
         t_act = timed(lambda i: act_iter(i, False), 60)
@@ -708,7 +714,7 @@ def run_b200(args):
                "train_env_steps_per_s": n / t_train, "train_ms_per_iteration": t_train * 1e3,
                "train_batch": 4096, "updates_per_iteration": 1,
                "act_fp32_env_steps_per_s": n / t_act32,
-               "env_step_external_actions_us": t_env * 1e6,
+               "policy_kernel_plus_env_step_external_actions_us": t_env * 1e6,
                "qnet_forward_fp32_ms": t_fwd * 1e3, "qnet_forward_fp32_tflops": flops * n / t_fwd / 1e12,
                "qnet_forward_bf16_ms": t_fwd_tc * 1e3, "qnet_forward_bf16_tflops": flops * n / t_fwd_tc / 1e12,
                "qnet_frac_of_bf16_sustained_peak": flops * n / t_fwd_tc / 1e12 / tf_peak,

@@ -61,10 +61,10 @@ namespace dq {
 #define DQ_GENS 3                // volume-generator warps per CTA, d <= 5
 #endif
 #ifndef DQ_WRITERS_D7
-#define DQ_WRITERS_D7 3
+#define DQ_WRITERS_D7 2
 #endif
 #ifndef DQ_GENS_D7
-#define DQ_GENS_D7 4
+#define DQ_GENS_D7 5
 #endif
 #ifndef DQ_QDEPTH
 #define DQ_QDEPTH 4              // queued volume attempts per lattice (power of two)
@@ -401,6 +401,17 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         u64* sq = &sm.q[0][0][0];
         for (int i = tid; i < kQ * kQW * kLpc; i += kThreads) sq[i] = gq[i];
     }
+    // the bit stream as the state stands at launch: every (lattice, layer) bitmap row into its place, by every thread of the CTA (a
+    // single-step launch would otherwise wait for its few writer threads to do this before they can look at the step's record)
+    if (obs0) {
+        for (int i = tid; i < kLpc * C; i += kThreads) {
+            const int l = i / C, c = i - l * C;
+            u64 w[PW];
+#pragma unroll
+            for (int j = 0; j < PW; ++j) w[j] = p.state[(ROW_BM + c * PW + j) * np + env0 + l];
+            place_layer<D>(sm.stream, l * p.obs_bits + c * L::P, w);
+        }
+    }
     if (tid < kLpc) {
         const u32 head = (u32)(p.state[ROW_META * np + env0 + tid] >> 32) & 0x7FFFFFFFu;
         u32 tail = p.qtail[env0 + tid];
@@ -648,17 +659,6 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         // ================================================================== WRITERS
         const int t = (role - 1) * 32 + lane;
         int ring_slot = ro.first_slot;
-        // the stream as the state stands at launch: every (lattice, layer) bitmap row into its place (while the physics warp runs step 0)
-        if (obs0) {
-            for (int i = t; i < kLpc * C; i += kWriterThreads) {
-                const int l = i / C, c = i - l * C;
-                u64 w[PW];
-#pragma unroll
-                for (int j = 0; j < PW; ++j) w[j] = p.state[(ROW_BM + c * PW + j) * np + env0 + l];
-                place_layer<D>(sm.stream, l * p.obs_bits + c * L::P, w);
-            }
-        }
-        bar_sync_named(BAR_WRITERS, kWriterThreads);
         for (int rs = 0; rs < ro.nsteps; ++rs) {
             const int r = rs & (kRing - 1);
             uint8_t* const obs = obs0 ? obs0 + (size_t)ring_slot * ro.slot_bytes : nullptr;
@@ -694,8 +694,8 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
             }
             if (rs + kRing < ro.nsteps) bar_arrive_named(BAR_EMPTY + r, 32 + kWriterThreads);     // this thread is done with the record
             bar_sync_named(BAR_WRITERS, kWriterThreads);
-            // (2) the tile's observation bytes
-            if (obs) write_observations(sm, p, obs, env0, nvalid, t, kWriterThreads);
+            // (2) the tile's observation bytes (the LAST step's are expanded by the whole CTA after the roles have met, see below)
+            if (obs && rs + 1 < ro.nsteps) write_observations(sm, p, obs, env0, nvalid, t, kWriterThreads);
             ring_slot = (ring_slot + 1 == ro.slots) ? 0 : ring_slot + 1;
         }
     } else {
@@ -749,6 +749,13 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         }
     }
     __syncthreads();
+    // ---- the last step's observation bytes, by every thread: the other roles have nothing left to do, and a single-step launch ends
+    //      when its expansion does
+    if (obs0) {
+        int last_slot = ro.first_slot + (ro.nsteps - 1) % ro.slots;
+        if (last_slot >= ro.slots) last_slot -= ro.slots;
+        write_observations(sm, p, obs0 + (size_t)last_slot * ro.slot_bytes, env0, nvalid, tid, kThreads);
+    }
     // ---- epilogue: the queues and their fill counters persist between launches
     if (q_in_smem) {
         const u64* sq = &sm.q[0][0][0];

@@ -20,14 +20,10 @@ variant() {   # name, extra flags; DQ_VARIANTS="w2g3 q8" restricts the build to 
     echo "built $OUT/libdq_$name.so"
 }
 variant w1g4     -DDQ_WRITERS=1 -DDQ_GENS=4
-variant w1g2     -DDQ_WRITERS=1 -DDQ_GENS=2
 variant w2g3     -DDQ_WRITERS=2 -DDQ_GENS=3
-variant w1g3pl   -DDQ_PHYS_LAST=1
 variant w1g3q8   -DDQ_QDEPTH=8
-variant w1g3mb5  -DDQ_MIN_BLOCKS=5
-variant d7w2g4   -DDQ_WRITERS_D7=2 -DDQ_GENS_D7=4
-variant d7w2g5   -DDQ_WRITERS_D7=2 -DDQ_GENS_D7=5
-variant d7w4g3   -DDQ_WRITERS_D7=4 -DDQ_GENS_D7=3
+variant d7w3g4   -DDQ_WRITERS_D7=3 -DDQ_GENS_D7=4
+variant d7w2g6   -DDQ_WRITERS_D7=2 -DDQ_GENS_D7=6
 if [ -n "$OLD_REV" ]; then      # same-box control: the env kernel of an earlier revision
     mkdir -p $OUT/old && git show $OLD_REV:$CS/dq_env.cu > $OUT/old/dq_env.cu && git show $OLD_REV:$CS/dq_lattice.cuh > $OUT/old/dq_lattice.cuh
     git show $OLD_REV:include/dq_decoding.h > $OUT/old/dq_decoding.h

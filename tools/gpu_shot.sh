@@ -22,7 +22,7 @@ run ab_new 60 python tools/prof_rollout.py
 done
 DQ_CALLS=6 DQ_ONLY_ROLLOUT=64 DQ_N=262144 run big 40 python tools/prof_rollout.py      # every SM fully loaded
 DQ_D=7 DQ_N=8192 run d7 40 python tools/prof_rollout.py
-for v in d7w2g4 d7w2g5 d7w4g3; do DQ_CALLS=12 DQ_ONLY_ROLLOUT=256 DQ_D=7 DQ_N=8192 DQ_DECODING_LIB=build/variants/libdq_$v.so run d7_$v 30 python tools/prof_rollout.py; done
+for v in d7w3g4 d7w2g6; do DQ_CALLS=12 DQ_ONLY_ROLLOUT=256 DQ_D=7 DQ_N=8192 DQ_DECODING_LIB=build/variants/libdq_$v.so run d7_$v 30 python tools/prof_rollout.py; done
 run hostprof 200 python tools/prof_host_path.py
 run bench 150 python bench.py --cpu-seconds 3 --no-dqn
 run bench20 100 python bench.py --cpu-seconds 1 --no-dqn --steps 20 --warmup 3

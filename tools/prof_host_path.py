@@ -43,6 +43,44 @@ def child():
                                                            L.dq_env_step_host_begin(h, hp(hb["actions"]), hp(hb["obs"]), hp(hb["reward"]), hp(hb["done"]), hp(hb["lifetime"]), hp(hb["legal"]), 1),
                                                            L.dq_env_step_host_end(h)))
     res["python_wrappers_step_us"] = timed(lambda i: (env.random_legal_actions_host(i), env.step_host_begin(), env.step_host_end()))
+    # the two-handle overlap pattern, with the time spent in each kind of call
+    half = n // 2
+    envs = [VecSurfaceCodeEnv(5, 0.007, 0.007, "DP", False, 5, None, n_envs=half, seed=4, env_id_base=k * half) for k in (0, 1)]
+    hbs = [e._host_buffers() for e in envs]
+    for e in envs:
+        e.reset_host()
+    acc = {"policy": 0.0, "begin": 0.0, "end": 0.0}
+
+    def begin(k, i, count):
+        t0 = time.perf_counter()
+        L.dq_policy_random_legal_host(envs[k]._h, hp(hbs[k]["legal"]), i, hp(hbs[k]["actions"]))
+        t1 = time.perf_counter()
+        rc = L.dq_env_step_host_begin(envs[k]._h, hp(hbs[k]["actions"]), hp(hbs[k]["obs"]), hp(hbs[k]["reward"]), hp(hbs[k]["done"]), hp(hbs[k]["lifetime"]), hp(hbs[k]["legal"]), 1)
+        assert rc == 0
+        t2 = time.perf_counter()
+        if count:
+            acc["policy"] += t1 - t0; acc["begin"] += t2 - t1
+
+    def end(k, count):
+        t0 = time.perf_counter()
+        assert L.dq_env_step_host_end(envs[k]._h) == 0
+        if count:
+            acc["end"] += time.perf_counter() - t0
+    for k in (0, 1):
+        begin(k, 0, False)
+    for i in range(4):
+        for k in (0, 1):
+            end(k, False); begin(k, 1 + i, False)
+    iters = 40
+    t0 = time.perf_counter()
+    for i in range(iters):
+        for k in (0, 1):
+            end(k, True); begin(k, 10 + i, True)
+    total = time.perf_counter() - t0
+    for k in (0, 1):
+        end(k, False)
+    res["two_handles_us_per_full_step"] = total / iters * 1e6
+    res["two_handles_breakdown_us"] = {k: v / iters * 1e6 for k, v in acc.items()}
     print("HOSTPROF " + json.dumps(res), flush=True)
 
 
