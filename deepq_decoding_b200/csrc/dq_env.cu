@@ -1209,39 +1209,7 @@ static void expand_packed_host(const u64* packed, size_t npad, int first, int la
     host_pool().parallel_for(nb, block);
 }
 
-#if defined(__x86_64__)
-__attribute__((target("avx2"))) static inline void mulhilo_x8(__m256i m, __m256i x, __m256i& hi, __m256i& lo) {      // 8 x (32 x 32 -> 64)
-    const __m256i pe = _mm256_mul_epu32(m, x);                                   // even lanes: 64-bit products
-    const __m256i po = _mm256_mul_epu32(m, _mm256_srli_epi64(x, 32));            // odd lanes
-    lo = _mm256_blend_epi32(pe, _mm256_slli_epi64(po, 32), 0xAA);
-    hi = _mm256_blend_epi32(_mm256_srli_epi64(pe, 32), po, 0xAA);
-}
-// word 0 of Philox4x32-10(counter = (id0 + lane, c1, 0, 1), key) for 8 consecutive stream ids: the policy draw of 8 lattices at once
-__attribute__((target("avx2"))) static inline void philox_word0_x8(uint32_t id0, uint32_t c1, uint32_t k0, uint32_t k1, uint32_t* out8) {
-    const __m256i M0 = _mm256_set1_epi32((int)0xD2511F53u), M1 = _mm256_set1_epi32((int)0xCD9E8D57u);
-    __m256i a = _mm256_add_epi32(_mm256_set1_epi32((int)id0), _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7));
-    __m256i b = _mm256_set1_epi32((int)c1), c = _mm256_setzero_si256(), d = _mm256_set1_epi32(1);
-    for (int r = 0; r < 10; ++r) {
-        __m256i h0, l0, h1, l1;
-        mulhilo_x8(M0, a, h0, l0);
-        mulhilo_x8(M1, c, h1, l1);
-        const __m256i n0 = _mm256_xor_si256(_mm256_xor_si256(h1, b), _mm256_set1_epi32((int)k0));
-        const __m256i n2 = _mm256_xor_si256(_mm256_xor_si256(h0, d), _mm256_set1_epi32((int)k1));
-        a = n0; b = l1; c = n2; d = l0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    _mm256_storeu_si256(reinterpret_cast<__m256i*>(out8), a);
-}
-#endif
-
-// The pick itself, compiled with the POPCNT instruction where the host has it (the generic build calls libgcc's table popcount:
-// ~10 of them per pick were the whole cost of the host policy).
-#if defined(__x86_64__)
-#define DQ_HOST_POPCNT __attribute__((target("popcnt")))
-#else
-#define DQ_HOST_POPCNT
-#endif
-static inline int generic_pick(const u64* m, int W, int A, u32 ux) {      // the same pick with the portable helpers
+static inline int generic_pick(const u64* m, int W, int A, u32 ux) {      // the pick with the portable helpers
     int cnt = 0;
     for (int w = 0; w < W; ++w) cnt += popc64(m[w]);
     int pick = (int)mulhi32(ux, (u32)cnt);
@@ -1252,28 +1220,50 @@ static inline int generic_pick(const u64* m, int W, int A, u32 ux) {      // the
     }
     return A - 1;
 }
-DQ_HOST_POPCNT static inline int host_select64(u64 x, int k) {      // position of the k-th set bit (k < popcount)
-    u32 w = (u32)x;
-    int base = 0;
-    const int c0 = __builtin_popcount(w);
-    if (k >= c0) { k -= c0; w = (u32)(x >> 32); base = 32; }
-    for (int sft = 16; sft >= 1; sft >>= 1) {
-        const int c = __builtin_popcount(w & ((1u << sft) - 1u));
-        if (k >= c) { k -= c; w >>= sft; base += sft; }
-    }
-    return base;
+#if defined(__x86_64__)
+// The same picks for `count` consecutive lattices with AVX2 + BMI2 + POPCNT: word 0 of Philox4x32-10(counter = (id, step, 0, 1)) for 8
+// stream ids at a time, POPCNT for the counts, PDEP + TZCNT for "the k-th set bit" (the portable build spends ~40 ns per lattice in
+// libgcc's table popcount and the branchy select; this one ~9 ns).
+#define DQ_X86_POLICY __attribute__((target("avx2,bmi2,popcnt")))
+DQ_X86_POLICY static inline __attribute__((always_inline)) void mulhilo_x8(__m256i m, __m256i x, __m256i& hi, __m256i& lo) {      // 8 x (32 x 32 -> 64)
+    const __m256i pe = _mm256_mul_epu32(m, x);                                   // even lanes: 64-bit products
+    const __m256i po = _mm256_mul_epu32(m, _mm256_srli_epi64(x, 32));            // odd lanes
+    lo = _mm256_blend_epi32(pe, _mm256_slli_epi64(po, 32), 0xAA);
+    hi = _mm256_blend_epi32(_mm256_srli_epi64(pe, 32), po, 0xAA);
 }
-DQ_HOST_POPCNT static inline int host_pick(const u64* m, int W, int A, u32 ux) {
-    int cnt = 0;
-    for (int w = 0; w < W; ++w) cnt += __builtin_popcountll(m[w]);
-    int pick = (int)(((u64)ux * (u32)cnt) >> 32);
-    for (int w = 0; w < W; ++w) {
-        const int c = __builtin_popcountll(m[w]);
-        if (pick < c) return w * 64 + host_select64(m[w], pick);
-        pick -= c;
+DQ_X86_POLICY static void policy_block_x86(const u64* legal, int W, int A, u32 id0, int count, u32 step, u32 key0, u32 key1, int32_t* actions) {
+    const __m256i M0 = _mm256_set1_epi32((int)0xD2511F53u), M1 = _mm256_set1_epi32((int)0xCD9E8D57u);
+    for (int base = 0; base < count; base += 8) {
+        __m256i a = _mm256_add_epi32(_mm256_set1_epi32((int)(id0 + (u32)base)), _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7));
+        __m256i b = _mm256_set1_epi32((int)step), c = _mm256_setzero_si256(), d = _mm256_set1_epi32(1);
+        u32 k0 = key0, k1 = key1;
+        for (int r = 0; r < 10; ++r) {
+            __m256i h0, l0, h1, l1;
+            mulhilo_x8(M0, a, h0, l0);
+            mulhilo_x8(M1, c, h1, l1);
+            const __m256i n0 = _mm256_xor_si256(_mm256_xor_si256(h1, b), _mm256_set1_epi32((int)k0));
+            const __m256i n2 = _mm256_xor_si256(_mm256_xor_si256(h0, d), _mm256_set1_epi32((int)k1));
+            a = n0; b = l1; c = n2; d = l0;
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        alignas(32) u32 u8[8];
+        _mm256_store_si256(reinterpret_cast<__m256i*>(u8), a);
+        const int m8 = count - base < 8 ? count - base : 8;
+        for (int k = 0; k < m8; ++k) {
+            const u64* m = legal + (size_t)(base + k) * W;
+            int cnt = 0;
+            for (int w = 0; w < W; ++w) cnt += (int)_mm_popcnt_u64(m[w]);
+            int pick = (int)(((u64)u8[k] * (u32)cnt) >> 32), act = A - 1;
+            for (int w = 0; w < W; ++w) {
+                const int cw = (int)_mm_popcnt_u64(m[w]);
+                if (pick < cw) { act = w * 64 + __builtin_ctzll(_pdep_u64(1ull << pick, m[w])); break; }
+                pick -= cw;
+            }
+            actions[base + k] = act;
+        }
     }
-    return A - 1;
 }
+#endif
 
 // Uniform pick over the sorted legal actions on the HOST (same draw as dq_policy_random_legal): for callers that drive the
 // *_host entry points and hold the legal masks in host memory.
@@ -1282,27 +1272,17 @@ extern "C" int dq_policy_random_legal_host(const dq_env* e, const uint64_t* h_le
     const EnvParams& p = e->p;
     const int per = 512, nb = (p.n + per - 1) / per;
 #if defined(__x86_64__)
-    static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("DQ_HOST_NO_AVX2");
-    static const bool have_popcnt = __builtin_cpu_supports("popcnt") && !getenv("DQ_HOST_NO_AVX2");
+    static const bool x86_fast = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("popcnt") && !getenv("DQ_HOST_NO_AVX2");
 #else
-    const bool avx2 = false, have_popcnt = false;
+    const bool x86_fast = false;
 #endif
     const std::function<void(int)> block = [&](int b) {
-        const int e1 = std::min(p.n, (b + 1) * per);
-        uint32_t u8[8];
-        for (int i = b * per; i < e1; ++i) {
-            u32 ux;
-            const int k = (i - b * per) & 7;
+        const int i0 = b * per, cnt = std::min(p.n, i0 + per) - i0;
 #if defined(__x86_64__)
-            if (avx2) {
-                if (k == 0) philox_word0_x8(p.env_id_base + (u32)i, step_index, p.k0, p.k1, u8);
-                ux = u8[k];
-            } else
+        if (x86_fast) { policy_block_x86(h_legal + (size_t)i0 * p.W, p.W, p.A, p.env_id_base + (u32)i0, cnt, step_index, p.k0, p.k1, h_actions + i0); return; }
 #endif
-            ux = philox4x32_10(p.env_id_base + (u32)i, step_index, 0u, 1u, p.k0, p.k1).x;
-            (void)k;
-            h_actions[i] = have_popcnt ? host_pick(h_legal + (size_t)i * p.W, p.W, p.A, ux) : generic_pick(h_legal + (size_t)i * p.W, p.W, p.A, ux);
-        }
+        for (int i = i0; i < i0 + cnt; ++i)
+            h_actions[i] = generic_pick(h_legal + (size_t)i * p.W, p.W, p.A, philox4x32_10(p.env_id_base + (u32)i, step_index, 0u, 1u, p.k0, p.k1).x);
     };
     host_pool().parallel_for(nb, block);
     return DQ_OK;

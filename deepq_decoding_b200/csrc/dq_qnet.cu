@@ -1393,12 +1393,12 @@ struct dq_qnet_tc {                     // bf16 buffers of the tensor-core path,
     __nv_bfloat16* act[kMaxConv + kMaxDense + 2];      // act[j] = bf16 output of layer j (not for the last one)
     __nv_bfloat16* wt[kMaxConv + kMaxDense + 2];
     int kpad[kMaxConv + kMaxDense + 2], npad[kMaxConv + kMaxDense + 2], bn[kMaxConv + kMaxDense + 2];
-    // DQ_QNET_FOLD_HEAD=1 (opt-in): Dense(num_actions) + dueling head folded into one affine map (dq_qnet_fold_head); the last
+    // Dense(num_actions) + dueling head folded into one affine map (dq_qnet_fold_head; DQ_QNET_FOLD_HEAD=0 turns it off); the last
     // tensor-core layer then multiplies with fold_wt / fold_b and writes Q itself
     float* fold_w; float* fold_b; __nv_bfloat16* fold_wt; int folded;
 };
 static bool tc_fold_enabled() {
-    static const bool on = [] { const char* e = getenv("DQ_QNET_FOLD_HEAD"); return e && e[0] == '1'; }();
+    static const bool on = [] { const char* e = getenv("DQ_QNET_FOLD_HEAD"); return !(e && e[0] == '0'); }();      // default on (measured: 0.127 -> 0.112 ms per 16 384 observations, same greedy agreement with fp32); =0 keeps the three layers apart
     return on;
 }
 static void tc_free(dq_qnet* h) {

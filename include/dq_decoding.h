@@ -210,8 +210,8 @@ int dq_qnet_prepare_tc(dq_qnet* net, const float* params, dq_stream stream);
 int dq_qnet_tc_activation(dq_qnet* net, int index, void** dev_ptr, int64_t* per_sample);   /* tests: bf16 activations */
 /* Inference only: Dense(num_actions), keras-rl's dueling Dense(num_actions + 1) and its 'avg' combine (SPTS:119-130,
  * enable_dueling_network=True) are all linear, so Q = h * w_out + b_out with w_out [K][num_actions] (K = units of the last
- * hidden dense layer) and b_out [num_actions], both device fp32.  With DQ_QNET_FOLD_HEAD=1 in the environment
- * dq_qnet_prepare_tc stages this map and dq_qnet_forward_tc ends in it (one launch instead of two). */
+ * hidden dense layer) and b_out [num_actions], both device fp32.  dq_qnet_prepare_tc stages this map and dq_qnet_forward_tc ends in it
+ * (one launch instead of three; DQ_QNET_FOLD_HEAD=0 in the environment keeps the layers apart). */
 int dq_qnet_fold_head(const dq_qnet* net, const float* params, float* w_out, float* b_out, dq_stream stream);
 /* Gradient of sum_b sum_a dq[b][a]*Q[b][a] for the batch of the last dq_qnet_forward call; grads is overwritten. */
 int dq_qnet_backward(dq_qnet* net, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
