@@ -52,9 +52,22 @@ RING = 16
 ROLL = 256         # env steps per rollout launch on the timed path
 METRIC = "env-steps/sec at d=5 depolarising p=0.007"
 UNIT = "env-steps/s"
+OBS_BYTES = 847               # C * (2d+1)^2 of the selected workload
 BYTES_PER_STEP = 996          # obs 847 + action 4 + reward 4 + done 1 + lifetime 4 + mask 8 + 2 x 64 state
 WORKLOAD = ("C3: d=5 DP p_phys=p_meas=0.007 volume_depth=5 use_Y=False, %d lattices/GPU, random-legal policy, "
             "referee = shipped nn_d5_DP_p5 tabulated" % N_PER_GPU)
+
+
+def bench_config(world):
+    """The `config` object of the JSON line: the same dict from both arms (the reference arm runs on this arm's config)."""
+    n = N_PER_GPU
+    return {"workload": WORKLOAD, "lattices_total": world * n, "lattices_per_gpu": n,
+            "l2": "GPU arm: each step writes its %.1f MB of observations into one of %d ring slots (%.0f MB > L2), so no step's writes are "
+                  "absorbed by the previous step's lines" % (n * OBS_BYTES / 1e6, RING, RING * n * OBS_BYTES / 1e6),
+            "launch": "GPU arm: the K timed steps run as dq_env_rollout_random launches of up to %d steps of every lattice (random-legal pick + "
+                      "env step per step; bit-identical to single-step launches), queued behind a 2 ms device-side delay so the event pair "
+                      "brackets device time; the launches actually made are listed in launch_detail" % ROLL,
+            "parallelism": "lattices sharded by rank, no data-path collective (the gradient exchange of training is measured in dqn_dp)"}
 
 
 def measured_peak():
@@ -175,8 +188,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU oracle port of the reference env on the host cores; each step is "
-                       "one vectorised step of 16384 lattices; the run is time-bounded, not step-bounded"},
+            "config": bench_config(args.gpus),
+            "reference_note": "CPU oracle port of the reference env on the host cores (all of them, whatever --gpus says); each step is "
+                              "one vectorised step of %d lattices; the run is time-bounded, not step-bounded" % N_PER_GPU,
             "cpu_baseline": dict(cb, value=value),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -223,7 +237,10 @@ def e2e_legs(L, _lib, torch, np, dist, dev, world, rank, n, K):
     memory.  The policy is the same random-legal pick as on the device path, computed on the host from the legal masks that came
     back (dq_policy_random_legal_host), so the workload mix equals the resident loop's and the CPU arm's."""
     from deepq_decoding_b200.envs import VecSurfaceCodeEnv
-    ke = min(K, 64)
+    # Host-side loops are exposed to whatever else the box's cores are doing: each leg times BLOCKS consecutive blocks of `ke` steps
+    # (barrier before each, max over ranks per block) and reports the MEDIAN block; every block's rate is listed.
+    ke = max(20, min(K, 64))
+    BLOCKS = 5
     half = n // 2
     envs = [VecSurfaceCodeEnv(D, P, P, MODEL, USE_Y, VD, None, n_envs=cnt, seed=SEED + 3, env_id_base=rank * n + base, device=dev)
             for base, cnt in ((0, half), (half, n - half))]
@@ -239,27 +256,36 @@ def e2e_legs(L, _lib, torch, np, dist, dev, world, rank, n, K):
         if world > 1:
             dist.barrier()
 
-    def rate(seconds):
-        t = torch.tensor([seconds], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return world * n * ke / float(t.item())
+    def timed_blocks(step, first):
+        """step(i) = one full step of every lattice of this rank, results landed in host memory"""
+        rates, i = [], first
+        for _ in range(BLOCKS):
+            sync_all()
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                step(i)
+                i += 1
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rates.append(world * n * ke / float(t.item()))
+        return sorted(rates)[BLOCKS // 2], rates
 
+    timing = "median of %d consecutive blocks of %d steps (wall clock around each block, max over ranks); block_values lists them all" % (BLOCKS, ke)
     # (a) the public call on one handle of n lattices: random-legal pick on the host, dq_env_step_host, every output landed -- per step
     whole.reset_host()
-    for i in range(4):
+
+    def one_handle_step(i):
         whole.random_legal_actions_host(i); whole.step_host_begin(); whole.step_host_end()
-    sync_all()
-    t0 = time.perf_counter()
-    for i in range(ke):
-        whole.random_legal_actions_host(4 + i); whole.step_host_begin(); whole.step_host_end()
-    dt = time.perf_counter() - t0
-    e2e = {"value": rate(dt), "unit": UNIT, "h2d_bytes_per_step": n * 4,
-           "d2h_bytes_per_step": n * small + (packed_bytes if host_expand else n * obs_bytes), "steps": ke,
-           "host_bytes_delivered_per_step": n * (obs_bytes + small),
+    for i in range(6):
+        one_handle_step(i)
+    val, rates = timed_blocks(one_handle_step, 6)
+    e2e = {"value": val, "unit": UNIT, "h2d_bytes_per_step": n * 4,
+           "d2h_bytes_per_step": n * small + (packed_bytes if host_expand else n * obs_bytes), "steps": ke * BLOCKS, "timing": timing,
+           "block_values": rates, "host_bytes_delivered_per_step": n * (obs_bytes + small),
            "api": "VecSurfaceCodeEnv.random_legal_actions_host + step_host_begin / step_host_end (dq_policy_random_legal_host, dq_env_step_host) on one "
                   "handle of %d lattices: uint8 observations [N,C,H,H], reward, done, lifetime and legal masks land in pinned host memory every step" % n,
-           "host_expand": host_expand,
+           "host_expand": host_expand, "host_threads": os.environ.get("DQ_HOST_THREADS", "default (usable CPUs - 1)"),
            "how": "the bitmap rows cross PCIe bit-packed and the library's host threads expand them into the byte observations"
                   if host_expand else "the kernel writes bytes; all of them are copied back",
            "policy": "uniform random-legal, computed on the host from the returned legal masks (same picks as the device policy)"}
@@ -276,18 +302,17 @@ def e2e_legs(L, _lib, torch, np, dist, dev, world, rank, n, K):
             step[k] += 1
         for k in (0, 1):
             begin(k)
-        for _ in range(8):
+
+        def two_handle_step(i):
             for k in (0, 1):
                 envs[k].step_host_end(); begin(k)
-        sync_all()
-        t0 = time.perf_counter()
-        for _ in range(ke):
-            for k in (0, 1):
-                envs[k].step_host_end(); begin(k)
-        dt2 = time.perf_counter() - t0
+        for i in range(6):
+            two_handle_step(i)
+        val2, rates2 = timed_blocks(two_handle_step, 0)
         for k in (0, 1):
             envs[k].step_host_end()
-        e2e["two_handles"] = {"value": rate(dt2), "unit": UNIT, "api": "the same calls on two handles of %d lattices, split begin / end, driven alternately" % half}
+        e2e["two_handles"] = {"value": val2, "unit": UNIT, "block_values": rates2,
+                              "api": "the same calls on two handles of %d lattices, split begin / end, driven alternately" % half}
     except Exception as ex:      # noqa: BLE001
         e2e["two_handles"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
     # (c) observations returned PACKED (one bit per cell, the rows the Q-network consumes): nothing to expand anywhere
@@ -297,16 +322,13 @@ def e2e_legs(L, _lib, torch, np, dist, dev, world, rank, n, K):
         hp = lambda t: C.c_void_p(t.data_ptr())
 
         def packed_step(i):
-            whole.random_legal_actions_host(100 + i)
+            whole.random_legal_actions_host(1000 + i)
             _lib.check(L.dq_env_step_host_packed(whole._h, hp(hb["actions"]), hp(pk), hp(hb["reward"]), hp(hb["done"]), hp(hb["lifetime"]), hp(hb["legal"]), 1))
-        for i in range(3):
+        for i in range(4):
             packed_step(i)
-        sync_all()
-        t0 = time.perf_counter()
-        for i in range(ke):
-            packed_step(3 + i)
-        e2e_packed = {"value": rate(time.perf_counter() - t0), "unit": UNIT, "h2d_bytes_per_step": n * 4,
-                      "d2h_bytes_per_step": packed_bytes + n * small, "steps": ke,
+        val3, rates3 = timed_blocks(packed_step, 4)
+        e2e_packed = {"value": val3, "unit": UNIT, "h2d_bytes_per_step": n * 4,
+                      "d2h_bytes_per_step": packed_bytes + n * small, "steps": ke * BLOCKS, "block_values": rates3,
                       "api": "dq_env_step_host_packed (observations as bit-packed rows uint64 [C*PW][stride]; envs.unpack_observations expands "
                              "them when a caller needs bytes), same policy"}
     except Exception as ex:      # noqa: BLE001 -- reported, not fatal (no collective between here and the next barrier on the success path either)
@@ -727,14 +749,9 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "lattices_total": world * n,
-                           "l2": "each step writes its %.1f MB of observations into one of %d ring slots (%.0f MB > L2), "
-                                 "so no step's writes are absorbed by the previous step's lines" % (
-                                     ring[0].numel() / 1e6, RING, ring.numel() / 1e6),
-                           "launch": "the %d timed steps ran as %d dq_env_rollout_random launch(es): %d of %d steps%s (random-legal pick + env step of every "
-                                     "lattice per step; bit-identical to single-step launches), queued behind a 2 ms device-side delay so the event pair "
-                                     "brackets device time" % (K, timed_launches, full, ROLL, (" and one of %d" % rest) if rest else ""),
-                           "parallelism": "lattices sharded by rank, no data-path collective (the gradient exchange of training is measured in dqn_dp)"},
+                "config": bench_config(world),
+                "launch_detail": "the %d timed steps ran as %d dq_env_rollout_random launch(es): %d of %d steps%s" % (
+                    K, timed_launches, full, ROLL, (" and one of %d" % rest) if rest else ""),
                 "clocks": clocks, "e2e": e2e, "e2e_packed": e2e_packed,
                 "gpu_launches": timed_launches, "single_step_launches": single,
                 "roofline": roof, "roofline_scaling": scaling, "other_workloads": others, "cpu_baseline": cb, "dqn_dp": dqn_dp, "dqn": dqn,
@@ -748,7 +765,9 @@ def run_b200(args):
 
 def select_workload(name):
     global D, VD, P, MODEL, N_PER_GPU, BYTES_PER_STEP, WORKLOAD, METRIC
+    global OBS_BYTES
     D, VD, P, MODEL, N_PER_GPU, BYTES_PER_STEP = WORKLOADS[name]
+    OBS_BYTES = (VD + (2 if MODEL == "DP" else 1)) * (2 * D + 1) ** 2
     if name != "c3":
         WORKLOAD = "%s: d=%d %s p_phys=p_meas=%g volume_depth=%d use_Y=False, %d lattices/GPU, random-legal policy, referee = %s" % (
             name.upper(), D, MODEL, P, VD, N_PER_GPU, "shipped nn_d5_X_p5 tabulated" if D == 5 else "minimum-weight table")

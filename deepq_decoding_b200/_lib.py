@@ -45,6 +45,7 @@ _SIGNATURES = {
     "dq_policy_random_legal_host": (_i, [_vp, _vp, _u32, _vp]),
     "dq_env_reset_host_packed": (_i, [_vp, _vp, _vp]),
     "dq_env_step_host_packed": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "dq_unpack_observations_host": (_i, [_vp, _i64, _i64, _i, _i, _vp]),
     "dq_env_get_state": (_i, [_vp, _vp, _vp]),
     "dq_env_set_state": (_i, [_vp, _vp, _vp]),
     "dq_policy_random_legal": (_i, [_vp, _vp, _u32, _vp, _vp]),
@@ -82,12 +83,27 @@ def exported_symbols():
     return sorted(_SIGNATURES)
 
 
+def _share_host_cores():
+    """Several ranks on one box (torchrun sets LOCAL_WORLD_SIZE): each gets its share of the CPUs for the library's host threads
+    (DQ_HOST_THREADS, read once when the pool starts) instead of every rank starting one thread per core."""
+    if "DQ_HOST_THREADS" in os.environ:
+        return
+    try:
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+    except ValueError:
+        local_world = 1
+    if local_world > 1:
+        cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        os.environ["DQ_HOST_THREADS"] = str(max(1, cpus // local_world))
+
+
 def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise DQError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "or `make -C deepq_decoding_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+        _share_host_cores()
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)

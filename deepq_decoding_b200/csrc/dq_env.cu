@@ -29,6 +29,9 @@
 // Replaces (reference paths relative to example_notebooks/): Environments.py:99-115 (reset),
 // :118-204 (step), :206-235, :238-314 and the Function_Library.py helpers they call.
 #include <cuda_runtime.h>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 #include <stdint.h>
 #include <string.h>
 #include <math.h>
@@ -1082,15 +1085,28 @@ static bool host_expand_enabled() {
 }
 
 namespace {
-struct HostPool {                 // persistent workers: blocks of a job are claimed from an atomic counter
+// Persistent host workers for the *_host entry points.  A job is `nb` blocks; every participant (the workers and the calling thread)
+// owns a contiguous range of them -- the SAME range on every call of the same shape, so the slice of the caller's buffer a thread
+// writes stays in that core's cache from step to step -- and steals from the other ranges once its own is done.  A range is one
+// 64-bit word [generation : 24 | end : 20 | next : 20] claimed by compare-and-swap: a worker that wakes up late holds a stale
+// generation and can never take a block of the job that followed.  The caller waits for BLOCKS (a counter), not for threads: a worker
+// that is slow to wake costs nothing.
+struct HostPool {
+    static constexpr int kMaxParts = 64;
+    struct alignas(64) Range { std::atomic<uint64_t> w{0}; };
     std::vector<std::thread> th;
     std::mutex m, run_m;
     std::condition_variable cv_job;
     const std::function<void(int)>* job = nullptr;
-    int nblocks = 0;
-    std::atomic<int> generation{0}, next{0}, active{0};
-    explicit HostPool(int n) {
-        for (int i = 0; i < n; ++i) th.emplace_back([this] { run(); });
+    Range range[kMaxParts];
+    int parts = 1;
+    std::atomic<uint32_t> generation{0};
+    alignas(64) std::atomic<int> done{0};
+    alignas(64) std::atomic<int> sleepers{0};
+    explicit HostPool(int workers) {
+        workers = std::max(0, std::min(workers, kMaxParts - 1));
+        parts = workers + 1;
+        for (int i = 0; i < workers; ++i) th.emplace_back([this, i] { run(i + 1); });
         for (auto& t : th) t.detach();            // the pool lives as long as the process
     }
     static void relax() {
@@ -1098,39 +1114,79 @@ struct HostPool {                 // persistent workers: blocks of a job are cla
         _mm_pause();
 #endif
     }
-    void run() {
-        int seen = 0;
+    static uint64_t pack(uint32_t gen, int end, int next) { return ((uint64_t)(gen & 0xFFFFFFu) << 40) | ((uint64_t)end << 20) | (uint64_t)next; }
+    // claim one block of generation `gen` from range r; -1: none left there (or the range belongs to a later job)
+    int claim(int r, uint32_t gen) {
+        uint64_t cur = range[r].w.load(std::memory_order_acquire);
+        for (;;) {
+            if ((uint32_t)(cur >> 40) != (gen & 0xFFFFFFu)) return -1;
+            const int end = (int)((cur >> 20) & 0xFFFFFu), next = (int)(cur & 0xFFFFFu);
+            if (next >= end) return -1;
+            if (range[r].w.compare_exchange_weak(cur, cur + 1, std::memory_order_acq_rel, std::memory_order_acquire)) return next;
+        }
+    }
+    void work(int self, uint32_t gen, const std::function<void(int)>& f) {
+        for (int k = 0; k < parts; ++k) {         // own range first, then the neighbours'
+            const int r = (self + k) % parts;
+            for (int b; (b = claim(r, gen)) >= 0;) {
+                f(b);
+                done.fetch_add(1, std::memory_order_acq_rel);
+            }
+        }
+    }
+    void run(int self) {
+        uint32_t seen = 0;
         for (;;) {
             // a step arrives every ~100 us while a host-buffer loop runs: spin briefly for the next job, then sleep
             int spins = 0;
             while (generation.load(std::memory_order_acquire) == seen) {
-                if (++spins < 20000) { relax(); continue; }
+                if (++spins < 4000) { relax(); continue; }
                 std::unique_lock<std::mutex> lk(m);
+                sleepers.fetch_add(1, std::memory_order_acq_rel);
                 cv_job.wait(lk, [&] { return generation.load(std::memory_order_acquire) != seen; });
+                sleepers.fetch_sub(1, std::memory_order_acq_rel);
             }
             seen = generation.load(std::memory_order_acquire);
-            const std::function<void(int)>* f = job;
-            const int nb = nblocks;
-            for (int b; (b = next.fetch_add(1)) < nb;) (*f)(b);
-            active.fetch_sub(1, std::memory_order_acq_rel);
+            const std::function<void(int)>* f = job;          // published before the generation it belongs to (or a later one: then no claim succeeds)
+            work(self, seen, *f);
         }
     }
     void parallel_for(int nb, const std::function<void(int)>& f) {      // the caller works too; one job at a time
+        if (nb <= 0) return;
+        if (nb == 1 || parts == 1 || nb >= (1 << 20)) { for (int b = 0; b < nb; ++b) f(b); return; }
         std::lock_guard<std::mutex> serial(run_m);
-        job = &f; nblocks = nb; next.store(0); active.store((int)th.size());
-        {
-            std::lock_guard<std::mutex> lk(m);
-            generation.fetch_add(1, std::memory_order_acq_rel);
+        const uint32_t gen = generation.load(std::memory_order_relaxed) + 1;
+        job = &f;
+        done.store(0, std::memory_order_relaxed);
+        for (int r = 0; r < parts; ++r) {
+            const int b0 = (int)((long long)nb * r / parts), b1 = (int)((long long)nb * (r + 1) / parts);
+            range[r].w.store(pack(gen, b1, b0), std::memory_order_release);
         }
-        cv_job.notify_all();
-        for (int b; (b = next.fetch_add(1)) < nb;) f(b);
-        while (active.load(std::memory_order_acquire) != 0) relax();
+        generation.store(gen, std::memory_order_release);
+        if (sleepers.load(std::memory_order_acquire) > 0) {
+            { std::lock_guard<std::mutex> lk(m); }
+            cv_job.notify_all();
+        }
+        work(0, gen, f);
+        while (done.load(std::memory_order_acquire) != nb) relax();
     }
 };
 
+static int usable_cpus() {
+#if defined(__linux__)
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) { const int c = CPU_COUNT(&set); if (c > 0) return c; }
+#endif
+    return std::max(1, (int)std::thread::hardware_concurrency());
+}
+
+// Threads that work on a host-side job, the caller included.  DQ_HOST_THREADS sets it (the Python binding derives it from
+// LOCAL_WORLD_SIZE so that the ranks of one box share the cores); default: the CPUs this process may run on, minus one that is left
+// to the rest of the process (interpreter threads, the driver's own) when there are eight or more.
 HostPool& host_pool() {
     static HostPool* pool = [] {
-        int n = (int)std::thread::hardware_concurrency();
+        int n = usable_cpus();
+        if (n >= 8) n -= 1;
         if (const char* v = getenv("DQ_HOST_THREADS")) n = atoi(v);
         return new HostPool(std::max(0, std::min(n, 32) - 1));
     }();
@@ -1178,19 +1234,43 @@ __attribute__((target("avx2"))) static void expand_lattices_avx2(const u64* pack
 }
 #endif
 
+#if defined(__x86_64__)
+// AVX-512BW: a mask register IS the bit row -- 64 bits -> 64 bytes of 0/1 in one instruction; the layer's last word leaves through a
+// byte-masked store (nothing is written past the layer).  A quarter of the AVX2 form's instructions; either way the expansion runs at
+// the cores' store bandwidth (measured: building the block's bit stream first and storing whole aligned lines, or non-temporal
+// stores, are no faster than this).
+__attribute__((target("avx512f,avx512bw"))) static void expand_lattices_avx512(const u64* packed, size_t npad, int e0, int e1, int C, int PW, int P, uint8_t* obs) {
+    const __m512i one = _mm512_set1_epi8(1);
+    const int tail = P - 64 * (PW - 1);                                   // cells in the layer's last word, 1..64
+    const __mmask64 tmask = tail >= 64 ? ~(__mmask64)0 : (((__mmask64)1 << tail) - 1);
+    for (int e = e0; e < e1; ++e) {
+        uint8_t* out = obs + (size_t)e * C * P;
+        const u64* col = packed + e;
+        for (int c = 0; c < C; ++c, out += P) {
+            for (int w = 0; w + 1 < PW; ++w)
+                _mm512_storeu_si512(out + 64 * w, _mm512_maskz_mov_epi8((__mmask64)col[(size_t)(c * PW + w) * npad], one));
+            const u64 last = col[(size_t)(c * PW + PW - 1) * npad];
+            _mm512_mask_storeu_epi8(out + 64 * (PW - 1), tmask, _mm512_maskz_mov_epi8((__mmask64)last, one));
+        }
+    }
+}
+#endif
+
 // packed rows [C*PW][npad] (bit i of layer c of lattice e = bit i%64 of row c*PW + i/64, column e) -> obs [n][C][P] bytes of 0/1,
 // for the lattices [first, last)
 static void expand_packed_host(const u64* packed, size_t npad, int first, int last, int C, int PW, int P, uint8_t* obs) {
     const u64* lut = byte_lut();
-    const int per = 128, nb = (last - first + per - 1) / per;
+    const int per = 64, nb = (last - first + per - 1) / per;
 #if defined(__x86_64__)
     static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("DQ_HOST_NO_AVX2");
+    static const bool avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && !getenv("DQ_HOST_NO_AVX512") && !getenv("DQ_HOST_NO_AVX2");
 #else
     const bool avx2 = false;
 #endif
     const std::function<void(int)> block = [&](int b) {
         const int e0 = first + b * per, e1 = std::min(last, e0 + per);
 #if defined(__x86_64__)
+        if (avx512) { expand_lattices_avx512(packed, npad, e0, e1, C, PW, P, obs); return; }
         if (avx2 && P >= 32) { expand_lattices_avx2(packed, npad, e0, e1, C, PW, P, obs); return; }
 #endif
         for (int e = e0; e < e1; ++e) {
@@ -1285,6 +1365,16 @@ extern "C" int dq_policy_random_legal_host(const dq_env* e, const uint64_t* h_le
             h_actions[i] = generic_pick(h_legal + (size_t)i * p.W, p.W, p.A, philox4x32_10(p.env_id_base + (u32)i, step_index, 0u, 1u, p.k0, p.k1).x);
     };
     host_pool().parallel_for(nb, block);
+    return DQ_OK;
+}
+
+// Host-side expansion on its own: the bit-packed rows a *_host_packed call returned -> byte observations [n][C][H][H] of 0/1
+// (what Environments.py hands to the agent).  Same code, same host threads, as the expansion inside dq_env_step_host.
+extern "C" int dq_unpack_observations_host(const uint64_t* h_packed, int64_t stride, int64_t n, int d, int channels, uint8_t* h_obs) {
+    if (!h_packed || !h_obs) return fail(DQ_EINVAL, "NULL argument");
+    if (d < 3 || d > 7 || !(d & 1) || channels < 1 || n < 0 || stride < n) return fail(DQ_EINVAL, "need odd d in [3, 7], channels >= 1 and stride >= n >= 0");
+    const int side = 2 * d + 1, P = side * side;
+    expand_packed_host(h_packed, (size_t)stride, 0, (int)n, channels, (P + 63) / 64, P, h_obs);
     return DQ_OK;
 }
 

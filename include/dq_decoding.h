@@ -130,8 +130,8 @@ int dq_env_step_host(dq_env* env, const int32_t* h_actions, uint8_t* h_obs, floa
  * and finishes the observations.  One call may be in flight per handle; two handles driven begin(A) begin(B) end(A) begin(A) end(B) ...
  * overlap one handle's kernel and PCIe traffic with the other's host-side work.
  * What crosses PCIe for h_obs are the bit-packed bitmap rows (7.5x fewer bytes at d = 5); host threads of the library expand them
- * into the caller's byte buffer in _end, range by range while the later ranges are still in flight (DQ_HOST_THREADS caps the
- * threads; DQ_HOST_EXPAND=0 makes the kernel write bytes and copies all of them back instead). */
+ * into the caller's byte buffer in _end, range by range while the later ranges are still in flight (DQ_HOST_THREADS = threads per
+ * process, default: the CPUs the process may run on, less one; the Python binding divides them by LOCAL_WORLD_SIZE; DQ_HOST_EXPAND=0 makes the kernel write bytes and copies all of them back instead). */
 int dq_env_step_host_begin(dq_env* env, const int32_t* h_actions, uint8_t* h_obs, float* h_reward, uint8_t* h_done,
                            int32_t* h_lifetime, uint64_t* h_legal_mask, int auto_reset);
 int dq_env_step_host_end(dq_env* env);
@@ -145,6 +145,10 @@ int dq_policy_random_legal_host(const dq_env* env, const uint64_t* h_legal_mask,
 int dq_env_reset_host_packed(dq_env* env, uint64_t* h_packed, uint64_t* h_legal_mask);
 int dq_env_step_host_packed(dq_env* env, const int32_t* h_actions, uint64_t* h_packed, float* h_reward, uint8_t* h_done,
                             int32_t* h_lifetime, uint64_t* h_legal_mask, int auto_reset);
+/* The expansion on its own, with the library's host threads: packed rows as returned above (stride = STATE_STRIDE) -> uint8
+ * h_obs[n][channels][2d+1][2d+1] of 0/1, the board_state of EN/Environments.py:204 for every lattice (padding_syndrome /
+ * padding_actions layout, :273-314). */
+int dq_unpack_observations_host(const uint64_t* h_packed, int64_t stride, int64_t n, int d, int channels, uint8_t* h_obs);
 
 /* Packed per-lattice state, uint64 [STATE_WORDS][STATE_STRIDE] on the device (layout in
  * DESIGN.md section 2): what env.hidden_state / completed_actions / lifetime / done hold in the

@@ -51,3 +51,41 @@ def test_argument_validation_precedes_device_use():
     assert L.dq_env_create(C.byref(h), 5, 1, 0, 0, 0.01, 0.01, 8, 0, 0, 0) == _lib.EINVAL
     assert L.dq_env_create(C.byref(h), 5, 1, 0, 5, 0.01, 0.01, 0, 0, 0, 0) == _lib.EINVAL
     assert L.dq_env_step(None, None, None, None, None, None, None, 1, None) == _lib.EINVAL
+
+
+_UNPACK_CHILD = r"""
+import ctypes as C, sys
+import numpy as np
+from deepq_decoding_b200 import _lib
+from deepq_decoding_b200.envs import unpack_observations
+L = _lib.lib()
+rng = np.random.default_rng(5)
+vp = lambda a: C.c_void_p(a.ctypes.data)
+for d, ch, n, stride in ((3, 4, 1, 32), (5, 7, 1000, 1024), (5, 6, 4097, 4128), (7, 9, 333, 352)):
+    side = 2 * d + 1
+    P, PW = side * side, (side * side + 63) // 64
+    rows = rng.integers(0, 2 ** 63, size=(ch * PW, stride), dtype=np.int64).view(np.uint64)
+    rows[PW - 1::PW] &= np.uint64((1 << (P - 64 * (PW - 1))) - 1)            # the kernel keeps bits >= P of a bitmap zero
+    obs = np.full((n + 1, ch, side, side), 7, dtype=np.uint8)                  # one lattice of slack: nothing may be written past n
+    assert L.dq_unpack_observations_host(vp(rows), stride, n, d, ch, vp(obs)) == 0
+    assert np.array_equal(obs[:n], unpack_observations(rows, n, d, ch)), (d, ch, n)
+    assert (obs[n] == 7).all(), "wrote past the last lattice"
+assert L.dq_unpack_observations_host(None, 1, 1, 5, 7, None) == _lib.EINVAL
+assert L.dq_unpack_observations_host(vp(rows), 4, 8, 5, 7, vp(obs)) == _lib.EINVAL      # stride < n
+print("ok")
+"""
+
+
+@pytest.mark.parametrize("isa", ["default", "no_avx512", "portable"])
+def test_host_unpack_matches_the_numpy_helper(isa):
+    """dq_unpack_observations_host (the expansion inside dq_env_step_host, on its own) against envs.unpack_observations, for each
+    instruction-set path of the library (chosen once per process, hence the child) and with several host threads."""
+    import subprocess
+    import sys
+    env = dict(os.environ, PYTHONPATH=ROOT, DQ_HOST_THREADS="4")
+    if isa == "no_avx512":
+        env["DQ_HOST_NO_AVX512"] = "1"
+    if isa == "portable":
+        env["DQ_HOST_NO_AVX2"] = "1"
+    r = subprocess.run([sys.executable, "-c", _UNPACK_CHILD], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
