@@ -726,6 +726,33 @@ def run_b200(args):
             if rring.filled >= 1:
                 agent.train_on_ring(rring, i)
         t_train = timed(train_iter, 40)
+        # the update alone (replay sample + 3 forwards + backward + Adam, batch 4096), in the three precision settings
+        t_upd32 = timed(lambda i: agent.train_on_ring(rring, i), 30)
+        upd = {"fp32_ms": t_upd32 * 1e3}
+        try:
+            agent_tc = A.DQNAgent(model=spec, nb_actions=env.num_actions, memory=A.SequentialMemory(limit=64 * n), nb_steps_warmup=0,
+                                  target_model_update=10 ** 9, policy=A.EpsGreedyQPolicy(eps=0.1), test_policy=A.GreedyQPolicy(masked_greedy=True),
+                                  enable_dueling_network=True, batch_size=4096, seed=SEED, device=dev, act_precision="bf16",
+                                  target_precision="bf16", train_precision="fp32")
+            agent_tc.compile(A.Adam(lr=1e-5), max_envs=n)
+            upd["bf16_targets_fp32_gradients_ms"] = timed(lambda i: agent_tc.train_on_ring(rring, i), 30) * 1e3
+            agent_tc.train_precision = "bf16"
+            upd["bf16_ms"] = timed(lambda i: agent_tc.train_on_ring(rring, i), 30) * 1e3
+            agent_tc.act_precision = "bf16"
+
+            def train_iter_tc(i):
+                rring.push_obs(rows_view)
+                a = agent_tc._act(env, rows_ptr.value, i, 0.1, True)
+                _lib.check(L.dq_env_step(h, vp(a), None, p_rew, p_done, p_life, p_legal, 1, cur()))
+                rring.push_outcome(a, env.reward, env.done)
+                agent_tc.train_on_ring(rring, i)
+            t_train_tc = timed(train_iter_tc, 40)
+            upd["train_bf16_env_steps_per_s"] = n / t_train_tc
+            upd["train_bf16_ms_per_iteration"] = t_train_tc * 1e3
+            upd["flops_per_update"] = 5 * 4096 * agent.model.flops_per_sample        # 3 forwards + backward (2 forward-equivalents)
+            upd["bf16_tflops"] = upd["flops_per_update"] / (upd["bf16_ms"] * 1e-3) / 1e12
+        except Exception as ex:      # noqa: BLE001 -- reported in the line
+            upd["error"] = "%s: %s" % (type(ex).__name__, str(ex)[:300])
         flops = agent.model.flops_per_sample
         tf_peak = 1393.5
         try:
@@ -734,14 +761,14 @@ def run_b200(args):
             pass
         dqn = {"act_env_steps_per_s": n / t_act, "act_ms_per_iteration": t_act * 1e3,
                "train_env_steps_per_s": n / t_train, "train_ms_per_iteration": t_train * 1e3,
-               "train_batch": 4096, "updates_per_iteration": 1,
+               "train_batch": 4096, "updates_per_iteration": 1, "update_ms": upd,
                "act_fp32_env_steps_per_s": n / t_act32,
                "policy_kernel_plus_env_step_external_actions_us": t_env * 1e6,
                "qnet_forward_fp32_ms": t_fwd * 1e3, "qnet_forward_fp32_tflops": flops * n / t_fwd / 1e12,
                "qnet_forward_bf16_ms": t_fwd_tc * 1e3, "qnet_forward_bf16_tflops": flops * n / t_fwd_tc / 1e12,
                "qnet_frac_of_bf16_sustained_peak": flops * n / t_fwd_tc / 1e12 / tf_peak,
                "cpu_serial_loop": cpu_serial_dqn_loop(min(6.0, max(0.5, args.cpu_seconds / 2))),
-               "qnet_precision": "acting: bf16 tcgen05 (fp32 accumulate in TMEM); updates: fp32 SIMT",
+               "qnet_precision": "acting: bf16 tcgen05 (fp32 accumulate in TMEM); train_*: fp32 SIMT updates (Keras arithmetic); update_ms.bf16_ms / train_bf16_*: tcgen05 forward and backward with fp32 master weights (DQNAgent(train_precision='bf16'))",
                "qnet_flops_per_sample": flops, "policy": "eps-greedy 0.1 over legal actions, masked greedy"}
 
     if rank == 0:

@@ -60,6 +60,8 @@ _SIGNATURES = {
     "dq_qnet_forward": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _i, _u64, _vp]),
     "dq_qnet_forward_tc": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "dq_qnet_prepare_tc": (_i, [_vp, _vp, _vp]),
+    "dq_qnet_forward_tc_train": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _u64, _vp]),
+    "dq_qnet_backward_tc": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "dq_qnet_fold_head": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "dq_qnet_tc_activation": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i64)]),
     "dq_qnet_backward": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),

@@ -166,7 +166,7 @@ class DQNAgent:
                  test_policy=None, gamma=0.99, enable_dueling_network=False, enable_double_dqn=True, batch_size=32,
                  train_interval=1, memory_interval=1, delta_clip=np.inf, dueling_type="avg", updates_per_step=1,
                  seed=0, device="cuda:0", flush_interval=64, process_group=None, act_precision="fp32", target_precision="fp32",
-                 collective="fused"):
+                 collective="fused", train_precision="fp32"):
         if not enable_double_dqn:
             raise NotImplementedError("the reference always runs double DQN (keras-rl default)")
         if dueling_type != "avg" or delta_clip != np.inf or memory_interval != 1:
@@ -184,8 +184,11 @@ class DQNAgent:
             raise ValueError("collective must be 'fused' (one peer-memory all-reduce+Adam kernel) or 'nccl' (all_reduce, then Adam)")
         self.collective = collective
         self.comm = None
-        self.act_precision = act_precision          # "fp32" (SIMT) or "bf16" (tcgen05 tensor cores) for action selection; updates are always fp32
+        self.act_precision = act_precision          # "fp32" (SIMT) or "bf16" (tcgen05 tensor cores) for action selection
         self.target_precision = target_precision    # precision of the two no-grad forwards on s' inside an update (Q_online, Q_target)
+        if train_precision not in ("fp32", "bf16"):
+            raise ValueError("train_precision must be 'fp32' (Keras arithmetic) or 'bf16' (tcgen05 forward and backward, fp32 master weights)")
+        self.train_precision = train_precision      # precision of the forward / backward pass of an update; Adam and the weights stay fp32
         self.optimizer = None
         self.model = None                           # QNetwork, built in compile()
         self.step, self.updates = 0, 0
@@ -303,15 +306,16 @@ class DQNAgent:
             m.forward_packed(s1.data_ptr(), B, B, out=self._qt[:B], params=self.target_params)
         _lib.check(self.L.dq_dqn_targets(p(self._qo), p(self._qt), p(reward), p(terminal), self.gamma, B, A, p(self._y), st))
         self.updates += 1
-        m.forward_packed(s0.data_ptr(), B, B, out=self._q[:B], train=True, dropout_seed=(self.seed << 20) ^ self.updates)
+        tp = self.train_precision
+        m.forward_packed(s0.data_ptr(), B, B, out=self._q[:B], train=True, dropout_seed=(self.seed << 20) ^ self.updates, precision=tp)
         _lib.check(self.L.dq_dqn_loss_grad(p(self._q), p(actions), p(self._y), B, A, p(self._dq), p(self._stats), st))
         o = self.optimizer
         if self.comm is not None:          # gradient mean over the ranks fused with the Adam step (csrc/dq_comm.cu)
-            m.backward_packed(s0.data_ptr(), B, B, self._dq, self.comm.grads())
+            m.backward_packed(s0.data_ptr(), B, B, self._dq, self.comm.grads(), precision=tp)
             self.comm.step(m.params, self.adam_m, self.adam_v, o, self.updates, st)
             m.params_changed()
             return
-        m.backward_packed(s0.data_ptr(), B, B, self._dq, self.grads)
+        m.backward_packed(s0.data_ptr(), B, B, self._dq, self.grads, precision=tp)
         scale = 1.0
         if self.process_group is not None:
             import torch.distributed as dist

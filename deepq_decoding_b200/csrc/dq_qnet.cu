@@ -906,6 +906,17 @@ extern "C" int dq_qnet_fold_head(const dq_qnet* h, const float* params, float* w
 
 namespace dq {
 
+struct TcArgs {
+    const __nv_bfloat16* X; Patch g;            // AMODE 0: input activation (channels-last bf16) and its patch geometry
+    const u64* packed; long long pstride;       // AMODE 1: packed observation rows [C*PW][pstride]
+    int C, PW, H, T;                            //          input layers, words per layer, side, taps per layer (ksz*ksz)
+    const __nv_bfloat16* Wt;                    // weights, transposed + zero-padded: [Npad][Kpad]
+    const float* bias;
+    void* Y; int ldy, out_bf16, relu;           // output rows of ldy elements
+    long long M; int N, K, Kpad;
+};
+
+// [tcgen05 kernels: begin]  (tests/emu_qnet.py swaps the marked regions for plain loops with the same arguments; the product builds them as written)
 __device__ __forceinline__ void cp_async16(u32 smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
@@ -920,15 +931,6 @@ __device__ __forceinline__ void umma_bf16(u32 tmem_d, uint64_t adesc, uint64_t b
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-struct TcArgs {
-    const __nv_bfloat16* X; Patch g;            // AMODE 0: input activation (channels-last bf16) and its patch geometry
-    const u64* packed; long long pstride;       // AMODE 1: packed observation rows [C*PW][pstride]
-    int C, PW, H, T;                            //          input layers, words per layer, side, taps per layer (ksz*ksz)
-    const __nv_bfloat16* Wt;                    // weights, transposed + zero-padded: [Npad][Kpad]
-    const float* bias;
-    void* Y; int ldy, out_bf16, relu;           // output rows of ldy elements
-    long long M; int N, K, Kpad;
-};
 
 // Epilogue of a 128 x BN accumulator tile: warp w owns TMEM lanes 32w..32w+31 = output rows; thread = one row.
 template <int BN>
@@ -1260,6 +1262,8 @@ tc_gemm_pipe_kernel(const TcArgs a) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((u32)(BN < 32 ? 32 : BN)) : "memory");
 }
 
+// [tcgen05 kernels: end]
+
 // Fused head for the acting path: y = x W + b for the last (tiny) dense layer, then the dueling combination.
 // 4 adjacent lanes share a sample; lane p owns the 4-column groups p, p+4, p+8, ... of the N outputs, so every weight read is
 // one 128-bit shared load shared by all samples of the warp.  W (rows padded to a multiple of 4), the bias and the CTA's 32
@@ -1375,6 +1379,243 @@ head_dueling_kernel(const float* __restrict__ x, const float* __restrict__ W, co
         }
     }
 }
+// ================================================================================================
+// bf16 tensor-core TRAINING path (opt-in: DQNAgent(train_precision="bf16")).  Forward = the tcgen05 layers above (unfolded head,
+// dropout on the bf16 activation); backward = per tensor-core layer j, with G_j the gradient at the layer's output:
+//   prep_dy      G_j (fp32, bf16, or gathered out of layer j+1's column gradient: col2im) x ReLU / dropout mask
+//                -> dYb [M][Npad] and its transpose dYT [Npad'][Mpad] (bf16), bias gradient = column sums
+//   im2colT      A_j^T [Kpad][Mpad] (bf16): the layer's patch matrix, transposed (layer 1: straight from the packed bits)
+//   tc_dw        dW_j[K][N] += A_j^T x dYT^T   -- contraction over the M = batch x positions rows, split over CTAs (grid.z), fp32
+//                atomics into the caller's gradient buffer
+//   tc_gemm      dCol_j[M][K] = dYb x W_j^T    -- the forward kernel with W_j's bf16 copy [K][Npad] as the "transposed weight"
+// Both GEMM operands are K-major for tcgen05 because the transposes are materialised (bf16, a few tens of MB at batch 4096).
+// fp32 master weights, fp32 accumulation in TMEM, fp32 gradients / Adam: the usual mixed-precision recipe.
+
+// [tcgen05 kernels: begin]
+// D[R][N] += At[R][k] * Bt[N][k]^T over this CTA's k blocks.  At rows are padded to a multiple of 128 (zeros), Bt rows to a multiple
+// of BN, both leading dimensions to a multiple of 64 elements.  128 x BN fp32 accumulator in TMEM, S-stage cp.async ring.
+template <int BN, int S>
+__global__ void __launch_bounds__(128)
+tc_dw_kernel(const __nv_bfloat16* __restrict__ At, long long lda, const __nv_bfloat16* __restrict__ Bt, long long ldb,
+             float* __restrict__ D, int ldd, int R, int N, int kb_total, int kb_per_cta) {
+    constexpr u32 STAGE = 16384u + (u32)BN * 128u;
+    extern __shared__ unsigned char tc_raw[];
+    __shared__ alignas(8) u64 mbar_free[S];
+    __shared__ u32 tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const u32 s_base = (smem_u32(tc_raw) + 1023u) & ~1023u;
+    const int r0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+    const int kb0 = blockIdx.z * kb_per_cta, KB = min(kb_per_cta, kb_total - kb0);
+    if (KB <= 0) return;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((u32)(BN < 32 ? 32 : BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) for (int s = 0; s < S; ++s) mbar_init(&mbar_free[s], 1);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const u32 tmem = tmem_slot;
+    const u32 idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(BN >> 3) << 17) | ((u32)(128 >> 4) << 24);
+    const __nv_bfloat16* a_base = At + (long long)r0 * lda + (long long)kb0 * 64;
+    const __nv_bfloat16* b_base = Bt + (long long)n0 * ldb + (long long)kb0 * 64;
+
+    auto load_chunk = [&](int kb) {
+        const u32 sA = s_base + (u32)(kb % S) * STAGE, sB = sA + 16384u;
+        const int c = tid & 7;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int rr = (tid >> 3) + 16 * j;
+            cp_async16(sA + (u32)rr * 128u + (u32)((c ^ (rr & 7)) << 4), a_base + (long long)rr * lda + kb * 64 + c * 8);
+        }
+        for (int i = tid; i < BN * 8; i += 128) {
+            const int cc = i & 7, n = i >> 3;
+            cp_async16(sB + (u32)n * 128u + (u32)((cc ^ (n & 7)) << 4), b_base + (long long)n * ldb + kb * 64 + cc * 8);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int kb = 0; kb < S - 1; ++kb) {
+        if (kb < KB) load_chunk(kb);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int kb = 0; kb < KB; ++kb) {
+        const int nk = kb + S - 1;
+        if (nk < KB) {
+            if (nk >= S) mbar_wait_or_trap(&mbar_free[nk % S], (u32)((nk / S - 1) & 1));
+            load_chunk(nk);
+        } else {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        asm volatile("cp.async.wait_group %0;" ::"n"(S - 1) : "memory");
+        fence_proxy_async();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const u32 sA = s_base + (u32)(kb % S) * STAGE;
+            const uint64_t da = umma_smem_desc(sA), db = umma_smem_desc(sA + 16384u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar_free[kb % S])) : "memory");
+        }
+    }
+    mbar_wait_or_trap(&mbar_free[(KB - 1) % S], (u32)(((KB - 1) / S) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: warp w owns TMEM lanes 32w.. = rows r0 + 32w + lane; fp32 atomics (several CTAs share every output)
+    const u32 taddr = tmem + ((u32)(warp * 32) << 16);
+    const int row = r0 + tid;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+        u32 v[16];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                     : "r"(taddr + (u32)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < R) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float f = __uint_as_float(v[j]);
+                if (n0 + c0 + j < N && f != 0.f) atomicAdd(D + (long long)row * ldd + n0 + c0 + j, f);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((u32)(BN < 32 ? 32 : BN)) : "memory");
+}
+
+// [tcgen05 kernels: end]
+
+// A^T[k][m] (bf16, rows 0..Kpad-1, columns 0..Mpad-1, zero outside K x M) of a patch matrix over a channels-last bf16 activation.
+// 64 x 64 tiles through shared memory: rows of A are read along k (contiguous within a patch segment), written along m.
+__global__ void __launch_bounds__(256)
+im2colT_kernel(const __nv_bfloat16* __restrict__ X, Patch g, long long M, int K, __nv_bfloat16* __restrict__ At, long long lda) {
+    __shared__ __nv_bfloat16 tile[64][66];
+    __shared__ long long rowoff[64];
+    __shared__ int coloff[64];
+    const int tid = threadIdx.x;
+    const long long m0 = (long long)blockIdx.x * 64;
+    const int k0 = blockIdx.y * 64;
+    if (tid < 64) rowoff[tid] = (m0 + tid < M) ? patch_row(g, m0 + tid) : -1;
+    else if (tid < 128) coloff[tid - 64] = (k0 + tid - 64 < K) ? patch_col(g, k0 + tid - 64) : -1;
+    __syncthreads();
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const int e = tid + i * 256, mm = e >> 6, kk = e & 63;
+        const long long ro = rowoff[mm];
+        const int co = coloff[kk];
+        tile[kk][mm] = (ro >= 0 && co >= 0) ? X[ro + co] : __float2bfloat16(0.f);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const int e = tid + i * 256, kk = e >> 6, mm = e & 63;
+        At[(long long)(k0 + kk) * lda + m0 + mm] = tile[kk][mm];
+    }
+}
+// Layer 1: the same matrix straight from the packed observation bits, rows in the parameter order k = tap * C + layer.
+__global__ void __launch_bounds__(256)
+im2colT_bits_kernel(const u64* __restrict__ packed, long long stride, ConvL L, int C, int PW, int H, long long M,
+                    __nv_bfloat16* __restrict__ At, long long lda, int Kpad) {
+    const long long m = (long long)blockIdx.x * 256 + threadIdx.x;          // column (< lda)
+    if (m >= lda) return;
+    const bool live = m < M;
+    const long long b = live ? m / L.P : 0;
+    const int pos = live ? (int)(m - b * L.P) : 0, oy = pos / L.oh, ox = pos - oy * L.oh;
+    const int T = L.ksz * L.ksz;
+    for (int ci = 0; ci < C; ++ci) {
+        const u32 taps = live ? layer_taps(packed, stride, b, ci, PW, H, oy * L.stride, ox * L.stride, L.ksz) : 0u;
+        for (int t = 0; t < T; ++t) At[(long long)(t * C + ci) * lda + m] = __float2bfloat16((float)((taps >> t) & 1u));
+    }
+    if (blockIdx.y == 0) for (int k = T * C; k < Kpad; ++k) At[(long long)k * lda + m] = __float2bfloat16(0.f);
+}
+
+// The gradient at a layer's output, masked and laid out for the two GEMMs of its backward step.
+//   src_mode 0: fp32 [M][N];  1: bf16 [M][N];  2: col2im -- G[m = (b, iy, ix)][c] = sum over the taps (ky, kx) of the layer ABOVE that
+//   read this cell of dcol[(b, oy, ox)][(ky*ksz + kx)*N + c]  (up: the patch geometry of the layer above, Kup its K)
+struct DySrc { const void* p; int mode; Patch up; int Kup; };
+__global__ void __launch_bounds__(256)
+prep_dy_kernel(DySrc src, const __nv_bfloat16* __restrict__ act, const float* __restrict__ mask, long long M, int N,
+               __nv_bfloat16* __restrict__ dYb, int ldyb, __nv_bfloat16* __restrict__ dYT, long long ldyt, int rows_t,
+               float* __restrict__ db) {
+    __shared__ float tile[64][65];
+    const int tid = threadIdx.x;
+    const long long m0 = (long long)blockIdx.x * 64;
+    const int n0 = blockIdx.y * 64;
+#pragma unroll 2
+    for (int i = 0; i < 16; ++i) {
+        const int e = tid + i * 256, mm = e >> 6, nn = e & 63;
+        const long long m = m0 + mm;
+        const int n = n0 + nn;
+        float gval = 0.f;
+        if (m < M && n < N) {
+            if (src.mode == 0) gval = reinterpret_cast<const float*>(src.p)[m * N + n];
+            else if (src.mode == 1) gval = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src.p)[m * N + n]);
+            else {
+                const Patch& u = src.up;                         // this layer's output map is the upper layer's input map: side u.ih
+                const int cells = u.ih * u.ih;
+                const long long b = m / cells;
+                const int pos = (int)(m - b * cells), iy = pos / u.ih, ix = pos - iy * u.ih;
+                const __nv_bfloat16* dc = reinterpret_cast<const __nv_bfloat16*>(src.p);
+                for (int ky = 0; ky < u.ksz; ++ky) {
+                    const int ty = iy - ky;
+                    if (ty < 0 || ty % u.stride) continue;
+                    const int oy = ty / u.stride;
+                    if (oy >= u.oh) continue;
+                    for (int kx = 0; kx < u.ksz; ++kx) {
+                        const int tx = ix - kx;
+                        if (tx < 0 || tx % u.stride) continue;
+                        const int ox = tx / u.stride;
+                        if (ox >= u.oh) continue;
+                        gval += __bfloat162float(dc[((b * u.P + oy * u.oh + ox) * (long long)src.Kup) + (ky * u.ksz + kx) * N + n]);
+                    }
+                }
+            }
+            if (act && !(__bfloat162float(act[m * N + n]) > 0.f)) gval = 0.f;
+            if (mask) gval *= mask[m * N + n];
+        }
+        const __nv_bfloat16 gb = __float2bfloat16(gval);
+        if (m < M && n < ldyb) dYb[m * ldyb + n] = gb;
+        tile[nn][mm] = __bfloat162float(gb);                     // the bias gradient sums what the GEMMs see
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int i = 0; i < 16; ++i) {
+        const int e = tid + i * 256, nn = e >> 6, mm = e & 63;
+        if (n0 + nn < rows_t && m0 + mm < ldyt) dYT[(long long)(n0 + nn) * ldyt + m0 + mm] = __float2bfloat16(tile[nn][mm]);
+    }
+    if (tid < 64 && n0 + tid < N) {
+        float sum = 0.f;
+#pragma unroll 8
+        for (int mm = 0; mm < 64; ++mm) sum += tile[tid][mm];
+        if (sum != 0.f) atomicAdd(db + n0 + tid, sum);
+    }
+}
+// fp32 W[K][N] -> bf16 Wb[rows][Npad] (same orientation, zero padded): the "transposed weight" of the dX GEMM
+__global__ void prep_wb_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wb, int K, int N, int rows, int Npad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * Npad) return;
+    const int k = i / Npad, n = i - k * Npad;
+    Wb[i] = __float2bfloat16((k < K && n < N) ? W[(size_t)k * N + n] : 0.f);
+}
+// training-mode dropout on a bf16 activation: the masks of dropout_kernel (same Philox words), kept in fp32 for the backward pass
+__global__ void dropout_bf16_kernel(__nv_bfloat16* __restrict__ Y, float* __restrict__ mask, long long n, float rate, u32 k0, u32 k1, u32 tag) {
+    const u32 thr = (u32)fminf(rate * 4294967296.f, 4294967295.f);
+    const float scale = 1.f / (1.f - rate);
+    for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 * 4 < n; i4 += (long long)gridDim.x * blockDim.x) {
+        const Philox4 u = philox4x32_10((u32)i4, (u32)(i4 >> 32), tag, 3u, k0, k1);
+        const u32 uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long i = i4 * 4 + j;
+            if (i < n) { const float mk = (uu[j] >= thr) ? scale : 0.f; mask[i] = mk; Y[i] = __float2bfloat16(__bfloat162float(Y[i]) * mk); }
+        }
+    }
+}
+
 // fp32 [K][N] -> bf16 [Npad][Kpad] (transposed, zero padded)
 // perm_C > 0 (layer 1): our K order is (layer, tap) while W's rows are (tap, layer): k' = ci*T + t  <-  k = t*C + ci
 __global__ void prep_wt_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt, int K, int N, int Kpad, int Npad, int perm_C) {
@@ -1396,7 +1637,9 @@ struct dq_qnet_tc {                     // bf16 buffers of the tensor-core path,
     // Dense(num_actions) + dueling head folded into one affine map (dq_qnet_fold_head; DQ_QNET_FOLD_HEAD=0 turns it off); the last
     // tensor-core layer then multiplies with fold_wt / fold_b and writes Q itself
     float* fold_w; float* fold_b; __nv_bfloat16* fold_wt; int folded;
+    struct dq_qnet_tcb* bwd;            // scratch of the bf16 backward pass (dq_qnet_backward_tc), allocated on first use
 };
+static void tcb_free(struct dq_qnet_tcb* b);
 static bool tc_fold_enabled() {
     static const bool on = [] { const char* e = getenv("DQ_QNET_FOLD_HEAD"); return !(e && e[0] == '0'); }();      // default on (measured: 0.127 -> 0.112 ms per 16 384 observations, same greedy agreement with fp32); =0 keeps the three layers apart
     return on;
@@ -1406,6 +1649,7 @@ static void tc_free(dq_qnet* h) {
     if (!tc) return;
     for (int i = 0; i < kMaxConv + kMaxDense + 2; ++i) { cudaFree(tc->act[i]); cudaFree(tc->wt[i]); }
     cudaFree(tc->fold_w); cudaFree(tc->fold_b); cudaFree(tc->fold_wt);
+    tcb_free(tc->bwd);
     delete tc;
     h->tc = nullptr;
 }
@@ -1527,8 +1771,8 @@ extern "C" int dq_qnet_prepare_tc(dq_qnet* h, const float* params, dq_stream str
 
 // Q values through the bf16 tcgen05 path (inference / acting only; training stays fp32).  Uses the weights staged by
 // the last dq_qnet_prepare_tc.  Shapes outside the path's coverage return DQ_EINVAL (callers choose the fp32 path).
-extern "C" int dq_qnet_forward_tc(dq_qnet* h, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
-                                  float* q_out, dq_stream stream) {
+static int tc_forward(dq_qnet* h, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
+                      float* q_out, int train, uint64_t dropout_seed, dq_stream stream) {
     if (!h || !params || !packed || !q_out) return qfail(DQ_EINVAL, "NULL argument");
     if (batch < 1 || batch > h->max_batch) return qfail(DQ_EINVAL, "batch exceeds max_batch of the handle");
     if (!h->tc) return qfail(DQ_ESTATE, "call dq_qnet_prepare_tc first");
@@ -1536,6 +1780,7 @@ extern "C" int dq_qnet_forward_tc(dq_qnet* h, const float* params, const uint64_
     cudaStream_t st = (cudaStream_t)stream;
     dq_qnet_tc* tc = (dq_qnet_tc*)h->tc;
     const int n_tc = tc_layers(c);
+    const bool folded = tc->folded && !train;              // training keeps Dense(num_actions) and the dueling layer apart (their gradients differ)
     for (int j = 0; j < n_tc; ++j) {
         TcArgs a;
         memset(&a, 0, sizeof(a));
@@ -1545,7 +1790,7 @@ extern "C" int dq_qnet_forward_tc(dq_qnet* h, const float* params, const uint64_
         else { const int i = j - c.n_conv; a.g = dense_patch(c.fc_in[i]); a.M = batch; a.N = c.fc_out[i]; a.K = c.fc_in[i]; }
         a.relu = last ? 0 : 1; a.out_bf16 = last ? 0 : 1; a.ldy = a.N;
         a.Y = last ? (void*)h->act_fc[c.n_hidden] : (void*)tc->act[j];
-        if (last && tc->folded) { a.Wt = tc->fold_wt; a.bias = tc->fold_b; a.Y = q_out; }      // N = num_actions: the rows are Q itself
+        if (last && folded) { a.Wt = tc->fold_wt; a.bias = tc->fold_b; a.Y = q_out; }      // N = num_actions: the rows are Q itself
         int rc;
         if (j == 0) {
             a.packed = (const u64*)packed; a.pstride = stride; a.C = c.C; a.PW = c.PW; a.H = c.H; a.T = c.conv[0].ksz * c.conv[0].ksz;
@@ -1555,8 +1800,15 @@ extern "C" int dq_qnet_forward_tc(dq_qnet* h, const float* params, const uint64_
             rc = launch_tc_bn<0>(a, tc->bn[j], tc->npad[j], st);
         }
         if (rc) return rc;
+        if (train && j >= c.n_conv && !last && c.drop[j - c.n_conv] > 0.f) {     // Dropout after a hidden dense layer (FL:366-370)
+            const int i = j - c.n_conv;
+            const long long n = batch * c.fc_out[i];
+            dropout_bf16_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(tc->act[j], h->mask_fc[i], n, c.drop[i], (u32)dropout_seed, (u32)(dropout_seed >> 32), (u32)i);
+            count_launch();
+        }
     }
-    if (tc->folded) { h->last_train = 0; QCUDA(cudaGetLastError()); return DQ_OK; }
+    h->last_train = train;
+    if (folded) { QCUDA(cudaGetLastError()); return DQ_OK; }
     // dueling head (tiny) in fp32 on the SIMT path
     const float* xf = h->act_fc[c.n_hidden];
     if (c.dueling) {
@@ -1579,7 +1831,166 @@ extern "C" int dq_qnet_forward_tc(dq_qnet* h, const float* params, const uint64_
     } else {
         QCUDA(cudaMemcpyAsync(q_out, xf, (size_t)batch * c.A * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    h->last_train = 0;
+    QCUDA(cudaGetLastError());
+    return DQ_OK;
+}
+extern "C" int dq_qnet_forward_tc(dq_qnet* h, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
+                                  float* q_out, dq_stream stream) {
+    return tc_forward(h, params, packed, stride, batch, q_out, 0, 0, stream);
+}
+// The forward pass of a bf16 update: same tensor-core layers, Dense(num_actions) and the dueling layer kept apart, dropout applied to
+// the bf16 activations (masks kept for dq_qnet_backward_tc).
+extern "C" int dq_qnet_forward_tc_train(dq_qnet* h, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
+                                        float* q_out, uint64_t dropout_seed, dq_stream stream) {
+    return tc_forward(h, params, packed, stride, batch, q_out, 1, dropout_seed, stream);
+}
+
+// ---- bf16 backward --------------------------------------------------------------------------------------------------------------
+struct dq_qnet_tcb {                    // scratch of dq_qnet_backward_tc, sized for `cap` samples, grown on demand
+    long long cap;
+    __nv_bfloat16 *at, *dyb, *dyt, *dcol, *wb;
+};
+struct TcbGeom { int K, N; long long rows, M, Mpad; int rowsA, bn_dw, rows_t, ldyb, bn_dx, npad_dx; };
+static int bn_for(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : 128); }
+static TcbGeom tcb_geom(const QCfg& c, int j, long long batch) {
+    TcbGeom g;
+    tc_shape(c, j, g.K, g.N, g.rows);
+    g.M = batch * g.rows; g.Mpad = (g.M + 63) / 64 * 64;
+    g.rowsA = (g.K + 127) / 128 * 128;
+    g.bn_dw = bn_for(g.N); g.rows_t = (g.N + g.bn_dw - 1) / g.bn_dw * g.bn_dw;
+    g.ldyb = (g.N + 63) / 64 * 64;
+    g.bn_dx = bn_for(g.K); g.npad_dx = (g.K + g.bn_dx - 1) / g.bn_dx * g.bn_dx;
+    return g;
+}
+static void tcb_free(dq_qnet_tcb* b) {
+    if (!b) return;
+    cudaFree(b->at); cudaFree(b->dyb); cudaFree(b->dyt); cudaFree(b->dcol); cudaFree(b->wb);
+    delete b;
+}
+static dq_qnet_tcb* tcb_of(dq_qnet* h, long long batch) {
+    dq_qnet_tc* tc = (dq_qnet_tc*)h->tc;
+    if (tc->bwd && tc->bwd->cap >= batch) return tc->bwd;
+    tcb_free(tc->bwd);
+    tc->bwd = nullptr;
+    const QCfg& c = h->c;
+    size_t n_at = 0, n_dyb = 0, n_dyt = 0, n_dcol = 0, n_wb = 0;
+    for (int j = 0; j < tc_layers(c); ++j) {
+        const TcbGeom g = tcb_geom(c, j, batch);
+        n_at = std::max<size_t>(n_at, (size_t)g.rowsA * (size_t)g.Mpad);
+        n_dyb = std::max<size_t>(n_dyb, (size_t)g.Mpad * (size_t)g.ldyb);
+        n_dyt = std::max<size_t>(n_dyt, (size_t)g.rows_t * (size_t)g.Mpad);
+        if (j > 0) { n_dcol = std::max<size_t>(n_dcol, (size_t)g.M * (size_t)g.K); n_wb = std::max<size_t>(n_wb, (size_t)g.npad_dx * (size_t)g.ldyb); }
+    }
+    dq_qnet_tcb* b = new dq_qnet_tcb();
+    memset(b, 0, sizeof(*b));
+    cudaError_t err = cudaMalloc(&b->at, n_at * 2);
+    if (err == cudaSuccess) err = cudaMalloc(&b->dyb, n_dyb * 2);
+    if (err == cudaSuccess) err = cudaMalloc(&b->dyt, n_dyt * 2);
+    if (err == cudaSuccess) err = cudaMalloc(&b->dcol, std::max<size_t>(n_dcol, 8) * 2);
+    if (err == cudaSuccess) err = cudaMalloc(&b->wb, std::max<size_t>(n_wb, 8) * 2);
+    if (err != cudaSuccess) { tcb_free(b); return nullptr; }
+    b->cap = batch;
+    tc->bwd = b;
+    return b;
+}
+template <int BN>
+static int launch_tc_dw(const __nv_bfloat16* At, long long lda, const __nv_bfloat16* Bt, long long ldb, float* D, int ldd, int R, int N,
+                        int rowsA, int rows_t, cudaStream_t st) {
+    constexpr int S = 4;
+    const size_t smem = (size_t)S * (16384 + (size_t)BN * 128) + 1024;
+    QCUDA(cudaFuncSetAttribute(tc_dw_kernel<BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int kb_total = (int)(lda / 64);
+    const int tiles = (rowsA / 128) * (rows_t / BN);
+    // the contraction (batch x positions) is cut into slices over grid.z: about two CTAs per SM, at least 8 chunks of 64 per CTA
+    int z = std::max(1, std::min(kb_total / 8, (2 * 148 + tiles - 1) / tiles));
+    const int per = (kb_total + z - 1) / z;
+    z = (kb_total + per - 1) / per;
+    tc_dw_kernel<BN, S><<<dim3(rowsA / 128, rows_t / BN, z), 128, smem, st>>>(At, lda, Bt, ldb, D, ldd, R, N, kb_total, per);
+    count_launch();
+    return DQ_OK;
+}
+
+// Gradients of sum_b sum_a dq[b][a]*Q[b][a] for the batch of the LAST dq_qnet_forward_tc_train call, through the tensor cores:
+// per layer two bf16 GEMMs with fp32 accumulation (dW over the batch, dX over the output channels); the dueling layer (51 x 52)
+// stays on the fp32 kernels.  grads (flat fp32, n_params) is overwritten.
+extern "C" int dq_qnet_backward_tc(dq_qnet* h, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
+                                   const float* dq, float* grads, dq_stream stream) {
+    if (!h || !params || !packed || !dq || !grads) return qfail(DQ_EINVAL, "NULL argument");
+    if (batch < 1 || batch > h->max_batch) return qfail(DQ_EINVAL, "batch exceeds max_batch of the handle");
+    if (!h->tc) return qfail(DQ_ESTATE, "call dq_qnet_prepare_tc and dq_qnet_forward_tc_train first");
+    const QCfg& c = h->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    dq_qnet_tc* tc = (dq_qnet_tc*)h->tc;
+    int prev = 0; cudaGetDevice(&prev); cudaSetDevice(h->device);
+    dq_qnet_tcb* sb = tcb_of(h, batch);
+    cudaSetDevice(prev);
+    if (!sb) return qfail(DQ_ECUDA, "allocating the backward scratch failed");
+    const int n_tc = tc_layers(c);
+    QCUDA(cudaMemsetAsync(grads, 0, (size_t)c.n_params * sizeof(float), st));
+    // head: G = gradient at the output of Dense(num_actions), fp32 [batch][A]
+    const float* G32 = dq;
+    if (c.dueling) {
+        const int i = c.n_fc - 1, t = c.n_conv + i, K = c.fc_in[i], N = c.fc_out[i];
+        float* dY = h->dact_fc[i];
+        dueling_bwd_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(dq, dY, batch, c.A);
+        const long long chunk = dw_chunk(batch, K, N);
+        dim3 gw((K + TB - 1) / TB, (N + TB - 1) / TB, (unsigned)((batch + chunk - 1) / chunk));
+        gemm_dw_kernel<<<gw, 256, 0, st>>>(h->act_fc[i - 1], dense_patch(K), dY, grads + c.w_off[t], batch, N, K, chunk);
+        colsum_kernel<<<dim3((N + 31) / 32, (unsigned)std::min<long long>(64, (batch + 7) / 8)), 256, 0, st>>>(dY, grads + c.b_off[t], batch, N);
+        dim3 gx((unsigned)((batch + TB - 1) / TB), (K + TB - 1) / TB);
+        gemm_dx_kernel<16><<<gx, 256, 0, st>>>(dY, params + c.w_off[t], h->dact_fc[i - 1], dense_patch(K), batch, N, K, 0);
+        count_launch(); count_launch(); count_launch(); count_launch();
+        G32 = h->dact_fc[i - 1];
+    }
+    for (int j = n_tc - 1; j >= 0; --j) {
+        const TcbGeom g = tcb_geom(c, j, batch);
+        // 1. the masked gradient at this layer's output, in the two layouts the GEMMs read, and the bias gradient
+        DySrc src;
+        memset(&src, 0, sizeof(src));
+        const __nv_bfloat16* act = nullptr;
+        const float* mask = nullptr;
+        if (j == n_tc - 1) { src.p = G32; src.mode = 0; }
+        else {
+            act = tc->act[j];                                                       // ReLU: pass where the (bf16) output is positive
+            if (j >= c.n_conv && h->last_train && c.drop[j - c.n_conv] > 0.f) mask = h->mask_fc[j - c.n_conv];
+            src.p = sb->dcol;
+            if (j + 1 < c.n_conv) { src.mode = 2; src.up = conv_patch(c.conv[j + 1]); src.Kup = c.conv[j + 1].K; }
+            else src.mode = 1;                                                      // a dense layer above: its column gradient is this layer's map
+        }
+        const int ncols = std::max(g.ldyb, g.rows_t);
+        prep_dy_kernel<<<dim3((unsigned)(g.Mpad / 64), (ncols + 63) / 64), 256, 0, st>>>(src, act, mask, g.M, g.N, sb->dyb, g.ldyb, sb->dyt, g.Mpad, g.rows_t,
+                                                                                      grads + c.b_off[j]);
+        count_launch();
+        // 2. A^T, then dW = A^T x dY over the batch
+        if (j == 0) {
+            const ConvL& L = c.conv[0];
+            im2colT_bits_kernel<<<dim3((unsigned)((g.Mpad + 255) / 256), 1), 256, 0, st>>>((const u64*)packed, stride, L, c.C, c.PW, c.H, g.M, sb->at, g.Mpad, g.rowsA);
+        } else {
+            const Patch pg = j < c.n_conv ? conv_patch(c.conv[j]) : dense_patch(g.K);
+            im2colT_kernel<<<dim3((unsigned)(g.Mpad / 64), g.rowsA / 64), 256, 0, st>>>(tc->act[j - 1], pg, g.M, g.K, sb->at, g.Mpad);
+        }
+        count_launch();
+        int rc;
+        switch (g.bn_dw) {
+            case 32: rc = launch_tc_dw<32>(sb->at, g.Mpad, sb->dyt, g.Mpad, grads + c.w_off[j], g.N, g.K, g.N, g.rowsA, g.rows_t, st); break;
+            case 64: rc = launch_tc_dw<64>(sb->at, g.Mpad, sb->dyt, g.Mpad, grads + c.w_off[j], g.N, g.K, g.N, g.rowsA, g.rows_t, st); break;
+            default: rc = launch_tc_dw<128>(sb->at, g.Mpad, sb->dyt, g.Mpad, grads + c.w_off[j], g.N, g.K, g.N, g.rowsA, g.rows_t, st); break;
+        }
+        if (rc) return rc;
+        if (j == 0) break;
+        // 3. column gradient dCol[M][K] = dY x W^T: the forward GEMM kernel with W's bf16 copy [K][N] as its "transposed weight"
+        {
+            const int total = g.npad_dx * g.ldyb;
+            prep_wb_kernel<<<(total + 255) / 256, 256, 0, st>>>(params + c.w_off[j], sb->wb, g.K, g.N, g.npad_dx, g.ldyb);
+            count_launch();
+            TcArgs a;
+            memset(&a, 0, sizeof(a));
+            a.X = sb->dyb; a.g = dense_patch(g.ldyb); a.Wt = sb->wb; a.bias = nullptr; a.Y = sb->dcol; a.ldy = g.K; a.out_bf16 = 1; a.relu = 0;
+            a.M = g.M; a.N = g.K; a.K = g.N; a.Kpad = g.ldyb;
+            rc = launch_tc_bn<0>(a, g.bn_dx, g.npad_dx, st);
+            if (rc) return rc;
+        }
+    }
     QCUDA(cudaGetLastError());
     return DQ_OK;
 }

@@ -174,15 +174,19 @@ class QNetwork:
         return out
 
     def forward_packed(self, packed_ptr, stride, batch, out=None, train=False, dropout_seed=0, params=None, precision="fp32"):
-        """precision: "fp32" (SIMT kernels, training-exact) or "bf16" (tcgen05 tensor-core path, acting only)."""
+        """precision: "fp32" (SIMT kernels, Keras-fp32 arithmetic) or "bf16" (tcgen05 tensor cores, fp32 accumulation)."""
         q = self._q[:batch] if out is None else out
         p = self.params if params is None else params
         if precision == "bf16":
-            if train or params is not None:
-                raise ValueError("the bf16 tensor-core path is inference-only and uses the network's own parameters")
+            if params is not None:
+                raise ValueError("the bf16 tensor-core path uses the network's own parameters (its staged bf16 copies)")
             if self._tc_dirty:
                 _lib.check(self.L.dq_qnet_prepare_tc(self._h, C.c_void_p(p.data_ptr()), self._stream()))
                 self._tc_dirty = False
+            if train:           # mixed-precision training forward: dropout applied, activations kept for backward_packed(precision="bf16")
+                _lib.check(self.L.dq_qnet_forward_tc_train(self._h, C.c_void_p(p.data_ptr()), C.c_void_p(packed_ptr), stride, batch,
+                                                           C.c_void_p(q.data_ptr()), int(dropout_seed), self._stream()))
+                return q
             _lib.check(self.L.dq_qnet_forward_tc(self._h, C.c_void_p(p.data_ptr()), C.c_void_p(packed_ptr), stride, batch,
                                                  C.c_void_p(q.data_ptr()), self._stream()))
             return q
@@ -200,12 +204,22 @@ class QNetwork:
         self._packed = packed
         return self.forward_packed(packed.data_ptr(), t.shape[0], t.shape[0], train=train, dropout_seed=dropout_seed, precision=precision)
 
+    def backward(self, dq, grads=None, precision="fp32"):
+        """Gradient (flat fp32) of sum(dq * Q) for the batch of the last forward(train=True) call."""
+        g = torch.zeros(self.num_params, dtype=torch.float32, device=self.device) if grads is None else grads
+        B = self._packed.shape[1]
+        return self.backward_packed(self._packed.data_ptr(), B, B, dq.contiguous(), g, precision=precision)
+
     def params_changed(self):
         """Tell the network its flat parameter buffer was modified in place (optimizer step, copy)."""
         self._tc_dirty = True
 
-    def backward_packed(self, packed_ptr, stride, batch, dq, grads, params=None):
+    def backward_packed(self, packed_ptr, stride, batch, dq, grads, params=None, precision="fp32"):
         p = self.params if params is None else params
+        if precision == "bf16":         # after forward_packed(train=True, precision="bf16") on the same batch
+            _lib.check(self.L.dq_qnet_backward_tc(self._h, C.c_void_p(p.data_ptr()), C.c_void_p(packed_ptr), stride, batch,
+                                                  C.c_void_p(dq.data_ptr()), C.c_void_p(grads.data_ptr()), self._stream()))
+            return grads
         _lib.check(self.L.dq_qnet_backward(self._h, C.c_void_p(p.data_ptr()), C.c_void_p(packed_ptr), stride, batch,
                                            C.c_void_p(dq.data_ptr()), C.c_void_p(grads.data_ptr()), self._stream()))
         return grads

@@ -212,6 +212,16 @@ int dq_qnet_forward_tc(dq_qnet* net, const float* params, const uint64_t* packed
 /* Stages the bf16 weight copies dq_qnet_forward_tc multiplies with; call after every change of `params`. */
 int dq_qnet_prepare_tc(dq_qnet* net, const float* params, dq_stream stream);
 int dq_qnet_tc_activation(dq_qnet* net, int index, void** dev_ptr, int64_t* per_sample);   /* tests: bf16 activations */
+/* bf16 tensor-core TRAINING step (model.train_on_batch of keras-rl's DQNAgent.backward, SPTS:119-152, in mixed precision: fp32
+ * master weights, bf16 operands, fp32 accumulation in TMEM, fp32 gradients).  dq_qnet_forward_tc_train is dq_qnet_forward_tc with
+ * dropout applied (mask from dropout_seed, the same Philox words as dq_qnet_forward) and Dense(num_actions) / the dueling layer kept
+ * apart; dq_qnet_backward_tc then overwrites `grads` with the gradient of sum_b sum_a dq[b][a]*Q[b][a] for that batch: per layer
+ * dW = A^T x dY (contraction over batch x positions, split over CTAs, fp32 atomics) and dCol = dY x W^T, both tcgen05 GEMMs.
+ * Same shape coverage and error behaviour as dq_qnet_forward_tc; call dq_qnet_prepare_tc after every change of `params`. */
+int dq_qnet_forward_tc_train(dq_qnet* net, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
+                             float* q_out, uint64_t dropout_seed, dq_stream stream);
+int dq_qnet_backward_tc(dq_qnet* net, const float* params, const uint64_t* packed, int64_t stride, int64_t batch,
+                        const float* dq, float* grads, dq_stream stream);
 /* Inference only: Dense(num_actions), keras-rl's dueling Dense(num_actions + 1) and its 'avg' combine (SPTS:119-130,
  * enable_dueling_network=True) are all linear, so Q = h * w_out + b_out with w_out [K][num_actions] (K = units of the last
  * hidden dense layer) and b_out [num_actions], both device fp32.  dq_qnet_prepare_tc stages this map and dq_qnet_forward_tc ends in it

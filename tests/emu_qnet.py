@@ -18,7 +18,45 @@ CUT = ("// =====================================================================
 TAIL = "static void tc_free(dq_qnet*) {}\n"
 QINFO_NUM_PARAMS, QINFO_PACKED_ROWS, QINFO_NUM_TENSORS, QINFO_FLOPS_PER_SAMPLE = range(4)
 
+OUT_TC = os.path.join(HERE, "host", "libdq_qnet_tc_emu.so")
+_HOST = os.path.join(HERE, "host")
+TC_SWAPS = (("// [tcgen05 kernels: begin]", "// [tcgen05 kernels: end]", open(os.path.join(_HOST, "tc_ref_gemm.inc")).read()),
+            ("// [tcgen05 kernels: begin]", "// [tcgen05 kernels: end]", open(os.path.join(_HOST, "tc_ref_dw.inc")).read()))
+
 _L = None
+_LTC = None
+
+
+def lib_tc():
+    """The WHOLE of dq_qnet.cu on the CPU, with the tcgen05 kernels swapped for plain loops (tests/host/tc_emu.h): the bf16
+    forward / backward drivers and every kernel around the GEMMs run as written."""
+    global _LTC
+    if _LTC is None:
+        deps = [os.path.join(_HOST, f) for f in ("tc_emu.h", "tc_ref_gemm.inc", "tc_ref_dw.inc")]
+        path = B.build(OUT_TC, [os.path.join(B.CSRC, "dq_env.cu"), (os.path.join(B.CSRC, "dq_qnet.cu"), None, "", TC_SWAPS)],
+                       extra_flags=("-include", os.path.join(_HOST, "tc_emu.h")), deps=deps)
+        L = C.CDLL(path)
+        _signatures(L)
+        vp, i, i64, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
+        L.dq_qnet_prepare_tc.argtypes = [vp, vp, vp]
+        L.dq_qnet_forward_tc.argtypes = [vp, vp, vp, i64, i64, vp, vp]
+        L.dq_qnet_forward_tc_train.argtypes = [vp, vp, vp, i64, i64, vp, u64, vp]
+        L.dq_qnet_backward_tc.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp]
+        _LTC = L
+    return _LTC
+
+
+def _signatures(L):
+    vp, i, i64, u64, u32, f, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_float, C.c_double
+    L.dq_last_error.restype = C.c_char_p
+    L.dq_qnet_create.argtypes = [C.POINTER(vp), i, i, i, vp, vp, vp, i, vp, vp, i, i, i64, i]
+    L.dq_qnet_destroy.argtypes = [vp]
+    L.dq_qnet_info.argtypes = [vp, i, C.POINTER(i64)]
+    L.dq_qnet_param_layout.argtypes = [vp, vp, vp]
+    L.dq_qnet_pack_obs.argtypes = [vp, vp, vp, i64, i64, vp]
+    L.dq_qnet_forward.argtypes = [vp, vp, vp, i64, i64, vp, i, u64, vp]
+    L.dq_qnet_backward.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp]
+    L.dq_qnet_activation.argtypes = [vp, i, C.POINTER(vp), C.POINTER(i64)]
 
 
 def lib():
@@ -50,16 +88,16 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def check(rc):
+def check(rc, L=None):
     if rc != 0:
-        raise RuntimeError("emulated ABI call failed (%d): %s" % (rc, lib().dq_last_error().decode()))
+        raise RuntimeError("emulated ABI call failed (%d): %s" % (rc, (L or lib()).dq_last_error().decode()))
 
 
 class EmuQNet:
     """Same construction arguments as deepq_decoding_b200.qnet.QNetwork; weights in Keras layouts in and out."""
 
-    def __init__(self, cc_layers, ff_layers, input_shape, num_actions, dueling=True, max_batch=256):
-        self.L = lib()
+    def __init__(self, cc_layers, ff_layers, input_shape, num_actions, dueling=True, max_batch=256, tc=False):
+        self.L = lib_tc() if tc else lib()
         self.cc, self.ff = [list(map(int, l)) for l in cc_layers], [[int(l[0]), float(l[1])] for l in ff_layers]
         self.C_in, self.H = int(input_shape[0]), int(input_shape[1])
         self.A, self.max_batch = int(num_actions), int(max_batch)
@@ -137,6 +175,24 @@ class EmuQNet:
         q = np.zeros((b, self.A), np.float32)
         check(self.L.dq_qnet_forward(self.h, _p(self.params), _p(packed), b, b, _p(q), int(train), dropout_seed, None))
         return q, packed
+
+    def forward_tc(self, packed, train=False, dropout_seed=0):
+        """bf16 path (tc=True handles only): prepare + forward; train keeps the head unfolded and applies dropout."""
+        b = packed.shape[1]
+        q = np.zeros((b, self.A), np.float32)
+        check(self.L.dq_qnet_prepare_tc(self.h, _p(self.params), None), self.L)
+        if train:
+            check(self.L.dq_qnet_forward_tc_train(self.h, _p(self.params), _p(packed), b, b, _p(q), dropout_seed, None), self.L)
+        else:
+            check(self.L.dq_qnet_forward_tc(self.h, _p(self.params), _p(packed), b, b, _p(q), None), self.L)
+        return q
+
+    def backward_tc(self, packed, dq):
+        b = packed.shape[1]
+        dq = np.ascontiguousarray(dq, dtype=np.float32)
+        grads = np.zeros(self.num_params, np.float32)
+        check(self.L.dq_qnet_backward_tc(self.h, _p(self.params), _p(packed), b, b, _p(dq), _p(grads), None), self.L)
+        return grads
 
     def fold_head(self):
         """(w [K][A], b [A]) with Q = h @ w + b for the output h of the last hidden dense layer (dq_qnet_fold_head)."""

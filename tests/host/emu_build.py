@@ -4,7 +4,9 @@ The product sources carry no emulation hooks: they are rewritten here, textually
 
   * `kernel<<<grid, block, smem, stream>>>(args);`  ->  `dq_emu::launch(grid, block, smem, [&]() { kernel(args); });`
   * `extern __shared__ T name[];`                   ->  `T* name = reinterpret_cast<T*>(DQ_EMU_DYNAMIC_SMEM);`
-  * everything from a cut marker on is dropped (the tcgen05 / TMEM path cannot run on a CPU) and replaced by a tail
+  * everything from a cut marker on is dropped (the tcgen05 / TMEM path cannot run on a CPU) and replaced by a tail; or
+    (the bf16 training variant of tests/emu_qnet.py) only the regions the source marks as tcgen05 kernels are swapped for
+    plain-loop stand-ins with the same launch arguments
   * includes of CUDA headers resolve to empty stubs in tests/host/emu_include/
 
 Nothing here is used, timed or shipped by the product.
@@ -85,8 +87,15 @@ def rewrite_launches(text):
         pos = a1
 
 
-def transform(path, cut_marker=None, tail=""):
+def transform(path, cut_marker=None, tail="", swaps=()):
+    """swaps: (begin marker, end marker, replacement) triples; the k-th marked region becomes the k-th replacement."""
     text = open(path).read()
+    pos = 0
+    for begin, end, repl in swaps:
+        i = text.index(begin, pos)
+        j = text.index(end, i) + len(end)
+        text = text[:i] + repl + text[j:]
+        pos = i + len(repl)
     if cut_marker:
         text = text[:text.index(cut_marker)] + "\n" + tail + "\n"
     text = re.sub(r'#include\s+"dq_ptx\.cuh"', "", text)
@@ -108,11 +117,11 @@ def build(out, sources, extra_flags=(), deps=()):
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(f) for f in all_deps):
         return out
     for s in sources:
-        path, cut, tail = (s, None, "") if isinstance(s, str) else s
-        gen = os.path.join(GEN, os.path.basename(path).replace(".cu", "_emu.cpp"))
+        path, cut, tail, *rest = (s, None, "") if isinstance(s, str) else s
+        gen = os.path.join(GEN, os.path.basename(out).replace(".so", "_") + os.path.basename(path).replace(".cu", "_emu.cpp"))
         with open(gen, "w") as f:
             f.write('#line 1 "%s"\n' % path)
-            f.write(transform(path, cut, tail))
+            f.write(transform(path, cut, tail, rest[0] if rest else ()))
         files.append(gen)
     cmd = ["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-DDQ_EMU", "-include", SHIM,
            "-fsanitize=alignment", "-fno-sanitize-recover=alignment", *(["-fsanitize=address"] if os.environ.get("DQ_EMU_ASAN") else []),      # x86 forgives misaligned loads, the GPU does not

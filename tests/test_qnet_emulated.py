@@ -10,7 +10,7 @@ import torch
 
 from oracle import oracle as O
 from oracle import qnet_ref as QR
-from qnet_util import REF_CC, golden_weights
+from qnet_util import REF_CC, golden_weights, Bf16SimQNet as _Bf16SimQNet, dropout_mask as _dropout_mask
 import emu_qnet as EQ
 
 Q_ATOL, G_RTOL = 2e-3, 2e-3
@@ -167,3 +167,43 @@ def test_emulated_folded_head_is_the_networks_head(which, A):
     want = y[:, :1] + y[:, 1:] - y[:, 1:].mean(axis=1, keepdims=True)
     got = h @ w.astype(np.float64) + b
     assert np.abs(got - want).max() < 1e-4 * max(1.0, np.abs(want).max())
+
+
+# ---- bf16 training path (dq_qnet_forward_tc_train / dq_qnet_backward_tc) ----------------------------------------------------
+# The tcgen05 GEMM kernels are swapped for plain loops (tests/host/tc_emu.h); everything around them runs as written.  The
+# reference is the torch network with the same roundings: bf16 weights and activations, fp32 accumulation, straight-through
+# gradients to the fp32 master weights -- so both sides take the same ReLU branches and the comparison is tight (the plain fp32
+# network differs from ANY bf16 forward by a few percent of the gradient norm: pre-activations within rounding distance of zero
+# flip their ReLU branch).
+@pytest.mark.parametrize("cfg", [(REF_CC, [(512, 0.2)], 7, 51, 48), ([[16, 3, 2], [8, 2, 1]], [(32, 0.0), (24, 0.25)], 6, 26, 40),
+                                 ([[8, 3, 2], [8, 2, 1]], [(16, 0.0)], 6, 26, 5)],
+                         ids=["reference_net", "small_two_dense", "ragged_batch"])
+def test_emulated_bf16_training_path_matches_rounded_autograd(cfg):
+    cc, ff, channels, A, B = cfg
+    rng = np.random.default_rng(11)
+    conv, dense = QR.glorot_uniform_params(rng, channels, cc, [u for u, _ in ff], A, 11)
+    for _, b in conv + dense:
+        b += rng.standard_normal(b.shape).astype(np.float32) * 0.05
+    q = EQ.EmuQNet(cc, [[u, r] for u, r in ff], (channels, 11, 11), A, max_batch=B, tc=True)
+    q.set_keras_weights(conv, dense)
+    net = _Bf16SimQNet(conv, dense, strides=[l[2] for l in cc])
+    boards = random_boards(B, channels, 3, density=0.2)
+    dq = rng.standard_normal((B, A)).astype(np.float32)
+    packed = q.pack(boards)
+    seed = 0x1234500077
+    masks = [torch.tensor(_dropout_mask(B, u, r, seed, i)) if r > 0 else None for i, (u, r) in enumerate(ff)]
+    # inference: folded head, no dropout
+    want_inf = net.forward(boards).detach().numpy()
+    assert np.abs(q.forward_tc(packed) - want_inf).max() < 2e-3
+    got_q = q.forward_tc(packed, train=True, dropout_seed=seed)
+    want_q = net.forward(boards, dropout_masks=masks)
+    assert np.abs(got_q - want_q.detach().numpy()).max() < 1e-4
+    (want_q * torch.tensor(dq)).sum().backward()
+    got = q.keras_grads(q.backward_tc(packed, dq))
+    for t, (g, prm) in enumerate(zip(got, net.parameters())):
+        want = prm.grad.numpy()
+        assert g.shape == want.shape
+        # dY and the column gradients are rounded to bf16 on their way into the GEMMs: a few 1e-3 of the tensor's norm
+        # (a 5-sample batch averages fewer roundings per entry: looser)
+        tol = 1e-2 if B >= 40 else 3e-2
+        assert np.linalg.norm(g - want) <= tol * np.linalg.norm(want) + 1e-6, (t, np.linalg.norm(g - want) / np.linalg.norm(want))

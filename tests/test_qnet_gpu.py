@@ -428,3 +428,74 @@ def test_reference_script_shape_runs_on_single_lattice(tmp_path):
     assert len(th["episode_lifetime"]) == 5 and th["episode_lifetimes_rolling_avg"][-1] == pytest.approx(np.mean(th["episode_lifetime"]))
     assert isinstance(dqn.forward(env.board_state), int)
     env.close()
+
+
+# ---- bf16 tensor-core training path -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [
+    (REF_CC, [[512, 0.2]], 7, 51, 1000),                            # the reference architecture, ragged batch (not a multiple of 128 / 64)
+    (REF_CC, [[512, 0.0]], 7, 51, 4096),                            # the bench's update batch
+    ([[16, 3, 2], [8, 2, 1]], [[32, 0.0], [24, 0.25]], 6, 26, 300),  # two hidden dense layers, narrow tiles
+])
+def test_bf16_training_path_matches_rounded_autograd(cfg):
+    """dq_qnet_forward_tc_train + dq_qnet_backward_tc against the torch network with the same roundings (tests/qnet_util.py;
+    the emulated test of the same name explains the reference).  Tolerance: 1e-2 of each gradient tensor's norm (dY and the column
+    gradients enter the GEMMs as bf16), Q within 2e-3."""
+    import torch
+    from deepq_decoding_b200.qnet import QNetwork
+    from qnet_util import Bf16SimQNet, dropout_mask
+    cc, ff, channels, A, B = cfg
+    q = QNetwork(cc, ff, (channels, 11, 11), A, dueling=True, max_batch=B, seed=7)
+    conv, dense = q.get_keras_weights()
+    rng = np.random.default_rng(3)
+    for _, b in conv + dense:
+        b += rng.standard_normal(b.shape).astype(np.float32) * 0.05
+    q.set_keras_weights(conv, dense)
+    net = Bf16SimQNet(conv, dense, strides=[l[2] for l in cc])
+    boards = random_boards(B, channels, 2, density=0.2)
+    dq = rng.standard_normal((B, A)).astype(np.float32)
+    seed = 0x1234500077
+    masks = [torch.tensor(dropout_mask(B, u, r, seed, i)) if r > 0 else None for i, (u, r) in enumerate(ff)]
+    got_q = q.forward(boards, train=True, dropout_seed=seed, precision="bf16").cpu().numpy()
+    want_q = net.forward(boards, dropout_masks=masks)
+    assert np.abs(got_q - want_q.detach().numpy()).max() < 2e-3
+    grads = q.backward(torch.tensor(dq).cuda(), precision="bf16")
+    (want_q * torch.tensor(dq)).sum().backward()
+    g = grads.cpu().numpy()
+    assert np.isfinite(g).all()
+    perm = q._flatten_perm()
+    for t, ((wo, bo, K, N), (kt, bt)) in enumerate(zip(q.layout, net.conv + net.dense)):
+        if t < len(cc):
+            want_w = kt.grad.permute(2, 3, 1, 0).reshape(K, N).numpy()
+        else:
+            want_w = kt.grad.numpy()
+            if t == len(cc):
+                want_w = want_w[perm]
+        got_w, got_b, want_b = g[wo:wo + K * N].reshape(K, N), g[bo:bo + N], bt.grad.numpy()
+        assert np.linalg.norm(got_w - want_w) <= 1e-2 * np.linalg.norm(want_w) + 1e-6, "kernel grad of tensor %d" % t
+        assert np.linalg.norm(got_b - want_b) <= 1e-2 * np.linalg.norm(want_b) + 1e-6, "bias grad of tensor %d" % t
+    # the fp32 path's gradient of the same batch: same direction (ReLU branches of near-zero pre-activations may differ)
+    q.forward(boards, train=True, dropout_seed=seed)
+    g32 = q.backward(torch.tensor(dq).cuda()).cpu().numpy()
+    cos = float(np.dot(g, g32) / (np.linalg.norm(g) * np.linalg.norm(g32)))
+    assert cos > 0.99, cos
+    q.close()
+
+
+def test_bf16_training_learns_like_fp32():
+    """The same short fit in both update precisions ends at comparable greedy lifetimes."""
+    from deepq_decoding_b200 import agents as A
+    from deepq_decoding_b200.envs import VecSurfaceCodeEnv
+    lifetimes = {}
+    for tp in ("fp32", "bf16"):
+        env = VecSurfaceCodeEnv(5, 0.007, 0.007, "X", False, 5, None, n_envs=2048, seed=5)
+        spec = A.build_convolutional_nn(REF_CC, REF_FF, env.observation_space.shape, env.num_actions)
+        pol = A.LinearAnnealedPolicy(A.EpsGreedyQPolicy(masked_greedy=False), attr="eps", value_max=1.0, value_min=0.05, value_test=0.0, nb_steps=1_000_000)
+        dqn = A.DQNAgent(model=spec, nb_actions=env.num_actions, memory=A.SequentialMemory(limit=200 * 2048), nb_steps_warmup=20_000,
+                         target_model_update=50_000, policy=pol, test_policy=A.GreedyQPolicy(masked_greedy=True), gamma=0.99,
+                         enable_dueling_network=True, batch_size=1024, act_precision="bf16", target_precision="bf16", train_precision=tp, seed=3)
+        dqn.compile(A.Adam(lr=1e-4), max_envs=2048)
+        dqn.fit(env, nb_steps=3_000_000, verbose=0)
+        assert bool(np.isfinite(dqn.model.params.cpu().numpy()).all())
+        lifetimes[tp] = float(np.mean(dqn.test(env, nb_episodes=2048, verbose=0).history["episode_lifetime"]))
+        env.close()
+    assert lifetimes["bf16"] > 0.6 * lifetimes["fp32"], lifetimes
