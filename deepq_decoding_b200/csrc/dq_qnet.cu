@@ -857,24 +857,27 @@ extern "C" int dq_replay_sample(const uint64_t* ring_obs, const int32_t* ring_ac
 // ------------------------------------------------------------------------------------------------ folded head (acting)
 // The layers after the last hidden dense layer are all linear: Dense(K -> A) (Function_Library.py:338-377), keras-rl's dueling
 // Dense(A -> A+1) and the 'avg' combine Q_a = y_0 + y_{a+1} - mean_a' y_{a'+1}.  For inference they are ONE affine map
-// Q = h * Wf + bf.  Thread r < K builds row r of Wf [K][A]; thread r == K builds bf.
+// Q = h * Wf + bf.
 namespace dq {
-__global__ void fold_head_kernel(const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ W3,
-                                 const float* __restrict__ b3, int K, int A, float* __restrict__ Wf, float* __restrict__ bf) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128)
+fold_head_kernel(const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ W3,
+                 const float* __restrict__ b3, int K, int A, float* __restrict__ Wf, float* __restrict__ bf) {
+    // one warp per row r (r < K: row r of Wf [K][A]; r == K: bf); lane = column c of the dueling layer (c = 0: state value, c = 1 + a: advantage a)
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (r > K) return;
-    const float* x = r < K ? W2 + (size_t)r * A : b2;          // the row of Dense(K -> A) this thread pushes through the head
+    const float* x = r < K ? W2 + (size_t)r * A : b2;          // the row of Dense(K -> A) this warp pushes through the head
     float* out = r < K ? Wf + (size_t)r * A : bf;
-    float y0 = r < K ? 0.f : b3[0], mean = 0.f;
-    for (int m = 0; m < A; ++m) y0 += x[m] * W3[(size_t)m * (A + 1)];
-    for (int a = 0; a < A; ++a) {
-        float y = r < K ? 0.f : b3[1 + a];
-        for (int m = 0; m < A; ++m) y += x[m] * W3[(size_t)m * (A + 1) + 1 + a];
-        out[a] = y;
-        mean += y;
+    float y0 = 0.f, sum = 0.f;
+    for (int c = lane; c <= A; c += 32) {
+        float y = r < K ? 0.f : b3[c];
+        for (int m = 0; m < A; ++m) y = fmaf(x[m], W3[(size_t)m * (A + 1) + c], y);
+        if (c == 0) y0 = y;
+        else { out[c - 1] = y; sum += y; }
     }
-    mean /= (float)A;
-    for (int a = 0; a < A; ++a) out[a] = y0 + out[a] - mean;
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    y0 = __shfl_sync(0xffffffffu, y0, 0);
+    const float mean = sum / (float)A;
+    for (int c = lane; c <= A; c += 32) if (c >= 1) out[c - 1] = y0 + out[c - 1] - mean;      // each lane re-reads only what it wrote
 }
 }  // namespace dq
 
@@ -884,7 +887,7 @@ extern "C" int dq_qnet_fold_head(const dq_qnet* h, const float* params, float* w
     if (!c.dueling || c.n_fc < 2) return qfail(DQ_EINVAL, "the network has no dueling head to fold");
     const int i2 = c.n_fc - 2, i3 = c.n_fc - 1, t2 = c.n_conv + i2, t3 = c.n_conv + i3, K = c.fc_in[i2];
     if (c.fc_out[i2] != c.A || c.fc_in[i3] != c.A || c.fc_out[i3] != c.A + 1) return qfail(DQ_EINVAL, "unexpected head shape");
-    fold_head_kernel<<<(unsigned)((K + 1 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(params + c.w_off[t2], params + c.b_off[t2], params + c.w_off[t3],
+    fold_head_kernel<<<(unsigned)((K + 1 + 3) / 4), 128, 0, (cudaStream_t)stream>>>(params + c.w_off[t2], params + c.b_off[t2], params + c.w_off[t3],
                                                                                       params + c.b_off[t3], K, c.A, w_out, b_out);
     count_launch();
     QCUDA(cudaGetLastError());
@@ -1387,7 +1390,7 @@ head_dueling_kernel(const float* __restrict__ x, const float* __restrict__ W, co
 //   im2colT      A_j^T [Kpad][Mpad] (bf16): the layer's patch matrix, transposed (layer 1: straight from the packed bits)
 //   tc_dw        dW_j[K][N] += A_j^T x dYT^T   -- contraction over the M = batch x positions rows, split over CTAs (grid.z), fp32
 //                atomics into the caller's gradient buffer
-//   tc_gemm      dCol_j[M][K] = dYb x W_j^T    -- the forward kernel with W_j's bf16 copy [K][Npad] as the "transposed weight"
+//   tc_gemm      dCol_j[M][K] = dYb x W_j^T    -- the forward kernel with W_j's bf16 copy [K][Npad] (staged by dq_qnet_prepare_tc) as the "transposed weight"
 // Both GEMM operands are K-major for tcgen05 because the transposes are materialised (bf16, a few tens of MB at batch 4096).
 // fp32 master weights, fp32 accumulation in TMEM, fp32 gradients / Adam: the usual mixed-precision recipe.
 
@@ -1490,30 +1493,38 @@ tc_dw_kernel(const __nv_bfloat16* __restrict__ At, long long lda, const __nv_bfl
 // [tcgen05 kernels: end]
 
 // A^T[k][m] (bf16, rows 0..Kpad-1, columns 0..Mpad-1, zero outside K x M) of a patch matrix over a channels-last bf16 activation.
-// 64 x 64 tiles through shared memory: rows of A are read along k (contiguous within a patch segment), written along m.
+// 64 x 64 tiles through shared memory.  cin % 8 == 0 (tc_check), so 8 consecutive k of a row are 16 contiguous bytes of the input:
+// a thread loads 8 k of one row, then stores 8 m of one k.
 __global__ void __launch_bounds__(256)
 im2colT_kernel(const __nv_bfloat16* __restrict__ X, Patch g, long long M, int K, __nv_bfloat16* __restrict__ At, long long lda) {
-    __shared__ __nv_bfloat16 tile[64][66];
+    __shared__ __align__(16) unsigned short tile[64][72];        // [k][m]; rows of 144 bytes keep the 16-byte reads of phase 2 aligned
     __shared__ long long rowoff[64];
-    __shared__ int coloff[64];
+    __shared__ int coloff[8];
     const int tid = threadIdx.x;
     const long long m0 = (long long)blockIdx.x * 64;
     const int k0 = blockIdx.y * 64;
     if (tid < 64) rowoff[tid] = (m0 + tid < M) ? patch_row(g, m0 + tid) : -1;
-    else if (tid < 128) coloff[tid - 64] = (k0 + tid - 64 < K) ? patch_col(g, k0 + tid - 64) : -1;
+    else if (tid < 72) coloff[tid - 64] = (k0 + (tid - 64) * 8 < K) ? patch_col(g, k0 + (tid - 64) * 8) : -1;
     __syncthreads();
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        const int e = tid + i * 256, mm = e >> 6, kk = e & 63;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int item = tid + i * 256, mm = item >> 3, kc = item & 7;
         const long long ro = rowoff[mm];
-        const int co = coloff[kk];
-        tile[kk][mm] = (ro >= 0 && co >= 0) ? X[ro + co] : __float2bfloat16(0.f);
+        const int co = coloff[kc];
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (ro >= 0 && co >= 0) v = *reinterpret_cast<const uint4*>(X + ro + co);
+        const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            tile[kc * 8 + 2 * j][mm] = (unsigned short)(w[j] & 0xFFFFu);
+            tile[kc * 8 + 2 * j + 1][mm] = (unsigned short)(w[j] >> 16);
+        }
     }
     __syncthreads();
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        const int e = tid + i * 256, kk = e >> 6, mm = e & 63;
-        At[(long long)(k0 + kk) * lda + m0 + mm] = tile[kk][mm];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int item = tid + i * 256, kk = item >> 3, mc = item & 7;
+        *reinterpret_cast<uint4*>(At + (long long)(k0 + kk) * lda + m0 + mc * 8) = *reinterpret_cast<const uint4*>(&tile[kk][mc * 8]);
     }
 }
 // Layer 1: the same matrix straight from the packed observation bits, rows in the parameter order k = tap * C + layer.
@@ -1537,6 +1548,13 @@ im2colT_bits_kernel(const u64* __restrict__ packed, long long stride, ConvL L, i
 //   src_mode 0: fp32 [M][N];  1: bf16 [M][N];  2: col2im -- G[m = (b, iy, ix)][c] = sum over the taps (ky, kx) of the layer ABOVE that
 //   read this cell of dcol[(b, oy, ox)][(ky*ksz + kx)*N + c]  (up: the patch geometry of the layer above, Kup its K)
 struct DySrc { const void* p; int mode; Patch up; int Kup; };
+__device__ __forceinline__ void bf16x8_to_float(const uint4& v, float* f) {
+    const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { f[2 * j] = __uint_as_float(w[j] << 16); f[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u); }
+}
+// 64 (rows m) x 64 (channels n) per CTA; a thread owns 8 consecutive channels of a row (N % 8 == 0 on the vector paths: one 16-byte load per
+// source, the cell geometry of the col2im gather computed once per 8 channels), then 8 consecutive rows of a channel of the transpose.
 __global__ void __launch_bounds__(256)
 prep_dy_kernel(DySrc src, const __nv_bfloat16* __restrict__ act, const float* __restrict__ mask, long long M, int N,
                __nv_bfloat16* __restrict__ dYb, int ldyb, __nv_bfloat16* __restrict__ dYT, long long ldyt, int rows_t,
@@ -1545,16 +1563,25 @@ prep_dy_kernel(DySrc src, const __nv_bfloat16* __restrict__ act, const float* __
     const int tid = threadIdx.x;
     const long long m0 = (long long)blockIdx.x * 64;
     const int n0 = blockIdx.y * 64;
-#pragma unroll 2
-    for (int i = 0; i < 16; ++i) {
-        const int e = tid + i * 256, mm = e >> 6, nn = e & 63;
+    const bool vec = (N & 7) == 0;
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {
+        const int item = tid + i * 256, mm = item >> 3, nn = (item & 7) * 8;
         const long long m = m0 + mm;
         const int n = n0 + nn;
-        float gval = 0.f;
+        float g[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = 0.f;
         if (m < M && n < N) {
-            if (src.mode == 0) gval = reinterpret_cast<const float*>(src.p)[m * N + n];
-            else if (src.mode == 1) gval = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src.p)[m * N + n]);
-            else {
+            if (src.mode == 0) {
+                const float* sp = reinterpret_cast<const float*>(src.p) + m * N + n;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (n + j < N) g[j] = sp[j];
+            } else if (src.mode == 1) {
+                const __nv_bfloat16* sp = reinterpret_cast<const __nv_bfloat16*>(src.p) + m * N + n;
+                if (vec) bf16x8_to_float(*reinterpret_cast<const uint4*>(sp), g);
+                else for (int j = 0; j < 8; ++j) if (n + j < N) g[j] = __bfloat162float(sp[j]);
+            } else {
                 const Patch& u = src.up;                         // this layer's output map is the upper layer's input map: side u.ih
                 const int cells = u.ih * u.ih;
                 const long long b = m / cells;
@@ -1570,22 +1597,55 @@ prep_dy_kernel(DySrc src, const __nv_bfloat16* __restrict__ act, const float* __
                         if (tx < 0 || tx % u.stride) continue;
                         const int ox = tx / u.stride;
                         if (ox >= u.oh) continue;
-                        gval += __bfloat162float(dc[((b * u.P + oy * u.oh + ox) * (long long)src.Kup) + (ky * u.ksz + kx) * N + n]);
+                        const __nv_bfloat16* sp = dc + ((b * u.P + oy * u.oh + ox) * (long long)src.Kup) + (ky * u.ksz + kx) * N + n;
+                        if (vec) {
+                            float t[8];
+                            bf16x8_to_float(*reinterpret_cast<const uint4*>(sp), t);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) g[j] += t[j];
+                        } else {
+                            for (int j = 0; j < 8; ++j) if (n + j < N) g[j] += __bfloat162float(sp[j]);
+                        }
                     }
                 }
             }
-            if (act && !(__bfloat162float(act[m * N + n]) > 0.f)) gval = 0.f;
-            if (mask) gval *= mask[m * N + n];
+            if (act) {
+                float a8[8];
+                if (vec) bf16x8_to_float(*reinterpret_cast<const uint4*>(act + m * N + n), a8);
+                else for (int j = 0; j < 8; ++j) a8[j] = (n + j < N) ? __bfloat162float(act[m * N + n + j]) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (!(a8[j] > 0.f)) g[j] = 0.f;
+            }
+            if (mask) {
+                if (vec) {
+                    const float4 k0 = *reinterpret_cast<const float4*>(mask + m * N + n), k1 = *reinterpret_cast<const float4*>(mask + m * N + n + 4);
+                    g[0] *= k0.x; g[1] *= k0.y; g[2] *= k0.z; g[3] *= k0.w; g[4] *= k1.x; g[5] *= k1.y; g[6] *= k1.z; g[7] *= k1.w;
+                } else {
+                    for (int j = 0; j < 8; ++j) if (n + j < N) g[j] *= mask[m * N + n + j];
+                }
+            }
         }
-        const __nv_bfloat16 gb = __float2bfloat16(gval);
-        if (m < M && n < ldyb) dYb[m * ldyb + n] = gb;
-        tile[nn][mm] = __bfloat162float(gb);                     // the bias gradient sums what the GEMMs see
+        u32 pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat16 lo = __float2bfloat16(g[2 * j]), hi = __float2bfloat16(g[2 * j + 1]);
+            tile[nn + 2 * j][mm] = __bfloat162float(lo);         // the bias gradient sums what the GEMMs see
+            tile[nn + 2 * j + 1][mm] = __bfloat162float(hi);
+            pk[j] = (u32)__bfloat16_as_ushort(lo) | ((u32)__bfloat16_as_ushort(hi) << 16);
+        }
+        if (m < M && n < ldyb) *reinterpret_cast<uint4*>(dYb + m * ldyb + n) = make_uint4(pk[0], pk[1], pk[2], pk[3]);      // ldyb % 64 == 0
     }
     __syncthreads();
-#pragma unroll 2
-    for (int i = 0; i < 16; ++i) {
-        const int e = tid + i * 256, nn = e >> 6, mm = e & 63;
-        if (n0 + nn < rows_t && m0 + mm < ldyt) dYT[(long long)(n0 + nn) * ldyt + m0 + mm] = __float2bfloat16(tile[nn][mm]);
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {
+        const int item = tid + i * 256, nn = item >> 3, mm = (item & 7) * 8;
+        if (n0 + nn < rows_t && m0 + mm < ldyt) {                // ldyt % 64 == 0: the 8 columns are inside the row
+            u32 pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                pk[j] = (u32)__bfloat16_as_ushort(__float2bfloat16(tile[nn][mm + 2 * j])) | ((u32)__bfloat16_as_ushort(__float2bfloat16(tile[nn][mm + 2 * j + 1])) << 16);
+            *reinterpret_cast<uint4*>(dYT + (long long)(n0 + nn) * ldyt + m0 + mm) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
     }
     if (tid < 64 && n0 + tid < N) {
         float sum = 0.f;
@@ -1593,13 +1653,6 @@ prep_dy_kernel(DySrc src, const __nv_bfloat16* __restrict__ act, const float* __
         for (int mm = 0; mm < 64; ++mm) sum += tile[tid][mm];
         if (sum != 0.f) atomicAdd(db + n0 + tid, sum);
     }
-}
-// fp32 W[K][N] -> bf16 Wb[rows][Npad] (same orientation, zero padded): the "transposed weight" of the dX GEMM
-__global__ void prep_wb_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wb, int K, int N, int rows, int Npad) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * Npad) return;
-    const int k = i / Npad, n = i - k * Npad;
-    Wb[i] = __float2bfloat16((k < K && n < N) ? W[(size_t)k * N + n] : 0.f);
 }
 // training-mode dropout on a bf16 activation: the masks of dropout_kernel (same Philox words), kept in fp32 for the backward pass
 __global__ void dropout_bf16_kernel(__nv_bfloat16* __restrict__ Y, float* __restrict__ mask, long long n, float rate, u32 k0, u32 k1, u32 tag) {
@@ -1616,15 +1669,24 @@ __global__ void dropout_bf16_kernel(__nv_bfloat16* __restrict__ Y, float* __rest
     }
 }
 
-// fp32 [K][N] -> bf16 [Npad][Kpad] (transposed, zero padded)
-// perm_C > 0 (layer 1): our K order is (layer, tap) while W's rows are (tap, layer): k' = ci*T + t  <-  k = t*C + ci
-__global__ void prep_wt_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt, int K, int N, int Kpad, int Npad, int perm_C) {
+// Every bf16 weight copy of the network in ONE launch (grid.y = job), from fp32 W [K][N]:
+//   mode 0: transposed, zero padded [d0 = Npad][d1 = Kpad] (the forward GEMMs' B operand); perm_C > 0 (layer 1): our K order is
+//           (layer, tap) while W's rows are (tap, layer): k' = ci*T + t  <-  k = t*C + ci
+//   mode 1: same orientation, zero padded [d0 = rows][d1 = Npad] (the "transposed weight" of the backward dX GEMM)
+struct PrepJob { const float* W; __nv_bfloat16* out; int K, N, d0, d1, mode, perm_C; };
+struct PrepJobs { PrepJob j[2 * (kMaxConv + kMaxDense + 2) + 1]; };
+__global__ void prep_weights_kernel(const PrepJobs jobs) {
+    const PrepJob& jb = jobs.j[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= Npad * Kpad) return;
-    const int n = i / Kpad, k = i - n * Kpad;
-    int ks = k;
-    if (perm_C > 0 && k < K) { const int T = K / perm_C, ci = k / T, t = k - ci * T; ks = t * perm_C + ci; }
-    Wt[i] = __float2bfloat16((n < N && k < K) ? W[(size_t)ks * N + n] : 0.f);
+    if (i >= jb.d0 * jb.d1) return;
+    const int r = i / jb.d1, q = i - r * jb.d1;
+    float v = 0.f;
+    if (jb.mode == 0) {                                         // r = n, q = k
+        int ks = q;
+        if (jb.perm_C > 0 && q < jb.K) { const int T = jb.K / jb.perm_C, ci = q / T, t = q - ci * T; ks = t * jb.perm_C + ci; }
+        if (r < jb.N && q < jb.K) v = jb.W[(size_t)ks * jb.N + r];
+    } else if (r < jb.K && q < jb.N) v = jb.W[(size_t)r * jb.N + q];      // r = k, q = n
+    jb.out[i] = __float2bfloat16(v);
 }
 
 }  // namespace dq
@@ -1633,6 +1695,7 @@ struct dq_qnet_tc {                     // bf16 buffers of the tensor-core path,
     // tensor-core layer j = tensor j of the flat layout: conv1 .. conv_n, hidden dense .., Dense(num_actions)
     __nv_bfloat16* act[kMaxConv + kMaxDense + 2];      // act[j] = bf16 output of layer j (not for the last one)
     __nv_bfloat16* wt[kMaxConv + kMaxDense + 2];
+    __nv_bfloat16* wb[kMaxConv + kMaxDense + 2];       // W itself in bf16, [K padded to the dX tile][N padded to 64]: the "transposed weight" of the backward dX GEMM
     int kpad[kMaxConv + kMaxDense + 2], npad[kMaxConv + kMaxDense + 2], bn[kMaxConv + kMaxDense + 2];
     // Dense(num_actions) + dueling head folded into one affine map (dq_qnet_fold_head; DQ_QNET_FOLD_HEAD=0 turns it off); the last
     // tensor-core layer then multiplies with fold_wt / fold_b and writes Q itself
@@ -1647,7 +1710,7 @@ static bool tc_fold_enabled() {
 static void tc_free(dq_qnet* h) {
     dq_qnet_tc* tc = (dq_qnet_tc*)h->tc;
     if (!tc) return;
-    for (int i = 0; i < kMaxConv + kMaxDense + 2; ++i) { cudaFree(tc->act[i]); cudaFree(tc->wt[i]); }
+    for (int i = 0; i < kMaxConv + kMaxDense + 2; ++i) { cudaFree(tc->act[i]); cudaFree(tc->wt[i]); cudaFree(tc->wb[i]); }
     cudaFree(tc->fold_w); cudaFree(tc->fold_b); cudaFree(tc->fold_wt);
     tcb_free(tc->bwd);
     delete tc;
@@ -1674,6 +1737,10 @@ static dq_qnet_tc* tc_of(dq_qnet* h) {
         tc->npad[j] = (N + tc->bn[j] - 1) / tc->bn[j] * tc->bn[j];
         err = cudaMalloc(&tc->wt[j], (size_t)tc->npad[j] * tc->kpad[j] * sizeof(__nv_bfloat16));
         if (err == cudaSuccess && j + 1 < n_tc) err = cudaMalloc(&tc->act[j], (size_t)h->max_batch * rows * N * sizeof(__nv_bfloat16));
+        if (err == cudaSuccess && j > 0) {
+            const int bn_dx = K <= 32 ? 32 : (K <= 64 ? 64 : 128);
+            err = cudaMalloc(&tc->wb[j], (size_t)((K + bn_dx - 1) / bn_dx * bn_dx) * ((N + 63) / 64 * 64) * sizeof(__nv_bfloat16));
+        }
     }
     if (err == cudaSuccess && tc_fold_enabled() && c.dueling && c.n_fc >= 2) {
         const int j = n_tc - 1, K = c.fc_in[c.n_fc - 2];
@@ -1748,12 +1815,18 @@ extern "C" int dq_qnet_prepare_tc(dq_qnet* h, const float* params, dq_stream str
     const QCfg& c = h->c;
     dq_qnet_tc* tc = tc_of(h);
     if (!tc) return qfail(DQ_ECUDA, "allocating the bf16 buffers failed");
+    PrepJobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
+    int nj = 0, max_total = 0;
+    auto add = [&](const float* W, __nv_bfloat16* out, int K, int N, int d0, int d1, int mode, int perm_C) {
+        jobs.j[nj++] = PrepJob{W, out, K, N, d0, d1, mode, perm_C};
+        max_total = std::max(max_total, d0 * d1);
+    };
     for (int j = 0; j < tc_layers(c); ++j) {
         int K, N; long long rows;
         tc_shape(c, j, K, N, rows);
-        const int total = tc->npad[j] * tc->kpad[j];
-        prep_wt_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params + c.w_off[j], tc->wt[j], K, N, tc->kpad[j], tc->npad[j], j == 0 ? c.C : 0);
-        count_launch();
+        add(params + c.w_off[j], tc->wt[j], K, N, tc->npad[j], tc->kpad[j], 0, j == 0 ? c.C : 0);
+        if (j > 0) { const int bn_dx = K <= 32 ? 32 : (K <= 64 ? 64 : 128); add(params + c.w_off[j], tc->wb[j], K, N, (K + bn_dx - 1) / bn_dx * bn_dx, (N + 63) / 64 * 64, 1, 0); }
     }
     if (tc->folded) {
         const int j = tc_layers(c) - 1;
@@ -1761,10 +1834,10 @@ extern "C" int dq_qnet_prepare_tc(dq_qnet* h, const float* params, dq_stream str
         tc_shape(c, j, K, N, rows);
         rc = dq_qnet_fold_head(h, params, tc->fold_w, tc->fold_b, stream);
         if (rc) return rc;
-        const int total = tc->npad[j] * tc->kpad[j];
-        prep_wt_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tc->fold_w, tc->fold_wt, K, N, tc->kpad[j], tc->npad[j], 0);
-        count_launch();
+        add(tc->fold_w, tc->fold_wt, K, N, tc->npad[j], tc->kpad[j], 0, 0);
     }
+    prep_weights_kernel<<<dim3((max_total + 255) / 256, nj), 256, 0, (cudaStream_t)stream>>>(jobs);
+    count_launch();
     QCUDA(cudaGetLastError());
     return DQ_OK;
 }
@@ -1848,7 +1921,7 @@ extern "C" int dq_qnet_forward_tc_train(dq_qnet* h, const float* params, const u
 // ---- bf16 backward --------------------------------------------------------------------------------------------------------------
 struct dq_qnet_tcb {                    // scratch of dq_qnet_backward_tc, sized for `cap` samples, grown on demand
     long long cap;
-    __nv_bfloat16 *at, *dyb, *dyt, *dcol, *wb;
+    __nv_bfloat16 *at, *dyb, *dyt, *dcol;
 };
 struct TcbGeom { int K, N; long long rows, M, Mpad; int rowsA, bn_dw, rows_t, ldyb, bn_dx, npad_dx; };
 static int bn_for(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : 128); }
@@ -1864,7 +1937,7 @@ static TcbGeom tcb_geom(const QCfg& c, int j, long long batch) {
 }
 static void tcb_free(dq_qnet_tcb* b) {
     if (!b) return;
-    cudaFree(b->at); cudaFree(b->dyb); cudaFree(b->dyt); cudaFree(b->dcol); cudaFree(b->wb);
+    cudaFree(b->at); cudaFree(b->dyb); cudaFree(b->dyt); cudaFree(b->dcol);
     delete b;
 }
 static dq_qnet_tcb* tcb_of(dq_qnet* h, long long batch) {
@@ -1873,13 +1946,13 @@ static dq_qnet_tcb* tcb_of(dq_qnet* h, long long batch) {
     tcb_free(tc->bwd);
     tc->bwd = nullptr;
     const QCfg& c = h->c;
-    size_t n_at = 0, n_dyb = 0, n_dyt = 0, n_dcol = 0, n_wb = 0;
+    size_t n_at = 0, n_dyb = 0, n_dyt = 0, n_dcol = 0;
     for (int j = 0; j < tc_layers(c); ++j) {
         const TcbGeom g = tcb_geom(c, j, batch);
         n_at = std::max<size_t>(n_at, (size_t)g.rowsA * (size_t)g.Mpad);
         n_dyb = std::max<size_t>(n_dyb, (size_t)g.Mpad * (size_t)g.ldyb);
         n_dyt = std::max<size_t>(n_dyt, (size_t)g.rows_t * (size_t)g.Mpad);
-        if (j > 0) { n_dcol = std::max<size_t>(n_dcol, (size_t)g.M * (size_t)g.K); n_wb = std::max<size_t>(n_wb, (size_t)g.npad_dx * (size_t)g.ldyb); }
+        if (j > 0) n_dcol = std::max<size_t>(n_dcol, (size_t)g.M * (size_t)g.K);
     }
     dq_qnet_tcb* b = new dq_qnet_tcb();
     memset(b, 0, sizeof(*b));
@@ -1887,7 +1960,6 @@ static dq_qnet_tcb* tcb_of(dq_qnet* h, long long batch) {
     if (err == cudaSuccess) err = cudaMalloc(&b->dyb, n_dyb * 2);
     if (err == cudaSuccess) err = cudaMalloc(&b->dyt, n_dyt * 2);
     if (err == cudaSuccess) err = cudaMalloc(&b->dcol, std::max<size_t>(n_dcol, 8) * 2);
-    if (err == cudaSuccess) err = cudaMalloc(&b->wb, std::max<size_t>(n_wb, 8) * 2);
     if (err != cudaSuccess) { tcb_free(b); return nullptr; }
     b->cap = batch;
     tc->bwd = b;
@@ -1901,8 +1973,9 @@ static int launch_tc_dw(const __nv_bfloat16* At, long long lda, const __nv_bfloa
     QCUDA(cudaFuncSetAttribute(tc_dw_kernel<BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int kb_total = (int)(lda / 64);
     const int tiles = (rowsA / 128) * (rows_t / BN);
-    // the contraction (batch x positions) is cut into slices over grid.z: about two CTAs per SM, at least 8 chunks of 64 per CTA
-    int z = std::max(1, std::min(kb_total / 8, (2 * 148 + tiles - 1) / tiles));
+    // the contraction (batch x positions) is cut into slices over grid.z: about two CTAs per SM, at least 16 chunks of 64 per CTA (measured at batch 4096: 4 -> 556 us per update, 8 -> 536, 16 -> 529, 32 -> 554, 64 -> 623)
+    static const int min_chunks = [] { const char* e = getenv("DQ_TC_DW_MINCHUNKS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
+    int z = std::max(1, std::min(kb_total / min_chunks, (2 * 148 + tiles - 1) / tiles));
     const int per = (kb_total + z - 1) / z;
     z = (kb_total + per - 1) / per;
     tc_dw_kernel<BN, S><<<dim3(rowsA / 128, rows_t / BN, z), 128, smem, st>>>(At, lda, Bt, ldb, D, ldd, R, N, kb_total, per);
@@ -1980,12 +2053,9 @@ extern "C" int dq_qnet_backward_tc(dq_qnet* h, const float* params, const uint64
         if (j == 0) break;
         // 3. column gradient dCol[M][K] = dY x W^T: the forward GEMM kernel with W's bf16 copy [K][N] as its "transposed weight"
         {
-            const int total = g.npad_dx * g.ldyb;
-            prep_wb_kernel<<<(total + 255) / 256, 256, 0, st>>>(params + c.w_off[j], sb->wb, g.K, g.N, g.npad_dx, g.ldyb);
-            count_launch();
             TcArgs a;
             memset(&a, 0, sizeof(a));
-            a.X = sb->dyb; a.g = dense_patch(g.ldyb); a.Wt = sb->wb; a.bias = nullptr; a.Y = sb->dcol; a.ldy = g.K; a.out_bf16 = 1; a.relu = 0;
+            a.X = sb->dyb; a.g = dense_patch(g.ldyb); a.Wt = tc->wb[j]; a.bias = nullptr; a.Y = sb->dcol; a.ldy = g.K; a.out_bf16 = 1; a.relu = 0;
             a.M = g.M; a.N = g.K; a.K = g.N; a.Kpad = g.ldyb;
             rc = launch_tc_bn<0>(a, g.bn_dx, g.npad_dx, st);
             if (rc) return rc;

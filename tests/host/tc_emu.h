@@ -17,5 +17,7 @@ static inline __nv_bfloat16 __float2bfloat16(float f) {
     return r;
 }
 static inline float __bfloat162float(__nv_bfloat16 b) { uint32_t u = (uint32_t)b.x << 16; float f; memcpy(&f, &u, 4); return f; }
+static inline unsigned short __bfloat16_as_ushort(__nv_bfloat16 b) { return b.x; }
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 struct alignas(16) float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
