@@ -906,6 +906,7 @@ extern "C" int dq_qnet_fold_head(const dq_qnet* h, const float* params, float* w
 // bias + ReLU + convert epilogue.  Several CTAs are resident per SM, so one CTA's copies overlap another's MMAs.
 // SASS evidence: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTCBAR (commit), LDGSTS (cp.async).
 #include <cuda_bf16.h>
+#include <cuda.h>           // CUtensorMap (types only: the encoder is looked up through the runtime)
 
 namespace dq {
 
@@ -1490,6 +1491,117 @@ tc_dw_kernel(const __nv_bfloat16* __restrict__ At, long long lda, const __nv_bfl
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((u32)(BN < 32 ? 32 : BN)) : "memory");
 }
 
+
+// The same GEMM with both operand tiles brought in by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B tensor maps: the hardware writes the
+// K-major swizzle atoms the UMMA descriptors expect) and a warp-specialised pipeline: one producer thread arms a stage's "full" mbarrier
+// with the stage's byte count and issues the two tile loads, one MMA thread waits for "full", issues the four tcgen05.mma of the chunk
+// and commits them to the stage's "empty" mbarrier; all four warps drain the accumulator at the end.  No thread of the CTA touches the
+// operand bytes.  SASS: UTMALDG, UTCHMMA, UTCBAR, SYNCS.
+struct Tmap2D { CUtensorMap m; };
+// bf16 matrix [rows][ld] (ld % 64 == 0, every column readable) as a tiled tensor map with boxes of 64 columns x box_rows rows
+static bool make_tmap_2d(Tmap2D* out, const __nv_bfloat16* base, long long rows, long long ld, int box_rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static const EncodeFn fn = [] {         // the driver entry point through the runtime: the library does not link libcuda
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return (EncodeFn)f;
+    }();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__nv_bfloat16)};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return fn(&out->m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+__device__ __forceinline__ void tma_load_2d(u32 smem_dst, const Tmap2D* map, int c_inner, int c_outer, u64* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer) : "memory");
+}
+template <int BN, int S>
+__global__ void __launch_bounds__(128)
+tc_dw_tma_kernel(const __grid_constant__ Tmap2D ta, const __grid_constant__ Tmap2D tb, float* __restrict__ D, int ldd, int R, int N,
+                 int kb_total, int kb_per_cta) {
+    constexpr u32 STAGE = 16384u + (u32)BN * 128u;
+    extern __shared__ unsigned char tc_raw[];
+    __shared__ alignas(8) u64 bar_full[S], bar_empty[S], bar_accum;
+    __shared__ u32 tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const u32 s_base = (smem_u32(tc_raw) + 1023u) & ~1023u;
+    const int r0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+    const int kb0 = blockIdx.z * kb_per_cta, KB = min(kb_per_cta, kb_total - kb0);
+    if (KB <= 0) return;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((u32)(BN < 32 ? 32 : BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        mbar_init(&bar_accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();                                        // the barriers are next touched by the async proxy (TMA, tcgen05.commit)
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const u32 tmem = tmem_slot;
+    if (warp == 0) {
+        if (lane == 0) {                                            // ---- producer
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % S;
+                if (kb >= S) mbar_wait_or_trap(&bar_empty[s], (u32)((kb / S - 1) & 1));      // the MMAs that read this stage have completed
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar_full[s])), "r"(STAGE) : "memory");
+                const u32 sA = s_base + (u32)s * STAGE;
+                tma_load_2d(sA, &ta, (kb0 + kb) * 64, r0, &bar_full[s]);
+                tma_load_2d(sA + 16384u, &tb, (kb0 + kb) * 64, n0, &bar_full[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {                                            // ---- MMA issuer
+            const u32 idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(BN >> 3) << 17) | ((u32)(128 >> 4) << 24);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % S;
+                mbar_wait_or_trap(&bar_full[s], (u32)((kb / S) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const u32 sA = s_base + (u32)s * STAGE;
+                const uint64_t da = umma_smem_desc(sA), db = umma_smem_desc(sA + 16384u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_empty[s])) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_accum)) : "memory");
+        }
+        __syncwarp();
+    }
+    mbar_wait_or_trap(&bar_accum, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const u32 taddr = tmem + ((u32)(warp * 32) << 16);
+    const int row = r0 + tid;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+        u32 v[16];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                     : "r"(taddr + (u32)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < R) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float f = __uint_as_float(v[j]);
+                if (n0 + c0 + j < N && f != 0.f) atomicAdd(D + (long long)row * ldd + n0 + c0 + j, f);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((u32)(BN < 32 ? 32 : BN)) : "memory");
+}
 // [tcgen05 kernels: end]
 
 // A^T[k][m] (bf16, rows 0..Kpad-1, columns 0..Mpad-1, zero outside K x M) of a patch matrix over a channels-last bf16 activation.
@@ -1978,7 +2090,15 @@ static int launch_tc_dw(const __nv_bfloat16* At, long long lda, const __nv_bfloa
     int z = std::max(1, std::min(kb_total / min_chunks, (2 * 148 + tiles - 1) / tiles));
     const int per = (kb_total + z - 1) / z;
     z = (kb_total + per - 1) / per;
-    tc_dw_kernel<BN, S><<<dim3(rowsA / 128, rows_t / BN, z), 128, smem, st>>>(At, lda, Bt, ldb, D, ldd, R, N, kb_total, per);
+    static const bool use_tma = [] { const char* e = getenv("DQ_TC_DW_TMA"); return !(e && e[0] == '0'); }();
+    if (use_tma) {
+        Tmap2D ta, tb;
+        if (!make_tmap_2d(&ta, At, rowsA, lda, 128) || !make_tmap_2d(&tb, Bt, rows_t, ldb, BN)) return qfail(DQ_ECUDA, "cuTensorMapEncodeTiled failed");
+        QCUDA(cudaFuncSetAttribute(tc_dw_tma_kernel<BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_dw_tma_kernel<BN, S><<<dim3(rowsA / 128, rows_t / BN, z), 128, smem, st>>>(ta, tb, D, ldd, R, N, kb_total, per);
+    } else {
+        tc_dw_kernel<BN, S><<<dim3(rowsA / 128, rows_t / BN, z), 128, smem, st>>>(At, lda, Bt, ldb, D, ldd, R, N, kb_total, per);
+    }
     count_launch();
     return DQ_OK;
 }
