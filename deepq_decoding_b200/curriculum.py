@@ -37,7 +37,8 @@ def train_point(spec_args, error_model, p, cfg, n_envs, steps, init=None, test_e
                      target_model_update=int(cfg.get("target_network_update_freq", 5000) * cfg.get("target_scale", 40)), policy=policy,
                      test_policy=A.GreedyQPolicy(masked_greedy=True), gamma=cfg.get("gamma", 0.99), enable_dueling_network=True,
                      batch_size=int(cfg.get("batch_size", 1024)), updates_per_step=int(cfg.get("updates_per_step", 2)), seed=seed,
-                     device=device, act_precision=cfg.get("act_precision", "bf16"))
+                     device=device, act_precision=cfg.get("act_precision", "bf16"), target_precision=cfg.get("target_precision", "fp32"),
+                     train_precision=cfg.get("train_precision", "fp32"))
     dqn.compile(A.Adam(lr=cfg.get("learning_rate", 1e-4)), max_envs=max(n_envs, test_episodes))
     if init is not None:
         dqn.model.params.copy_(init["params"].to(dqn.model.device))

@@ -34,6 +34,7 @@ ap.add_argument("--gamma", type=float, default=0.99)
 ap.add_argument("--seed", type=int, default=0)
 ap.add_argument("--act", default="bf16")
 ap.add_argument("--target", dest="target_prec", default="fp32", help="precision of the no-grad forwards inside an update")
+ap.add_argument("--train", dest="train_prec", default="fp32", help="precision of an update's forward / backward pass (bf16: tcgen05, fp32 master weights)")
 ap.add_argument("--test-episodes", type=int, default=8192)
 ap.add_argument("--curriculum", default="", help="p:steps,p:steps,... trained in order, carrying weights and replay memory over (tex:592-609)")
 ap.add_argument("--eps-max-continue", type=float, default=0.3)
@@ -45,7 +46,7 @@ spec = A.build_convolutional_nn([[64, 3, 2], [32, 2, 1], [32, 2, 1]], [[512, 0.2
 policy = A.LinearAnnealedPolicy(A.EpsGreedyQPolicy(masked_greedy=False), attr="eps", value_max=1.0, value_min=a.eps_min, value_test=0.0, nb_steps=a.eps_steps)
 dqn = A.DQNAgent(model=spec, nb_actions=env.num_actions, memory=A.SequentialMemory(limit=int(a.buffer)), nb_steps_warmup=int(a.warmup),
                  target_model_update=int(a.target), policy=policy, test_policy=A.GreedyQPolicy(masked_greedy=True), gamma=a.gamma,
-                 enable_dueling_network=True, batch_size=a.batch, updates_per_step=a.updates, seed=a.seed, act_precision=a.act, target_precision=a.target_prec)
+                 enable_dueling_network=True, batch_size=a.batch, updates_per_step=a.updates, seed=a.seed, act_precision=a.act, target_precision=a.target_prec, train_precision=a.train_prec)
 dqn.compile(A.Adam(lr=a.lr), max_envs=max(a.envs, a.test_episodes))
 phases = [(a.p, a.steps)] if not a.curriculum else [(float(x.split(":")[0]), float(x.split(":")[1])) for x in a.curriculum.split(",")]
 t0 = time.time()
