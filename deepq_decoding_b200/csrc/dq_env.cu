@@ -170,6 +170,19 @@ __device__ __forceinline__ void spin_pause(unsigned ns = 20) {
     __nanosleep(ns);
 #endif
 }
+// Programmatic dependent launch (single-step launches are queued with the attribute, see launch_env): the NEXT launch's CTAs may be
+// scheduled as soon as every CTA of this one has said so, and wait in griddepcontrol.wait -- before their first access to global
+// memory -- until this grid has completed and its writes are visible.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() {
+#ifndef DQ_EMU
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#ifndef DQ_EMU
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ u32 sm_id() {
 #ifdef DQ_EMU
     return blockIdx.x;
@@ -371,6 +384,20 @@ __device__ __forceinline__ void write_observations(const Smem& sm, const EnvPara
     }
 }
 
+// Words [w0, w1) of the tile's stream again (16-byte aligned tiles only): the span of a lattice that drew a fresh volume in a launch
+// whose observations were expanded BEFORE the step (see `early` in env_step_kernel).
+__device__ __forceinline__ void rewrite_observation_word(const Smem& sm, uint8_t* out, int vbytes, int w) {
+    const int g = w * 32, full = vbytes & ~31;
+    if (g >= vbytes) return;
+    const u32 word = sm.stream[w];
+    if (g < full) {
+        store_obs16(out + g, expand16(sm, word));
+        store_obs16(out + g + 16, expand16(sm, word >> 16));
+    } else {
+        for (int b = 0; b < vbytes - full; ++b) out[full + b] = (uint8_t)((word >> b) & 1u);
+    }
+}
+
 template <int D, bool RESET>
 __global__ void __launch_bounds__(Roles<D>::kThreads, DQ_MIN_BLOCKS)
 env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t* __restrict__ obs0,
@@ -390,24 +417,38 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     const int C = p.vd + p.layers;
     const int nvalid = max(0, min(kLpc, p.n - env0));
     const size_t np = (size_t)p.npad;
-    // built-in policy: every CTA reads the step index before its first barrier; the last CTA to finish advances it
-    const u32 step0 = policy_ctr ? *reinterpret_cast<volatile u32*>(policy_ctr) : 0u;
     // A rollout keeps the tile's volume queues in shared memory for the launch; a single step pops and refills the device-memory copy in place.
     const bool q_in_smem = ro.nsteps > 1;
+    // A single-step launch is one pass of the physics warp's dependent chain, and nothing of that chain needs the expansion table or the
+    // bit stream: there the physics warp (warp 0 of the default role placement) leaves the table and the placement to the other warps,
+    // ARRIVES at the prologue barrier instead of waiting at it, and starts its chain at once.
+    const bool phys_skip = (DQ_ROTATE == 0) && (DQ_PHYS_LAST == 0) && !q_in_smem;
+    const int ptid = phys_skip ? tid - 32 : tid, pthreads = phys_skip ? kThreads - 32 : kThreads;
+    // ---- prologue, part 1 (no global memory: may run while the previous launch is still finishing): the expansion table
+    pdl_launch_dependents();
+    if (ptid >= 0)
+        for (int i = ptid; i < 256; i += pthreads)
+            sm.lut8[i] = (u64)((((u32)i & 0xFu) * 0x00204081u) & 0x01010101u) | ((u64)((((u32)i >> 4) * 0x00204081u) & 0x01010101u) << 32);
+    pdl_wait();
+    // built-in policy: every CTA reads the step index before its first barrier; the last CTA to finish advances it
+    const u32 step0 = policy_ctr ? *reinterpret_cast<volatile u32*>(policy_ctr) : 0u;
     u64* const gq = p.queue + (size_t)blockIdx.x * (kQ * kQW * kLpc);
     volatile u64* const qp = q_in_smem ? &sm.q[0][0][0] : gq;             // (the generators' stores go through this generic pointer)
 
-    // ---- prologue: layer bitmaps, expansion table, queue and its counters
-    for (int i = tid; i < 256; i += kThreads)
-        sm.lut8[i] = (u64)((((u32)i & 0xFu) * 0x00204081u) & 0x01010101u) | ((u64)((((u32)i >> 4) * 0x00204081u) & 0x01010101u) << 32);
+    // ---- prologue, part 2: layer bitmaps, queue and its counters
+    // A single-step launch would end with the whole tile's expansion AFTER the chain.  Most of those bytes do not depend on the step (a
+    // light step changes ONE byte of its lattice's observation): the writer warps expand the stream as it stands at launch while the
+    // chain runs, patch that byte when the record arrives, and only the lattices that drew a fresh volume are expanded again at the end.
+    uint8_t* const obs_tile0 = obs0 ? obs0 + (size_t)ro.first_slot * ro.slot_bytes + (size_t)env0 * p.obs_bits : nullptr;
+    const bool early = !RESET && ro.nsteps == 1 && obs0 != nullptr && (reinterpret_cast<uintptr_t>(obs_tile0) & 15) == 0;
     if (q_in_smem) {
         u64* sq = &sm.q[0][0][0];
         for (int i = tid; i < kQ * kQW * kLpc; i += kThreads) sq[i] = gq[i];
     }
     // the bit stream as the state stands at launch: every (lattice, layer) bitmap row into its place, by every thread of the CTA (a
     // single-step launch would otherwise wait for its few writer threads to do this before they can look at the step's record)
-    if (obs0) {
-        for (int i = tid; i < kLpc * C; i += kThreads) {
+    if (obs0 && ptid >= 0) {
+        for (int i = ptid; i < kLpc * C; i += pthreads) {
             const int l = i / C, c = i - l * C;
             u64 w[PW];
 #pragma unroll
@@ -433,7 +474,12 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
 #endif
         }
     }
-    __syncthreads();
+    if (phys_skip) {
+        if (warp == 0) { __threadfence_block(); __syncwarp(); bar_arrive_named(0, kThreads); }      // counters and flags are published; no wait
+        else bar_sync_named(0, kThreads);
+    } else {
+        __syncthreads();
+    }
 #if DQ_PHYS_LAST
     const int role = (kThreads / 32) - 1 - warp;                                   // the physics warp is the CTA's last warp
 #else
@@ -662,6 +708,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
         // ================================================================== WRITERS
         const int t = (role - 1) * 32 + lane;
         int ring_slot = ro.first_slot;
+        if (early) write_observations(sm, p, obs0 + (size_t)ro.first_slot * ro.slot_bytes, env0, nvalid, t, kWriterThreads);
         for (int rs = 0; rs < ro.nsteps; ++rs) {
             const int r = rs & (kRing - 1);
             uint8_t* const obs = obs0 ? obs0 + (size_t)ring_slot * ro.slot_bytes : nullptr;
@@ -676,6 +723,7 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
                     if (obs0) {
                         const int sb = t * p.obs_bits + (p.vd + (ab >> 16)) * L::P + pos;
                         atomicOr(&sm.stream[sb >> 5], 1u << (sb & 31));
+                        if (early) obs_tile0[sb] = 1;                     // byte i of the tile's observations is bit i of the stream
                     }
                 }
             }
@@ -754,7 +802,15 @@ env_step_kernel(const EnvParams p, const int32_t* __restrict__ actions, uint8_t*
     __syncthreads();
     // ---- the last step's observation bytes, by every thread: the other roles have nothing left to do, and a single-step launch ends
     //      when its expansion does
-    if (obs0) {
+    if (early) {
+        const u32 vm = sm.rec_volmask[0];
+        const int wpl = (p.obs_bits + 31) / 32 + 1, items = __popc(vm) * wpl, vbytes = nvalid * p.obs_bits;
+        for (int i = tid; i < items; i += kThreads) {
+            const int k = i / wpl, slot = select64((u64)vm, k);
+            const int w = ((slot * p.obs_bits) >> 5) + (i - k * wpl);
+            if (w < (((slot + 1) * p.obs_bits + 31) >> 5)) rewrite_observation_word(sm, obs_tile0, vbytes, w);
+        }
+    } else if (obs0) {
         int last_slot = ro.first_slot + (ro.nsteps - 1) % ro.slots;
         if (last_slot >= ro.slots) last_slot -= ro.slots;
         write_observations(sm, p, obs0 + (size_t)last_slot * ro.slot_bytes, env0, nvalid, tid, kThreads);
@@ -1010,11 +1066,28 @@ static int launch_env(dq_env* e, const int32_t* actions, uint8_t* obs, float* re
     p.q_reset = e->q_reset ? 1 : 0;
     e->q_reset = false;
     const dim3 grid(p.npad / kLpc);
+    // single-step launches carry the programmatic-dependent-launch attribute (pdl_wait in the kernel): back-to-back steps overlap one
+    // launch's scheduling and table build with the previous launch's tail.  DQ_ENV_PDL=0 turns it off.
+    static const bool pdl_on = [] { const char* v = getenv("DQ_ENV_PDL"); return !(v && v[0] == '0'); }();
+    const bool pdl = pdl_on && ro.nsteps == 1;
+#ifdef DQ_EMU
+#define DQ_LAUNCH_ENV(DD) env_step_kernel<DD, RESET><<<grid, dim3(Roles<DD>::kThreads), e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro)
+#else
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.dynamicSmemBytes = e->smem_bytes; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+#define DQ_LAUNCH_ENV(DD) (cfg.blockDim = dim3(Roles<DD>::kThreads), (void)cudaLaunchKernelEx(&cfg, env_step_kernel<DD, RESET>, p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro))
+#endif
     switch (p.d) {
-        case 3: env_step_kernel<3, RESET><<<grid, dim3(Roles<3>::kThreads), e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;
-        case 5: env_step_kernel<5, RESET><<<grid, dim3(Roles<5>::kThreads), e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;
-        case 7: env_step_kernel<7, RESET><<<grid, dim3(Roles<7>::kThreads), e->smem_bytes, st>>>(p, actions, obs, reward, done, lifetime, legal, auto_reset, pctr, aout, ro); break;
+        case 3: DQ_LAUNCH_ENV(3); break;
+        case 5: DQ_LAUNCH_ENV(5); break;
+        case 7: DQ_LAUNCH_ENV(7); break;
     }
+#undef DQ_LAUNCH_ENV
+    (void)pdl;
     g_launches.fetch_add(1);
     DQ_CUDA(cudaGetLastError());
     return DQ_OK;

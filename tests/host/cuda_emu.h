@@ -133,12 +133,13 @@ inline void block_barrier() {
     }
 }
 
-// bar.sync id, count / bar.arrive id, count.  The hardware executes barrier instructions per WARP, as if all its threads were active:
+// bar.sync id, count / bar.arrive id, count (id 0 is the barrier __syncthreads uses: a kernel may address it by number as long as the two
+// uses do not overlap in time; the emulation keeps separate counters for them).  The hardware executes barrier instructions per WARP, as if all its threads were active:
 // a warp arrives as one unit of 32.  The fibers of a warp therefore first meet (a warp-wide rendez-vous), one of them adds the warp's
 // 32 arrivals, and -- for bar.sync -- all of them wait for the phase to complete.  Callers must be warp-converged, as on the GPU.
 inline void named_barrier_impl(int id, int count, bool wait) {
     Cta& c = *cta();
-    if (id < 1 || id > 15 || count % 32) { fprintf(stderr, "dq_emu: bad named barrier (%d, %d)\n", id, count); abort(); }
+    if (id < 0 || id > 15 || count % 32) { fprintf(stderr, "dq_emu: bad named barrier (%d, %d)\n", id, count); abort(); }
     const int w = c.cur >> 5, lane = c.cur & 31;
     const uint32_t lanes = lanes_of_warp(c, w);
     int gen = c.nbar_gen[id];
