@@ -40,6 +40,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("rep")
     ap.add_argument("lib", nargs="?", default="deepq_decoding_b200/libdq_decoding.so")
+    ap.add_argument("--source", default="deepq_decoding_b200/csrc/dq_env.cu", help="the dq_env.cu the captured library was built from")
     ap.add_argument("--top", type=int, default=30)
     ap.add_argument("--kernel", default="env_step_kernelILi5ELb0")
     a = ap.parse_args()
@@ -47,7 +48,7 @@ def main():
     hdr, rows = T.source_page(a.rep)
     assert len(seq) == len(rows), "capture and library are different builds (%d vs %d instructions)" % (len(rows), len(seq))
     ci = {n: i for i, n in enumerate(hdr)}
-    ranges, k0 = role_ranges("deepq_decoding_b200/csrc/dq_env.cu")
+    ranges, k0 = role_ranges(a.source)
     per_line, per_role = collections.defaultdict(lambda: [0, 0, 0]), collections.defaultdict(lambda: [0, 0, 0])
     tot = [0, 0, 0]
     for (addr, loc, op), r in zip(seq, rows):
