@@ -34,6 +34,43 @@ namespace dq {
 extern thread_local std::string g_err_q;
 void count_launch();
 
+// ---- Programmatic dependent launch for the chains of small kernels (a bf16 forward is 5 launches, a bf16 update 45): a kernel launched
+// through DQ_LAUNCH_PDL may be SCHEDULED while its predecessor in the stream is still running; it must call pdl_wait() before its first
+// access to global memory (nothing before that point may read or write anything another kernel touches), and calls
+// pdl_launch_dependents() once it holds every resource a successor could compete for (tensor memory above all: a successor that took
+// the last TMEM columns and then waited for this grid would starve this grid's own CTAs).  In a launch without the attribute both are
+// no-ops, so the same kernels serve the plain launches of the fp32 path.  DQ_QNET_PDL=0 launches everything plainly.
+__device__ __forceinline__ void pdl_launch_dependents() {
+#ifndef DQ_EMU
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#ifndef DQ_EMU
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+#ifdef DQ_EMU
+#define DQ_LAUNCH_PDL(kernel, grid, block, smem, st, ...) kernel<<<grid, block, smem, st>>>(__VA_ARGS__)
+#else
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("DQ_QNET_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#define DQ_LAUNCH_PDL(kernel, grid, block, smem, st, ...) dq::launch_pdl(kernel, dim3(grid), dim3(block), smem, st, __VA_ARGS__)
+#endif
+
 constexpr int kMaxConv = 4, kMaxDense = 4;
 
 struct ConvL { int cin, ih, oh, ksz, stride, filters, K, P; };     // square maps; K = ksz*ksz*cin; P = oh*oh
@@ -230,6 +267,7 @@ gemm_fwd_kernel(const float* __restrict__ X, Patch g, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 gemm_dw_kernel(const float* __restrict__ X, Patch g, const float* __restrict__ dY, float* __restrict__ dW,
                long long M, int N, int K, long long m_chunk) {
+    pdl_launch_dependents(); pdl_wait();
     __shared__ float As[TK][TB + 4], Bs[TK][TB + 4];
     __shared__ int coloff[TB];
     __shared__ long long rowoff[TK];
@@ -295,6 +333,7 @@ template <int NS>
 __global__ void __launch_bounds__(256)
 gemm_dx_kernel(const float* __restrict__ dY, const float* __restrict__ W, float* __restrict__ dX, Patch g,
                long long M, int N, int K, int overlap) {
+    pdl_launch_dependents(); pdl_wait();
     __shared__ float As[NS][TB + 4], Bs[NS][TB + 4];
     __shared__ long long rowoff[TB];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -381,6 +420,7 @@ __global__ void dropout_kernel(float* __restrict__ Y, float* __restrict__ mask, 
     }
 }
 __global__ void colsum_kernel(const float* __restrict__ dY, float* __restrict__ db, long long M, int N) {
+    pdl_launch_dependents(); pdl_wait();
     // grid.x covers columns in blocks of 32; each block reduces a slice of rows (grid.y) and adds atomically
     __shared__ float part[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
@@ -406,6 +446,7 @@ __global__ void dueling_fwd_kernel(const float* __restrict__ y, float* __restric
     for (int a = 0; a < A; ++a) q[b * A + a] = base + r[1 + a];
 }
 __global__ void dueling_bwd_kernel(const float* __restrict__ dq, float* __restrict__ dy, long long B, int A) {
+    pdl_launch_dependents(); pdl_wait();
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     float s = 0.f;
@@ -416,6 +457,7 @@ __global__ void dueling_bwd_kernel(const float* __restrict__ dq, float* __restri
 // Keras-2 Adam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v EMA; p -= lr_t*m/(sqrt(v)+eps).  g is scaled by gscale first
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
                             long long n, float lr_t, float b1, float b2, float eps, float gscale) {
+    pdl_launch_dependents(); pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float pi = p[i], mi = m[i], vi = v[i];
         dq::adam_update(pi, mi, vi, __fmul_rn(g[i], gscale), lr_t, b1, b2, eps);
@@ -425,6 +467,7 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ m, float*
 // double-DQN target: y = r + gamma*(1-terminal)*Qt[argmax_a Qo[a]]   (ties -> lowest index)
 __global__ void dqn_target_kernel(const float* __restrict__ qo, const float* __restrict__ qt, const float* __restrict__ r,
                                   const uint8_t* __restrict__ term, float gamma, long long B, int A, float* __restrict__ y) {
+    pdl_launch_dependents(); pdl_wait();
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     int best = 0; float bv = qo[b * A];
@@ -434,6 +477,7 @@ __global__ void dqn_target_kernel(const float* __restrict__ qo, const float* __r
 // loss = mean_b 0.5*(y - Q[b][a_b])^2;  dQ = d loss / dQ;  stats += {sum of 0.5*err^2, sum of max_a Q}
 __global__ void dqn_loss_grad_kernel(const float* __restrict__ q, const int32_t* __restrict__ act, const float* __restrict__ y,
                                      long long B, int A, float* __restrict__ dq, float* __restrict__ stats) {
+    pdl_launch_dependents(); pdl_wait();
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float l = 0.f, mq = 0.f;
     if (b < B) {
@@ -454,6 +498,7 @@ __global__ void dqn_loss_grad_kernel(const float* __restrict__ q, const int32_t*
 __global__ void eps_greedy_kernel(const float* __restrict__ q, const u64* __restrict__ legal, int n, int W, int A, u32 env_id_base,
                                   u32 step, u32* __restrict__ ctr, u32 k0, u32 k1, u32 eps_thr, int masked_greedy,
                                   int32_t* __restrict__ actions) {
+    pdl_launch_dependents(); pdl_wait();
     __shared__ u32 s_step;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (ctr) {
@@ -505,6 +550,7 @@ __global__ void replay_sample_kernel(const u64* __restrict__ ring_obs, const int
                                      u32 k0, u32 k1, u32 draw, u64* __restrict__ s0, u64* __restrict__ s1,
                                      int32_t* __restrict__ act, float* __restrict__ rew, uint8_t* __restrict__ term,
                                      int32_t* __restrict__ picked) {
+    pdl_launch_dependents(); pdl_wait();
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     // transitions live in the `filled` most recent completed slots; slot `head` is the one being written next
@@ -802,7 +848,7 @@ extern "C" int dq_adam_step(float* params, float* m, float* v, const float* grad
                             float eps, int64_t t, float grad_scale, dq_stream stream) {
     if (!params || !m || !v || !grads || n < 1 || t < 1) return qfail(DQ_EINVAL, "bad argument");
     const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t));
-    adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, m, v, grads, n, (float)lr_t, beta1, beta2, eps, grad_scale);
+    DQ_LAUNCH_PDL(adam_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, params, m, v, grads, n, (float)lr_t, beta1, beta2, eps, grad_scale);
     count_launch();
     QCUDA(cudaGetLastError());
     return DQ_OK;
@@ -811,7 +857,7 @@ extern "C" int dq_adam_step(float* params, float* m, float* v, const float* grad
 extern "C" int dq_dqn_targets(const float* q_online_next, const float* q_target_next, const float* reward, const uint8_t* terminal,
                               float gamma, int64_t batch, int num_actions, float* y, dq_stream stream) {
     if (!q_online_next || !q_target_next || !reward || !terminal || !y || batch < 1) return qfail(DQ_EINVAL, "bad argument");
-    dqn_target_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(q_online_next, q_target_next, reward, terminal, gamma, batch, num_actions, y);
+    DQ_LAUNCH_PDL(dqn_target_kernel, (unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream, q_online_next, q_target_next, reward, terminal, gamma, batch, num_actions, y);
     count_launch();
     QCUDA(cudaGetLastError());
     return DQ_OK;
@@ -820,7 +866,7 @@ extern "C" int dq_dqn_targets(const float* q_online_next, const float* q_target_
 extern "C" int dq_dqn_loss_grad(const float* q, const int32_t* actions, const float* y, int64_t batch, int num_actions, float* dq,
                                 float* stats, dq_stream stream) {
     if (!q || !actions || !y || !dq || batch < 1) return qfail(DQ_EINVAL, "bad argument");
-    dqn_loss_grad_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(q, actions, y, batch, num_actions, dq, stats);
+    DQ_LAUNCH_PDL(dqn_loss_grad_kernel, (unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream, q, actions, y, batch, num_actions, dq, stats);
     count_launch();
     QCUDA(cudaGetLastError());
     return DQ_OK;
@@ -832,7 +878,7 @@ extern "C" int dq_policy_eps_greedy(const float* q, const uint64_t* legal, int64
     if (!q || !legal || !actions || n < 1 || mask_words < 1 || mask_words > 3) return qfail(DQ_EINVAL, "bad argument");
     double t = floor(eps * 4294967296.0);
     const u32 thr = eps <= 0.0 ? 0u : (t >= 4294967295.0 ? 0xFFFFFFFFu : (u32)t);
-    eps_greedy_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(q, (const u64*)legal, (int)n, mask_words, num_actions, env_id_base,
+    DQ_LAUNCH_PDL(eps_greedy_kernel, (unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream, q, (const u64*)legal, (int)n, mask_words, num_actions, env_id_base,
                                                                                       step_index, dev_step_counter, (u32)seed, (u32)(seed >> 32), thr,
                                                                                       masked_greedy, actions);
     count_launch();
@@ -846,7 +892,7 @@ extern "C" int dq_replay_sample(const uint64_t* ring_obs, const int32_t* ring_ac
                                 int32_t* picked, dq_stream stream) {
     if (!ring_obs || !ring_act || !ring_rew || !ring_term || !s0 || !s1 || !act || !rew || !term) return qfail(DQ_EINVAL, "NULL argument");
     if (filled < 1 || filled >= capacity || batch < 1) return qfail(DQ_EINVAL, "replay ring holds no complete transition yet");
-    replay_sample_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const u64*)ring_obs, ring_act, ring_rew, ring_term, rows, npad, (int)n,
+    DQ_LAUNCH_PDL(replay_sample_kernel, (unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream, (const u64*)ring_obs, ring_act, ring_rew, ring_term, rows, npad, (int)n,
                                                                                              capacity, head, filled, batch, (u32)seed, (u32)(seed >> 32), draw_index,
                                                                                              (u64*)s0, (u64*)s1, act, rew, term, picked);
     count_launch();
@@ -862,6 +908,7 @@ namespace dq {
 __global__ void __launch_bounds__(128)
 fold_head_kernel(const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ W3,
                  const float* __restrict__ b3, int K, int A, float* __restrict__ Wf, float* __restrict__ bf) {
+    pdl_launch_dependents(); pdl_wait();
     // one warp per row r (r < K: row r of Wf [K][A]; r == K: bf); lane = column c of the dueling layer (c = 0: state value, c = 1 + a: advantage a)
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (r > K) return;
@@ -887,7 +934,7 @@ extern "C" int dq_qnet_fold_head(const dq_qnet* h, const float* params, float* w
     if (!c.dueling || c.n_fc < 2) return qfail(DQ_EINVAL, "the network has no dueling head to fold");
     const int i2 = c.n_fc - 2, i3 = c.n_fc - 1, t2 = c.n_conv + i2, t3 = c.n_conv + i3, K = c.fc_in[i2];
     if (c.fc_out[i2] != c.A || c.fc_in[i3] != c.A || c.fc_out[i3] != c.A + 1) return qfail(DQ_EINVAL, "unexpected head shape");
-    fold_head_kernel<<<(unsigned)((K + 1 + 3) / 4), 128, 0, (cudaStream_t)stream>>>(params + c.w_off[t2], params + c.b_off[t2], params + c.w_off[t3],
+    DQ_LAUNCH_PDL(fold_head_kernel, (unsigned)((K + 1 + 3) / 4), 128, 0, (cudaStream_t)stream, params + c.w_off[t2], params + c.b_off[t2], params + c.w_off[t3],
                                                                                       params + c.b_off[t3], K, c.A, w_out, b_out);
     count_launch();
     QCUDA(cudaGetLastError());
@@ -1056,6 +1103,8 @@ tc_gemm_kernel(const TcArgs a) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) mbar_init(&mbar, 1);
+    if (warp == 0) pdl_launch_dependents();                         // by the warp that has just taken the CTA's TMEM columns: a successor cannot starve it
+    pdl_wait();                                                     // first global access below
     if (tid < BN) sbias[tid] = (a.bias && n0 + tid < a.N) ? a.bias[n0 + tid] : 0.f;
     {   // B: weight rows, spread over the CTA (independent of A)
         const int total = BN * KB * 8;
@@ -1198,6 +1247,8 @@ tc_gemm_pipe_kernel(const TcArgs a) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) for (int s = 0; s < S; ++s) mbar_init(&mbar_free[s], 1);
+    if (warp == 0) pdl_launch_dependents();
+    pdl_wait();
     if (tid < BN) sbias[tid] = (a.bias && n0 + tid < a.N) ? a.bias[n0 + tid] : 0.f;
     if (tid < KB * 8) koff[tid] = (tid * 8 < a.K) ? patch_col(a.g, tid * 8) : -1;
     const int r = tid;
@@ -1277,6 +1328,7 @@ template <int MAXG>                                     // 4-column groups per l
 __global__ void __launch_bounds__(128)
 head_dueling_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
                     float* __restrict__ q, long long B, int K, int N, int A, int dueling) {
+    pdl_launch_dependents(); pdl_wait();
     extern __shared__ __align__(16) float hw[];         // W [K][N4], bias [N4], x tile [32][K]
     const int N4 = (N + 3) & ~3, G = N4 >> 2;
     float* hb = hw + K * N4;
@@ -1450,6 +1502,8 @@ tc_dw_tma_kernel(const __grid_constant__ Tmap2D ta, const __grid_constant__ Tmap
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();                                        // the barriers are next touched by the async proxy (TMA, tcgen05.commit)
     }
+    if (warp == 0) pdl_launch_dependents();
+    pdl_wait();                                                     // the TMA loads and the gradient atomics come after this point
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1516,6 +1570,7 @@ tc_dw_tma_kernel(const __grid_constant__ Tmap2D ta, const __grid_constant__ Tmap
 // a thread loads 8 k of one row, then stores 8 m of one k.
 __global__ void __launch_bounds__(256)
 im2colT_kernel(const __nv_bfloat16* __restrict__ X, Patch g, long long M, int K, __nv_bfloat16* __restrict__ At, long long lda) {
+    pdl_launch_dependents(); pdl_wait();
     __shared__ __align__(16) unsigned short tile[64][72];        // [k][m]; rows of 144 bytes keep the 16-byte reads of phase 2 aligned
     __shared__ long long rowoff[64];
     __shared__ int coloff[8];
@@ -1550,6 +1605,7 @@ im2colT_kernel(const __nv_bfloat16* __restrict__ X, Patch g, long long M, int K,
 __global__ void __launch_bounds__(256)
 im2colT_bits_kernel(const u64* __restrict__ packed, long long stride, ConvL L, int C, int PW, int H, long long M,
                     __nv_bfloat16* __restrict__ At, long long lda, int Kpad) {
+    pdl_launch_dependents(); pdl_wait();
     const long long m = (long long)blockIdx.x * 256 + threadIdx.x;          // column (< lda)
     if (m >= lda) return;
     const bool live = m < M;
@@ -1578,6 +1634,7 @@ __global__ void __launch_bounds__(256)
 prep_dy_kernel(DySrc src, const __nv_bfloat16* __restrict__ act, const float* __restrict__ mask, long long M, int N,
                __nv_bfloat16* __restrict__ dYb, int ldyb, __nv_bfloat16* __restrict__ dYT, long long ldyt, int rows_t,
                float* __restrict__ db) {
+    pdl_launch_dependents(); pdl_wait();
     __shared__ float tile[64][65];
     const int tid = threadIdx.x;
     const long long m0 = (long long)blockIdx.x * 64;
@@ -1675,6 +1732,7 @@ prep_dy_kernel(DySrc src, const __nv_bfloat16* __restrict__ act, const float* __
 }
 // training-mode dropout on a bf16 activation: the masks of dropout_kernel (same Philox words), kept in fp32 for the backward pass
 __global__ void dropout_bf16_kernel(__nv_bfloat16* __restrict__ Y, float* __restrict__ mask, long long n, float rate, u32 k0, u32 k1, u32 tag) {
+    pdl_launch_dependents(); pdl_wait();
     const u32 thr = (u32)fminf(rate * 4294967296.f, 4294967295.f);
     const float scale = 1.f / (1.f - rate);
     for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 * 4 < n; i4 += (long long)gridDim.x * blockDim.x) {
@@ -1695,6 +1753,7 @@ __global__ void dropout_bf16_kernel(__nv_bfloat16* __restrict__ Y, float* __rest
 struct PrepJob { const float* W; __nv_bfloat16* out; int K, N, d0, d1, mode, perm_C; };
 struct PrepJobs { PrepJob j[2 * (kMaxConv + kMaxDense + 2) + 1]; };
 __global__ void prep_weights_kernel(const PrepJobs jobs) {
+    pdl_launch_dependents(); pdl_wait();
     const PrepJob& jb = jobs.j[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= jb.d0 * jb.d1) return;
@@ -1788,10 +1847,10 @@ static int launch_tc(const TcArgs& a, int npad, cudaStream_t st) {
         const size_t smem = (deep ? 4 : 2) * (16384 + (size_t)BN * 128) + 1024;
         if (deep) {
             QCUDA(cudaFuncSetAttribute(tc_gemm_pipe_kernel<BN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tc_gemm_pipe_kernel<BN, 4><<<grid, 128, smem, st>>>(a);
+            DQ_LAUNCH_PDL((tc_gemm_pipe_kernel<BN, 4>), grid, 128, smem, st, a);
         } else {
             QCUDA(cudaFuncSetAttribute(tc_gemm_pipe_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tc_gemm_pipe_kernel<BN, 2><<<grid, 128, smem, st>>>(a);
+            DQ_LAUNCH_PDL((tc_gemm_pipe_kernel<BN, 2>), grid, 128, smem, st, a);
         }
         count_launch();
         return DQ_OK;
@@ -1800,7 +1859,7 @@ static int launch_tc(const TcArgs& a, int npad, cudaStream_t st) {
     if (smem > 227 * 1024) return qfail(DQ_EINVAL, "tensor-core tile does not fit shared memory");
     QCUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((a.M + 127) / 128), npad / BN);
-    tc_gemm_kernel<BN, AMODE><<<grid, 128, smem, st>>>(a);
+    DQ_LAUNCH_PDL((tc_gemm_kernel<BN, AMODE>), grid, 128, smem, st, a);
     count_launch();
     return DQ_OK;
 }
@@ -1855,7 +1914,7 @@ extern "C" int dq_qnet_prepare_tc(dq_qnet* h, const float* params, dq_stream str
         if (rc) return rc;
         add(tc->fold_w, tc->fold_wt, K, N, tc->npad[j], tc->kpad[j], 0, 0);
     }
-    prep_weights_kernel<<<dim3((max_total + 255) / 256, nj), 256, 0, (cudaStream_t)stream>>>(jobs);
+    DQ_LAUNCH_PDL(prep_weights_kernel, dim3((max_total + 255) / 256, nj), 256, 0, (cudaStream_t)stream, jobs);
     count_launch();
     QCUDA(cudaGetLastError());
     return DQ_OK;
@@ -1895,7 +1954,7 @@ static int tc_forward(dq_qnet* h, const float* params, const uint64_t* packed, i
         if (train && j >= c.n_conv && !last && c.drop[j - c.n_conv] > 0.f) {     // Dropout after a hidden dense layer (FL:366-370)
             const int i = j - c.n_conv;
             const long long n = batch * c.fc_out[i];
-            dropout_bf16_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(tc->act[j], h->mask_fc[i], n, c.drop[i], (u32)dropout_seed, (u32)(dropout_seed >> 32), (u32)i);
+            DQ_LAUNCH_PDL(dropout_bf16_kernel, grid_for((n + 3) / 4, 256), 256, 0, st, tc->act[j], h->mask_fc[i], n, c.drop[i], (u32)dropout_seed, (u32)(dropout_seed >> 32), (u32)i);
             count_launch();
         }
     }
@@ -1909,11 +1968,11 @@ static int tc_forward(dq_qnet* h, const float* params, const uint64_t* packed, i
         const size_t smem = (size_t)(K * N4 + N4 + kHeadSamples * K) * sizeof(float);
         const unsigned hgrid = (unsigned)((batch + kHeadSamples - 1) / kHeadSamples);
         if (N <= 64 && smem <= 48 * 1024) {
-            head_dueling_kernel<4><<<hgrid, 128, smem, st>>>(xf, params + c.w_off[t], params + c.b_off[t], q_out, batch, K, N, c.A, 1);
+            DQ_LAUNCH_PDL((head_dueling_kernel<4>), hgrid, 128, smem, st, xf, params + c.w_off[t], params + c.b_off[t], q_out, batch, K, N, c.A, 1);
             count_launch();
         } else if (N <= 128 && smem <= 200 * 1024) {
             QCUDA(cudaFuncSetAttribute(head_dueling_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            head_dueling_kernel<8><<<hgrid, 128, smem, st>>>(xf, params + c.w_off[t], params + c.b_off[t], q_out, batch, K, N, c.A, 1);
+            DQ_LAUNCH_PDL((head_dueling_kernel<8>), hgrid, 128, smem, st, xf, params + c.w_off[t], params + c.b_off[t], q_out, batch, K, N, c.A, 1);
             count_launch();
         } else {
             launch_gemm_fwd(xf, dense_patch(K), params + c.w_off[t], params + c.b_off[t], h->act_fc[i], batch, N, K, 0, st);
@@ -1999,7 +2058,7 @@ static int launch_tc_dw(const __nv_bfloat16* At, long long lda, const __nv_bfloa
     z = (kb_total + per - 1) / per;
     Tmap2D ta, tb;
     if (!make_tmap_2d(&ta, At, rowsA, lda, 128) || !make_tmap_2d(&tb, Bt, rows_t, ldb, BN)) return qfail(DQ_ECUDA, "cuTensorMapEncodeTiled failed");
-    tc_dw_tma_kernel<BN, S><<<dim3(rowsA / 128, rows_t / BN, z), 128, smem, st>>>(ta, tb, D, ldd, R, N, kb_total, per);
+    DQ_LAUNCH_PDL((tc_dw_tma_kernel<BN, S>), dim3(rowsA / 128, rows_t / BN, z), 128, smem, st, ta, tb, D, ldd, R, N, kb_total, per);
     count_launch();
     return DQ_OK;
 }
@@ -2026,13 +2085,13 @@ extern "C" int dq_qnet_backward_tc(dq_qnet* h, const float* params, const uint64
     if (c.dueling) {
         const int i = c.n_fc - 1, t = c.n_conv + i, K = c.fc_in[i], N = c.fc_out[i];
         float* dY = h->dact_fc[i];
-        dueling_bwd_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(dq, dY, batch, c.A);
+        DQ_LAUNCH_PDL(dueling_bwd_kernel, (unsigned)((batch + 127) / 128), 128, 0, st, dq, dY, batch, c.A);
         const long long chunk = dw_chunk(batch, K, N);
         dim3 gw((K + TB - 1) / TB, (N + TB - 1) / TB, (unsigned)((batch + chunk - 1) / chunk));
-        gemm_dw_kernel<<<gw, 256, 0, st>>>(h->act_fc[i - 1], dense_patch(K), dY, grads + c.w_off[t], batch, N, K, chunk);
-        colsum_kernel<<<dim3((N + 31) / 32, (unsigned)std::min<long long>(64, (batch + 7) / 8)), 256, 0, st>>>(dY, grads + c.b_off[t], batch, N);
+        DQ_LAUNCH_PDL(gemm_dw_kernel, gw, 256, 0, st, h->act_fc[i - 1], dense_patch(K), dY, grads + c.w_off[t], batch, N, K, chunk);
+        DQ_LAUNCH_PDL(colsum_kernel, dim3((N + 31) / 32, (unsigned)std::min<long long>(64, (batch + 7) / 8)), 256, 0, st, dY, grads + c.b_off[t], batch, N);
         dim3 gx((unsigned)((batch + TB - 1) / TB), (K + TB - 1) / TB);
-        gemm_dx_kernel<16><<<gx, 256, 0, st>>>(dY, params + c.w_off[t], h->dact_fc[i - 1], dense_patch(K), batch, N, K, 0);
+        DQ_LAUNCH_PDL((gemm_dx_kernel<16>), gx, 256, 0, st, dY, params + c.w_off[t], h->dact_fc[i - 1], dense_patch(K), batch, N, K, 0);
         count_launch(); count_launch(); count_launch(); count_launch();
         G32 = h->dact_fc[i - 1];
     }
@@ -2052,16 +2111,16 @@ extern "C" int dq_qnet_backward_tc(dq_qnet* h, const float* params, const uint64
             else src.mode = 1;                                                      // a dense layer above: its column gradient is this layer's map
         }
         const int ncols = std::max(g.ldyb, g.rows_t);
-        prep_dy_kernel<<<dim3((unsigned)(g.Mpad / 64), (ncols + 63) / 64), 256, 0, st>>>(src, act, mask, g.M, g.N, sb->dyb, g.ldyb, sb->dyt, g.Mpad, g.rows_t,
+        DQ_LAUNCH_PDL(prep_dy_kernel, dim3((unsigned)(g.Mpad / 64), (ncols + 63) / 64), 256, 0, st, src, act, mask, g.M, g.N, sb->dyb, g.ldyb, sb->dyt, g.Mpad, g.rows_t,
                                                                                       grads + c.b_off[j]);
         count_launch();
         // 2. A^T, then dW = A^T x dY over the batch
         if (j == 0) {
             const ConvL& L = c.conv[0];
-            im2colT_bits_kernel<<<dim3((unsigned)((g.Mpad + 255) / 256), 1), 256, 0, st>>>((const u64*)packed, stride, L, c.C, c.PW, c.H, g.M, sb->at, g.Mpad, g.rowsA);
+            DQ_LAUNCH_PDL(im2colT_bits_kernel, dim3((unsigned)((g.Mpad + 255) / 256), 1), 256, 0, st, (const u64*)packed, stride, L, c.C, c.PW, c.H, g.M, sb->at, g.Mpad, g.rowsA);
         } else {
             const Patch pg = j < c.n_conv ? conv_patch(c.conv[j]) : dense_patch(g.K);
-            im2colT_kernel<<<dim3((unsigned)(g.Mpad / 64), g.rowsA / 64), 256, 0, st>>>(tc->act[j - 1], pg, g.M, g.K, sb->at, g.Mpad);
+            DQ_LAUNCH_PDL(im2colT_kernel, dim3((unsigned)(g.Mpad / 64), g.rowsA / 64), 256, 0, st, tc->act[j - 1], pg, g.M, g.K, sb->at, g.Mpad);
         }
         count_launch();
         int rc;
