@@ -460,6 +460,11 @@ def dqn_data_parallel_leg(L, _lib, torch, np, dist, dev, world, rank, n):
                                      "episodes": episodes, "mean_lifetime_cycles": mean, "standard_error": se,
                                      "logical_error_rate_per_cycle": 1.0 / mean, "reference_published_mean_lifetime": 270.42,
                                      "within_3_se_of_published": bool(abs(mean - 270.42) <= 3 * se),
+                                     # the published figure is itself a sample mean: all_results.p holds 270.42121212... = 446195 / 1650, i.e. at
+                                     # most 1650 test episodes; with this run's spread its standard error is std / sqrt(1650)
+                                     "published_episodes_at_most": 1650,
+                                     "published_standard_error_at_least": float(se * np.sqrt(episodes / 1650.0)),
+                                     "consistent_with_published_3_sigma": bool(abs(mean - 270.42) <= 3 * np.sqrt(se * se * (1.0 + episodes / 1650.0))),
                                      "eval_seconds": time.perf_counter() - t0, "merged_with": "parallel.reduce_lifetimes over %d rank(s)" % world}
         ev_env.close()
     return out
