@@ -286,7 +286,9 @@ def e2e_legs(L, _lib, torch, np, dist, dev, world, rank, n, K):
            "api": "VecSurfaceCodeEnv.random_legal_actions_host + step_host_begin / step_host_end (dq_policy_random_legal_host, dq_env_step_host) on one "
                   "handle of %d lattices: uint8 observations [N,C,H,H], reward, done, lifetime and legal masks land in pinned host memory every step" % n,
            "host_expand": host_expand, "host_threads": os.environ.get("DQ_HOST_THREADS", "default (usable CPUs - 1)"),
-           "how": "the bitmap rows cross PCIe bit-packed and the library's host threads expand them into the byte observations"
+           "how": ("the bitmap rows cross PCIe bit-packed (DMA) and the library's host threads expand them into the byte observations; "
+                   "the kernel reads the actions from, and stores reward / done / lifetime / legal masks into, the caller's pinned buffers "
+                   "(zero-copy: those bytes cross PCIe inside the timed region by the kernel's own loads and stores; DQ_HOST_ZEROCOPY=0 for DMA copies)")
                   if host_expand else "the kernel writes bytes; all of them are copied back",
            "policy": "uniform random-legal, computed on the host from the returned legal masks (same picks as the device policy)"}
     # (b) two handles of n/2 lattices driven alternately -- begin(A) begin(B) end(A) policy(A) begin(A) end(B) ... -- so that one handle's

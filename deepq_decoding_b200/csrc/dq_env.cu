@@ -867,6 +867,7 @@ struct HostCall {                // outputs of a host-buffer call between its be
     uint8_t* obs; float* reward; uint8_t* done; int32_t* life; uint64_t* legal;
     int chunks, first[kHostChunks], last[kHostChunks];
     bool pending;
+    bool direct;                 // the kernel stored the small outputs straight into the caller's (pinned) buffers
 };
 
 struct dq_env {
@@ -879,6 +880,8 @@ struct dq_env {
     u32* policy_ctr;             // {step index, finished-CTA count} for dq_policy_random_legal_next
     int32_t* s_actions; uint8_t* s_obs; float* s_reward; uint8_t* s_done; int32_t* s_life; u64* s_legal;      // s_reward .. s_legal point into s_small
     uint8_t* s_small; uint8_t* h_small; size_t small_bytes;
+    int32_t* h_actions_pin; bool zero_copy, direct_ok;
+    const void* alias_host[8]; void* alias_dev[8]; int alias_n;          // pinned caller buffers seen so far -> their device addresses      // zero-copy form of the host-buffer calls: the kernel reads the actions from, and writes the small outputs to, pinned host memory
     u64* h_packed;               // pinned landing buffer of the bit-packed observation rows (host-side expansion)
     bool q_reset;                // the next launch must discard the queued volume attempts (noise rates changed)
     cudaEvent_t h_ev[kHostChunks];   // "this lattice range of the rows has landed"
@@ -992,6 +995,7 @@ extern "C" int dq_env_destroy(dq_env* e) {
         cudaStreamSynchronize(e->hstream);
         cudaFree(e->s_actions); cudaFree(e->s_obs); cudaFree(e->s_small);
         if (e->h_small) cudaFreeHost(e->h_small);
+        if (e->h_actions_pin) cudaFreeHost(e->h_actions_pin);
         if (e->h_packed) cudaFreeHost(e->h_packed);
         for (int c = 0; c < kHostChunks; ++c) if (e->h_ev[c]) cudaEventDestroy(e->h_ev[c]);
         if (e->h_ev_small) cudaEventDestroy(e->h_ev_small);
@@ -1139,10 +1143,28 @@ static int ensure_staging(dq_env* e) {
     e->small_bytes = n * p.W * 8 + n * 4 + n * 4 + n;
     DQ_CUDA(cudaMalloc(&e->s_small, e->small_bytes));
     DQ_CUDA(cudaMallocHost(&e->h_small, e->small_bytes));
-    e->s_legal = reinterpret_cast<u64*>(e->s_small);
-    e->s_reward = reinterpret_cast<float*>(e->s_small + n * p.W * 8);
-    e->s_life = reinterpret_cast<int32_t*>(e->s_small + n * p.W * 8 + n * 4);
-    e->s_done = reinterpret_cast<uint8_t*>(e->s_small + n * p.W * 8 + n * 8);
+    // Zero-copy (default; DQ_HOST_ZEROCOPY=0 for the copy form): a step's chain of DMA operations -- actions in, small outputs out --
+    // costs more in launch and completion latency than the 64 KB + 270 KB are worth on the bus.  The kernel reads the actions straight
+    // from a pinned host buffer (one coalesced PCIe read at the head of the physics chain) and stores reward / done / lifetime / legal
+    // masks straight into the pinned block the caller's buffers are filled from (posted writes); only the bitmap rows still travel by copy.
+    // When the caller's own buffers are pinned (cudaHostAlloc / cudaHostRegister: the Python binding's are), the kernel reads and writes
+    // THEM and nothing is staged at all; DQ_HOST_DIRECT=0 keeps the library's staging block.  (Both switches are read per handle.)
+    const char* zv = getenv("DQ_HOST_ZEROCOPY");
+    const char* dv = getenv("DQ_HOST_DIRECT");
+    const bool zc = !(zv && zv[0] == '0');
+    e->zero_copy = zc;
+    e->direct_ok = zc && !(dv && dv[0] == '0');
+    uint8_t* base = e->s_small;
+    if (zc) {
+        DQ_CUDA(cudaMallocHost(&e->h_actions_pin, n * 4));
+        void* dev_alias = nullptr;
+        DQ_CUDA(cudaHostGetDevicePointer(&dev_alias, e->h_small, 0));
+        base = static_cast<uint8_t*>(dev_alias);
+    }
+    e->s_legal = reinterpret_cast<u64*>(base);
+    e->s_reward = reinterpret_cast<float*>(base + n * p.W * 8);
+    e->s_life = reinterpret_cast<int32_t*>(base + n * p.W * 8 + n * 4);
+    e->s_done = reinterpret_cast<uint8_t*>(base + n * p.W * 8 + n * 8);
     for (int c = 0; c < kHostChunks; ++c) DQ_CUDA(cudaEventCreateWithFlags(&e->h_ev[c], cudaEventDisableTiming));
     DQ_CUDA(cudaEventCreateWithFlags(&e->h_ev_small, cudaEventDisableTiming));
     return DQ_OK;
@@ -1463,7 +1485,8 @@ static int queue_outputs(dq_env* e, bool bytes_on_device, uint64_t* h_packed_use
     const EnvParams& p = e->p;
     cudaStream_t s = e->hstream;
     HostCall& hc = e->hc;
-    if (hc.reward || hc.done || hc.life) DQ_CUDA(cudaMemcpyAsync(e->h_small, e->s_small, e->small_bytes, cudaMemcpyDeviceToHost, s));
+    if (e->zero_copy) { /* the kernel has stored them in h_small (or in the caller's pinned buffers) itself */ }
+    else if (hc.reward || hc.done || hc.life) DQ_CUDA(cudaMemcpyAsync(e->h_small, e->s_small, e->small_bytes, cudaMemcpyDeviceToHost, s));
     else if (hc.legal) DQ_CUDA(cudaMemcpyAsync(e->h_small, e->s_small, (size_t)p.n * p.W * 8, cudaMemcpyDeviceToHost, s));
     DQ_CUDA(cudaEventRecord(e->h_ev_small, s));
     const size_t rows = (size_t)(e->state_rows - ROW_BM), words = rows * p.npad;
@@ -1491,6 +1514,18 @@ static int queue_outputs(dq_env* e, bool bytes_on_device, uint64_t* h_packed_use
     return DQ_OK;
 }
 
+// device address of a caller buffer if it is pinned host memory, else NULL (looked up once per buffer)
+static void* pinned_alias(dq_env* e, const void* h) {
+    if (!h || !e->direct_ok) return nullptr;
+    for (int i = 0; i < e->alias_n; ++i) if (e->alias_host[i] == h) return e->alias_dev[i];
+    void* dev = nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost) dev = at.devicePointer;
+    else cudaGetLastError();                                   // (older drivers report unregistered memory as an error)
+    if (e->alias_n < 8) { e->alias_host[e->alias_n] = h; e->alias_dev[e->alias_n] = dev; ++e->alias_n; }
+    return dev;
+}
+
 static int host_begin(dq_env* e, bool reset, const int32_t* h_actions, uint8_t* h_obs, uint64_t* h_packed_user, float* h_reward, uint8_t* h_done,
                       int32_t* h_life, uint64_t* h_legal, int auto_reset) {
     if (e->hc.pending) return fail(DQ_ESTATE, "a host-buffer call is already in flight on this handle: call dq_env_step_host_end first");
@@ -1502,12 +1537,31 @@ static int host_begin(dq_env* e, bool reset, const int32_t* h_actions, uint8_t* 
     if (bytes_on_device && !e->s_obs) DQ_CUDA(cudaMalloc(&e->s_obs, (size_t)p.n * p.obs_bits));
     e->hc = HostCall{};
     e->hc.obs = h_obs; e->hc.reward = h_reward; e->hc.done = h_done; e->hc.life = h_life; e->hc.legal = h_legal;
+    // small outputs: straight into the caller's buffers when every one of them is pinned, else through the staging block
+    float* d_reward = e->s_reward; uint8_t* d_done = e->s_done; int32_t* d_life = e->s_life; u64* d_legal = e->s_legal;
+    {
+        void* ar = pinned_alias(e, h_reward); void* ad = pinned_alias(e, h_done); void* al = pinned_alias(e, h_life); void* ag = pinned_alias(e, h_legal);
+        if ((!h_reward || ar) && (!h_done || ad) && (!h_life || al) && (!h_legal || ag) && (h_reward || h_done || h_life || h_legal)) {
+            d_reward = static_cast<float*>(ar); d_done = static_cast<uint8_t*>(ad); d_life = static_cast<int32_t*>(al); d_legal = static_cast<u64*>(ag);
+            e->hc.direct = true;
+        }
+    }
     if (reset) {
-        rc = launch_env<true>(e, nullptr, bytes_on_device ? e->s_obs : nullptr, nullptr, nullptr, nullptr, h_legal ? e->s_legal : nullptr, 1, e->hstream);
+        rc = launch_env<true>(e, nullptr, bytes_on_device ? e->s_obs : nullptr, nullptr, nullptr, nullptr, h_legal ? d_legal : nullptr, 1, e->hstream);
     } else {
-        DQ_CUDA(cudaMemcpyAsync(e->s_actions, h_actions, (size_t)p.n * 4, cudaMemcpyHostToDevice, e->hstream));
-        rc = launch_env<false>(e, e->s_actions, bytes_on_device ? e->s_obs : nullptr, h_reward ? e->s_reward : nullptr,
-                               h_done ? e->s_done : nullptr, h_life ? e->s_life : nullptr, h_legal ? e->s_legal : nullptr, auto_reset, e->hstream);
+        const int32_t* d_actions = e->s_actions;
+        if (void* aa = pinned_alias(e, h_actions)) {
+            d_actions = static_cast<const int32_t*>(aa);                   // the caller must leave it alone until the call's end, as with any async copy
+        } else if (e->zero_copy) {
+            memcpy(e->h_actions_pin, h_actions, (size_t)p.n * 4);          // (no launch of this handle is in flight: hc.pending was false)
+            void* dev_alias = nullptr;
+            DQ_CUDA(cudaHostGetDevicePointer(&dev_alias, e->h_actions_pin, 0));
+            d_actions = static_cast<const int32_t*>(dev_alias);
+        } else {
+            DQ_CUDA(cudaMemcpyAsync(e->s_actions, h_actions, (size_t)p.n * 4, cudaMemcpyHostToDevice, e->hstream));
+        }
+        rc = launch_env<false>(e, d_actions, bytes_on_device ? e->s_obs : nullptr, h_reward ? d_reward : nullptr,
+                               h_done ? d_done : nullptr, h_life ? d_life : nullptr, h_legal ? d_legal : nullptr, auto_reset, e->hstream);
     }
     if (rc) return rc;
     return queue_outputs(e, bytes_on_device, h_packed_user);
@@ -1521,7 +1575,7 @@ static int host_end(dq_env* e) {
     hc.pending = false;
     const int side = 2 * p.d + 1, P = side * side;
     DQ_CUDA(cudaEventSynchronize(e->h_ev_small));
-    {
+    if (!hc.direct) {
         const size_t n = (size_t)p.n;
         if (hc.legal) memcpy(hc.legal, e->h_small, n * p.W * 8);
         if (hc.reward) memcpy(hc.reward, e->h_small + n * p.W * 8, n * 4);

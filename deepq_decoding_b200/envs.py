@@ -189,67 +189,77 @@ class VecSurfaceCodeEnv:
 
     # ---- host-buffer API (what the e2e benchmark times) ----
     def _host_buffers(self):
+        """Pinned host buffers of the host-buffer calls, with their ctypes pointers and numpy views made ONCE (a step of 16 384 lattices
+        lasts ~100 us: rebuilding six pointers and five views per call was a tenth of it)."""
         if self._host is None:
             N = self.n_envs
             pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
-            self._host = dict(actions=pin((N,), torch.int32), obs=pin(tuple(self.obs.shape), torch.uint8),
-                              reward=pin((N,), torch.float32), done=pin((N,), torch.uint8),
-                              lifetime=pin((N,), torch.int32), legal=pin((N, self.mask_words), torch.int64))
+            hb = dict(actions=pin((N,), torch.int32), obs=pin(tuple(self.obs.shape), torch.uint8),
+                      reward=pin((N,), torch.float32), done=pin((N,), torch.uint8),
+                      lifetime=pin((N,), torch.int32), legal=pin((N, self.mask_words), torch.int64))
+            hb["ptr"] = {k: _ptr(v) for k, v in hb.items()}
+            hb["np"] = dict(actions=hb["actions"].numpy(), obs=hb["obs"].numpy(), reward=hb["reward"].numpy(),
+                            done=hb["done"].numpy().view(np.bool_),          # the library writes 0 / 1
+                            lifetime=hb["lifetime"].numpy(), legal=hb["legal"].numpy().view(np.uint64))
+            hb["info"] = {"lifetime": hb["np"]["lifetime"], "legal_mask": hb["np"]["legal"]}
+            self._host = hb
         return self._host
 
     def _packed_host_buffer(self):
         hb = self._host_buffers()
         if "packed" not in hb:
             hb["packed"] = torch.empty((self.state_words - ROW_BM, self.state_stride), dtype=torch.int64).pin_memory()
+            hb["ptr"]["packed"] = _ptr(hb["packed"])
+            hb["np"]["packed"] = hb["packed"].numpy().view(np.uint64)
         return hb["packed"]
 
     def reset_host(self, packed=False):
         """`packed=True`: the observations come back as the bit-packed rows the Q-network consumes (uint64
-        [C*PW][state_stride], see `unpack_observations`) instead of uint8 [N, C, H, H]: 7.5x fewer bytes over PCIe."""
+        [C*PW][state_stride], see `unpack_observations`) instead of uint8 [N, C, H, H]: 7.5x fewer bytes over PCIe.
+        The returned arrays are views of the handle's pinned buffers: the next host-buffer call overwrites them."""
         hb = self._host_buffers()
+        P, V = hb["ptr"], hb["np"]
         if packed:
-            pk = self._packed_host_buffer()
-            _lib.check(self.L.dq_env_reset_host_packed(self._h, _ptr(pk), _ptr(hb["legal"])))
-            return pk.numpy().view(np.uint64), hb["legal"].numpy().view(np.uint64)
-        _lib.check(self.L.dq_env_reset_host(self._h, _ptr(hb["obs"]), _ptr(hb["legal"])))
-        return hb["obs"].numpy(), hb["legal"].numpy().view(np.uint64)
+            self._packed_host_buffer()
+            _lib.check(self.L.dq_env_reset_host_packed(self._h, P["packed"], P["legal"]))
+            return V["packed"], V["legal"]
+        _lib.check(self.L.dq_env_reset_host(self._h, P["obs"], P["legal"]))
+        return V["obs"], V["legal"]
 
     def step_host(self, actions, packed=False):
         hb = self._host_buffers()
-        hb["actions"].numpy()[:] = np.asarray(actions, dtype=np.int32)
+        P, V = hb["ptr"], hb["np"]
+        V["actions"][:] = np.asarray(actions, dtype=np.int32)
         if packed:
-            pk = self._packed_host_buffer()
-            _lib.check(self.L.dq_env_step_host_packed(self._h, _ptr(hb["actions"]), _ptr(pk), _ptr(hb["reward"]),
-                                                      _ptr(hb["done"]), _ptr(hb["lifetime"]), _ptr(hb["legal"]), int(self.auto_reset)))
-            return (pk.numpy().view(np.uint64), hb["reward"].numpy(), hb["done"].numpy().astype(bool),
-                    {"lifetime": hb["lifetime"].numpy(), "legal_mask": hb["legal"].numpy().view(np.uint64)})
-        _lib.check(self.L.dq_env_step_host(self._h, _ptr(hb["actions"]), _ptr(hb["obs"]), _ptr(hb["reward"]),
-                                           _ptr(hb["done"]), _ptr(hb["lifetime"]), _ptr(hb["legal"]), int(self.auto_reset)))
-        return (hb["obs"].numpy(), hb["reward"].numpy(), hb["done"].numpy().astype(bool),
-                {"lifetime": hb["lifetime"].numpy(), "legal_mask": hb["legal"].numpy().view(np.uint64)})
+            self._packed_host_buffer()
+            _lib.check(self.L.dq_env_step_host_packed(self._h, P["actions"], P["packed"], P["reward"], P["done"], P["lifetime"], P["legal"],
+                                                      int(self.auto_reset)))
+            return V["packed"], V["reward"], V["done"], hb["info"]
+        _lib.check(self.L.dq_env_step_host(self._h, P["actions"], P["obs"], P["reward"], P["done"], P["lifetime"], P["legal"], int(self.auto_reset)))
+        return V["obs"], V["reward"], V["done"], hb["info"]
 
     def step_host_begin(self, actions=None):
         """First half of `step_host` (dq_env_step_host_begin): queues the copy-in, the launch and the copy-outs and returns at once.
         `actions=None` uses what is already in the pinned action buffer (e.g. written by `random_legal_actions_host`).  Two
         environments stepped begin(A) begin(B) end(A) begin(A) end(B) ... overlap one's GPU work with the other's host-side work."""
         hb = self._host_buffers()
+        P = hb["ptr"]
         if actions is not None:
-            hb["actions"].numpy()[:] = np.asarray(actions, dtype=np.int32)
-        _lib.check(self.L.dq_env_step_host_begin(self._h, _ptr(hb["actions"]), _ptr(hb["obs"]), _ptr(hb["reward"]),
-                                                 _ptr(hb["done"]), _ptr(hb["lifetime"]), _ptr(hb["legal"]), int(self.auto_reset)))
+            hb["np"]["actions"][:] = np.asarray(actions, dtype=np.int32)
+        _lib.check(self.L.dq_env_step_host_begin(self._h, P["actions"], P["obs"], P["reward"], P["done"], P["lifetime"], P["legal"], int(self.auto_reset)))
 
     def step_host_end(self):
         hb = self._host_buffers()
         _lib.check(self.L.dq_env_step_host_end(self._h))
-        return (hb["obs"].numpy(), hb["reward"].numpy(), hb["done"].numpy().astype(bool),
-                {"lifetime": hb["lifetime"].numpy(), "legal_mask": hb["legal"].numpy().view(np.uint64)})
+        V = hb["np"]
+        return V["obs"], V["reward"], V["done"], hb["info"]
 
     def random_legal_actions_host(self, step_index):
         """The random-legal policy on the host (dq_policy_random_legal_host): picks from the legal masks of the latest host-buffer
         call into the pinned action buffer, which is returned (and is what `step_host_begin()` sends)."""
         hb = self._host_buffers()
-        _lib.check(self.L.dq_policy_random_legal_host(self._h, _ptr(hb["legal"]), int(step_index) & 0xFFFFFFFF, _ptr(hb["actions"])))
-        return hb["actions"].numpy()
+        _lib.check(self.L.dq_policy_random_legal_host(self._h, hb["ptr"]["legal"], int(step_index) & 0xFFFFFFFF, hb["ptr"]["actions"]))
+        return hb["np"]["actions"]
 
     # ---- packed state (parity tests, checkpoints) ----
     def get_state_words(self):

@@ -174,7 +174,10 @@ def test_emulated_host_calls_plain_and_threaded_expansion():
         "        olegal = want[4]\n"
         "print('ok')\n"
     ) % os.path.dirname(os.path.abspath(__file__))
-    for expand, threads, extra in (("1", "1", {}), ("1", "5", {}), ("1", "3", {"DQ_HOST_NO_AVX2": "1"}), ("0", "2", {})):
+    # (the small outputs and the actions: straight into / out of the caller's buffers -- the emulation reports every buffer as pinned --,
+    #  through the library's pinned staging block, or by DMA copies)
+    for expand, threads, extra in (("1", "1", {}), ("1", "5", {}), ("1", "3", {"DQ_HOST_NO_AVX2": "1"}), ("0", "2", {}),
+                                   ("1", "2", {"DQ_HOST_DIRECT": "0"}), ("1", "2", {"DQ_HOST_ZEROCOPY": "0"}), ("0", "2", {"DQ_HOST_ZEROCOPY": "0"})):
         out = subprocess.run([sys.executable, "-c", code, expand], env=dict(os.environ, DQ_HOST_EXPAND=expand, DQ_HOST_THREADS=threads, **extra),
                              capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]

@@ -117,6 +117,33 @@ def test_host_buffer_entry_points_and_noise_setter():
     env.close()
 
 
+def test_host_buffer_calls_with_pageable_caller_buffers():
+    """The C ABI's *_host calls with ordinary (pageable) numpy buffers -- the library stages through its own pinned block -- against the
+    binding's pinned buffers, which the kernel reads and writes directly: same outputs, both equal to the oracle."""
+    import ctypes as C
+    from deepq_decoding_b200 import _lib
+    env, o = make_pair(5, "DP", False, 5, 0.02, 300, seed=9)
+    raw, _ = make_pair(5, "DP", False, 5, 0.02, 300, seed=9)
+    L = _lib.lib()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    n, Wm = 300, env.mask_words
+    obs = np.zeros((n,) + tuple(env.obs.shape[1:]), np.uint8); legal = np.zeros((n, Wm), np.uint64)
+    rew = np.zeros(n, np.float32); done = np.zeros(n, np.uint8); life = np.zeros(n, np.int32)
+    _lib.check(L.dq_env_reset_host(raw._h, vp(obs), vp(legal)))
+    pobs, plegal = env.reset_host(); oobs, olegal = o.reset()
+    assert np.array_equal(obs, oobs) and np.array_equal(legal, olegal) and np.array_equal(pobs, oobs)
+    for t in range(25):
+        acts = np.ascontiguousarray(o.random_legal_actions(olegal, t), dtype=np.int32)
+        _lib.check(L.dq_env_step_host(raw._h, vp(acts), vp(obs), vp(rew), vp(done), vp(life), vp(legal), 1))
+        pobs, prew, pdone, pinfo = env.step_host(acts)
+        oobs, orew, odone, olife, olegal = o.step(acts, auto_reset=True)
+        assert np.array_equal(obs, oobs) and np.array_equal(rew, orew) and np.array_equal(done, odone) and np.array_equal(life, olife)
+        assert np.array_equal(legal, olegal)
+        assert np.array_equal(pobs, oobs) and np.array_equal(prew, orew) and np.array_equal(pdone, odone.astype(bool))
+        assert np.array_equal(pinfo["lifetime"], olife) and np.array_equal(pinfo["legal_mask"], olegal)
+    env.close(); raw.close()
+
+
 def test_sharding_is_invisible():
     """Lattices [0,N) on one handle == two handles covering [0,N/2) and [N/2,N) (stream id = global index)."""
     import torch
