@@ -412,14 +412,14 @@ def dqn_data_parallel_leg(L, _lib, torch, np, dist, dev, world, rank, n):
     # ---- (2) short sharded fit through both collectives
     spec_args = ([[64, 3, 2], [32, 2, 1], [32, 2, 1]], [[512, 0.2]])
 
-    def short_fit(collective):
+    def short_fit(collective, train_precision="fp32"):
         env = VecSurfaceCodeEnv(D, P, P, MODEL, USE_Y, VD, None, n_envs=n, seed=SEED + 21, env_id_base=rank * n, device=dev)
         spec = A.build_convolutional_nn(spec_args[0], spec_args[1], env.observation_space.shape, env.num_actions)
         pol = A.LinearAnnealedPolicy(A.EpsGreedyQPolicy(masked_greedy=False), attr="eps", value_max=1.0, value_min=0.05, value_test=0.0, nb_steps=20 * n)
         dqn = A.DQNAgent(model=spec, nb_actions=env.num_actions, memory=A.SequentialMemory(limit=16 * n), nb_steps_warmup=4 * n,
                          target_model_update=10 * n, policy=pol, test_policy=A.GreedyQPolicy(masked_greedy=True), gamma=0.99,
                          enable_dueling_network=True, batch_size=1024, seed=0, device=dev, process_group=group, collective=collective,
-                         act_precision="bf16")
+                         act_precision="bf16", target_precision=train_precision, train_precision=train_precision)
         dqn.compile(A.Adam(lr=1e-4), max_envs=n)
         if world > 1:
             parallel.broadcast_params_(dqn.model.params)
@@ -441,6 +441,17 @@ def dqn_data_parallel_leg(L, _lib, torch, np, dist, dev, world, rank, n):
         lo, hi = pn.clone(), pn.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         ident = ident and bool(torch.equal(lo.view(torch.int32), hi.view(torch.int32)))
+    # the same fit with the updates on the tensor cores (bf16 forward / backward writing its gradient straight into the exchange region)
+    try:
+        pb, _, secs_bf16 = short_fit("fused", "bf16")
+        ident_bf16 = True
+        if world > 1:
+            lo, hi = pb.clone(), pb.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            ident_bf16 = bool(torch.equal(lo.view(torch.int32), hi.view(torch.int32)))
+        out.update({"fit_seconds_fused_bf16_updates": secs_bf16, "identical_bf16_updates": ident_bf16, "fit_finite_bf16_updates": bool(torch.isfinite(pb).all())})
+    except Exception as ex:      # noqa: BLE001 -- reported in the line
+        out["bf16_updates_error"] = "%s: %s" % (type(ex).__name__, str(ex)[:200])
     out.update({"identical": ident, "fit_updates": upd, "fit_env_steps": 24 * n * world, "fit_seconds_fused": secs,
                 "fit_finite": bool(torch.isfinite(pf).all()),
                 "fused_vs_nccl_max_abs_diff": float((pf - pn).abs().max()),

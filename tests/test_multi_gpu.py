@@ -101,7 +101,7 @@ def test_fused_allreduce_adam_is_bit_identical_to_nccl_then_adam(tmp_path):
         assert res["same_as_nccl"], res["max_diff"]          # world 2: one fp32 add either way -> the same bits
 
 
-def _fit_worker(rank, world, port, out, collective, total):
+def _fit_worker(rank, world, port, out, collective, total, train_precision="fp32"):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     from deepq_decoding_b200 import agents as A, parallel
     from deepq_decoding_b200.envs import VecSurfaceCodeEnv
@@ -113,7 +113,8 @@ def _fit_worker(rank, world, port, out, collective, total):
     pol = A.LinearAnnealedPolicy(A.EpsGreedyQPolicy(masked_greedy=False), attr="eps", value_max=1.0, value_min=0.02, value_test=0.0, nb_steps=40000)
     dqn = A.DQNAgent(model=spec, nb_actions=env.num_actions, memory=A.SequentialMemory(limit=100000), nb_steps_warmup=10000,
                      target_model_update=20000, policy=pol, test_policy=A.GreedyQPolicy(masked_greedy=True), gamma=0.99,
-                     enable_dueling_network=True, batch_size=256, seed=0, device=dev, process_group=dist.group.WORLD, collective=collective)
+                     enable_dueling_network=True, batch_size=256, seed=0, device=dev, process_group=dist.group.WORLD, collective=collective,
+                     act_precision="bf16" if train_precision == "bf16" else "fp32", target_precision=train_precision, train_precision=train_precision)
     dqn.compile(A.Adam(lr=1e-4), max_envs=count)
     parallel.broadcast_params_(dqn.model.params)
     dqn.target_params.copy_(dqn.model.params)
@@ -135,6 +136,18 @@ def test_sharded_fit_keeps_ranks_in_step(tmp_path, collective, total):
     warm-up, train_interval and termination fall on the same iteration everywhere and the number of collectives matches."""
     _need_two_gpus()
     mp.spawn(_fit_worker, args=(2, 31500 + os.getpid() % 2000, str(tmp_path), collective, total), nprocs=2, join=True)
+    res = [torch.load(os.path.join(tmp_path, "f%d.pt" % r), weights_only=False) for r in (0, 1)]
+    for r in res:
+        assert r["identical"] and r["finite"] and r["updates"] > 20 and r["moved"] > 0 and r["fused"] == (collective == "fused")
+    assert res[0]["updates"] == res[1]["updates"]
+
+
+@pytest.mark.parametrize("collective", ["fused", "nccl"])
+def test_sharded_fit_with_tensor_core_updates(tmp_path, collective):
+    """The same sharded fit with bf16 updates: dq_qnet_backward_tc adds its gradient (fp32 atomics) straight into the exchange region
+    (fused) or into the buffer NCCL reduces; the ranks' parameters stay bit-identical."""
+    _need_two_gpus()
+    mp.spawn(_fit_worker, args=(2, 33500 + os.getpid() % 2000, str(tmp_path), collective, 2048, "bf16"), nprocs=2, join=True)
     res = [torch.load(os.path.join(tmp_path, "f%d.pt" % r), weights_only=False) for r in (0, 1)]
     for r in res:
         assert r["identical"] and r["finite"] and r["updates"] > 20 and r["moved"] > 0 and r["fused"] == (collective == "fused")

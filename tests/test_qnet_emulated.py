@@ -207,3 +207,26 @@ def test_emulated_bf16_training_path_matches_rounded_autograd(cfg):
         # (a 5-sample batch averages fewer roundings per entry: looser)
         tol = 1e-2 if B >= 40 else 3e-2
         assert np.linalg.norm(g - want) <= tol * np.linalg.norm(want) + 1e-6, (t, np.linalg.norm(g - want) / np.linalg.norm(want))
+
+
+def test_emulated_bf16_backward_scratch_regrows_with_the_batch():
+    """dq_qnet_backward_tc sizes its scratch for the first batch it sees and regrows it for a larger one: the gradient of a batch
+    does not depend on what the handle computed before."""
+    cc, ff, channels, A = [[8, 3, 2], [8, 2, 1]], [[16, 0.0]], 6, 26
+    rng = np.random.default_rng(5)
+    conv, dense = QR.glorot_uniform_params(rng, channels, cc, [16], A, 11)
+    boards = random_boards(24, channels, 4, density=0.2)
+    dq = rng.standard_normal((24, A)).astype(np.float32)
+
+    def grads(warm_up_batch):
+        q = EQ.EmuQNet(cc, ff, (channels, 11, 11), A, max_batch=24, tc=True)
+        q.set_keras_weights(conv, dense)
+        if warm_up_batch:
+            pk = q.pack(boards[:warm_up_batch])
+            q.forward_tc(pk, train=True)
+            q.backward_tc(pk, dq[:warm_up_batch])
+        pk = q.pack(boards)
+        q.forward_tc(pk, train=True)
+        return q.backward_tc(pk, dq)
+    fresh, regrown = grads(0), grads(7)
+    assert np.array_equal(fresh, regrown) and np.abs(fresh).max() > 0
