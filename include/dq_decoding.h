@@ -121,7 +121,12 @@ int dq_env_rollout_random(dq_env* env, int n_steps, uint8_t* obs_ring, int ring_
                           uint8_t* done, int32_t* lifetime, uint64_t* legal, int32_t* actions_out, int auto_reset,
                           dq_stream stream);
 
-/* Same two calls with HOST buffers (the path bench.py's e2e number times). */
+/* Same two calls with HOST buffers (the path bench.py's e2e number times).  The observation crosses PCIe bit-packed and is expanded into
+ * h_obs by the library's host threads.  The small arrays do not travel by DMA: the kernel reads h_actions from, and stores reward / done /
+ * lifetime / legal masks into, pinned host memory -- the caller's own buffers when they are pinned (cudaHostAlloc / cudaHostRegister, looked
+ * up once per buffer address and handle: a buffer passed here must keep its pinned-or-pageable nature while the handle lives), otherwise a
+ * pinned block of the handle that is memcpy'd to / from the pageable buffers.  h_actions must not be modified between a _begin and its _end.
+ * DQ_HOST_ZEROCOPY=0 / DQ_HOST_DIRECT=0 / DQ_HOST_EXPAND=0 in the environment select the DMA-copy / staged / byte-copy forms (same results). */
 int dq_env_reset_host(dq_env* env, uint8_t* h_obs, uint64_t* h_legal_mask);
 int dq_env_step_host(dq_env* env, const int32_t* h_actions, uint8_t* h_obs, float* h_reward,
                      uint8_t* h_done, int32_t* h_lifetime, uint64_t* h_legal_mask, int auto_reset);
