@@ -175,19 +175,20 @@ def test_emulated_folded_head_is_the_networks_head(which, A):
 # gradients to the fp32 master weights -- so both sides take the same ReLU branches and the comparison is tight (the plain fp32
 # network differs from ANY bf16 forward by a few percent of the gradient norm: pre-activations within rounding distance of zero
 # flip their ReLU branch).
-@pytest.mark.parametrize("cfg", [(REF_CC, [(512, 0.2)], 7, 51, 48), ([[16, 3, 2], [8, 2, 1]], [(32, 0.0), (24, 0.25)], 6, 26, 40),
-                                 ([[8, 3, 2], [8, 2, 1]], [(16, 0.0)], 6, 26, 5)],
-                         ids=["reference_net", "small_two_dense", "ragged_batch"])
+@pytest.mark.parametrize("cfg", [(REF_CC, [(512, 0.2)], 7, 51, 48, 11), ([[16, 3, 2], [8, 2, 1]], [(32, 0.0), (24, 0.25)], 6, 26, 40, 11),
+                                 ([[8, 3, 2], [8, 2, 1]], [(16, 0.0)], 6, 26, 5, 11),
+                                 ([[16, 3, 2], [8, 2, 1], [8, 2, 1]], [(64, 0.2)], 9, 99, 12, 15)],      # BASELINE config C5's geometry: d = 7, 9 x 15 x 15, 99 actions
+                         ids=["reference_net", "small_two_dense", "ragged_batch", "d7_geometry"])
 def test_emulated_bf16_training_path_matches_rounded_autograd(cfg):
-    cc, ff, channels, A, B = cfg
+    cc, ff, channels, A, B, side = cfg
     rng = np.random.default_rng(11)
-    conv, dense = QR.glorot_uniform_params(rng, channels, cc, [u for u, _ in ff], A, 11)
+    conv, dense = QR.glorot_uniform_params(rng, channels, cc, [u for u, _ in ff], A, side)
     for _, b in conv + dense:
         b += rng.standard_normal(b.shape).astype(np.float32) * 0.05
-    q = EQ.EmuQNet(cc, [[u, r] for u, r in ff], (channels, 11, 11), A, max_batch=B, tc=True)
+    q = EQ.EmuQNet(cc, [[u, r] for u, r in ff], (channels, side, side), A, max_batch=B, tc=True)
     q.set_keras_weights(conv, dense)
     net = _Bf16SimQNet(conv, dense, strides=[l[2] for l in cc])
-    boards = random_boards(B, channels, 3, density=0.2)
+    boards = random_boards(B, channels, 3, side=side, density=0.2)
     dq = rng.standard_normal((B, A)).astype(np.float32)
     packed = q.pack(boards)
     seed = 0x1234500077

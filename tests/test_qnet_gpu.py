@@ -435,6 +435,7 @@ def test_reference_script_shape_runs_on_single_lattice(tmp_path):
     (REF_CC, [[512, 0.2]], 7, 51, 1000),                            # the reference architecture, ragged batch (not a multiple of 128 / 64)
     (REF_CC, [[512, 0.0]], 7, 51, 4096),                            # the bench's update batch
     ([[16, 3, 2], [8, 2, 1]], [[32, 0.0], [24, 0.25]], 6, 26, 300),  # two hidden dense layers, narrow tiles
+    (REF_CC, [[512, 0.2]], 9, 99, 700, 15),                         # BASELINE config C5's geometry: d = 7, 9 x 15 x 15 observations, 99 actions
 ])
 def test_bf16_training_path_matches_rounded_autograd(cfg):
     """dq_qnet_forward_tc_train + dq_qnet_backward_tc against the torch network with the same roundings (tests/qnet_util.py;
@@ -443,15 +444,16 @@ def test_bf16_training_path_matches_rounded_autograd(cfg):
     import torch
     from deepq_decoding_b200.qnet import QNetwork
     from qnet_util import Bf16SimQNet, dropout_mask
-    cc, ff, channels, A, B = cfg
-    q = QNetwork(cc, ff, (channels, 11, 11), A, dueling=True, max_batch=B, seed=7)
+    cc, ff, channels, A, B = cfg[:5]
+    side = cfg[5] if len(cfg) > 5 else 11
+    q = QNetwork(cc, ff, (channels, side, side), A, dueling=True, max_batch=B, seed=7)
     conv, dense = q.get_keras_weights()
     rng = np.random.default_rng(3)
     for _, b in conv + dense:
         b += rng.standard_normal(b.shape).astype(np.float32) * 0.05
     q.set_keras_weights(conv, dense)
     net = Bf16SimQNet(conv, dense, strides=[l[2] for l in cc])
-    boards = random_boards(B, channels, 2, density=0.2)
+    boards = (np.random.default_rng(2).random((B, channels, side, side)) < 0.2).astype(np.uint8)
     dq = rng.standard_normal((B, A)).astype(np.float32)
     seed = 0x1234500077
     masks = [torch.tensor(dropout_mask(B, u, r, seed, i)) if r > 0 else None for i, (u, r) in enumerate(ff)]
