@@ -108,6 +108,11 @@ class History:
         for k, v in kw.items():
             self.history.setdefault(k, []).append(v)
 
+    def extend(self, **kw):
+        """Many episodes at once: every value is a sequence of the same length (numpy arrays become Python scalars, as `add` stores)."""
+        for k, v in kw.items():
+            self.history.setdefault(k, []).extend(v.tolist() if hasattr(v, "tolist") else v)
+
 
 class QNetSpec:
     """What `build_convolutional_nn` returns: the architecture, built into a `QNetwork` by the agent."""
@@ -401,14 +406,20 @@ class DQNAgent:
                 upd_window, eps_sum, eps_n = 0, 0.0, 0
                 now = time.time()
                 per_episode_s = (now - t_last) / max(1, int(done.sum()))
+                ep_life, ep_nb, ep_rew, ep_len = [], [], [], []
                 for j in range(k + 1):
                     ep_reward += rew[j]; ep_steps += 1
-                    nb = int(self.step - (k - j) * step_inc)
-                    for i in np.nonzero(done[j])[0]:
-                        entry = book.finish_episode(life[j, i], nb)       # rolling / best / stop rules: episodes.py
-                        hist.add(loss=loss, mean_q=mean_q, mean_eps=mean_eps, episode_reward=float(ep_reward[i]),
-                                 nb_episode_steps=int(ep_steps[i]), nb_steps=nb, duration=per_episode_s, **entry)
-                        ep_reward[i], ep_steps[i] = 0.0, 0
+                    idx = np.nonzero(done[j])[0]
+                    if idx.size:
+                        ep_life.append(life[j, idx]); ep_nb.append(np.full(idx.size, int(self.step - (k - j) * step_inc), np.int64))
+                        ep_rew.append(ep_reward[idx]); ep_len.append(ep_steps[idx])
+                        ep_reward[idx] = 0.0; ep_steps[idx] = 0
+                if ep_life:                                            # rolling / best / stop rules for the whole drain at once: episodes.py
+                    nbs = np.concatenate(ep_nb)
+                    entry = book.finish_many(np.concatenate(ep_life), nbs)
+                    m = nbs.size
+                    hist.extend(loss=[loss] * m, mean_q=[mean_q] * m, mean_eps=[mean_eps] * m, episode_reward=np.concatenate(ep_rew),
+                                nb_episode_steps=np.concatenate(ep_len), nb_steps=nbs, duration=[per_episode_s] * m, **entry)
                 stop = stop or book.stop
                 if self.comm is not None:
                     self.comm.check()                   # a peer that never arrived: abort here, not after the run

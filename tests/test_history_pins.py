@@ -65,6 +65,28 @@ def test_episode_bookkeeping_reproduces_shipped_history(name):
 
 
 @pytest.mark.parametrize("name", NAMES)
+def test_batched_bookkeeping_equals_the_per_episode_form_on_shipped_history(name):
+    """`EpisodeBook.finish_many` (what the vectorised `fit` calls once per drain) over the shipped lifetimes in ragged batches: the same
+    entries and the same final state, to the bit, as `finish_episode` one episode at a time."""
+    g = lambda k: PINS["%s/%s" % (name, k)]
+    L, success, patience, min_steps = g("hyper")[:4]
+    life, nb_steps = np.asarray(g("lifetime")), np.asarray(g("nb_steps"))
+    one, many = episodes.EpisodeBook(int(L), success, patience, min_steps), episodes.EpisodeBook(int(L), success, patience, min_steps)
+    want = [one.finish_episode(int(a), int(b)) for a, b in zip(life, nb_steps)]
+    rng, k, got = np.random.default_rng(len(life)), 0, {}
+    while k < len(life):
+        m = int(rng.integers(0, 700))
+        for key, v in many.finish_many(life[k:k + m], nb_steps[k:k + m]).items():
+            got.setdefault(key, []).extend(np.asarray(v).tolist())
+        k += m
+    for key in want[0]:
+        assert got[key] == [w[key] for w in want], key
+    assert (one.stop, one.episode, one.best_avg, one.best_episode, one.win_n, one.win_sum) == \
+           (many.stop, many.episode, many.best_avg, many.best_episode, many.win_n, many.win_sum) and np.array_equal(one.win, many.win)
+    assert np.allclose(got["episode_lifetimes_rolling_avg"], g("rolling"), rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", NAMES)
 def test_epsilon_schedule_at_first_training_steps(name):
     """loss / mean_q / mean_eps are NaN for every episode that ends by step nb_steps_warmup; the first logged mean_eps is the mean
     of eps(s) over the 0-based step indices s = warmup+1 .. nb_steps-1 of the episode that crosses the warm-up: metrics (and
