@@ -235,6 +235,7 @@ class DQNAgent:
         self._y = torch.zeros(B, dtype=torch.float32, device=dev)
         self._stats = torch.zeros(2, dtype=torch.float32, device=dev)
         self._actions = None
+        self._side = None
         return self
 
     def load_weights(self, path):
@@ -304,8 +305,19 @@ class DQNAgent:
         B, A, st, m = s0.shape[1], self.nb_actions, self._st(), self.model
         p = lambda t: C.c_void_p(t.data_ptr())
         if self.target_model is not None:
+            # Q_online(s') and Q_target(s') are independent chains of five small kernels each (two handles, two sets of buffers): the target
+            # network's chain runs on a side stream beside the online network's
+            main = torch.cuda.current_stream(m.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=m.device)
+                self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+            self._ev_fork.record(main)
+            self._side.wait_event(self._ev_fork)
+            with torch.cuda.stream(self._side):
+                self.target_model.forward_packed(s1.data_ptr(), B, B, out=self._qt[:B], precision="bf16")
+                self._ev_join.record(self._side)
             m.forward_packed(s1.data_ptr(), B, B, out=self._qo[:B], precision="bf16")
-            self.target_model.forward_packed(s1.data_ptr(), B, B, out=self._qt[:B], precision="bf16")
+            main.wait_event(self._ev_join)
         else:
             m.forward_packed(s1.data_ptr(), B, B, out=self._qo[:B])
             m.forward_packed(s1.data_ptr(), B, B, out=self._qt[:B], params=self.target_params)
