@@ -1999,7 +1999,11 @@ extern "C" int dq_qnet_forward_tc_train(dq_qnet* h, const float* params, const u
 // ---- bf16 backward --------------------------------------------------------------------------------------------------------------
 struct dq_qnet_tcb {                    // scratch of dq_qnet_backward_tc, sized for `cap` samples, grown on demand
     long long cap;
-    __nv_bfloat16 *at, *dyb, *dyt, *dcol;
+    __nv_bfloat16 *at, *dyb, *dcol;
+    __nv_bfloat16* dyt[kMaxConv + kMaxDense + 2];       // one transposed gradient per layer: layer j's weight-gradient GEMM reads it on the
+                                                        // side stream while the caller's stream is already staging layer j-1
+    cudaStream_t side;                                  // the weight-gradient chain (A^T, dW GEMM) of every layer, see dq_qnet_backward_tc
+    cudaEvent_t ev_layer[kMaxConv + kMaxDense + 2], ev_start, ev_done;
 };
 struct TcbGeom { int K, N; long long rows, M, Mpad; int rowsA, bn_dw, rows_t, ldyb, bn_dx, npad_dx; };
 static int bn_for(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : 128); }
@@ -2015,7 +2019,11 @@ static TcbGeom tcb_geom(const QCfg& c, int j, long long batch) {
 }
 static void tcb_free(dq_qnet_tcb* b) {
     if (!b) return;
-    cudaFree(b->at); cudaFree(b->dyb); cudaFree(b->dyt); cudaFree(b->dcol);
+    cudaFree(b->at); cudaFree(b->dyb); cudaFree(b->dcol);
+    for (int j = 0; j < kMaxConv + kMaxDense + 2; ++j) { cudaFree(b->dyt[j]); if (b->ev_layer[j]) cudaEventDestroy(b->ev_layer[j]); }
+    if (b->ev_start) cudaEventDestroy(b->ev_start);
+    if (b->ev_done) cudaEventDestroy(b->ev_done);
+    if (b->side) cudaStreamDestroy(b->side);
     delete b;
 }
 static dq_qnet_tcb* tcb_of(dq_qnet* h, long long batch) {
@@ -2024,19 +2032,23 @@ static dq_qnet_tcb* tcb_of(dq_qnet* h, long long batch) {
     tcb_free(tc->bwd);
     tc->bwd = nullptr;
     const QCfg& c = h->c;
-    size_t n_at = 0, n_dyb = 0, n_dyt = 0, n_dcol = 0;
+    size_t n_at = 0, n_dyb = 0, n_dcol = 0;
+    dq_qnet_tcb* b = new dq_qnet_tcb();
+    memset(b, 0, sizeof(*b));
+    cudaError_t err = cudaSuccess;
     for (int j = 0; j < tc_layers(c); ++j) {
         const TcbGeom g = tcb_geom(c, j, batch);
         n_at = std::max<size_t>(n_at, (size_t)g.rowsA * (size_t)g.Mpad);
         n_dyb = std::max<size_t>(n_dyb, (size_t)g.Mpad * (size_t)g.ldyb);
-        n_dyt = std::max<size_t>(n_dyt, (size_t)g.rows_t * (size_t)g.Mpad);
         if (j > 0) n_dcol = std::max<size_t>(n_dcol, (size_t)g.M * (size_t)g.K);
+        if (err == cudaSuccess) err = cudaMalloc(&b->dyt[j], (size_t)g.rows_t * (size_t)g.Mpad * 2);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_layer[j], cudaEventDisableTiming);
     }
-    dq_qnet_tcb* b = new dq_qnet_tcb();
-    memset(b, 0, sizeof(*b));
-    cudaError_t err = cudaMalloc(&b->at, n_at * 2);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_start, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaMalloc(&b->at, n_at * 2);
     if (err == cudaSuccess) err = cudaMalloc(&b->dyb, n_dyb * 2);
-    if (err == cudaSuccess) err = cudaMalloc(&b->dyt, n_dyt * 2);
     if (err == cudaSuccess) err = cudaMalloc(&b->dcol, std::max<size_t>(n_dcol, 8) * 2);
     if (err != cudaSuccess) { tcb_free(b); return nullptr; }
     b->cap = batch;
@@ -2080,6 +2092,15 @@ extern "C" int dq_qnet_backward_tc(dq_qnet* h, const float* params, const uint64
     if (!sb) return qfail(DQ_ECUDA, "allocating the backward scratch failed");
     const int n_tc = tc_layers(c);
     QCUDA(cudaMemsetAsync(grads, 0, (size_t)c.n_params * sizeof(float), st));
+    // Two chains per layer share only the staged gradient: the COLUMN-gradient chain (dX GEMM -> the staging of the layer below) is what
+    // the next layer waits for and stays on the caller's stream; the WEIGHT-gradient chain (A^T, dW GEMM) of every layer runs on a side
+    // stream, released layer by layer by an event and joined at the end (DQ_TC_BWD_STREAMS=0: everything on the caller's stream).
+    static const bool two_streams = [] { const char* e = getenv("DQ_TC_BWD_STREAMS"); return !(e && e[0] == '0'); }();
+    cudaStream_t sw = two_streams ? sb->side : st;
+    if (two_streams) {
+        QCUDA(cudaEventRecord(sb->ev_start, st));                   // the gradient buffer is zero, the previous user of the scratch is done
+        QCUDA(cudaStreamWaitEvent(sb->side, sb->ev_start, 0));
+    }
     // head: G = gradient at the output of Dense(num_actions), fp32 [batch][A]
     const float* G32 = dq;
     if (c.dueling) {
@@ -2111,23 +2132,27 @@ extern "C" int dq_qnet_backward_tc(dq_qnet* h, const float* params, const uint64
             else src.mode = 1;                                                      // a dense layer above: its column gradient is this layer's map
         }
         const int ncols = std::max(g.ldyb, g.rows_t);
-        DQ_LAUNCH_PDL(prep_dy_kernel, dim3((unsigned)(g.Mpad / 64), (ncols + 63) / 64), 256, 0, st, src, act, mask, g.M, g.N, sb->dyb, g.ldyb, sb->dyt, g.Mpad, g.rows_t,
+        DQ_LAUNCH_PDL(prep_dy_kernel, dim3((unsigned)(g.Mpad / 64), (ncols + 63) / 64), 256, 0, st, src, act, mask, g.M, g.N, sb->dyb, g.ldyb, sb->dyt[j], g.Mpad, g.rows_t,
                                                                                       grads + c.b_off[j]);
         count_launch();
+        if (two_streams) {
+            QCUDA(cudaEventRecord(sb->ev_layer[j], st));
+            QCUDA(cudaStreamWaitEvent(sb->side, sb->ev_layer[j], 0));
+        }
         // 2. A^T, then dW = A^T x dY over the batch
         if (j == 0) {
             const ConvL& L = c.conv[0];
-            DQ_LAUNCH_PDL(im2colT_bits_kernel, dim3((unsigned)((g.Mpad + 255) / 256), 1), 256, 0, st, (const u64*)packed, stride, L, c.C, c.PW, c.H, g.M, sb->at, g.Mpad, g.rowsA);
+            DQ_LAUNCH_PDL(im2colT_bits_kernel, dim3((unsigned)((g.Mpad + 255) / 256), 1), 256, 0, sw, (const u64*)packed, stride, L, c.C, c.PW, c.H, g.M, sb->at, g.Mpad, g.rowsA);
         } else {
             const Patch pg = j < c.n_conv ? conv_patch(c.conv[j]) : dense_patch(g.K);
-            DQ_LAUNCH_PDL(im2colT_kernel, dim3((unsigned)(g.Mpad / 64), g.rowsA / 64), 256, 0, st, tc->act[j - 1], pg, g.M, g.K, sb->at, g.Mpad);
+            DQ_LAUNCH_PDL(im2colT_kernel, dim3((unsigned)(g.Mpad / 64), g.rowsA / 64), 256, 0, sw, tc->act[j - 1], pg, g.M, g.K, sb->at, g.Mpad);
         }
         count_launch();
         int rc;
         switch (g.bn_dw) {
-            case 32: rc = launch_tc_dw<32>(sb->at, g.Mpad, sb->dyt, g.Mpad, grads + c.w_off[j], g.N, g.K, g.N, g.rowsA, g.rows_t, st); break;
-            case 64: rc = launch_tc_dw<64>(sb->at, g.Mpad, sb->dyt, g.Mpad, grads + c.w_off[j], g.N, g.K, g.N, g.rowsA, g.rows_t, st); break;
-            default: rc = launch_tc_dw<128>(sb->at, g.Mpad, sb->dyt, g.Mpad, grads + c.w_off[j], g.N, g.K, g.N, g.rowsA, g.rows_t, st); break;
+            case 32: rc = launch_tc_dw<32>(sb->at, g.Mpad, sb->dyt[j], g.Mpad, grads + c.w_off[j], g.N, g.K, g.N, g.rowsA, g.rows_t, sw); break;
+            case 64: rc = launch_tc_dw<64>(sb->at, g.Mpad, sb->dyt[j], g.Mpad, grads + c.w_off[j], g.N, g.K, g.N, g.rowsA, g.rows_t, sw); break;
+            default: rc = launch_tc_dw<128>(sb->at, g.Mpad, sb->dyt[j], g.Mpad, grads + c.w_off[j], g.N, g.K, g.N, g.rowsA, g.rows_t, sw); break;
         }
         if (rc) return rc;
         if (j == 0) break;
@@ -2140,6 +2165,10 @@ extern "C" int dq_qnet_backward_tc(dq_qnet* h, const float* params, const uint64
             rc = launch_tc_bn<0>(a, g.bn_dx, g.npad_dx, st);
             if (rc) return rc;
         }
+    }
+    if (two_streams) {
+        QCUDA(cudaEventRecord(sb->ev_done, sb->side));
+        QCUDA(cudaStreamWaitEvent(st, sb->ev_done, 0));             // the caller's stream sees the whole gradient
     }
     QCUDA(cudaGetLastError());
     return DQ_OK;
