@@ -215,6 +215,9 @@ class DQNAgent:
             self.target_model = QNetwork(s.cc_layers, s.ff_layers, s.input_shape, s.num_actions, dueling=self.dueling,
                                          max_batch=self.batch_size, device=self.device, seed=self.seed)
             self.target_model.params = self.target_params
+        # a second handle on the ONLINE parameters for the no-grad forward of an update, so that it can run beside the training forward
+        # (which uses the first handle's tensor-core buffers when train_precision is bf16)
+        self.online_twin = None                     # built by update() when it is first needed
         self.grads = torch.zeros(n, dtype=torch.float32, device=self.model.device)
         self.adam_m, self.adam_v = torch.zeros_like(self.grads), torch.zeros_like(self.grads)
         if self.process_group is not None and self.collective == "fused":
@@ -304,27 +307,41 @@ class DQNAgent:
         """backward() of keras-rl for one batch of packed transitions (all device tensors)."""
         B, A, st, m = s0.shape[1], self.nb_actions, self._st(), self.model
         p = lambda t: C.c_void_p(t.data_ptr())
+        tp = self.train_precision
         if self.target_model is not None:
-            # Q_online(s') and Q_target(s') are independent chains of five small kernels each (two handles, two sets of buffers): the target
-            # network's chain runs on a side stream beside the online network's
+            # Q_target(s'), Q_online(s') and the training forward on s are three independent chains of five to seven small kernels: they run
+            # on three streams (the target network and -- when the training forward also uses the tensor-core buffers -- a twin of the
+            # online network have their own handles, i.e. their own activation buffers and staged weights)
             main = torch.cuda.current_stream(m.device)
             if self._side is None:
-                self._side = torch.cuda.Stream(device=m.device)
-                self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
-            self._ev_fork.record(main)
-            self._side.wait_event(self._ev_fork)
-            with torch.cuda.stream(self._side):
+                self._side = (torch.cuda.Stream(device=m.device), torch.cuda.Stream(device=m.device))
+                self._ev = tuple(torch.cuda.Event() for _ in range(3))
+            fork, join_t, join_o = self._ev
+            fork.record(main)
+            with torch.cuda.stream(self._side[0]):
+                self._side[0].wait_event(fork)
                 self.target_model.forward_packed(s1.data_ptr(), B, B, out=self._qt[:B], precision="bf16")
-                self._ev_join.record(self._side)
-            m.forward_packed(s1.data_ptr(), B, B, out=self._qo[:B], precision="bf16")
-            main.wait_event(self._ev_join)
+                join_t.record(self._side[0])
+            if tp == "bf16" and self.online_twin is None:
+                sp = self.spec
+                self.online_twin = QNetwork(sp.cc_layers, sp.ff_layers, sp.input_shape, sp.num_actions, dueling=self.dueling,
+                                            max_batch=self.batch_size, device=self.device, seed=self.seed)
+                self.online_twin.share_params_with(m)
+            online = self.online_twin if tp == "bf16" else m
+            with torch.cuda.stream(self._side[1]):
+                self._side[1].wait_event(fork)
+                online.forward_packed(s1.data_ptr(), B, B, out=self._qo[:B], precision="bf16")
+                join_o.record(self._side[1])
+            self.updates += 1
+            m.forward_packed(s0.data_ptr(), B, B, out=self._q[:B], train=True, dropout_seed=(self.seed << 20) ^ self.updates, precision=tp)
+            main.wait_event(join_t); main.wait_event(join_o)
+            _lib.check(self.L.dq_dqn_targets(p(self._qo), p(self._qt), p(reward), p(terminal), self.gamma, B, A, p(self._y), st))
         else:
             m.forward_packed(s1.data_ptr(), B, B, out=self._qo[:B])
             m.forward_packed(s1.data_ptr(), B, B, out=self._qt[:B], params=self.target_params)
-        _lib.check(self.L.dq_dqn_targets(p(self._qo), p(self._qt), p(reward), p(terminal), self.gamma, B, A, p(self._y), st))
-        self.updates += 1
-        tp = self.train_precision
-        m.forward_packed(s0.data_ptr(), B, B, out=self._q[:B], train=True, dropout_seed=(self.seed << 20) ^ self.updates, precision=tp)
+            _lib.check(self.L.dq_dqn_targets(p(self._qo), p(self._qt), p(reward), p(terminal), self.gamma, B, A, p(self._y), st))
+            self.updates += 1
+            m.forward_packed(s0.data_ptr(), B, B, out=self._q[:B], train=True, dropout_seed=(self.seed << 20) ^ self.updates, precision=tp)
         _lib.check(self.L.dq_dqn_loss_grad(p(self._q), p(actions), p(self._y), B, A, p(self._dq), p(self._stats), st))
         o = self.optimizer
         if self.comm is not None:          # gradient mean over the ranks fused with the Adam step (csrc/dq_comm.cu)

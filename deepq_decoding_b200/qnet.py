@@ -102,7 +102,7 @@ class QNetwork:
             flat[wo:wo + K * N] = k.reshape(-1)
             flat[bo:bo + N] = np.asarray(b, np.float32)
         self.params.copy_(torch.from_numpy(flat))
-        self._tc_dirty = True
+        self.params_changed()
 
     def get_keras_weights(self):
         flat = self.params.detach().cpu().numpy()
@@ -211,8 +211,20 @@ class QNetwork:
         return self.backward_packed(self._packed.data_ptr(), B, B, dq.contiguous(), g, precision=precision)
 
     def params_changed(self):
-        """Tell the network its flat parameter buffer was modified in place (optimizer step, copy)."""
+        """Tell the network its flat parameter buffer was modified in place (optimizer step, copy).  Handles that share the buffer
+        (`share_params_with`) are told too."""
         self._tc_dirty = True
+        for other in getattr(self, "_sharers", ()):
+            other._tc_dirty = True
+
+    def share_params_with(self, owner):
+        """Make this handle a second view of `owner`'s parameters (own activation buffers and staged bf16 weights, same flat fp32
+        buffer): what lets two forwards of one network run side by side on two streams."""
+        self.params = owner.params
+        self._tc_dirty = True
+        if not hasattr(owner, "_sharers"):
+            owner._sharers = []
+        owner._sharers.append(self)
 
     def backward_packed(self, packed_ptr, stride, batch, dq, grads, params=None, precision="fp32"):
         p = self.params if params is None else params
