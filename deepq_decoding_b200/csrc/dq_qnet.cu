@@ -1317,6 +1317,99 @@ tc_gemm_pipe_kernel(const TcArgs a) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((u32)(BN < 32 ? 32 : BN)) : "memory");
 }
 
+
+struct Tmap2D { CUtensorMap m; };
+// bf16 matrix [rows][ld] (ld % 8 == 0) as a tiled tensor map with boxes of 64 columns x box_rows rows; columns >= cols and rows >= rows read as zero
+static bool make_tmap_2d(Tmap2D* out, const __nv_bfloat16* base, long long rows, long long ld, int box_rows, long long cols = -1) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static const EncodeFn fn = [] {         // the driver entry point through the runtime: the library does not link libcuda
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return (EncodeFn)f;
+    }();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)(cols < 0 ? ld : cols), (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__nv_bfloat16)};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return fn(&out->m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+__device__ __forceinline__ void tma_load_2d(u32 smem_dst, const Tmap2D* map, int c_inner, int c_outer, u64* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer) : "memory");
+}
+// Dense layers (A = a plain [M][K] bf16 matrix, K <= 512): every K block of the tile has its own shared-memory stage and "full" mbarrier,
+// so ONE producer thread puts all of the tile's loads in flight at once (TMA, SWIZZLE_128B) -- a dense layer of this network is a
+// handful of CTAs whose time is the latency of their loads, not bandwidth -- and the MMA thread consumes the stages in order; the
+// epilogue is the forward kernels' (bias + ReLU + convert, rows staged through the freed operand memory).
+template <int BN>
+__global__ void __launch_bounds__(128)
+tc_gemm_tma_kernel(const __grid_constant__ Tmap2D ta, const __grid_constant__ Tmap2D tw, const TcArgs a) {
+    constexpr u32 STAGE = 16384u + (u32)BN * 128u;
+    extern __shared__ unsigned char tc_raw[];
+    __shared__ alignas(8) u64 bar_full[8], bar_accum;
+    __shared__ u32 tmem_slot;
+    __shared__ alignas(16) float sbias[BN];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KB = a.Kpad >> 6;                                     // <= 8 (host-checked)
+    const u32 s_base = (smem_u32(tc_raw) + 1023u) & ~1023u;
+    const long long m0 = (long long)blockIdx.x * 128;
+    const int n0 = blockIdx.y * BN;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((u32)(BN < 32 ? 32 : BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int s = 0; s < KB; ++s) mbar_init(&bar_full[s], 1);
+        mbar_init(&bar_accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    if (warp == 0) pdl_launch_dependents();
+    pdl_wait();
+    if (tid < BN) sbias[tid] = (a.bias && n0 + tid < a.N) ? a.bias[n0 + tid] : 0.f;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const u32 tmem = tmem_slot;
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar_full[kb])), "r"(STAGE) : "memory");
+                const u32 sA = s_base + (u32)kb * STAGE;
+                tma_load_2d(sA, &ta, kb * 64, (int)m0, &bar_full[kb]);
+                tma_load_2d(sA + 16384u, &tw, kb * 64, n0, &bar_full[kb]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const u32 idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(BN >> 3) << 17) | ((u32)(128 >> 4) << 24);
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait_or_trap(&bar_full[kb], 0u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const u32 sA = s_base + (u32)kb * STAGE;
+                const uint64_t da = umma_smem_desc(sA), db = umma_smem_desc(sA + 16384u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_accum)) : "memory");
+        }
+        __syncwarp();
+    }
+    mbar_wait_or_trap(&bar_accum, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const long long m = m0 + tid;
+    tc_epilogue<BN>(a, tmem, warp, m, m < a.M, n0, sbias, s_base);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((u32)(BN < 32 ? 32 : BN)) : "memory");
+}
 // [tcgen05 kernels: end]
 
 // Fused head for the acting path: y = x W + b for the last (tiny) dense layer, then the dueling combination.
@@ -1456,29 +1549,6 @@ head_dueling_kernel(const float* __restrict__ x, const float* __restrict__ W, co
 // and commits them to the stage's "empty" mbarrier; all four warps drain the accumulator at the end.  No thread of the CTA touches the
 // operand bytes.  SASS: UTMALDG, UTCHMMA, UTCBAR, SYNCS.  Measured against the same GEMM fed by a 128-thread cp.async ring (the forward
 // kernel's scheme): 5-9 % less time per dW launch, 529 -> 521 us per batch-4096 update.
-struct Tmap2D { CUtensorMap m; };
-// bf16 matrix [rows][ld] (ld % 64 == 0, every column readable) as a tiled tensor map with boxes of 64 columns x box_rows rows
-static bool make_tmap_2d(Tmap2D* out, const __nv_bfloat16* base, long long rows, long long ld, int box_rows) {
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static const EncodeFn fn = [] {         // the driver entry point through the runtime: the library does not link libcuda
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
-        return (EncodeFn)f;
-    }();
-    if (!fn) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__nv_bfloat16)};
-    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1u, 1u};
-    return fn(&out->m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-__device__ __forceinline__ void tma_load_2d(u32 smem_dst, const Tmap2D* map, int c_inner, int c_outer, u64* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer) : "memory");
-}
 template <int BN, int S>
 __global__ void __launch_bounds__(128)
 tc_dw_tma_kernel(const __grid_constant__ Tmap2D ta, const __grid_constant__ Tmap2D tb, float* __restrict__ D, int ldd, int R, int N,
@@ -1872,6 +1942,31 @@ static int launch_tc_bn(const TcArgs& a, int bn, int npad, cudaStream_t st) {
     }
 }
 
+// dense layers through the TMA-fed kernel: A = [M][K] bf16 with leading dimension lda, all K blocks resident (Kpad <= 512)
+template <int BN>
+static int launch_tc_dense_tma(const TcArgs& a, long long lda, int npad, cudaStream_t st) {
+    const int KB = a.Kpad >> 6;
+    const size_t smem = (size_t)KB * (16384 + (size_t)BN * 128) + 1024;
+    Tmap2D ta, tw;
+    if (!make_tmap_2d(&ta, a.X, a.M, lda, 128, a.K) || !make_tmap_2d(&tw, a.Wt, npad, a.Kpad, BN)) return qfail(DQ_ECUDA, "cuTensorMapEncodeTiled failed");
+    QCUDA(cudaFuncSetAttribute(tc_gemm_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DQ_LAUNCH_PDL((tc_gemm_tma_kernel<BN>), dim3((unsigned)((a.M + 127) / 128), npad / BN), 128, smem, st, ta, tw, a);
+    count_launch();
+    return DQ_OK;
+}
+static bool tc_dense_tma_ok(const TcArgs& a, int bn) {
+    static const bool on = [] { const char* e = getenv("DQ_TC_DENSE_TMA"); return !(e && e[0] == '0'); }();
+    const int KB = a.Kpad >> 6;
+    return on && KB >= 1 && KB <= 8 && (size_t)KB * (16384 + (size_t)bn * 128) + 1024 <= 227 * 1024 && (a.K % 8) == 0;
+}
+static int launch_tc_dense(const TcArgs& a, long long lda, int bn, int npad, cudaStream_t st) {
+    switch (bn) {
+        case 32: return launch_tc_dense_tma<32>(a, lda, npad, st);
+        case 64: return launch_tc_dense_tma<64>(a, lda, npad, st);
+        default: return launch_tc_dense_tma<128>(a, lda, npad, st);
+    }
+}
+
 static int tc_check(const dq_qnet* h) {
     const QCfg& c = h->c;
     if (c.n_hidden < 1) return qfail(DQ_EINVAL, "tensor-core path needs >= 1 hidden dense layer");
@@ -1948,7 +2043,8 @@ static int tc_forward(dq_qnet* h, const float* params, const uint64_t* packed, i
             rc = launch_tc_bn<1>(a, tc->bn[j], tc->npad[j], st);
         } else {
             a.X = tc->act[j - 1];
-            rc = launch_tc_bn<0>(a, tc->bn[j], tc->npad[j], st);
+            if (j >= c.n_conv && tc_dense_tma_ok(a, tc->bn[j])) rc = launch_tc_dense(a, a.K, tc->bn[j], tc->npad[j], st);      // dense layer: its input rows are contiguous
+            else rc = launch_tc_bn<0>(a, tc->bn[j], tc->npad[j], st);
         }
         if (rc) return rc;
         if (train && j >= c.n_conv && !last && c.drop[j - c.n_conv] > 0.f) {     // Dropout after a hidden dense layer (FL:366-370)
