@@ -1944,26 +1944,27 @@ static int launch_tc_bn(const TcArgs& a, int bn, int npad, cudaStream_t st) {
 
 // dense layers through the TMA-fed kernel: A = [M][K] bf16 with leading dimension lda, all K blocks resident (Kpad <= 512)
 template <int BN>
-static int launch_tc_dense_tma(const TcArgs& a, long long lda, int npad, cudaStream_t st) {
+static int launch_tc_dense_tma(const TcArgs& a, long long lda, long long cols, int npad, cudaStream_t st) {
     const int KB = a.Kpad >> 6;
     const size_t smem = (size_t)KB * (16384 + (size_t)BN * 128) + 1024;
     Tmap2D ta, tw;
-    if (!make_tmap_2d(&ta, a.X, a.M, lda, 128, a.K) || !make_tmap_2d(&tw, a.Wt, npad, a.Kpad, BN)) return qfail(DQ_ECUDA, "cuTensorMapEncodeTiled failed");
+    if (!make_tmap_2d(&ta, a.X, a.M, lda, 128, cols) || !make_tmap_2d(&tw, a.Wt, npad, a.Kpad, BN)) return qfail(DQ_ECUDA, "cuTensorMapEncodeTiled failed");
     QCUDA(cudaFuncSetAttribute(tc_gemm_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DQ_LAUNCH_PDL((tc_gemm_tma_kernel<BN>), dim3((unsigned)((a.M + 127) / 128), npad / BN), 128, smem, st, ta, tw, a);
     count_launch();
     return DQ_OK;
 }
-static bool tc_dense_tma_ok(const TcArgs& a, int bn) {
+static bool tc_dense_tma_ok(const TcArgs& a, int bn, long long lda) {
     static const bool on = [] { const char* e = getenv("DQ_TC_DENSE_TMA"); return !(e && e[0] == '0'); }();
     const int KB = a.Kpad >> 6;
-    return on && KB >= 1 && KB <= 8 && (size_t)KB * (16384 + (size_t)bn * 128) + 1024 <= 227 * 1024 && (a.K % 8) == 0;
+    return on && KB >= 1 && KB <= 8 && (size_t)KB * (16384 + (size_t)bn * 128) + 1024 <= 227 * 1024 && (lda % 8) == 0;
 }
-static int launch_tc_dense(const TcArgs& a, long long lda, int bn, int npad, cudaStream_t st) {
+// lda = leading dimension of A, cols = its readable columns (anything beyond reads as zero)
+static int launch_tc_dense(const TcArgs& a, long long lda, long long cols, int bn, int npad, cudaStream_t st) {
     switch (bn) {
-        case 32: return launch_tc_dense_tma<32>(a, lda, npad, st);
-        case 64: return launch_tc_dense_tma<64>(a, lda, npad, st);
-        default: return launch_tc_dense_tma<128>(a, lda, npad, st);
+        case 32: return launch_tc_dense_tma<32>(a, lda, cols, npad, st);
+        case 64: return launch_tc_dense_tma<64>(a, lda, cols, npad, st);
+        default: return launch_tc_dense_tma<128>(a, lda, cols, npad, st);
     }
 }
 
@@ -2043,7 +2044,7 @@ static int tc_forward(dq_qnet* h, const float* params, const uint64_t* packed, i
             rc = launch_tc_bn<1>(a, tc->bn[j], tc->npad[j], st);
         } else {
             a.X = tc->act[j - 1];
-            if (j >= c.n_conv && tc_dense_tma_ok(a, tc->bn[j])) rc = launch_tc_dense(a, a.K, tc->bn[j], tc->npad[j], st);      // dense layer: its input rows are contiguous
+            if (j >= c.n_conv && tc_dense_tma_ok(a, tc->bn[j], a.K)) rc = launch_tc_dense(a, a.K, a.K, tc->bn[j], tc->npad[j], st);      // dense layer: its input rows are contiguous
             else rc = launch_tc_bn<0>(a, tc->bn[j], tc->npad[j], st);
         }
         if (rc) return rc;
@@ -2258,7 +2259,8 @@ extern "C" int dq_qnet_backward_tc(dq_qnet* h, const float* params, const uint64
             memset(&a, 0, sizeof(a));
             a.X = sb->dyb; a.g = dense_patch(g.ldyb); a.Wt = tc->wb[j]; a.bias = nullptr; a.Y = sb->dcol; a.ldy = g.K; a.out_bf16 = 1; a.relu = 0;
             a.M = g.M; a.N = g.K; a.K = g.N; a.Kpad = g.ldyb;
-            rc = launch_tc_bn<0>(a, g.bn_dx, g.npad_dx, st);
+            // (the staged gradient is a plain [M][ldyb] matrix whatever the layer: the dense-layer kernel, all K blocks in flight)
+            rc = tc_dense_tma_ok(a, g.bn_dx, g.ldyb) ? launch_tc_dense(a, g.ldyb, g.ldyb, g.bn_dx, g.npad_dx, st) : launch_tc_bn<0>(a, g.bn_dx, g.npad_dx, st);
             if (rc) return rc;
         }
     }
