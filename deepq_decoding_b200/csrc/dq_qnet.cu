@@ -1330,12 +1330,23 @@ static bool make_tmap_2d(Tmap2D* out, const __nv_bfloat16* base, long long rows,
         return (EncodeFn)f;
     }();
     if (!fn) return false;
+    // a tensor map is a pure function of these arguments: the last few are kept (an update re-encodes the same ~30 maps every time)
+    struct Key { const void* base; long long rows, ld, cols; int box; };
+    struct Slot { Key k; Tmap2D m; };
+    static thread_local Slot cache[64];
+    static thread_local int used = 0, next = 0;
+    const Key key{base, rows, ld, cols, box_rows};
+    for (int i = 0; i < used; ++i)
+        if (cache[i].k.base == key.base && cache[i].k.rows == key.rows && cache[i].k.ld == key.ld && cache[i].k.cols == key.cols && cache[i].k.box == key.box) { *out = cache[i].m; return true; }
     const cuuint64_t dims[2] = {(cuuint64_t)(cols < 0 ? ld : cols), (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__nv_bfloat16)};
     const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1u, 1u};
-    return fn(&out->m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (fn(&out->m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    const int slot = used < 64 ? used++ : (next = (next + 1) % 64);
+    cache[slot].k = key; cache[slot].m = *out;
+    return true;
 }
 __device__ __forceinline__ void tma_load_2d(u32 smem_dst, const Tmap2D* map, int c_inner, int c_outer, u64* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -1907,6 +1918,27 @@ static bool tc_pipe_enabled() {
     static const bool on = [] { const char* e = getenv("DQ_TC_PIPE"); return !(e && e[0] == '0'); }();
     return on;
 }
+// Opt a kernel in to all the dynamic shared memory the device allows beside its static part, once per (kernel, device): the attribute is a cap, not a
+// reservation, and a driver call per launch is measurable when an update is 75 launches of a few microseconds.
+template <auto Kernel>                  // one instantiation, and one set of flags, per kernel FUNCTION (a type parameter would merge all kernels of one signature)
+static cudaError_t allow_big_smem() {
+#ifdef DQ_EMU
+    return cudaSuccess;
+#else
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    cudaFuncAttributes fa;
+    int optin = 0;
+    cudaError_t e = cudaFuncGetAttributes(&fa, Kernel);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);      // the opt-in limit covers static + dynamic
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
+#endif
+}
+
 template <int BN, int AMODE>
 static int launch_tc(const TcArgs& a, int npad, cudaStream_t st) {
     if (AMODE == 0 && (a.Kpad >> 6) >= 2 && tc_pipe_enabled()) {
@@ -1916,10 +1948,10 @@ static int launch_tc(const TcArgs& a, int npad, cudaStream_t st) {
         const bool deep = (long long)grid.x * grid.y <= 2 * 148 && (a.Kpad >> 6) >= 4;
         const size_t smem = (deep ? 4 : 2) * (16384 + (size_t)BN * 128) + 1024;
         if (deep) {
-            QCUDA(cudaFuncSetAttribute(tc_gemm_pipe_kernel<BN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QCUDA((allow_big_smem<tc_gemm_pipe_kernel<BN, 4>>()));
             DQ_LAUNCH_PDL((tc_gemm_pipe_kernel<BN, 4>), grid, 128, smem, st, a);
         } else {
-            QCUDA(cudaFuncSetAttribute(tc_gemm_pipe_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QCUDA((allow_big_smem<tc_gemm_pipe_kernel<BN, 2>>()));
             DQ_LAUNCH_PDL((tc_gemm_pipe_kernel<BN, 2>), grid, 128, smem, st, a);
         }
         count_launch();
@@ -1927,7 +1959,7 @@ static int launch_tc(const TcArgs& a, int npad, cudaStream_t st) {
     }
     const size_t smem = (size_t)(128 + BN) * (a.Kpad >> 6) * 128 + 1024;
     if (smem > 227 * 1024) return qfail(DQ_EINVAL, "tensor-core tile does not fit shared memory");
-    QCUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QCUDA((allow_big_smem<tc_gemm_kernel<BN, AMODE>>()));
     dim3 grid((unsigned)((a.M + 127) / 128), npad / BN);
     DQ_LAUNCH_PDL((tc_gemm_kernel<BN, AMODE>), grid, 128, smem, st, a);
     count_launch();
@@ -1949,7 +1981,7 @@ static int launch_tc_dense_tma(const TcArgs& a, long long lda, long long cols, i
     const size_t smem = (size_t)KB * (16384 + (size_t)BN * 128) + 1024;
     Tmap2D ta, tw;
     if (!make_tmap_2d(&ta, a.X, a.M, lda, 128, cols) || !make_tmap_2d(&tw, a.Wt, npad, a.Kpad, BN)) return qfail(DQ_ECUDA, "cuTensorMapEncodeTiled failed");
-    QCUDA(cudaFuncSetAttribute(tc_gemm_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QCUDA((allow_big_smem<tc_gemm_tma_kernel<BN>>()));
     DQ_LAUNCH_PDL((tc_gemm_tma_kernel<BN>), dim3((unsigned)((a.M + 127) / 128), npad / BN), 128, smem, st, ta, tw, a);
     count_launch();
     return DQ_OK;
@@ -2157,7 +2189,7 @@ static int launch_tc_dw(const __nv_bfloat16* At, long long lda, const __nv_bfloa
                         int rowsA, int rows_t, cudaStream_t st) {
     constexpr int S = 4;
     const size_t smem = (size_t)S * (16384 + (size_t)BN * 128) + 1024;
-    QCUDA(cudaFuncSetAttribute(tc_dw_tma_kernel<BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QCUDA((allow_big_smem<tc_dw_tma_kernel<BN, S>>()));
     const int kb_total = (int)(lda / 64);
     const int tiles = (rowsA / 128) * (rows_t / BN);
     // the contraction (batch x positions) is cut into slices over grid.z: about two CTAs per SM, at least 16 chunks of 64 per CTA (measured at batch 4096: 4 -> 556 us per update, 8 -> 536, 16 -> 529, 32 -> 554, 64 -> 623)
