@@ -454,6 +454,58 @@ __global__ void dueling_bwd_kernel(const float* __restrict__ dq, float* __restri
     dy[b * (A + 1)] = s;
     for (int a = 0; a < A; ++a) dy[b * (A + 1) + 1 + a] = dq[b * A + a] - s / (float)A;
 }
+// The whole backward step of the dueling layer Dense(A -> A+1) + 'avg' combine in ONE launch (it is 4 of the 45 launches of a bf16
+// update, all on the chain every other layer waits for): per CTA of 32 samples, dY = combine^T(dq) in shared memory, then
+//   dX[b][k] = sum_n dY[b][n] W[k][n]      (the gradient at the output of Dense(A), what the tensor-core layers consume)
+//   dW[k][n] += sum_b x[b][k] dY[b][n],  db[n] += sum_b dY[b][n]      (fp32 atomics: one partial per CTA)
+// x = the layer's input (Dense(A) output, fp32 [B][K]), W [K][N = A+1], K = A.
+constexpr int kHeadBwdSamples = 32;
+__global__ void __launch_bounds__(128)
+head_dueling_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ x, const float* __restrict__ W, long long B, int K, int N, int A,
+                        float* __restrict__ dX, float* __restrict__ dW, float* __restrict__ db) {
+    pdl_launch_dependents(); pdl_wait();
+    extern __shared__ __align__(16) float hb[];          // W [K][N], dY [32][N], x [32][K]
+    float* sW = hb;
+    float* sY = sW + K * N;
+    float* sX = sY + kHeadBwdSamples * N;
+    const int tid = threadIdx.x;
+    const long long b0 = (long long)blockIdx.x * kHeadBwdSamples;
+    const int nrow = (int)min((long long)kHeadBwdSamples, B - b0);
+    for (int i = tid; i < K * N; i += 128) sW[i] = W[i];
+    for (int i = tid; i < kHeadBwdSamples * K; i += 128) sX[i] = (i / K < nrow) ? x[b0 * K + i] : 0.f;
+    if (tid < kHeadBwdSamples) {                            // dueling_bwd_kernel for one sample
+        float* y = sY + tid * N;
+        if (tid < nrow) {
+            const float* g = dq + (b0 + tid) * A;
+            float sum = 0.f;
+            for (int a = 0; a < A; ++a) sum += g[a];
+            y[0] = sum;
+            for (int a = 0; a < A; ++a) y[1 + a] = g[a] - sum / (float)A;
+        } else {
+            for (int n = 0; n < N; ++n) y[n] = 0.f;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < nrow * K; i += 128) {
+        const int r = i / K, k = i - r * K;
+        const float* y = sY + r * N;
+        const float* w = sW + k * N;
+        float acc = 0.f;
+        for (int n = 0; n < N; ++n) acc = fmaf(y[n], w[n], acc);
+        dX[(b0 + r) * K + k] = acc;
+    }
+    for (int i = tid; i < K * N; i += 128) {
+        const int k = i / N, n = i - k * N;
+        float acc = 0.f;
+        for (int r = 0; r < kHeadBwdSamples; ++r) acc = fmaf(sX[r * K + k], sY[r * N + n], acc);
+        if (acc != 0.f) atomicAdd(dW + i, acc);
+    }
+    if (tid < N) {
+        float acc = 0.f;
+        for (int r = 0; r < kHeadBwdSamples; ++r) acc += sY[r * N + tid];
+        if (acc != 0.f) atomicAdd(db + tid, acc);
+    }
+}
 // Keras-2 Adam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v EMA; p -= lr_t*m/(sqrt(v)+eps).  g is scaled by gscale first
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
                             long long n, float lr_t, float b1, float b2, float eps, float gscale) {
@@ -2234,15 +2286,22 @@ extern "C" int dq_qnet_backward_tc(dq_qnet* h, const float* params, const uint64
     const float* G32 = dq;
     if (c.dueling) {
         const int i = c.n_fc - 1, t = c.n_conv + i, K = c.fc_in[i], N = c.fc_out[i];
-        float* dY = h->dact_fc[i];
-        DQ_LAUNCH_PDL(dueling_bwd_kernel, (unsigned)((batch + 127) / 128), 128, 0, st, dq, dY, batch, c.A);
-        const long long chunk = dw_chunk(batch, K, N);
-        dim3 gw((K + TB - 1) / TB, (N + TB - 1) / TB, (unsigned)((batch + chunk - 1) / chunk));
-        DQ_LAUNCH_PDL(gemm_dw_kernel, gw, 256, 0, st, h->act_fc[i - 1], dense_patch(K), dY, grads + c.w_off[t], batch, N, K, chunk);
-        DQ_LAUNCH_PDL(colsum_kernel, dim3((N + 31) / 32, (unsigned)std::min<long long>(64, (batch + 7) / 8)), 256, 0, st, dY, grads + c.b_off[t], batch, N);
-        dim3 gx((unsigned)((batch + TB - 1) / TB), (K + TB - 1) / TB);
-        DQ_LAUNCH_PDL((gemm_dx_kernel<16>), gx, 256, 0, st, dY, params + c.w_off[t], h->dact_fc[i - 1], dense_patch(K), batch, N, K, 0);
-        count_launch(); count_launch(); count_launch(); count_launch();
+        const size_t smem = (size_t)(K * N + kHeadBwdSamples * N + kHeadBwdSamples * K) * sizeof(float);
+        if (N <= 128 && smem <= 48 * 1024) {               // the dueling layer of every shipped configuration: one fused launch
+            DQ_LAUNCH_PDL(head_dueling_bwd_kernel, (unsigned)((batch + kHeadBwdSamples - 1) / kHeadBwdSamples), 128, smem, st, dq, h->act_fc[i - 1], params + c.w_off[t],
+                          (long long)batch, K, N, c.A, h->dact_fc[i - 1], grads + c.w_off[t], grads + c.b_off[t]);
+            count_launch();
+        } else {
+            float* dY = h->dact_fc[i];
+            DQ_LAUNCH_PDL(dueling_bwd_kernel, (unsigned)((batch + 127) / 128), 128, 0, st, dq, dY, batch, c.A);
+            const long long chunk = dw_chunk(batch, K, N);
+            dim3 gw((K + TB - 1) / TB, (N + TB - 1) / TB, (unsigned)((batch + chunk - 1) / chunk));
+            DQ_LAUNCH_PDL(gemm_dw_kernel, gw, 256, 0, st, h->act_fc[i - 1], dense_patch(K), dY, grads + c.w_off[t], batch, N, K, chunk);
+            DQ_LAUNCH_PDL(colsum_kernel, dim3((N + 31) / 32, (unsigned)std::min<long long>(64, (batch + 7) / 8)), 256, 0, st, dY, grads + c.b_off[t], batch, N);
+            dim3 gx((unsigned)((batch + TB - 1) / TB), (K + TB - 1) / TB);
+            DQ_LAUNCH_PDL((gemm_dx_kernel<16>), gx, 256, 0, st, dY, params + c.w_off[t], h->dact_fc[i - 1], dense_patch(K), batch, N, K, 0);
+            count_launch(); count_launch(); count_launch(); count_launch();
+        }
         G32 = h->dact_fc[i - 1];
     }
     for (int j = n_tc - 1; j >= 0; --j) {
