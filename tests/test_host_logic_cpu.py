@@ -148,3 +148,25 @@ def test_exploration_schedule_and_config_objects():
         A.SequentialMemory(limit=10, window_length=4)
     spec = A.build_convolutional_nn([[64, 3, 2]], [[512, 0.2]], (7, 11, 11), 51)
     assert spec.input_shape == (7, 11, 11) and spec.num_actions == 51
+
+
+@pytest.mark.parametrize("L,thr,pat,min_steps", [(1000, 1e5, 1e9, 0), (7, 300, 5, 100), (1, 50, 2, 0), (50, 1e9, 30, 2000)])
+def test_episode_book_batched_form_equals_per_episode_form(L, thr, pat, min_steps):
+    """EpisodeBook.finish_many (one call per drain of the vectorised fit) against finish_episode one episode at a time, on random
+    lifetimes in ragged batches (empty ones included), short windows and active stop rules: same entries, same state, to the bit."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("dq_episodes", os.path.join(os.path.dirname(HERE), "deepq_decoding_b200", "episodes.py"))
+    ep = importlib.util.module_from_spec(spec); spec.loader.exec_module(ep)
+    rng = np.random.default_rng(L)
+    a, b, steps = ep.EpisodeBook(L, thr, pat, min_steps), ep.EpisodeBook(L, thr, pat, min_steps), 0
+    for chunk in range(30):
+        m = int(rng.integers(0, 300))
+        life = (rng.geometric(0.02, size=m) * 5).astype(np.int64)
+        nb = steps + np.cumsum(rng.integers(1, 50, size=m))
+        steps = int(nb[-1]) if m else steps
+        want = [a.finish_episode(int(x), int(y)) for x, y in zip(life, nb)]
+        got = b.finish_many(life, nb)
+        for k in got:
+            assert np.asarray(got[k]).tolist() == [w[k] for w in want], (chunk, k)
+        assert (a.stop, a.episode, a.best_avg, a.best_episode, a.win_n, a.win_sum) == (b.stop, b.episode, b.best_avg, b.best_episode, b.win_n, b.win_sum)
+        assert np.array_equal(a.win, b.win)
